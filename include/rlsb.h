@@ -1,0 +1,159 @@
+/* rlsb.h — C ABI of librlsb.so: the B200-native (sm_100a) kernels behind the DreamerV2
+ * imagination + lambda-return + actor-critic hot path of Midren/rl_sandbox.
+ *
+ * The reference has NO native/FFI layer (it is pure PyTorch), so there is no pre-existing
+ * binding to match; each entry point below names the reference Python code it replaces
+ * (paths relative to the reference checkout, rl_sandbox/...).  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - no allocation, no synchronisation and no exceptions inside: the caller passes
+ *     workspaces, everything is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, < 0 = argument error, > 0 = cudaError_t;
+ *   - re-entrant per stream; fp32 tensors are row-major with the reference's shapes.
+ */
+#ifndef RLSB_H
+#define RLSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLSB_ABI_VERSION 1
+
+/* ---- library / device ------------------------------------------------------------------- */
+int rlsb_abi_version(void);
+/* 0 when the current device is sm_100 (B200); negative otherwise (the library has no fallback) */
+int rlsb_check_device(void);
+const char* rlsb_error_string(int code);
+
+/* ---- K2: lambda-return + shifted-cumprod weights + advantage --------------------------------
+ * replaces ImaginativeCritic._lambda_return (agents/dreamer/ac.py:52-62), the discount
+ * shift+cumprod of DreamerV2.train (agents/dreamer_v2.py:192-197) and the advantage of
+ * ImaginativeActor.calculate_loss (agents/dreamer/ac.py:118).
+ *   r, v, d : (T, N) fp32 time-major (layout_batch_major = 0) or (N, T) (= 1), T = H + 1
+ *   vs      : (H, N)     V_t = r_t + d_t * ((1-lambda) v_{t+1} + lambda V_{t+1}),  V_H = v_H
+ *   w       : (T, N)     w_0 = 1, w_t = w_{t-1} * d_{t-1}                 (may be NULL)
+ *   adv     : (H-1, N)   adv_t = vs_{t+1} - v_t                           (may be NULL)
+ * time-major results are bit-identical to the reference's fp32 loop. */
+int rlsb_lambda_return_fwd(const float* r, const float* v, const float* d, int T, int64_t N,
+                           float lambda_, float* vs, float* w, float* adv,
+                           int layout_batch_major, void* stream);
+/* gradients of sum(g_vs * vs) w.r.t. r, v, d (time-major); any output may be NULL */
+int rlsb_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
+                           int T, int64_t N, float lambda_, float* g_r, float* g_v, float* g_d,
+                           void* stream);
+
+/* ---- categorical sampler (bit-exact test surface) -------------------------------------------
+ * replaces OneHotCategoricalStraightThrough(...).sample() as used by Dist / DistLayer('onehot')
+ * (agents/dreamer/common.py:27-28, utils/dists.py:177-179): idx = argmax_k(logits_k + g(u_k)),
+ * g(u) = -log(-log u) evaluated with the bit-reproducible log of rlsb_detmath.h; ties -> lowest k.
+ *   logits, uniforms : (rows, classes) fp32;  idx : (rows) int32 */
+int rlsb_sample_categorical(const float* logits, const float* uniforms, int64_t rows, int classes,
+                            int32_t* idx, void* stream);
+/* Philox4x32-10 uniforms exactly as the imagination kernels draw them (for RNG parity tests):
+ * out[i] = uniform(seed, n = n0 + i / per_row, t, stream_id, e = i % per_row) */
+int rlsb_philox_uniform(uint64_t seed, uint32_t n0, uint32_t t, uint32_t stream_id, int per_row,
+                        int64_t count, float* out, void* stream);
+
+/* ---- operand packing + tcgen05 GEMM (building blocks, exported for tests) -------------------
+ * Packed layout: see rl_sandbox_b200/csrc/rlsb_ptx.cuh::packed_index (SWIZZLE_128B tile image). */
+int rlsb_pack_rows(const float* src, int64_t ld_src, int rows_src, void* dst_bf16, int row_block,
+                   int rows_dst_pad, int k_pad, int dst_k0, int src_c0, int len, void* stream);
+/* out[M, N] (fp32, ld = ldo) = A[M, K] * W[N, K]^T + bias ; A packed (row block 128),
+ * W packed with row block `rb` (n_blocks * rb >= N).  Thin wrapper over the kernel every
+ * layer of the imagination path uses (replaces nn.Linear, utils/fc_nn.py:14-21). */
+int rlsb_gemm_bias(const void* a_packed, int k_pad, const void* w_packed, int rb, int n_blocks,
+                   const float* bias_padded, int M, int N, float* out, int64_t ldo, float* stats,
+                   void* stream);
+/* fused full-row variant: out = act(LayerNorm(A W^T + b)) written as packed bf16 [M_pad, out_kpad];
+ * gamma/beta NULL => no LayerNorm; act: 0 none, 1 ELU, 2 ReLU  (fc_nn.py:14-21, rssm.py:136-152) */
+int rlsb_gemm_ln_act(const void* a_packed, int k_pad, const void* w_packed, int rb,
+                     const float* bias_padded, int M, int N, const float* gamma, const float* beta,
+                     float eps, int act, void* out_packed, int out_kpad, void* stream);
+
+/* ---- K1: imagination rollout ----------------------------------------------------------------
+ * replaces DreamerV2.imagine_trajectory (agents/dreamer_v2.py:68-96) with everything it calls:
+ * ImaginativeActor.forward (agents/dreamer/ac.py:103-104), WorldModel.predict_next
+ * (agents/dreamer/world_model.py:131-140), RSSM.predict_next (agents/dreamer/rssm.py:176-193),
+ * GRUCell.forward (agents/dreamer/common.py:69-81), State.stoch sampling (rssm.py:34-37) and the
+ * target-critic read of ImaginativeCritic.lambda_return (agents/dreamer/ac.py:65). */
+typedef struct {
+  int32_t D;                /* rssm_dim (deterministic state width) */
+  int32_t groups;           /* latent_dim  = 32 categorical variables */
+  int32_t classes;          /* latent_classes = 32 */
+  int32_t A;                /* actions_num */
+  int32_t hidden;           /* head MLP width (400) */
+  int32_t discrete;         /* 1: one-hot categorical actor, 0: truncated-normal actor (2A outputs) */
+  int32_t layer_norm;       /* config `layer_norm` (first head LN and the GRU LN exist regardless) */
+  int32_t predict_discount; /* discount head present */
+  int32_t with_critic;      /* also evaluate the target critic on every state */
+  int32_t H;                /* horizon */
+} rlsb_imagine_cfg;
+
+/* fp32 parameters in nn.Linear layout (weight = [out, in] row-major); NULL = absent.
+ * mlp arrays are indexed by Linear layer 0..4 and LayerNorm 0..3 (fc_nn.py Sequential indices
+ * 0,3,6,9,12 and 1,4,7,10). */
+typedef struct {
+  const float* w[5];
+  const float* b[5];
+  const float* ln_g[4];
+  const float* ln_b[4];
+} rlsb_mlp_params;
+
+typedef struct {
+  const float* img_in_w;  const float* img_in_b;     /* pre_determ_recurrent.0  (D, S+A)      */
+  const float* img_in_ln_g; const float* img_in_ln_b;/* pre_determ_recurrent.1  (D) or NULL   */
+  const float* gru_w;     const float* gru_b;        /* determ_recurrent._layer (3D, 2D)      */
+  const float* gru_ln_g;  const float* gru_ln_b;     /* determ_recurrent._norm  (3D)          */
+  const float* prior1_w;  const float* prior1_b;     /* ensemble_prior_estimator.0 (D, D)     */
+  const float* prior1_ln_g; const float* prior1_ln_b;/* ensemble_prior_estimator.1 or NULL    */
+  const float* prior2_w;  const float* prior2_b;     /* ensemble_prior_estimator.3 (S, D)     */
+  rlsb_mlp_params actor;                             /* actor.actor.*                         */
+  rlsb_mlp_params reward;                            /* world_model.reward_predictor.*        */
+  rlsb_mlp_params discount;                          /* world_model.discount_predictor.*      */
+  rlsb_mlp_params critic;                            /* critic.target_critic.*                */
+} rlsb_imagine_params;
+
+typedef struct {
+  /* explicit noise (parity mode) or NULL (Philox mode keyed by seed) */
+  const float* latent_uniforms;  /* (H, N, groups*classes) */
+  const float* action_noise;     /* (H, N, A): uniforms if discrete else standard normals */
+  uint64_t seed;
+  uint32_t row_offset;           /* global index of start state 0 of this shard */
+  /* (H, N, A) actions to replay instead of sampling the actor (metrics caller of
+   * imagine_trajectory(state, precomp_actions, horizon), dreamer_v2.py:83-84), or NULL */
+  const float* precomp_actions;
+} rlsb_noise;
+
+typedef struct {
+  float* determ;        /* (H+1, N, D)              row 0 = start state (written by the call)   */
+  float* logits;        /* (H+1, N, groups*classes)  row 0 = start logits (copied)               */
+  uint8_t* stoch_idx;   /* (H+1, N, groups)          row 0 = argmax of the start one-hot         */
+  float* stoch;         /* (H+1, N, groups*classes) one-hot fp32, or NULL                        */
+  float* actions;       /* (H+1, N, A)               row 0 = 0                                   */
+  float* rewards;       /* (H+1, N)                                                              */
+  float* discounts;     /* (H+1, N)                  row 0 = 1                                   */
+  float* values;        /* (H+1, N) target critic, or NULL                                       */
+  float* actor_raw;     /* (H, N, A or 2A) raw actor head outputs per step, or NULL              */
+} rlsb_imagine_out;
+
+/* bytes needed for packed weights / activation workspace for N start states */
+size_t rlsb_imagine_packed_bytes(const rlsb_imagine_cfg* cfg);
+size_t rlsb_imagine_workspace_bytes(const rlsb_imagine_cfg* cfg, int64_t N);
+/* fp32 nn.Linear parameters -> packed bf16 tile images + padded fp32 vectors */
+int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* params, void* packed,
+                      void* stream);
+/* h0: (N, D) fp32; z0: (N, groups*classes) fp32 one-hot; logits0: (N, groups*classes) or NULL */
+int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0,
+                     const float* z0, const float* logits0, const rlsb_noise* noise,
+                     const rlsb_imagine_out* out, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLSB_H */

@@ -1,0 +1,312 @@
+"""oracle_port.py — TEST INFRASTRUCTURE ONLY.  Never imported by rl_sandbox_b200 (the product).
+
+CPU restatement (fp32, torch-CPU / numpy tensor arithmetic, explicit noise) of the DreamerV2
+imagination + lambda-return + actor-critic hot path of Midren/rl_sandbox.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it.
+
+Every function names the reference code it restates (paths relative to the reference's
+``rl_sandbox/`` package).  The restatement is pinned against the reference itself: the golden
+vectors under tests/golden/ were produced by importing the real reference modules in the build
+container (oracle/gen_golden.py) and tests/test_oracle.py checks this port against them.
+
+``bf16=True`` rounds the operands of every Linear to bfloat16 (fp32 accumulate) — the arithmetic
+the CUDA path performs on the tensor cores — so that algorithmic differences can be told apart
+from precision differences.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+_HERE = Path(__file__).resolve().parent
+_clib = None
+
+
+def clib():
+    """C oracle (oracle/rlsb_oracle.c): deterministic log / Gumbel / Philox / lambda-return."""
+    global _clib
+    if _clib is None:
+        so = _HERE / "liboracle.so"
+        if not so.exists():
+            import subprocess
+            subprocess.check_call(["make", "-C", os.fspath(_HERE)], stdout=subprocess.DEVNULL)
+        _clib = C.CDLL(os.fspath(so))
+        _clib.orc_logf.restype = C.c_float
+        _clib.orc_logf.argtypes = [C.c_float]
+    return _clib
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def gumbel(u) -> torch.Tensor:
+    """g(u) = -log(-log u) with the bit-reproducible log (see rlsb_oracle.c)."""
+    un = np.ascontiguousarray(torch.as_tensor(u).detach().cpu().numpy(), dtype=np.float32)
+    g = np.empty_like(un)
+    clib().orc_gumbel_array(_fp(un), _fp(g), C.c_int64(un.size))
+    return torch.from_numpy(g)
+
+
+def det_logf(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    clib().orc_logf_array(_fp(x), _fp(y), C.c_int64(x.size))
+    return y
+
+
+def philox_uniform(seed: int, n0: int, t: int, stream: int, per_row: int, rows: int) -> np.ndarray:
+    out = np.empty((rows, per_row), dtype=np.float32)
+    clib().orc_philox_uniform(C.c_uint64(seed), C.c_uint32(n0), C.c_uint32(t), C.c_uint32(stream),
+                              C.c_int(per_row), C.c_int64(out.size), _fp(out))
+    return out
+
+
+def sample_categorical(logits, uniforms) -> torch.Tensor:
+    """OneHotCategorical.sample as Gumbel-max: utils/dists.py:177-179, agents/dreamer/rssm.py:34-37.
+    idx = argmax_k(logits_k + g(u_k)); ties -> lowest index (torch.argmax)."""
+    lg = np.ascontiguousarray(torch.as_tensor(logits).detach().cpu().numpy(), dtype=np.float32)
+    un = np.ascontiguousarray(torch.as_tensor(uniforms).detach().cpu().numpy(), dtype=np.float32)
+    classes = lg.shape[-1]
+    rows = lg.size // classes
+    idx = np.empty(rows, dtype=np.int32)
+    clib().orc_sample_categorical(_fp(lg), _fp(un), C.c_int64(rows), C.c_int(classes), _fp(idx))
+    return torch.from_numpy(idx.reshape(lg.shape[:-1]).astype(np.int64))
+
+
+def lambda_return_c(r, v, d, lam: float):
+    """C oracle of ac.py:52-62 + dreamer_v2.py:192-197 + ac.py:118 on (T, N) arrays."""
+    r = np.ascontiguousarray(r, dtype=np.float32)
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    T, N = r.shape
+    vs = np.empty((T - 1, N), np.float32)
+    w = np.empty((T, N), np.float32)
+    adv = np.empty((max(T - 2, 0), N), np.float32)
+    clib().orc_lambda_return(_fp(r), _fp(v), _fp(d), C.c_int(T), C.c_int64(N), C.c_float(lam), _fp(vs), _fp(w),
+                             _fp(adv))
+    return vs, w, adv
+
+
+def lambda_return_loop(vs: torch.Tensor, rs: torch.Tensor, ds: torch.Tensor, lam: float) -> torch.Tensor:
+    """ImaginativeCritic._lambda_return, agents/dreamer/ac.py:52-62 (vs has one more row than rs)."""
+    out = [vs[-1]]
+    for i in range(rs.shape[0] - 1, -1, -1):
+        out.append(rs[i] + ds[i] * ((1 - lam) * vs[i + 1] + lam * out[-1]))
+    return torch.stack(out[::-1])[:-1]
+
+
+# ------------------------------------------------------------------------------------------------
+# layers
+# ------------------------------------------------------------------------------------------------
+def _r(x: torch.Tensor, bf16: bool) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32) if bf16 else x
+
+
+def linear(x, w, b, bf16=False):
+    """nn.Linear: x W^T + b."""
+    y = _r(x, bf16) @ _r(w, bf16).t()
+    return y + b if b is not None else y
+
+
+def layer_norm(x, g, b, eps=1e-5):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * g + b
+
+
+def elu(x):
+    return torch.where(x > 0, x, torch.expm1(x))
+
+
+def mlp(x, sd: dict, prefix: str, bf16=False):
+    """utils/fc_nn.py:4-23 with num_layers=5: Linear 0,3,6,9,12; LN 1 always, 4/7/10 iff present."""
+    for li in (0, 3, 6, 9):
+        x = linear(x, sd[f"{prefix}{li}.weight"], sd[f"{prefix}{li}.bias"], bf16)
+        if f"{prefix}{li + 1}.weight" in sd:
+            x = layer_norm(x, sd[f"{prefix}{li + 1}.weight"], sd[f"{prefix}{li + 1}.bias"])
+        x = elu(x)
+    return linear(x, sd[f"{prefix}12.weight"], sd[f"{prefix}12.bias"], bf16)
+
+
+def gru_cell(x, h, sd, prefix, bf16=False):
+    """GRUCell.forward, agents/dreamer/common.py:69-81 (LayerNorm over all 3D, update bias -1)."""
+    parts = linear(torch.cat([x, h], -1), sd[prefix + "_layer.weight"], sd[prefix + "_layer.bias"], bf16)
+    parts = layer_norm(parts, sd[prefix + "_norm.weight"], sd[prefix + "_norm.bias"])
+    reset, cand, update = parts.chunk(3, -1)
+    reset = torch.sigmoid(reset)
+    cand = torch.tanh(reset * cand)
+    update = torch.sigmoid(update - 1.0)
+    return update * cand + (1 - update) * h
+
+
+def rssm_predict_next(h, z, a, sd, rp="recurrent_model.", bf16=False):
+    """RSSM.predict_next, agents/dreamer/rssm.py:176-193 (discrete_rssm = false)."""
+    x = linear(torch.cat([z, a], -1), sd[rp + "pre_determ_recurrent.0.weight"], sd[rp + "pre_determ_recurrent.0.bias"], bf16)
+    if rp + "pre_determ_recurrent.1.weight" in sd:
+        x = layer_norm(x, sd[rp + "pre_determ_recurrent.1.weight"], sd[rp + "pre_determ_recurrent.1.bias"])
+    x = elu(x)
+    h2 = gru_cell(x, h, sd, rp + "determ_recurrent.", bf16)
+    y = linear(h2, sd[rp + "ensemble_prior_estimator.0.weight"], sd[rp + "ensemble_prior_estimator.0.bias"], bf16)
+    if rp + "ensemble_prior_estimator.1.weight" in sd:
+        y = layer_norm(y, sd[rp + "ensemble_prior_estimator.1.weight"], sd[rp + "ensemble_prior_estimator.1.bias"])
+    y = elu(y)
+    logits = linear(y, sd[rp + "ensemble_prior_estimator.3.weight"], sd[rp + "ensemble_prior_estimator.3.bias"], bf16)
+    return h2, logits
+
+
+def bernoulli_mode(logit):
+    """torch Bernoulli(logits).mode as used at world_model.py:137: (p >= .5), NaN where p == .5."""
+    p = torch.sigmoid(logit)
+    m = (p >= 0.5).to(p.dtype)
+    m[p == 0.5] = float("nan")
+    return m
+
+
+def imagine(wm_sd, actor_sd, critic_sd, h0, z0, *, H, A, discrete, predict_discount, latent_uniforms,
+            action_noise, logits0=None, precomp_actions=None, bf16=False, teacher=None, groups=32, classes=32,
+            target_prefix="target_critic."):
+    """DreamerV2.imagine_trajectory (agents/dreamer_v2.py:68-96) + WorldModel.predict_next
+    (agents/dreamer/world_model.py:131-140) + the target-critic read of lambda_return (ac.py:65).
+
+    h0 (N,D), z0 (N,1024) one-hot.  latent_uniforms (H,N,1024), action_noise (H,N,A) (uniforms for a
+    discrete actor, standard normals otherwise).  ``teacher``: optional dict with 'determ' / 'stoch'
+    (H+1,N,.) — when given, step t starts from the teacher's state t (teacher forcing) so one-step
+    quantities can be compared without error accumulation."""
+    N = h0.shape[0]
+    S = groups * classes
+    h, z = h0.clone(), z0.clone()
+    out = {k: [] for k in ("determ", "logits", "stoch", "stoch_idx", "actions", "rewards", "discounts", "values",
+                           "actor_raw")}
+    out["determ"].append(h)
+    out["logits"].append(logits0 if logits0 is not None else torch.zeros(N, S))
+    out["stoch"].append(z)
+    out["stoch_idx"].append(z.view(N, groups, classes).argmax(-1))
+    out["actions"].append(torch.zeros(N, A))
+    for t in range(H + 1):
+        if teacher is not None:
+            h, z = teacher["determ"][t], teacher["stoch"][t]
+        s = torch.cat([h, z], -1)
+        out["rewards"].append(mlp(s, wm_sd, "reward_predictor.", bf16).squeeze(-1))
+        if t == 0 or not predict_discount:
+            out["discounts"].append(torch.ones(N))
+        else:
+            out["discounts"].append(bernoulli_mode(mlp(s, wm_sd, "discount_predictor.", bf16).squeeze(-1)))
+        if critic_sd is not None:
+            out["values"].append(mlp(s, critic_sd, target_prefix, bf16).squeeze(-1))
+        if t == H:
+            break
+        raw = mlp(s, actor_sd, "actor.", bf16)
+        out["actor_raw"].append(raw)
+        if precomp_actions is not None:
+            a = precomp_actions[t]
+        elif discrete:
+            idx = sample_categorical(raw, action_noise[t])
+            a = torch.nn.functional.one_hot(idx, A).float()
+        else:
+            mu, sd_ = raw.chunk(2, -1)
+            a = torch.tanh(mu) + (2 * torch.sigmoid(sd_ / 2) + 0.1) * action_noise[t]  # unclamped rsample
+        h, logits = rssm_predict_next(h, z, a, wm_sd, bf16=bf16)
+        idx = sample_categorical(logits.view(N, groups, classes), latent_uniforms[t].view(N, groups, classes))
+        z = torch.nn.functional.one_hot(idx, classes).float().view(N, S)
+        out["determ"].append(h); out["logits"].append(logits); out["stoch"].append(z)
+        out["stoch_idx"].append(idx); out["actions"].append(a)
+    return {k: torch.stack(v) for k, v in out.items() if len(v)}
+
+
+# ------------------------------------------------------------------------------------------------
+# losses (agents/dreamer/ac.py:68-81, 113-146; agents/dreamer_v2.py:184-207)
+# ------------------------------------------------------------------------------------------------
+LOG_SQRT_2PI = 0.5 * math.log(2 * math.pi)
+
+
+def normal_logprob(x, mean, std=None):
+    if std is None:
+        return -0.5 * (x - mean) ** 2 - LOG_SQRT_2PI
+    return -((x - mean) ** 2) / (2 * std ** 2) - torch.log(std) - LOG_SQRT_2PI
+
+
+def ac_losses(traj, actor_sd, critic_sd, *, lam, discrete, rho, eta, bf16=False):
+    """Returns dict with vs, w, loss_critic, loss_actor (+ parts) for a trajectory dict from imagine()."""
+    zs = torch.cat([traj["determ"], traj["stoch"]], -1)          # (H+1, N, Z)
+    r, v, d = traj["rewards"], traj["values"], traj["discounts"]  # (H+1, N)
+    vs = lambda_return_loop(v, r[:-1], d, lam)                    # (H, N)
+    w = torch.cumprod(torch.cat([torch.ones_like(d[:1]), d[:-1]], 0), 0)
+    pred = mlp(zs[:-1], critic_sd, "critic.", bf16).squeeze(-1)
+    loss_critic = -(normal_logprob(vs, pred) * w[:-1]).mean()
+    raw = mlp(zs[:-2], actor_sd, "actor.", bf16)
+    adv = vs[1:] - v[:-2]
+    acts = traj["actions"][1:-1]
+    if discrete:
+        logp_all = torch.log_softmax(raw, -1)
+        logp = (logp_all * acts).sum(-1)
+        ent = -(logp_all.exp() * logp_all).sum(-1)
+    else:
+        mu, s_ = raw.chunk(2, -1)
+        loc, scale = torch.tanh(mu), 2 * torch.sigmoid(s_ / 2) + 0.1
+        logp = normal_logprob(acts, loc, scale).sum(-1)
+        ent = (0.5 + LOG_SQRT_2PI + torch.log(scale)).sum(-1)
+    l_reinforce = -(rho * logp * w[:-2] * adv).mean()
+    l_dyn = -((1 - rho) * vs[1:] * w[:-2]).mean() if rho != 1.0 else torch.tensor(0.0)
+    l_ent = -(eta * ent * w[:-2]).mean()
+    return dict(vs=vs, w=w, adv=adv, loss_critic=loss_critic, loss_actor=l_reinforce + l_dyn + l_ent,
+                loss_actor_reinforce=l_reinforce, loss_actor_dynamics_backprop=l_dyn, loss_actor_entropy=l_ent)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic parameters with the reference's state-dict names and default nn.Linear init
+# ------------------------------------------------------------------------------------------------
+def _lin(gen, out_f, in_f):
+    bound = 1.0 / math.sqrt(in_f)
+    w = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * bound
+    b = (torch.rand(out_f, generator=gen) * 2 - 1) * bound
+    return w, b
+
+
+def make_mlp_sd(gen, prefix, n_in, n_out, hidden, layer_norm, randomize_ln=True):
+    sd = {}
+    dims = [n_in, hidden, hidden, hidden, hidden, n_out]
+    for i, li in enumerate((0, 3, 6, 9, 12)):
+        sd[f"{prefix}{li}.weight"], sd[f"{prefix}{li}.bias"] = _lin(gen, dims[i + 1], dims[i])
+        if li != 12 and (li == 0 or layer_norm):
+            g = 1 + 0.1 * torch.randn(hidden, generator=gen) if randomize_ln else torch.ones(hidden)
+            b = 0.1 * torch.randn(hidden, generator=gen) if randomize_ln else torch.zeros(hidden)
+            sd[f"{prefix}{li + 1}.weight"], sd[f"{prefix}{li + 1}.bias"] = g, b
+    return sd
+
+
+def make_params(seed, *, D, A, discrete, layer_norm, predict_discount, hidden=400, S=1024):
+    """Random parameters under the reference's names."""
+    gen = torch.Generator().manual_seed(seed)
+    wm, rp = {}, "recurrent_model."
+    wm[rp + "pre_determ_recurrent.0.weight"], wm[rp + "pre_determ_recurrent.0.bias"] = _lin(gen, D, S + A)
+    wm[rp + "determ_recurrent._layer.weight"], wm[rp + "determ_recurrent._layer.bias"] = _lin(gen, 3 * D, 2 * D)
+    wm[rp + "determ_recurrent._norm.weight"] = 1 + 0.1 * torch.randn(3 * D, generator=gen)
+    wm[rp + "determ_recurrent._norm.bias"] = 0.1 * torch.randn(3 * D, generator=gen)
+    wm[rp + "ensemble_prior_estimator.0.weight"], wm[rp + "ensemble_prior_estimator.0.bias"] = _lin(gen, D, D)
+    wm[rp + "ensemble_prior_estimator.3.weight"], wm[rp + "ensemble_prior_estimator.3.bias"] = _lin(gen, S, D)
+    if layer_norm:
+        for name in ("pre_determ_recurrent.1", "ensemble_prior_estimator.1"):
+            wm[rp + name + ".weight"] = 1 + 0.1 * torch.randn(D, generator=gen)
+            wm[rp + name + ".bias"] = 0.1 * torch.randn(D, generator=gen)
+    wm.update(make_mlp_sd(gen, "reward_predictor.", D + S, 1, hidden, layer_norm))
+    if predict_discount:
+        wm.update(make_mlp_sd(gen, "discount_predictor.", D + S, 1, hidden, layer_norm))
+    actor = make_mlp_sd(gen, "actor.", D + S, A if discrete else 2 * A, hidden, layer_norm)
+    critic = make_mlp_sd(gen, "critic.", D + S, 1, hidden, layer_norm)
+    critic.update(make_mlp_sd(gen, "target_critic.", D + S, 1, hidden, layer_norm))
+    return wm, actor, critic
+
+
+def make_start(seed, N, D, groups=32, classes=32):
+    """determ ~ 0.5 N(0,1); stoch = one-hot of randint(classes) per group."""
+    gen = torch.Generator().manual_seed(seed)
+    h0 = 0.5 * torch.randn(N, D, generator=gen)
+    idx = torch.randint(0, classes, (N, groups), generator=gen)
+    z0 = torch.nn.functional.one_hot(idx, classes).float().view(N, groups * classes)
+    return h0, z0

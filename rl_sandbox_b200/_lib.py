@@ -1,0 +1,116 @@
+"""ctypes binding of librlsb.so (the C ABI declared in include/rlsb.h).
+
+There is deliberately NO fallback: if the shared library is missing, or a kernel entry point is
+called without a B200 (sm_100) device, an exception is raised.  PyTorch is used only for device
+memory and streams; every pointer crossing this boundary is a raw device address.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "librlsb.so"
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class RlsbError(RuntimeError):
+    pass
+
+
+class ImagineCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "predict_discount",
+        "with_critic", "H")]
+
+
+class MlpParams(C.Structure):
+    _fields_ = [("w", C.c_void_p * 5), ("b", C.c_void_p * 5), ("ln_g", C.c_void_p * 4),
+                ("ln_b", C.c_void_p * 4)]
+
+
+class ImagineParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "img_in_w", "img_in_b", "img_in_ln_g", "img_in_ln_b", "gru_w", "gru_b", "gru_ln_g", "gru_ln_b",
+        "prior1_w", "prior1_b", "prior1_ln_g", "prior1_ln_b", "prior2_w", "prior2_b")] + [
+        ("actor", MlpParams), ("reward", MlpParams), ("discount", MlpParams), ("critic", MlpParams)]
+
+
+class Noise(C.Structure):
+    _fields_ = [("latent_uniforms", C.c_void_p), ("action_noise", C.c_void_p), ("seed", C.c_uint64),
+                ("row_offset", C.c_uint32), ("precomp_actions", C.c_void_p)]
+
+
+class ImagineOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "determ", "logits", "stoch_idx", "stoch", "actions", "rewards", "discounts", "values",
+        "actor_raw")]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load librlsb.so; raise loudly when it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RlsbError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(or `make -C {_HERE / 'csrc'}`).  rl_sandbox_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    vp, i32, i64, f32, u32, u64, sz = (C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint32,
+                                       C.c_uint64, C.c_size_t)
+    sig = {
+        "rlsb_abi_version": (C.c_int, []),
+        "rlsb_check_device": (C.c_int, []),
+        "rlsb_error_string": (C.c_char_p, [i32]),
+        "rlsb_lambda_return_fwd": (C.c_int, [vp, vp, vp, i32, i64, f32, vp, vp, vp, i32, vp]),
+        "rlsb_lambda_return_bwd": (C.c_int, [vp, vp, vp, vp, i32, i64, f32, vp, vp, vp, vp]),
+        "rlsb_sample_categorical": (C.c_int, [vp, vp, i64, i32, vp, vp]),
+        "rlsb_philox_uniform": (C.c_int, [u64, u32, u32, u32, i32, i64, vp, vp]),
+        "rlsb_pack_rows": (C.c_int, [vp, i64, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "rlsb_gemm_bias": (C.c_int, [vp, i32, vp, i32, i32, vp, i32, i32, vp, i64, vp, vp]),
+        "rlsb_gemm_ln_act": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, f32, i32, vp, i32, vp]),
+        "rlsb_imagine_packed_bytes": (sz, [C.POINTER(ImagineCfg)]),
+        "rlsb_imagine_workspace_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
+        "rlsb_imagine_pack": (C.c_int, [C.POINTER(ImagineCfg), C.POINTER(ImagineParams), vp, vp]),
+        "rlsb_imagine_fwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, vp, vp, vp, C.POINTER(Noise),
+                                       C.POINTER(ImagineOut), vp, vp]),
+    }
+    optional = {
+        "rlsb_slot_attention_workspace_bytes", "rlsb_slot_attention_packed_bytes",
+        "rlsb_slot_attention_pack", "rlsb_slot_attention_fwd",
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._rlsb_optional = optional
+    if lib.rlsb_abi_version() != 1:
+        raise RlsbError("librlsb.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def exported_symbols() -> list[str]:
+    """Names declared in include/rlsb.h (used by the CPU test that checks the export table)."""
+    import re
+    hdr = (_HERE.parent / "include" / "rlsb.h").read_text()
+    return sorted(set(re.findall(r"\b(rlsb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = load().rlsb_error_string(code).decode()
+        raise RlsbError(f"librlsb {what} failed with code {code}: {msg}")
+
+
+def require_device() -> None:
+    import torch
+    if not torch.cuda.is_available():
+        raise RlsbError("rl_sandbox_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")
+    check(load().rlsb_check_device(), "rlsb_check_device")

@@ -1,0 +1,114 @@
+// rlsb_capi.cu — extern "C" surface declared in include/rlsb.h (everything except the K1
+// entry points, which live next to their planner in rlsb_imagine.cu, and K3 in rlsb_slot.cu).
+#include "../../include/rlsb.h"
+
+#include "rlsb_detmath.h"
+#include "rlsb_gemm.cuh"
+#include "rlsb_kernels.cuh"
+
+using namespace rlsb;
+
+namespace {
+__global__ void philox_uniform_kernel(uint64_t seed, uint32_t n0, uint32_t t, uint32_t stream_id,
+                                      int per_row, long long count, float* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t n = n0 + static_cast<uint32_t>(i / per_row);
+  const uint32_t e = static_cast<uint32_t>(i % per_row);
+  out[i] = rlsb_noise_uniform(seed, n, t, stream_id, e);
+}
+}  // namespace
+
+extern "C" int rlsb_abi_version(void) { return RLSB_ABI_VERSION; }
+
+extern "C" int rlsb_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return -100;
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10 || minor != 0) return -101;  // built for sm_100a only; no fallback path exists
+  return 0;
+}
+
+extern "C" const char* rlsb_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  switch (code) {
+    case -100: return "no CUDA device";
+    case -101: return "device is not sm_100 (B200); librlsb has no fallback";
+    default: return "invalid argument";
+  }
+}
+
+extern "C" int rlsb_lambda_return_fwd(const float* r, const float* v, const float* d, int T, int64_t N,
+                                      float lambda_, float* vs, float* w, float* adv,
+                                      int layout_batch_major, void* stream) {
+  if (!r || !v || !d || !vs) return -1;
+  return launch_lambda_return(r, v, d, T, N, lambda_, vs, w, adv, layout_batch_major,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rlsb_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
+                                      int T, int64_t N, float lambda_, float* g_r, float* g_v, float* g_d,
+                                      void* stream) {
+  if (!g_vs || !v || !d || !vs) return -1;
+  return launch_lambda_return_bwd(g_vs, v, d, vs, T, N, lambda_, g_r, g_v, g_d,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rlsb_sample_categorical(const float* logits, const float* uniforms, int64_t rows, int classes,
+                                       int32_t* idx, void* stream) {
+  if (!logits || !uniforms || !idx || classes <= 0) return -1;
+  return launch_sample_categorical(logits, uniforms, rows, classes, idx, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rlsb_philox_uniform(uint64_t seed, uint32_t n0, uint32_t t, uint32_t stream_id, int per_row,
+                                   int64_t count, float* out, void* stream) {
+  if (!out || per_row <= 0 || count <= 0) return -1;
+  philox_uniform_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      seed, n0, t, stream_id, per_row, count, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int rlsb_pack_rows(const float* src, int64_t ld_src, int rows_src, void* dst_bf16, int row_block,
+                              int rows_dst_pad, int k_pad, int dst_k0, int src_c0, int len, void* stream) {
+  if (!src || !dst_bf16) return -1;
+  PackSeg seg{dst_k0, src_c0, len};
+  return launch_pack(src, ld_src, rows_src, static_cast<__nv_bfloat16*>(dst_bf16), row_block, rows_dst_pad,
+                     k_pad, 1, &seg, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rlsb_gemm_bias(const void* a_packed, int k_pad, const void* w_packed, int rb, int n_blocks,
+                              const float* bias_padded, int M, int N, float* out, int64_t ldo, float* stats,
+                              void* stream) {
+  if (!a_packed || !w_packed || !out || (k_pad % 64) != 0) return -1;
+  GemmParams g{};
+  g.A[0] = static_cast<const __nv_bfloat16*>(a_packed);
+  g.a_ktiles[0] = k_pad / 64;
+  g.n_seg = 1;
+  g.W = static_cast<const __nv_bfloat16*>(w_packed);
+  g.RB = rb; g.NB = n_blocks; g.G = 1;
+  g.M = M; g.m_tiles = (M + 127) / 128; g.N = N;
+  g.bias = bias_padded;
+  g.out_f32 = out; g.ldo = ldo; g.stats = stats;
+  return launch_gemm(g, stats ? EPI_STATS : EPI_PLAIN, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int rlsb_gemm_ln_act(const void* a_packed, int k_pad, const void* w_packed, int rb,
+                                const float* bias_padded, int M, int N, const float* gamma, const float* beta,
+                                float eps, int act, void* out_packed, int out_kpad, void* stream) {
+  if (!a_packed || !w_packed || !out_packed || (k_pad % 64) != 0) return -1;
+  GemmParams g{};
+  g.A[0] = static_cast<const __nv_bfloat16*>(a_packed);
+  g.a_ktiles[0] = k_pad / 64;
+  g.n_seg = 1;
+  g.W = static_cast<const __nv_bfloat16*>(w_packed);
+  g.RB = rb; g.NB = 1; g.G = 1;
+  g.M = M; g.m_tiles = (M + 127) / 128; g.N = N;
+  g.bias = bias_padded;
+  g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.act = act;
+  g.out_bf16 = static_cast<__nv_bfloat16*>(out_packed); g.out_kpad = out_kpad;
+  return launch_gemm(g, EPI_LN_ACT, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,57 @@
+// rlsb_gemm.cuh — parameters of the tcgen05 row-block GEMM used by every contraction on the
+// imagination path (reference call sites: rssm.py:179-192, common.py:69-81, fc_nn.py:4-23).
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace rlsb {
+
+constexpr int kTileM = 128;      // rows per M tile == TMEM lanes
+constexpr int kTileK = 64;       // bf16 elements per 128-byte swizzled row
+constexpr int kMaxSeg = 3;       // K segments (concatenated inputs, e.g. cat[x, h])
+constexpr int kGemmThreads = 192;  // warp0 = bulk-copy producer, warp1 = MMA issuer, warps2-5 = epilogue
+
+enum GemmEpilogue : int {
+  EPI_PLAIN = 0,   // out_f32[m][col] = acc + bias                         (row-major fp32)
+  EPI_STATS = 1,   // EPI_PLAIN + per-(row, n-block) (mean, M2) partials    (for a later LayerNorm)
+  EPI_LN_ACT = 2,  // full row in TMEM: [LayerNorm] -> activation -> packed bf16 (+ optional fp32)
+};
+
+enum Activation : int { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2 };
+
+struct GemmParams {
+  // ---- A: packed bf16 [M_pad x K_s] (row block 128), one pointer per K segment -------------
+  const __nv_bfloat16* A[kMaxSeg];
+  int a_ktiles[kMaxSeg];            // K_s / 64
+  long long a_group_stride[kMaxSeg];  // elements between groups (0 = shared by all groups)
+  int n_seg;
+  // ---- B: packed bf16 weights [(G*NB*RB) x K_total] with row block RB ------------------------
+  const __nv_bfloat16* W;
+  int RB;  // rows (output columns) per n-block: multiple of 32, <= 512
+  int NB;  // n-blocks per group
+  int G;   // groups (independent heads sharing the launch)
+  // ---- problem ------------------------------------------------------------------------------
+  int M;        // valid rows
+  int m_tiles;  // ceil(M / 128)
+  int N;        // valid output columns per group (<= NB*RB)
+  const float* bias;  // [G][NB*RB] (zero padded) or nullptr
+  // ---- EPI_PLAIN / EPI_STATS ----------------------------------------------------------------
+  float* out_f32;              // [G][M_pad][ldo]
+  long long ldo;
+  long long out_group_stride;  // elements
+  float* stats;                // [G][NB][M_pad][2] = (mean, M2) over the block's valid columns
+  // ---- EPI_LN_ACT ---------------------------------------------------------------------------
+  const float* ln_gamma;  // [G][RB] or nullptr (=> no LayerNorm)
+  const float* ln_beta;
+  float ln_eps;
+  int act;
+  __nv_bfloat16* out_bf16;  // packed [G][M_pad x out_kpad]
+  int out_kpad;             // multiple of 64, >= N
+  long long out_bf16_group_stride;
+};
+
+// Launch on `stream`; returns cudaError_t as int (0 = ok) or a negative argument error.
+int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream);
+
+}  // namespace rlsb

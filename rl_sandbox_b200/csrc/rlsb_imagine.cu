@@ -1,0 +1,433 @@
+// rlsb_imagine.cu — K1: the imagination rollout (DreamerV2.imagine_trajectory,
+// agents/dreamer_v2.py:68-96) as a stream-ordered chain of tcgen05 GEMMs with fused epilogues
+// plus small HBM-bound kernels; one C-ABI call enqueues all H steps (CUDA-graph capturable).
+//
+// Data layout in HBM
+//   * recurrent state h: fp32 row-major inside the caller's `determ` output (H+1, N, D) — the
+//     GRU update h' = u*c + (1-u)*h is carried in fp32 — plus a packed bf16 image (ping-pong)
+//     that feeds the tensor cores;
+//   * stochastic state z: uint8 class indices (H+1, N, 32) + packed bf16 one-hot image;
+//   * every bf16 operand (activations and weights) is stored as SWIZZLE_128B tile images so a
+//     pipeline stage is one contiguous bulk copy (rlsb_ptx.cuh::packed_index).
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rlsb.h"
+#include "rlsb_gemm.cuh"
+#include "rlsb_kernels.cuh"
+
+namespace rlsb {
+
+namespace {
+
+inline int ru(int x, int m) { return (x + m - 1) / m * m; }
+inline size_t rus(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+struct LayerPlan {
+  int N = 0;       // valid outputs per group
+  int RB = 0, NB = 0, G = 1;
+  int kp = 0;      // padded K (sum of segments)
+  size_t w_off = 0;     // bytes into packed blob (bf16 tiles)
+  size_t bias_off = 0;  // fp32 [G][NB*RB]
+  size_t g_off = 0, b_off = 0;  // fp32 LN params: [G][RB] (full-row) or [N] (stats path)
+  bool fullrow = false;
+};
+
+void plan_nb(LayerPlan& L) {
+  if (ru(L.N, 32) <= 512) {
+    L.NB = 1;
+    L.RB = ru(L.N, 32);
+    L.fullrow = true;
+  } else {
+    L.NB = (L.N + 255) / 256;
+    L.RB = ru((L.N + L.NB - 1) / L.NB, 32);
+    L.fullrow = false;
+  }
+}
+
+struct Plan {
+  int D, S, A, Hd, Dp, Sp, Ap, Hp, Aout, G;
+  int g_actor, g_reward, g_discount, g_critic;
+  LayerPlan img_in, gru, prior1, prior2, head[5];
+  size_t packed_bytes;
+};
+
+size_t place(size_t& cursor, size_t bytes) {
+  cursor = rus(cursor, 1024);
+  size_t off = cursor;
+  cursor += bytes;
+  return off;
+}
+
+int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
+  if (c.classes != 32 || c.groups <= 0 || c.groups > 64) return -10;
+  if (c.D <= 0 || c.A <= 0 || c.hidden <= 0 || c.H <= 0) return -11;
+  P.D = c.D; P.S = c.groups * c.classes; P.A = c.A; P.Hd = c.hidden;
+  P.Dp = ru(P.D, 64); P.Sp = ru(P.S, 64); P.Ap = ru(P.A, 64); P.Hp = ru(P.Hd, 64);
+  P.Aout = c.discrete ? c.A : 2 * c.A;
+  if (P.Aout > 32 || P.Ap > 64) return -12;
+  if (ru(P.Hd, 32) > 512) return -13;
+  int g = 0;
+  P.g_actor = g++;
+  P.g_reward = g++;
+  P.g_discount = c.predict_discount ? g++ : -1;
+  P.g_critic = c.with_critic ? g++ : -1;
+  P.G = g;
+
+  size_t cur = 0;
+  auto finish = [&](LayerPlan& L, int ln_len_per_group) {
+    plan_nb(L);
+    L.w_off = place(cur, static_cast<size_t>(L.G) * L.NB * L.RB * L.kp * 2);
+    L.bias_off = place(cur, static_cast<size_t>(L.G) * L.NB * L.RB * 4);
+    L.g_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
+    L.b_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
+  };
+  P.img_in.N = P.D; P.img_in.kp = P.Sp + P.Ap; finish(P.img_in, ru(P.D, 32));
+  P.gru.N = 3 * P.D; P.gru.kp = 2 * P.Dp;      finish(P.gru, 3 * P.D);
+  P.prior1.N = P.D; P.prior1.kp = P.Dp;        finish(P.prior1, ru(P.D, 32));
+  P.prior2.N = P.S; P.prior2.kp = P.Dp;        finish(P.prior2, 32);
+  for (int l = 0; l < 5; ++l) {
+    LayerPlan& L = P.head[l];
+    L.G = P.G;
+    L.N = (l == 4) ? P.Aout : P.Hd;
+    L.kp = (l == 0) ? (P.Dp + P.Sp) : P.Hp;
+    finish(L, ru(L.N, 32));
+  }
+  P.packed_bytes = rus(cur, 1024);
+  return 0;
+}
+
+struct Workspace {
+  size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
+  long long ld_scratch;
+  int m_pad;
+  size_t bytes;
+};
+
+void make_workspace(const Plan& P, long long N, Workspace& W) {
+  const int m_pad = ru(static_cast<int>(N), 128);
+  W.m_pad = m_pad;
+  size_t cur = 0;
+  for (int i = 0; i < 2; ++i) W.hbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
+  for (int i = 0; i < 2; ++i) W.zbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Sp * 2);
+  W.abf = place(cur, static_cast<size_t>(m_pad) * P.Ap * 2);
+  W.xbf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
+  W.ybf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
+  for (int i = 0; i < 2; ++i) W.hid[i] = place(cur, static_cast<size_t>(P.G) * m_pad * P.Hp * 2);
+  W.ld_scratch = ru(3 * P.D, 4);
+  W.scratch = place(cur, static_cast<size_t>(m_pad) * W.ld_scratch * 4);
+  int nbmax = P.gru.NB;
+  if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
+  W.stats = place(cur, static_cast<size_t>(nbmax) * m_pad * 2 * 4);
+  W.head_out = place(cur, static_cast<size_t>(P.G) * m_pad * 32 * 4);
+  W.bytes = rus(cur, 1024);
+}
+
+__global__ void copy_pad_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad,
+                                float fill) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = (src && i < n) ? src[i] : fill;
+}
+
+int copy_pad(const float* src, int n, float* dst, int n_pad, float fill, cudaStream_t s) {
+  copy_pad_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(src, n, dst, n_pad, fill);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// one-hot fp32 rows -> uint8 class index per group (start state only)
+__global__ void onehot_to_idx_kernel(const float* __restrict__ z, long long N, int groups, int classes,
+                                     uint8_t* __restrict__ idx) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= N * groups) return;
+  const float* p = z + i * classes;
+  int best = 0;
+  float bv = p[0];
+  for (int k = 1; k < classes; ++k)
+    if (p[k] > bv) { bv = p[k]; best = k; }
+  idx[i] = static_cast<uint8_t>(best);
+}
+
+#define RLSB_TRY(expr)            \
+  do {                            \
+    int _e = (expr);              \
+    if (_e != 0) return _e;       \
+  } while (0)
+
+const rlsb_mlp_params* head_params(const rlsb_imagine_params& p, const Plan& P, int g) {
+  if (g == P.g_actor) return &p.actor;
+  if (g == P.g_reward) return &p.reward;
+  if (g == P.g_discount) return &p.discount;
+  return &p.critic;
+}
+
+}  // namespace
+
+}  // namespace rlsb
+
+using namespace rlsb;
+
+extern "C" size_t rlsb_imagine_packed_bytes(const rlsb_imagine_cfg* cfg) {
+  Plan P;
+  if (!cfg || make_plan(*cfg, P) != 0) return 0;
+  return P.packed_bytes;
+}
+
+extern "C" size_t rlsb_imagine_workspace_bytes(const rlsb_imagine_cfg* cfg, int64_t N) {
+  Plan P;
+  if (!cfg || N <= 0 || make_plan(*cfg, P) != 0) return 0;
+  Workspace W;
+  make_workspace(P, N, W);
+  return W.bytes;
+}
+
+extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* prm, void* packed,
+                                 void* stream_) {
+  if (!cfg || !prm || !packed) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  Plan P;
+  RLSB_TRY(make_plan(*cfg, P));
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  auto wptr = [&](const LayerPlan& L) { return reinterpret_cast<__nv_bfloat16*>(base + L.w_off); };
+  auto fptr = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+
+  // ---- RSSM layers (rssm.py:136-152, common.py:58-63) ----
+  {
+    const LayerPlan& L = P.img_in;  // input = cat[stoch, action]
+    PackSeg segs[2] = {{0, 0, P.S}, {P.Sp, P.S, P.A}};
+    RLSB_TRY(launch_pack(prm->img_in_w, P.S + P.A, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 2, segs, s));
+    RLSB_TRY(copy_pad(prm->img_in_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
+    if (prm->img_in_ln_g) {
+      RLSB_TRY(copy_pad(prm->img_in_ln_g, L.N, fptr(L.g_off), ru(L.N, 32), 1.f, s));
+      RLSB_TRY(copy_pad(prm->img_in_ln_b, L.N, fptr(L.b_off), ru(L.N, 32), 0.f, s));
+    }
+  }
+  {
+    const LayerPlan& L = P.gru;  // input = cat[x, h]
+    PackSeg segs[2] = {{0, 0, P.D}, {P.Dp, P.D, P.D}};
+    RLSB_TRY(launch_pack(prm->gru_w, 2 * P.D, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 2, segs, s));
+    RLSB_TRY(copy_pad(prm->gru_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
+    RLSB_TRY(copy_pad(prm->gru_ln_g, L.N, fptr(L.g_off), L.N, 1.f, s));
+    RLSB_TRY(copy_pad(prm->gru_ln_b, L.N, fptr(L.b_off), L.N, 0.f, s));
+  }
+  {
+    const LayerPlan& L = P.prior1;
+    PackSeg segs[1] = {{0, 0, P.D}};
+    RLSB_TRY(launch_pack(prm->prior1_w, P.D, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 1, segs, s));
+    RLSB_TRY(copy_pad(prm->prior1_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
+    if (prm->prior1_ln_g) {
+      RLSB_TRY(copy_pad(prm->prior1_ln_g, L.N, fptr(L.g_off), ru(L.N, 32), 1.f, s));
+      RLSB_TRY(copy_pad(prm->prior1_ln_b, L.N, fptr(L.b_off), ru(L.N, 32), 0.f, s));
+    }
+  }
+  {
+    const LayerPlan& L = P.prior2;
+    PackSeg segs[1] = {{0, 0, P.D}};
+    RLSB_TRY(launch_pack(prm->prior2_w, P.D, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 1, segs, s));
+    RLSB_TRY(copy_pad(prm->prior2_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
+  }
+  // ---- heads (fc_nn.py:4-23): groups share one launch per layer ----
+  for (int l = 0; l < 5; ++l) {
+    const LayerPlan& L = P.head[l];
+    for (int g = 0; g < P.G; ++g) {
+      const rlsb_mlp_params* hp = head_params(*prm, P, g);
+      if (!hp->w[l]) return -20;
+      const int n_out = (l == 4) ? ((g == P.g_actor) ? P.Aout : 1) : P.Hd;
+      __nv_bfloat16* dst = wptr(L) + static_cast<size_t>(g) * L.NB * L.RB * L.kp;
+      if (l == 0) {  // input = cat[determ, stoch]  (rssm.py:29-31)
+        PackSeg segs[2] = {{0, 0, P.D}, {P.Dp, P.D, P.S}};
+        RLSB_TRY(launch_pack(hp->w[l], P.D + P.S, n_out, dst, L.RB, L.NB * L.RB, L.kp, 2, segs, s));
+      } else {
+        PackSeg segs[1] = {{0, 0, P.Hd}};
+        RLSB_TRY(launch_pack(hp->w[l], P.Hd, n_out, dst, L.RB, L.NB * L.RB, L.kp, 1, segs, s));
+      }
+      RLSB_TRY(copy_pad(hp->b[l], n_out, fptr(L.bias_off) + static_cast<size_t>(g) * L.NB * L.RB,
+                        L.NB * L.RB, 0.f, s));
+      if (l < 4) {
+        const int lnp = ru(L.N, 32);
+        // fc_nn.py:15 — the first LayerNorm always exists; later ones only with layer_norm
+        RLSB_TRY(copy_pad(hp->ln_g[l], L.N, fptr(L.g_off) + static_cast<size_t>(g) * lnp, lnp, 1.f, s));
+        RLSB_TRY(copy_pad(hp->ln_b[l], L.N, fptr(L.b_off) + static_cast<size_t>(g) * lnp, lnp, 0.f, s));
+      }
+    }
+  }
+  return 0;
+}
+
+extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0,
+                                const float* z0, const float* logits0, const rlsb_noise* noise,
+                                const rlsb_imagine_out* out, void* workspace, void* stream_) {
+  if (!cfg || !packed || !h0 || !z0 || !noise || !out || !workspace || N <= 0) return -1;
+  if (!out->determ || !out->logits || !out->stoch_idx || !out->actions || !out->rewards || !out->discounts)
+    return -2;
+  if (N > (1LL << 30)) return -3;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  Plan P;
+  RLSB_TRY(make_plan(*cfg, P));
+  Workspace W;
+  make_workspace(P, N, W);
+  const int M = static_cast<int>(N);
+  const int m_pad = W.m_pad;
+  const int m_tiles = m_pad / 128;
+  const int H = cfg->H;
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto wbf = [&](const LayerPlan& L) { return reinterpret_cast<const __nv_bfloat16*>(pk + L.w_off); };
+  auto pf = [&](size_t off) { return reinterpret_cast<const float*>(pk + off); };
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  float* scratch = reinterpret_cast<float*>(ws + W.scratch);
+  float* stats = reinterpret_cast<float*>(ws + W.stats);
+  float* head_out = reinterpret_cast<float*>(ws + W.head_out);
+  const bool ln = cfg->layer_norm != 0;
+  const float eps = 1e-5f;
+  const size_t ND = static_cast<size_t>(N) * P.D, NS = static_cast<size_t>(N) * P.S;
+
+  // ---- start state ---------------------------------------------------------------------------
+  {
+    PackSeg seg[1] = {{0, 0, P.D}};
+    RLSB_TRY(launch_pack(h0, P.D, M, bf(W.hbf[0]), 128, m_pad, P.Dp, 1, seg, s));
+    PackSeg segz[1] = {{0, 0, P.S}};
+    RLSB_TRY(launch_pack(z0, P.S, M, bf(W.zbf[0]), 128, m_pad, P.Sp, 1, segz, s));
+    // rows >= N of the other one-hot image are never written by the sampler: clear its last M tile
+    const size_t tile_row_bytes = static_cast<size_t>(P.Sp / 64) * 128 * 64 * 2;
+    cudaError_t e = cudaMemsetAsync(ws + W.zbf[1] + static_cast<size_t>(m_tiles - 1) * tile_row_bytes, 0,
+                                    tile_row_bytes, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaMemcpyAsync(out->determ, h0, ND * 4, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (logits0) e = cudaMemcpyAsync(out->logits, logits0, NS * 4, cudaMemcpyDeviceToDevice, s);
+    else e = cudaMemsetAsync(out->logits, 0, NS * 4, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (out->stoch) {
+      e = cudaMemcpyAsync(out->stoch, z0, NS * 4, cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    e = cudaMemsetAsync(out->actions, 0, static_cast<size_t>(N) * P.A * 4, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const long long tot = N * cfg->groups;
+    onehot_to_idx_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(z0, N, cfg->groups,
+                                                                                  cfg->classes, out->stoch_idx);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+
+  auto base_gemm = [&](const LayerPlan& L) {
+    GemmParams g{};
+    g.W = wbf(L); g.RB = L.RB; g.NB = L.NB; g.G = L.G;
+    g.M = M; g.m_tiles = m_tiles; g.N = L.N;
+    g.bias = pf(L.bias_off);
+    g.ln_eps = eps;
+    return g;
+  };
+
+  // Linear -> [LN] -> ELU -> packed bf16, for a single-group RSSM layer
+  auto rssm_layer = [&](const LayerPlan& L, GemmParams g, bool has_ln, __nv_bfloat16* outp) -> int {
+    if (L.fullrow) {
+      g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
+      g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
+      g.act = ACT_ELU;
+      g.out_bf16 = outp; g.out_kpad = P.Dp; g.out_bf16_group_stride = 0;
+      return launch_gemm(g, EPI_LN_ACT, s);
+    }
+    g.out_f32 = scratch; g.ldo = W.ld_scratch; g.out_group_stride = 0; g.stats = stats;
+    RLSB_TRY(launch_gemm(g, has_ln ? EPI_STATS : EPI_PLAIN, s));
+    return launch_ln_act(scratch, W.ld_scratch, stats, L.NB, L.RB, M, m_pad, L.N,
+                         has_ln ? pf(L.g_off) : nullptr, has_ln ? pf(L.b_off) : nullptr, eps, ACT_ELU,
+                         outp, P.Dp, s);
+  };
+
+  int cur = 0;
+  for (int t = 0; t <= H; ++t) {
+    const __nv_bfloat16* hb = bf(W.hbf[cur]);
+    const __nv_bfloat16* zb = bf(W.zbf[cur]);
+    // ---- heads on s_t = cat[h_t, z_t]: actor, reward, discount, target critic -------------------
+    for (int l = 0; l < 5; ++l) {
+      const LayerPlan& L = P.head[l];
+      GemmParams g = base_gemm(L);
+      if (l == 0) {
+        g.n_seg = 2;
+        g.A[0] = hb; g.a_ktiles[0] = P.Dp / 64; g.a_group_stride[0] = 0;
+        g.A[1] = zb; g.a_ktiles[1] = P.Sp / 64; g.a_group_stride[1] = 0;
+      } else {
+        g.n_seg = 1;
+        g.A[0] = bf(W.hid[(l - 1) & 1]); g.a_ktiles[0] = P.Hp / 64;
+        g.a_group_stride[0] = static_cast<long long>(m_pad) * P.Hp;
+      }
+      if (l < 4) {
+        const bool has_ln = (l == 0) || ln;
+        g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
+        g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
+        g.act = ACT_ELU;
+        g.out_bf16 = bf(W.hid[l & 1]); g.out_kpad = P.Hp;
+        g.out_bf16_group_stride = static_cast<long long>(m_pad) * P.Hp;
+        RLSB_TRY(launch_gemm(g, EPI_LN_ACT, s));
+      } else {
+        g.out_f32 = head_out; g.ldo = 32; g.out_group_stride = static_cast<long long>(m_pad) * 32;
+        RLSB_TRY(launch_gemm(g, EPI_PLAIN, s));
+      }
+    }
+    HeadFinishParams hf{};
+    hf.head_out = head_out; hf.ldo = 32; hf.group_stride = static_cast<long long>(m_pad) * 32;
+    hf.g_actor = P.g_actor; hf.g_reward = P.g_reward; hf.g_discount = P.g_discount; hf.g_critic = P.g_critic;
+    hf.M = M; hf.m_pad = m_pad; hf.A = P.A; hf.discrete = cfg->discrete;
+    hf.first_step = (t == 0); hf.want_action = (t < H);
+    hf.noise.explicit_noise = noise->action_noise ? noise->action_noise + static_cast<size_t>(t) * N * P.A : nullptr;
+    hf.noise.ld = P.A; hf.noise.seed = noise->seed; hf.noise.step = static_cast<uint32_t>(t);
+    hf.noise.row_offset = noise->row_offset;
+    hf.reward_out = out->rewards + static_cast<size_t>(t) * N;
+    hf.discount_out = out->discounts + static_cast<size_t>(t) * N;
+    hf.value_out = out->values ? out->values + static_cast<size_t>(t) * N : nullptr;
+    hf.action_out = (t < H) ? out->actions + static_cast<size_t>(t + 1) * N * P.A : nullptr;
+    hf.actor_raw_out = (out->actor_raw && t < H) ? out->actor_raw + static_cast<size_t>(t) * N * P.Aout : nullptr;
+    hf.precomp = (noise->precomp_actions && t < H) ? noise->precomp_actions + static_cast<size_t>(t) * N * P.A : nullptr;
+    hf.action_packed = bf(W.abf); hf.a_kpad = P.Ap;
+    RLSB_TRY(launch_head_finish(hf, s));
+    if (t == H) break;
+
+    const int nxt = cur ^ 1;
+    // ---- x = ELU(LN?(W_in [z, a] + b))                                   rssm.py:179 ----------
+    {
+      GemmParams g = base_gemm(P.img_in);
+      g.n_seg = 2;
+      g.A[0] = zb; g.a_ktiles[0] = P.Sp / 64;
+      g.A[1] = bf(W.abf); g.a_ktiles[1] = P.Ap / 64;
+      RLSB_TRY(rssm_layer(P.img_in, g, ln, bf(W.xbf)));
+    }
+    // ---- h' = GRU(x, h)                                    rssm.py:181, common.py:69-81 ----------
+    {
+      GemmParams g = base_gemm(P.gru);
+      g.n_seg = 2;
+      g.A[0] = bf(W.xbf); g.a_ktiles[0] = P.Dp / 64;
+      g.A[1] = hb; g.a_ktiles[1] = P.Dp / 64;
+      g.out_f32 = scratch; g.ldo = W.ld_scratch; g.stats = stats;
+      RLSB_TRY(launch_gemm(g, EPI_STATS, s));
+      RLSB_TRY(launch_gru_gate(scratch, W.ld_scratch, stats, P.gru.NB, P.gru.RB, M, m_pad, P.D,
+                               pf(P.gru.g_off), pf(P.gru.b_off), eps, -1.0f,
+                               out->determ + static_cast<size_t>(t) * ND, P.D,
+                               out->determ + static_cast<size_t>(t + 1) * ND, P.D, bf(W.hbf[nxt]), P.Dp, s));
+    }
+    // ---- prior logits = W2 ELU(LN?(W1 h' + b1)) + b2                      rssm.py:192 ----------
+    {
+      GemmParams g = base_gemm(P.prior1);
+      g.n_seg = 1;
+      g.A[0] = bf(W.hbf[nxt]); g.a_ktiles[0] = P.Dp / 64;
+      RLSB_TRY(rssm_layer(P.prior1, g, ln, bf(W.ybf)));
+      GemmParams g2 = base_gemm(P.prior2);
+      g2.n_seg = 1;
+      g2.A[0] = bf(W.ybf); g2.a_ktiles[0] = P.Dp / 64;
+      g2.out_f32 = out->logits + static_cast<size_t>(t + 1) * NS; g2.ldo = P.S;
+      RLSB_TRY(launch_gemm(g2, EPI_PLAIN, s));
+    }
+    // ---- z' ~ OneHotCategoricalST(logits)                                rssm.py:34-37 ----------
+    {
+      NoiseSpec ns{};
+      ns.explicit_noise = noise->latent_uniforms ? noise->latent_uniforms + static_cast<size_t>(t) * NS : nullptr;
+      ns.ld = P.S; ns.seed = noise->seed; ns.step = static_cast<uint32_t>(t); ns.row_offset = noise->row_offset;
+      RLSB_TRY(launch_sample_latent(out->logits + static_cast<size_t>(t + 1) * NS, P.S, M, cfg->groups,
+                                    cfg->classes, ns, out->stoch_idx + static_cast<size_t>(t + 1) * N * cfg->groups,
+                                    bf(W.zbf[nxt]), P.Sp,
+                                    out->stoch ? out->stoch + static_cast<size_t>(t + 1) * NS : nullptr, P.S, s));
+    }
+    cur = nxt;
+  }
+  return 0;
+}

@@ -1,0 +1,666 @@
+// rlsb_kernels.cu — HBM-bound kernels of the imagination path: operand packing, LayerNorm /
+// GRU-gate application, categorical sampling, head post-processing and the lambda-return scan.
+#include "rlsb_kernels.cuh"
+
+#include "rlsb_detmath.h"
+#include "rlsb_gemm.cuh"
+#include "rlsb_ptx.cuh"
+
+namespace rlsb {
+
+namespace {
+
+__device__ __forceinline__ uint32_t bf2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == ACT_ELU) return x > 0.f ? x : expm1f(x);
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
+  return x;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------
+// pack: one thread per 16-byte destination chunk (8 bf16)
+// ------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* src;
+  long long ld_src;
+  int rows_src;
+  __nv_bfloat16* dst;
+  int RB, rows_dst_pad, k_pad, n_seg;
+  PackSeg seg[3];
+};
+
+__global__ void pack_kernel(const PackArgs a) {
+  const long long chunks_per_row = a.k_pad >> 3;
+  const long long total = static_cast<long long>(a.rows_dst_pad) * chunks_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / chunks_per_row;
+    const int k0 = static_cast<int>(i - row * chunks_per_row) << 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = 0.f;
+      if (row < a.rows_src) {
+        const int k = k0 + j;
+        for (int s = 0; s < a.n_seg; ++s) {
+          const int off = k - a.seg[s].dst_k0;
+          if (off >= 0 && off < a.seg[s].len)
+            x = __ldg(a.src + row * a.ld_src + a.seg[s].src_c0 + off);
+        }
+      }
+      v[j] = x;
+    }
+    uint4 pk = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+    const size_t idx = packed_index(static_cast<size_t>(row), static_cast<size_t>(k0),
+                                    static_cast<size_t>(a.k_pad), a.RB);
+    *reinterpret_cast<uint4*>(a.dst + idx) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// combine per-block (mean, M2) partials (Chan et al.) into row mean / rstd
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void combine_stats(const float* stats, int NB, int RB, int m_pad, int m,
+                                              int N, float eps, float& mean, float& rstd) {
+  const float2* st = reinterpret_cast<const float2*>(stats);
+  float tot = 0.f;
+  for (int b = 0; b < NB; ++b) {
+    const int nb = min(RB, N - b * RB);
+    if (nb > 0) tot += static_cast<float>(nb) * __ldg(&st[static_cast<size_t>(b) * m_pad + m]).x;
+  }
+  mean = tot / static_cast<float>(N);
+  float m2 = 0.f;
+  for (int b = 0; b < NB; ++b) {
+    const int nb = min(RB, N - b * RB);
+    if (nb > 0) {
+      const float2 s = __ldg(&st[static_cast<size_t>(b) * m_pad + m]);
+      const float d = s.x - mean;
+      m2 += s.y + static_cast<float>(nb) * d * d;
+    }
+  }
+  rstd = 1.0f / sqrtf(m2 / static_cast<float>(N) + eps);
+}
+
+struct LnActArgs {
+  const float* scratch;
+  long long ld;
+  const float* stats;
+  int NB, RB, M, m_pad, N;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int act;
+  __nv_bfloat16* out;
+  int out_kpad;
+};
+
+__global__ void ln_act_kernel(const LnActArgs a) {
+  const int chunks_per_row = a.out_kpad >> 3;
+  const long long total = static_cast<long long>(a.m_pad) * chunks_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / chunks_per_row);
+    const int c0 = static_cast<int>(i - static_cast<long long>(m) * chunks_per_row) << 3;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = 0.f;
+    if (m < a.M && c0 < a.N) {
+      float mean = 0.f, rstd = 1.f;
+      if (a.gamma) combine_stats(a.stats, a.NB, a.RB, a.m_pad, m, a.N, a.eps, mean, rstd);
+      const float* src = a.scratch + static_cast<size_t>(m) * a.ld + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j < a.N) {
+          float v = src[j];
+          if (a.gamma) v = (v - mean) * rstd * __ldg(a.gamma + c0 + j) + __ldg(a.beta + c0 + j);
+          y[j] = act_apply(v, a.act);
+        }
+      }
+    }
+    uint4 pk = make_uint4(bf2(y[0], y[1]), bf2(y[2], y[3]), bf2(y[4], y[5]), bf2(y[6], y[7]));
+    const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0),
+                                    static_cast<size_t>(a.out_kpad), kTileM);
+    *reinterpret_cast<uint4*>(a.out + idx) = pk;
+  }
+}
+
+struct GruArgs {
+  const float* scratch;
+  long long ld;
+  const float* stats;
+  int NB, RB, M, m_pad, D;
+  const float* gamma;
+  const float* beta;
+  float eps, update_bias;
+  const float* h_prev;
+  long long ld_h;
+  float* h_next;
+  long long ld_hn;
+  __nv_bfloat16* h_packed;
+  int kpad;
+};
+
+__global__ void gru_gate_kernel(const GruArgs a) {
+  const int chunks_per_row = a.kpad >> 3;
+  const long long total = static_cast<long long>(a.m_pad) * chunks_per_row;
+  const int D = a.D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / chunks_per_row);
+    const int c0 = static_cast<int>(i - static_cast<long long>(m) * chunks_per_row) << 3;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = 0.f;
+    if (m < a.M && c0 < D) {
+      float mean, rstd;
+      combine_stats(a.stats, a.NB, a.RB, a.m_pad, m, 3 * D, a.eps, mean, rstd);
+      const float* src = a.scratch + static_cast<size_t>(m) * a.ld;
+      const float* hp = a.h_prev + static_cast<size_t>(m) * a.ld_h;
+      float* hn = a.h_next + static_cast<size_t>(m) * a.ld_hn;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        if (c < D) {
+          const float pr = (src[c] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
+          const float pc = (src[D + c] - mean) * rstd * __ldg(a.gamma + D + c) + __ldg(a.beta + D + c);
+          const float pu =
+              (src[2 * D + c] - mean) * rstd * __ldg(a.gamma + 2 * D + c) + __ldg(a.beta + 2 * D + c);
+          const float r = sigmoidf_(pr);
+          const float cand = tanhf(r * pc);
+          const float u = sigmoidf_(pu + a.update_bias);
+          const float h = u * cand + (1.0f - u) * hp[c];
+          hn[c] = h;
+          y[j] = h;
+        }
+      }
+    }
+    uint4 pk = make_uint4(bf2(y[0], y[1]), bf2(y[2], y[3]), bf2(y[4], y[5]), bf2(y[6], y[7]));
+    const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0),
+                                    static_cast<size_t>(a.kpad), kTileM);
+    *reinterpret_cast<uint4*>(a.h_packed + idx) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// noise
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float noise_uniform(const NoiseSpec& ns, int m, uint32_t stream,
+                                               uint32_t e) {
+  if (ns.explicit_noise) return __ldg(ns.explicit_noise + static_cast<size_t>(m) * ns.ld + e);
+  return rlsb_noise_uniform(ns.seed, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, e);
+}
+
+// Box-Muller on two Philox uniforms (device-only path; parity tests pass explicit normals)
+__device__ __forceinline__ float noise_normal(const NoiseSpec& ns, int m, uint32_t stream, uint32_t e) {
+  if (ns.explicit_noise) return __ldg(ns.explicit_noise + static_cast<size_t>(m) * ns.ld + e);
+  const float u1 = rlsb_noise_uniform(ns.seed, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, 2 * e);
+  const float u2 = rlsb_noise_uniform(ns.seed, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, 2 * e + 1);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// ------------------------------------------------------------------------------------------
+// latent sampling: one thread per (row, group); classes == 32
+// ------------------------------------------------------------------------------------------
+struct SampleLatentArgs {
+  const float* logits;
+  long long ld;
+  int M, groups;
+  NoiseSpec noise;
+  uint8_t* idx_out;
+  __nv_bfloat16* onehot_packed;
+  int kpad;
+  float* onehot_f32;
+  long long ld_f32;
+};
+
+__global__ void sample_latent_kernel(const SampleLatentArgs a) {
+  const long long total = static_cast<long long>(a.M) * a.groups;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int m = static_cast<int>(i / a.groups);
+  const int g = static_cast<int>(i - static_cast<long long>(m) * a.groups);
+  const float4* lp = reinterpret_cast<const float4*>(a.logits + static_cast<size_t>(m) * a.ld + g * 32);
+  float best = 0.f;
+  int best_k = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 l4 = __ldg(lp + q);
+    float u[4];
+    if (a.noise.explicit_noise) {
+      const float4 u4 = __ldg(reinterpret_cast<const float4*>(a.noise.explicit_noise +
+                                                              static_cast<size_t>(m) * a.noise.ld + g * 32) + q);
+      u[0] = u4.x; u[1] = u4.y; u[2] = u4.z; u[3] = u4.w;
+    } else {
+      uint32_t o[4];
+      rlsb_philox4x32(a.noise.row_offset + static_cast<uint32_t>(m), a.noise.step, 0u,
+                      static_cast<uint32_t>(g * 8 + q), static_cast<uint32_t>(a.noise.seed),
+                      static_cast<uint32_t>(a.noise.seed >> 32), o);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) u[t] = rlsb_u32_to_uniform(o[t]);
+    }
+    const float l[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float s = __fadd_rn(l[t], rlsb_gumbel(u[t]));
+      const int k = q * 4 + t;
+      if (k == 0 || s > best) {  // strict '>' keeps the lowest index on ties (== argmax)
+        best = s;
+        best_k = k;
+      }
+    }
+  }
+  a.idx_out[static_cast<size_t>(m) * a.groups + g] = static_cast<uint8_t>(best_k);
+  if (a.onehot_packed) {
+    // group g occupies columns [32g, 32g+32): 4 chunks of 8 bf16
+    const int c0 = g * 32;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      const int rel = best_k - ch * 8;
+      if (rel >= 0 && rel < 8) w[rel >> 1] = (rel & 1) ? 0x3F800000u : 0x00003F80u;  // bf16 1.0
+      const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0 + ch * 8),
+                                      static_cast<size_t>(a.kpad), kTileM);
+      *reinterpret_cast<uint4*>(a.onehot_packed + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  if (a.onehot_f32) {
+    float4* op = reinterpret_cast<float4*>(a.onehot_f32 + static_cast<size_t>(m) * a.ld_f32 + g * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int rel = best_k - q * 4;
+      if (rel == 0) o.x = 1.f;
+      if (rel == 1) o.y = 1.f;
+      if (rel == 2) o.z = 1.f;
+      if (rel == 3) o.w = 1.f;
+      op[q] = o;
+    }
+  }
+}
+
+// generic categorical (rows x classes) with explicit uniforms: indices only
+__global__ void sample_categorical_kernel(const float* __restrict__ logits,
+                                          const float* __restrict__ uniforms, long long rows,
+                                          int classes, int32_t* __restrict__ idx_out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= rows) return;
+  const float* l = logits + i * classes;
+  const float* u = uniforms + i * classes;
+  float best = 0.f;
+  int best_k = 0;
+  for (int k = 0; k < classes; ++k) {
+    const float s = __fadd_rn(__ldg(l + k), rlsb_gumbel(__ldg(u + k)));
+    if (k == 0 || s > best) {
+      best = s;
+      best_k = k;
+    }
+  }
+  idx_out[i] = best_k;
+}
+
+// ------------------------------------------------------------------------------------------
+// head post-processing: reward / value / discount read-out + action draw (one thread per row)
+// ------------------------------------------------------------------------------------------
+__global__ void head_finish_kernel(const HeadFinishParams p) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= p.m_pad) return;
+  const bool valid = m < p.M;
+  if (valid) {
+    if (p.g_reward >= 0 && p.reward_out)
+      p.reward_out[m] = p.head_out[p.g_reward * p.group_stride + static_cast<long long>(m) * p.ldo];
+    if (p.g_critic >= 0 && p.value_out)
+      p.value_out[m] = p.head_out[p.g_critic * p.group_stride + static_cast<long long>(m) * p.ldo];
+    if (p.discount_out) {
+      float d = 1.0f;
+      if (p.g_discount >= 0 && !p.first_step) {
+        // torch Bernoulli(logits).mode: (probs >= 0.5), NaN where probs == 0.5 (world_model.py:137)
+        const float x = p.head_out[p.g_discount * p.group_stride + static_cast<long long>(m) * p.ldo];
+        const float pr = sigmoidf_(x);
+        d = pr > 0.5f ? 1.0f : (pr == 0.5f ? __int_as_float(0x7fc00000) : 0.0f);
+      }
+      p.discount_out[m] = d;
+    }
+  }
+  if (!p.want_action || p.g_actor < 0) return;
+  const float* ao = p.head_out + p.g_actor * p.group_stride + static_cast<long long>(m) * p.ldo;
+  // zero the padded packed row first (a_kpad is 64 for every shipped config)
+  float act[64];
+  for (int k = 0; k < p.a_kpad && k < 64; ++k) act[k] = 0.f;
+  if (valid && p.precomp) {
+    for (int k = 0; k < p.A; ++k) act[k] = p.precomp[static_cast<size_t>(m) * p.A + k];
+    if (p.action_out)
+      for (int k = 0; k < p.A; ++k) p.action_out[static_cast<size_t>(m) * p.A + k] = act[k];
+  } else if (valid) {
+    if (p.discrete) {
+      float best = 0.f;
+      int best_k = 0;
+      for (int k = 0; k < p.A; ++k) {
+        const float u = p.noise.explicit_noise
+                            ? __ldg(p.noise.explicit_noise + static_cast<size_t>(m) * p.noise.ld + k)
+                            : rlsb_noise_uniform(p.noise.seed, p.noise.row_offset + m, p.noise.step, 1u, k);
+        const float s = __fadd_rn(ao[k], rlsb_gumbel(u));
+        if (k == 0 || s > best) {
+          best = s;
+          best_k = k;
+        }
+        if (p.actor_raw_out) p.actor_raw_out[static_cast<size_t>(m) * p.A + k] = ao[k];
+      }
+      act[best_k] = 1.0f;
+    } else {
+      // TruncatedNormal(tanh(mu), 2*sigmoid(s/2)+0.1).rsample() == unclamped Normal.rsample
+      // (dists.py:108-129 overrides only sample(); dreamer_v2.py:87 calls rsample)
+      for (int k = 0; k < p.A; ++k) {
+        const float mu = tanhf(ao[k]);
+        const float sd = 2.0f * sigmoidf_(ao[p.A + k] * 0.5f) + 0.1f;
+        const float e = noise_normal(p.noise, m, 1u, k);
+        act[k] = mu + e * sd;
+        if (p.actor_raw_out) {
+          p.actor_raw_out[static_cast<size_t>(m) * 2 * p.A + k] = ao[k];
+          p.actor_raw_out[static_cast<size_t>(m) * 2 * p.A + p.A + k] = ao[p.A + k];
+        }
+      }
+    }
+    if (p.action_out)
+      for (int k = 0; k < p.A; ++k) p.action_out[static_cast<size_t>(m) * p.A + k] = act[k];
+  }
+  if (p.action_packed) {
+    for (int c0 = 0; c0 < p.a_kpad; c0 += 8) {
+      uint4 pk = make_uint4(bf2(act[c0], act[c0 + 1]), bf2(act[c0 + 2], act[c0 + 3]),
+                            bf2(act[c0 + 4], act[c0 + 5]), bf2(act[c0 + 6], act[c0 + 7]));
+      const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0),
+                                      static_cast<size_t>(p.a_kpad), kTileM);
+      *reinterpret_cast<uint4*>(p.action_packed + idx) = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: lambda-return reverse scan + shifted cumprod weights + advantage
+//   time-major layout (T, N): one thread per start state, operations in the reference's order
+//   (ac.py:57-58: rs[i] + ds[i] * ((1-l)*vs[i+1] + l*V)), each rounded once => bit-identical
+//   to the fp32 torch loop.
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void lambda_return_tm_kernel(const float* __restrict__ r, const float* __restrict__ v,
+                                        const float* __restrict__ d, int T, long long N, float c1,
+                                        float c2, float* __restrict__ vs, float* __restrict__ w,
+                                        float* __restrict__ adv) {
+  const long long n0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * VEC;
+  if (n0 >= N) return;
+  const int H = T - 1;
+  float V[VEC], vnext[VEC];
+  if (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(v + static_cast<size_t>(H) * N + n0);
+    V[0] = t.x; V[1 % VEC] = t.y; V[2 % VEC] = t.z; V[3 % VEC] = t.w;
+  } else {
+    V[0] = v[static_cast<size_t>(H) * N + n0];
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) vnext[j] = V[j];
+  float Vup[VEC];  // V[t+1] (needed for adv[t] = vs[t+1] - v[t])
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) Vup[j] = 0.f;
+  for (int t = H - 1; t >= 0; --t) {
+    float rr[VEC], dd[VEC], vv[VEC];
+    const size_t off = static_cast<size_t>(t) * N + n0;
+    if (VEC == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(r + off);
+      const float4 b = *reinterpret_cast<const float4*>(d + off);
+      const float4 c = *reinterpret_cast<const float4*>(v + off);
+      rr[0] = a.x; rr[1 % VEC] = a.y; rr[2 % VEC] = a.z; rr[3 % VEC] = a.w;
+      dd[0] = b.x; dd[1 % VEC] = b.y; dd[2 % VEC] = b.z; dd[3 % VEC] = b.w;
+      vv[0] = c.x; vv[1 % VEC] = c.y; vv[2 % VEC] = c.z; vv[3 % VEC] = c.w;
+    } else {
+      rr[0] = r[off]; dd[0] = d[off]; vv[0] = v[off];
+    }
+    float out[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float mix = __fadd_rn(__fmul_rn(c1, vnext[j]), __fmul_rn(c2, V[j]));
+      out[j] = __fadd_rn(rr[j], __fmul_rn(dd[j], mix));
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(vs + off) = make_float4(out[0], out[1 % VEC], out[2 % VEC], out[3 % VEC]);
+    } else {
+      vs[off] = out[0];
+    }
+    if (adv && t <= H - 2 && t + 1 <= H - 1) {
+      // adv[t] = vs[t+1] - v[t]
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(adv + off) =
+            make_float4(__fsub_rn(V[0], vv[0]), __fsub_rn(V[1 % VEC], vv[1 % VEC]),
+                        __fsub_rn(V[2 % VEC], vv[2 % VEC]), __fsub_rn(V[3 % VEC], vv[3 % VEC]));
+      } else {
+        adv[off] = __fsub_rn(V[0], vv[0]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      Vup[j] = V[j];
+      V[j] = out[j];
+      vnext[j] = vv[j];
+    }
+  }
+  (void)Vup;
+  if (w) {
+    // w[0] = 1, w[t] = w[t-1] * d[t-1]   (dreamer_v2.py:194-197)
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 1.0f;
+    for (int t = 0; t < T; ++t) {
+      const size_t off = static_cast<size_t>(t) * N + n0;
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(w + off) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+        const float4 b = *reinterpret_cast<const float4*>(d + off);
+        acc[0] = __fmul_rn(acc[0], b.x);
+        acc[1 % VEC] = __fmul_rn(acc[1 % VEC], b.y);
+        acc[2 % VEC] = __fmul_rn(acc[2 % VEC], b.z);
+        acc[3 % VEC] = __fmul_rn(acc[3 % VEC], b.w);
+      } else {
+        w[off] = acc[0];
+        acc[0] = __fmul_rn(acc[0], d[off]);
+      }
+    }
+  }
+}
+
+// batch-major layout (N, T), T <= 32: warp-shuffle reverse scan over affine maps
+//   V_t = a_t + b_t * V_{t+1},  a_t = r_t + d_t*(1-l)*v_{t+1},  b_t = d_t*l
+__global__ void lambda_return_bm_kernel(const float* __restrict__ r, const float* __restrict__ v,
+                                        const float* __restrict__ d, int T, int Tp, long long N,
+                                        float c1, float c2, float* __restrict__ vs,
+                                        float* __restrict__ w, float* __restrict__ adv) {
+  const int rows_per_warp = 32 / Tp;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / Tp;   // which row inside the warp
+  const int t = lane - sub * Tp;
+  const long long n = warp_global * rows_per_warp + sub;
+  const int H = T - 1;
+  const bool active = (n < N) && (t < T);
+  float rt = 0.f, dt = 0.f, vt = 0.f;
+  if (active) {
+    const size_t off = static_cast<size_t>(n) * T + t;
+    rt = r[off]; dt = d[off]; vt = v[off];
+  }
+  const float vnext = __shfl_down_sync(0xffffffffu, vt, 1);
+  float a, b;
+  if (t < H) {
+    a = rt + dt * (c1 * vnext);
+    b = dt * c2;
+  } else {  // t == H holds the bootstrap, t > H padding
+    a = (t == H) ? vt : 0.f;
+    b = 0.f;
+  }
+  // shifted cumprod: inclusive scan of d, then shift by one
+  float cp = dt;
+  for (int off = 1; off < Tp; off <<= 1) {
+    const float a2 = __shfl_down_sync(0xffffffffu, a, off);
+    const float b2 = __shfl_down_sync(0xffffffffu, b, off);
+    const float c_up = __shfl_up_sync(0xffffffffu, cp, off);
+    if (t + off < Tp) {
+      a = a + b * a2;
+      b = b * b2;
+    }
+    if (t >= off) cp = cp * c_up;
+  }
+  float wt = __shfl_up_sync(0xffffffffu, cp, 1);
+  if (t == 0) wt = 1.0f;
+  const float Vn = __shfl_down_sync(0xffffffffu, a, 1);  // V_{t+1}
+  if (active) {
+    if (t < H) vs[static_cast<size_t>(n) * H + t] = a;
+    if (w) w[static_cast<size_t>(n) * T + t] = wt;
+    if (adv && t < H - 1) adv[static_cast<size_t>(n) * (H - 1) + t] = Vn - vt;
+  }
+}
+
+// backward of the reverse scan = forward scan (time-major); gradients w.r.t. r, v, d
+__global__ void lambda_return_bwd_kernel(const float* __restrict__ g_vs, const float* __restrict__ v,
+                                         const float* __restrict__ d, const float* __restrict__ vs,
+                                         int T, long long N, float c1, float c2,
+                                         float* __restrict__ g_r, float* __restrict__ g_v,
+                                         float* __restrict__ g_d) {
+  const long long n = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (n >= N) return;
+  const int H = T - 1;
+  float G = 0.f;       // dL/dV_t (total)
+  float carry = 0.f;   // contribution flowing from V_{t-1}
+  if (g_v) g_v[n] = 0.f;
+  for (int t = 0; t < H; ++t) {
+    const size_t off = static_cast<size_t>(t) * N + n;
+    G = g_vs[off] + carry;
+    const float dt = d[off];
+    const float vn = v[off + N];
+    const float Vn = (t + 1 < H) ? vs[off + N] : vn;  // V_{t+1}; V_H = v_H
+    if (g_r) g_r[off] = G;
+    if (g_d) g_d[off] = G * (c1 * vn + c2 * Vn);
+    if (g_v) {
+      float gv = G * dt * c1;
+      if (t + 1 == H) gv += G * dt * c2;  // bootstrap V_H = v_H
+      g_v[off + N] = gv;
+    }
+    carry = G * dt * c2;
+  }
+  if (g_d) g_d[static_cast<size_t>(H) * N + n] = 0.f;
+  if (g_r) g_r[static_cast<size_t>(H) * N + n] = 0.f;
+}
+
+inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
+                int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream) {
+  if (n_seg < 0 || n_seg > 3 || (k_pad % 64) != 0 || RB <= 0 || (rows_dst_pad % RB) != 0) return -1;
+  PackArgs a{};
+  a.src = src; a.ld_src = ld_src; a.rows_src = rows_src; a.dst = dst; a.RB = RB;
+  a.rows_dst_pad = rows_dst_pad; a.k_pad = k_pad; a.n_seg = n_seg;
+  for (int s = 0; s < n_seg; ++s) a.seg[s] = segs[s];
+  const long long total = static_cast<long long>(rows_dst_pad) * (k_pad / 8);
+  pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB, int RB, int M,
+                  int m_pad, int N, const float* gamma, const float* beta, float eps, int act,
+                  __nv_bfloat16* out, int out_kpad, cudaStream_t stream) {
+  LnActArgs a{scratch, ld, stats, NB, RB, M, m_pad, N, gamma, beta, eps, act, out, out_kpad};
+  const long long total = static_cast<long long>(m_pad) * (out_kpad / 8);
+  ln_act_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_gru_gate(const float* scratch, long long ld, const float* stats, int NB, int RB, int M,
+                    int m_pad, int D, const float* gamma, const float* beta, float eps,
+                    float update_bias, const float* h_prev, long long ld_h, float* h_next,
+                    long long ld_hn, __nv_bfloat16* h_next_packed, int kpad, cudaStream_t stream) {
+  GruArgs a{scratch, ld, stats, NB, RB, M, m_pad, D, gamma, beta, eps, update_bias,
+            h_prev, ld_h, h_next, ld_hn, h_next_packed, kpad};
+  const long long total = static_cast<long long>(m_pad) * (kpad / 8);
+  gru_gate_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_sample_latent(const float* logits, long long ld, int M, int groups, int classes,
+                         NoiseSpec noise, uint8_t* idx_out, __nv_bfloat16* onehot_packed, int kpad,
+                         float* onehot_f32, long long ld_f32, cudaStream_t stream) {
+  if (classes != 32) return -1;
+  SampleLatentArgs a{logits, ld, M, groups, noise, idx_out, onehot_packed, kpad, onehot_f32, ld_f32};
+  const long long total = static_cast<long long>(M) * groups;
+  const int block = 128;
+  sample_latent_kernel<<<static_cast<unsigned>((total + block - 1) / block), block, 0, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_sample_categorical(const float* logits, const float* uniforms, long long rows, int classes,
+                              int32_t* idx_out, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  const int block = 128;
+  sample_categorical_kernel<<<static_cast<unsigned>((rows + block - 1) / block), block, 0, stream>>>(
+      logits, uniforms, rows, classes, idx_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream) {
+  if (p.a_kpad > 64 || (p.a_kpad % 8) != 0) return -1;
+  const int block = 128;
+  head_finish_kernel<<<(p.m_pad + block - 1) / block, block, 0, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_lambda_return(const float* r, const float* v, const float* d, int T, long long N,
+                         float lambda_, float* vs, float* w, float* adv, int layout_batch_major,
+                         cudaStream_t stream) {
+  if (T < 2 || N <= 0) return -1;
+  // (1 - lambda) is formed in double like the Python expression in ac.py:58, then rounded to fp32
+  const float c1 = static_cast<float>(1.0 - static_cast<double>(lambda_));
+  const float c2 = lambda_;
+  const int block = 256;
+  if (layout_batch_major) {
+    if (T > 32) return -2;
+    int Tp = 1;
+    while (Tp < T) Tp <<= 1;
+    const long long warps = (N + (32 / Tp) - 1) / (32 / Tp);
+    const long long threads = warps * 32;
+    lambda_return_bm_kernel<<<static_cast<unsigned>((threads + block - 1) / block), block, 0, stream>>>(
+        r, v, d, T, Tp, N, c1, c2, vs, w, adv);
+  } else {
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(v) |
+                                       reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(vs) |
+                                       reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(adv)) % 16 == 0);
+    if (vec) {
+      const long long threads = N / 4;
+      lambda_return_tm_kernel<4><<<static_cast<unsigned>((threads + block - 1) / block), block, 0, stream>>>(
+          r, v, d, T, N, c1, c2, vs, w, adv);
+    } else {
+      lambda_return_tm_kernel<1><<<static_cast<unsigned>((N + block - 1) / block), block, 0, stream>>>(
+          r, v, d, T, N, c1, c2, vs, w, adv);
+    }
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
+                             int T, long long N, float lambda_, float* g_r, float* g_v, float* g_d,
+                             cudaStream_t stream) {
+  if (T < 2 || N <= 0) return -1;
+  const float c1 = static_cast<float>(1.0 - static_cast<double>(lambda_));
+  const float c2 = lambda_;
+  const int block = 256;
+  lambda_return_bwd_kernel<<<static_cast<unsigned>((N + block - 1) / block), block, 0, stream>>>(
+      g_vs, v, d, vs, T, N, c1, c2, g_r, g_v, g_d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace rlsb

@@ -1,0 +1,80 @@
+// rlsb_kernels.cuh — launchers for the non-GEMM kernels (packing, LayerNorm/gates, sampling,
+// lambda-return scan, slot attention).  All launchers return cudaError_t as int.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace rlsb {
+
+struct PackSeg {
+  int dst_k0;  // first destination column (inside the padded K axis)
+  int src_c0;  // first source column
+  int len;     // columns
+};
+
+// fp32 row-major [rows_src x *] (leading dim ld_src) -> packed bf16 [rows_dst_pad x k_pad] with
+// row block RB; everything not covered by a segment (and rows >= rows_src) is written as zero.
+int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
+                int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream);
+
+// scratch fp32 [M_pad x ld] + per-block (mean, M2) partials -> [LayerNorm] -> act -> packed bf16
+int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB, int RB, int M,
+                  int m_pad, int N, const float* gamma, const float* beta, float eps, int act,
+                  __nv_bfloat16* out, int out_kpad, cudaStream_t stream);
+
+// GRU gate update (reference: common.py:69-81).  scratch = W[x,h]+b over 3D columns
+// (reset | cand | update), LayerNorm over all 3D jointly, then
+//   r = sigmoid(p_r); c = tanh(r * p_c); u = sigmoid(p_u + update_bias); h' = u*c + (1-u)*h
+int launch_gru_gate(const float* scratch, long long ld, const float* stats, int NB, int RB, int M,
+                    int m_pad, int D, const float* gamma, const float* beta, float eps,
+                    float update_bias, const float* h_prev, long long ld_h, float* h_next,
+                    long long ld_hn, __nv_bfloat16* h_next_packed, int kpad, cudaStream_t stream);
+
+struct NoiseSpec {
+  const float* explicit_noise;  // uniforms (categorical) / normals (continuous) or nullptr
+  long long ld;                 // row stride of the explicit tensor (elements)
+  uint64_t seed;                // Philox key when explicit_noise == nullptr
+  uint32_t step;                // imagination step (Philox counter word)
+  uint32_t row_offset;          // global index of local row 0 (multi-GPU sharding)
+};
+
+// 32x32 (groups x classes) straight-through categorical draw by Gumbel-max with the
+// deterministic transform of rlsb_detmath.h (reference: rssm.py:34-37, dists.py:177-179).
+int launch_sample_latent(const float* logits, long long ld, int M, int groups, int classes,
+                         NoiseSpec noise, uint8_t* idx_out, __nv_bfloat16* onehot_packed, int kpad,
+                         float* onehot_f32, long long ld_f32, cudaStream_t stream);
+
+// standalone categorical sampler on arbitrary (rows x groups x classes<=64) logits: indices only
+int launch_sample_categorical(const float* logits, const float* uniforms, long long rows, int classes,
+                              int32_t* idx_out, cudaStream_t stream);
+
+struct HeadFinishParams {
+  const float* head_out;  // [G][m_pad][ldo]
+  long long ldo, group_stride;
+  int g_actor, g_reward, g_discount, g_critic;  // group ids, -1 = absent
+  int M, m_pad, A;
+  int discrete;
+  int first_step;  // t == 0: discount := 1
+  int want_action; // t < H
+  NoiseSpec noise;
+  float* reward_out;    // [M]
+  float* discount_out;  // [M]
+  float* value_out;     // [M]
+  float* action_out;    // [M][A]   (actions[t+1])
+  float* actor_raw_out; // [M][A or 2A] raw actor head output (logits / mean,std pre-activations) or nullptr
+  const float* precomp; // [M][A] action to replay instead of sampling, or nullptr
+  __nv_bfloat16* action_packed;  // [m_pad x a_kpad]
+  int a_kpad;
+};
+int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream);
+
+// K2 (reference: ac.py:52-66 + dreamer_v2.py:192-197 + ac.py:118)
+int launch_lambda_return(const float* r, const float* v, const float* d, int T, long long N,
+                         float lambda_, float* vs, float* w, float* adv, int layout_batch_major,
+                         cudaStream_t stream);
+int launch_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
+                             int T, long long N, float lambda_, float* g_r, float* g_v, float* g_d,
+                             cudaStream_t stream);
+
+}  // namespace rlsb

@@ -1,0 +1,322 @@
+"""Torch-facing wrappers over the C ABI (include/rlsb.h).
+
+torch supplies device memory and the current stream; all arithmetic happens in librlsb.so.
+Every function raises if the library or a B200 device is missing — there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ImagineCfg, ImagineOut, ImagineParams, MlpParams, Noise, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise _lib.RlsbError(f"expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    return t.contiguous()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+def lambda_return(r: torch.Tensor, v: torch.Tensor, d: torch.Tensor, lambda_: float,
+                  batch_major: bool = False, want_weights: bool = True, want_adv: bool = True):
+    """lambda-return + cumprod weights + advantage (ac.py:52-66, dreamer_v2.py:192-197, ac.py:118).
+
+    time-major: r, v, d are (T, N[, 1]); returns vs (T-1, N), w (T, N), adv (T-2, N).
+    """
+    _lib.require_device()
+    lib = _lib.load()
+    r, v, d = _f32c(r), _f32c(v), _f32c(d)
+    if batch_major:
+        N, T = r.shape[0], r.shape[1]
+        vs = torch.empty((N, T - 1), device=r.device, dtype=torch.float32)
+        w = torch.empty((N, T), device=r.device, dtype=torch.float32) if want_weights else None
+        adv = torch.empty((N, T - 2), device=r.device, dtype=torch.float32) if want_adv else None
+    else:
+        T = r.shape[0]
+        N = r[0].numel()
+        vs = torch.empty((T - 1,) + tuple(r.shape[1:]), device=r.device, dtype=torch.float32)
+        w = torch.empty_like(r) if want_weights else None
+        adv = torch.empty((T - 2,) + tuple(r.shape[1:]), device=r.device, dtype=torch.float32) if want_adv else None
+    if v.numel() != r.numel() or d.numel() != r.numel():
+        raise _lib.RlsbError("lambda_return: r, v, d must have the same number of elements (T*N)")
+    check(lib.rlsb_lambda_return_fwd(r.data_ptr(), v.data_ptr(), d.data_ptr(), T, N, float(lambda_),
+                                     vs.data_ptr(), _ptr(w), _ptr(adv), int(batch_major), _stream()),
+          "rlsb_lambda_return_fwd")
+    return vs, w, adv
+
+
+def lambda_return_bwd(g_vs, v, d, vs, lambda_):
+    _lib.require_device()
+    lib = _lib.load()
+    g_vs, v, d, vs = _f32c(g_vs), _f32c(v), _f32c(d), _f32c(vs)
+    T = v.shape[0]
+    N = v[0].numel()
+    g_r, g_v, g_d = torch.empty_like(v), torch.empty_like(v), torch.empty_like(v)
+    check(lib.rlsb_lambda_return_bwd(g_vs.data_ptr(), v.data_ptr(), d.data_ptr(), vs.data_ptr(), T, N,
+                                     float(lambda_), g_r.data_ptr(), g_v.data_ptr(), g_d.data_ptr(), _stream()),
+          "rlsb_lambda_return_bwd")
+    return g_r, g_v, g_d
+
+
+class LambdaReturnFn(torch.autograd.Function):
+    """Differentiable K2 (needed when rho != 1: dynamics back-propagation, ac.py:121-123)."""
+
+    @staticmethod
+    def forward(ctx, r, v, d, lambda_):
+        vs, _, _ = lambda_return(r, v, d, lambda_, want_weights=False, want_adv=False)
+        ctx.save_for_backward(v, d, vs)
+        ctx.lambda_ = lambda_
+        return vs
+
+    @staticmethod
+    def backward(ctx, g_vs):
+        v, d, vs = ctx.saved_tensors
+        g_r, g_v, g_d = lambda_return_bwd(g_vs.contiguous(), v, d, vs, ctx.lambda_)
+        return g_r, g_v, g_d, None
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler / RNG
+# ------------------------------------------------------------------------------------------------
+def sample_categorical(logits: torch.Tensor, uniforms: torch.Tensor) -> torch.Tensor:
+    """idx = argmax_k(logits + gumbel(u)) over the last axis (dists.py:177-179); int32 indices."""
+    _lib.require_device()
+    lib = _lib.load()
+    logits, uniforms = _f32c(logits), _f32c(uniforms)
+    classes = logits.shape[-1]
+    rows = logits.numel() // classes
+    idx = torch.empty(logits.shape[:-1], device=logits.device, dtype=torch.int32)
+    check(lib.rlsb_sample_categorical(logits.data_ptr(), uniforms.data_ptr(), rows, classes, idx.data_ptr(),
+                                      _stream()), "rlsb_sample_categorical")
+    return idx
+
+
+def philox_uniform(seed: int, n0: int, t: int, stream_id: int, per_row: int, rows: int,
+                   device="cuda") -> torch.Tensor:
+    _lib.require_device()
+    lib = _lib.load()
+    out = torch.empty((rows, per_row), device=device, dtype=torch.float32)
+    check(lib.rlsb_philox_uniform(seed, n0, t, stream_id, per_row, out.numel(), out.data_ptr(), _stream()),
+          "rlsb_philox_uniform")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# packed operands + GEMM (test surface for the kernel every layer uses)
+# ------------------------------------------------------------------------------------------------
+def pack_rows(x: torch.Tensor, row_block: int = 128, rows_pad: Optional[int] = None,
+              k_pad: Optional[int] = None) -> torch.Tensor:
+    _lib.require_device()
+    lib = _lib.load()
+    x = _f32c(x)
+    rows, cols = x.shape
+    rows_pad = rows_pad or round_up(rows, row_block)
+    k_pad = k_pad or round_up(cols, 64)
+    out = torch.empty(rows_pad * k_pad, device=x.device, dtype=torch.bfloat16)
+    check(lib.rlsb_pack_rows(x.data_ptr(), cols, rows, out.data_ptr(), row_block, rows_pad, k_pad, 0, 0, cols,
+                             _stream()), "rlsb_pack_rows")
+    return out
+
+
+def unpack_rows(packed: torch.Tensor, rows: int, cols: int, row_block: int = 128,
+                k_pad: Optional[int] = None) -> torch.Tensor:
+    """Inverse of the packed layout (host-side index math; tests only)."""
+    k_pad = k_pad or round_up(cols, 64)
+    dev = packed.device
+    r = torch.arange(rows, device=dev).view(-1, 1)
+    k = torch.arange(cols, device=dev).view(1, -1)
+    rb, rr = r // row_block, r % row_block
+    kt, kk = k // 64, k % 64
+    chunk = (kk // 8) ^ (rr % 8)
+    idx = ((rb * (k_pad // 64) + kt) * row_block + rr) * 64 + chunk * 8 + (kk % 8)
+    return packed[idx.reshape(-1)].view(rows, cols).float()
+
+
+def plan_blocks(n: int) -> tuple[int, int]:
+    """(row_block, n_blocks) the library uses for an output width n (see rlsb_imagine.cu::plan_nb)."""
+    if round_up(n, 32) <= 512:
+        return round_up(n, 32), 1
+    nb = (n + 255) // 256
+    return round_up((n + nb - 1) // nb, 32), nb
+
+
+def gemm_bias(a_packed, k_pad, w_packed, rb, nb, bias, M, N, want_stats=False):
+    _lib.require_device()
+    lib = _lib.load()
+    m_pad = round_up(M, 128)
+    out = torch.zeros((m_pad, N), device=a_packed.device, dtype=torch.float32)
+    stats = torch.zeros((nb, m_pad, 2), device=a_packed.device, dtype=torch.float32) if want_stats else None
+    bias_p = torch.zeros(rb * nb, device=a_packed.device, dtype=torch.float32)
+    if bias is not None:
+        bias_p[:N] = bias
+    check(lib.rlsb_gemm_bias(a_packed.data_ptr(), k_pad, w_packed.data_ptr(), rb, nb, bias_p.data_ptr(), M, N,
+                             out.data_ptr(), N, _ptr(stats), _stream()), "rlsb_gemm_bias")
+    return out[:M], stats
+
+
+def gemm_ln_act(a_packed, k_pad, w_packed, rb, bias, M, N, gamma, beta, eps, act, out_kpad=None):
+    _lib.require_device()
+    lib = _lib.load()
+    m_pad = round_up(M, 128)
+    out_kpad = out_kpad or round_up(N, 64)
+    out = torch.empty(m_pad * out_kpad, device=a_packed.device, dtype=torch.bfloat16)
+    pad = lambda t, fill: None if t is None else torch.cat(
+        [t.float(), torch.full((rb - N,), fill, device=t.device)]).contiguous()
+    bias_p, g_p, b_p = pad(bias, 0.0), pad(gamma, 1.0), pad(beta, 0.0)
+    check(lib.rlsb_gemm_ln_act(a_packed.data_ptr(), k_pad, w_packed.data_ptr(), rb, _ptr(bias_p), M, N,
+                               _ptr(g_p), _ptr(b_p), float(eps), int(act), out.data_ptr(), out_kpad, _stream()),
+          "rlsb_gemm_ln_act")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ImagineConfig:
+    D: int
+    A: int
+    discrete: bool
+    layer_norm: bool
+    predict_discount: bool
+    H: int = 15
+    groups: int = 32
+    classes: int = 32
+    hidden: int = 400
+    with_critic: bool = True
+
+    def to_c(self) -> ImagineCfg:
+        return ImagineCfg(self.D, self.groups, self.classes, self.A, self.hidden, int(self.discrete),
+                          int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H)
+
+
+def _mlp_params(sd: dict, prefix: str, keep: list) -> MlpParams:
+    """fc_nn.py Sequential indices: Linear 0,3,6,9,12; LayerNorm 1,4,7,10."""
+    mp = MlpParams()
+    for i, li in enumerate((0, 3, 6, 9, 12)):
+        w, b = _f32c(sd[f"{prefix}{li}.weight"]), _f32c(sd[f"{prefix}{li}.bias"])
+        keep += [w, b]
+        mp.w[i], mp.b[i] = w.data_ptr(), b.data_ptr()
+    for i, li in enumerate((1, 4, 7, 10)):
+        key = f"{prefix}{li}.weight"
+        if key in sd:
+            g, b = _f32c(sd[key]), _f32c(sd[f"{prefix}{li}.bias"])
+            keep += [g, b]
+            mp.ln_g[i], mp.ln_b[i] = g.data_ptr(), b.data_ptr()
+    return mp
+
+
+class ImaginationEngine:
+    """Owns the packed bf16 weight images and the activation workspace of K1.
+
+    ``pack`` must be called whenever the fp32 parameters change (once per optimizer step);
+    ``rollout`` replaces DreamerV2.imagine_trajectory (dreamer_v2.py:68-96) for N start states.
+    """
+
+    def __init__(self, cfg: ImagineConfig, device="cuda"):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.ccfg = cfg.to_c()
+        self.device = torch.device(device)
+        nbytes = self.lib.rlsb_imagine_packed_bytes(C.byref(self.ccfg))
+        if nbytes == 0:
+            raise _lib.RlsbError(f"unsupported imagination config {cfg}")
+        self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+        self._ws = None
+        self._ws_rows = 0
+
+    # state-dict keys follow SURVEY Appendix A.1 / A.2 (reference module attribute names)
+    def pack(self, wm_sd: dict, actor_sd: dict, critic_sd: Optional[dict],
+             rssm_prefix="recurrent_model.", target_prefix="target_critic.") -> None:
+        keep: list = []
+        p = ImagineParams()
+
+        def take(sd, key):
+            if key not in sd:
+                return None
+            t = _f32c(sd[key])
+            keep.append(t)
+            return t.data_ptr()
+
+        rp = rssm_prefix
+        p.img_in_w, p.img_in_b = take(wm_sd, rp + "pre_determ_recurrent.0.weight"), take(wm_sd, rp + "pre_determ_recurrent.0.bias")
+        p.img_in_ln_g, p.img_in_ln_b = take(wm_sd, rp + "pre_determ_recurrent.1.weight"), take(wm_sd, rp + "pre_determ_recurrent.1.bias")
+        p.gru_w, p.gru_b = take(wm_sd, rp + "determ_recurrent._layer.weight"), take(wm_sd, rp + "determ_recurrent._layer.bias")
+        p.gru_ln_g, p.gru_ln_b = take(wm_sd, rp + "determ_recurrent._norm.weight"), take(wm_sd, rp + "determ_recurrent._norm.bias")
+        p.prior1_w, p.prior1_b = take(wm_sd, rp + "ensemble_prior_estimator.0.weight"), take(wm_sd, rp + "ensemble_prior_estimator.0.bias")
+        p.prior1_ln_g, p.prior1_ln_b = take(wm_sd, rp + "ensemble_prior_estimator.1.weight"), take(wm_sd, rp + "ensemble_prior_estimator.1.bias")
+        p.prior2_w, p.prior2_b = take(wm_sd, rp + "ensemble_prior_estimator.3.weight"), take(wm_sd, rp + "ensemble_prior_estimator.3.bias")
+        p.actor = _mlp_params(actor_sd, "actor.", keep)
+        p.reward = _mlp_params(wm_sd, "reward_predictor.", keep)
+        if self.cfg.predict_discount:
+            p.discount = _mlp_params(wm_sd, "discount_predictor.", keep)
+        if self.cfg.with_critic:
+            p.critic = _mlp_params(critic_sd, target_prefix, keep)
+        check(self.lib.rlsb_imagine_pack(C.byref(self.ccfg), C.byref(p), self.packed.data_ptr(), _stream()),
+              "rlsb_imagine_pack")
+        # `keep` tensors must outlive the enqueued pack kernels: stream-ordered frees make that safe
+        self._keep = keep
+
+    def workspace(self, n: int) -> torch.Tensor:
+        if self._ws is None or self._ws_rows < n:
+            nbytes = self.lib.rlsb_imagine_workspace_bytes(C.byref(self.ccfg), n)
+            self._ws = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+            self._ws_rows = n
+        return self._ws
+
+    def rollout(self, h0: torch.Tensor, z0: torch.Tensor, logits0: Optional[torch.Tensor] = None,
+                latent_uniforms: Optional[torch.Tensor] = None, action_noise: Optional[torch.Tensor] = None,
+                seed: int = 0, row_offset: int = 0, precomp_actions: Optional[torch.Tensor] = None,
+                horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
+                out: Optional[dict] = None) -> dict:
+        cfg = self.cfg
+        H = horizon if horizon is not None else cfg.H
+        ccfg = cfg.to_c()
+        ccfg.H = H
+        h0, z0 = _f32c(h0), _f32c(z0)
+        n = h0.shape[0]
+        S = cfg.groups * cfg.classes
+        dev = h0.device
+        if out is None:
+            out = {
+                "determ": torch.empty((H + 1, n, cfg.D), device=dev, dtype=torch.float32),
+                "logits": torch.empty((H + 1, n, S), device=dev, dtype=torch.float32),
+                "stoch_idx": torch.empty((H + 1, n, cfg.groups), device=dev, dtype=torch.uint8),
+                "stoch": torch.empty((H + 1, n, S), device=dev, dtype=torch.float32) if want_stoch else None,
+                "actions": torch.empty((H + 1, n, cfg.A), device=dev, dtype=torch.float32),
+                "rewards": torch.empty((H + 1, n), device=dev, dtype=torch.float32),
+                "discounts": torch.empty((H + 1, n), device=dev, dtype=torch.float32),
+                "values": torch.empty((H + 1, n), device=dev, dtype=torch.float32) if cfg.with_critic else None,
+                "actor_raw": torch.empty((H, n, cfg.A if cfg.discrete else 2 * cfg.A), device=dev,
+                                         dtype=torch.float32) if want_actor_raw else None,
+            }
+        co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
+                                                      "rewards", "discounts", "values", "actor_raw")])
+        nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)),
+                   _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
+                   _ptr(None if precomp_actions is None else _f32c(precomp_actions)))
+        ws = self.workspace(n)
+        check(self.lib.rlsb_imagine_fwd(C.byref(ccfg), self.packed.data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
+                                        _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
+                                        C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")
+        return out

@@ -1,0 +1,211 @@
+"""Stand-alone GPU probe (not a pytest file): exercises every C-ABI entry point against the oracle
+and prints error statistics.  Used for bring-up on a B200 via gpurun; the pytest suite covers the
+same ground with assertions."""
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import oracle_port as orc  # noqa: E402
+from rl_sandbox_b200 import ops  # noqa: E402
+
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def stat(name, got, ref, atol=0.0):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    err = (got - ref).abs()
+    rel = err / (ref.abs() + 1e-6)
+    scale = ref.abs().max().item()
+    print(f"  {name:28s} max_abs={err.max().item():.3e} mean_abs={err.mean().item():.3e} "
+          f"max|ref|={scale:.3e} nan={int(torch.isnan(got).sum())}", flush=True)
+    return err.max().item()
+
+
+def section(title):
+    print(f"\n=== {title} ===", flush=True)
+
+
+def run(fn):
+    try:
+        t0 = time.time()
+        fn()
+        torch.cuda.synchronize()
+        print(f"  [{fn.__name__} ok in {time.time() - t0:.2f}s]", flush=True)
+    except Exception:
+        traceback.print_exc()
+        print(f"  [{fn.__name__} FAILED]", flush=True)
+
+
+def t_lambda():
+    section("K2 lambda-return vs C oracle (bit-exact) ")
+    T, N = 16, 1000
+    g = torch.Generator().manual_seed(1)
+    r, v = torch.randn(T, N, generator=g), torch.randn(T, N, generator=g)
+    d = (torch.rand(T, N, generator=g) > 0.1).float()
+    vs_o, w_o, adv_o = orc.lambda_return_c(r.numpy(), v.numpy(), d.numpy(), 0.95)
+    vs, w, adv = ops.lambda_return(r.to(dev), v.to(dev), d.to(dev), 0.95)
+    print("  bit-exact vs:", bool((vs.cpu().numpy() == vs_o).all()), " w:", bool((w.cpu().numpy() == w_o).all()),
+          " adv:", bool((adv.cpu().numpy() == adv_o).all()))
+    loop = orc.lambda_return_loop(v, r[:-1], d, 0.95)
+    print("  bit-exact vs torch loop:", bool((vs.cpu() == loop).all()))
+    vs2, w2, adv2 = ops.lambda_return(r.t().contiguous().to(dev), v.t().contiguous().to(dev),
+                                      d.t().contiguous().to(dev), 0.95, batch_major=True)
+    stat("batch-major vs", vs2.t(), torch.from_numpy(vs_o))
+    stat("batch-major w", w2.t(), torch.from_numpy(w_o))
+    stat("batch-major adv", adv2.t(), torch.from_numpy(adv_o))
+    # backward vs autograd
+    rr, vv, dd = r.clone().requires_grad_(), v.clone().requires_grad_(), d.clone().requires_grad_()
+    out = orc.lambda_return_loop(vv, rr[:-1], dd, 0.95)
+    gvs = torch.randn(T - 1, N, generator=g)
+    (out * gvs).sum().backward()
+    g_r, g_v, g_d = ops.lambda_return_bwd(gvs.to(dev), v.to(dev), d.to(dev), vs, 0.95)
+    stat("bwd g_r", g_r[:-1], rr.grad[:-1]); stat("bwd g_v", g_v, vv.grad); stat("bwd g_d", g_d[:-1], dd.grad[:-1])
+
+
+def t_rng():
+    section("Philox / sampler vs C oracle (bit-exact)")
+    u = ops.philox_uniform(1234567890123, 7, 3, 0, 1024, 50).cpu().numpy()
+    uo = orc.philox_uniform(1234567890123, 7, 3, 0, 1024, 50)
+    print("  philox bit-exact:", bool((u == uo).all()), "min/max", u.min(), u.max())
+    g = torch.Generator().manual_seed(2)
+    logits = torch.randn(4000, 32, 32, generator=g) * 2
+    un = torch.rand(4000, 32, 32, generator=g)
+    idx = ops.sample_categorical(logits.to(dev), un.to(dev)).cpu().long()
+    idx_o = orc.sample_categorical(logits, un)
+    print("  sampler mismatches:", int((idx != idx_o).sum()), "of", idx.numel())
+    # distribution sanity: empirical frequencies follow softmax
+    lg = torch.tensor([[0.0, 1.0, 2.0, -1.0]]).repeat(200000, 1)
+    un2 = torch.rand(200000, 4, generator=g)
+    f = torch.bincount(ops.sample_categorical(lg.to(dev), un2.to(dev)).cpu().long(), minlength=4) / 200000.0
+    print("  freq", f.tolist(), "softmax", torch.softmax(lg[0], 0).tolist())
+
+
+def t_pack():
+    section("pack / unpack round trip")
+    x = torch.randn(300, 200, device=dev)
+    p = ops.pack_rows(x)
+    y = ops.unpack_rows(p, 300, 200)
+    stat("pack->unpack vs bf16(x)", y, x.bfloat16().float())
+
+
+def gemm_case(M, K, N, stats=False):
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    rb, nb = ops.plan_blocks(N)
+    kp = ops.round_up(K, 64)
+    xp = ops.pack_rows(x)
+    wp = ops.pack_rows(w, row_block=rb, rows_pad=rb * nb, k_pad=kp)
+    out, st = ops.gemm_bias(xp, kp, wp, rb, nb, b, M, N, want_stats=stats)
+    ref = x.bfloat16().float() @ w.bfloat16().float().t() + b
+    e = stat(f"gemm M{M} K{K} N{N} rb{rb} nb{nb}", out, ref)
+    if stats:
+        # recombine partial stats
+        mean = ref.mean(-1)
+        var = ref.var(-1, unbiased=False)
+        cnt = torch.tensor([min(rb, N - i * rb) for i in range(nb)], device=dev).float().view(-1, 1)
+        mb, m2b = st[:, :M, 0], st[:, :M, 1]
+        mean_c = (cnt * mb).sum(0) / N
+        var_c = (m2b + cnt * (mb - mean_c) ** 2).sum(0) / N
+        stat("  stats mean", mean_c, mean); stat("  stats var", var_c, var)
+    return e
+
+
+def t_gemm():
+    section("tcgen05 GEMM (plain / stats)")
+    gemm_case(128, 64, 32)
+    gemm_case(128, 64, 256)
+    gemm_case(300, 128, 64)
+    gemm_case(300, 448, 400)
+    gemm_case(1000, 2048, 3072, stats=True)
+    gemm_case(5000, 1088, 1024, stats=True)
+    gemm_case(777, 256, 600, stats=True)
+
+
+def t_gemm_ln():
+    section("tcgen05 GEMM + LayerNorm + ELU (full-row epilogue)")
+    for (M, K, N, use_ln) in [(300, 448, 400, True), (1000, 2048, 400, True), (300, 256, 200, False), (260, 448, 17, False)]:
+        g = torch.Generator().manual_seed(M + K + N)
+        x = torch.randn(M, K, generator=g).to(dev)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+        b = torch.randn(N, generator=g).to(dev)
+        gam = (1 + 0.1 * torch.randn(N, generator=g)).to(dev)
+        bet = (0.1 * torch.randn(N, generator=g)).to(dev)
+        rb, nb = ops.plan_blocks(N)
+        kp = ops.round_up(K, 64)
+        xp = ops.pack_rows(x)
+        wp = ops.pack_rows(w, row_block=rb, rows_pad=rb, k_pad=kp)
+        okp = ops.round_up(N, 64)
+        outp = ops.gemm_ln_act(xp, kp, wp, rb, b, M, N, gam if use_ln else None, bet if use_ln else None, 1e-5, 1, okp)
+        y = ops.unpack_rows(outp, M, okp, k_pad=okp)
+        pre = x.bfloat16().float() @ w.bfloat16().float().t() + b
+        if use_ln:
+            pre = torch.nn.functional.layer_norm(pre, (N,), gam, bet, 1e-5)
+        ref = torch.nn.functional.elu(pre).bfloat16().float()
+        stat(f"ln_act M{M} K{K} N{N} ln={use_ln}", y[:, :N], ref)
+        if okp > N:
+            print("   padding columns zero:", bool((y[:, N:] == 0).all()))
+
+
+def imagine_case(D, A, discrete, layer_norm, predict_discount, N, H=4):
+    wm, actor, critic = orc.make_params(3, D=D, A=A, discrete=discrete, layer_norm=layer_norm,
+                                        predict_discount=predict_discount)
+    h0, z0 = orc.make_start(4, N, D)
+    g = torch.Generator().manual_seed(5)
+    lat_u = torch.rand(H, N, 1024, generator=g)
+    act_n = torch.rand(H, N, A, generator=g) if discrete else torch.randn(H, N, A, generator=g)
+    cfg = ops.ImagineConfig(D=D, A=A, discrete=discrete, layer_norm=layer_norm, predict_discount=predict_discount, H=H)
+    eng = ops.ImaginationEngine(cfg)
+    to = lambda sd: {k: v.to(dev) for k, v in sd.items()}
+    eng.pack(to(wm), to(actor), to(critic))
+    out = eng.rollout(h0.to(dev), z0.to(dev), None, lat_u.to(dev), act_n.to(dev), want_actor_raw=True)
+    torch.cuda.synchronize()
+    print(f" -- config D={D} A={A} discrete={discrete} ln={layer_norm} pd={predict_discount} N={N} H={H}")
+    for bf16 in (True, False):
+        ref = orc.imagine(wm, actor, critic, h0, z0, H=H, A=A, discrete=discrete, predict_discount=predict_discount,
+                          latent_uniforms=lat_u, action_noise=act_n, bf16=bf16)
+        print(f"  free-running vs oracle(bf16={bf16}):")
+        mism = (out["stoch_idx"].cpu().long() != ref["stoch_idx"]).float().mean(dim=(1, 2))
+        print("   latent idx mismatch rate per step:", [f"{x:.4f}" for x in mism.tolist()])
+        if discrete:
+            am = (out["actions"].cpu().argmax(-1) != ref["actions"].argmax(-1)).float().mean(1)
+            print("   action mismatch rate per step:", [f"{x:.4f}" for x in am.tolist()])
+        for k in ("determ", "logits", "rewards", "values", "discounts", "actor_raw"):
+            if out.get(k) is not None and k in ref:
+                stat(f"{k} (t<=1)", out[k][:2], ref[k][:2])
+        # teacher-forced: feed the GPU trajectory's states to the oracle and compare one-step outputs
+        teacher = {"determ": out["determ"].cpu(), "stoch": out["stoch"].cpu()}
+        tf = orc.imagine(wm, actor, critic, h0, z0, H=H, A=A, discrete=discrete, predict_discount=predict_discount,
+                         latent_uniforms=lat_u, action_noise=act_n, bf16=bf16, teacher=teacher,
+                         precomp_actions=out["actions"].cpu()[1:])
+        print(f"  teacher-forced vs oracle(bf16={bf16}):")
+        for k in ("determ", "logits", "rewards", "values", "actor_raw"):
+            if out.get(k) is not None and k in tf:
+                stat(k, out[k], tf[k])
+        mism = (out["stoch_idx"].cpu().long()[1:] != tf["stoch_idx"][1:]).float().mean().item()
+        print(f"   latent idx mismatch (teacher-forced, own logits differ slightly): {mism:.5f}")
+        # exact check: sampler applied to the GPU's OWN logits must reproduce the GPU's indices
+        own = orc.sample_categorical(out["logits"][1:].cpu().view(H, N, 32, 32), lat_u.view(H, N, 32, 32))
+        print("   idx == oracle_sampler(GPU logits, uniforms):", bool((own == out["stoch_idx"][1:].cpu().long()).all()))
+
+
+def t_imagine():
+    section("K1 imagination rollout vs oracle port")
+    imagine_case(200, 12, False, False, False, 300)
+    imagine_case(1024, 17, True, True, True, 300)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), torch.__version__)
+    which = sys.argv[1:] or ["lambda", "rng", "pack", "gemm", "gemm_ln", "imagine"]
+    table = dict(lambda_=t_lambda, rng=t_rng, pack=t_pack, gemm=t_gemm, gemm_ln=t_gemm_ln, imagine=t_imagine)
+    table["lambda"] = t_lambda
+    for w in which:
+        run(table[w])
