@@ -39,13 +39,14 @@ const char* rlsb_error_string(int code);
  *   vs      : (H, N)     V_t = r_t + d_t * ((1-lambda) v_{t+1} + lambda V_{t+1}),  V_H = v_H
  *   w       : (T, N)     w_0 = 1, w_t = w_{t-1} * d_{t-1}                 (may be NULL)
  *   adv     : (H-1, N)   adv_t = vs_{t+1} - v_t                           (may be NULL)
- * time-major results are bit-identical to the reference's fp32 loop. */
+ * lambda_ is a double because the reference forms (1 - lambda) in Python double arithmetic before
+ * it meets the fp32 tensors; time-major results are bit-identical to the reference's fp32 loop. */
 int rlsb_lambda_return_fwd(const float* r, const float* v, const float* d, int T, int64_t N,
-                           float lambda_, float* vs, float* w, float* adv,
+                           double lambda_, float* vs, float* w, float* adv,
                            int layout_batch_major, void* stream);
 /* gradients of sum(g_vs * vs) w.r.t. r, v, d (time-major); any output may be NULL */
 int rlsb_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
-                           int T, int64_t N, float lambda_, float* g_r, float* g_v, float* g_d,
+                           int T, int64_t N, double lambda_, float* g_r, float* g_v, float* g_d,
                            void* stream);
 
 /* ---- categorical sampler (bit-exact test surface) -------------------------------------------

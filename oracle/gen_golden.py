@@ -1,0 +1,133 @@
+"""gen_golden.py — TEST INFRASTRUCTURE.  Generates tests/golden/*.npz|json by RUNNING THE REFERENCE
+(imported unmodified from /root/reference through oracle/ref_harness.py) on seeded inputs and
+explicit noise.  Run in the build container only:  python -m oracle.gen_golden
+
+Fixtures
+  lambda_known_answers.json   the five known-answer vectors of the reference's own
+                              test/dreamer/test_critic.py:14-62, repaired for today's signature
+                              (SURVEY 4): the code reads vs[i+1], so the value sequence is shifted
+                              by one (a dummy v_0 is prepended) and gamma is folded into ds.  Each
+                              expected vector is the literal from the reference test AND is
+                              re-checked here against the reference's ImaginativeCritic._lambda_return.
+  imagine_<case>.npz          DreamerV2.imagine_trajectory (dreamer_v2.py:68-96) outputs, the
+                              target-critic values, lambda-returns (ac.py:64-66), cumprod weights
+                              (dreamer_v2.py:192-197) and the critic / actor losses
+                              (ac.py:68-81, 113-146) computed by the reference's own methods.
+Parameters are NOT stored: they are regenerated from a seed by oracle_port.make_params (the same
+tensors are loaded into the reference modules here), start states by oracle_port.make_start.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import oracle_port as orc
+from . import ref_harness as rh
+
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+CASES = {
+    # config 1 dims (agent/dreamer_v2_crafter.yaml): D=1024, discrete A=17, layer_norm, discount head
+    "c1": dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, N=6, H=3,
+               entropy_scale=3e-3, gamma=0.999, param_seed=11, start_seed=12, noise_seed=13),
+    # config 2 dims (agent/dreamer_v2.yaml): D=200, continuous A=12, no layer_norm, no discount head
+    "c2": dict(D=200, A=12, discrete=False, layer_norm=False, predict_discount=False, N=6, H=3,
+               entropy_scale=1e-5, gamma=0.99, param_seed=21, start_seed=22, noise_seed=23),
+    # longer horizon / more rows, config-2 dims (cheap to store)
+    "c2_long": dict(D=200, A=6, discrete=True, layer_norm=True, predict_discount=True, N=40, H=15,
+                    entropy_scale=1e-4, gamma=0.99, param_seed=31, start_seed=32, noise_seed=33),
+}
+
+
+def make_noise(case):
+    g = torch.Generator().manual_seed(case["noise_seed"])
+    H, N, A = case["H"], case["N"], case["A"]
+    lat = torch.rand(H, N, 1024, generator=g)
+    act = torch.rand(H, N, A, generator=g) if case["discrete"] else torch.randn(H, N, A, generator=g)
+    return lat, act
+
+
+def known_answers():
+    # literals from the reference's test/dreamer/test_critic.py:14-62
+    t = lambda *a: [float(x) for x in a]
+    ar = list(range(1, 11))
+    cases = [
+        dict(name="discount_0", lam=0.0, gamma=0.0, rs=t(*ar), vs_old=[1.0] * 10, expected=t(*ar), ref="test_critic.py:14-23"),
+        dict(name="lambda_0", lam=0.0, gamma=1.0, rs=[1.0] * 10, vs_old=t(*ar), expected=t(*range(2, 12)), ref="test_critic.py:25-34"),
+        dict(name="lambda_0_gamma_0_5", lam=0.0, gamma=0.5, rs=[1.0] * 10, vs_old=t(2, 2, 4, 4, 6, 6, 8, 8, 10, 10),
+             expected=t(2, 2, 3, 3, 4, 4, 5, 5, 6, 6), ref="test_critic.py:36-45"),
+        dict(name="lambda_1", lam=1.0, gamma=1.0, rs=[1.0] * 10, vs_old=t(*ar), expected=t(*range(20, 10, -1)), ref="test_critic.py:47-56"),
+        dict(name="lambda_1_gamma_0_5", lam=1.0, gamma=0.5, rs=[0.0] * 10, vs_old=t(*[2 ** k for k in range(1, 11)]),
+             expected=t(*[2 ** k for k in range(0, 10)]), ref="test_critic.py:58-62"),
+    ]
+    rh._import_reference()
+    from rl_sandbox.agents.dreamer.ac import ImaginativeCritic
+    critic = ImaginativeCritic(discount_factor=1, update_interval=100, soft_update_fraction=1,
+                               value_target_lambda=0.95, latent_dim=10, layer_norm=False)
+    for c in cases:
+        c["vs"] = [0.0] + c["vs_old"]               # state values v_0..v_10 (v_0 is never read)
+        c["ds"] = [c["gamma"]] * 11                   # gamma * ts
+        critic.lambda_ = c["lam"]
+        got = critic._lambda_return(torch.tensor(c["vs"]), torch.tensor(c["rs"]), torch.tensor(c["ds"]))
+        assert torch.equal(got, torch.tensor(c["expected"])), (c["name"], got)
+    (OUT / "lambda_known_answers.json").write_text(json.dumps(cases, indent=1))
+    print("lambda_known_answers.json: 5 vectors verified against the reference")
+
+
+def run_case(name, case):
+    D, A, H, N = case["D"], case["A"], case["H"], case["N"]
+    wm_sd, actor_sd, critic_sd = orc.make_params(case["param_seed"], D=D, A=A, discrete=case["discrete"],
+                                                 layer_norm=case["layer_norm"], predict_discount=case["predict_discount"])
+    h0, z0 = orc.make_start(case["start_seed"], N, D)
+    lat, act = make_noise(case)
+    agent = rh.build_agent(D=D, A=A, discrete=case["discrete"], layer_norm=case["layer_norm"],
+                           predict_discount=case["predict_discount"], H=H, entropy_scale=case["entropy_scale"],
+                           gamma=case["gamma"])
+    rh.load_params(agent, wm_sd, actor_sd, critic_sd)
+    state = rh.ref_state(agent, h0, z0)
+    q = rh.NoiseQueue(lat, act)
+    with rh.injected_noise(q):
+        # agents/dreamer_v2.py:182-207 (second half of DreamerV2.train), reference methods only
+        states, actions, rewards, discounts = agent.imagine_trajectory(state)
+        zs = states.combined
+        rewards = agent.world_model.reward_normalizer(rewards.float())
+        discounts = discounts.float()
+        values = agent.critic.target_critic(zs).mode
+        vs = agent.critic.lambda_return(zs, rewards[:-1], discounts)
+        w = torch.cumprod(torch.cat([torch.ones_like(discounts[:1]), discounts[:-1]], dim=0), dim=0).detach()
+        losses_c, metrics_c = agent.critic.calculate_loss(zs[:-1], vs, w[:-1])
+        losses_a, metrics_a = agent.actor.calculate_loss(zs[:-2], vs[1:], agent.critic.target_critic(zs[:-2]).mode,
+                                                         w[:-2], actions[1:-1])
+    assert q.log[:2] == (["action", "latent"] if case["discrete"] else ["action_normal", "latent"]), q.log[:4]
+    assert not q.latent and not q.action, "noise not fully consumed"
+    f = lambda x: x.detach().squeeze(-1).numpy().astype(np.float32) if x.dim() == 3 and x.shape[-1] == 1 else x.detach().numpy().astype(np.float32)
+    out = dict(
+        determ=states.determ.detach().numpy(), logits=states.stoch_logits.detach().reshape(H + 1, N, 1024).numpy(),
+        stoch_idx=states.stoch.detach().reshape(H + 1, N, 32, 32).argmax(-1).numpy().astype(np.uint8),
+        actions=actions.detach().numpy(), rewards=f(rewards), discounts=f(discounts), values=f(values), vs=f(vs), w=f(w),
+        loss_critic=np.float32(losses_c["loss_critic"].item()), loss_actor=np.float32(losses_a["loss_actor"].item()),
+        loss_actor_reinforce=np.float32(float(losses_a["loss_actor_reinforce"])),
+        loss_actor_dynamics_backprop=np.float32(float(losses_a["loss_actor_dynamics_backprop"])),
+        loss_actor_entropy=np.float32(float(losses_a["loss_actor_entropy"])),
+        critic_avg_target_value=np.float32(metrics_c["critic/avg_target_value"].item()),
+        critic_avg_lambda_value=np.float32(metrics_c["critic/avg_lambda_value"].item()),
+        critic_avg_predicted_value=np.float32(metrics_c["critic/avg_predicted_value"].item()),
+        meta=json.dumps({**case, "lam": 0.95, "rho": 1.0 if case["discrete"] else 0.0}),
+    )
+    np.savez_compressed(OUT / f"imagine_{name}.npz", **out)
+    print(f"imagine_{name}.npz written:", {k: getattr(v, 'shape', None) for k, v in out.items() if k != 'meta'})
+
+
+def main():
+    assert rh.available(), "reference checkout not found"
+    OUT.mkdir(parents=True, exist_ok=True)
+    known_answers()
+    for name, case in CASES.items():
+        run_case(name, case)
+
+
+if __name__ == "__main__":
+    main()

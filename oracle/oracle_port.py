@@ -88,7 +88,7 @@ def lambda_return_c(r, v, d, lam: float):
     vs = np.empty((T - 1, N), np.float32)
     w = np.empty((T, N), np.float32)
     adv = np.empty((max(T - 2, 0), N), np.float32)
-    clib().orc_lambda_return(_fp(r), _fp(v), _fp(d), C.c_int(T), C.c_int64(N), C.c_float(lam), _fp(vs), _fp(w),
+    clib().orc_lambda_return(_fp(r), _fp(v), _fp(d), C.c_int(T), C.c_int64(N), C.c_double(lam), _fp(vs), _fp(w),
                              _fp(adv))
     return vs, w, adv
 

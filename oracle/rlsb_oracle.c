@@ -109,10 +109,10 @@ void orc_philox_uniform(uint64_t seed, uint32_t n0, uint32_t t, uint32_t stream,
 
 /* time-major (T,N): V_H = v_H; V_t = r_t + d_t*((1-l) v_{t+1} + l V_{t+1}) in the reference's
  * operation order, one fp32 rounding per op (torch evaluates each op as a separate kernel). */
-void orc_lambda_return(const float* r, const float* v, const float* d, int T, int64_t N, float lambda_,
+void orc_lambda_return(const float* r, const float* v, const float* d, int T, int64_t N, double lambda_,
                        float* vs, float* w, float* adv) {
   const int H = T - 1;
-  const float c1 = (float)(1.0 - (double)lambda_), c2 = lambda_;
+  const float c1 = (float)(1.0 - lambda_), c2 = (float)lambda_;
   for (int64_t n = 0; n < N; ++n) {
     float V = v[(int64_t)H * N + n];
     for (int t = H - 1; t >= 0; --t) {

@@ -43,7 +43,7 @@ extern "C" const char* rlsb_error_string(int code) {
 }
 
 extern "C" int rlsb_lambda_return_fwd(const float* r, const float* v, const float* d, int T, int64_t N,
-                                      float lambda_, float* vs, float* w, float* adv,
+                                      double lambda_, float* vs, float* w, float* adv,
                                       int layout_batch_major, void* stream) {
   if (!r || !v || !d || !vs) return -1;
   return launch_lambda_return(r, v, d, T, N, lambda_, vs, w, adv, layout_batch_major,
@@ -51,7 +51,7 @@ extern "C" int rlsb_lambda_return_fwd(const float* r, const float* v, const floa
 }
 
 extern "C" int rlsb_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
-                                      int T, int64_t N, float lambda_, float* g_r, float* g_v, float* g_d,
+                                      int T, int64_t N, double lambda_, float* g_r, float* g_v, float* g_d,
                                       void* stream) {
   if (!g_vs || !v || !d || !vs) return -1;
   return launch_lambda_return_bwd(g_vs, v, d, vs, T, N, lambda_, g_r, g_v, g_d,

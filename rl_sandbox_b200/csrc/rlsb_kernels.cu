@@ -620,12 +620,12 @@ int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream) {
 }
 
 int launch_lambda_return(const float* r, const float* v, const float* d, int T, long long N,
-                         float lambda_, float* vs, float* w, float* adv, int layout_batch_major,
+                         double lambda_, float* vs, float* w, float* adv, int layout_batch_major,
                          cudaStream_t stream) {
   if (T < 2 || N <= 0) return -1;
   // (1 - lambda) is formed in double like the Python expression in ac.py:58, then rounded to fp32
-  const float c1 = static_cast<float>(1.0 - static_cast<double>(lambda_));
-  const float c2 = lambda_;
+  const float c1 = static_cast<float>(1.0 - lambda_);
+  const float c2 = static_cast<float>(lambda_);
   const int block = 256;
   if (layout_batch_major) {
     if (T > 32) return -2;
@@ -652,11 +652,11 @@ int launch_lambda_return(const float* r, const float* v, const float* d, int T, 
 }
 
 int launch_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
-                             int T, long long N, float lambda_, float* g_r, float* g_v, float* g_d,
+                             int T, long long N, double lambda_, float* g_r, float* g_v, float* g_d,
                              cudaStream_t stream) {
   if (T < 2 || N <= 0) return -1;
-  const float c1 = static_cast<float>(1.0 - static_cast<double>(lambda_));
-  const float c2 = lambda_;
+  const float c1 = static_cast<float>(1.0 - lambda_);
+  const float c2 = static_cast<float>(lambda_);
   const int block = 256;
   lambda_return_bwd_kernel<<<static_cast<unsigned>((N + block - 1) / block), block, 0, stream>>>(
       g_vs, v, d, vs, T, N, c1, c2, g_r, g_v, g_d);

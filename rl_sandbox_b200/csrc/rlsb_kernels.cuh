@@ -71,10 +71,10 @@ int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream);
 
 // K2 (reference: ac.py:52-66 + dreamer_v2.py:192-197 + ac.py:118)
 int launch_lambda_return(const float* r, const float* v, const float* d, int T, long long N,
-                         float lambda_, float* vs, float* w, float* adv, int layout_batch_major,
+                         double lambda_, float* vs, float* w, float* adv, int layout_batch_major,
                          cudaStream_t stream);
 int launch_lambda_return_bwd(const float* g_vs, const float* v, const float* d, const float* vs,
-                             int T, long long N, float lambda_, float* g_r, float* g_v, float* g_d,
+                             int T, long long N, double lambda_, float* g_r, float* g_v, float* g_d,
                              cudaStream_t stream);
 
 }  // namespace rlsb

@@ -1,0 +1,55 @@
+"""CPU tests of the boundary: the C-ABI library builds, loads, and exports every symbol that
+include/rlsb.h declares.  No compute calls (no GPU here)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from rl_sandbox_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _lib.exported_symbols()
+    assert len(names) >= 14
+    out = subprocess.check_output(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [n for n in names if n not in exported]
+    assert not missing, f"declared in include/rlsb.h but not exported: {missing}"
+    assert lib.rlsb_abi_version() == 1
+
+
+def test_no_torch_types_in_abi():
+    hdr = (ROOT / "include" / "rlsb.h").read_text()
+    assert "torch" not in hdr.lower().replace("pytorch", "") and "at::" not in hdr
+
+
+def test_sass_contains_blackwell_instructions():
+    sass = subprocess.check_output(["cuobjdump", "-sass", str(_lib.LIB_PATH)], text=True)
+    assert "UTCHMMA" in sass, "tcgen05.mma missing from SASS"
+    assert "UBLKCP" in sass, "bulk (TMA engine) copies missing from SASS"
+    assert "LDTM" in sass, "tcgen05.ld missing from SASS"
+    assert "sm_100a" in subprocess.check_output(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], text=True)
+
+
+def test_fails_loudly_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rl_sandbox_b200 import ops
+    with pytest.raises(_lib.RlsbError):
+        ops.lambda_return(torch.zeros(4, 8), torch.zeros(4, 8), torch.ones(4, 8), 0.95)
+    assert _lib.load().rlsb_check_device() != 0
+
+
+def test_argument_errors_are_negative_codes():
+    lib = _lib.load()
+    assert lib.rlsb_lambda_return_fwd(None, None, None, 16, 8, 0.95, None, None, None, 0, None) < 0
+    cfg = _lib.ImagineCfg(1024, 32, 31, 17, 400, 1, 1, 1, 1, 15)   # classes != 32 -> unsupported
+    assert lib.rlsb_imagine_packed_bytes(C.byref(cfg)) == 0
+    cfg = _lib.ImagineCfg(1024, 32, 32, 17, 400, 1, 1, 1, 1, 15)
+    assert lib.rlsb_imagine_packed_bytes(C.byref(cfg)) > 20_000_000
+    assert lib.rlsb_imagine_workspace_bytes(C.byref(cfg), 800) > 0

@@ -1,0 +1,95 @@
+"""CPU tests: the oracle (oracle/) against the golden vectors generated from the reference itself."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_port as orc
+from tests._golden import known_answers, load_case
+
+
+def test_det_logf_accuracy():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.random(200000).astype(np.float32) * 0.9999 + 1e-7,
+                        np.float32(10.0) ** rng.uniform(-19, 3, 50000).astype(np.float32)])
+    y = orc.det_logf(x)
+    ref = np.log(x.astype(np.float64))
+    ulp = np.abs(y - ref) / np.spacing(np.abs(ref).astype(np.float32))
+    assert ulp.max() < 1.5
+
+
+def test_gumbel_distribution():
+    g = torch.Generator().manual_seed(0)
+    x = orc.gumbel(torch.rand(400000, generator=g))
+    assert abs(x.mean().item() - 0.5772) < 0.01 and abs(x.var().item() - np.pi ** 2 / 6) < 0.03
+
+
+def test_sampler_matches_softmax_and_argmax_ties():
+    g = torch.Generator().manual_seed(1)
+    lg = torch.tensor([[0.0, 1.0, 2.0, -1.0]]).repeat(200000, 1)
+    idx = orc.sample_categorical(lg, torch.rand(200000, 4, generator=g))
+    f = torch.bincount(idx, minlength=4) / 200000.0
+    assert torch.allclose(f, torch.softmax(lg[0], 0), atol=5e-3)
+    # identical scores -> lowest index, like torch.argmax
+    assert orc.sample_categorical(torch.zeros(3, 5), torch.full((3, 5), 0.5)).tolist() == [0, 0, 0]
+
+
+def test_philox_known_answer():
+    # Random123 known-answer test for philox4x32-10 (kat_vectors): counter/key all ones-complement
+    import ctypes as C
+    out = (C.c_uint32 * 4)()
+    orc.clib().orc_philox_raw(C.c_uint32(0xffffffff), C.c_uint32(0xffffffff), C.c_uint32(0xffffffff),
+                              C.c_uint32(0xffffffff), C.c_uint32(0xffffffff), C.c_uint32(0xffffffff), out)
+    assert [hex(v) for v in out] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    orc.clib().orc_philox_raw(C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), out)
+    assert [hex(v) for v in out] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    u = orc.philox_uniform(42, 0, 0, 0, 1024, 64)
+    assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("case", known_answers(), ids=lambda c: c["name"])
+def test_lambda_known_answers(case):
+    """The reference's own test vectors (test/dreamer/test_critic.py:14-62), repaired."""
+    vs, rs, ds = (np.array(case[k], np.float32).reshape(-1, 1) for k in ("vs", "rs", "ds"))
+    rs11 = np.concatenate([rs, np.zeros((1, 1), np.float32)])
+    out, w, adv = orc.lambda_return_c(rs11, vs, ds, case["lam"])
+    assert out[:, 0].tolist() == case["expected"]
+    loop = orc.lambda_return_loop(torch.tensor(case["vs"]), torch.tensor(case["rs"]), torch.tensor(case["ds"]), case["lam"])
+    assert loop.tolist() == case["expected"]
+
+
+def test_lambda_c_oracle_is_bit_identical_to_reference_loop():
+    g = torch.Generator().manual_seed(3)
+    T, N = 16, 777
+    r, v = torch.randn(T, N, generator=g), torch.randn(T, N, generator=g)
+    # imagined discounts are Bernoulli modes, i.e. exactly 0 or 1 (world_model.py:136-139)
+    d = (torch.rand(T, N, generator=g) > 0.15).float()
+    vs, w, adv = orc.lambda_return_c(r.numpy(), v.numpy(), d.numpy(), 0.95)
+    assert torch.equal(torch.from_numpy(vs), orc.lambda_return_loop(v, r[:-1], d, 0.95))
+    w_ref = torch.cumprod(torch.cat([torch.ones_like(d[:1]), d[:-1]]), 0)
+    assert torch.equal(torch.from_numpy(w), w_ref)
+    assert torch.equal(torch.from_numpy(adv), torch.from_numpy(vs)[1:] - v[:-2])
+    # general (non-binary) discounts: torch's CPU cumprod accumulates in double, the oracle in fp32
+    d2 = d * 0.999
+    vs2, w2, _ = orc.lambda_return_c(r.numpy(), v.numpy(), d2.numpy(), 0.95)
+    assert torch.equal(torch.from_numpy(vs2), orc.lambda_return_loop(v, r[:-1], d2, 0.95))
+    torch.testing.assert_close(torch.from_numpy(w2), torch.cumprod(torch.cat([torch.ones_like(d2[:1]), d2[:-1]]), 0),
+                               rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", ["c1", "c2", "c2_long"])
+def test_oracle_port_matches_reference_rollout(name):
+    """oracle_port.imagine / ac_losses vs the tensors the reference's modules produced."""
+    c = load_case(name)
+    m, gold = c["meta"], c["gold"]
+    out = orc.imagine(c["wm"], c["actor"], c["critic"], c["h0"], c["z0"], H=m["H"], A=m["A"], discrete=m["discrete"],
+                      predict_discount=m["predict_discount"], latent_uniforms=c["lat"], action_noise=c["act"])
+    assert torch.equal(out["stoch_idx"], gold["stoch_idx"].long()), "categorical indices must be bit-exact"
+    for k in ("determ", "logits", "actions", "rewards", "values"):
+        torch.testing.assert_close(out[k], gold[k], rtol=1e-4, atol=2e-5, msg=lambda s: f"{k}: {s}")
+    assert torch.equal(torch.nan_to_num(out["discounts"], nan=-1), torch.nan_to_num(gold["discounts"], nan=-1))
+    losses = orc.ac_losses(out, c["actor"], c["critic"], lam=m["lam"], discrete=m["discrete"], rho=m["rho"],
+                           eta=m["entropy_scale"])
+    torch.testing.assert_close(losses["vs"], gold["vs"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(losses["w"], gold["w"], rtol=0, atol=0)
+    for k in ("loss_critic", "loss_actor", "loss_actor_reinforce", "loss_actor_dynamics_backprop", "loss_actor_entropy"):
+        torch.testing.assert_close(losses[k].float(), gold[k], rtol=1e-4, atol=1e-6, msg=lambda s: f"{k}: {s}")
