@@ -1,3 +1,3 @@
 make -C oracle >/dev/null 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$?
+timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo pytest_exit=$?
 tail -30 gpurun_out/pytest_gpu.log
