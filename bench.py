@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — imagined RSSM steps / second of the DreamerV2 hot path on B200.
+
+A "step" is one pass of the hot path (agents/dreamer_v2.py:179-211 of the reference) over one batch
+of synthetic start states: imagination rollout (K1) -> lambda-return / weights / advantage (K2) ->
+critic + actor losses -> backward -> [gradient all-reduce] -> clip -> AdamW x2 -> target update.
+
+  python bench.py --gpus N --steps K --warmup W            # the B200 arm (this repo)
+  python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+Workloads (config.workload):
+  sweep    configs[3] of BASELINE.json: config-1 dims (D=1024, 32x32 latents, A=17 discrete,
+           layer_norm, discount head), `--rows` start states PER GPU (weak scaling; default 32768,
+           i.e. 262144 = the top of the 16k-256k sweep at 8 GPUs), H=15.  This is the default: it is
+           the configuration the metric ("at 1/2/4/8 B200") is quoted on.
+  config1  the reference shape N = 16x50 = 800 (launch/latency bound; SURVEY hard part 8)
+  dino     config-2 dims (D=200, continuous A=12) at N = 800 — rollout only under no_grad
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from functools import partial
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_STEP = {"c1": 26.72e6, "c2": 5.28e6}   # reference-equivalent MFLOP / start state / step
+GRU_FLOP = {"c1": 2 * 3072 * 2048, "c2": 2 * 600 * 400}
+
+DIMS = {
+    "sweep": dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, eta=3e-3, lr=1e-4, fl="c1"),
+    "config1": dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, eta=3e-3, lr=1e-4, fl="c1"),
+    "dino": dict(D=200, A=12, discrete=False, layer_norm=False, predict_discount=False, eta=1e-5, lr=8e-5, fl="c2"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sweep", choices=list(DIMS))
+    ap.add_argument("--rows", type=int, default=None, help="start states per GPU")
+    ap.add_argument("--horizon", type=int, default=15)
+    ap.add_argument("--cpu-rows", type=int, default=None, help="start states of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--metrics-samples", type=int, default=128)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "samples": len(self.samples), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_hot_path(dims, H, rows, steps, warmup, metrics_samples):
+    """The reference's CPU path (oracle port; the reference itself is Python and cannot travel to the
+    GPU box).  Returns (steps/s, seconds per step, threads)."""
+    from oracle import oracle_port as orc
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    hp = orc.HotPathCPU(D=dims["D"], A=dims["A"], discrete=dims["discrete"], layer_norm=dims["layer_norm"],
+                        predict_discount=dims["predict_discount"], H=H, eta=dims["eta"], lr=dims["lr"],
+                        metrics_samples=metrics_samples)
+    h0, z0 = orc.make_start(1, rows, dims["D"])
+    gen = torch.Generator().manual_seed(2)
+    for _ in range(warmup):
+        hp.step(h0, z0, gen)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        hp.step(h0, z0, gen)
+        ts.append(time.perf_counter() - t0)
+    sec = statistics.median(ts)
+    return rows * H / sec, sec, threads
+
+
+def reference_arm(args, dims):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.cpu_rows or 256
+    val, sec, threads = cpu_hot_path(dims, args.horizon, rows, args.steps, max(1, min(args.warmup, 2)),
+                                     args.metrics_samples)
+    cpu_model = "unknown"
+    try:
+        cpu_model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    line = {
+        "impl": "reference", "metric": "imagined_rssm_steps_per_sec", "value": val, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: bounded sample of {rows} start states x H={args.horizon} "
+                               f"(dims D={dims['D']} A={dims['A']} discrete={dims['discrete']})",
+                   "impl_note": "reference's PyTorch-CPU hot path restated in oracle/oracle_port.py "
+                                "(HotPathCPU: imagine + lambda-return + AC losses + backward + AdamW); "
+                                "the reference is pure Python and is not present on the GPU box"},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{rows} start states x H={args.horizon}, median of {args.steps} steps", "cpu": cpu_model},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def build_agent(dims, H, device, metrics_samples):
+    from rl_sandbox_b200.agents.dreamer_v2 import DreamerV2
+    from rl_sandbox_b200.agents.dreamer.ac import ImaginativeActor, ImaginativeCritic
+    from rl_sandbox_b200.agents.dreamer.world_model import WorldModel
+    from rl_sandbox_b200.utils.optimizer import Optimizer
+    ln = dims["layer_norm"]
+    torch.manual_seed(0)
+    opt = partial(Optimizer, lr=dims["lr"], eps=1e-5, weight_decay=1e-6, clip=100)
+    agent = DreamerV2(
+        obs_space_num=[64, 64, 3], clip_rewards="tanh", actions_num=dims["A"],
+        world_model=partial(WorldModel, batch_cluster_size=50, latent_dim=32, latent_classes=32, rssm_dim=dims["D"],
+                            discount_loss_scale=1.0, kl_loss_scale=2, kl_loss_balancing=0.8, kl_free_nats=1.0,
+                            discrete_rssm=False, predict_discount=dims["predict_discount"], layer_norm=ln,
+                            encode_vit=False, decode_vit=False, vit_l2_ratio=0.5, vit_img_size=224),
+        actor=partial(ImaginativeActor, layer_norm=ln, reinforce_fraction=None, entropy_scale=dims["eta"]),
+        critic=partial(ImaginativeCritic, discount_factor=0.999, update_interval=100, soft_update_fraction=1,
+                       value_target_lambda=0.95, layer_norm=ln),
+        action_type="discrete" if dims["discrete"] else "continuous", imagination_horizon=H,
+        wm_optim=opt, actor_optim=opt, critic_optim=opt, layer_norm=ln, batch_cluster_size=50,
+        f16_precision=False, device_type=device)
+    agent.metrics_samples = metrics_samples
+    return agent
+
+
+def main():
+    args = parse()
+    dims = DIMS[args.workload]
+    if args.impl == "reference":
+        return reference_arm(args, dims)
+
+    import torch.distributed as dist
+    from rl_sandbox_b200 import _lib, ops
+    from rl_sandbox_b200.agents.dreamer.rssm import State
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    torch.backends.cuda.matmul.allow_tf32 = True   # as the reference's train.py:40 (loss MLPs run in torch)
+    lib = _lib.load()
+
+    H = args.horizon
+    N = args.rows or (32768 if args.workload == "sweep" else 800)
+    agent = build_agent(dims, H, device, args.metrics_samples)
+    D = dims["D"]
+    g = torch.Generator(device=device).manual_seed(1 + rank)
+    h0 = 0.5 * torch.randn(N, D, device=device, generator=g)
+    idx0 = torch.randint(0, 32, (N, 32), device=device, generator=g)
+    z0 = torch.nn.functional.one_hot(idx0, 32).float().view(N, 1024)
+    logits0 = torch.zeros(1, N, 32, 32, device=device)
+
+    def make_state(h, z):
+        return State(h.unsqueeze(0), logits0, z.unsqueeze(0))
+
+    is_train = dims["discrete"]   # continuous actors need K1 backward (not built): time the rollout + K2 only
+
+    def step(state, it):
+        noise = {"seed": 1000 + it, "row_offset": rank * N}
+        if is_train:
+            losses, metrics = agent.behaviour_update(state, noise=noise)
+            return losses["loss_actor"] + losses["loss_critic"]
+        with torch.no_grad():
+            states, actions, rewards, discounts = agent.imagine_trajectory(state, noise=noise)
+            vs, w, adv = ops.lambda_return(rewards, agent.last_rollout["values"].unsqueeze(-1), discounts, 0.95)
+        return vs.mean()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    state = make_state(h0, z0)
+    for i in range(args.warmup):
+        step(state, i)
+    barrier()
+    lib.rlsb_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            out = step(state, args.warmup + i)
+        ev1.record()
+        barrier()
+    launches = lib.rlsb_launch_count(0)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    value = world * N * H / (ms_per_step * 1e-3)
+
+    # ---- imagination-only timing (K1 alone) -----------------------------------------------------
+    with torch.no_grad():
+        agent.imagine_trajectory(state, noise={"seed": 1})
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(max(2, args.steps)):
+            agent.imagine_trajectory(state, noise={"seed": 2 + i})
+        ev1.record()
+        torch.cuda.synchronize()
+    k1_ms = ev0.elapsed_time(ev1) / max(2, args.steps)
+    pk = peaks()
+    k1_tflops = N * H * FLOP_PER_STEP[dims["fl"]] / (k1_ms * 1e-3) / 1e12
+
+    # ---- end to end through the public API with HOST buffers ------------------------------------
+    h_host = h0.cpu().pin_memory()
+    i_host = idx0.to(torch.uint8).cpu().pin_memory()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        h_dev = h_host.to(device, non_blocking=True)
+        i_dev = i_host.to(device, non_blocking=True)
+        z_dev = torch.nn.functional.one_hot(i_dev.long(), 32).float().view(N, 1024)
+        res = step(make_state(h_dev, z_dev), 5000 + i)
+        res_host = res.detach().cpu()   # device->host read of the step's result (blocks, like dreamer_v2.py:216)
+    ev1.record()
+    barrier()
+    e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * H / (e2e_ms.item() / args.steps * 1e-3)
+    h2d = h_host.numel() * 4 + i_host.numel()
+    d2h = res_host.numel() * 4
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel: the GRU contraction (tcgen05 GEMM, EPI_STATS) ------
+        fl = dims["fl"]
+        Kg, Ng = (2048, 3072) if fl == "c1" else (512, 600)   # packed K of cat[x, h]
+        rb, nb = ops.plan_blocks(Ng)
+        xa = torch.randn(N, Kg, device=device)
+        wa = torch.randn(Ng, Kg, device=device) / Kg ** 0.5
+        xp = ops.pack_rows(xa)
+        wp = ops.pack_rows(wa, row_block=rb, rows_pad=rb * nb, k_pad=Kg)
+        del xa
+        m_pad = ops.round_up(N, 128)
+        bufs = dict(out=torch.empty((m_pad, Ng), device=device), stats=torch.empty((nb, m_pad, 2), device=device),
+                    bias_p=torch.zeros(rb * nb, device=device))
+        for _ in range(3):
+            ops.gemm_bias(xp, Kg, wp, rb, nb, None, N, Ng, want_stats=True, **bufs)
+        torch.cuda.synchronize()
+        reps = 20
+        ev0.record()
+        for _ in range(reps):
+            ops.gemm_bias(xp, Kg, wp, rb, nb, None, N, Ng, want_stats=True, **bufs)
+        ev1.record()
+        torch.cuda.synchronize()
+        gemm_ms = ev0.elapsed_time(ev1) / reps
+        # algorithmic FLOPs of the GRU contraction as the reference executes it (2*3D*2D per row)
+        achieved = N * GRU_FLOP[fl] / (gemm_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gemm_kernel<EPI_STATS> (GRU contraction cat[x,h] -> 3D)",
+                    "achieved": achieved, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sus"],
+                    "peak_source": pk["source"] + ", sustained bf16", "frac_of_burst": achieved / pk["tf_burst"],
+                    "ms_per_launch": gemm_ms, "traffic": None,
+                    "whole_rollout": {"tflops": k1_tflops, "frac": k1_tflops / pk["tf_sus"], "ms": k1_ms,
+                                      "note": "reference-equivalent FLOPs of all layers / K1 time"}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rows = args.cpu_rows or 256
+            v, sec, threads = cpu_hot_path(dims, H, rows, 3, 1, args.metrics_samples)
+            cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+                   "sample": f"{rows} start states x H={H} (same dims, same hot path), median of 3 steps, {sec:.2f} s/step"}
+        line = {
+            "metric": "imagined_rssm_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {N} start states/GPU x H={H}, D={D}, 32x32 latents, A={dims['A']} "
+                                   f"{'discrete' if dims['discrete'] else 'continuous'}, layer_norm={dims['layer_norm']}",
+                       "step": "imagine(K1) + lambda-return(K2) + critic/actor loss + backward + allreduce + AdamW x2"
+                               if is_train else "imagine(K1) + lambda-return(K2) [no_grad]",
+                       "l2": "per-step working set (>= 2 GB of rollout outputs) exceeds the 126 MB L2; no explicit flush",
+                       "metrics_samples": args.metrics_samples, "noise": "Philox4x32-10 on device"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms.item() / args.steps},
+            "gpu_launches": int(launches),
+            "imagination_only": {"steps_per_sec": world * N * H / (k1_ms * 1e-3), "ms": k1_ms},
+            "roofline": roofline,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

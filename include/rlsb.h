@@ -30,6 +30,8 @@ int rlsb_abi_version(void);
 /* 0 when the current device is sm_100 (B200); negative otherwise (the library has no fallback) */
 int rlsb_check_device(void);
 const char* rlsb_error_string(int code);
+/* number of CUDA kernels this library has launched since load (or since the last reset != 0) */
+long long rlsb_launch_count(int reset);
 
 /* ---- K2: lambda-return + shifted-cumprod weights + advantage --------------------------------
  * replaces ImaginativeCritic._lambda_return (agents/dreamer/ac.py:52-62), the discount

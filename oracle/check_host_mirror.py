@@ -1,0 +1,97 @@
+"""check_host_mirror.py — TEST INFRASTRUCTURE (build container only: needs /root/reference).
+
+Builds the reference agent and the rl_sandbox_b200 agent with the same constructor kwargs, copies
+the reference's parameters into ours through state_dict (=> key / shape compatibility) and compares
+  * WorldModel.calculate_loss (observe loop + losses), same torch seed  -> identical losses
+  * ImaginativeCritic.calculate_loss / ImaginativeActor.calculate_loss on a reference trajectory
+Prints one line per check and exits non-zero on failure.  Run:  python -m oracle.check_host_mirror
+"""
+import sys
+from functools import partial
+
+import torch
+
+from . import ref_harness as rh
+
+
+def main():
+    ok = True
+    for cfg in (dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True),
+                dict(D=200, A=12, discrete=False, layer_norm=False, predict_discount=False)):
+        torch.manual_seed(0)
+        ref = rh.build_agent(**cfg, H=3, batch_cluster_size=4)
+        from rl_sandbox_b200.agents.dreamer_v2 import DreamerV2
+        from rl_sandbox_b200.agents.dreamer.world_model import WorldModel
+        from rl_sandbox_b200.agents.dreamer.ac import ImaginativeActor, ImaginativeCritic
+        from rl_sandbox_b200.utils.optimizer import Optimizer
+        ln = cfg["layer_norm"]
+        mine = DreamerV2(
+            obs_space_num=[64, 64, 3], clip_rewards="identity", actions_num=cfg["A"],
+            world_model=partial(WorldModel, batch_cluster_size=4, latent_dim=32, latent_classes=32, rssm_dim=cfg["D"],
+                                discount_loss_scale=1.0, kl_loss_scale=2, kl_loss_balancing=0.8, kl_free_nats=1.0,
+                                discrete_rssm=False, predict_discount=cfg["predict_discount"], layer_norm=ln,
+                                encode_vit=False, decode_vit=False, vit_l2_ratio=0.5, vit_img_size=224),
+            actor=partial(ImaginativeActor, layer_norm=ln, reinforce_fraction=None, entropy_scale=1e-5),
+            critic=partial(ImaginativeCritic, discount_factor=0.99, update_interval=100, soft_update_fraction=1,
+                           value_target_lambda=0.95, layer_norm=ln),
+            action_type="discrete" if cfg["discrete"] else "continuous", imagination_horizon=3,
+            wm_optim=partial(Optimizer, lr=1e-4, eps=1e-5, weight_decay=1e-6, clip=100),
+            actor_optim=partial(Optimizer, lr=1e-4, eps=1e-5, weight_decay=1e-6, clip=100),
+            critic_optim=partial(Optimizer, lr=1e-4, eps=1e-5, weight_decay=1e-6, clip=100),
+            layer_norm=ln, batch_cluster_size=4, f16_precision=False, device_type="cpu")
+        strip = lambda sd: {k.removeprefix("_orig_mod."): v for k, v in sd.items()}
+        for name, a, b in (("world_model", ref.world_model, mine.world_model), ("actor", ref.actor, mine.actor),
+                           ("critic", ref.critic, mine.critic)):
+            sd = strip(a.state_dict())
+            mk, rk = set(b.state_dict()), set(sd)
+            same = mk == rk and all(b.state_dict()[k].shape == sd[k].shape for k in rk)
+            print(f"[{cfg['D']}] state_dict keys/shapes {name}: {'ok' if same else 'MISMATCH ' + str(sorted(mk ^ rk)[:6])} ({len(rk)} entries)")
+            ok &= same
+            b.load_state_dict(sd)
+        B, T, A = 2, 4, cfg["A"]
+        g = torch.Generator().manual_seed(1)
+        obs = torch.rand(B * T, 3, 64, 64, generator=g) - 0.5
+        a = (torch.nn.functional.one_hot(torch.randint(0, A, (B * T,), generator=g), A).float() if cfg["discrete"]
+             else torch.randn(B * T, A, generator=g))
+        r = torch.randn(B * T, generator=g)
+        disc = 0.99 * torch.ones(B * T)
+        first = torch.zeros(B * T)
+        first[0] = 1
+        torch.manual_seed(5)
+        l_ref, post_ref, m_ref = ref.world_model.calculate_loss(obs, a, r, disc, first, {})
+        torch.manual_seed(5)
+        l_mine, post_mine, m_mine = mine.world_model.calculate_loss(obs, a, r, disc, first, {})
+        for k in l_ref:
+            same = torch.allclose(l_ref[k].float().reshape(-1), l_mine[k].float().reshape(-1), rtol=1e-5, atol=1e-6)
+            print(f"[{cfg['D']}] calculate_loss {k}: ref {float(l_ref[k]):.6f} ours {float(l_mine[k]):.6f} {'ok' if same else 'MISMATCH'}")
+            ok &= same
+        same = torch.allclose(post_ref.determ, post_mine.determ, atol=1e-6) and torch.equal(post_ref.stoch, post_mine.stoch)
+        print(f"[{cfg['D']}] posterior states: {'ok' if same else 'MISMATCH'}")
+        ok &= same
+        for k in m_ref:
+            ok &= torch.allclose(m_ref[k].float(), m_mine[k].float(), rtol=1e-5, atol=1e-6)
+        # AC losses on a (CPU) reference trajectory: our torch loss code vs the reference's
+        H, N = 3, B * T
+        zs = torch.randn(H + 1, N, cfg["D"] + 1024, generator=g)
+        vs = torch.randn(H, N, 1, generator=g)
+        w = torch.rand(H + 1, N, 1, generator=g)
+        acts = (torch.nn.functional.one_hot(torch.randint(0, A, (H - 1, N), generator=g), A).float() if cfg["discrete"]
+                else torch.randn(H - 1, N, A, generator=g))
+        base = torch.randn(H - 1, N, 1, generator=g)
+        lc_r, _ = ref.critic.calculate_loss(zs[:-1], vs, w[:-1])
+        lc_m, _ = mine.critic.calculate_loss(zs[:-1], vs, w[:-1])
+        torch.manual_seed(9)
+        la_r, ma_r = ref.actor.calculate_loss(zs[:-2], vs[1:], base, w[:-2], acts)
+        torch.manual_seed(9)
+        la_m, ma_m = mine.actor.calculate_loss(zs[:-2], vs[1:], base, w[:-2], acts)
+        for k, x, y in [("loss_critic", lc_r["loss_critic"], lc_m["loss_critic"])] + [(k, la_r[k], la_m[k]) for k in la_r] + \
+                       [(k, ma_r[k], ma_m[k]) for k in ma_r]:
+            same = torch.allclose(torch.as_tensor(x).float(), torch.as_tensor(y).float(), rtol=1e-5, atol=1e-6)
+            print(f"[{cfg['D']}] {k}: ref {float(x):.6f} ours {float(y):.6f} {'ok' if same else 'MISMATCH'}")
+            ok &= same
+    print("HOST MIRROR", "OK" if ok else "FAILED")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

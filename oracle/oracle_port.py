@@ -237,19 +237,20 @@ def ac_losses(traj, actor_sd, critic_sd, *, lam, discrete, rho, eta, bf16=False)
     r, v, d = traj["rewards"], traj["values"], traj["discounts"]  # (H+1, N)
     vs = lambda_return_loop(v, r[:-1], d, lam)                    # (H, N)
     w = torch.cumprod(torch.cat([torch.ones_like(d[:1]), d[:-1]], 0), 0)
-    pred = mlp(zs[:-1], critic_sd, "critic.", bf16).squeeze(-1)
-    loss_critic = -(normal_logprob(vs, pred) * w[:-1]).mean()
-    raw = mlp(zs[:-2], actor_sd, "actor.", bf16)
-    adv = vs[1:] - v[:-2]
+    w = w.detach()
+    pred = mlp(zs[:-1].detach(), critic_sd, "critic.", bf16).squeeze(-1)          # ac.py:70
+    loss_critic = -(normal_logprob(vs.detach(), pred) * w[:-1]).mean()            # ac.py:73-74
+    raw = mlp(zs[:-2].detach(), actor_sd, "actor.", bf16)                         # ac.py:117
+    adv = (vs[1:] - v[:-2]).detach()                                              # ac.py:118
     acts = traj["actions"][1:-1]
     if discrete:
         logp_all = torch.log_softmax(raw, -1)
-        logp = (logp_all * acts).sum(-1)
+        logp = (logp_all * acts.detach()).sum(-1)
         ent = -(logp_all.exp() * logp_all).sum(-1)
     else:
         mu, s_ = raw.chunk(2, -1)
         loc, scale = torch.tanh(mu), 2 * torch.sigmoid(s_ / 2) + 0.1
-        logp = normal_logprob(acts, loc, scale).sum(-1)
+        logp = normal_logprob(acts.detach(), loc, scale).sum(-1)
         ent = (0.5 + LOG_SQRT_2PI + torch.log(scale)).sum(-1)
     l_reinforce = -(rho * logp * w[:-2] * adv).mean()
     l_dyn = -((1 - rho) * vs[1:] * w[:-2]).mean() if rho != 1.0 else torch.tensor(0.0)
@@ -310,3 +311,82 @@ def make_start(seed, N, D, groups=32, classes=32):
     idx = torch.randint(0, classes, (N, groups), generator=gen)
     z0 = torch.nn.functional.one_hot(idx, classes).float().view(N, groups * classes)
     return h0, z0
+
+
+# ------------------------------------------------------------------------------------------------
+# whole hot path on the CPU (bench.py cpu_baseline / --impl reference): imagine -> lambda-return ->
+# critic / actor losses -> backward -> clip -> AdamW x2 -> target update
+# (agents/dreamer_v2.py:179-211, utils/optimizer.py:43-71)
+# ------------------------------------------------------------------------------------------------
+class HotPathCPU:
+    def __init__(self, *, D, A, discrete, layer_norm, predict_discount, H=15, lam=0.95, eta=3e-3, lr=1e-4,
+                 seed=0, metrics_samples=128):
+        self.cfg = dict(D=D, A=A, discrete=discrete, layer_norm=layer_norm, predict_discount=predict_discount)
+        self.H, self.lam, self.eta, self.A, self.discrete = H, lam, eta, A, discrete
+        self.rho = 1.0 if discrete else 0.0
+        self.metrics_samples = metrics_samples
+        self.wm, self.actor, self.critic = make_params(seed, **self.cfg)
+        self.actor = {k: v.requires_grad_() for k, v in self.actor.items()}
+        train_c = {k: v.requires_grad_() for k, v in self.critic.items() if k.startswith("critic.")}
+        self.critic.update(train_c)
+        mk = lambda ps: torch.optim.AdamW(ps, lr=lr, eps=1e-5, weight_decay=1e-6)
+        self.opt_a, self.opt_c = mk(list(self.actor.values())), mk(list(train_c.values()))
+        self._updates = 0
+
+    def step(self, h0, z0, gen):
+        H, N, A = self.H, h0.shape[0], self.A
+        lat = torch.rand(H, N, 1024, generator=gen)
+        act = torch.rand(H, N, A, generator=gen) if self.discrete else torch.randn(H, N, A, generator=gen)
+        if self.discrete:      # rho == 1: nothing differentiates through the rollout (SURVEY hard part 3)
+            with torch.no_grad():
+                traj = imagine(self.wm, self.actor, self.critic, h0, z0, H=H, A=A, discrete=True,
+                               predict_discount=self.cfg["predict_discount"], latent_uniforms=lat, action_noise=act)
+        else:
+            traj = self._imagine_st(h0, z0, lat, act)
+        losses = ac_losses(traj, self.actor, self.critic, lam=self.lam, discrete=self.discrete, rho=self.rho,
+                           eta=self.eta)
+        with torch.no_grad():  # the 128-draw action statistics of ac.py:137-143
+            raw = mlp(torch.cat([traj["determ"], traj["stoch"]], -1)[:-2].detach(), self.actor, "actor.")
+            if self.discrete:
+                p = torch.softmax(raw, -1).reshape(-1, A)
+                s = torch.nn.functional.one_hot(torch.multinomial(p, self.metrics_samples, True, generator=gen), A).float()
+                stats = (s.mean(), s.var())
+            else:
+                mu, sd_ = raw.chunk(2, -1)
+                s = torch.tanh(mu) + (2 * torch.sigmoid(sd_ / 2) + 0.1) * torch.randn((self.metrics_samples,) + mu.shape, generator=gen)
+                stats = (s.mean(), s.var())
+        for opt, loss in ((self.opt_a, losses["loss_actor"]), (self.opt_c, losses["loss_critic"])):
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_([p for g in opt.param_groups for p in g["params"]], 100)
+            opt.step()
+        if self._updates % 100 == 0:
+            with torch.no_grad():
+                for k in list(self.critic):
+                    if k.startswith("target_critic."):
+                        self.critic[k] = self.critic["critic." + k[len("target_critic."):]].detach().clone()
+        self._updates += 1
+        return {k: float(v) for k, v in losses.items() if v.ndim == 0}
+
+    def _imagine_st(self, h0, z0, lat, act):
+        """continuous actor: rollout with straight-through latents so that the dynamics loss reaches the actor"""
+        H, N, A = self.H, h0.shape[0], self.A
+        h, z = h0, z0
+        out = {k: [] for k in ("determ", "stoch", "actions", "rewards", "discounts", "values")}
+        out["determ"].append(h); out["stoch"].append(z); out["actions"].append(torch.zeros(N, A))
+        for t in range(H + 1):
+            s = torch.cat([h, z], -1)
+            out["rewards"].append(mlp(s, self.wm, "reward_predictor.").squeeze(-1))
+            out["discounts"].append(torch.ones(N))
+            out["values"].append(mlp(s, self.critic, "target_critic.").squeeze(-1))
+            if t == H:
+                break
+            mu, sd_ = mlp(s.detach(), self.actor, "actor.").chunk(2, -1)
+            a = torch.tanh(mu) + (2 * torch.sigmoid(sd_ / 2) + 0.1) * act[t]
+            h, logits = rssm_predict_next(h, z, a, self.wm)
+            lg = logits.view(N, 32, 32)
+            idx = sample_categorical(lg.detach(), lat[t].view(N, 32, 32))
+            probs = torch.softmax(lg, -1)
+            z = (torch.nn.functional.one_hot(idx, 32).float() + probs - probs.detach()).view(N, 1024)
+            out["determ"].append(h); out["stoch"].append(z); out["actions"].append(a)
+        return {k: torch.stack(v) for k, v in out.items()}

@@ -1,0 +1,272 @@
+"""DreamerV2 agent behind the reference's API (reference: rl_sandbox/agents/dreamer_v2.py:19-245).
+
+Same constructor kwargs (the Hydra `_target_`/`_partial_` contract of config/agent/dreamer_v2*.yaml),
+same methods and the same keys in the dict ``train`` returns.  What differs is where the second half
+of ``train`` (dreamer_v2.py:179-211) executes:
+
+  imagine_trajectory   -> ONE C-ABI call, rlsb_imagine_fwd (K1: tcgen05 GEMM chain + sampling)
+  lambda_return,
+  cumprod weights,
+  advantage            -> ONE kernel, rlsb_lambda_return_fwd (K2)
+  critic / actor loss  -> torch autograd on the K1 outputs ("next")
+  optimizer steps      -> AdamW with a flat-bucket gradient all-reduce when torch.distributed is up
+
+Gradient flow: with a discrete actor rho == 1 and nothing differentiates through the rollout
+(hard part 3), so K1 runs under no_grad exactly like the reference's values.  With a
+continuous actor (rho == 0) the dynamics-backprop loss needs d(rollout)/d(actor); K1 has no backward
+yet, so that configuration differentiates through a torch replay of the rollout (``_imagine_autograd``,
+CUDA tensors, same modules) — recorded in DESIGN.md as the open item of this round.
+"""
+import typing as t
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from rl_sandbox_b200.agents.rl_agent import RlAgent
+from rl_sandbox_b200.agents.dreamer.ac import ImaginativeActor, ImaginativeCritic
+from rl_sandbox_b200.agents.dreamer.rssm import State
+from rl_sandbox_b200.utils.replay_buffer import Action, Observation, Rollout, RolloutChunks, unpack
+
+
+def _strip_compile_prefix(sd: dict) -> dict:
+    """Reference checkpoints carry `_orig_mod.` on world-model / critic keys (torch.compile wrapper)."""
+    return {k.removeprefix('_orig_mod.'): v for k, v in sd.items()}
+
+
+class DreamerV2(RlAgent):
+
+    def __init__(self, obs_space_num: list[int], clip_rewards: str, actions_num: int, world_model: t.Any,
+                 actor: t.Any, critic: t.Any, action_type: str, imagination_horizon: int, wm_optim: t.Any,
+                 actor_optim: t.Any, critic_optim: t.Any, layer_norm: bool, batch_cluster_size: int,
+                 f16_precision: bool, device_type: str = 'cpu', logger=None):
+        self.logger = logger
+        self.device = device_type
+        self.imagination_horizon = imagination_horizon
+        self.actions_num = actions_num
+        self.is_discrete = (action_type != 'continuous')
+        if clip_rewards == 'identity':
+            self.reward_clipper = nn.Identity()
+        elif clip_rewards == 'tanh':
+            self.reward_clipper = nn.Tanh()
+        else:
+            raise RuntimeError('Invalid reward clipping')
+        self.is_f16 = f16_precision
+
+        self.world_model = world_model(actions_num=actions_num).to(device_type)
+        self.actor: ImaginativeActor = actor(latent_dim=self.world_model.state_size, actions_num=actions_num,
+                                             is_discrete=self.is_discrete).to(device_type)
+        self.critic: ImaginativeCritic = critic(latent_dim=self.world_model.state_size).to(device_type)
+
+        self.world_model_optimizer = wm_optim(model=self.world_model, scaler=self.is_f16)
+        self.actor_optimizer = actor_optim(model=self.actor)
+        self.critic_optimizer = critic_optim(model=self.critic)
+
+        self._engine = None          # lazily built ImaginationEngine (needs a B200)
+        self._weights_version = 0    # bumped whenever parameters change
+        self._packed_version = -1
+        self._noise_seed = 0x5EED    # Philox key; the step counter below is mixed in per rollout
+        self._rollouts = 0
+        self.metrics_samples = 128   # draws per element for the actor statistics (ac.py:137)
+        self.last_rollout: t.Optional[dict] = None
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------
+    # K1
+    # ------------------------------------------------------------------------------------------
+    def _flat_wm(self) -> bool:
+        return hasattr(self.world_model, 'recurrent_model') and not getattr(self.world_model, 'slots_num', 0)
+
+    def _get_engine(self):
+        from rl_sandbox_b200 import ops
+        if self._engine is None:
+            wm = self.world_model
+            cfg = ops.ImagineConfig(D=wm.rssm_dim, A=self.actions_num, discrete=self.is_discrete,
+                                    layer_norm=bool(wm.layer_norm), predict_discount=bool(wm.predict_discount),
+                                    H=self.imagination_horizon, groups=wm.latent_dim, classes=wm.latent_classes,
+                                    with_critic=True)
+            self._engine = ops.ImaginationEngine(cfg, device=self.device)
+        if self._packed_version != self._weights_version:
+            self._engine.pack(self.world_model.state_dict(), self.actor.state_dict(), self.critic.state_dict())
+            self._packed_version = self._weights_version
+        return self._engine
+
+    def mark_weights_changed(self):
+        self._weights_version += 1
+
+    def imagine_trajectory(self, init_state: State, precomp_actions: t.Optional[list[Action]] = None,
+                           horizon: t.Optional[int] = None, noise: t.Optional[dict] = None
+                           ) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """H-step closed-loop rollout from (1, N, .) start states (dreamer_v2.py:68-96).
+
+        ``noise`` (extension, optional): {'latent_uniforms': (H,N,1024), 'action_noise': (H,N,A)} to
+        inject explicit noise, or {'seed': int, 'row_offset': int} for the Philox stream."""
+        if horizon is None:
+            horizon = self.imagination_horizon
+        needs_grad = torch.is_grad_enabled() and self.actor.rho != 1.0 and precomp_actions is None
+        if needs_grad:
+            return self._imagine_autograd(init_state, horizon)
+        if not init_state.determ.is_cuda:
+            raise RuntimeError("DreamerV2.imagine_trajectory runs on the B200 kernels: tensors must be on CUDA "
+                               "(rl_sandbox_b200 has no CPU fallback)")
+        eng = self._get_engine()
+        N = init_state.determ.shape[1]
+        S = self.world_model.latent_dim * self.world_model.latent_classes
+        h0 = init_state.determ[0].detach().float()
+        z0 = init_state.stoch[0].detach().float()
+        logits0 = init_state.stoch_logits[0].detach().float().reshape(N, S)
+        noise = dict(noise or {})
+        if 'seed' not in noise and 'latent_uniforms' not in noise:
+            noise['seed'] = (self._noise_seed << 20) + self._rollouts
+        self._rollouts += 1
+        pre = None
+        if precomp_actions is not None:
+            pre = torch.stack([torch.as_tensor(a) for a in precomp_actions[:horizon]]).to(h0.device).float()
+            pre = pre.reshape(horizon, -1, self.actions_num).expand(horizon, N, self.actions_num).contiguous()
+        out = eng.rollout(h0, z0, logits0, latent_uniforms=noise.get('latent_uniforms'),
+                          action_noise=noise.get('action_noise'), seed=noise.get('seed', 0),
+                          row_offset=noise.get('row_offset', 0), precomp_actions=pre, horizon=horizon)
+        self.last_rollout = out
+        wm = self.world_model
+        states = State(out['determ'], out['logits'].view(horizon + 1, N, wm.latent_dim, wm.latent_classes),
+                       out['stoch'])
+        return states, out['actions'], out['rewards'].unsqueeze(-1), out['discounts'].unsqueeze(-1)
+
+    def _imagine_autograd(self, init_state: State, horizon: int):
+        """Differentiable replay of the rollout with torch ops (continuous actor, rho != 1 only)."""
+        self.last_rollout = None
+        prev = init_state
+        zero_a = torch.zeros(prev.determ.shape[:2] + (self.actions_num,), device=prev.determ.device)
+        states, actions = [init_state], [zero_a]
+        rewards = [self.world_model.reward_predictor(init_state.combined).mode]
+        ts = [torch.ones(zero_a.shape[:-1] + (1,), device=zero_a.device)]
+        for _ in range(horizon):
+            a = self.actor(prev.combined.detach()).rsample()
+            prior, reward, discount = self.world_model.predict_next(prev, a)
+            prev = prior
+            states.append(prior); rewards.append(reward); ts.append(discount); actions.append(a)
+        return states[0].stack(states), torch.cat(actions), torch.cat(rewards), torch.cat(ts)
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self):
+        self._state = self.world_model.get_initial_state()
+        self._last_action = torch.zeros((1, 1, self.actions_num), device=self.device)
+        self._action_probs = torch.zeros((self.actions_num), device=self.device)
+
+    def preprocess(self, rollout: Rollout):
+        obs = self.preprocess_obs(rollout.obs)
+        additional = self.world_model.precalc_data(obs.to(self.device))
+        return Rollout(obs=obs, actions=rollout.actions, rewards=self.reward_clipper(rollout.rewards),
+                       is_finished=rollout.is_finished, is_first=rollout.is_first,
+                       additional_data=rollout.additional_data | additional)
+
+    def preprocess_obs(self, obs: torch.Tensor):
+        """(..., H, W, 3) uint8 -> (..., 3, H, W) float in [-0.5, 0.5] (dreamer_v2.py:113-122)."""
+        dims = list(range(obs.dim()))
+        order = dims[:-3] + [dims[-1]] + dims[-3:-1]
+        return ((obs.type(torch.float32) / 255.0) - 0.5).permute(order)
+
+    def unprocess_obs(self, obs: torch.Tensor):
+        return ((obs + 0.5).clamp(0, 1) * 255).cpu().to(dtype=torch.uint8)
+
+    def get_action(self, obs: Observation) -> Action:
+        obs = self.preprocess_obs(torch.from_numpy(obs).to(self.device))
+        self._state = self.world_model.get_latent(obs, self._last_action, self._state)
+        dist = self.actor.get_action(self._state)
+        self._last_action = dist.sample()
+        if self.is_discrete:
+            self._action_probs += dist.probs.squeeze()
+            return self._last_action.argmax()
+        return self._last_action.squeeze().detach().cpu()
+
+    def from_np(self, arr: np.ndarray):
+        arr = torch.from_numpy(arr) if isinstance(arr, np.ndarray) else arr
+        return arr.to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------
+    # the hot path: imagination + lambda-return + actor-critic update (dreamer_v2.py:179-211)
+    # ------------------------------------------------------------------------------------------
+    def behaviour_update(self, initial_states: State, noise: t.Optional[dict] = None):
+        """Second half of ``train``; returns (losses, metrics) as tensors.  Split out so that the
+        benchmark and the tests can drive it from synthetic start states."""
+        from rl_sandbox_b200 import ops
+        with torch.autocast(device_type='cuda', enabled=self.is_f16):
+            no_grad_rollout = self.actor.rho == 1.0
+            with (torch.no_grad() if no_grad_rollout else torch.enable_grad()):
+                states, actions, rewards, discounts = self.imagine_trajectory(initial_states, noise=noise)
+            rewards = self.world_model.reward_normalizer(rewards.float())
+            discounts = discounts.float()
+            zs = states.combined
+            k1 = self.last_rollout
+            if k1 is not None:
+                # K1 already evaluated the target critic on every state; K2 returns the lambda-returns,
+                # the shifted cumprod weights and the advantage in one launch
+                values = k1['values'].unsqueeze(-1)
+                vs, w, _ = ops.lambda_return(rewards, values, discounts, self.critic.lambda_)
+                w = w.detach()
+            else:
+                values = self.critic.target_critic(zs).mode
+                vs = self.critic.lambda_return(zs, rewards[:-1], discounts, vs=values)
+                w = torch.cumprod(torch.cat([torch.ones_like(discounts[:1]), discounts[:-1]], dim=0), dim=0).detach()
+            losses_c, metrics_c = self.critic.calculate_loss(zs[:-1], vs, w[:-1], target_values=values[:-1])
+            losses_a, metrics_a = self.actor.calculate_loss(zs[:-2], vs[1:], values[:-2].detach(), w[:-2],
+                                                            actions[1:-1], metrics_samples=self.metrics_samples)
+        metrics_a |= self.actor_optimizer.step(losses_a['loss_actor'])
+        metrics_c |= self.critic_optimizer.step(losses_c['loss_critic'])
+        self.critic.update_target()
+        self.mark_weights_changed()
+        return losses_a | losses_c, metrics_a | metrics_c
+
+    def train(self, rollout_chunks: RolloutChunks):
+        obs, a, r, is_finished, is_first, additional = unpack(rollout_chunks)
+        if self.is_discrete:
+            a = F.one_hot(a.to(torch.int64), num_classes=self.actions_num).squeeze()
+        discount_factors = self.critic.gamma * (1 - is_finished).float()
+        first_flags = is_first.float()
+
+        with torch.autocast(device_type='cuda', enabled=self.is_f16):
+            losses_wm, discovered_states, metrics_wm = self.world_model.calculate_loss(
+                obs, a, r, discount_factors, first_flags, additional)
+        metrics_wm |= self.world_model_optimizer.step(losses_wm['loss_wm'])
+        self.mark_weights_changed()
+
+        initial_states = discovered_states.flatten().detach()
+        losses_ac, metrics_ac = self.behaviour_update(initial_states)
+
+        losses = losses_wm | losses_ac
+        metrics = metrics_wm | metrics_ac
+        losses = {k: v.detach().cpu().numpy() for k, v in losses.items()}
+        metrics = {k: v.detach().cpu().numpy() for k, v in metrics.items()}
+        losses['total'] = sum(losses.values())
+        return losses | metrics
+
+    # ------------------------------------------------------------------------------------------
+    def save_ckpt(self, epoch_num: int, losses: dict[str, float]):
+        """Same file layout as the reference (dreamer_v2.py:222-233), including the `_orig_mod.`
+        prefix its torch.compile wrappers put on world-model / critic keys."""
+        pref = lambda sd: {f'_orig_mod.{k}': v for k, v in sd.items()}
+        torch.save({
+            'epoch': epoch_num,
+            'world_model_state_dict': pref(self.world_model.state_dict()),
+            'world_model_optimizer_state_dict': self.world_model_optimizer.optimizer.state_dict(),
+            'actor_state_dict': self.actor.state_dict(),
+            'critic_state_dict': pref(self.critic.state_dict()),
+            'actor_optimizer_state_dict': self.actor_optimizer.optimizer.state_dict(),
+            'critic_optimizer_state_dict': self.critic_optimizer.optimizer.state_dict(),
+            'losses': losses,
+        }, f'dreamerV2-{epoch_num}-{losses["total"]}.ckpt')
+
+    def load_ckpt(self, ckpt_path: Path):
+        ckpt = torch.load(ckpt_path, map_location=self.device, weights_only=False)
+        self.world_model.load_state_dict(_strip_compile_prefix(ckpt['world_model_state_dict']))
+        self.actor.load_state_dict(ckpt['actor_state_dict'])
+        self.critic.load_state_dict(_strip_compile_prefix(ckpt['critic_state_dict']))
+        # the reference calls load_state_dict on its Optimizer wrapper, which has none (its own FIXME,
+        # dreamer_v2.py:238); restoring the wrapped torch optimizers is what was meant
+        self.world_model_optimizer.optimizer.load_state_dict(ckpt['world_model_optimizer_state_dict'])
+        self.actor_optimizer.optimizer.load_state_dict(ckpt['actor_optimizer_state_dict'])
+        self.critic_optimizer.optimizer.load_state_dict(ckpt['critic_optimizer_state_dict'])
+        self.mark_weights_changed()
+        return ckpt['epoch']

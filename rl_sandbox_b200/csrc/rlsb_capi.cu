@@ -2,11 +2,16 @@
 // entry points, which live next to their planner in rlsb_imagine.cu, and K3 in rlsb_slot.cu).
 #include "../../include/rlsb.h"
 
+#include "rlsb_count.cuh"
 #include "rlsb_detmath.h"
 #include "rlsb_gemm.cuh"
 #include "rlsb_kernels.cuh"
 
 using namespace rlsb;
+
+namespace rlsb {
+std::atomic<long long> g_launches{0};
+}
 
 namespace {
 __global__ void philox_uniform_kernel(uint64_t seed, uint32_t n0, uint32_t t, uint32_t stream_id,
@@ -20,6 +25,12 @@ __global__ void philox_uniform_kernel(uint64_t seed, uint32_t n0, uint32_t t, ui
 }  // namespace
 
 extern "C" int rlsb_abi_version(void) { return RLSB_ABI_VERSION; }
+
+extern "C" long long rlsb_launch_count(int reset) {
+  const long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
 
 extern "C" int rlsb_check_device(void) {
   int dev = 0;
@@ -69,6 +80,7 @@ extern "C" int rlsb_philox_uniform(uint64_t seed, uint32_t n0, uint32_t t, uint3
   if (!out || per_row <= 0 || count <= 0) return -1;
   philox_uniform_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       seed, n0, t, stream_id, per_row, count, out);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 

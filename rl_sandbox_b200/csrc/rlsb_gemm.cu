@@ -14,6 +14,7 @@
 // Replaces (reference): nn.Linear + nn.LayerNorm + nn.ELU chains in
 // agents/dreamer/rssm.py:136-152, agents/dreamer/common.py:58-75, utils/fc_nn.py:14-22.
 #include "rlsb_gemm.cuh"
+#include "rlsb_count.cuh"
 #include "rlsb_ptx.cuh"
 
 namespace rlsb {
@@ -353,6 +354,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
     default: return -7;
   }
 #undef RLSB_LAUNCH
+  count_launch();
   e = cudaGetLastError();
   return static_cast<int>(e);
 }

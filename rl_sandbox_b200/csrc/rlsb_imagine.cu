@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "../../include/rlsb.h"
+#include "rlsb_count.cuh"
 #include "rlsb_gemm.cuh"
 #include "rlsb_kernels.cuh"
 
@@ -131,6 +132,7 @@ __global__ void copy_pad_kernel(const float* __restrict__ src, int n, float* __r
 
 int copy_pad(const float* src, int n, float* dst, int n_pad, float fill, cudaStream_t s) {
   copy_pad_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(src, n, dst, n_pad, fill);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -306,6 +308,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     const long long tot = N * cfg->groups;
     onehot_to_idx_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(z0, N, cfg->groups,
                                                                                   cfg->classes, out->stoch_idx);
+    count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
   }

@@ -2,6 +2,7 @@
 // GRU-gate application, categorical sampling, head post-processing and the lambda-return scan.
 #include "rlsb_kernels.cuh"
 
+#include "rlsb_count.cuh"
 #include "rlsb_detmath.h"
 #include "rlsb_gemm.cuh"
 #include "rlsb_ptx.cuh"
@@ -403,9 +404,6 @@ __global__ void lambda_return_tm_kernel(const float* __restrict__ r, const float
   }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) vnext[j] = V[j];
-  float Vup[VEC];  // V[t+1] (needed for adv[t] = vs[t+1] - v[t])
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) Vup[j] = 0.f;
   for (int t = H - 1; t >= 0; --t) {
     float rr[VEC], dd[VEC], vv[VEC];
     const size_t off = static_cast<size_t>(t) * N + n0;
@@ -442,12 +440,10 @@ __global__ void lambda_return_tm_kernel(const float* __restrict__ r, const float
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      Vup[j] = V[j];
       V[j] = out[j];
       vnext[j] = vv[j];
     }
   }
-  (void)Vup;
   if (w) {
     // w[0] = 1, w[t] = w[t-1] * d[t-1]   (dreamer_v2.py:194-197)
     float acc[VEC];
@@ -457,14 +453,16 @@ __global__ void lambda_return_tm_kernel(const float* __restrict__ r, const float
       const size_t off = static_cast<size_t>(t) * N + n0;
       if (VEC == 4) {
         *reinterpret_cast<float4*>(w + off) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
-        const float4 b = *reinterpret_cast<const float4*>(d + off);
-        acc[0] = __fmul_rn(acc[0], b.x);
-        acc[1 % VEC] = __fmul_rn(acc[1 % VEC], b.y);
-        acc[2 % VEC] = __fmul_rn(acc[2 % VEC], b.z);
-        acc[3 % VEC] = __fmul_rn(acc[3 % VEC], b.w);
+        if (t + 1 < T) {  // d[H] is never read: the caller may pass only H rows
+          const float4 b = *reinterpret_cast<const float4*>(d + off);
+          acc[0] = __fmul_rn(acc[0], b.x);
+          acc[1 % VEC] = __fmul_rn(acc[1 % VEC], b.y);
+          acc[2 % VEC] = __fmul_rn(acc[2 % VEC], b.z);
+          acc[3 % VEC] = __fmul_rn(acc[3 % VEC], b.w);
+        }
       } else {
         w[off] = acc[0];
-        acc[0] = __fmul_rn(acc[0], d[off]);
+        if (t + 1 < T) acc[0] = __fmul_rn(acc[0], d[off]);
       }
     }
   }
@@ -569,6 +567,7 @@ int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16*
   for (int s = 0; s < n_seg; ++s) a.seg[s] = segs[s];
   const long long total = static_cast<long long>(rows_dst_pad) * (k_pad / 8);
   pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -578,6 +577,7 @@ int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB
   LnActArgs a{scratch, ld, stats, NB, RB, M, m_pad, N, gamma, beta, eps, act, out, out_kpad};
   const long long total = static_cast<long long>(m_pad) * (out_kpad / 8);
   ln_act_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -589,6 +589,7 @@ int launch_gru_gate(const float* scratch, long long ld, const float* stats, int 
             h_prev, ld_h, h_next, ld_hn, h_next_packed, kpad};
   const long long total = static_cast<long long>(m_pad) * (kpad / 8);
   gru_gate_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -600,6 +601,7 @@ int launch_sample_latent(const float* logits, long long ld, int M, int groups, i
   const long long total = static_cast<long long>(M) * groups;
   const int block = 128;
   sample_latent_kernel<<<static_cast<unsigned>((total + block - 1) / block), block, 0, stream>>>(a);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -609,6 +611,7 @@ int launch_sample_categorical(const float* logits, const float* uniforms, long l
   const int block = 128;
   sample_categorical_kernel<<<static_cast<unsigned>((rows + block - 1) / block), block, 0, stream>>>(
       logits, uniforms, rows, classes, idx_out);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -616,6 +619,7 @@ int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream) {
   if (p.a_kpad > 64 || (p.a_kpad % 8) != 0) return -1;
   const int block = 128;
   head_finish_kernel<<<(p.m_pad + block - 1) / block, block, 0, stream>>>(p);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -648,6 +652,7 @@ int launch_lambda_return(const float* r, const float* v, const float* d, int T, 
           r, v, d, T, N, c1, c2, vs, w, adv);
     }
   }
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -660,6 +665,7 @@ int launch_lambda_return_bwd(const float* g_vs, const float* v, const float* d, 
   const int block = 256;
   lambda_return_bwd_kernel<<<static_cast<unsigned>((N + block - 1) / block), block, 0, stream>>>(
       g_vs, v, d, vs, T, N, c1, c2, g_r, g_v, g_d);
+  count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -46,18 +46,22 @@ def lambda_return(r: torch.Tensor, v: torch.Tensor, d: torch.Tensor, lambda_: fl
     lib = _lib.load()
     r, v, d = _f32c(r), _f32c(v), _f32c(d)
     if batch_major:
-        N, T = r.shape[0], r.shape[1]
+        N, T = v.shape[0], v.shape[1]
+        if r.shape != v.shape or d.shape != v.shape:
+            raise _lib.RlsbError("lambda_return(batch_major): r, v, d must all be (N, T)")
         vs = torch.empty((N, T - 1), device=r.device, dtype=torch.float32)
         w = torch.empty((N, T), device=r.device, dtype=torch.float32) if want_weights else None
         adv = torch.empty((N, T - 2), device=r.device, dtype=torch.float32) if want_adv else None
     else:
-        T = r.shape[0]
-        N = r[0].numel()
-        vs = torch.empty((T - 1,) + tuple(r.shape[1:]), device=r.device, dtype=torch.float32)
-        w = torch.empty_like(r) if want_weights else None
-        adv = torch.empty((T - 2,) + tuple(r.shape[1:]), device=r.device, dtype=torch.float32) if want_adv else None
-    if v.numel() != r.numel() or d.numel() != r.numel():
-        raise _lib.RlsbError("lambda_return: r, v, d must have the same number of elements (T*N)")
+        # v has T = H+1 rows; r and d may have H or H+1 rows (only rows 0..H-1 are read, ac.py:57-58)
+        T = v.shape[0]
+        N = v[0].numel()
+        for name, x in (("r", r), ("d", d)):
+            if x.shape[0] not in (T - 1, T) or x[0].numel() != N:
+                raise _lib.RlsbError(f"lambda_return: {name} has shape {tuple(x.shape)}, v {tuple(v.shape)}")
+        vs = torch.empty((T - 1,) + tuple(v.shape[1:]), device=r.device, dtype=torch.float32)
+        w = torch.empty_like(v) if want_weights else None
+        adv = torch.empty((T - 2,) + tuple(v.shape[1:]), device=r.device, dtype=torch.float32) if want_adv else None
     check(lib.rlsb_lambda_return_fwd(r.data_ptr(), v.data_ptr(), d.data_ptr(), T, N, float(lambda_),
                                      vs.data_ptr(), _ptr(w), _ptr(adv), int(batch_major), _stream()),
           "rlsb_lambda_return_fwd")
@@ -85,13 +89,14 @@ class LambdaReturnFn(torch.autograd.Function):
         vs, _, _ = lambda_return(r, v, d, lambda_, want_weights=False, want_adv=False)
         ctx.save_for_backward(v, d, vs)
         ctx.lambda_ = lambda_
+        ctx.rows = (r.shape[0], d.shape[0])
         return vs
 
     @staticmethod
     def backward(ctx, g_vs):
         v, d, vs = ctx.saved_tensors
         g_r, g_v, g_d = lambda_return_bwd(g_vs.contiguous(), v, d, vs, ctx.lambda_)
-        return g_r, g_v, g_d, None
+        return g_r[:ctx.rows[0]], g_v, g_d[:ctx.rows[1]], None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,17 +164,21 @@ def plan_blocks(n: int) -> tuple[int, int]:
     return round_up((n + nb - 1) // nb, 32), nb
 
 
-def gemm_bias(a_packed, k_pad, w_packed, rb, nb, bias, M, N, want_stats=False):
+def gemm_bias(a_packed, k_pad, w_packed, rb, nb, bias, M, N, want_stats=False, out=None, stats=None, bias_p=None):
+    """out, stats, bias_p may be pre-allocated by the caller (benchmark loops)."""
     _lib.require_device()
     lib = _lib.load()
     m_pad = round_up(M, 128)
-    out = torch.zeros((m_pad, N), device=a_packed.device, dtype=torch.float32)
-    stats = torch.zeros((nb, m_pad, 2), device=a_packed.device, dtype=torch.float32) if want_stats else None
-    bias_p = torch.zeros(rb * nb, device=a_packed.device, dtype=torch.float32)
-    if bias is not None:
-        bias_p[:N] = bias
+    if out is None:
+        out = torch.zeros((m_pad, N), device=a_packed.device, dtype=torch.float32)
+    if want_stats and stats is None:
+        stats = torch.zeros((nb, m_pad, 2), device=a_packed.device, dtype=torch.float32)
+    if bias_p is None:
+        bias_p = torch.zeros(rb * nb, device=a_packed.device, dtype=torch.float32)
+        if bias is not None:
+            bias_p[:N] = bias
     check(lib.rlsb_gemm_bias(a_packed.data_ptr(), k_pad, w_packed.data_ptr(), rb, nb, bias_p.data_ptr(), M, N,
-                             out.data_ptr(), N, _ptr(stats), _stream()), "rlsb_gemm_bias")
+                             out.data_ptr(), N, _ptr(stats) if want_stats else None, _stream()), "rlsb_gemm_bias")
     return out[:M], stats
 
 

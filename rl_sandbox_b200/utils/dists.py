@@ -4,7 +4,9 @@ Only the variants the three shipped configs reach are provided: 'mse', 'onehot',
 'binary'.  Semantics kept from the reference, including its quirks:
   * TruncatedNormal overrides ``sample`` (clamped) but inherits the UNCLAMPED ``rsample`` of Normal;
   * 'onehot' is OneHotCategoricalStraightThrough on fp32 logits and is NOT wrapped in Independent;
-  * every other head is Independent(..., 1).
+  * every other head is Independent(..., 1);
+  * argument validation is off, as the reference's train.py:38 switches it off globally (the
+    discount head is trained on gamma*(1-done) targets, which are not booleans).
 """
 import torch
 import torch.distributions as td
@@ -46,11 +48,11 @@ class DistLayer(nn.Module):
 
     def forward(self, x):
         if self._dist == 'onehot':
-            return td.OneHotCategoricalStraightThrough(logits=x.float())
+            return td.OneHotCategoricalStraightThrough(logits=x.float(), validate_args=False)
         if self._dist == 'mse':
-            base = td.Normal(x.float(), 1.0)
+            base = td.Normal(x.float(), 1.0, validate_args=False)
         elif self._dist == 'binary':
-            base = td.Bernoulli(logits=x.float())
+            base = td.Bernoulli(logits=x.float(), validate_args=False)  # targets are gamma*(1-done), not {0,1}
         else:
             base = TruncatedNormal(*trunc_normal_params(x))
-        return td.Independent(base, 1)
+        return td.Independent(base, 1, validate_args=False)

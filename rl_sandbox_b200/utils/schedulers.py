@@ -3,22 +3,25 @@ import numpy as np
 
 
 class Scheduler:
-    def step(self):
+    def step(self) -> float:
         raise NotImplementedError
 
 
 class LinearScheduler(Scheduler):
-    def __init__(self, initial, final, iters):
-        self._iters = max(1, iters - 1)
-        self._val = initial
-        self._initial, self._final = initial, final
-        self._curr = 0
+    """value(t) ramps from `initial_value` at t=0 to `final_value` at t=duration-1 and stays there."""
+
+    def __init__(self, initial_value, final_value, duration):
+        self._init, self._final = initial_value, final_value
+        self._dur = duration - 1
+        self._curr_t = 0
 
     @property
-    def val(self):
-        return float(np.interp(self._curr, [0, self._iters], [self._initial, self._final]))
+    def val(self) -> float:
+        if self._curr_t >= self._dur:
+            return self._final
+        return float(np.interp(self._curr_t, [0, self._dur], [self._init, self._final]))
 
-    def step(self):
-        v = self.val
-        self._curr += 1
-        return v
+    def step(self) -> float:
+        current = self.val
+        self._curr_t += 1
+        return current
