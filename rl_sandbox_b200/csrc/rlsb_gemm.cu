@@ -21,6 +21,10 @@ namespace rlsb {
 
 namespace {
 
+constexpr int kEpiWarps = 16;                       // 4 TMEM lane quarters x 4 column quarters
+constexpr int kEpiThreads = kEpiWarps * 32;         // 512
+constexpr int kMaxRB = 512;
+
 struct SmemCtl {
   uint64_t full[8];
   uint64_t empty[8];
@@ -28,10 +32,15 @@ struct SmemCtl {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
+  float bias[2][kMaxRB];    // double-buffered per-tile epilogue parameters
+  float gamma[2][kMaxRB];
+  float beta[2][kMaxRB];
+  float2 part[4][kTileM];   // per column-quarter partial (sum, sumsq) of each row
 };
 
 __device__ __forceinline__ float act_apply(float x, int act) {
-  if (act == ACT_ELU) return x > 0.f ? x : expm1f(x);
+  // ELU as the reference evaluates it on the CPU: exp(x) - 1 for x <= 0 (ATen elu kernel)
+  if (act == ACT_ELU) return x > 0.f ? x : __expf(x) - 1.0f;
   if (act == ACT_RELU) return fmaxf(x, 0.f);
   return x;
 }
@@ -39,6 +48,18 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void epi_bar(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
+}
+
+// work item -> (m_tile, g, nb).  The n-block index runs fastest so that the CTAs resident at any
+// moment share a handful of A tiles (L2 hits) while the whole weight matrix stays L2 resident.
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& gnb) {
+  const int per_m = p.G * p.NB;
+  m_tile = w / per_m;
+  gnb = w - m_tile * per_m;
 }
 
 template <int EPI>
@@ -69,7 +90,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&ctl->tmem_full[b], 1);
-        mbar_init(&ctl->tmem_empty[b], 128);
+        mbar_init(&ctl->tmem_empty[b], kEpiWarps);
       }
       fence_mbar_init();
     }
@@ -88,8 +109,8 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int m_tile = w % p.m_tiles;
-        const int gnb = w / p.m_tiles;  // g * NB + nb
+        int m_tile, gnb;
+        decode_work(p, w, m_tile, gnb);
         const int g = gnb / p.NB;
         const __nv_bfloat16* wsrc =
             p.W + static_cast<size_t>(gnb) * kt_total * (static_cast<size_t>(p.RB) * kTileK);
@@ -159,144 +180,173 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, one TMEM lane (row) per thread ===============
-    const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;        // row inside the 128-row tile
+    // ===================== epilogue: 16 warps ==============================================
+    // warp -> (q, cq): q = TMEM lane quarter it may address (hardware: warp id % 4) = 32 rows,
+    // cq = which quarter of the 8-column chunks it owns (chunk c belongs to cq = c % 4).
+    // Row statistics are combined across the 4 column quarters through shared memory.
+    const int q = warp & 3;
+    const int cq = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int tid_e = threadIdx.x - 64;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int m_pad = p.m_tiles * kTileM;
+    const int my_chunks = p.RB >> 5;  // (RB / 8) / 4
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
-      const int m_tile = w % p.m_tiles;
-      const int gnb = w / p.m_tiles;
+      int m_tile, gnb;
+      decode_work(p, w, m_tile, gnb);
       const int g = gnb / p.NB;
       const int nb = gnb - g * p.NB;
       const int buf = (nbuf == 2) ? (it & 1) : 0;
       const uint32_t use = (nbuf == 2) ? static_cast<uint32_t>(it >> 1) : static_cast<uint32_t>(it);
+      const int col0 = nb * p.RB;                   // first column of this block inside the group
+      const int n_valid = min(p.RB, p.N - col0);    // valid columns in this block (may be <= 0)
+      const int pb = it & 1;
+      // ---- stage this tile's parameters (overlaps the tile's main loop) ------------------------
+      {
+        const size_t poff = static_cast<size_t>(g) * p.NB * p.RB + col0;
+        for (int i = tid_e; i < p.RB; i += kEpiThreads) {
+          ctl->bias[pb][i] = p.bias ? __ldg(p.bias + poff + i) : 0.f;
+          if (EPI == EPI_LN_ACT && p.ln_gamma) {
+            ctl->gamma[pb][i] = __ldg(p.ln_gamma + static_cast<size_t>(g) * p.RB + i);
+            ctl->beta[pb][i] = __ldg(p.ln_beta + static_cast<size_t>(g) * p.RB + i);
+          }
+        }
+      }
+      epi_bar(1);
+      const float* sbias = ctl->bias[pb];
       mbar_wait(&ctl->tmem_full[buf], use & 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * buf_cols) + lane_addr;
       const int m = m_tile * kTileM + row;
-      const int col0 = nb * p.RB;                     // first column of this block inside the group
-      const int n_valid = min(p.RB, p.N - col0);      // valid columns in this block (may be <= 0)
-      const float* bias = p.bias ? p.bias + static_cast<size_t>(g) * p.NB * p.RB + col0 : nullptr;
+      const bool has_ln = (EPI == EPI_LN_ACT) && (p.ln_gamma != nullptr);
 
-      if (EPI == EPI_PLAIN || EPI == EPI_STATS) {
-        float* orow = p.out_f32 + static_cast<size_t>(g) * p.out_group_stride +
-                      static_cast<size_t>(m) * p.ldo + col0;
-        const bool vec_ok = ((p.ldo & 3) == 0) && ((col0 & 3) == 0);
-        float sum = 0.f;
-        for (int c = 0; c < p.RB; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_d + static_cast<uint32_t>(c), r);
+      // ---- pass 1: statistics (EPI_STATS / LayerNorm) and/or plain fp32 output ------------------
+      float mean = 0.f, rstd = 1.f;
+      if (EPI == EPI_PLAIN || EPI == EPI_STATS || has_ln) {
+        float sum = 0.f, sq = 0.f;
+        float* orow = (EPI == EPI_LN_ACT) ? nullptr
+                                          : p.out_f32 + static_cast<size_t>(g) * p.out_group_stride +
+                                                static_cast<size_t>(m) * p.ldo + col0;
+        const bool vec_ok = (EPI != EPI_LN_ACT) && ((p.ldo & 3) == 0) && ((col0 & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
+        for (int i0 = 0; i0 < my_chunks; i0 += 4) {
+          uint32_t r[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (i0 + u < my_chunks) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * (i0 + u)) * 8), r[u]);
           tmem_ld_wait();
-          if (m < p.M && c < n_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float v[4];
+          for (int u = 0; u < 4; ++u) {
+            if (i0 + u < my_chunks) {
+              const int c = (cq + 4 * (i0 + u)) * 8;
+              float v[8];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                v[t] = __uint_as_float(r[j + t]) + (bias ? __ldg(bias + c + j + t) : 0.f);
-                if (c + j + t < n_valid) sum += v[t];
-              }
-              if (vec_ok && c + j + 3 < n_valid) {
-                *reinterpret_cast<float4*>(orow + c + j) = make_float4(v[0], v[1], v[2], v[3]);
-              } else {
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[u][j]) + sbias[c + j];
+              if (c + 8 <= n_valid) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  if (c + j + t < n_valid) orow[c + j + t] = v[t];
-              }
-            }
-          }
-        }
-        if (EPI == EPI_STATS) {
-          const float mean = n_valid > 0 ? sum / static_cast<float>(n_valid) : 0.f;
-          float m2 = 0.f;
-          for (int c = 0; c < p.RB; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_d + static_cast<uint32_t>(c), r);
-            tmem_ld_wait();
-            if (c < n_valid) {
+                for (int j = 0; j < 8; ++j) {
+                  sum += v[j];
+                  sq = fmaf(v[j], v[j], sq);
+                }
+                if (EPI != EPI_LN_ACT && m < p.M) {
+                  if (vec_ok) {
+                    *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(orow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                  } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (c + j < n_valid) {
-                  const float d = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f) - mean;
-                  m2 += d * d;
+                    for (int j = 0; j < 8; ++j) orow[c + j] = v[j];
+                  }
+                }
+              } else if (c < n_valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (c + j < n_valid) {
+                    sum += v[j];
+                    sq = fmaf(v[j], v[j], sq);
+                    if (EPI != EPI_LN_ACT && m < p.M) orow[c + j] = v[j];
+                  }
                 }
               }
             }
           }
-          float2* st = reinterpret_cast<float2*>(p.stats) +
-                       (static_cast<size_t>(gnb) * m_pad + static_cast<size_t>(m));
-          *st = make_float2(mean, m2);
         }
-      } else {  // EPI_LN_ACT : the block holds the whole row (NB == 1)
-        const float* gam = p.ln_gamma ? p.ln_gamma + static_cast<size_t>(g) * p.RB : nullptr;
-        const float* bet = p.ln_beta ? p.ln_beta + static_cast<size_t>(g) * p.RB : nullptr;
-        float mean = 0.f, rstd = 1.f;
-        if (gam) {
-          float sum = 0.f;
-          for (int c = 0; c < n_valid; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_d + static_cast<uint32_t>(c), r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c + j < n_valid) sum += __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+        if (EPI == EPI_STATS || has_ln) {
+          ctl->part[cq][row] = make_float2(sum, sq);
+          epi_bar(2);
+          const float2 a0 = ctl->part[0][row], a1 = ctl->part[1][row], a2 = ctl->part[2][row],
+                       a3 = ctl->part[3][row];
+          const float tsum = (a0.x + a1.x) + (a2.x + a3.x);
+          const float tsq = (a0.y + a1.y) + (a2.y + a3.y);
+          if (EPI == EPI_STATS) {
+            // per-(row, n-block) partials (sum, sum of squares); the consumer combines the blocks
+            if (cq == 0)
+              reinterpret_cast<float2*>(p.stats)[static_cast<size_t>(gnb) * m_pad + m] = make_float2(tsum, tsq);
+          } else {
+            const float inv_n = 1.0f / static_cast<float>(n_valid);
+            mean = tsum * inv_n;
+            const float var = fmaxf(tsq * inv_n - mean * mean, 0.f);
+            rstd = 1.0f / sqrtf(var + p.ln_eps);
           }
-          mean = sum / static_cast<float>(n_valid);
-          float m2 = 0.f;
-          for (int c = 0; c < n_valid; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_d + static_cast<uint32_t>(c), r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c + j < n_valid) {
-                const float d = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f) - mean;
-                m2 += d * d;
-              }
-          }
-          rstd = 1.0f / sqrtf(m2 / static_cast<float>(n_valid) + p.ln_eps);
         }
+      }
+
+      // ---- pass 2 (EPI_LN_ACT): normalise, activate, write the packed bf16 operand image --------
+      if (EPI == EPI_LN_ACT) {
+        const float* sgam = ctl->gamma[pb];
+        const float* sbet = ctl->beta[pb];
         __nv_bfloat16* obase = p.out_bf16 + static_cast<size_t>(g) * p.out_bf16_group_stride;
         const int out_ktiles = p.out_kpad >> 6;
-        for (int c = 0; c < p.out_kpad; c += 32) {
-          uint32_t r[32];
-          if (c < p.RB) {  // warp-uniform
-            tmem_ld32(tmem_d + static_cast<uint32_t>(c), r);
-            tmem_ld_wait();
-          }
-          float y[32];
+        const int out_chunks = (p.out_kpad - col0 < p.RB ? p.out_kpad - col0 : p.RB) >> 3;
+        const int tot_chunks = p.RB >> 3;
+        for (int i0 = 0; i0 < my_chunks; i0 += 4) {
+          uint32_t r[4][8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = 0.f;
-            if (c + j < n_valid) {
-              v = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
-              if (gam) v = (v - mean) * rstd * __ldg(gam + c + j) + __ldg(bet + c + j);
-              v = act_apply(v, p.act);
+          for (int u = 0; u < 4; ++u)
+            if (i0 + u < my_chunks) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * (i0 + u)) * 8), r[u]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ch = cq + 4 * (i0 + u);
+            if (i0 + u < my_chunks && ch < out_chunks) {
+              const int c = ch * 8;
+              float y[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float v = 0.f;
+                if (c + j < n_valid) {
+                  v = __uint_as_float(r[u][j]) + sbias[c + j];
+                  if (has_ln) v = (v - mean) * rstd * sgam[c + j] + sbet[c + j];
+                  v = act_apply(v, p.act);
+                }
+                y[j] = v;
+              }
+              const int oc = col0 + c;  // output column
+              __nv_bfloat16* trow = obase + (static_cast<size_t>(m_tile) * out_ktiles + (oc >> 6)) *
+                                                (kTileM * kTileK) +
+                                    static_cast<size_t>(row) * kTileK;
+              const int chunk = ((oc & 63) >> 3) ^ (row & 7);
+              *reinterpret_cast<uint4*>(trow + chunk * 8) =
+                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                             pack_bf16x2(y[6], y[7]));
             }
-            y[j] = v;
           }
-          // packed store: tile (m_tile, c/64), row `row`, chunks (c%64)/8 .. +3, swizzled
-          const int kt = c >> 6;
-          __nv_bfloat16* trow = obase + (static_cast<size_t>(m_tile) * out_ktiles + kt) *
-                                            (kTileM * kTileK) +
-                                static_cast<size_t>(row) * kTileK;
-          const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint4 pk;
-            pk.x = pack_bf16x2(y[ch * 8 + 0], y[ch * 8 + 1]);
-            pk.y = pack_bf16x2(y[ch * 8 + 2], y[ch * 8 + 3]);
-            pk.z = pack_bf16x2(y[ch * 8 + 4], y[ch * 8 + 5]);
-            pk.w = pack_bf16x2(y[ch * 8 + 6], y[ch * 8 + 7]);
-            const int chunk = (chunk0 + ch) ^ (row & 7);
-            *reinterpret_cast<uint4*>(trow + chunk * 8) = pk;
+        }
+        // zero the padding columns [RB, out_kpad) of the packed image (last block only)
+        if (nb == p.NB - 1) {
+          for (int ch = tot_chunks + cq; ch < ((p.out_kpad - col0) >> 3); ch += 4) {
+            const int oc = col0 + ch * 8;
+            __nv_bfloat16* trow = obase + (static_cast<size_t>(m_tile) * out_ktiles + (oc >> 6)) *
+                                              (kTileM * kTileK) +
+                                  static_cast<size_t>(row) * kTileK;
+            const int chunk = ((oc & 63) >> 3) ^ (row & 7);
+            *reinterpret_cast<uint4*>(trow + chunk * 8) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(&ctl->tmem_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
     }
   }
 
@@ -327,6 +377,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   }
   const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2;
   const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256;
+  static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return -6;

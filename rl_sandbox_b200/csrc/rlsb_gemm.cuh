@@ -10,7 +10,7 @@ namespace rlsb {
 constexpr int kTileM = 128;      // rows per M tile == TMEM lanes
 constexpr int kTileK = 64;       // bf16 elements per 128-byte swizzled row
 constexpr int kMaxSeg = 3;       // K segments (concatenated inputs, e.g. cat[x, h])
-constexpr int kGemmThreads = 192;  // warp0 = bulk-copy producer, warp1 = MMA issuer, warps2-5 = epilogue
+constexpr int kGemmThreads = 576;  // warp0 = bulk-copy producer, warp1 = MMA issuer, warps2-17 = epilogue
 
 enum GemmEpilogue : int {
   EPI_PLAIN = 0,   // out_f32[m][col] = acc + bias                         (row-major fp32)
@@ -40,7 +40,7 @@ struct GemmParams {
   float* out_f32;              // [G][M_pad][ldo]
   long long ldo;
   long long out_group_stride;  // elements
-  float* stats;                // [G][NB][M_pad][2] = (mean, M2) over the block's valid columns
+  float* stats;                // [G][NB][M_pad][2] = (sum, sum of squares) over the block's valid columns
   // ---- EPI_LN_ACT ---------------------------------------------------------------------------
   const float* ln_gamma;  // [G][RB] or nullptr (=> no LayerNorm)
   const float* ln_beta;

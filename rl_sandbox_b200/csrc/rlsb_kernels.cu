@@ -65,27 +65,34 @@ __global__ void pack_kernel(const PackArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// combine per-block (mean, M2) partials (Chan et al.) into row mean / rstd
+// LayerNorm statistics from the per-(row, n-block) partials (sum, sum of squares) the GEMM
+// epilogue wrote: one warp works on one row, lane b fetches block b, shuffle-reduce.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void combine_stats(const float* stats, int NB, int RB, int m_pad, int m,
-                                              int N, float eps, float& mean, float& rstd) {
+__device__ __forceinline__ void row_stats_warp(const float* stats, int NB, int m_pad, int m, int N,
+                                               float eps, float& mean, float& rstd) {
   const float2* st = reinterpret_cast<const float2*>(stats);
-  float tot = 0.f;
-  for (int b = 0; b < NB; ++b) {
-    const int nb = min(RB, N - b * RB);
-    if (nb > 0) tot += static_cast<float>(nb) * __ldg(&st[static_cast<size_t>(b) * m_pad + m]).x;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f, q = 0.f;
+  for (int b = lane; b < NB; b += 32) {
+    const float2 v = __ldg(&st[static_cast<size_t>(b) * m_pad + m]);
+    s += v.x;
+    q += v.y;
   }
-  mean = tot / static_cast<float>(N);
-  float m2 = 0.f;
-  for (int b = 0; b < NB; ++b) {
-    const int nb = min(RB, N - b * RB);
-    if (nb > 0) {
-      const float2 s = __ldg(&st[static_cast<size_t>(b) * m_pad + m]);
-      const float d = s.x - mean;
-      m2 += s.y + static_cast<float>(nb) * d * d;
-    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  rstd = 1.0f / sqrtf(m2 / static_cast<float>(N) + eps);
+  const float inv_n = 1.0f / static_cast<float>(N);
+  mean = s * inv_n;
+  rstd = 1.0f / sqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + eps);
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(-2.0f * fabsf(x));
+  const float t = (1.0f - e) / (1.0f + e);
+  return copysignf(t, x);
 }
 
 struct LnActArgs {
@@ -101,26 +108,43 @@ struct LnActArgs {
   int out_kpad;
 };
 
+// one warp per (row, group of 32 eight-column chunks)
 __global__ void ln_act_kernel(const LnActArgs a) {
   const int chunks_per_row = a.out_kpad >> 3;
-  const long long total = static_cast<long long>(a.m_pad) * chunks_per_row;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int m = static_cast<int>(i / chunks_per_row);
-    const int c0 = static_cast<int>(i - static_cast<long long>(m) * chunks_per_row) << 3;
+  const int gpr = (chunks_per_row + 31) >> 5;
+  const long long total = static_cast<long long>(a.m_pad) * gpr;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long wi = warp0; wi < total; wi += nwarps) {
+    const int m = static_cast<int>(wi / gpr);
+    const int chunk = static_cast<int>(wi - static_cast<long long>(m) * gpr) * 32 + lane;
+    const int c0 = chunk << 3;
+    float mean = 0.f, rstd = 1.f;
+    const bool row_ok = m < a.M;
+    if (row_ok && a.gamma) row_stats_warp(a.stats, a.NB, a.m_pad, m, a.N, a.eps, mean, rstd);
+    if (chunk >= chunks_per_row) continue;
     float y[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = 0.f;
-    if (m < a.M && c0 < a.N) {
-      float mean = 0.f, rstd = 1.f;
-      if (a.gamma) combine_stats(a.stats, a.NB, a.RB, a.m_pad, m, a.N, a.eps, mean, rstd);
+    if (row_ok && c0 < a.N) {
       const float* src = a.scratch + static_cast<size_t>(m) * a.ld + c0;
+      float v[8];
+      if (c0 + 8 <= a.N && (a.ld & 3) == 0) {
+        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < a.N) ? src[j] : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (c0 + j < a.N) {
-          float v = src[j];
-          if (a.gamma) v = (v - mean) * rstd * __ldg(a.gamma + c0 + j) + __ldg(a.beta + c0 + j);
-          y[j] = act_apply(v, a.act);
+          float t = v[j];
+          if (a.gamma) t = (t - mean) * rstd * __ldg(a.gamma + c0 + j) + __ldg(a.beta + c0 + j);
+          if (a.act == ACT_ELU) t = t > 0.f ? t : __expf(t) - 1.0f;
+          else if (a.act == ACT_RELU) t = fmaxf(t, 0.f);
+          y[j] = t;
         }
       }
     }
@@ -147,38 +171,67 @@ struct GruArgs {
   int kpad;
 };
 
+__device__ __forceinline__ void load8(const float* p, bool vec, int valid, float (&v)[8]) {
+  if (vec && valid >= 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < valid ? p[j] : 0.f;
+  }
+}
+
 __global__ void gru_gate_kernel(const GruArgs a) {
   const int chunks_per_row = a.kpad >> 3;
-  const long long total = static_cast<long long>(a.m_pad) * chunks_per_row;
+  const int gpr = (chunks_per_row + 31) >> 5;
+  const long long total = static_cast<long long>(a.m_pad) * gpr;
   const int D = a.D;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int m = static_cast<int>(i / chunks_per_row);
-    const int c0 = static_cast<int>(i - static_cast<long long>(m) * chunks_per_row) << 3;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = ((a.ld & 3) == 0) && ((D & 3) == 0) && ((a.ld_h & 3) == 0) && ((a.ld_hn & 3) == 0);
+  for (long long wi = warp0; wi < total; wi += nwarps) {
+    const int m = static_cast<int>(wi / gpr);
+    const int chunk = static_cast<int>(wi - static_cast<long long>(m) * gpr) * 32 + lane;
+    const int c0 = chunk << 3;
+    const bool row_ok = m < a.M;
+    float mean = 0.f, rstd = 1.f;
+    if (row_ok) row_stats_warp(a.stats, a.NB, a.m_pad, m, 3 * D, a.eps, mean, rstd);
+    if (chunk >= chunks_per_row) continue;
     float y[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = 0.f;
-    if (m < a.M && c0 < D) {
-      float mean, rstd;
-      combine_stats(a.stats, a.NB, a.RB, a.m_pad, m, 3 * D, a.eps, mean, rstd);
-      const float* src = a.scratch + static_cast<size_t>(m) * a.ld;
-      const float* hp = a.h_prev + static_cast<size_t>(m) * a.ld_h;
-      float* hn = a.h_next + static_cast<size_t>(m) * a.ld_hn;
+    if (row_ok && c0 < D) {
+      const int valid = min(8, D - c0);
+      const float* src = a.scratch + static_cast<size_t>(m) * a.ld + c0;
+      float pr[8], pc[8], pu[8], hp[8], gr[8], gc[8], gu[8], br[8], bc[8], bu[8];
+      load8(src, vec, valid, pr);
+      load8(src + D, vec, valid, pc);
+      load8(src + 2 * D, vec, valid, pu);
+      load8(a.h_prev + static_cast<size_t>(m) * a.ld_h + c0, vec, valid, hp);
+      load8(a.gamma + c0, vec, valid, gr);
+      load8(a.gamma + D + c0, vec, valid, gc);
+      load8(a.gamma + 2 * D + c0, vec, valid, gu);
+      load8(a.beta + c0, vec, valid, br);
+      load8(a.beta + D + c0, vec, valid, bc);
+      load8(a.beta + 2 * D + c0, vec, valid, bu);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        if (c < D) {
-          const float pr = (src[c] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
-          const float pc = (src[D + c] - mean) * rstd * __ldg(a.gamma + D + c) + __ldg(a.beta + D + c);
-          const float pu =
-              (src[2 * D + c] - mean) * rstd * __ldg(a.gamma + 2 * D + c) + __ldg(a.beta + 2 * D + c);
-          const float r = sigmoidf_(pr);
-          const float cand = tanhf(r * pc);
-          const float u = sigmoidf_(pu + a.update_bias);
-          const float h = u * cand + (1.0f - u) * hp[c];
-          hn[c] = h;
-          y[j] = h;
+        if (j < valid) {
+          const float r = fast_sigmoid((pr[j] - mean) * rstd * gr[j] + br[j]);
+          const float cand = fast_tanh(r * ((pc[j] - mean) * rstd * gc[j] + bc[j]));
+          const float u = fast_sigmoid((pu[j] - mean) * rstd * gu[j] + bu[j] + a.update_bias);
+          y[j] = u * cand + (1.0f - u) * hp[j];
         }
+      }
+      float* hn = a.h_next + static_cast<size_t>(m) * a.ld_hn + c0;
+      if (vec && valid == 8) {
+        *reinterpret_cast<float4*>(hn) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(hn + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < valid) hn[j] = y[j];
       }
     }
     uint4 pk = make_uint4(bf2(y[0], y[1]), bf2(y[2], y[3]), bf2(y[4], y[5]), bf2(y[6], y[7]));
@@ -575,7 +628,7 @@ int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB
                   int m_pad, int N, const float* gamma, const float* beta, float eps, int act,
                   __nv_bfloat16* out, int out_kpad, cudaStream_t stream) {
   LnActArgs a{scratch, ld, stats, NB, RB, M, m_pad, N, gamma, beta, eps, act, out, out_kpad};
-  const long long total = static_cast<long long>(m_pad) * (out_kpad / 8);
+  const long long total = static_cast<long long>(m_pad) * ((out_kpad / 8 + 31) / 32) * 32;
   ln_act_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
@@ -587,7 +640,7 @@ int launch_gru_gate(const float* scratch, long long ld, const float* stats, int 
                     long long ld_hn, __nv_bfloat16* h_next_packed, int kpad, cudaStream_t stream) {
   GruArgs a{scratch, ld, stats, NB, RB, M, m_pad, D, gamma, beta, eps, update_bias,
             h_prev, ld_h, h_next, ld_hn, h_next_packed, kpad};
-  const long long total = static_cast<long long>(m_pad) * (kpad / 8);
+  const long long total = static_cast<long long>(m_pad) * ((kpad / 8 + 31) / 32) * 32;
   gru_gate_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());

@@ -110,10 +110,8 @@ def gemm_case(M, K, N, stats=False):
         # recombine partial stats
         mean = ref.mean(-1)
         var = ref.var(-1, unbiased=False)
-        cnt = torch.tensor([min(rb, N - i * rb) for i in range(nb)], device=dev).float().view(-1, 1)
-        mb, m2b = st[:, :M, 0], st[:, :M, 1]
-        mean_c = (cnt * mb).sum(0) / N
-        var_c = (m2b + cnt * (mb - mean_c) ** 2).sum(0) / N
+        mean_c = st[:, :M, 0].sum(0) / N
+        var_c = st[:, :M, 1].sum(0) / N - mean_c ** 2
         stat("  stats mean", mean_c, mean); stat("  stats var", var_c, var)
     return e
 
