@@ -156,6 +156,43 @@ int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N,
                      const float* z0, const float* logits0, const rlsb_noise* noise,
                      const rlsb_imagine_out* out, void* workspace, void* stream);
 
+/* ---- K3: slot attention ---------------------------------------------------------------------
+ * replaces SlotAttention.forward (rl_sandbox/vision/slot_attention.py:52-77) for explicit
+ * prev_slots (the caller draws the initial slots, slot_attention.py:46-50 /
+ * world_model_slots_attention.py:278-279):
+ *   k, v = W_kv LN(X)                      once              (tcgen05 GEMM, bf16 k/v kept in HBM)
+ *   per iteration: q = W_q LN(slots); attn = softmax_over_slots(scale q k^T) + eps;
+ *                  attn /= sum_over_tokens; upd = attn v      (one CTA per frame streams k, v once)
+ *                  slots = GRUCell(upd, slots); slots += W2 ReLU(W1 LN(slots) + b1) + b2
+ * X: (B, tokens, dim) fp32, prev_slots: (B, slots, dim) fp32  ->  out_slots (B, slots, dim) fp32,
+ * out_attn (B, slots, tokens) fp32 = the last iteration's normalised attention (may be NULL). */
+typedef struct {
+  int32_t slots;   /* 4  */
+  int32_t dim;     /* 384 (multiple of 64, <= 512) */
+  int32_t tokens;  /* 196 */
+  int32_t iters;   /* slots_iter_num */
+} rlsb_slot_cfg;
+
+typedef struct {
+  const float* inputs_norm_g; const float* inputs_norm_b;   /* inputs_norm   (dim)            */
+  const float* inputs_proj_w;                               /* inputs_proj   (2 dim, dim)     */
+  const float* slots_norm_g;  const float* slots_norm_b;    /* slots_norm    (dim)            */
+  const float* slots_proj_w;                                /* slots_proj    (dim, dim)       */
+  const float* gru_w_ih; const float* gru_w_hh;             /* slots_reccur  (3 dim, dim)     */
+  const float* gru_b_ih; const float* gru_b_hh;             /*               (3 dim)          */
+  const float* slots_norm2_g; const float* slots_norm2_b;   /* slots_norm_2  (dim)            */
+  const float* mlp_w1; const float* mlp_b1;                 /* slots_proj_2.0 (4 dim, dim)    */
+  const float* mlp_w2; const float* mlp_b2;                 /* slots_proj_2.2 (dim, 4 dim)    */
+} rlsb_slot_params;
+
+size_t rlsb_slot_attention_packed_bytes(const rlsb_slot_cfg* cfg);
+size_t rlsb_slot_attention_workspace_bytes(const rlsb_slot_cfg* cfg, int64_t B);
+int rlsb_slot_attention_pack(const rlsb_slot_cfg* cfg, const rlsb_slot_params* params, void* packed,
+                             void* stream);
+int rlsb_slot_attention_fwd(const rlsb_slot_cfg* cfg, const void* packed, int64_t B, const float* X,
+                            const float* prev_slots, float* out_slots, float* out_attn,
+                            void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

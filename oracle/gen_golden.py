@@ -9,6 +9,8 @@ Fixtures
                               by one (a dummy v_0 is prepended) and gamma is folded into ds.  Each
                               expected vector is the literal from the reference test AND is
                               re-checked here against the reference's ImaginativeCritic._lambda_return.
+  slot_attention.npz          SlotAttention.forward of the reference (vision/slot_attention.py:52-77),
+                              4 slots x 384, 196 tokens, 2 iterations, explicit prev_slots.
   imagine_<case>.npz          DreamerV2.imagine_trajectory (dreamer_v2.py:68-96) outputs, the
                               target-critic values, lambda-returns (ac.py:64-66), cumprod weights
                               (dreamer_v2.py:192-197) and the critic / actor losses
@@ -121,10 +123,37 @@ def run_case(name, case):
     print(f"imagine_{name}.npz written:", {k: getattr(v, 'shape', None) for k, v in out.items() if k != 'meta'})
 
 
+SLOT_CASE = dict(B=3, tokens=196, dim=384, slots=4, iters=2, param_seed=41, input_seed=42)
+
+
+def slot_inputs(case=SLOT_CASE):
+    g = torch.Generator().manual_seed(case["input_seed"])
+    X = torch.randn(case["B"], case["tokens"], case["dim"], generator=g)
+    prev = torch.randn(case["B"], case["slots"], case["dim"], generator=g)
+    return X, prev
+
+
+def run_slot_attention():
+    """SlotAttention.forward of the reference (vision/slot_attention.py:52-77) with explicit prev_slots."""
+    rh._import_reference()
+    from rl_sandbox.vision.slot_attention import SlotAttention
+    c = SLOT_CASE
+    sd = orc.make_slot_params(c["param_seed"], c["dim"], c["slots"])
+    mod = SlotAttention(c["slots"], c["dim"], c["iters"], use_prev_slots=False)
+    mod.load_state_dict(sd, strict=True)
+    X, prev = slot_inputs()
+    with torch.no_grad():
+        out = mod(X, prev)
+    np.savez_compressed(OUT / "slot_attention.npz", slots=out.numpy(), attn=mod.last_attention.numpy(),
+                        meta=json.dumps(c))
+    print("slot_attention.npz written:", out.shape, mod.last_attention.shape)
+
+
 def main():
     assert rh.available(), "reference checkout not found"
     OUT.mkdir(parents=True, exist_ok=True)
     known_answers()
+    run_slot_attention()
     for name, case in CASES.items():
         run_case(name, case)
 

@@ -390,3 +390,56 @@ class HotPathCPU:
             z = (torch.nn.functional.one_hot(idx, 32).float() + probs - probs.detach()).view(N, 1024)
             out["determ"].append(h); out["stoch"].append(z); out["actions"].append(a)
         return {k: torch.stack(v) for k, v in out.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 oracle: SlotAttention.forward, rl_sandbox/vision/slot_attention.py:52-77 (explicit prev_slots)
+# ------------------------------------------------------------------------------------------------
+def slot_attention(X, slots, sd, n_iter, bf16=False, prefix=""):
+    """X (B,T,dim), slots (B,K,dim); sd holds the reference's parameter names.  Returns (slots, attn).
+    bf16=True rounds the operands of the contractions that the CUDA path runs on tensor cores
+    (k/v projection, q, GRU, MLP) and stores k, v in bf16, like the kernel."""
+    g = lambda k: sd[prefix + k]
+    dim = X.shape[-1]
+    B, K = slots.shape[0], slots.shape[1]
+    ln = lambda x, n: layer_norm(x, g(n + ".weight"), g(n + ".bias"))
+    kv = linear(ln(X, "inputs_norm"), g("inputs_proj.weight"), None, bf16)
+    if bf16:
+        kv = _r(kv, True)
+    k, v = kv.chunk(2, -1)
+    attn = None
+    for _ in range(n_iter):
+        prev = slots
+        q = linear(ln(slots, "slots_norm"), g("slots_proj.weight"), None, bf16)
+        logits = dim ** -0.5 * torch.einsum("bik,bjk->bij", q, k)
+        attn = torch.softmax(logits, dim=1) + 1e-8                      # softmax over SLOTS
+        attn = attn / attn.sum(-1, keepdim=True)                         # renormalise over tokens
+        upd = torch.einsum("bjd,bij->bid", v, attn).reshape(B * K, dim)
+        h = prev.reshape(B * K, dim)
+        gi = linear(upd, g("slots_reccur.weight_ih"), g("slots_reccur.bias_ih"), bf16)
+        gh = linear(h, g("slots_reccur.weight_hh"), g("slots_reccur.bias_hh"), bf16)
+        ir, iz, in_ = gi.chunk(3, -1)
+        hr, hz, hn = gh.chunk(3, -1)
+        r, z = torch.sigmoid(ir + hr), torch.sigmoid(iz + hz)
+        n = torch.tanh(in_ + r * hn)
+        s = ((1 - z) * n + z * h).reshape(B, K, dim)
+        hid = torch.relu(linear(ln(s, "slots_norm_2"), g("slots_proj_2.0.weight"), g("slots_proj_2.0.bias"), bf16))
+        slots = s + linear(hid, g("slots_proj_2.2.weight"), g("slots_proj_2.2.bias"), bf16)
+    return slots, attn
+
+
+def make_slot_params(seed, dim=384, slots=4):
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name in ("inputs_norm", "slots_norm", "slots_norm_2"):
+        sd[name + ".weight"] = 1 + 0.1 * torch.randn(dim, generator=gen)
+        sd[name + ".bias"] = 0.1 * torch.randn(dim, generator=gen)
+    sd["inputs_proj.weight"], _ = _lin(gen, 2 * dim, dim)
+    sd["slots_proj.weight"], _ = _lin(gen, dim, dim)
+    sd["slots_reccur.weight_ih"], sd["slots_reccur.bias_ih"] = _lin(gen, 3 * dim, dim)
+    sd["slots_reccur.weight_hh"], sd["slots_reccur.bias_hh"] = _lin(gen, 3 * dim, dim)
+    sd["slots_proj_2.0.weight"], sd["slots_proj_2.0.bias"] = _lin(gen, 4 * dim, dim)
+    sd["slots_proj_2.2.weight"], sd["slots_proj_2.2.bias"] = _lin(gen, dim, 4 * dim)
+    sd["slots_mu"] = torch.randn(1, slots, dim, generator=gen)
+    sd["slots_logsigma"] = 0.1 * torch.randn(1, slots, dim, generator=gen)
+    return sd

@@ -49,6 +49,17 @@ class ImagineOut(C.Structure):
         "actor_raw")]
 
 
+class SlotCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("slots", "dim", "tokens", "iters")]
+
+
+class SlotParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "inputs_norm_g", "inputs_norm_b", "inputs_proj_w", "slots_norm_g", "slots_norm_b", "slots_proj_w",
+        "gru_w_ih", "gru_w_hh", "gru_b_ih", "gru_b_hh", "slots_norm2_g", "slots_norm2_b",
+        "mlp_w1", "mlp_b1", "mlp_w2", "mlp_b2")]
+
+
 _lib = None
 
 
@@ -82,15 +93,16 @@ def load() -> C.CDLL:
         "rlsb_imagine_fwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, vp, vp, vp, C.POINTER(Noise),
                                        C.POINTER(ImagineOut), vp, vp]),
     }
-    optional = {
-        "rlsb_slot_attention_workspace_bytes", "rlsb_slot_attention_packed_bytes",
-        "rlsb_slot_attention_pack", "rlsb_slot_attention_fwd",
-    }
+    sig.update({
+        "rlsb_slot_attention_packed_bytes": (sz, [C.POINTER(SlotCfg)]),
+        "rlsb_slot_attention_workspace_bytes": (sz, [C.POINTER(SlotCfg), i64]),
+        "rlsb_slot_attention_pack": (C.c_int, [C.POINTER(SlotCfg), C.POINTER(SlotParams), vp, vp]),
+        "rlsb_slot_attention_fwd": (C.c_int, [C.POINTER(SlotCfg), vp, i64, vp, vp, vp, vp, vp, vp]),
+    })
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    lib._rlsb_optional = optional
     if lib.rlsb_abi_version() != 1:
         raise RlsbError("librlsb.so ABI version mismatch; rebuild")
     _lib = lib

@@ -365,7 +365,7 @@ int g_num_sms = 0;
 int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   if (p.RB <= 0 || p.RB > 512 || (p.RB % 32) != 0) return -1;
   if (p.n_seg < 1 || p.n_seg > kMaxSeg) return -2;
-  if (epilogue == EPI_LN_ACT && p.NB != 1) return -3;
+  if (epilogue == EPI_LN_ACT && p.NB != 1 && p.ln_gamma != nullptr) return -3;  // LayerNorm needs the whole row
   if (p.M <= 0 || p.m_tiles != (p.M + kTileM - 1) / kTileM) return -4;
   if (epilogue == EPI_LN_ACT && ((p.out_kpad % 64) != 0 || p.out_kpad < p.N)) return -5;
   if (g_num_sms == 0) {

@@ -122,14 +122,10 @@ __global__ void ln_act_kernel(const LnActArgs a) {
     const int c0 = chunk << 3;
     float mean = 0.f, rstd = 1.f;
     const bool row_ok = m < a.M;
-    if (row_ok && a.gamma) row_stats_warp(a.stats, a.NB, a.m_pad, m, a.N, a.eps, mean, rstd);
-    if (chunk >= chunks_per_row) continue;
-    float y[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] = 0.f;
-    if (row_ok && c0 < a.N) {
+    const bool act = row_ok && chunk < chunks_per_row && c0 < a.N;
+    float v[8];
+    if (act) {
       const float* src = a.scratch + static_cast<size_t>(m) * a.ld + c0;
-      float v[8];
       if (c0 + 8 <= a.N && (a.ld & 3) == 0) {
         const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
         v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
@@ -137,6 +133,13 @@ __global__ void ln_act_kernel(const LnActArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (c0 + j < a.N) ? src[j] : 0.f;
       }
+    }
+    if (row_ok && a.gamma) row_stats_warp(a.stats, a.NB, a.m_pad, m, a.N, a.eps, mean, rstd);
+    if (chunk >= chunks_per_row) continue;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = 0.f;
+    if (act) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (c0 + j < a.N) {
@@ -195,16 +198,11 @@ __global__ void gru_gate_kernel(const GruArgs a) {
     const int chunk = static_cast<int>(wi - static_cast<long long>(m) * gpr) * 32 + lane;
     const int c0 = chunk << 3;
     const bool row_ok = m < a.M;
-    float mean = 0.f, rstd = 1.f;
-    if (row_ok) row_stats_warp(a.stats, a.NB, a.m_pad, m, 3 * D, a.eps, mean, rstd);
-    if (chunk >= chunks_per_row) continue;
-    float y[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] = 0.f;
-    if (row_ok && c0 < D) {
-      const int valid = min(8, D - c0);
+    const bool act = row_ok && chunk < chunks_per_row && c0 < D;
+    const int valid = act ? min(8, D - c0) : 0;
+    float pr[8], pc[8], pu[8], hp[8], gr[8], gc[8], gu[8], br[8], bc[8], bu[8];
+    if (act) {  // all loads in flight before the shuffle-synchronised statistics
       const float* src = a.scratch + static_cast<size_t>(m) * a.ld + c0;
-      float pr[8], pc[8], pu[8], hp[8], gr[8], gc[8], gu[8], br[8], bc[8], bu[8];
       load8(src, vec, valid, pr);
       load8(src + D, vec, valid, pc);
       load8(src + 2 * D, vec, valid, pu);
@@ -215,6 +213,14 @@ __global__ void gru_gate_kernel(const GruArgs a) {
       load8(a.beta + c0, vec, valid, br);
       load8(a.beta + D + c0, vec, valid, bc);
       load8(a.beta + 2 * D + c0, vec, valid, bu);
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (row_ok) row_stats_warp(a.stats, a.NB, a.m_pad, m, 3 * D, a.eps, mean, rstd);
+    if (chunk >= chunks_per_row) continue;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = 0.f;
+    if (act) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (j < valid) {

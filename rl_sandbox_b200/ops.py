@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ImagineCfg, ImagineOut, ImagineParams, MlpParams, Noise, check
+from ._lib import ImagineCfg, ImagineOut, ImagineParams, MlpParams, Noise, SlotCfg, SlotParams, check
 
 
 def _stream() -> int:
@@ -329,3 +329,57 @@ class ImaginationEngine:
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K3
+# ------------------------------------------------------------------------------------------------
+class SlotAttentionEngine:
+    """Packed weights + workspace of K3 (SlotAttention.forward, vision/slot_attention.py:52-77)."""
+
+    KEYS = {"inputs_norm_g": "inputs_norm.weight", "inputs_norm_b": "inputs_norm.bias",
+            "inputs_proj_w": "inputs_proj.weight", "slots_norm_g": "slots_norm.weight",
+            "slots_norm_b": "slots_norm.bias", "slots_proj_w": "slots_proj.weight",
+            "gru_w_ih": "slots_reccur.weight_ih", "gru_w_hh": "slots_reccur.weight_hh",
+            "gru_b_ih": "slots_reccur.bias_ih", "gru_b_hh": "slots_reccur.bias_hh",
+            "slots_norm2_g": "slots_norm_2.weight", "slots_norm2_b": "slots_norm_2.bias",
+            "mlp_w1": "slots_proj_2.0.weight", "mlp_b1": "slots_proj_2.0.bias",
+            "mlp_w2": "slots_proj_2.2.weight", "mlp_b2": "slots_proj_2.2.bias"}
+
+    def __init__(self, slots: int, dim: int, tokens: int, iters: int, device="cuda"):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.cfg = SlotCfg(slots, dim, tokens, iters)
+        self.slots, self.dim, self.tokens, self.iters = slots, dim, tokens, iters
+        self.device = torch.device(device)
+        nbytes = self.lib.rlsb_slot_attention_packed_bytes(C.byref(self.cfg))
+        if nbytes == 0:
+            raise _lib.RlsbError(f"unsupported slot-attention config slots={slots} dim={dim} tokens={tokens}")
+        self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+        self._ws, self._ws_b = None, 0
+
+    def pack(self, sd: dict, prefix: str = "") -> None:
+        p, keep = SlotParams(), []
+        for field, key in self.KEYS.items():
+            t = _f32c(sd[prefix + key])
+            keep.append(t)
+            setattr(p, field, t.data_ptr())
+        check(self.lib.rlsb_slot_attention_pack(C.byref(self.cfg), C.byref(p), self.packed.data_ptr(), _stream()),
+              "rlsb_slot_attention_pack")
+        self._keep = keep
+
+    def forward(self, X: torch.Tensor, prev_slots: torch.Tensor, want_attn: bool = True):
+        X, prev_slots = _f32c(X), _f32c(prev_slots)
+        B = X.shape[0]
+        if X.shape[1:] != (self.tokens, self.dim) or prev_slots.shape != (B, self.slots, self.dim):
+            raise _lib.RlsbError(f"slot attention: X {tuple(X.shape)} prev_slots {tuple(prev_slots.shape)}")
+        if self._ws is None or self._ws_b < B:
+            self._ws = torch.zeros(self.lib.rlsb_slot_attention_workspace_bytes(C.byref(self.cfg), B),
+                                   device=self.device, dtype=torch.uint8)
+            self._ws_b = B
+        out = torch.empty_like(prev_slots)
+        attn = torch.empty((B, self.slots, self.tokens), device=X.device, dtype=torch.float32) if want_attn else None
+        check(self.lib.rlsb_slot_attention_fwd(C.byref(self.cfg), self.packed.data_ptr(), B, X.data_ptr(),
+                                               prev_slots.data_ptr(), out.data_ptr(), _ptr(attn), self._ws.data_ptr(),
+                                               _stream()), "rlsb_slot_attention_fwd")
+        return out, attn

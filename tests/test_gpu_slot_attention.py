@@ -1,0 +1,86 @@
+"""GPU parity tests of K3 (slot attention) through the C ABI and through the module boundary."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_port as orc
+from oracle.gen_golden import SLOT_CASE, slot_inputs
+from tests._golden import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_rms(x, r, tag):
+    x, r = x.double().cpu(), r.double().cpu()
+    e = ((x - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt()).item()
+    print(f"[parity] {tag}: rel-RMS error {e:.3e} over {r.numel()} values")
+    return e
+
+
+def test_k3_vs_reference_golden(cuda):
+    from rl_sandbox_b200 import ops
+    c = SLOT_CASE
+    z = np.load(GOLDEN / "slot_attention.npz")
+    sd = orc.make_slot_params(c["param_seed"], c["dim"], c["slots"])
+    X, prev = slot_inputs()
+    eng = ops.SlotAttentionEngine(c["slots"], c["dim"], c["tokens"], c["iters"])
+    eng.pack({k: v.cuda() for k, v in sd.items()})
+    out, attn = eng.forward(X.cuda(), prev.cuda())
+    # vs the reference's own tensors (fp32): bf16 contractions, 2 iterations x (q, GRU, MLP) deep
+    assert rel_rms(out, torch.from_numpy(z["slots"]), "slot_attention.slots vs reference") < 1e-2
+    assert rel_rms(attn, torch.from_numpy(z["attn"]), "slot_attention.attn vs reference") < 1e-2
+    # vs the oracle evaluated with the kernel's operand rounding
+    o2, a2 = orc.slot_attention(X, prev, sd, c["iters"], bf16=True)
+    assert rel_rms(out, o2, "slot_attention.slots vs bf16 oracle") < 2e-3
+    assert rel_rms(attn, a2, "slot_attention.attn vs bf16 oracle") < 2e-3
+    # attention is a distribution over tokens for every slot
+    torch.testing.assert_close(attn.sum(-1).cpu(), torch.ones(c["B"], c["slots"]), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,tokens,slots,iters", [(1, 196, 4, 2), (5, 64, 4, 1), (800, 196, 4, 2), (7, 50, 6, 3)])
+def test_k3_shapes_vs_bf16_oracle(cuda, B, tokens, slots, iters):
+    from rl_sandbox_b200 import ops
+    dim = 384
+    sd = orc.make_slot_params(B + tokens, dim, slots)
+    g = torch.Generator().manual_seed(B)
+    X, prev = torch.randn(B, tokens, dim, generator=g), torch.randn(B, slots, dim, generator=g)
+    eng = ops.SlotAttentionEngine(slots, dim, tokens, iters)
+    eng.pack({k: v.cuda() for k, v in sd.items()})
+    out, attn = eng.forward(X.cuda(), prev.cuda())
+    n = min(B, 16)   # the CPU oracle on a subset of frames keeps the test fast
+    o2, a2 = orc.slot_attention(X[:n], prev[:n], sd, iters, bf16=True)
+    assert rel_rms(out[:n], o2, f"slots B={B} T={tokens} K={slots} it={iters}") < 3e-3
+    assert rel_rms(attn[:n], a2, "attn") < 3e-3
+    assert torch.isfinite(out).all()
+    # frames are independent: a frame's result does not depend on its batch neighbours
+    if B > 1:
+        o1, _ = eng.forward(X[1:2].cuda().contiguous(), prev[1:2].cuda().contiguous())
+        assert rel_rms(o1, out[1:2], "frame independence") < 1e-5
+
+
+def test_module_boundary_dispatches_to_kernel(cuda):
+    """rl_sandbox.vision.slot_attention.SlotAttention(num_slots, n_dim, n_iter, use_prev_slots).forward(X, prev)."""
+    from rl_sandbox.vision.slot_attention import PositionalEmbedding, SlotAttention
+    from rl_sandbox_b200 import _lib
+    c = SLOT_CASE
+    mod = SlotAttention(c["slots"], c["dim"], c["iters"], use_prev_slots=False).cuda()
+    mod.load_state_dict(orc.make_slot_params(c["param_seed"], c["dim"], c["slots"]))
+    X, prev = slot_inputs()
+    before = _lib.load().rlsb_launch_count(0)
+    with torch.no_grad():
+        out = mod(X.cuda(), prev.cuda())
+    assert _lib.load().rlsb_launch_count(0) > before, "forward did not run the librlsb kernels"
+    z = np.load(GOLDEN / "slot_attention.npz")
+    assert rel_rms(out, torch.from_numpy(z["slots"]), "module vs reference") < 1e-2
+    assert mod.last_attention.shape == (c["B"], c["slots"], c["tokens"])
+    # training-time (grad) evaluation agrees with the kernel path
+    out_g = mod(X.cuda().requires_grad_(), prev.cuda())
+    assert out_g.requires_grad and rel_rms(out_g.detach(), out, "autograd path vs kernel path") < 1e-2
+    # prev_slots=None draws the initial slots like the reference (slot_attention.py:46-50)
+    with torch.no_grad():
+        o = mod(X.cuda(), None)
+    assert o.shape == (c["B"], c["slots"], c["dim"]) and mod.prev_slots is not None
+    pe = PositionalEmbedding(c["dim"], (14, 14)).cuda()
+    assert pe(torch.zeros(2, c["dim"], 14, 14, device="cuda")).shape == (2, c["dim"], 14, 14)

@@ -93,3 +93,18 @@ def test_oracle_port_matches_reference_rollout(name):
     torch.testing.assert_close(losses["w"], gold["w"], rtol=0, atol=0)
     for k in ("loss_critic", "loss_actor", "loss_actor_reinforce", "loss_actor_dynamics_backprop", "loss_actor_entropy"):
         torch.testing.assert_close(losses[k].float(), gold[k], rtol=1e-4, atol=1e-6, msg=lambda s: f"{k}: {s}")
+
+
+def test_oracle_slot_attention_matches_reference():
+    """oracle_port.slot_attention vs the reference's SlotAttention.forward (tests/golden/slot_attention.npz)."""
+    import json
+    from tests._golden import GOLDEN
+    from oracle.gen_golden import SLOT_CASE, slot_inputs
+    z = np.load(GOLDEN / "slot_attention.npz")
+    assert json.loads(str(z["meta"])) == SLOT_CASE
+    sd = orc.make_slot_params(SLOT_CASE["param_seed"], SLOT_CASE["dim"], SLOT_CASE["slots"])
+    X, prev = slot_inputs()
+    out, attn = orc.slot_attention(X, prev, sd, SLOT_CASE["iters"])
+    torch.testing.assert_close(out, torch.from_numpy(z["slots"]), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(attn, torch.from_numpy(z["attn"]), rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(attn.sum(-1), torch.ones(3, 4), rtol=1e-5, atol=1e-5)
