@@ -96,6 +96,10 @@ typedef struct {
   int32_t predict_discount; /* discount head present */
   int32_t with_critic;      /* also evaluate the target critic on every state */
   int32_t H;                /* horizon */
+  /* torch's Bernoulli(logits).mode is (p >= 0.5) with NaN where p == 0.5 exactly
+   * (world_model.py:137).  1 = reproduce that NaN (reference-exact), 0 = ties resolve to 1 —
+   * a single NaN discount poisons every parameter through the losses. */
+  int32_t discount_nan_on_tie;
 } rlsb_imagine_cfg;
 
 /* fp32 parameters in nn.Linear layout (weight = [out, in] row-major); NULL = absent.

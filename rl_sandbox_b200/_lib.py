@@ -23,7 +23,7 @@ class RlsbError(RuntimeError):
 class ImagineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "predict_discount",
-        "with_critic", "H")]
+        "with_critic", "H", "discount_nan_on_tie")]
 
 
 class MlpParams(C.Structure):

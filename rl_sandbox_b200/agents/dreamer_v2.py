@@ -70,6 +70,9 @@ class DreamerV2(RlAgent):
         self._noise_seed = 0x5EED    # Philox key; the step counter below is mixed in per rollout
         self._rollouts = 0
         self.metrics_samples = 128   # draws per element for the actor statistics (ac.py:137)
+        # torch's Bernoulli.mode yields NaN when p == 0.5 exactly (world_model.py:137); one such discount
+        # turns every parameter into NaN through the losses.  False = ties resolve to 1.
+        self.reference_exact_discount_nan = False
         self.last_rollout: t.Optional[dict] = None
         self.reset()
 
@@ -86,7 +89,7 @@ class DreamerV2(RlAgent):
             cfg = ops.ImagineConfig(D=wm.rssm_dim, A=self.actions_num, discrete=self.is_discrete,
                                     layer_norm=bool(wm.layer_norm), predict_discount=bool(wm.predict_discount),
                                     H=self.imagination_horizon, groups=wm.latent_dim, classes=wm.latent_classes,
-                                    with_critic=True)
+                                    with_critic=True, discount_nan_on_tie=self.reference_exact_discount_nan)
             self._engine = ops.ImaginationEngine(cfg, device=self.device)
         if self._packed_version != self._weights_version:
             self._engine.pack(self.world_model.state_dict(), self.actor.state_dict(), self.critic.state_dict())

@@ -372,7 +372,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     hf.head_out = head_out; hf.ldo = 32; hf.group_stride = static_cast<long long>(m_pad) * 32;
     hf.g_actor = P.g_actor; hf.g_reward = P.g_reward; hf.g_discount = P.g_discount; hf.g_critic = P.g_critic;
     hf.M = M; hf.m_pad = m_pad; hf.A = P.A; hf.discrete = cfg->discrete;
-    hf.first_step = (t == 0); hf.want_action = (t < H);
+    hf.first_step = (t == 0); hf.want_action = (t < H); hf.nan_on_tie = cfg->discount_nan_on_tie;
     hf.noise.explicit_noise = noise->action_noise ? noise->action_noise + static_cast<size_t>(t) * N * P.A : nullptr;
     hf.noise.ld = P.A; hf.noise.seed = noise->seed; hf.noise.step = static_cast<uint32_t>(t);
     hf.noise.row_offset = noise->row_offset;

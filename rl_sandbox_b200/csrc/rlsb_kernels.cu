@@ -382,7 +382,7 @@ __global__ void head_finish_kernel(const HeadFinishParams p) {
         // torch Bernoulli(logits).mode: (probs >= 0.5), NaN where probs == 0.5 (world_model.py:137)
         const float x = p.head_out[p.g_discount * p.group_stride + static_cast<long long>(m) * p.ldo];
         const float pr = sigmoidf_(x);
-        d = pr > 0.5f ? 1.0f : (pr == 0.5f ? __int_as_float(0x7fc00000) : 0.0f);
+        d = pr > 0.5f ? 1.0f : (pr == 0.5f ? (p.nan_on_tie ? __int_as_float(0x7fc00000) : 1.0f) : 0.0f);
       }
       p.discount_out[m] = d;
     }

@@ -56,6 +56,7 @@ struct HeadFinishParams {
   int M, m_pad, A;
   int discrete;
   int first_step;  // t == 0: discount := 1
+  int nan_on_tie;  // Bernoulli.mode NaN at p == 0.5 (reference-exact) vs tie -> 1
   int want_action; // t < H
   NoiseSpec noise;
   float* reward_out;    // [M]

@@ -212,10 +212,12 @@ class ImagineConfig:
     classes: int = 32
     hidden: int = 400
     with_critic: bool = True
+    discount_nan_on_tie: bool = True   # reference-exact Bernoulli.mode (NaN at p == 0.5)
 
     def to_c(self) -> ImagineCfg:
         return ImagineCfg(self.D, self.groups, self.classes, self.A, self.hidden, int(self.discrete),
-                          int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H)
+                          int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H,
+                          int(self.discount_nan_on_tie))
 
 
 def _mlp_params(sd: dict, prefix: str, keep: list) -> MlpParams:

@@ -23,8 +23,11 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_no_torch_types_in_abi():
+    import re
     hdr = (ROOT / "include" / "rlsb.h").read_text()
-    assert "torch" not in hdr.lower().replace("pytorch", "") and "at::" not in hdr
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)       # declarations only (comments cite the reference)
+    assert "torch" not in code.lower() and "at::" not in code and "Tensor" not in code
+    assert 'extern "C"' in code
 
 
 def test_sass_contains_blackwell_instructions():
@@ -48,8 +51,8 @@ def test_fails_loudly_without_device():
 def test_argument_errors_are_negative_codes():
     lib = _lib.load()
     assert lib.rlsb_lambda_return_fwd(None, None, None, 16, 8, 0.95, None, None, None, 0, None) < 0
-    cfg = _lib.ImagineCfg(1024, 32, 31, 17, 400, 1, 1, 1, 1, 15)   # classes != 32 -> unsupported
+    cfg = _lib.ImagineCfg(1024, 32, 31, 17, 400, 1, 1, 1, 1, 15, 1)   # classes != 32 -> unsupported
     assert lib.rlsb_imagine_packed_bytes(C.byref(cfg)) == 0
-    cfg = _lib.ImagineCfg(1024, 32, 32, 17, 400, 1, 1, 1, 1, 15)
+    cfg = _lib.ImagineCfg(1024, 32, 32, 17, 400, 1, 1, 1, 1, 15, 1)
     assert lib.rlsb_imagine_packed_bytes(C.byref(cfg)) > 20_000_000
     assert lib.rlsb_imagine_workspace_bytes(C.byref(cfg), 800) > 0

@@ -175,3 +175,27 @@ def test_ragged_sizes_and_single_row(ops, cuda):
                           predict_discount=False, latent_uniforms=lat, action_noise=act, bf16=True)
         assert rel_rms(out["determ"][1], ref["determ"][1]) < 1e-3
         assert torch.isfinite(out["determ"]).all()
+
+
+def test_bernoulli_mode_tie_semantics(ops, cuda):
+    """world_model.py:137: Bernoulli(logits).mode == (p >= .5), NaN where p == .5.  A discount head whose
+    output is exactly 0 (zero weights and bias in its last layer) hits the tie on every row."""
+    c = load_case("c2_long")
+    m = c["meta"]
+    wm = dict(c["wm"])
+    wm["discount_predictor.12.weight"] = torch.zeros_like(wm["discount_predictor.12.weight"])
+    wm["discount_predictor.12.bias"] = torch.zeros_like(wm["discount_predictor.12.bias"])
+    to = lambda sd: {k: v.to(cuda) for k, v in sd.items()}
+    for exact in (True, False):
+        cfg = ops.ImagineConfig(D=m["D"], A=m["A"], discrete=True, layer_norm=True, predict_discount=True, H=2,
+                                discount_nan_on_tie=exact)
+        eng = ops.ImaginationEngine(cfg)
+        eng.pack(to(wm), to(c["actor"]), to(c["critic"]))
+        out = eng.rollout(c["h0"].to(cuda), c["z0"].to(cuda), None, c["lat"][:2].to(cuda), c["act"][:2].to(cuda))
+        d = out["discounts"].cpu()
+        assert torch.equal(d[0], torch.ones(m["N"]))            # ts[0] is defined as 1, never the head
+        if exact:
+            assert torch.isnan(d[1:]).all()                      # == orc.bernoulli_mode(zeros)
+            assert torch.isnan(orc.bernoulli_mode(torch.zeros(3))).all()
+        else:
+            assert torch.equal(d[1:], torch.ones(2, m["N"]))
