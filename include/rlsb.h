@@ -32,6 +32,9 @@ int rlsb_check_device(void);
 const char* rlsb_error_string(int code);
 /* number of CUDA kernels this library has launched since load (or since the last reset != 0) */
 long long rlsb_launch_count(int reset);
+/* tuning: CTAs per thread-block cluster sharing one weight block via TMA multicast (1, 2 or 4;
+ * default 2, env RLSB_CLUSTER).  Returns the value in effect. */
+int rlsb_set_cluster_size(int cs);
 
 /* ---- K2: lambda-return + shifted-cumprod weights + advantage --------------------------------
  * replaces ImaginativeCritic._lambda_return (agents/dreamer/ac.py:52-62), the discount

@@ -32,6 +32,11 @@ extern "C" long long rlsb_launch_count(int reset) {
   return v;
 }
 
+extern "C" int rlsb_set_cluster_size(int cs) {
+  set_gemm_cluster_size(cs);
+  return gemm_cluster_size();
+}
+
 extern "C" int rlsb_check_device(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -13,6 +13,8 @@
 //
 // Replaces (reference): nn.Linear + nn.LayerNorm + nn.ELU chains in
 // agents/dreamer/rssm.py:136-152, agents/dreamer/common.py:58-75, utils/fc_nn.py:14-22.
+#include <cstdlib>
+
 #include "rlsb_gemm.cuh"
 #include "rlsb_count.cuh"
 #include "rlsb_ptx.cuh"
@@ -32,7 +34,7 @@ struct SmemCtl {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad;
-  float bias[2][kMaxRB];    // double-buffered per-tile epilogue parameters
+  alignas(16) float bias[2][kMaxRB];    // double-buffered per-tile epilogue parameters
   float gamma[2][kMaxRB];
   float beta[2][kMaxRB];
   float2 part[4][kTileM];   // per column-quarter partial (sum, sumsq) of each row
@@ -56,15 +58,18 @@ __device__ __forceinline__ void epi_bar(int id) {
 
 // work item -> (m_tile, g, nb).  The n-block index runs fastest so that the CTAs resident at any
 // moment share a handful of A tiles (L2 hits) while the whole weight matrix stays L2 resident.
-__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& gnb) {
+// With a cluster of `cs` CTAs, the CTAs of one cluster take `cs` consecutive M tiles of the SAME
+// (g, nb): they consume the same weight block, which is fetched once per cluster (multicast).
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int cs, int rank, int& m_tile, int& gnb) {
   const int per_m = p.G * p.NB;
-  m_tile = w / per_m;
-  gnb = w - m_tile * per_m;
+  const int m_super = w / per_m;
+  gnb = w - m_super * per_m;
+  m_tile = m_super * cs + rank;
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
+gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -79,14 +84,18 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
 
   int kt_total = 0;
   for (int s = 0; s < p.n_seg; ++s) kt_total += p.a_ktiles[s];
-  const int total_work = p.G * p.NB * p.m_tiles;
+  const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);   // (cluster-)work items
   const int buf_cols = (nbuf == 2) ? 256 : 512;
+  const int rank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = static_cast<int>(blockIdx.x) / cs;
+  const int num_clusters = static_cast<int>(gridDim.x) / cs;
+  const uint16_t cta_mask = static_cast<uint16_t>((1u << cs) - 1u);
 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(&ctl->full[s], 1);
-        mbar_init(&ctl->empty[s], 1);
+        mbar_init(&ctl->empty[s], static_cast<uint32_t>(cs));   // released by every CTA of the cluster
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&ctl->tmem_full[b], 1);
@@ -101,6 +110,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
@@ -108,9 +118,11 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const uint32_t b_slice = b_bytes / static_cast<uint32_t>(cs);
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
         int m_tile, gnb;
-        decode_work(p, w, m_tile, gnb);
+        decode_work(p, w, cs, rank, m_tile, gnb);
+        if (m_tile >= p.m_tiles) m_tile = p.m_tiles - 1;   // padding CTA of the last cluster: valid loads, no stores
         const int g = gnb / p.NB;
         const __nv_bfloat16* wsrc =
             p.W + static_cast<size_t>(gnb) * kt_total * (static_cast<size_t>(p.RB) * kTileK);
@@ -126,8 +138,15 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
             mbar_expect_tx(&ctl->full[stage], stage_bytes);
             bulk_g2s(sa, asrc + static_cast<size_t>(kt) * (kTileM * kTileK), a_bytes,
                      &ctl->full[stage]);
-            bulk_g2s(sb, wsrc + static_cast<size_t>(kt_glob) * (static_cast<size_t>(p.RB) * kTileK),
-                     b_bytes, &ctl->full[stage]);
+            const __nv_bfloat16* wtile = wsrc + static_cast<size_t>(kt_glob) * (static_cast<size_t>(p.RB) * kTileK);
+            if (cs == 1) {
+              bulk_g2s(sb, wtile, b_bytes, &ctl->full[stage]);
+            } else {
+              // this CTA fetches rows [rank*RB/cs, (rank+1)*RB/cs) of the block for the whole cluster
+              bulk_g2s_multicast(sb + static_cast<size_t>(rank) * b_slice,
+                                 reinterpret_cast<const uint8_t*>(wtile) + static_cast<size_t>(rank) * b_slice,
+                                 b_slice, &ctl->full[stage], cta_mask);
+            }
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
@@ -146,7 +165,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
         const int buf = (nbuf == 2) ? (it & 1) : 0;
         const uint32_t use = (nbuf == 2) ? static_cast<uint32_t>(it >> 1) : static_cast<uint32_t>(it);
         mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);
@@ -170,7 +189,9 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
               umma_bf16(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
                         bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
           }
-          umma_commit(&ctl->empty[stage]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in every CTA of the cluster: peers multicast into it) when these MMAs retire
+          if (cs == 1) umma_commit(&ctl->empty[stage]);
+          else umma_commit_multicast(&ctl->empty[stage], cta_mask);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -192,9 +213,10 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
     const int m_pad = p.m_tiles * kTileM;
     const int my_chunks = p.RB >> 5;  // (RB / 8) / 4
     int it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
       int m_tile, gnb;
-      decode_work(p, w, m_tile, gnb);
+      decode_work(p, w, cs, rank, m_tile, gnb);
+      const bool tile_ok = m_tile < p.m_tiles;   // false only for the padding CTA of the last cluster
       const int g = gnb / p.NB;
       const int nb = gnb - g * p.NB;
       const int buf = (nbuf == 2) ? (it & 1) : 0;
@@ -218,7 +240,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
       mbar_wait(&ctl->tmem_full[buf], use & 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * buf_cols) + lane_addr;
-      const int m = m_tile * kTileM + row;
+      const int m = tile_ok ? m_tile * kTileM + row : p.M + kTileM;   // padding tile: every row invalid
       const bool has_ln = (EPI == EPI_LN_ACT) && (p.ln_gamma != nullptr);
 
       // ---- pass 1: statistics (EPI_STATS / LayerNorm) and/or plain fp32 output ------------------
@@ -241,8 +263,14 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
             if (i0 + u < my_chunks) {
               const int c = (cq + 4 * (i0 + u)) * 8;
               float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[u][j]) + sbias[c + j];
+              {
+                const float4 b0 = *reinterpret_cast<const float4*>(sbias + c);
+                const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + 4);
+                v[0] = __uint_as_float(r[u][0]) + b0.x; v[1] = __uint_as_float(r[u][1]) + b0.y;
+                v[2] = __uint_as_float(r[u][2]) + b0.z; v[3] = __uint_as_float(r[u][3]) + b0.w;
+                v[4] = __uint_as_float(r[u][4]) + b1.x; v[5] = __uint_as_float(r[u][5]) + b1.y;
+                v[6] = __uint_as_float(r[u][6]) + b1.z; v[7] = __uint_as_float(r[u][7]) + b1.w;
+              }
               if (c + 8 <= n_valid) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -280,7 +308,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
           const float tsq = (a0.y + a1.y) + (a2.y + a3.y);
           if (EPI == EPI_STATS) {
             // per-(row, n-block) partials (sum, sum of squares); the consumer combines the blocks
-            if (cq == 0)
+            if (cq == 0 && tile_ok)
               reinterpret_cast<float2*>(p.stats)[static_cast<size_t>(gnb) * m_pad + m] = make_float2(tsum, tsq);
           } else {
             const float inv_n = 1.0f / static_cast<float>(n_valid);
@@ -292,9 +320,10 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
       }
 
       // ---- pass 2 (EPI_LN_ACT): normalise, activate, write the packed bf16 operand image --------
-      if (EPI == EPI_LN_ACT) {
+      if (EPI == EPI_LN_ACT && tile_ok) {
         const float* sgam = ctl->gamma[pb];
         const float* sbet = ctl->beta[pb];
+        const float nmr = -mean * rstd;
         __nv_bfloat16* obase = p.out_bf16 + static_cast<size_t>(g) * p.out_bf16_group_stride;
         const int out_ktiles = p.out_kpad >> 6;
         const int out_chunks = (p.out_kpad - col0 < p.RB ? p.out_kpad - col0 : p.RB) >> 3;
@@ -311,15 +340,37 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
             if (i0 + u < my_chunks && ch < out_chunks) {
               const int c = ch * 8;
               float y[8];
+              if (c + 8 <= n_valid) {
+                const float4 b0 = *reinterpret_cast<const float4*>(sbias + c);
+                const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                if (has_ln) {
+                  const float4 g0 = *reinterpret_cast<const float4*>(sgam + c);
+                  const float4 g1 = *reinterpret_cast<const float4*>(sgam + c + 4);
+                  const float4 e0 = *reinterpret_cast<const float4*>(sbet + c);
+                  const float4 e1 = *reinterpret_cast<const float4*>(sbet + c + 4);
+                  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                  const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float v = 0.f;
-                if (c + j < n_valid) {
-                  v = __uint_as_float(r[u][j]) + sbias[c + j];
-                  if (has_ln) v = (v - mean) * rstd * sgam[c + j] + sbet[c + j];
-                  v = act_apply(v, p.act);
+                  for (int j = 0; j < 8; ++j) {
+                    const float xh = fmaf(__uint_as_float(r[u][j]) + bb[j], rstd, nmr);  // (x - mean) * rstd
+                    y[j] = act_apply(fmaf(xh, gg[j], ee[j]), p.act);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[j] = act_apply(__uint_as_float(r[u][j]) + bb[j], p.act);
                 }
-                y[j] = v;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float v = 0.f;
+                  if (c + j < n_valid) {
+                    v = __uint_as_float(r[u][j]) + sbias[c + j];
+                    if (has_ln) v = fmaf(fmaf(v, rstd, nmr), sgam[c + j], sbet[c + j]);
+                    v = act_apply(v, p.act);
+                  }
+                  y[j] = v;
+                }
               }
               const int oc = col0 + c;  // output column
               __nv_bfloat16* trow = obase + (static_cast<size_t>(m_tile) * out_ktiles + (oc >> 6)) *
@@ -352,6 +403,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // nobody leaves while a peer may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -359,8 +411,14 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf) {
 }
 
 int g_num_sms = 0;
+int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
 
 }  // namespace
+
+void set_gemm_cluster_size(int cs) {
+  if (cs == 1 || cs == 2 || cs == 4) g_cluster_size = cs;
+}
+int gemm_cluster_size() { return g_cluster_size; }
 
 int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   if (p.RB <= 0 || p.RB > 512 || (p.RB % 32) != 0) return -1;
@@ -374,6 +432,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return static_cast<int>(e);
+    if (const char* env = getenv("RLSB_CLUSTER")) set_gemm_cluster_size(atoi(env));
   }
   const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2;
   const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256;
@@ -383,10 +442,27 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   if (stages < 2) return -6;
   const int nbuf = p.RB <= 256 ? 2 : 1;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + sizeof(SmemCtl) + 1024;
-  const int total_work = p.G * p.NB * p.m_tiles;
-  const int grid = total_work < g_num_sms ? total_work : g_num_sms;
+  // cluster size along M: CTAs of a cluster share the weight block (TMA multicast)
+  int cs = g_cluster_size;
+  while (cs > 1 && ((p.RB / cs) % 8 != 0 || p.m_tiles < cs)) cs >>= 1;
+  const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
+  int clusters = g_num_sms / cs;
+  if (total_work < clusters) clusters = total_work;
+  const int grid = clusters * cs;
 
   cudaError_t e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cs);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
 #define RLSB_LAUNCH(EPI)                                                                         \
   do {                                                                                           \
     static bool attr_done = false;                                                               \
@@ -396,7 +472,8 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
       if (e != cudaSuccess) return static_cast<int>(e);                                          \
       attr_done = true;                                                                          \
     }                                                                                            \
-    gemm_kernel<EPI><<<grid, kGemmThreads, smem, stream>>>(p, stages, nbuf);                     \
+    e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI>, p, stages, nbuf, cs);                         \
+    if (e != cudaSuccess) return static_cast<int>(e);                                            \
   } while (0)
   switch (epilogue) {
     case EPI_PLAIN: RLSB_LAUNCH(EPI_PLAIN); break;

@@ -54,4 +54,8 @@ struct GemmParams {
 // Launch on `stream`; returns cudaError_t as int (0 = ok) or a negative argument error.
 int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream);
 
+// CTAs per thread-block cluster that share one weight block through TMA multicast (1, 2 or 4)
+void set_gemm_cluster_size(int cs);
+int gemm_cluster_size();
+
 }  // namespace rlsb

@@ -80,6 +80,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// multicast variant: the bytes land at the same CTA-relative offset in every CTA of `cta_mask`
+// and complete_tx is signalled on each destination CTA's mbarrier at the same offset.
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                   uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
 // shared -> global bulk store (bulk-group completion)
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
@@ -136,6 +146,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of `cta_mask` (cluster multicast)
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // TMEM -> registers: 32 lanes x 32 consecutive 32-bit columns (thread i gets lane base+i).

@@ -130,9 +130,20 @@ def test_pack_roundtrip(ops, cuda):
         assert torch.equal(ops.unpack_rows(ops.pack_rows(x), rows, cols), x.bfloat16().float())
 
 
+@pytest.fixture(params=[1, 2, 4], ids=lambda c: f"cluster{c}")
+def cluster(request):
+    """CTAs per cluster sharing a weight block through TMA multicast."""
+    from rl_sandbox_b200 import _lib
+    lib = _lib.load()
+    assert lib.rlsb_set_cluster_size(request.param) == request.param
+    yield request.param
+    lib.rlsb_set_cluster_size(2)
+
+
 @pytest.mark.parametrize("M,K,N", [(128, 64, 32), (300, 128, 64), (300, 448, 400), (1000, 2048, 3072),
-                                   (5000, 1088, 1024), (777, 256, 600), (1, 64, 17), (129, 1280, 400)])
-def test_tcgen05_gemm_vs_fp32_reference(ops, cuda, M, K, N):
+                                   (5000, 1088, 1024), (777, 256, 600), (1, 64, 17), (129, 1280, 400),
+                                   (40000, 448, 400)])
+def test_tcgen05_gemm_vs_fp32_reference(ops, cuda, cluster, M, K, N):
     """acc in fp32 on bf16-rounded operands: compare with torch fp32 matmul on the same rounded operands."""
     g = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=g).to(cuda)
@@ -153,8 +164,8 @@ def test_tcgen05_gemm_vs_fp32_reference(ops, cuda, M, K, N):
 
 @pytest.mark.parametrize("M,K,N,use_ln,act", [(300, 448, 400, True, 1), (1000, 2048, 400, True, 1),
                                               (300, 256, 200, False, 1), (260, 448, 17, False, 0),
-                                              (130, 384, 384, True, 2)])
-def test_tcgen05_gemm_layernorm_act_epilogue(ops, cuda, M, K, N, use_ln, act):
+                                              (130, 384, 384, True, 2), (33000, 448, 400, True, 1)])
+def test_tcgen05_gemm_layernorm_act_epilogue(ops, cuda, cluster, M, K, N, use_ln, act):
     g = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=g).to(cuda)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
