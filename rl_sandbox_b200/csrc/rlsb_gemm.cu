@@ -40,17 +40,87 @@ struct SmemCtl {
   float2 part[4][kTileM];   // per column-quarter partial (sum, sumsq) of each row
 };
 
-__device__ __forceinline__ float act_apply(float x, int act) {
-  // ELU as the reference evaluates it on the CPU: exp(x) - 1 for x <= 0 (ATen elu kernel)
-  if (act == ACT_ELU) return x > 0.f ? x : __expf(x) - 1.0f;
-  if (act == ACT_RELU) return fmaxf(x, 0.f);
-  return x;
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int ACT>
+__device__ __forceinline__ float act_apply(float x) {
+  // ELU as the reference evaluates it on the CPU: exp(x) - 1 for x <= 0 (ATen elu kernel)
+  if (ACT == ACT_ELU) return x > 0.f ? x : ex2_approx(x * 1.4426950408889634f) - 1.0f;
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  return x;
+}
+
+// pass 2 of the full-row epilogue for one 8-column chunk: bias, [LayerNorm affine], activation,
+// bf16 pack, one 16-byte store into the packed operand image.
+template <int ACT, bool LN>
+__device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int n_valid, uint32_t s_bias,
+                                             uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
+                                             __nv_bfloat16* dst) {
+  float y[8];
+  if (c >= n_valid) {  // padding columns of the block
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = 0.f;
+  } else {
+    const float4 b0 = lds128(s_bias + 4u * c), b1 = lds128(s_bias + 4u * c + 16u);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    if (LN) {
+      const float4 g0 = lds128(s_gam + 4u * c), g1 = lds128(s_gam + 4u * c + 16u);
+      const float4 e0 = lds128(s_bet + 4u * c), e1 = lds128(s_bet + 4u * c + 16u);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(__uint_as_float(r[j]) + bb[j], rstd, nmr);  // (x - mean) * rstd
+        y[j] = act_apply<ACT>(fmaf(xh, gg[j], ee[j]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = act_apply<ACT>(__uint_as_float(r[j]) + bb[j]);
+    }
+    if (c + 8 > n_valid) {  // partial chunk (N not a multiple of 8)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j >= n_valid) y[j] = 0.f;
+    }
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                              pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+}
+
+template <int ACT, bool LN>
+__device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chunks, int n_valid, int col0, int row,
+                                             uint32_t s_bias, uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
+                                             __nv_bfloat16* obase) {
+  for (int i0 = 0; i0 < my_chunks; i0 += 2) {
+    uint32_t r0[8], r1[8];
+    const int c0 = (cq + 4 * i0) * 8, c1 = c0 + 32;
+    const bool two = i0 + 1 < my_chunks;
+    tmem_ld8(tmem_d + static_cast<uint32_t>(c0), r0);
+    if (two) tmem_ld8(tmem_d + static_cast<uint32_t>(c1), r1);
+    tmem_ld_wait();
+    {
+      const int oc = col0 + c0;
+      ln_act_chunk<ACT, LN>(r0, c0, n_valid, s_bias, s_gam, s_bet, rstd, nmr,
+                            obase + static_cast<size_t>(oc >> 6) * (kTileM * kTileK) +
+                                ((((oc & 63) >> 3) ^ (row & 7)) << 3));
+    }
+    if (two) {
+      const int oc = col0 + c1;
+      ln_act_chunk<ACT, LN>(r1, c1, n_valid, s_bias, s_gam, s_bet, rstd, nmr,
+                            obase + static_cast<size_t>(oc >> 6) * (kTileM * kTileK) +
+                                ((((oc & 63) >> 3) ^ (row & 7)) << 3));
+    }
+  }
+}
+
 
 __device__ __forceinline__ void epi_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
@@ -212,6 +282,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int m_pad = p.m_tiles * kTileM;
     const int my_chunks = p.RB >> 5;  // (RB / 8) / 4
+    const uint32_t s_part = smem_u32(&ctl->part[0][0]);
     int it = 0;
     for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
       int m_tile, gnb;
@@ -224,24 +295,26 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       const int col0 = nb * p.RB;                   // first column of this block inside the group
       const int n_valid = min(p.RB, p.N - col0);    // valid columns in this block (may be <= 0)
       const int pb = it & 1;
+      const uint32_t s_bias = smem_u32(&ctl->bias[pb][0]);
+      const uint32_t s_gam = smem_u32(&ctl->gamma[pb][0]);
+      const uint32_t s_bet = smem_u32(&ctl->beta[pb][0]);
+      const bool has_ln = (EPI == EPI_LN_ACT) && (p.ln_gamma != nullptr);
       // ---- stage this tile's parameters (overlaps the tile's main loop) ------------------------
       {
         const size_t poff = static_cast<size_t>(g) * p.NB * p.RB + col0;
         for (int i = tid_e; i < p.RB; i += kEpiThreads) {
-          ctl->bias[pb][i] = p.bias ? __ldg(p.bias + poff + i) : 0.f;
-          if (EPI == EPI_LN_ACT && p.ln_gamma) {
-            ctl->gamma[pb][i] = __ldg(p.ln_gamma + static_cast<size_t>(g) * p.RB + i);
-            ctl->beta[pb][i] = __ldg(p.ln_beta + static_cast<size_t>(g) * p.RB + i);
+          sts32(s_bias + 4u * i, p.bias ? __ldg(p.bias + poff + i) : 0.f);
+          if (has_ln) {
+            sts32(s_gam + 4u * i, __ldg(p.ln_gamma + static_cast<size_t>(g) * p.RB + i));
+            sts32(s_bet + 4u * i, __ldg(p.ln_beta + static_cast<size_t>(g) * p.RB + i));
           }
         }
       }
       epi_bar(1);
-      const float* sbias = ctl->bias[pb];
       mbar_wait(&ctl->tmem_full[buf], use & 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * buf_cols) + lane_addr;
       const int m = tile_ok ? m_tile * kTileM + row : p.M + kTileM;   // padding tile: every row invalid
-      const bool has_ln = (EPI == EPI_LN_ACT) && (p.ln_gamma != nullptr);
 
       // ---- pass 1: statistics (EPI_STATS / LayerNorm) and/or plain fp32 output ------------------
       float mean = 0.f, rstd = 1.f;
@@ -252,58 +325,55 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
                                                 static_cast<size_t>(m) * p.ldo + col0;
         const bool vec_ok = (EPI != EPI_LN_ACT) && ((p.ldo & 3) == 0) && ((col0 & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
-        for (int i0 = 0; i0 < my_chunks; i0 += 4) {
-          uint32_t r[4][8];
+        const bool store = (EPI != EPI_LN_ACT) && (m < p.M);
+        auto pass1_chunk = [&](const uint32_t (&r)[8], int c) {
+          const float4 b0 = lds128(s_bias + 4u * c), b1 = lds128(s_bias + 4u * c + 16u);
+          float v[8];
+          v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
+          v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
+          v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
+          v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
+          if (c + 8 <= n_valid) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (i0 + u < my_chunks) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * (i0 + u)) * 8), r[u]);
-          tmem_ld_wait();
+            for (int j = 0; j < 8; ++j) {
+              sum += v[j];
+              sq = fmaf(v[j], v[j], sq);
+            }
+            if (store) {
+              if (vec_ok) {
+                *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(orow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (i0 + u < my_chunks) {
-              const int c = (cq + 4 * (i0 + u)) * 8;
-              float v[8];
-              {
-                const float4 b0 = *reinterpret_cast<const float4*>(sbias + c);
-                const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + 4);
-                v[0] = __uint_as_float(r[u][0]) + b0.x; v[1] = __uint_as_float(r[u][1]) + b0.y;
-                v[2] = __uint_as_float(r[u][2]) + b0.z; v[3] = __uint_as_float(r[u][3]) + b0.w;
-                v[4] = __uint_as_float(r[u][4]) + b1.x; v[5] = __uint_as_float(r[u][5]) + b1.y;
-                v[6] = __uint_as_float(r[u][6]) + b1.z; v[7] = __uint_as_float(r[u][7]) + b1.w;
+                for (int j = 0; j < 8; ++j) orow[c + j] = v[j];
               }
-              if (c + 8 <= n_valid) {
+            }
+          } else if (c < n_valid) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  sum += v[j];
-                  sq = fmaf(v[j], v[j], sq);
-                }
-                if (EPI != EPI_LN_ACT && m < p.M) {
-                  if (vec_ok) {
-                    *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(orow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) orow[c + j] = v[j];
-                  }
-                }
-              } else if (c < n_valid) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (c + j < n_valid) {
-                    sum += v[j];
-                    sq = fmaf(v[j], v[j], sq);
-                    if (EPI != EPI_LN_ACT && m < p.M) orow[c + j] = v[j];
-                  }
-                }
+            for (int j = 0; j < 8; ++j) {
+              if (c + j < n_valid) {
+                sum += v[j];
+                sq = fmaf(v[j], v[j], sq);
+                if (store) orow[c + j] = v[j];
               }
             }
           }
+        };
+        for (int i0 = 0; i0 < my_chunks; i0 += 2) {
+          uint32_t r0[8], r1[8];
+          const int c0 = (cq + 4 * i0) * 8, c1 = c0 + 32;
+          const bool two = i0 + 1 < my_chunks;
+          tmem_ld8(tmem_d + static_cast<uint32_t>(c0), r0);
+          if (two) tmem_ld8(tmem_d + static_cast<uint32_t>(c1), r1);
+          tmem_ld_wait();
+          pass1_chunk(r0, c0);
+          if (two) pass1_chunk(r1, c1);
         }
         if (EPI == EPI_STATS || has_ln) {
-          ctl->part[cq][row] = make_float2(sum, sq);
+          sts64(s_part + 8u * (cq * kTileM + row), sum, sq);
           epi_bar(2);
-          const float2 a0 = ctl->part[0][row], a1 = ctl->part[1][row], a2 = ctl->part[2][row],
-                       a3 = ctl->part[3][row];
+          const float2 a0 = lds64(s_part + 8u * row), a1 = lds64(s_part + 8u * (kTileM + row)),
+                       a2 = lds64(s_part + 8u * (2 * kTileM + row)), a3 = lds64(s_part + 8u * (3 * kTileM + row));
           const float tsum = (a0.x + a1.x) + (a2.x + a3.x);
           const float tsq = (a0.y + a1.y) + (a2.y + a3.y);
           if (EPI == EPI_STATS) {
@@ -321,75 +391,28 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
 
       // ---- pass 2 (EPI_LN_ACT): normalise, activate, write the packed bf16 operand image --------
       if (EPI == EPI_LN_ACT && tile_ok) {
-        const float* sgam = ctl->gamma[pb];
-        const float* sbet = ctl->beta[pb];
         const float nmr = -mean * rstd;
-        __nv_bfloat16* obase = p.out_bf16 + static_cast<size_t>(g) * p.out_bf16_group_stride;
-        const int out_ktiles = p.out_kpad >> 6;
-        const int out_chunks = (p.out_kpad - col0 < p.RB ? p.out_kpad - col0 : p.RB) >> 3;
+        __nv_bfloat16* obase = p.out_bf16 + static_cast<size_t>(g) * p.out_bf16_group_stride +
+                               static_cast<size_t>(m_tile) * (p.out_kpad >> 6) * (kTileM * kTileK) +
+                               static_cast<size_t>(row) * kTileK;
         const int tot_chunks = p.RB >> 3;
-        for (int i0 = 0; i0 < my_chunks; i0 += 4) {
-          uint32_t r[4][8];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (i0 + u < my_chunks) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * (i0 + u)) * 8), r[u]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int ch = cq + 4 * (i0 + u);
-            if (i0 + u < my_chunks && ch < out_chunks) {
-              const int c = ch * 8;
-              float y[8];
-              if (c + 8 <= n_valid) {
-                const float4 b0 = *reinterpret_cast<const float4*>(sbias + c);
-                const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                if (has_ln) {
-                  const float4 g0 = *reinterpret_cast<const float4*>(sgam + c);
-                  const float4 g1 = *reinterpret_cast<const float4*>(sgam + c + 4);
-                  const float4 e0 = *reinterpret_cast<const float4*>(sbet + c);
-                  const float4 e1 = *reinterpret_cast<const float4*>(sbet + c + 4);
-                  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                  const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float xh = fmaf(__uint_as_float(r[u][j]) + bb[j], rstd, nmr);  // (x - mean) * rstd
-                    y[j] = act_apply(fmaf(xh, gg[j], ee[j]), p.act);
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] = act_apply(__uint_as_float(r[u][j]) + bb[j], p.act);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float v = 0.f;
-                  if (c + j < n_valid) {
-                    v = __uint_as_float(r[u][j]) + sbias[c + j];
-                    if (has_ln) v = fmaf(fmaf(v, rstd, nmr), sgam[c + j], sbet[c + j]);
-                    v = act_apply(v, p.act);
-                  }
-                  y[j] = v;
-                }
-              }
-              const int oc = col0 + c;  // output column
-              __nv_bfloat16* trow = obase + (static_cast<size_t>(m_tile) * out_ktiles + (oc >> 6)) *
-                                                (kTileM * kTileK) +
-                                    static_cast<size_t>(row) * kTileK;
-              const int chunk = ((oc & 63) >> 3) ^ (row & 7);
-              *reinterpret_cast<uint4*>(trow + chunk * 8) =
-                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                             pack_bf16x2(y[6], y[7]));
-            }
-          }
+#define RLSB_P2(ACT, LN) \
+  ln_act_pass2<ACT, LN>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase)
+        if (has_ln) {
+          if (p.act == ACT_ELU) RLSB_P2(ACT_ELU, true);
+          else if (p.act == ACT_RELU) RLSB_P2(ACT_RELU, true);
+          else RLSB_P2(ACT_NONE, true);
+        } else {
+          if (p.act == ACT_ELU) RLSB_P2(ACT_ELU, false);
+          else if (p.act == ACT_RELU) RLSB_P2(ACT_RELU, false);
+          else RLSB_P2(ACT_NONE, false);
         }
+#undef RLSB_P2
         // zero the padding columns [RB, out_kpad) of the packed image (last block only)
         if (nb == p.NB - 1) {
           for (int ch = tot_chunks + cq; ch < ((p.out_kpad - col0) >> 3); ch += 4) {
             const int oc = col0 + ch * 8;
-            __nv_bfloat16* trow = obase + (static_cast<size_t>(m_tile) * out_ktiles + (oc >> 6)) *
-                                              (kTileM * kTileK) +
-                                  static_cast<size_t>(row) * kTileK;
+            __nv_bfloat16* trow = obase + static_cast<size_t>(oc >> 6) * (kTileM * kTileK);
             const int chunk = ((oc & 63) >> 3) ^ (row & 7);
             *reinterpret_cast<uint4*>(trow + chunk * 8) = make_uint4(0u, 0u, 0u, 0u);
           }

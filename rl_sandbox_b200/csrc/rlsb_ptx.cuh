@@ -31,6 +31,30 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// explicit shared-space accesses (a pointer derived through integer arithmetic from the dynamic
+// shared buffer loses its address space and compiles to slow generic LD/ST)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
