@@ -60,14 +60,19 @@ __device__ __forceinline__ float act_apply(float x) {
 
 // pass 2 of the full-row epilogue for one 8-column chunk: bias, [LayerNorm affine], activation,
 // bf16 pack, one 16-byte store into the packed operand image.
-template <int ACT, bool LN>
+template <int ACT, bool LN, bool SAVE>
 __device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int n_valid, uint32_t s_bias,
                                              uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
-                                             __nv_bfloat16* dst) {
+                                             __nv_bfloat16* dst, __nv_bfloat16* dst_pre, bool row_ok) {
   float y[8];
-  if (c >= n_valid) {  // padding columns of the block
+  float pre[8];
+  if (c >= n_valid || (SAVE && !row_ok)) {  // padding columns of the block / invalid row (training forward)
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = 0.f;
+    if (SAVE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre[j] = 0.f;
+    }
   } else {
     const float4 b0 = lds128(s_bias + 4u * c), b1 = lds128(s_bias + 4u * c + 16u);
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -79,26 +84,37 @@ __device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = fmaf(__uint_as_float(r[j]) + bb[j], rstd, nmr);  // (x - mean) * rstd
+        if (SAVE) pre[j] = xh;
         y[j] = act_apply<ACT>(fmaf(xh, gg[j], ee[j]));
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = act_apply<ACT>(__uint_as_float(r[j]) + bb[j]);
+      for (int j = 0; j < 8; ++j) {
+        const float a = __uint_as_float(r[j]) + bb[j];
+        if (SAVE) pre[j] = a;
+        y[j] = act_apply<ACT>(a);
+      }
     }
     if (c + 8 > n_valid) {  // partial chunk (N not a multiple of 8)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (c + j >= n_valid) y[j] = 0.f;
+        if (c + j >= n_valid) {
+          y[j] = 0.f;
+          if (SAVE) pre[j] = 0.f;
+        }
     }
   }
   *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
                                               pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  if (SAVE)
+    *reinterpret_cast<uint4*>(dst_pre) = make_uint4(pack_bf16x2(pre[0], pre[1]), pack_bf16x2(pre[2], pre[3]),
+                                                    pack_bf16x2(pre[4], pre[5]), pack_bf16x2(pre[6], pre[7]));
 }
 
-template <int ACT, bool LN>
+template <int ACT, bool LN, bool SAVE>
 __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chunks, int n_valid, int col0, int row,
                                              uint32_t s_bias, uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
-                                             __nv_bfloat16* obase) {
+                                             __nv_bfloat16* obase, __nv_bfloat16* pbase, bool row_ok) {
   for (int i0 = 0; i0 < my_chunks; i0 += 2) {
     uint32_t r0[8], r1[8];
     const int c0 = (cq + 4 * i0) * 8, c1 = c0 + 32;
@@ -108,15 +124,15 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
     tmem_ld_wait();
     {
       const int oc = col0 + c0;
-      ln_act_chunk<ACT, LN>(r0, c0, n_valid, s_bias, s_gam, s_bet, rstd, nmr,
-                            obase + static_cast<size_t>(oc >> 6) * (kTileM * kTileK) +
-                                ((((oc & 63) >> 3) ^ (row & 7)) << 3));
+      const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
+      ln_act_chunk<ACT, LN, SAVE>(r0, c0, n_valid, s_bias, s_gam, s_bet, rstd, nmr, obase + off,
+                                  SAVE ? pbase + off : nullptr, row_ok);
     }
     if (two) {
       const int oc = col0 + c1;
-      ln_act_chunk<ACT, LN>(r1, c1, n_valid, s_bias, s_gam, s_bet, rstd, nmr,
-                            obase + static_cast<size_t>(oc >> 6) * (kTileM * kTileK) +
-                                ((((oc & 63) >> 3) ^ (row & 7)) << 3));
+      const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
+      ln_act_chunk<ACT, LN, SAVE>(r1, c1, n_valid, s_bias, s_gam, s_bet, rstd, nmr, obase + off,
+                                  SAVE ? pbase + off : nullptr, row_ok);
     }
   }
 }

@@ -15,7 +15,8 @@ constexpr int kGemmThreads = 576;  // warp0 = bulk-copy producer, warp1 = MMA is
 enum GemmEpilogue : int {
   EPI_PLAIN = 0,   // out_f32[m][col] = acc + bias                         (row-major fp32)
   EPI_STATS = 1,   // EPI_PLAIN + per-(row, n-block) (mean, M2) partials    (for a later LayerNorm)
-  EPI_LN_ACT = 2,  // full row in TMEM: [LayerNorm] -> activation -> packed bf16 (+ optional fp32)
+  EPI_LN_ACT = 2,  // full row in TMEM: [LayerNorm] -> activation -> packed bf16 (+ optional saves for backward)
+  EPI_BWD = 3,     // full row in TMEM: acc = dL/d(act output); ELU' and LayerNorm backward -> packed bf16 dL/d(pre-LN)
 };
 
 enum Activation : int { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2 };
@@ -49,10 +50,26 @@ struct GemmParams {
   __nv_bfloat16* out_bf16;  // packed [G][M_pad x out_kpad]
   int out_kpad;             // multiple of 64, >= N
   long long out_bf16_group_stride;
+  // ---- stacked row blocks (H per-step images of m_pad rows each): row m is valid iff
+  //      (m % row_period) < row_valid; row_period == 0 => valid iff m < M.  Invalid rows are
+  //      written as zeros by EPI_LN_ACT / EPI_BWD so they never contribute to a weight gradient.
+  int row_period, row_valid;
+  // ---- EPI_LN_ACT, training forward: keep what the backward pass needs ---------------------
+  __nv_bfloat16* save_pre;  // packed like out_bf16: normalised x_hat (LayerNorm) or the pre-activation (no LN)
+  float* save_rstd;         // [G][M_pad] 1/sqrt(var + eps) per row (LayerNorm only) or nullptr
+  // ---- EPI_BWD: acc[m][n] = dL/dy, y = act(gamma * pre + beta) (LN) or act(pre) ---------------
+  //   dL/da = acc * act'(a);  LN: dxh = dL/da * gamma, out = rstd * (dxh - mean(dxh) - pre * mean(dxh * pre))
+  //   column sums over valid rows: d_gamma = sum dL/da * pre, d_beta = sum dL/da -> col_part[cta][g][2][RB]
+  const __nv_bfloat16* bwd_pre;  // packed [G][M_pad x out_kpad] (same geometry as out_bf16)
+  const float* bwd_rstd;         // [G][M_pad] or nullptr
+  float* col_part;               // [gridDim.x][G][2][RB] (zeroed by the launcher) or nullptr
+  int group_major;               // work order: all M tiles of group 0, then group 1, ... (EPI_BWD)
 };
 
 // Launch on `stream`; returns cudaError_t as int (0 = ok) or a negative argument error.
 int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream);
+// number of CTAs launch_gemm will use for `p` (size of the col_part buffer of EPI_BWD)
+int gemm_grid_size(const GemmParams& p);
 
 // CTAs per thread-block cluster that share one weight block through TMA multicast (1, 2 or 4)
 void set_gemm_cluster_size(int cs);
