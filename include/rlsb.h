@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RLSB_ABI_VERSION 1
+#define RLSB_ABI_VERSION 2
 
 /* ---- library / device ------------------------------------------------------------------- */
 int rlsb_abi_version(void);
@@ -81,6 +81,14 @@ int rlsb_gemm_bias(const void* a_packed, int k_pad, const void* w_packed, int rb
 int rlsb_gemm_ln_act(const void* a_packed, int k_pad, const void* w_packed, int rb,
                      const float* bias_padded, int M, int N, const float* gamma, const float* beta,
                      float eps, int act, void* out_packed, int out_kpad, void* stream);
+
+/* out[n_pad, k_pad] (fp32 row-major) = dY[M, n_pad]^T X[M, k_pad]: the weight-gradient contraction of
+ * nn.Linear's autograd; both operands are the packed row-block-128 activation images (read as MN-major
+ * tensor-core operands, no transposes).  Rows >= M of the images must be zero.  Test surface of the kernel
+ * rlsb_ac_update uses for every layer. */
+size_t rlsb_gemm_wgrad_workspace_bytes(int n_pad, int k_pad, int M);
+int rlsb_gemm_wgrad(const void* dy_packed, int n_pad, const void* x_packed, int k_pad, int M, float* out,
+                    void* workspace, void* stream);
 
 /* ---- K1: imagination rollout ----------------------------------------------------------------
  * replaces DreamerV2.imagine_trajectory (agents/dreamer_v2.py:68-96) with everything it calls:
@@ -150,6 +158,11 @@ typedef struct {
   float* discounts;     /* (H+1, N)                  row 0 = 1                                   */
   float* values;        /* (H+1, N) target critic, or NULL                                       */
   float* actor_raw;     /* (H, N, A or 2A) raw actor head outputs per step, or NULL              */
+  /* packed bf16 tile images of the states, one slot of rlsb_packed_rows(N) rows per step, kept for
+   * rlsb_ac_update: (H+1) x [rows x round_up(D,64)] and (H+1) x [rows x round_up(groups*classes,64)]
+   * (both or neither; NULL = the rollout ping-pongs inside its workspace) */
+  void* determ_packed;
+  void* stoch_packed;
 } rlsb_imagine_out;
 
 /* bytes needed for packed weights / activation workspace for N start states */
@@ -162,6 +175,64 @@ int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* pa
 int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0,
                      const float* z0, const float* logits0, const rlsb_noise* noise,
                      const rlsb_imagine_out* out, void* workspace, void* stream);
+
+/* ---- K4: actor-critic update -------------------------------------------------------------------
+ * replaces, for a discrete actor (rho == 1: nothing differentiates through the rollout,
+ * agents/dreamer/ac.py:90-92,121-125), the loss half of DreamerV2.train
+ * (agents/dreamer_v2.py:199-207): ImaginativeCritic.calculate_loss (agents/dreamer/ac.py:68-81),
+ * ImaginativeActor.calculate_loss (ac.py:113-146) and the two loss.backward() calls of
+ * Optimizer.step (utils/optimizer.py:55-57).  Outputs are the fp32 parameter gradients in nn.Linear /
+ * nn.LayerNorm layout (the caller all-reduces, clips and applies AdamW) and the scalar losses / metrics.
+ * The states come as the packed bf16 images rlsb_imagine_fwd leaves in determ_packed / stoch_packed;
+ * steps 0..H-1 are used (critic: all H, actor: the first H-1, ac.py / dreamer_v2.py:203-206). */
+typedef struct {
+  int32_t D, groups, classes, A, hidden;
+  int32_t discrete;        /* must be 1 (continuous actors need the K1 backward pass) */
+  int32_t layer_norm;
+  int32_t H;               /* imagination horizon */
+  float rho;               /* reinforce fraction (1 for discrete actors) */
+  float eta;               /* entropy scale */
+  int32_t metrics_samples; /* draws per element behind actor/avg_val, avg_sd, min_val, max_val (ac.py:137); 0 = skip */
+} rlsb_ac_cfg;
+
+typedef struct {
+  float* w[5];
+  float* b[5];
+  float* ln_g[4];
+  float* ln_b[4];          /* NULL where the MLP has no LayerNorm */
+} rlsb_mlp_grads;
+
+enum {
+  RLSB_AC_LOSS_CRITIC = 0,
+  RLSB_AC_LOSS_ACTOR_REINFORCE = 1,
+  RLSB_AC_LOSS_ACTOR_DYNAMICS = 2,
+  RLSB_AC_LOSS_ACTOR_ENTROPY = 3,
+  RLSB_AC_LOSS_ACTOR = 4,
+  RLSB_AC_CRITIC_AVG_TARGET = 5,
+  RLSB_AC_CRITIC_AVG_LAMBDA = 6,
+  RLSB_AC_CRITIC_AVG_PRED = 7,
+  RLSB_AC_ACTOR_AVG_VAL = 8,
+  RLSB_AC_ACTOR_MEAN_VAL = 9,
+  RLSB_AC_ACTOR_AVG_SD = 10,
+  RLSB_AC_ACTOR_MIN_VAL = 11,
+  RLSB_AC_ACTOR_MAX_VAL = 12,
+  RLSB_AC_SCALARS = 16
+};
+
+/* rows of one packed per-step image for N start states (N rounded up to the 128-row tile) */
+size_t rlsb_packed_rows(int64_t N);
+size_t rlsb_ac_packed_bytes(const rlsb_ac_cfg* cfg);
+size_t rlsb_ac_workspace_bytes(const rlsb_ac_cfg* cfg, int64_t N);
+/* actor = ImaginativeActor.actor.*, critic = ImaginativeCritic.critic.* (the trained copy, not the target) */
+int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor, const rlsb_mlp_params* critic,
+                 void* packed, void* stream);
+/* vs: (H, N) lambda-returns; w: (H+1, N) cumprod weights; values: (H+1, N) target critic (baseline and
+ * critic/avg_target_value); actions: (H+1, N, A) one-hot (row t+1 = action taken in state t);
+ * scalars: RLSB_AC_SCALARS floats (device).  seed keys the Philox stream of the metric draws. */
+int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,
+                   const void* stoch_packed, const float* vs, const float* w, const float* values,
+                   const float* actions, uint64_t seed, const rlsb_mlp_grads* actor_grads,
+                   const rlsb_mlp_grads* critic_grads, float* scalars, void* workspace, void* stream);
 
 /* ---- K3: slot attention ---------------------------------------------------------------------
  * replaces SlotAttention.forward (rl_sandbox/vision/slot_attention.py:52-77) for explicit

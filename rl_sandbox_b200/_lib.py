@@ -46,7 +46,25 @@ class Noise(C.Structure):
 class ImagineOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "determ", "logits", "stoch_idx", "stoch", "actions", "rewards", "discounts", "values",
-        "actor_raw")]
+        "actor_raw", "determ_packed", "stoch_packed")]
+
+
+class AcCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "H")] + [
+        ("rho", C.c_float), ("eta", C.c_float), ("metrics_samples", C.c_int32)]
+
+
+class MlpGrads(C.Structure):
+    _fields_ = [("w", C.c_void_p * 5), ("b", C.c_void_p * 5), ("ln_g", C.c_void_p * 4),
+                ("ln_b", C.c_void_p * 4)]
+
+
+AC_SCALAR_NAMES = {
+    "loss_critic": 0, "loss_actor_reinforce": 1, "loss_actor_dynamics_backprop": 2, "loss_actor_entropy": 3,
+    "loss_actor": 4, "critic/avg_target_value": 5, "critic/avg_lambda_value": 6, "critic/avg_predicted_value": 7,
+    "actor/avg_val": 8, "actor/mean_val": 9, "actor/avg_sd": 10, "actor/min_val": 11, "actor/max_val": 12}
+AC_SCALARS = 16
+ABI_VERSION = 2
 
 
 class SlotCfg(C.Structure):
@@ -100,11 +118,21 @@ def load() -> C.CDLL:
         "rlsb_slot_attention_pack": (C.c_int, [C.POINTER(SlotCfg), C.POINTER(SlotParams), vp, vp]),
         "rlsb_slot_attention_fwd": (C.c_int, [C.POINTER(SlotCfg), vp, i64, vp, vp, vp, vp, vp, vp]),
     })
+    sig.update({
+        "rlsb_packed_rows": (sz, [i64]),
+        "rlsb_gemm_wgrad_workspace_bytes": (sz, [i32, i32, i32]),
+        "rlsb_gemm_wgrad": (C.c_int, [vp, i32, vp, i32, i32, vp, vp, vp]),
+        "rlsb_ac_packed_bytes": (sz, [C.POINTER(AcCfg)]),
+        "rlsb_ac_workspace_bytes": (sz, [C.POINTER(AcCfg), i64]),
+        "rlsb_ac_pack": (C.c_int, [C.POINTER(AcCfg), C.POINTER(MlpParams), C.POINTER(MlpParams), vp, vp]),
+        "rlsb_ac_update": (C.c_int, [C.POINTER(AcCfg), vp, i64, vp, vp, vp, vp, vp, vp, u64, C.POINTER(MlpGrads),
+                                     C.POINTER(MlpGrads), vp, vp, vp]),
+    })
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.rlsb_abi_version() != 1:
+    if lib.rlsb_abi_version() != ABI_VERSION:
         raise RlsbError("librlsb.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -65,6 +65,9 @@ class DreamerV2(RlAgent):
         self.critic_optimizer = critic_optim(model=self.critic)
 
         self._engine = None          # lazily built ImaginationEngine (needs a B200)
+        self._ac_engine = None       # lazily built ACUpdateEngine (K4: fused critic/actor losses + backward)
+        self._ac_packed_version = -1
+        self.fused_ac_update = True  # False: torch autograd on the K1 outputs (the reference's op sequence)
         self._weights_version = 0    # bumped whenever parameters change
         self._packed_version = -1
         self._noise_seed = 0x5EED    # Philox key; the step counter below is mixed in per rollout
@@ -96,12 +99,28 @@ class DreamerV2(RlAgent):
             self._packed_version = self._weights_version
         return self._engine
 
+    def _get_ac_engine(self):
+        from rl_sandbox_b200 import ops
+        eng = self._get_engine()
+        if self._ac_engine is None or self._ac_engine.ccfg.metrics_samples != self.metrics_samples:
+            self._ac_engine = ops.ACUpdateEngine(eng.cfg, rho=float(self.actor.rho), eta=float(self.actor.eta),
+                                                 metrics_samples=self.metrics_samples, device=self.device)
+            self._ac_packed_version = -1
+        if self._ac_packed_version != self._weights_version:
+            self._ac_engine.pack(self.actor.state_dict(), self.critic.state_dict())
+            self._ac_packed_version = self._weights_version
+        return self._ac_engine
+
+    def _can_fuse_ac(self) -> bool:
+        return (self.fused_ac_update and self.is_discrete and self.actor.rho == 1.0 and not self.is_f16 and
+                self._flat_wm() and str(self.device).startswith('cuda') and self.world_model.rssm_dim > 0)
+
     def mark_weights_changed(self):
         self._weights_version += 1
 
     def imagine_trajectory(self, init_state: State, precomp_actions: t.Optional[list[Action]] = None,
-                           horizon: t.Optional[int] = None, noise: t.Optional[dict] = None
-                           ) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
+                           horizon: t.Optional[int] = None, noise: t.Optional[dict] = None,
+                           keep_packed: bool = False) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
         """H-step closed-loop rollout from (1, N, .) start states (dreamer_v2.py:68-96).
 
         ``noise`` (extension, optional): {'latent_uniforms': (H,N,1024), 'action_noise': (H,N,A)} to
@@ -130,7 +149,8 @@ class DreamerV2(RlAgent):
             pre = pre.reshape(horizon, -1, self.actions_num).expand(horizon, N, self.actions_num).contiguous()
         out = eng.rollout(h0, z0, logits0, latent_uniforms=noise.get('latent_uniforms'),
                           action_noise=noise.get('action_noise'), seed=noise.get('seed', 0),
-                          row_offset=noise.get('row_offset', 0), precomp_actions=pre, horizon=horizon)
+                          row_offset=noise.get('row_offset', 0), precomp_actions=pre, horizon=horizon,
+                          keep_packed=keep_packed, want_stoch=not keep_packed)
         self.last_rollout = out
         wm = self.world_model
         states = State(out['determ'], out['logits'].view(horizon + 1, N, wm.latent_dim, wm.latent_classes),
@@ -195,6 +215,8 @@ class DreamerV2(RlAgent):
         """Second half of ``train``; returns (losses, metrics) as tensors.  Split out so that the
         benchmark and the tests can drive it from synthetic start states."""
         from rl_sandbox_b200 import ops
+        if self._can_fuse_ac():
+            return self._behaviour_update_fused(initial_states, noise)
         with torch.autocast(device_type='cuda', enabled=self.is_f16):
             no_grad_rollout = self.actor.rho == 1.0
             with (torch.no_grad() if no_grad_rollout else torch.enable_grad()):
@@ -221,6 +243,29 @@ class DreamerV2(RlAgent):
         self.critic.update_target()
         self.mark_weights_changed()
         return losses_a | losses_c, metrics_a | metrics_c
+
+    def _behaviour_update_fused(self, initial_states: State, noise: t.Optional[dict]):
+        """Discrete actor (rho == 1): K1 rollout keeping the packed state images -> K2 -> K4 (critic / actor
+        forward, losses, backward to parameter gradients in librlsb) -> all-reduce, clip, AdamW."""
+        from rl_sandbox_b200 import _lib, ops
+        with torch.no_grad():
+            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True)
+            k1 = self.last_rollout
+            # reward_normalizer is the identity (momentum 1.0, world_model.py:111; SURVEY hard part 7)
+            vs, w, _ = ops.lambda_return(k1['rewards'], k1['values'], k1['discounts'], self.critic.lambda_)
+            ac = self._get_ac_engine()
+            scal = ac.update(k1, vs, w, self.actor.actor, self.critic.critic, seed=self._noise_seed + self._rollouts,
+                             horizon=k1['determ'].shape[0] - 1)
+        metrics_a = self.actor_optimizer.step_with_grads()
+        metrics_c = self.critic_optimizer.step_with_grads()
+        self.critic.update_target()
+        self.mark_weights_changed()
+        idx = _lib.AC_SCALAR_NAMES
+        scal = scal.clone()
+        losses = {k: scal[idx[k]] for k in ('loss_actor_reinforce', 'loss_actor_dynamics_backprop',
+                                            'loss_actor_entropy', 'loss_actor', 'loss_critic')}
+        metrics = {k: scal[i] for k, i in idx.items() if '/' in k}
+        return losses, metrics | metrics_a | metrics_c
 
     def train(self, rollout_chunks: RolloutChunks):
         obs, a, r, is_finished, is_first, additional = unpack(rollout_chunks)

@@ -6,6 +6,7 @@
 #include "rlsb_detmath.h"
 #include "rlsb_gemm.cuh"
 #include "rlsb_kernels.cuh"
+#include "rlsb_wgrad.cuh"
 
 using namespace rlsb;
 
@@ -128,4 +129,34 @@ extern "C" int rlsb_gemm_ln_act(const void* a_packed, int k_pad, const void* w_p
   g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.act = act;
   g.out_bf16 = static_cast<__nv_bfloat16*>(out_packed); g.out_kpad = out_kpad;
   return launch_gemm(g, EPI_LN_ACT, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t rlsb_gemm_wgrad_workspace_bytes(int n_pad, int k_pad, int M) {
+  WgradParams wp{};
+  wp.n_tiles = n_pad / 64; wp.G = 1; wp.m_tiles = (M + 127) / 128; wp.n_seg = 1; wp.x_ktiles[0] = k_pad / 64;
+  if (n_pad <= 0 || k_pad <= 0 || (n_pad % 64) || (k_pad % 64) || M <= 0 || plan_wgrad(wp) != 0) return 0;
+  return wgrad_partial_bytes(wp);
+}
+
+extern "C" int rlsb_gemm_wgrad(const void* dy_packed, int n_pad, const void* x_packed, int k_pad, int M, float* out,
+                               void* workspace, void* stream) {
+  if (!dy_packed || !x_packed || !out || !workspace || (n_pad % 64) || (k_pad % 64) || M <= 0) return -1;
+  WgradParams wp{};
+  wp.dY = static_cast<const __nv_bfloat16*>(dy_packed);
+  wp.n_tiles = n_pad / 64; wp.G = 1; wp.m_tiles = (M + 127) / 128;
+  wp.n_seg = 1;
+  wp.X[0] = static_cast<const __nv_bfloat16*>(x_packed);
+  wp.x_ktiles[0] = k_pad / 64;
+  wp.x_mtile_stride[0] = static_cast<long long>(k_pad) * 128;
+  wp.partial = static_cast<float*>(workspace);
+  int e = plan_wgrad(wp);
+  if (e != 0) return e;
+  e = launch_wgrad(wp, static_cast<cudaStream_t>(stream));
+  if (e != 0) return e;
+  WgradReduceParams rp{};
+  rp.partial = wp.partial; rp.splits = wp.splits; rp.G = 1; rp.rows_pad = wp.n_slices * 128; rp.ld = k_pad;
+  rp.w_dst[0] = out; rp.n_out[0] = n_pad; rp.ld_dst = k_pad; rp.n_seg = 1;
+  rp.seg[0] = PackSeg{0, 0, k_pad};
+  rp.ones_col = -1;
+  return launch_wgrad_reduce(rp, static_cast<cudaStream_t>(stream));
 }

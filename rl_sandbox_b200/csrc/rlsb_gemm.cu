@@ -147,15 +147,171 @@ __device__ __forceinline__ void epi_bar(int id) {
 // With a cluster of `cs` CTAs, the CTAs of one cluster take `cs` consecutive M tiles of the SAME
 // (g, nb): they consume the same weight block, which is fetched once per cluster (multicast).
 __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int cs, int rank, int& m_tile, int& gnb) {
+  if (p.group_major) {   // all M tiles of (g, nb) 0, then 1, ...: a CTA meets each group once (EPI_BWD column sums)
+    const int m_supers = (p.m_tiles + cs - 1) / cs;
+    gnb = w / m_supers;
+    m_tile = (w - gnb * m_supers) * cs + rank;
+    return;
+  }
   const int per_m = p.G * p.NB;
   const int m_super = w / per_m;
   gnb = w - m_super * per_m;
   m_tile = m_super * cs + rank;
 }
 
+__device__ __forceinline__ bool row_is_valid(const GemmParams& p, int m) {
+  return p.row_period > 0 ? (m < p.M && (m % p.row_period) < p.row_valid) : (m < p.M);
+}
+
+// column sums over the 32 rows a warp holds, for the 8 columns of one chunk: 9 shuffles instead of 40.
+// On return the lanes with (lane & 3) == 0 hold the total of column
+//   ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).
+__device__ __forceinline__ float colsum8(const float (&v)[8], int lane) {
+  float w4[4], w2[2];
+  const bool h16 = (lane & 16) != 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float mine = h16 ? v[4 + j] : v[j];
+    const float other = h16 ? v[j] : v[4 + j];
+    w4[j] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+  }
+  const bool h8 = (lane & 8) != 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float mine = h8 ? w4[2 + j] : w4[j];
+    const float other = h8 ? w4[j] : w4[2 + j];
+    w2[j] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+  }
+  const bool h4 = (lane & 4) != 0;
+  float s = (h4 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? w2[0] : w2[1], 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return s;
+}
+
+__device__ __forceinline__ void red_shared_add(uint32_t a, float x) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_grad(float a) {
+  if (ACT == ACT_ELU) return a > 0.f ? 1.0f : ex2_approx(a * 1.4426950408889634f);
+  if (ACT == ACT_RELU) return a > 0.f ? 1.0f : 0.f;
+  return 1.0f;
+}
+
+// EPI_BWD, one 8-column chunk: g = dL/dy (TMEM) and the saved pre (x_hat or pre-activation) ->
+// da = g * act'(a), dxh = da * gamma.  Returns da / dxh in place; pre is unpacked into `pre`.
+template <int ACT, bool LN>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[8], const uint4& pre_bits, int c, int n_valid,
+                                          uint32_t s_gam, uint32_t s_bet, bool row_ok, float (&da)[8],
+                                          float (&dxh)[8], float (&pre)[8]) {
+  unpack_bf16x8(pre_bits, pre);
+  if (LN) {
+    const float4 g0 = lds128(s_gam + 4u * c), g1 = lds128(s_gam + 4u * c + 16u);
+    const float4 e0 = lds128(s_bet + 4u * c), e1 = lds128(s_bet + 4u * c + 16u);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = row_ok && (c + j < n_valid);
+      const float a = fmaf(pre[j], gg[j], ee[j]);
+      da[j] = ok ? __uint_as_float(r[j]) * act_grad<ACT>(a) : 0.f;
+      dxh[j] = da[j] * gg[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = row_ok && (c + j < n_valid);
+      da[j] = ok ? __uint_as_float(r[j]) * act_grad<ACT>(pre[j]) : 0.f;
+      dxh[j] = da[j];
+    }
+  }
+}
+
+// the whole EPI_BWD epilogue of one tile (see GemmParams); returns nothing, writes out_bf16 / smem column sums
+template <int ACT, bool LN>
+__device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, int cq, int my_chunks, int n_valid,
+                                         int row, int lane, bool row_ok, uint32_t s_gam, uint32_t s_bet,
+                                         uint32_t s_part, uint32_t s_acc, float rstd,
+                                         const __nv_bfloat16* pbase, __nv_bfloat16* obase) {
+  float s1 = 0.f, s2 = 0.f;
+  const bool colsum = LN && p.col_part != nullptr;
+  for (int i = 0; i < my_chunks; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (c >= n_valid) break;   // warp-uniform
+    uint32_t r[8];
+    tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);
+    const size_t off = static_cast<size_t>(c >> 6) * (kTileM * kTileK) + ((((c & 63) >> 3) ^ (row & 7)) << 3);
+    const uint4 pb = *reinterpret_cast<const uint4*>(pbase + off);
+    tmem_ld_wait();
+    float da[8], dxh[8], pre[8];
+    bwd_chunk<ACT, LN>(r, pb, c, n_valid, s_gam, s_bet, row_ok, da, dxh, pre);
+    if (LN) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1 += dxh[j];
+        s2 = fmaf(dxh[j], pre[j], s2);
+      }
+      if (colsum) {
+        float dg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dg[j] = da[j] * pre[j];
+        const float cg = colsum8(dg, lane);
+        const float cb = colsum8(da, lane);
+        if ((lane & 3) == 0) {
+          const int col = c + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+          red_shared_add(s_acc + 4u * col, cg);
+          red_shared_add(s_acc + 4u * (p.RB + col), cb);
+        }
+      }
+    } else {
+      *reinterpret_cast<uint4*>(obase + off) = make_uint4(pack_bf16x2(dxh[0], dxh[1]), pack_bf16x2(dxh[2], dxh[3]),
+                                                          pack_bf16x2(dxh[4], dxh[5]), pack_bf16x2(dxh[6], dxh[7]));
+    }
+  }
+  if (LN) {
+    sts64(s_part + 8u * (cq * kTileM + row), s1, s2);
+    epi_bar(2);
+    const float2 a0 = lds64(s_part + 8u * row), a1 = lds64(s_part + 8u * (kTileM + row)),
+                 a2 = lds64(s_part + 8u * (2 * kTileM + row)), a3 = lds64(s_part + 8u * (3 * kTileM + row));
+    const float inv_n = 1.0f / static_cast<float>(n_valid);
+    const float m1 = ((a0.x + a1.x) + (a2.x + a3.x)) * inv_n;
+    const float m2 = ((a0.y + a1.y) + (a2.y + a3.y)) * inv_n;
+    for (int i = 0; i < my_chunks; ++i) {
+      const int c = (cq + 4 * i) * 8;
+      if (c >= n_valid) break;
+      uint32_t r[8];
+      tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);
+      const size_t off = static_cast<size_t>(c >> 6) * (kTileM * kTileK) + ((((c & 63) >> 3) ^ (row & 7)) << 3);
+      const uint4 pb = *reinterpret_cast<const uint4*>(pbase + off);
+      tmem_ld_wait();
+      float da[8], dxh[8], pre[8], o[8];
+      bwd_chunk<ACT, LN>(r, pb, c, n_valid, s_gam, s_bet, row_ok, da, dxh, pre);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = row_ok && (c + j < n_valid);
+        o[j] = ok ? rstd * (dxh[j] - m1 - pre[j] * m2) : 0.f;
+      }
+      *reinterpret_cast<uint4*>(obase + off) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) {
+  constexpr bool kLnAct = (EPI == EPI_LN_ACT || EPI == EPI_LN_ACT_SAVE);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -299,11 +455,28 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
     const int m_pad = p.m_tiles * kTileM;
     const int my_chunks = p.RB >> 5;  // (RB / 8) / 4
     const uint32_t s_part = smem_u32(&ctl->part[0][0]);
+    // EPI_BWD: per-CTA column sums (d_gamma | d_beta) of the current group live in the (unused) bias buffers
+    const uint32_t s_acc = smem_u32(&ctl->bias[0][0]);
+    const bool bwd_colsum = (EPI == EPI_BWD) && p.col_part != nullptr && p.ln_gamma != nullptr;
+    int g_acc = -1;
+    auto flush_colsum = [&](int g_old) {
+      epi_bar(3);
+      if (g_old >= 0) {
+        float* dst = p.col_part + (static_cast<size_t>(blockIdx.x) * p.G + g_old) * 2 * p.RB;
+        for (int i = tid_e; i < 2 * p.RB; i += kEpiThreads) dst[i] = lds32(s_acc + 4u * i);
+      }
+      for (int i = tid_e; i < 2 * p.RB; i += kEpiThreads) sts32(s_acc + 4u * i, 0.f);
+      epi_bar(3);
+    };
     int it = 0;
     for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
       int m_tile, gnb;
       decode_work(p, w, cs, rank, m_tile, gnb);
       const bool tile_ok = m_tile < p.m_tiles;   // false only for the padding CTA of the last cluster
+      if (bwd_colsum && gnb / p.NB != g_acc) {
+        flush_colsum(g_acc);
+        g_acc = gnb / p.NB;
+      }
       const int g = gnb / p.NB;
       const int nb = gnb - g * p.NB;
       const int buf = (nbuf == 2) ? (it & 1) : 0;
@@ -314,12 +487,12 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       const uint32_t s_bias = smem_u32(&ctl->bias[pb][0]);
       const uint32_t s_gam = smem_u32(&ctl->gamma[pb][0]);
       const uint32_t s_bet = smem_u32(&ctl->beta[pb][0]);
-      const bool has_ln = (EPI == EPI_LN_ACT) && (p.ln_gamma != nullptr);
+      const bool has_ln = (kLnAct || EPI == EPI_BWD) && (p.ln_gamma != nullptr);
       // ---- stage this tile's parameters (overlaps the tile's main loop) ------------------------
       {
         const size_t poff = static_cast<size_t>(g) * p.NB * p.RB + col0;
         for (int i = tid_e; i < p.RB; i += kEpiThreads) {
-          sts32(s_bias + 4u * i, p.bias ? __ldg(p.bias + poff + i) : 0.f);
+          if (EPI != EPI_BWD) sts32(s_bias + 4u * i, p.bias ? __ldg(p.bias + poff + i) : 0.f);
           if (has_ln) {
             sts32(s_gam + 4u * i, __ldg(p.ln_gamma + static_cast<size_t>(g) * p.RB + i));
             sts32(s_bet + 4u * i, __ldg(p.ln_beta + static_cast<size_t>(g) * p.RB + i));
@@ -331,17 +504,48 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * buf_cols) + lane_addr;
       const int m = tile_ok ? m_tile * kTileM + row : p.M + kTileM;   // padding tile: every row invalid
+      const bool row_ok = tile_ok && row_is_valid(p, m);
+
+      if (EPI == EPI_BWD) {
+        if (tile_ok) {
+          const size_t img = static_cast<size_t>(g) * p.out_bf16_group_stride +
+                             static_cast<size_t>(m_tile) * (p.out_kpad >> 6) * (kTileM * kTileK) +
+                             static_cast<size_t>(row) * kTileK;
+          const float rs = (has_ln && row_ok) ? __ldg(p.bwd_rstd + static_cast<size_t>(g) * m_pad + m) : 0.f;
+#define RLSB_B(ACT, LN) \
+  bwd_tile<ACT, LN>(p, tmem_d, cq, my_chunks, n_valid, row, lane, row_ok, s_gam, s_bet, s_part, s_acc, rs, \
+                    p.bwd_pre + img, p.out_bf16 + img)
+          if (has_ln) {
+            if (p.act == ACT_ELU) RLSB_B(ACT_ELU, true);
+            else RLSB_B(ACT_NONE, true);
+          } else {
+            if (p.act == ACT_ELU) RLSB_B(ACT_ELU, false);
+            else RLSB_B(ACT_NONE, false);
+          }
+#undef RLSB_B
+          // zero the padding columns [n_valid rounded down to a chunk .. out_kpad) of the packed image
+          for (int ch = (n_valid >> 3) + cq; ch < (p.out_kpad >> 3); ch += 4) {
+            if (ch * 8 < n_valid) continue;   // partial chunk was written above
+            __nv_bfloat16* trow = p.out_bf16 + img + static_cast<size_t>(ch >> 3) * (kTileM * kTileK);
+            *reinterpret_cast<uint4*>(trow + (((ch & 7) ^ (row & 7)) << 3)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+        continue;
+      }
 
       // ---- pass 1: statistics (EPI_STATS / LayerNorm) and/or plain fp32 output ------------------
       float mean = 0.f, rstd = 1.f;
       if (EPI == EPI_PLAIN || EPI == EPI_STATS || has_ln) {
         float sum = 0.f, sq = 0.f;
-        float* orow = (EPI == EPI_LN_ACT) ? nullptr
+        float* orow = (kLnAct) ? nullptr
                                           : p.out_f32 + static_cast<size_t>(g) * p.out_group_stride +
                                                 static_cast<size_t>(m) * p.ldo + col0;
-        const bool vec_ok = (EPI != EPI_LN_ACT) && ((p.ldo & 3) == 0) && ((col0 & 3) == 0) &&
+        const bool vec_ok = (!kLnAct) && ((p.ldo & 3) == 0) && ((col0 & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
-        const bool store = (EPI != EPI_LN_ACT) && (m < p.M);
+        const bool store = (!kLnAct) && row_ok;
         auto pass1_chunk = [&](const uint32_t (&r)[8], int c) {
           const float4 b0 = lds128(s_bias + 4u * c), b1 = lds128(s_bias + 4u * c + 16u);
           float v[8];
@@ -401,27 +605,33 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             mean = tsum * inv_n;
             const float var = fmaxf(tsq * inv_n - mean * mean, 0.f);
             rstd = 1.0f / sqrtf(var + p.ln_eps);
+            if (p.save_rstd && cq == 0 && tile_ok) p.save_rstd[static_cast<size_t>(g) * m_pad + m] = rstd;
           }
         }
       }
 
       // ---- pass 2 (EPI_LN_ACT): normalise, activate, write the packed bf16 operand image --------
-      if (EPI == EPI_LN_ACT && tile_ok) {
+      if (kLnAct && tile_ok) {
         const float nmr = -mean * rstd;
         __nv_bfloat16* obase = p.out_bf16 + static_cast<size_t>(g) * p.out_bf16_group_stride +
                                static_cast<size_t>(m_tile) * (p.out_kpad >> 6) * (kTileM * kTileK) +
                                static_cast<size_t>(row) * kTileK;
         const int tot_chunks = p.RB >> 3;
-#define RLSB_P2(ACT, LN) \
-  ln_act_pass2<ACT, LN>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase)
-        if (has_ln) {
-          if (p.act == ACT_ELU) RLSB_P2(ACT_ELU, true);
-          else if (p.act == ACT_RELU) RLSB_P2(ACT_RELU, true);
-          else RLSB_P2(ACT_NONE, true);
+        __nv_bfloat16* pbase = p.save_pre ? p.save_pre + (obase - p.out_bf16) : nullptr;
+#define RLSB_P2(ACT, LN, SAVE) \
+  ln_act_pass2<ACT, LN, SAVE>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase, \
+                              pbase, row_ok)
+        if (EPI == EPI_LN_ACT_SAVE) {   // training forward (ELU only): also keep x_hat / the pre-activation
+          if (has_ln) RLSB_P2(ACT_ELU, true, EPI == EPI_LN_ACT_SAVE);
+          else RLSB_P2(ACT_ELU, false, EPI == EPI_LN_ACT_SAVE);
+        } else if (has_ln) {
+          if (p.act == ACT_ELU) RLSB_P2(ACT_ELU, true, false);
+          else if (p.act == ACT_RELU) RLSB_P2(ACT_RELU, true, false);
+          else RLSB_P2(ACT_NONE, true, false);
         } else {
-          if (p.act == ACT_ELU) RLSB_P2(ACT_ELU, false);
-          else if (p.act == ACT_RELU) RLSB_P2(ACT_RELU, false);
-          else RLSB_P2(ACT_NONE, false);
+          if (p.act == ACT_ELU) RLSB_P2(ACT_ELU, false, false);
+          else if (p.act == ACT_RELU) RLSB_P2(ACT_RELU, false, false);
+          else RLSB_P2(ACT_NONE, false, false);
         }
 #undef RLSB_P2
         // zero the padding columns [RB, out_kpad) of the packed image (last block only)
@@ -438,6 +648,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
     }
+    if (bwd_colsum) flush_colsum(g_acc);
   }
 
   tc_fence_before();
@@ -459,12 +670,8 @@ void set_gemm_cluster_size(int cs) {
 }
 int gemm_cluster_size() { return g_cluster_size; }
 
-int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
-  if (p.RB <= 0 || p.RB > 512 || (p.RB % 32) != 0) return -1;
-  if (p.n_seg < 1 || p.n_seg > kMaxSeg) return -2;
-  if (epilogue == EPI_LN_ACT && p.NB != 1 && p.ln_gamma != nullptr) return -3;  // LayerNorm needs the whole row
-  if (p.M <= 0 || p.m_tiles != (p.M + kTileM - 1) / kTileM) return -4;
-  if (epilogue == EPI_LN_ACT && ((p.out_kpad % 64) != 0 || p.out_kpad < p.N)) return -5;
+namespace {
+int init_device_info() {
   if (g_num_sms == 0) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -472,6 +679,39 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return static_cast<int>(e);
     if (const char* env = getenv("RLSB_CLUSTER")) set_gemm_cluster_size(atoi(env));
+  }
+  return 0;
+}
+int pick_cluster(const GemmParams& p) {
+  int cs = g_cluster_size;
+  while (cs > 1 && ((p.RB / cs) % 8 != 0 || p.m_tiles < cs)) cs >>= 1;
+  return cs;
+}
+}  // namespace
+
+int gemm_grid_size(const GemmParams& p) {
+  if (init_device_info() != 0) return 0;
+  const int cs = pick_cluster(p);
+  const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
+  int clusters = g_num_sms / cs;
+  if (total_work < clusters) clusters = total_work;
+  return clusters * cs;
+}
+
+int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
+  if (p.RB <= 0 || p.RB > 512 || (p.RB % 32) != 0) return -1;
+  if (p.n_seg < 1 || p.n_seg > kMaxSeg) return -2;
+  if (epilogue == EPI_LN_ACT && p.save_pre) epilogue = EPI_LN_ACT_SAVE;
+  if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB != 1 && p.ln_gamma != nullptr) return -3;  // LayerNorm needs the whole row
+  if (p.M <= 0 || p.m_tiles != (p.M + kTileM - 1) / kTileM) return -4;
+  if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE || epilogue == EPI_BWD) && ((p.out_kpad % 64) != 0 || p.out_kpad < p.N)) return -5;
+  if (epilogue == EPI_BWD && (p.NB != 1 || !p.bwd_pre || !p.out_bf16 || !p.group_major ||
+                              (p.ln_gamma && !p.bwd_rstd) || (p.act != ACT_ELU && p.act != ACT_NONE)))
+    return -8;
+  if (epilogue == EPI_LN_ACT_SAVE && (p.act != ACT_ELU || p.NB != 1)) return -9;
+  {
+    const int ie = init_device_info();
+    if (ie != 0) return ie;
   }
   const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2;
   const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256;
@@ -482,14 +722,17 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   const int nbuf = p.RB <= 256 ? 2 : 1;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + sizeof(SmemCtl) + 1024;
   // cluster size along M: CTAs of a cluster share the weight block (TMA multicast)
-  int cs = g_cluster_size;
-  while (cs > 1 && ((p.RB / cs) % 8 != 0 || p.m_tiles < cs)) cs >>= 1;
+  const int cs = pick_cluster(p);
   const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
   int clusters = g_num_sms / cs;
   if (total_work < clusters) clusters = total_work;
   const int grid = clusters * cs;
 
   cudaError_t e;
+  if (epilogue == EPI_BWD && p.col_part && p.ln_gamma) {
+    e = cudaMemsetAsync(p.col_part, 0, static_cast<size_t>(grid) * p.G * 2 * p.RB * sizeof(float), stream);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kGemmThreads);
@@ -518,6 +761,8 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
     case EPI_PLAIN: RLSB_LAUNCH(EPI_PLAIN); break;
     case EPI_STATS: RLSB_LAUNCH(EPI_STATS); break;
     case EPI_LN_ACT: RLSB_LAUNCH(EPI_LN_ACT); break;
+    case EPI_BWD: RLSB_LAUNCH(EPI_BWD); break;
+    case EPI_LN_ACT_SAVE: RLSB_LAUNCH(EPI_LN_ACT_SAVE); break;
     default: return -7;
   }
 #undef RLSB_LAUNCH

@@ -16,6 +16,7 @@ enum GemmEpilogue : int {
   EPI_PLAIN = 0,   // out_f32[m][col] = acc + bias                         (row-major fp32)
   EPI_STATS = 1,   // EPI_PLAIN + per-(row, n-block) (mean, M2) partials    (for a later LayerNorm)
   EPI_LN_ACT = 2,  // full row in TMEM: [LayerNorm] -> activation -> packed bf16 (+ optional saves for backward)
+  EPI_LN_ACT_SAVE = 4,  // EPI_LN_ACT that also stores save_pre / save_rstd (selected by the launcher when save_pre != nullptr)
   EPI_BWD = 3,     // full row in TMEM: acc = dL/d(act output); ELU' and LayerNorm backward -> packed bf16 dL/d(pre-LN)
 };
 

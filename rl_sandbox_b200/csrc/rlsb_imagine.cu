@@ -283,16 +283,33 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   const float eps = 1e-5f;
   const size_t ND = static_cast<size_t>(N) * P.D, NS = static_cast<size_t>(N) * P.S;
 
+  // packed bf16 state images: ping-pong in the workspace, or — when the caller keeps them for the
+  // actor-critic update (rlsb_ac_update) — one slot per step in the caller's buffers
+  const bool keep = out->determ_packed != nullptr && out->stoch_packed != nullptr;
+  if ((out->determ_packed != nullptr) != (out->stoch_packed != nullptr)) return -4;
+  auto himg = [&](int t) {
+    return keep ? static_cast<__nv_bfloat16*>(out->determ_packed) + static_cast<size_t>(t) * m_pad * P.Dp
+                : bf(W.hbf[t & 1]);
+  };
+  auto zimg = [&](int t) {
+    return keep ? static_cast<__nv_bfloat16*>(out->stoch_packed) + static_cast<size_t>(t) * m_pad * P.Sp
+                : bf(W.zbf[t & 1]);
+  };
+
   // ---- start state ---------------------------------------------------------------------------
   {
     PackSeg seg[1] = {{0, 0, P.D}};
-    RLSB_TRY(launch_pack(h0, P.D, M, bf(W.hbf[0]), 128, m_pad, P.Dp, 1, seg, s));
+    RLSB_TRY(launch_pack(h0, P.D, M, himg(0), 128, m_pad, P.Dp, 1, seg, s));
     PackSeg segz[1] = {{0, 0, P.S}};
-    RLSB_TRY(launch_pack(z0, P.S, M, bf(W.zbf[0]), 128, m_pad, P.Sp, 1, segz, s));
-    // rows >= N of the other one-hot image are never written by the sampler: clear its last M tile
+    RLSB_TRY(launch_pack(z0, P.S, M, zimg(0), 128, m_pad, P.Sp, 1, segz, s));
+    // rows >= N of the other one-hot images are never written by the sampler: clear their last M tile
     const size_t tile_row_bytes = static_cast<size_t>(P.Sp / 64) * 128 * 64 * 2;
-    cudaError_t e = cudaMemsetAsync(ws + W.zbf[1] + static_cast<size_t>(m_tiles - 1) * tile_row_bytes, 0,
-                                    tile_row_bytes, s);
+    cudaError_t e = cudaSuccess;
+    if (M != m_pad) {
+      for (int t = 1; t <= (keep ? H : 1) && e == cudaSuccess; ++t)
+        e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(zimg(t)) + static_cast<size_t>(m_tiles - 1) * tile_row_bytes, 0,
+                            tile_row_bytes, s);
+    }
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaMemcpyAsync(out->determ, h0, ND * 4, cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -338,10 +355,9 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
                          outp, P.Dp, s);
   };
 
-  int cur = 0;
   for (int t = 0; t <= H; ++t) {
-    const __nv_bfloat16* hb = bf(W.hbf[cur]);
-    const __nv_bfloat16* zb = bf(W.zbf[cur]);
+    const __nv_bfloat16* hb = himg(t);
+    const __nv_bfloat16* zb = zimg(t);
     // ---- heads on s_t = cat[h_t, z_t]: actor, reward, discount, target critic -------------------
     for (int l = 0; l < 5; ++l) {
       const LayerPlan& L = P.head[l];
@@ -386,7 +402,6 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     RLSB_TRY(launch_head_finish(hf, s));
     if (t == H) break;
 
-    const int nxt = cur ^ 1;
     // ---- x = ELU(LN?(W_in [z, a] + b))                                   rssm.py:179 ----------
     {
       GemmParams g = base_gemm(P.img_in);
@@ -406,13 +421,13 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       RLSB_TRY(launch_gru_gate(scratch, W.ld_scratch, stats, P.gru.NB, P.gru.RB, M, m_pad, P.D,
                                pf(P.gru.g_off), pf(P.gru.b_off), eps, -1.0f,
                                out->determ + static_cast<size_t>(t) * ND, P.D,
-                               out->determ + static_cast<size_t>(t + 1) * ND, P.D, bf(W.hbf[nxt]), P.Dp, s));
+                               out->determ + static_cast<size_t>(t + 1) * ND, P.D, himg(t + 1), P.Dp, s));
     }
     // ---- prior logits = W2 ELU(LN?(W1 h' + b1)) + b2                      rssm.py:192 ----------
     {
       GemmParams g = base_gemm(P.prior1);
       g.n_seg = 1;
-      g.A[0] = bf(W.hbf[nxt]); g.a_ktiles[0] = P.Dp / 64;
+      g.A[0] = himg(t + 1); g.a_ktiles[0] = P.Dp / 64;
       RLSB_TRY(rssm_layer(P.prior1, g, ln, bf(W.ybf)));
       GemmParams g2 = base_gemm(P.prior2);
       g2.n_seg = 1;
@@ -427,10 +442,9 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       ns.ld = P.S; ns.seed = noise->seed; ns.step = static_cast<uint32_t>(t); ns.row_offset = noise->row_offset;
       RLSB_TRY(launch_sample_latent(out->logits + static_cast<size_t>(t + 1) * NS, P.S, M, cfg->groups,
                                     cfg->classes, ns, out->stoch_idx + static_cast<size_t>(t + 1) * N * cfg->groups,
-                                    bf(W.zbf[nxt]), P.Sp,
+                                    zimg(t + 1), P.Sp,
                                     out->stoch ? out->stoch + static_cast<size_t>(t + 1) * NS : nullptr, P.S, s));
     }
-    cur = nxt;
   }
   return 0;
 }

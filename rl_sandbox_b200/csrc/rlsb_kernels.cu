@@ -64,6 +64,25 @@ __global__ void pack_kernel(const PackArgs a) {
   }
 }
 
+__global__ void pack_transposed_kernel(const float* __restrict__ src, long long ld_src, int cols, int rows,
+                                       __nv_bfloat16* __restrict__ dst, int RB, int rows_dst_pad, int k_pad) {
+  const long long chunks_per_row = k_pad >> 3;
+  const long long total = static_cast<long long>(rows_dst_pad) * chunks_per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // consecutive threads take consecutive ROWS of the same chunk: coalesced reads of src[c][r..]
+    const long long ch = i / rows_dst_pad;
+    const long long row = i - ch * rows_dst_pad;
+    const int k0 = static_cast<int>(ch) << 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (row < rows && k0 + j < cols) ? __ldg(src + static_cast<long long>(k0 + j) * ld_src + row) : 0.f;
+    const size_t idx = packed_index(static_cast<size_t>(row), static_cast<size_t>(k0), static_cast<size_t>(k_pad), RB);
+    *reinterpret_cast<uint4*>(dst + idx) = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm statistics from the per-(row, n-block) partials (sum, sum of squares) the GEMM
 // epilogue wrote: one warp works on one row, lane b fetches block b, shuffle-reduce.
@@ -626,6 +645,17 @@ int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16*
   for (int s = 0; s < n_seg; ++s) a.seg[s] = segs[s];
   const long long total = static_cast<long long>(rows_dst_pad) * (k_pad / 8);
   pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_pack_transposed(const float* src, long long ld_src, int cols, int rows, __nv_bfloat16* dst, int RB,
+                           int rows_dst_pad, int k_pad, cudaStream_t stream) {
+  if (!src || !dst || (k_pad & 63) || (rows_dst_pad % RB) || cols > k_pad || rows > rows_dst_pad) return -1;
+  const long long total = static_cast<long long>(rows_dst_pad) * (k_pad >> 3);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_transposed_kernel<<<blocks, 256, 0, stream>>>(src, ld_src, cols, rows, dst, RB, rows_dst_pad, k_pad);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

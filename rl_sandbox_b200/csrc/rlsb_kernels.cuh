@@ -18,6 +18,11 @@ struct PackSeg {
 int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
                 int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream);
 
+// transposed variant: logical T[r][c] = src[c * ld_src + r] for r < rows, c < cols (nn.Linear weight
+// [cols = out, rows = in] -> operand whose rows are the in-features), zero padded
+int launch_pack_transposed(const float* src, long long ld_src, int cols, int rows, __nv_bfloat16* dst, int RB,
+                           int rows_dst_pad, int k_pad, cudaStream_t stream);
+
 // scratch fp32 [M_pad x ld] + per-block (mean, M2) partials -> [LayerNorm] -> act -> packed bf16
 int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB, int RB, int M,
                   int m_pad, int N, const float* gamma, const float* beta, float eps, int act,

@@ -251,6 +251,24 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);       // m_dim
 }
 
+// MN-major operand (the contraction index is the ROW index of the stored image): rows of 128 bytes
+// hold 64 consecutive M/N elements, 8-row groups (8 contraction indices) are `SBO` = 1024 bytes
+// apart, the next 64 M/N elements start `lbo_bytes` further on; SWIZZLE_128B as above.  Stepping
+// the contraction by 16 rows = +2048 bytes on the start address.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // LBO: stride between 64-element M/N groups
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;                   // SBO: stride between 8-row K groups
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with both operands MN-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // ----------------------------------------------------------------------------------------
 // packed ("UMMA-ready") global layout shared by every bf16 operand in this library.
 //

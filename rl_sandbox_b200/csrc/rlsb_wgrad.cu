@@ -1,0 +1,290 @@
+// rlsb_wgrad.cu — weight gradients of the actor / critic MLPs on tcgen05 (see rlsb_wgrad.cuh).
+//
+//   dW[g][n][k] = sum_m dY[g][m][n] * X[g][m][k]
+//
+// One CTA owns one output tile (128 n-rows x up to 512 k-columns, fp32 in TMEM) and a contiguous
+// range of M tiles ("split"); partial tiles are written to HBM and summed by wgrad_reduce_kernel
+// in a fixed order (deterministic; no atomics), which also scatters them into the nn.Linear
+// weight / bias gradient layout.
+//
+// The contraction runs over the ROW index of the packed activation images, i.e. both operands are
+// MN-major for the tensor core.  A pipeline stage holds 32 rows of every participating 64-column
+// tile: 4 KB pieces, each one contiguous cp.async.bulk, laid out so that consecutive 64-column
+// groups are 4 KB apart (LBO) and 8-row groups 1 KB apart (SBO).
+#include "rlsb_wgrad.cuh"
+
+#include "rlsb_count.cuh"
+#include "rlsb_gemm.cuh"
+#include "rlsb_ptx.cuh"
+
+namespace rlsb {
+
+namespace {
+
+constexpr int kWgThreads = 192;       // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kWgRows = 32;           // contraction rows per stage
+constexpr uint32_t kPiece = kWgRows * 128;  // bytes of one 64-column tile slice
+constexpr int kWgMaxStages = 8;
+
+struct WgCtl {
+  uint64_t full[kWgMaxStages];
+  uint64_t empty[kWgMaxStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams p, const int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- which output tile / which M range -----------------------------------------------------
+  const int items = p.G * p.n_slices * p.n_chunks;
+  const int item = static_cast<int>(blockIdx.x) % items;
+  const int split = static_cast<int>(blockIdx.x) / items;
+  const int kc = item % p.n_chunks;
+  const int ns = (item / p.n_chunks) % p.n_slices;
+  const int g = item / (p.n_chunks * p.n_slices);
+  const int m0 = static_cast<int>(static_cast<long long>(split) * p.m_tiles / p.splits);
+  const int m1 = static_cast<int>(static_cast<long long>(split + 1) * p.m_tiles / p.splits);
+  const int kt0 = kc * p.kc_tiles;
+  const int nkt = min(p.kc_tiles, p.kt_total - kt0);   // k tiles of this chunk (1..8)
+  const int na = min(2, p.n_tiles - ns * 2);            // dY tiles of this slice (1..2)
+  const uint32_t stage_bytes = static_cast<uint32_t>(2 + p.kc_tiles) * kPiece;
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(smem + static_cast<size_t>(stages) * stage_bytes);
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(&ctl->full[s], 1);
+        mbar_init(&ctl->empty[s], 1);
+      }
+      mbar_init(&ctl->tmem_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&ctl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resolve the source of every k tile of this chunk once
+      const __nv_bfloat16* xsrc[8];
+      long long xstride[8];
+      for (int j = 0; j < nkt; ++j) {
+        int kt = kt0 + j, s = 0;
+        while (kt >= p.x_ktiles[s]) {
+          kt -= p.x_ktiles[s];
+          ++s;
+        }
+        xsrc[j] = p.X[s] + static_cast<size_t>(g) * p.x_group_stride[s] + static_cast<size_t>(kt) * (kTileM * kTileK);
+        xstride[j] = p.x_mtile_stride[s];
+      }
+      const __nv_bfloat16* ysrc = p.dY + static_cast<size_t>(g) * p.dy_group_stride +
+                                  static_cast<size_t>(ns) * 2 * (kTileM * kTileK);
+      const long long ystride = static_cast<long long>(p.n_tiles) * (kTileM * kTileK);
+      const uint32_t tx = static_cast<uint32_t>(na + nkt) * kPiece;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = m0; mt < m1; ++mt) {
+        for (int sub = 0; sub < kTileM / kWgRows; ++sub) {
+          mbar_wait(&ctl->empty[stage], phase ^ 1u);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          mbar_expect_tx(&ctl->full[stage], tx);
+          const size_t roff = static_cast<size_t>(sub) * kWgRows * kTileK;   // elements
+          for (int a = 0; a < na; ++a)
+            bulk_g2s(sa + a * kPiece, ysrc + mt * ystride + static_cast<size_t>(a) * (kTileM * kTileK) + roff, kPiece,
+                     &ctl->full[stage]);
+          for (int j = 0; j < nkt; ++j)
+            bulk_g2s(sa + (2 + j) * kPiece, xsrc[j] + mt * xstride[j] + roff, kPiece, &ctl->full[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const int n0 = nkt > 4 ? 256 : nkt * 64;
+      const int n1 = nkt * 64 - n0;
+      const uint32_t idesc0 = make_idesc_bf16_mn(128, static_cast<uint32_t>(n0));
+      const uint32_t idesc1 = n1 > 0 ? make_idesc_bf16_mn(128, static_cast<uint32_t>(n1)) : 0u;
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int mt = m0; mt < m1; ++mt) {
+        for (int sub = 0; sub < kTileM / kWgRows; ++sub) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t adesc = make_smem_desc_mn_sw128(sa, kPiece);
+          const uint64_t bdesc0 = make_smem_desc_mn_sw128(sa + 2 * kPiece, kPiece);
+          const uint64_t bdesc1 = make_smem_desc_mn_sw128(sa + 6 * kPiece, kPiece);
+#pragma unroll
+          for (int kk = 0; kk < kWgRows / 16; ++kk) {
+            const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+            const uint64_t adv = static_cast<uint64_t>(kk) * (2048u >> 4);   // 16 rows of 128 bytes
+            umma_bf16(tmem_base, adesc + adv, bdesc0 + adv, idesc0, acc);
+            if (n1 > 0) umma_bf16(tmem_base + 256u, adesc + adv, bdesc1 + adv, idesc1, acc);
+          }
+          first = false;
+          umma_commit(&ctl->empty[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      umma_commit(&ctl->tmem_full);
+    }
+  } else {
+    // ---- epilogue: TMEM -> fp32 partial tile ---------------------------------------------------
+    const int q = warp & 3;
+    const int n = q * 32 + lane;
+    const int n_glob = ns * 128 + n;
+    const int rows_pad = p.n_slices * 128;
+    const int ld = p.kt_total * 64;
+    mbar_wait(&ctl->tmem_full, 0u);
+    tc_fence_after();
+    float* dst = p.partial + ((static_cast<size_t>(split) * p.G + g) * rows_pad + n_glob) * ld + kt0 * 64;
+    const bool row_ok = n_glob < p.n_tiles * 64;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = 0; c < nkt * 64; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + static_cast<uint32_t>(c), r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
+  const long long total = static_cast<long long>(p.G) * p.rows_pad * p.ld;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % p.ld);
+    const int n = static_cast<int>((i / p.ld) % p.rows_pad);
+    const int g = static_cast<int>(i / (static_cast<long long>(p.ld) * p.rows_pad));
+    if (n >= p.n_out[g]) continue;
+    float* dst = nullptr;
+    if (col == p.ones_col) {
+      if (p.b_dst[g]) dst = p.b_dst[g] + n;
+    } else if (p.w_dst[g]) {
+      for (int s = 0; s < p.n_seg; ++s) {
+        const int off = col - p.seg[s].dst_k0;
+        if (off >= 0 && off < p.seg[s].len) dst = p.w_dst[g] + static_cast<size_t>(n) * p.ld_dst + p.seg[s].src_c0 + off;
+      }
+    }
+    if (!dst) continue;
+    float acc = 0.f;
+    const size_t stride = static_cast<size_t>(p.G) * p.rows_pad * p.ld;
+    const float* src = p.partial + i;
+    for (int s = 0; s < p.splits; ++s) acc += __ldg(src + s * stride);
+    *dst = acc;
+  }
+}
+
+__global__ void colsum_reduce_kernel(const ColsumReduceParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.G * 2 * p.RB) return;
+  const int col = i % p.RB;
+  const int which = (i / p.RB) & 1;
+  const int g = i / (2 * p.RB);
+  if (col >= p.N) return;
+  float* dst = which == 0 ? p.dgamma[g] : p.dbeta[g];
+  if (!dst) return;
+  float acc = 0.f;
+  const size_t stride = static_cast<size_t>(p.G) * 2 * p.RB;
+  for (int c = 0; c < p.ctas; ++c) acc += __ldg(p.col_part + c * stride + i);
+  dst[col] = acc;
+}
+
+int g_wg_sms = 0;
+
+}  // namespace
+
+int plan_wgrad(WgradParams& p) {
+  if (p.n_seg < 1 || p.n_seg > kWgMaxSeg || p.G < 1 || p.G > kWgMaxGroups || p.n_tiles < 1 || p.m_tiles < 1) return -1;
+  if (g_wg_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  p.kt_total = 0;
+  for (int s = 0; s < p.n_seg; ++s) p.kt_total += p.x_ktiles[s];
+  const int chunks = (p.kt_total + 7) / 8;
+  p.kc_tiles = (p.kt_total + chunks - 1) / chunks;
+  p.n_chunks = (p.kt_total + p.kc_tiles - 1) / p.kc_tiles;
+  p.n_slices = (p.n_tiles + 1) / 2;
+  const int items = p.G * p.n_slices * p.n_chunks;
+  int splits = g_wg_sms / items;
+  if (splits < 1) splits = 1;
+  if (splits > p.m_tiles) splits = p.m_tiles;
+  p.splits = splits;
+  return 0;
+}
+
+size_t wgrad_partial_bytes(const WgradParams& p) {
+  return static_cast<size_t>(p.splits) * p.G * p.n_slices * 128 * p.kt_total * 64 * sizeof(float);
+}
+
+int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
+  if (!p.dY || !p.partial || p.splits < 1 || p.kc_tiles < 1 || p.kc_tiles > 8) return -1;
+  const int stage_bytes = (2 + p.kc_tiles) * static_cast<int>(kPiece);
+  int stages = (227 * 1024 - 1024 - static_cast<int>(sizeof(WgCtl)) - 256) / stage_bytes;
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  if (stages < 2) return -2;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + sizeof(WgCtl) + 1024;
+  static bool attr_done = false;
+  cudaError_t e;
+  if (!attr_done) {
+    e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done = true;
+  }
+  const int grid = p.G * p.n_slices * p.n_chunks * p.splits;
+  wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(p, stages);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_wgrad_reduce(const WgradReduceParams& p, cudaStream_t stream) {
+  const long long total = static_cast<long long>(p.G) * p.rows_pad * p.ld;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_colsum_reduce(const ColsumReduceParams& p, cudaStream_t stream) {
+  const int total = p.G * 2 * p.RB;
+  colsum_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace rlsb

@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ImagineCfg, ImagineOut, ImagineParams, MlpParams, Noise, SlotCfg, SlotParams, check
+from ._lib import (AcCfg, ImagineCfg, ImagineOut, ImagineParams, MlpGrads, MlpParams, Noise, SlotCfg,
+                   SlotParams, check)
 
 
 def _stream() -> int:
@@ -197,6 +198,17 @@ def gemm_ln_act(a_packed, k_pad, w_packed, rb, bias, M, N, gamma, beta, eps, act
     return out
 
 
+def gemm_wgrad(dy_packed, n_pad, x_packed, k_pad, M):
+    """out[n_pad, k_pad] = dY^T X from two packed images (weight-gradient contraction; test surface)."""
+    _lib.require_device()
+    lib = _lib.load()
+    ws = torch.empty(lib.rlsb_gemm_wgrad_workspace_bytes(n_pad, k_pad, M), device=dy_packed.device, dtype=torch.uint8)
+    out = torch.zeros((n_pad, k_pad), device=dy_packed.device, dtype=torch.float32)
+    check(lib.rlsb_gemm_wgrad(dy_packed.data_ptr(), n_pad, x_packed.data_ptr(), k_pad, M, out.data_ptr(),
+                              ws.data_ptr(), _stream()), "rlsb_gemm_wgrad")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # K1
 # ------------------------------------------------------------------------------------------------
@@ -299,7 +311,7 @@ class ImaginationEngine:
                 latent_uniforms: Optional[torch.Tensor] = None, action_noise: Optional[torch.Tensor] = None,
                 seed: int = 0, row_offset: int = 0, precomp_actions: Optional[torch.Tensor] = None,
                 horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
-                out: Optional[dict] = None) -> dict:
+                out: Optional[dict] = None, keep_packed: bool = False) -> dict:
         cfg = self.cfg
         H = horizon if horizon is not None else cfg.H
         ccfg = cfg.to_c()
@@ -321,8 +333,14 @@ class ImaginationEngine:
                 "actor_raw": torch.empty((H, n, cfg.A if cfg.discrete else 2 * cfg.A), device=dev,
                                          dtype=torch.float32) if want_actor_raw else None,
             }
+        if keep_packed and out.get("determ_packed") is None:
+            # packed bf16 state images, one slot per step, kept for the actor-critic update (K4)
+            rows = round_up(n, 128)
+            out["determ_packed"] = torch.empty((H + 1, rows, round_up(cfg.D, 64)), device=dev, dtype=torch.bfloat16)
+            out["stoch_packed"] = torch.empty((H + 1, rows, round_up(S, 64)), device=dev, dtype=torch.bfloat16)
         co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
-                                                      "rewards", "discounts", "values", "actor_raw")])
+                                                      "rewards", "discounts", "values", "actor_raw",
+                                                      "determ_packed", "stoch_packed")])
         nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)),
                    _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
                    _ptr(None if precomp_actions is None else _f32c(precomp_actions)))
@@ -331,6 +349,81 @@ class ImaginationEngine:
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K4
+# ------------------------------------------------------------------------------------------------
+def _mlp_grads(module_seq, keep: list) -> MlpGrads:
+    """Gradient pointers of an fc_nn Sequential (Linear at 0,3,6,9,12; LayerNorm|Identity at 1,4,7,10);
+    .grad tensors are allocated here when missing — the kernels overwrite every element."""
+    mg = MlpGrads()
+
+    def grad_of(p):
+        if p.grad is None or p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+            p.grad = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+        keep.append(p.grad)
+        return p.grad.data_ptr()
+
+    for i, li in enumerate((0, 3, 6, 9, 12)):
+        mg.w[i], mg.b[i] = grad_of(module_seq[li].weight), grad_of(module_seq[li].bias)
+    for i, li in enumerate((1, 4, 7, 10)):
+        m = module_seq[li]
+        if isinstance(m, torch.nn.LayerNorm):
+            mg.ln_g[i], mg.ln_b[i] = grad_of(m.weight), grad_of(m.bias)
+    return mg
+
+
+class ACUpdateEngine:
+    """Packed weights + workspace of K4 (critic / actor losses and their backward pass, ac.py:68-81,113-146)."""
+
+    def __init__(self, cfg: ImagineConfig, rho: float, eta: float, metrics_samples: int = 128, device="cuda"):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.ccfg = AcCfg(cfg.D, cfg.groups, cfg.classes, cfg.A, cfg.hidden, int(cfg.discrete), int(cfg.layer_norm),
+                          cfg.H, float(rho), float(eta), int(metrics_samples))
+        self.device = torch.device(device)
+        nbytes = self.lib.rlsb_ac_packed_bytes(C.byref(self.ccfg))
+        if nbytes == 0:
+            raise _lib.RlsbError(f"unsupported actor-critic update config {cfg} (continuous actors need K1 backward)")
+        self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+        self._ws, self._ws_rows = None, 0
+        self.scalars = torch.zeros(_lib.AC_SCALARS, device=self.device, dtype=torch.float32)
+
+    def pack(self, actor_sd: dict, critic_sd: dict, actor_prefix="actor.", critic_prefix="critic.") -> None:
+        keep: list = []
+        a = _mlp_params(actor_sd, actor_prefix, keep)
+        c = _mlp_params(critic_sd, critic_prefix, keep)
+        check(self.lib.rlsb_ac_pack(C.byref(self.ccfg), C.byref(a), C.byref(c), self.packed.data_ptr(), _stream()),
+              "rlsb_ac_pack")
+        self._keep = keep
+
+    def update(self, rollout: dict, vs: torch.Tensor, w: torch.Tensor, actor_seq, critic_seq, seed: int = 0,
+               horizon: Optional[int] = None) -> torch.Tensor:
+        """Writes .grad of every parameter of ``actor_seq`` / ``critic_seq`` (fc_nn Sequentials) and returns the
+        RLSB_AC_SCALARS loss / metric vector (device tensor, see _lib.AC_SCALAR_NAMES)."""
+        if rollout.get("determ_packed") is None:
+            raise _lib.RlsbError("ACUpdateEngine.update needs a rollout made with keep_packed=True")
+        n = rollout["determ"].shape[1]
+        H = horizon if horizon is not None else self.cfg.H
+        ccfg = AcCfg.from_buffer_copy(self.ccfg)
+        ccfg.H = H
+        if self._ws is None or self._ws_rows < n:
+            nbytes = self.lib.rlsb_ac_workspace_bytes(C.byref(ccfg), n)
+            self._ws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+            self._ws_rows = n
+        keep: list = []
+        ga, gc = _mlp_grads(actor_seq, keep), _mlp_grads(critic_seq, keep)
+        vs, w = _f32c(vs), _f32c(w)
+        values, actions = _f32c(rollout["values"]), _f32c(rollout["actions"])
+        if vs.numel() != H * n or w.numel() != (H + 1) * n:
+            raise _lib.RlsbError(f"ACUpdateEngine.update: vs {tuple(vs.shape)} / w {tuple(w.shape)} for H={H}, N={n}")
+        check(self.lib.rlsb_ac_update(C.byref(ccfg), self.packed.data_ptr(), n, rollout["determ_packed"].data_ptr(),
+                                      rollout["stoch_packed"].data_ptr(), vs.data_ptr(), w.data_ptr(),
+                                      values.data_ptr(), actions.data_ptr(), seed, C.byref(ga), C.byref(gc),
+                                      self.scalars.data_ptr(), self._ws.data_ptr(), _stream()), "rlsb_ac_update")
+        return self.scalars
 
 
 # ------------------------------------------------------------------------------------------------

@@ -57,11 +57,19 @@ class Optimizer:
         self.clip = clip
 
     def step(self, loss):
-        metrics = {}
         self.optimizer.zero_grad(set_to_none=True)
         (self.scaler.scale(loss) if self.scaler else loss).backward()
         if self.scaler:
             self.scaler.unscale_(self.optimizer)
+        return self._apply()
+
+    def step_with_grads(self):
+        """Same as ``step`` from the all-reduce on, for gradients a kernel already wrote into ``.grad``
+        (rlsb_ac_update replaces zero_grad + loss.backward(), optimizer.py:55-57)."""
+        return self._apply()
+
+    def _apply(self):
+        metrics = {}
         allreduce_grads_(self.model.parameters())
         if self.log_grad:
             for tag, value in self.model.named_parameters():
