@@ -111,6 +111,9 @@ typedef struct {
    * (world_model.py:137).  1 = reproduce that NaN (reference-exact), 0 = ties resolve to 1 —
    * a single NaN discount poisons every parameter through the losses. */
   int32_t discount_nan_on_tie;
+  /* 1: the packed blob also holds the transposed weight images rlsb_imagine_bwd needs
+   * (continuous actors, rho != 1: dynamics back-propagation, ac.py:121-123); requires D <= 512 */
+  int32_t with_backward;
 } rlsb_imagine_cfg;
 
 /* fp32 parameters in nn.Linear layout (weight = [out, in] row-major); NULL = absent.
@@ -163,6 +166,8 @@ typedef struct {
    * (both or neither; NULL = the rollout ping-pongs inside its workspace) */
   void* determ_packed;
   void* stoch_packed;
+  /* activation tape for rlsb_imagine_bwd (rlsb_imagine_tape_bytes bytes), or NULL */
+  void* tape;
 } rlsb_imagine_out;
 
 /* bytes needed for packed weights / activation workspace for N start states */
@@ -176,9 +181,23 @@ int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N,
                      const float* z0, const float* logits0, const rlsb_noise* noise,
                      const rlsb_imagine_out* out, void* workspace, void* stream);
 
+/* backward of the rollout w.r.t. the sampled actions (activation gradients only: the world model and the
+ * target critic receive no parameter update from the actor loss, dreamer_v2.py:199-207):
+ *   g_rewards, g_values : (H+1, N) d loss / d rewards[t], d loss / d values[t]  (rlsb_lambda_return_bwd)
+ *   g_actions           : (H, N, A) d loss / d a_t, a_t = the action sampled in state t (out.actions[t+1])
+ * Chain per step (reference autograd of predict_next): reward / critic heads -> [h_t, z_t];
+ * z_t = onehot + probs - probs.detach() -> prior logits -> prior MLP -> h_t; GRU + LayerNorm backward ->
+ * (x_t, h_{t-1}); x_t -> (z_{t-1}, a_{t-1}).  The forward call must have been given out.tape. */
+size_t rlsb_imagine_tape_bytes(const rlsb_imagine_cfg* cfg, int64_t N);
+size_t rlsb_imagine_bwd_workspace_bytes(const rlsb_imagine_cfg* cfg, int64_t N);
+int rlsb_imagine_bwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const rlsb_imagine_out* fwd,
+                     const float* g_rewards, const float* g_values, float* g_actions, void* workspace,
+                     void* stream);
+
 /* ---- K4: actor-critic update -------------------------------------------------------------------
- * replaces, for a discrete actor (rho == 1: nothing differentiates through the rollout,
- * agents/dreamer/ac.py:90-92,121-125), the loss half of DreamerV2.train
+ * replaces the loss half of DreamerV2.train (for a discrete actor rho == 1 and nothing differentiates
+ * through the rollout, agents/dreamer/ac.py:90-92,121-125; for a continuous actor the dynamics term enters
+ * through g_actions)
  * (agents/dreamer_v2.py:199-207): ImaginativeCritic.calculate_loss (agents/dreamer/ac.py:68-81),
  * ImaginativeActor.calculate_loss (ac.py:113-146) and the two loss.backward() calls of
  * Optimizer.step (utils/optimizer.py:55-57).  Outputs are the fp32 parameter gradients in nn.Linear /
@@ -187,7 +206,7 @@ int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N,
  * steps 0..H-1 are used (critic: all H, actor: the first H-1, ac.py / dreamer_v2.py:203-206). */
 typedef struct {
   int32_t D, groups, classes, A, hidden;
-  int32_t discrete;        /* must be 1 (continuous actors need the K1 backward pass) */
+  int32_t discrete;        /* 1: one-hot categorical actor; 0: TruncatedNormal actor (2A outputs) */
   int32_t layer_norm;
   int32_t H;               /* imagination horizon */
   float rho;               /* reinforce fraction (1 for discrete actors) */
@@ -228,10 +247,12 @@ int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor, const rls
                  void* packed, void* stream);
 /* vs: (H, N) lambda-returns; w: (H+1, N) cumprod weights; values: (H+1, N) target critic (baseline and
  * critic/avg_target_value); actions: (H+1, N, A) one-hot (row t+1 = action taken in state t);
+ * g_actions: (H, N, A) d loss_actor / d a_t from rlsb_imagine_bwd when rho != 1 (continuous actor), else NULL;
  * scalars: RLSB_AC_SCALARS floats (device).  seed keys the Philox stream of the metric draws. */
 int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,
                    const void* stoch_packed, const float* vs, const float* w, const float* values,
-                   const float* actions, uint64_t seed, const rlsb_mlp_grads* actor_grads,
+                   const float* actions, const float* g_actions, uint64_t seed,
+                   const rlsb_mlp_grads* actor_grads,
                    const rlsb_mlp_grads* critic_grads, float* scalars, void* workspace, void* stream);
 
 /* ---- K3: slot attention ---------------------------------------------------------------------

@@ -11,6 +11,11 @@ Fixtures
                               re-checked here against the reference's ImaginativeCritic._lambda_return.
   slot_attention.npz          SlotAttention.forward of the reference (vision/slot_attention.py:52-77),
                               4 slots x 384, 196 tokens, 2 iterations, explicit prev_slots.
+                              Also the GRADIENTS the reference's autograd produces for
+                              loss_actor.backward() / loss_critic.backward() (optimizer.py:55-57):
+                              d loss_actor / d actions (continuous actors: the quantity rlsb_imagine_bwd
+                              returns), and per parameter tensor its L2 norm and 64 probed entries
+                              (indices from grad_probe_indices()).
   imagine_<case>.npz          DreamerV2.imagine_trajectory (dreamer_v2.py:68-96) outputs, the
                               target-critic values, lambda-returns (ac.py:64-66), cumprod weights
                               (dreamer_v2.py:192-197) and the critic / actor losses
@@ -38,6 +43,9 @@ CASES = {
     # config 2 dims (agent/dreamer_v2.yaml): D=200, continuous A=12, no layer_norm, no discount head
     "c2": dict(D=200, A=12, discrete=False, layer_norm=False, predict_discount=False, N=6, H=3,
                entropy_scale=1e-5, gamma=0.99, param_seed=21, start_seed=22, noise_seed=23),
+    # config-2 dims with layer_norm on: pins the LayerNorm-backward branches of the rollout's backward pass
+    "c2_ln": dict(D=200, A=12, discrete=False, layer_norm=True, predict_discount=False, N=6, H=3,
+                  entropy_scale=1e-5, gamma=0.99, param_seed=51, start_seed=52, noise_seed=53),
     # longer horizon / more rows, config-2 dims (cheap to store)
     "c2_long": dict(D=200, A=6, discrete=True, layer_norm=True, predict_discount=True, N=40, H=15,
                     entropy_scale=1e-4, gamma=0.99, param_seed=31, start_seed=32, noise_seed=33),
@@ -79,6 +87,12 @@ def known_answers():
     print("lambda_known_answers.json: 5 vectors verified against the reference")
 
 
+def grad_probe_indices(numel: int, k: int = 64) -> torch.Tensor:
+    """the probed flat indices of a parameter gradient (shared by the generator and the tests)"""
+    g = torch.Generator().manual_seed(1000003 + numel)
+    return torch.randint(0, numel, (k,), generator=g)
+
+
 def run_case(name, case):
     D, A, H, N = case["D"], case["A"], case["H"], case["N"]
     wm_sd, actor_sd, critic_sd = orc.make_params(case["param_seed"], D=D, A=A, discrete=case["discrete"],
@@ -91,6 +105,18 @@ def run_case(name, case):
     rh.load_params(agent, wm_sd, actor_sd, critic_sd)
     state = rh.ref_state(agent, h0, z0)
     q = rh.NoiseQueue(lat, act)
+    # observation seam (no arithmetic changed): remember the action tensor each predict_next receives so that
+    # d loss_actor / d a_t can be read off after backward
+    seen_actions = []
+    orig_predict_next = agent.world_model.predict_next
+
+    def spy_predict_next(prev_state, a):
+        if a.requires_grad:
+            a.retain_grad()
+        seen_actions.append(a)
+        return orig_predict_next(prev_state, a)
+
+    agent.world_model.predict_next = spy_predict_next
     with rh.injected_noise(q):
         # agents/dreamer_v2.py:182-207 (second half of DreamerV2.train), reference methods only
         states, actions, rewards, discounts = agent.imagine_trajectory(state)
@@ -103,6 +129,22 @@ def run_case(name, case):
         losses_c, metrics_c = agent.critic.calculate_loss(zs[:-1], vs, w[:-1])
         losses_a, metrics_a = agent.actor.calculate_loss(zs[:-2], vs[1:], agent.critic.target_critic(zs[:-2]).mode,
                                                          w[:-2], actions[1:-1])
+        # the gradients of Optimizer.step (utils/optimizer.py:55-57), reference autograd
+        for p_ in list(agent.actor.parameters()) + list(agent.critic.parameters()):
+            p_.grad = None
+        losses_a["loss_actor"].backward(retain_graph=True)
+        losses_c["loss_critic"].backward()
+    grad_names, grad_norms, grad_probes = [], [], []
+    for prefix, mod in (("actor.", agent.actor.actor), ("critic.", agent.critic.critic)):
+        for n_, p_ in mod.named_parameters():
+            g_ = p_.grad if p_.grad is not None else torch.zeros_like(p_)
+            grad_names.append(prefix + n_)
+            grad_norms.append(g_.norm().item())
+            grad_probes.append(g_.flatten()[grad_probe_indices(g_.numel())].numpy())
+    if seen_actions and seen_actions[0].grad is not None:
+        g_actions = torch.cat([a_.grad for a_ in seen_actions]).detach().numpy()   # (H, N, A): d loss_actor / d a_t
+    else:
+        g_actions = np.zeros((0,), np.float32)
     assert q.log[:2] == (["action", "latent"] if case["discrete"] else ["action_normal", "latent"]), q.log[:4]
     assert not q.latent and not q.action, "noise not fully consumed"
     f = lambda x: x.detach().squeeze(-1).numpy().astype(np.float32) if x.dim() == 3 and x.shape[-1] == 1 else x.detach().numpy().astype(np.float32)
@@ -117,7 +159,9 @@ def run_case(name, case):
         critic_avg_target_value=np.float32(metrics_c["critic/avg_target_value"].item()),
         critic_avg_lambda_value=np.float32(metrics_c["critic/avg_lambda_value"].item()),
         critic_avg_predicted_value=np.float32(metrics_c["critic/avg_predicted_value"].item()),
-        meta=json.dumps({**case, "lam": 0.95, "rho": 1.0 if case["discrete"] else 0.0}),
+        grad_actions=g_actions.astype(np.float32), grad_norms=np.asarray(grad_norms, np.float32),
+        grad_probes=np.stack(grad_probes).astype(np.float32),
+        meta=json.dumps({**case, "lam": 0.95, "rho": 1.0 if case["discrete"] else 0.0, "grad_names": grad_names}),
     )
     np.savez_compressed(OUT / f"imagine_{name}.npz", **out)
     print(f"imagine_{name}.npz written:", {k: getattr(v, 'shape', None) for k, v in out.items() if k != 'meta'})

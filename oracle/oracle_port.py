@@ -259,6 +259,55 @@ def ac_losses(traj, actor_sd, critic_sd, *, lam, discrete, rho, eta, bf16=False)
                 loss_actor_reinforce=l_reinforce, loss_actor_dynamics_backprop=l_dyn, loss_actor_entropy=l_ent)
 
 
+def imagine_st(wm, actor, critic, h0, z0, lat, act, *, H, A, bf16=False, keep_action_grads=False):
+    """Differentiable rollout for a continuous actor (rho != 1): the autograd graph DreamerV2.imagine_trajectory
+    builds (dreamer_v2.py:83-91) — actor on the DETACHED state, unclamped rsample, straight-through latents
+    (rssm.py:34-37), reward head and target critic on every state.  lat: uniforms (H,N,1024), act: normals (H,N,A)."""
+    N = h0.shape[0]
+    h, z = h0, z0
+    out = {k: [] for k in ("determ", "stoch", "actions", "rewards", "discounts", "values", "stoch_idx")}
+    out["determ"].append(h); out["stoch"].append(z); out["actions"].append(torch.zeros(N, A))
+    out["stoch_idx"].append(z.view(N, 32, 32).argmax(-1))
+    step_actions = []
+    for t in range(H + 1):
+        s = torch.cat([h, z], -1)
+        out["rewards"].append(mlp(s, wm, "reward_predictor.", bf16).squeeze(-1))
+        out["discounts"].append(torch.ones(N))
+        out["values"].append(mlp(s, critic, "target_critic.", bf16).squeeze(-1))
+        if t == H:
+            break
+        mu, sd_ = mlp(s.detach(), actor, "actor.", bf16).chunk(2, -1)
+        a = torch.tanh(mu) + (2 * torch.sigmoid(sd_ / 2) + 0.1) * act[t]
+        if keep_action_grads and a.requires_grad:
+            a.retain_grad()
+        step_actions.append(a)
+        h, logits = rssm_predict_next(h, z, a, wm, bf16=bf16)
+        lg = logits.view(N, 32, 32)
+        idx = sample_categorical(lg.detach(), lat[t].view(N, 32, 32))
+        probs = torch.softmax(lg, -1)
+        z = (torch.nn.functional.one_hot(idx, 32).float() + probs - probs.detach()).view(N, 1024)
+        out["determ"].append(h); out["stoch"].append(z); out["actions"].append(a); out["stoch_idx"].append(idx)
+    traj = {k: torch.stack(v) for k, v in out.items()}
+    traj["_step_actions"] = step_actions
+    return traj
+
+
+def continuous_update_grads(wm, actor, critic, h0, z0, lat, act, *, H, A, lam=0.95, rho=0.0, eta=1e-5, bf16=False):
+    """loss_actor.backward() / loss_critic.backward() of the continuous-actor hot path (dreamer_v2.py:182-207,
+    optimizer.py:55-57): returns losses, d loss_actor / d a_t (H,N,A) and the parameter gradients."""
+    actor = {k: v.detach().clone().requires_grad_() for k, v in actor.items()}
+    critic = {k: (v.detach().clone().requires_grad_() if k.startswith("critic.") else v.detach()) for k, v in critic.items()}
+    traj = imagine_st(wm, actor, critic, h0, z0, lat, act, H=H, A=A, bf16=bf16, keep_action_grads=True)
+    losses = ac_losses(traj, actor, critic, lam=lam, discrete=False, rho=rho, eta=eta, bf16=bf16)
+    losses["loss_actor"].backward(retain_graph=True)
+    g_actions = torch.stack([a.grad if a.grad is not None else torch.zeros_like(a) for a in traj["_step_actions"]])
+    losses["loss_critic"].backward()
+    grads = {k: v.grad for k, v in actor.items()}
+    grads |= {k: v.grad for k, v in critic.items() if k.startswith("critic.")}
+    return dict(losses={k: v.detach() for k, v in losses.items()}, g_actions=g_actions.detach(), grads=grads,
+                traj={k: (v.detach() if torch.is_tensor(v) else v) for k, v in traj.items() if k != "_step_actions"})
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic parameters with the reference's state-dict names and default nn.Linear init
 # ------------------------------------------------------------------------------------------------
@@ -370,26 +419,7 @@ class HotPathCPU:
 
     def _imagine_st(self, h0, z0, lat, act):
         """continuous actor: rollout with straight-through latents so that the dynamics loss reaches the actor"""
-        H, N, A = self.H, h0.shape[0], self.A
-        h, z = h0, z0
-        out = {k: [] for k in ("determ", "stoch", "actions", "rewards", "discounts", "values")}
-        out["determ"].append(h); out["stoch"].append(z); out["actions"].append(torch.zeros(N, A))
-        for t in range(H + 1):
-            s = torch.cat([h, z], -1)
-            out["rewards"].append(mlp(s, self.wm, "reward_predictor.").squeeze(-1))
-            out["discounts"].append(torch.ones(N))
-            out["values"].append(mlp(s, self.critic, "target_critic.").squeeze(-1))
-            if t == H:
-                break
-            mu, sd_ = mlp(s.detach(), self.actor, "actor.").chunk(2, -1)
-            a = torch.tanh(mu) + (2 * torch.sigmoid(sd_ / 2) + 0.1) * act[t]
-            h, logits = rssm_predict_next(h, z, a, self.wm)
-            lg = logits.view(N, 32, 32)
-            idx = sample_categorical(lg.detach(), lat[t].view(N, 32, 32))
-            probs = torch.softmax(lg, -1)
-            z = (torch.nn.functional.one_hot(idx, 32).float() + probs - probs.detach()).view(N, 1024)
-            out["determ"].append(h); out["stoch"].append(z); out["actions"].append(a)
-        return {k: torch.stack(v) for k, v in out.items()}
+        return imagine_st(self.wm, self.actor, self.critic, h0, z0, lat, act, H=self.H, A=self.A)
 
 
 # ------------------------------------------------------------------------------------------------

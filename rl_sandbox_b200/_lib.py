@@ -23,7 +23,7 @@ class RlsbError(RuntimeError):
 class ImagineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "predict_discount",
-        "with_critic", "H", "discount_nan_on_tie")]
+        "with_critic", "H", "discount_nan_on_tie", "with_backward")]
 
 
 class MlpParams(C.Structure):
@@ -46,7 +46,7 @@ class Noise(C.Structure):
 class ImagineOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "determ", "logits", "stoch_idx", "stoch", "actions", "rewards", "discounts", "values",
-        "actor_raw", "determ_packed", "stoch_packed")]
+        "actor_raw", "determ_packed", "stoch_packed", "tape")]
 
 
 class AcCfg(C.Structure):
@@ -125,8 +125,11 @@ def load() -> C.CDLL:
         "rlsb_ac_packed_bytes": (sz, [C.POINTER(AcCfg)]),
         "rlsb_ac_workspace_bytes": (sz, [C.POINTER(AcCfg), i64]),
         "rlsb_ac_pack": (C.c_int, [C.POINTER(AcCfg), C.POINTER(MlpParams), C.POINTER(MlpParams), vp, vp]),
-        "rlsb_ac_update": (C.c_int, [C.POINTER(AcCfg), vp, i64, vp, vp, vp, vp, vp, vp, u64, C.POINTER(MlpGrads),
+        "rlsb_ac_update": (C.c_int, [C.POINTER(AcCfg), vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(MlpGrads),
                                      C.POINTER(MlpGrads), vp, vp, vp]),
+        "rlsb_imagine_tape_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
+        "rlsb_imagine_bwd_workspace_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
+        "rlsb_imagine_bwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, C.POINTER(ImagineOut), vp, vp, vp, vp, vp]),
     })
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -92,7 +92,8 @@ class DreamerV2(RlAgent):
             cfg = ops.ImagineConfig(D=wm.rssm_dim, A=self.actions_num, discrete=self.is_discrete,
                                     layer_norm=bool(wm.layer_norm), predict_discount=bool(wm.predict_discount),
                                     H=self.imagination_horizon, groups=wm.latent_dim, classes=wm.latent_classes,
-                                    with_critic=True, discount_nan_on_tie=self.reference_exact_discount_nan)
+                                    with_critic=True, discount_nan_on_tie=self.reference_exact_discount_nan,
+                                    with_backward=(not self.is_discrete) and wm.rssm_dim <= 512 and wm.rssm_dim % 8 == 0)
             self._engine = ops.ImaginationEngine(cfg, device=self.device)
         if self._packed_version != self._weights_version:
             self._engine.pack(self.world_model.state_dict(), self.actor.state_dict(), self.critic.state_dict())
@@ -112,22 +113,27 @@ class DreamerV2(RlAgent):
         return self._ac_engine
 
     def _can_fuse_ac(self) -> bool:
-        return (self.fused_ac_update and self.is_discrete and self.actor.rho == 1.0 and not self.is_f16 and
-                self._flat_wm() and str(self.device).startswith('cuda') and self.world_model.rssm_dim > 0)
+        if not (self.fused_ac_update and not self.is_f16 and self._flat_wm() and str(self.device).startswith('cuda')):
+            return False
+        if self.is_discrete:
+            return self.actor.rho == 1.0   # nothing differentiates through the rollout (ac.py:121-125)
+        # continuous actor: dynamics back-propagation runs through rlsb_imagine_bwd (needs the tape: D <= 512)
+        return self.world_model.rssm_dim <= 512 and self.world_model.rssm_dim % 8 == 0
 
     def mark_weights_changed(self):
         self._weights_version += 1
 
     def imagine_trajectory(self, init_state: State, precomp_actions: t.Optional[list[Action]] = None,
                            horizon: t.Optional[int] = None, noise: t.Optional[dict] = None,
-                           keep_packed: bool = False) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
+                           keep_packed: bool = False, tape: bool = False
+                           ) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
         """H-step closed-loop rollout from (1, N, .) start states (dreamer_v2.py:68-96).
 
         ``noise`` (extension, optional): {'latent_uniforms': (H,N,1024), 'action_noise': (H,N,A)} to
         inject explicit noise, or {'seed': int, 'row_offset': int} for the Philox stream."""
         if horizon is None:
             horizon = self.imagination_horizon
-        needs_grad = torch.is_grad_enabled() and self.actor.rho != 1.0 and precomp_actions is None
+        needs_grad = torch.is_grad_enabled() and self.actor.rho != 1.0 and precomp_actions is None and not tape
         if needs_grad:
             return self._imagine_autograd(init_state, horizon)
         if not init_state.determ.is_cuda:
@@ -150,7 +156,7 @@ class DreamerV2(RlAgent):
         out = eng.rollout(h0, z0, logits0, latent_uniforms=noise.get('latent_uniforms'),
                           action_noise=noise.get('action_noise'), seed=noise.get('seed', 0),
                           row_offset=noise.get('row_offset', 0), precomp_actions=pre, horizon=horizon,
-                          keep_packed=keep_packed, want_stoch=not keep_packed)
+                          keep_packed=keep_packed, want_stoch=not keep_packed, tape=tape)
         self.last_rollout = out
         wm = self.world_model
         states = State(out['determ'], out['logits'].view(horizon + 1, N, wm.latent_dim, wm.latent_classes),
@@ -249,13 +255,22 @@ class DreamerV2(RlAgent):
         forward, losses, backward to parameter gradients in librlsb) -> all-reduce, clip, AdamW."""
         from rl_sandbox_b200 import _lib, ops
         with torch.no_grad():
-            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True)
+            dyn = self.actor.rho != 1.0   # dynamics back-propagation (ac.py:121-123): K2 bwd -> K1 bwd -> g_actions
+            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True, tape=dyn)
             k1 = self.last_rollout
+            H, n = k1['determ'].shape[0] - 1, k1['determ'].shape[1]
             # reward_normalizer is the identity (momentum 1.0, world_model.py:111; SURVEY hard part 7)
             vs, w, _ = ops.lambda_return(k1['rewards'], k1['values'], k1['discounts'], self.critic.lambda_)
+            g_actions = None
+            if dyn:
+                # d/d vs of -mean((1 - rho) * vs[1:] * w[:-2]) (vs has H rows: V_0 .. V_{H-1})
+                g_vs = torch.zeros_like(vs)
+                g_vs[1:] = w[:H - 1] * (-(1.0 - float(self.actor.rho)) / ((H - 1) * n))
+                g_r, g_v, _ = ops.lambda_return_bwd(g_vs, k1['values'], k1['discounts'], vs, self.critic.lambda_)
+                g_actions = self._engine.backward(k1, g_r, g_v)
             ac = self._get_ac_engine()
             scal = ac.update(k1, vs, w, self.actor.actor, self.critic.critic, seed=self._noise_seed + self._rollouts,
-                             horizon=k1['determ'].shape[0] - 1)
+                             horizon=H, g_actions=g_actions)
         metrics_a = self.actor_optimizer.step_with_grads()
         metrics_c = self.critic_optimizer.step_with_grads()
         self.critic.update_target()

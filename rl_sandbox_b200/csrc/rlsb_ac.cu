@@ -52,10 +52,9 @@ struct AcPlan {
 
 int make_ac_plan(const rlsb_ac_cfg& c, AcPlan& P) {
   if (c.classes != 32 || c.groups <= 0 || c.groups > 64 || c.D <= 0 || c.A <= 0 || c.hidden <= 0 || c.H < 2) return -10;
-  if (!c.discrete) return -14;   // the continuous actor needs the K1 backward pass (dynamics back-propagation)
   P.D = c.D; P.S = c.groups * c.classes; P.A = c.A; P.Hd = c.hidden; P.H = c.H;
   P.Dp = ru(P.D, 64); P.Sp = ru(P.S, 64); P.Hp = ru(P.Hd, 64);
-  P.Aout = c.A;
+  P.Aout = c.discrete ? c.A : 2 * c.A;   // TruncatedNormal head: (mean | std) pre-activations (dists.py:187-190)
   if (P.Aout > 32 || ru(P.Hd, 32) > 512) return -12;
   size_t cur = 0;
   for (int l = 0; l < 5; ++l) {
@@ -150,8 +149,15 @@ __global__ void ones_tile_kernel(__nv_bfloat16* dst) {
 // ------------------------------------------------------------------------------------------
 enum AcAccum {
   ACC_LOSS_CRITIC = 0, ACC_REINFORCE, ACC_ENTROPY, ACC_PRED, ACC_TARGET, ACC_LAMBDA, ACC_AVG_SD, ACC_MEAN_VAL,
-  ACC_COUNT
+  ACC_DYNAMICS, ACC_AVG_VAL, ACC_COUNT
 };
+constexpr int kAccMinKey = 12, kAccMaxKey = 13;   // int-encoded float min / max live in accum[12], accum[13] (low words)
+
+__device__ __forceinline__ int float_key(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 struct AcLossArgs {
   const float* head_out;   // [2][M][32]
@@ -161,6 +167,8 @@ struct AcLossArgs {
   const float* w;          // (H+1, N)
   const float* values;     // (H+1, N) target critic
   const float* actions;    // (H+1, N, A)
+  const float* g_actions;  // (H, N, A) d loss / d a_t from rlsb_imagine_bwd (continuous actor) or nullptr
+  int discrete;
   float rho, eta;
   int metrics_samples;
   uint64_t seed;
@@ -195,7 +203,73 @@ __global__ void __launch_bounds__(128) ac_loss_kernel(const AcLossArgs a) {
       acc[ACC_TARGET] = __ldg(a.values + ti);
       acc[ACC_LAMBDA] = target;
       // ---- actor (ac.py:113-146), states 0..H-2 ---------------------------------------------------
-      if (t < a.H - 1) {
+      if (!a.discrete) {
+        // ---- TruncatedNormal actor (dists.py:108-129,187-190): mu = tanh(raw), sd = 2 sigmoid(raw_s / 2) + 0.1 ----
+        // The loss terms cover states 0..H-2 (ac.py:113-135); the dynamics gradient d loss / d a_t reaches the
+        // actor through EVERY sampled action a_0..a_{H-1} (a_{H-1} moves s_H and with it the bootstrap value).
+        const bool in_loss = t < a.H - 1;
+        const float* lg = a.head_out + m * 32;
+        const float vnext = in_loss ? __ldg(a.vs + ti + a.N) : 0.f;
+        const float adv = in_loss ? vnext - __ldg(a.values + ti) : 0.f;
+        const float* act = a.actions + (ti + a.N) * a.A;
+        const float inv_cnt = in_loss ? 1.0f / (static_cast<float>(a.H - 1) * static_cast<float>(a.N)) : 0.f;
+        if (in_loss) acc[ACC_DYNAMICS] = -(1.0f - a.rho) * vnext * wt;
+        float logp = 0.f, ent = 0.f, sum_mu = 0.f, sum_avg = 0.f, sum_sd = 0.f;
+        float smin = 3.0e38f, smax = -3.0e38f;
+        for (int k = 0; k < a.A; ++k) {
+          const float mu = tanhf(lg[k]);
+          const float sg = 1.0f / (1.0f + expf(-0.5f * lg[a.A + k]));
+          const float sd = 2.0f * sg + 0.1f;
+          const float e = (__ldg(act + k) - mu) / sd;
+          const float lsd = logf(sd);
+          logp += -0.5f * e * e - lsd - 0.91893853320467274f;
+          ent += 1.4189385332046727f + lsd;
+          const float ga = a.g_actions ? __ldg(a.g_actions + ti * a.A + k) : 0.f;
+          const float g_mu = ga + (-a.rho * wt * adv * (e / sd)) * inv_cnt;
+          const float g_sd = ga * e + (-a.rho * wt * adv * ((e * e - 1.0f) / sd) - a.eta * wt / sd) * inv_cnt;
+          dya[k] = g_mu * (1.0f - mu * mu);
+          dya[a.A + k] = g_sd * sg * (1.0f - sg);
+          sum_mu += mu;
+          if (a.metrics_samples > 0 && in_loss) {   // `metrics_samples` draws mu + sd * eps per element (ac.py:137-143)
+            float s1 = 0.f, s2 = 0.f, emin = 3.0e38f, emax = -3.0e38f;
+            for (int sidx = 0; sidx < a.metrics_samples; sidx += 4) {
+              uint32_t o[4];
+              rlsb_philox4x32(static_cast<uint32_t>(m), static_cast<uint32_t>(m >> 32) ^ (static_cast<uint32_t>(k) << 8), 7u,
+                              static_cast<uint32_t>(sidx >> 2), static_cast<uint32_t>(a.seed),
+                              static_cast<uint32_t>(a.seed >> 32), o);
+              float z[4];
+              const float r0 = sqrtf(-2.0f * __logf(rlsb_u32_to_uniform(o[0])));
+              const float r1 = sqrtf(-2.0f * __logf(rlsb_u32_to_uniform(o[2])));
+              __sincosf(6.2831853071795865f * rlsb_u32_to_uniform(o[1]), &z[1], &z[0]);
+              __sincosf(6.2831853071795865f * rlsb_u32_to_uniform(o[3]), &z[3], &z[2]);
+              z[0] *= r0; z[1] *= r0; z[2] *= r1; z[3] *= r1;
+              for (int j = 0; j < 4 && sidx + j < a.metrics_samples; ++j) {
+                s1 += z[j];
+                s2 = fmaf(z[j], z[j], s2);
+                emin = fminf(emin, z[j]);
+                emax = fmaxf(emax, z[j]);
+              }
+            }
+            const float inv_s = 1.0f / static_cast<float>(a.metrics_samples);
+            const float mbar = s1 * inv_s;
+            sum_avg += mu + sd * mbar;
+            sum_sd += sd * sqrtf(fmaxf(s2 * inv_s - mbar * mbar, 0.f));
+            smin = fminf(smin, mu + sd * emin);
+            smax = fmaxf(smax, mu + sd * emax);
+          }
+        }
+        if (in_loss) {
+          acc[ACC_REINFORCE] = -a.rho * logp * wt * adv;
+          acc[ACC_ENTROPY] = -a.eta * ent * wt;
+          acc[ACC_MEAN_VAL] = sum_mu;
+          acc[ACC_AVG_VAL] = sum_avg;
+          acc[ACC_AVG_SD] = sum_sd;
+        }
+        if (a.metrics_samples > 0 && in_loss) {
+          atomicMin(reinterpret_cast<int*>(a.accum + kAccMinKey), float_key(smin));
+          atomicMax(reinterpret_cast<int*>(a.accum + kAccMaxKey), float_key(smax));
+        }
+      } else if (t < a.H - 1) {
         const float* lg = a.head_out + m * 32;
         const float adv = __ldg(a.vs + ti + a.N) - __ldg(a.values + ti);   // (vs[1:] - baseline[:-2])
         const float* act = a.actions + (ti + a.N) * a.A;                    // actions[1:-1]
@@ -299,7 +373,8 @@ __global__ void __launch_bounds__(128) ac_loss_kernel(const AcLossArgs a) {
   }
 }
 
-__global__ void ac_finalize_kernel(const double* accum, int H, long long N, int A, int metrics_samples, float* out) {
+__global__ void ac_finalize_kernel(const double* accum, int H, long long N, int A, int metrics_samples, int discrete,
+                                   float* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double nc = static_cast<double>(H) * N, na = static_cast<double>(H - 1) * N;
   const float lc = static_cast<float>(accum[ACC_LOSS_CRITIC] / nc);
@@ -307,15 +382,21 @@ __global__ void ac_finalize_kernel(const double* accum, int H, long long N, int 
   const float le = static_cast<float>(accum[ACC_ENTROPY] / na);
   out[RLSB_AC_LOSS_CRITIC] = lc;
   out[RLSB_AC_LOSS_ACTOR_REINFORCE] = lr;
-  out[RLSB_AC_LOSS_ACTOR_DYNAMICS] = 0.f;
+  const float ld = static_cast<float>(accum[ACC_DYNAMICS] / na);   // 0 for rho == 1 (ac.py:124-125)
+  out[RLSB_AC_LOSS_ACTOR_DYNAMICS] = ld;
   out[RLSB_AC_LOSS_ACTOR_ENTROPY] = le;
-  out[RLSB_AC_LOSS_ACTOR] = lr + 0.f + le;
+  out[RLSB_AC_LOSS_ACTOR] = lr + ld + le;
   out[RLSB_AC_CRITIC_AVG_TARGET] = static_cast<float>(accum[ACC_TARGET] / nc);
   out[RLSB_AC_CRITIC_AVG_LAMBDA] = static_cast<float>(accum[ACC_LAMBDA] / nc);
   out[RLSB_AC_CRITIC_AVG_PRED] = static_cast<float>(accum[ACC_PRED] / nc);
   const float mean_val = static_cast<float>(accum[ACC_MEAN_VAL] / (na * A));
   out[RLSB_AC_ACTOR_MEAN_VAL] = mean_val;
-  if (metrics_samples > 0) {
+  if (metrics_samples > 0 && !discrete) {
+    out[RLSB_AC_ACTOR_AVG_VAL] = static_cast<float>(accum[ACC_AVG_VAL] / (na * A));
+    out[RLSB_AC_ACTOR_AVG_SD] = static_cast<float>(accum[ACC_AVG_SD] / (na * A));
+    out[RLSB_AC_ACTOR_MIN_VAL] = key_float(*reinterpret_cast<const int*>(accum + kAccMinKey));
+    out[RLSB_AC_ACTOR_MAX_VAL] = key_float(*reinterpret_cast<const int*>(accum + kAccMaxKey));
+  } else if (metrics_samples > 0) {
     out[RLSB_AC_ACTOR_AVG_VAL] = 1.0f / static_cast<float>(A);   // sum_k f_k == 1 for every element
     out[RLSB_AC_ACTOR_AVG_SD] = static_cast<float>(accum[ACC_AVG_SD] / (na * A));
     out[RLSB_AC_ACTOR_MIN_VAL] = A > 1 ? 0.f : 1.f;               // one-hot draws
@@ -398,7 +479,8 @@ extern "C" int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor
 
 extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,
                               const void* stoch_packed, const float* vs, const float* w, const float* values,
-                              const float* actions, uint64_t seed, const rlsb_mlp_grads* actor_grads,
+                              const float* actions, const float* g_actions, uint64_t seed,
+                              const rlsb_mlp_grads* actor_grads,
                               const rlsb_mlp_grads* critic_grads, float* scalars, void* workspace, void* stream_) {
   if (!cfg || !packed || !determ_packed || !stoch_packed || !vs || !w || !values || !actions || !actor_grads ||
       !critic_grads || !scalars || !workspace || N <= 0)
@@ -460,18 +542,24 @@ extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_
   // ---- losses, metrics, d(loss)/d(head outputs) ---------------------------------------------------
   cudaError_t ce = cudaMemsetAsync(accum, 0, kScalars * sizeof(double), s);
   if (ce != cudaSuccess) return static_cast<int>(ce);
+  // running min / max of the metric draws as order-preserving int keys: +3.4e38 / very negative sentinels
+  ce = cudaMemsetAsync(accum + kAccMinKey, 0x7f, sizeof(double), s);
+  if (ce != cudaSuccess) return static_cast<int>(ce);
+  ce = cudaMemsetAsync(accum + kAccMaxKey, 0x80, sizeof(double), s);
+  if (ce != cudaSuccess) return static_cast<int>(ce);
   {
     AcLossArgs a{};
     a.head_out = head_out; a.group_stride = static_cast<long long>(M) * 32;
     a.m_pad = W.m_pad; a.N = static_cast<int>(N); a.H = P.H; a.A = P.A;
-    a.vs = vs; a.w = w; a.values = values; a.actions = actions;
+    a.vs = vs; a.w = w; a.values = values; a.actions = actions; a.g_actions = g_actions;
+    a.discrete = cfg->discrete;
     a.rho = cfg->rho; a.eta = cfg->eta; a.metrics_samples = cfg->metrics_samples; a.seed = seed;
     a.dy4 = bfw(W.dy4); a.accum = accum;
     ac_loss_kernel<<<static_cast<unsigned>((W.M + 127) / 128), 128, 0, s>>>(a);
     count_launch();
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return static_cast<int>(ce);
-    ac_finalize_kernel<<<1, 32, 0, s>>>(accum, P.H, N, P.A, cfg->metrics_samples, scalars);
+    ac_finalize_kernel<<<1, 32, 0, s>>>(accum, P.H, N, P.A, cfg->metrics_samples, cfg->discrete, scalars);
     count_launch();
   }
 

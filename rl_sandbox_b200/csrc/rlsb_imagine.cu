@@ -15,114 +15,14 @@
 #include "../../include/rlsb.h"
 #include "rlsb_count.cuh"
 #include "rlsb_gemm.cuh"
+#include "rlsb_imagine_plan.cuh"
 #include "rlsb_kernels.cuh"
 
 namespace rlsb {
 
+using namespace k1;
+
 namespace {
-
-inline int ru(int x, int m) { return (x + m - 1) / m * m; }
-inline size_t rus(size_t x, size_t m) { return (x + m - 1) / m * m; }
-
-struct LayerPlan {
-  int N = 0;       // valid outputs per group
-  int RB = 0, NB = 0, G = 1;
-  int kp = 0;      // padded K (sum of segments)
-  size_t w_off = 0;     // bytes into packed blob (bf16 tiles)
-  size_t bias_off = 0;  // fp32 [G][NB*RB]
-  size_t g_off = 0, b_off = 0;  // fp32 LN params: [G][RB] (full-row) or [N] (stats path)
-  bool fullrow = false;
-};
-
-void plan_nb(LayerPlan& L) {
-  if (ru(L.N, 32) <= 512) {
-    L.NB = 1;
-    L.RB = ru(L.N, 32);
-    L.fullrow = true;
-  } else {
-    L.NB = (L.N + 255) / 256;
-    L.RB = ru((L.N + L.NB - 1) / L.NB, 32);
-    L.fullrow = false;
-  }
-}
-
-struct Plan {
-  int D, S, A, Hd, Dp, Sp, Ap, Hp, Aout, G;
-  int g_actor, g_reward, g_discount, g_critic;
-  LayerPlan img_in, gru, prior1, prior2, head[5];
-  size_t packed_bytes;
-};
-
-size_t place(size_t& cursor, size_t bytes) {
-  cursor = rus(cursor, 1024);
-  size_t off = cursor;
-  cursor += bytes;
-  return off;
-}
-
-int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
-  if (c.classes != 32 || c.groups <= 0 || c.groups > 64) return -10;
-  if (c.D <= 0 || c.A <= 0 || c.hidden <= 0 || c.H <= 0) return -11;
-  P.D = c.D; P.S = c.groups * c.classes; P.A = c.A; P.Hd = c.hidden;
-  P.Dp = ru(P.D, 64); P.Sp = ru(P.S, 64); P.Ap = ru(P.A, 64); P.Hp = ru(P.Hd, 64);
-  P.Aout = c.discrete ? c.A : 2 * c.A;
-  if (P.Aout > 32 || P.Ap > 64) return -12;
-  if (ru(P.Hd, 32) > 512) return -13;
-  int g = 0;
-  P.g_actor = g++;
-  P.g_reward = g++;
-  P.g_discount = c.predict_discount ? g++ : -1;
-  P.g_critic = c.with_critic ? g++ : -1;
-  P.G = g;
-
-  size_t cur = 0;
-  auto finish = [&](LayerPlan& L, int ln_len_per_group) {
-    plan_nb(L);
-    L.w_off = place(cur, static_cast<size_t>(L.G) * L.NB * L.RB * L.kp * 2);
-    L.bias_off = place(cur, static_cast<size_t>(L.G) * L.NB * L.RB * 4);
-    L.g_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
-    L.b_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
-  };
-  P.img_in.N = P.D; P.img_in.kp = P.Sp + P.Ap; finish(P.img_in, ru(P.D, 32));
-  P.gru.N = 3 * P.D; P.gru.kp = 2 * P.Dp;      finish(P.gru, 3 * P.D);
-  P.prior1.N = P.D; P.prior1.kp = P.Dp;        finish(P.prior1, ru(P.D, 32));
-  P.prior2.N = P.S; P.prior2.kp = P.Dp;        finish(P.prior2, 32);
-  for (int l = 0; l < 5; ++l) {
-    LayerPlan& L = P.head[l];
-    L.G = P.G;
-    L.N = (l == 4) ? P.Aout : P.Hd;
-    L.kp = (l == 0) ? (P.Dp + P.Sp) : P.Hp;
-    finish(L, ru(L.N, 32));
-  }
-  P.packed_bytes = rus(cur, 1024);
-  return 0;
-}
-
-struct Workspace {
-  size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
-  long long ld_scratch;
-  int m_pad;
-  size_t bytes;
-};
-
-void make_workspace(const Plan& P, long long N, Workspace& W) {
-  const int m_pad = ru(static_cast<int>(N), 128);
-  W.m_pad = m_pad;
-  size_t cur = 0;
-  for (int i = 0; i < 2; ++i) W.hbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
-  for (int i = 0; i < 2; ++i) W.zbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Sp * 2);
-  W.abf = place(cur, static_cast<size_t>(m_pad) * P.Ap * 2);
-  W.xbf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
-  W.ybf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
-  for (int i = 0; i < 2; ++i) W.hid[i] = place(cur, static_cast<size_t>(P.G) * m_pad * P.Hp * 2);
-  W.ld_scratch = ru(3 * P.D, 4);
-  W.scratch = place(cur, static_cast<size_t>(m_pad) * W.ld_scratch * 4);
-  int nbmax = P.gru.NB;
-  if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
-  W.stats = place(cur, static_cast<size_t>(nbmax) * m_pad * 2 * 4);
-  W.head_out = place(cur, static_cast<size_t>(P.G) * m_pad * 32 * 4);
-  W.bytes = rus(cur, 1024);
-}
 
 __global__ void copy_pad_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad,
                                 float fill) {
@@ -180,6 +80,14 @@ extern "C" size_t rlsb_imagine_workspace_bytes(const rlsb_imagine_cfg* cfg, int6
   Workspace W;
   make_workspace(P, N, W);
   return W.bytes;
+}
+
+extern "C" size_t rlsb_imagine_tape_bytes(const rlsb_imagine_cfg* cfg, int64_t N) {
+  Plan P;
+  if (!cfg || N <= 0 || make_plan(*cfg, P) != 0 || !P.bwd) return 0;
+  Tape T;
+  make_tape(P, N, cfg->H, T);
+  return T.bytes;
 }
 
 extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* prm, void* packed,
@@ -250,6 +158,39 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
         RLSB_TRY(copy_pad(hp->ln_g[l], L.N, fptr(L.g_off) + static_cast<size_t>(g) * lnp, lnp, 1.f, s));
         RLSB_TRY(copy_pad(hp->ln_b[l], L.N, fptr(L.b_off) + static_cast<size_t>(g) * lnp, lnp, 0.f, s));
       }
+      if (P.bwd) {   // transposed images for the dX GEMMs of rlsb_imagine_bwd
+        const TLayer& T = P.t_head[l];
+        __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(base + T.off);
+        if (l >= 1) {
+          PackSeg rs[1] = {{0, 0, P.Hd}};
+          RLSB_TRY(launch_pack_transposed_seg(hp->w[l], P.Hd, n_out, tb + static_cast<size_t>(g) * T.NB * T.RB * T.kp,
+                                              T.RB, T.NB * T.RB, T.kp, 0, T.kp, 1, rs, s));
+        } else if (g >= P.gb0 && g < P.gb0 + P.Gb) {
+          // layer 0: the gradient-carrying groups share one K axis (their dX contributions add up)
+          PackSeg rs[2] = {{0, 0, P.D}, {P.Dp, P.D, P.S}};
+          RLSB_TRY(launch_pack_transposed_seg(hp->w[0], P.D + P.S, P.Hd, tb, T.RB, T.NB * T.RB, T.kp,
+                                              (g - P.gb0) * P.Hp, P.Hp, 2, rs, s));
+        }
+      }
+    }
+  }
+  if (P.bwd) {
+    auto tptr = [&](const TLayer& T) { return reinterpret_cast<__nv_bfloat16*>(base + T.off); };
+    {
+      PackSeg rs[1] = {{0, 0, P.D}};
+      RLSB_TRY(launch_pack_transposed_seg(prm->prior2_w, P.D, P.S, tptr(P.t_prior2), P.t_prior2.RB,
+                                          P.t_prior2.NB * P.t_prior2.RB, P.t_prior2.kp, 0, P.t_prior2.kp, 1, rs, s));
+      RLSB_TRY(launch_pack_transposed_seg(prm->prior1_w, P.D, P.D, tptr(P.t_prior1), P.t_prior1.RB,
+                                          P.t_prior1.NB * P.t_prior1.RB, P.t_prior1.kp, 0, P.t_prior1.kp, 1, rs, s));
+      // GRU weight (3D, 2D): in-features [x | h]
+      RLSB_TRY(launch_pack_transposed_seg(prm->gru_w, 2 * P.D, 3 * P.D, tptr(P.t_gru_x), P.t_gru_x.RB,
+                                          P.t_gru_x.NB * P.t_gru_x.RB, P.t_gru_x.kp, 0, P.t_gru_x.kp, 1, rs, s));
+      PackSeg rh[1] = {{0, P.D, P.D}};
+      RLSB_TRY(launch_pack_transposed_seg(prm->gru_w, 2 * P.D, 3 * P.D, tptr(P.t_gru_h), P.t_gru_h.RB,
+                                          P.t_gru_h.NB * P.t_gru_h.RB, P.t_gru_h.kp, 0, P.t_gru_h.kp, 1, rh, s));
+      PackSeg ri[2] = {{0, 0, P.S}, {P.Sp, P.S, P.A}};
+      RLSB_TRY(launch_pack_transposed_seg(prm->img_in_w, P.S + P.A, P.D, tptr(P.t_img_in), P.t_img_in.RB,
+                                          P.t_img_in.NB * P.t_img_in.RB, P.t_img_in.kp, 0, P.t_img_in.kp, 2, ri, s));
     }
   }
   return 0;
@@ -285,6 +226,13 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
 
   // packed bf16 state images: ping-pong in the workspace, or — when the caller keeps them for the
   // actor-critic update (rlsb_ac_update) — one slot per step in the caller's buffers
+  Tape TP{};
+  uint8_t* tape = static_cast<uint8_t*>(out->tape);
+  if (tape) {
+    if (!P.bwd) return -5;
+    make_tape(P, N, H, TP);
+  }
+  auto tp = [&](int t, size_t off) { return tape + static_cast<size_t>(t) * TP.step_bytes + off; };
   const bool keep = out->determ_packed != nullptr && out->stoch_packed != nullptr;
   if ((out->determ_packed != nullptr) != (out->stoch_packed != nullptr)) return -4;
   auto himg = [&](int t) {
@@ -340,12 +288,15 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   };
 
   // Linear -> [LN] -> ELU -> packed bf16, for a single-group RSSM layer
-  auto rssm_layer = [&](const LayerPlan& L, GemmParams g, bool has_ln, __nv_bfloat16* outp) -> int {
+  auto rssm_layer = [&](const LayerPlan& L, GemmParams g, bool has_ln, __nv_bfloat16* outp, uint8_t* save_pre,
+                        uint8_t* save_rstd) -> int {
     if (L.fullrow) {
       g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
       g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
       g.act = ACT_ELU;
       g.out_bf16 = outp; g.out_kpad = P.Dp; g.out_bf16_group_stride = 0;
+      g.save_pre = reinterpret_cast<__nv_bfloat16*>(save_pre);
+      g.save_rstd = has_ln ? reinterpret_cast<float*>(save_rstd) : nullptr;
       return launch_gemm(g, EPI_LN_ACT, s);
     }
     g.out_f32 = scratch; g.ldo = W.ld_scratch; g.out_group_stride = 0; g.stats = stats;
@@ -378,6 +329,10 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
         g.act = ACT_ELU;
         g.out_bf16 = bf(W.hid[l & 1]); g.out_kpad = P.Hp;
         g.out_bf16_group_stride = static_cast<long long>(m_pad) * P.Hp;
+        if (tape) {
+          g.save_pre = reinterpret_cast<__nv_bfloat16*>(tp(t, TP.head_pre[l]));
+          g.save_rstd = has_ln ? reinterpret_cast<float*>(tp(t, TP.head_rstd[l])) : nullptr;
+        }
         RLSB_TRY(launch_gemm(g, EPI_LN_ACT, s));
       } else {
         g.out_f32 = head_out; g.ldo = 32; g.out_group_stride = static_cast<long long>(m_pad) * 32;
@@ -408,7 +363,8 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       g.n_seg = 2;
       g.A[0] = zb; g.a_ktiles[0] = P.Sp / 64;
       g.A[1] = bf(W.abf); g.a_ktiles[1] = P.Ap / 64;
-      RLSB_TRY(rssm_layer(P.img_in, g, ln, bf(W.xbf)));
+      RLSB_TRY(rssm_layer(P.img_in, g, ln, bf(W.xbf), tape ? tp(t + 1, TP.x_pre) : nullptr,
+                          tape ? tp(t + 1, TP.x_rstd) : nullptr));
     }
     // ---- h' = GRU(x, h)                                    rssm.py:181, common.py:69-81 ----------
     {
@@ -416,9 +372,12 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       g.n_seg = 2;
       g.A[0] = bf(W.xbf); g.a_ktiles[0] = P.Dp / 64;
       g.A[1] = hb; g.a_ktiles[1] = P.Dp / 64;
-      g.out_f32 = scratch; g.ldo = W.ld_scratch; g.stats = stats;
+      // with a tape the pre-LayerNorm gate activations of this transition are kept (slot t+1)
+      float* gsc = tape ? reinterpret_cast<float*>(tp(t + 1, TP.gru_scratch)) : scratch;
+      float* gst = tape ? reinterpret_cast<float*>(tp(t + 1, TP.gru_stats)) : stats;
+      g.out_f32 = gsc; g.ldo = W.ld_scratch; g.stats = gst;
       RLSB_TRY(launch_gemm(g, EPI_STATS, s));
-      RLSB_TRY(launch_gru_gate(scratch, W.ld_scratch, stats, P.gru.NB, P.gru.RB, M, m_pad, P.D,
+      RLSB_TRY(launch_gru_gate(gsc, W.ld_scratch, gst, P.gru.NB, P.gru.RB, M, m_pad, P.D,
                                pf(P.gru.g_off), pf(P.gru.b_off), eps, -1.0f,
                                out->determ + static_cast<size_t>(t) * ND, P.D,
                                out->determ + static_cast<size_t>(t + 1) * ND, P.D, himg(t + 1), P.Dp, s));
@@ -428,7 +387,8 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       GemmParams g = base_gemm(P.prior1);
       g.n_seg = 1;
       g.A[0] = himg(t + 1); g.a_ktiles[0] = P.Dp / 64;
-      RLSB_TRY(rssm_layer(P.prior1, g, ln, bf(W.ybf)));
+      RLSB_TRY(rssm_layer(P.prior1, g, ln, bf(W.ybf), tape ? tp(t + 1, TP.y_pre) : nullptr,
+                          tape ? tp(t + 1, TP.y_rstd) : nullptr));
       GemmParams g2 = base_gemm(P.prior2);
       g2.n_seg = 1;
       g2.A[0] = bf(W.ybf); g2.a_ktiles[0] = P.Dp / 64;

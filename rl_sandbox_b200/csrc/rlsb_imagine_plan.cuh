@@ -1,0 +1,179 @@
+// rlsb_imagine_plan.cuh — layout of the packed weight blob, the activation workspace and the
+// activation tape of K1 (shared by the forward rollout, rlsb_imagine.cu, and its backward pass,
+// rlsb_imagine_bwd.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/rlsb.h"
+
+namespace rlsb {
+namespace k1 {
+
+inline int ru(int x, int m) { return (x + m - 1) / m * m; }
+inline size_t rus(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+struct LayerPlan {
+  int N = 0;       // valid outputs per group
+  int RB = 0, NB = 0, G = 1;
+  int kp = 0;      // padded K (sum of segments)
+  size_t w_off = 0;     // bytes into packed blob (bf16 tiles)
+  size_t bias_off = 0;  // fp32 [G][NB*RB]
+  size_t g_off = 0, b_off = 0;  // fp32 LN params: [G][RB] (full-row) or [N] (stats path)
+  bool fullrow = false;
+};
+
+inline void plan_nb(LayerPlan& L) {
+  if (ru(L.N, 32) <= 512) {
+    L.NB = 1;
+    L.RB = ru(L.N, 32);
+    L.fullrow = true;
+  } else {
+    L.NB = (L.N + 255) / 256;
+    L.RB = ru((L.N + L.NB - 1) / L.NB, 32);
+    L.fullrow = false;
+  }
+}
+
+// transposed weight image for a backward (dX) GEMM: rows = in-features (padded), K = out-features
+struct TLayer {
+  int RB = 0, NB = 0, kp = 0;
+  size_t off = 0;
+};
+
+struct Plan {
+  int D, S, A, Hd, Dp, Sp, Ap, Hp, Aout, G;
+  int g_actor, g_reward, g_discount, g_critic;
+  LayerPlan img_in, gru, prior1, prior2, head[5];
+  // ---- backward (cfg.with_backward): dX operands ----
+  bool bwd = false;
+  int Gb = 0, gb0 = 0;       // head groups that carry gradient: gb0 .. gb0+Gb-1 (reward .. target critic)
+  int G3p = 0;               // 3D padded to 64 (K of the GRU dX GEMMs)
+  TLayer t_head[5];          // l = 1..4: [G][RB=ru(Hd,32)][kp]; l = 0: K-concatenated groups, rows = Dp+Sp
+  TLayer t_prior2, t_prior1, t_gru_x, t_gru_h, t_img_in;
+  size_t packed_bytes;
+};
+
+inline size_t place(size_t& cursor, size_t bytes) {
+  cursor = rus(cursor, 1024);
+  size_t off = cursor;
+  cursor += bytes;
+  return off;
+}
+
+inline int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
+  if (c.classes != 32 || c.groups <= 0 || c.groups > 64) return -10;
+  if (c.D <= 0 || c.A <= 0 || c.hidden <= 0 || c.H <= 0) return -11;
+  P.D = c.D; P.S = c.groups * c.classes; P.A = c.A; P.Hd = c.hidden;
+  P.Dp = ru(P.D, 64); P.Sp = ru(P.S, 64); P.Ap = ru(P.A, 64); P.Hp = ru(P.Hd, 64);
+  P.Aout = c.discrete ? c.A : 2 * c.A;
+  if (P.Aout > 32 || P.Ap > 64) return -12;
+  if (ru(P.Hd, 32) > 512) return -13;
+  int g = 0;
+  P.g_actor = g++;
+  P.g_reward = g++;
+  P.g_discount = c.predict_discount ? g++ : -1;
+  P.g_critic = c.with_critic ? g++ : -1;
+  P.G = g;
+
+  size_t cur = 0;
+  auto finish = [&](LayerPlan& L, int ln_len_per_group) {
+    plan_nb(L);
+    L.w_off = place(cur, static_cast<size_t>(L.G) * L.NB * L.RB * L.kp * 2);
+    L.bias_off = place(cur, static_cast<size_t>(L.G) * L.NB * L.RB * 4);
+    L.g_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
+    L.b_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
+  };
+  P.img_in.N = P.D; P.img_in.kp = P.Sp + P.Ap; finish(P.img_in, ru(P.D, 32));
+  P.gru.N = 3 * P.D; P.gru.kp = 2 * P.Dp;      finish(P.gru, 3 * P.D);
+  P.prior1.N = P.D; P.prior1.kp = P.Dp;        finish(P.prior1, ru(P.D, 32));
+  P.prior2.N = P.S; P.prior2.kp = P.Dp;        finish(P.prior2, 32);
+  for (int l = 0; l < 5; ++l) {
+    LayerPlan& L = P.head[l];
+    L.G = P.G;
+    L.N = (l == 4) ? P.Aout : P.Hd;
+    L.kp = (l == 0) ? (P.Dp + P.Sp) : P.Hp;
+    finish(L, ru(L.N, 32));
+  }
+  P.bwd = c.with_backward != 0;
+  if (P.bwd) {
+    if (!P.img_in.fullrow || !P.prior1.fullrow || P.g_critic < 0) return -15;   // backward: D <= 512 and a critic
+    P.gb0 = P.g_reward;
+    P.Gb = P.g_critic - P.g_reward + 1;
+    P.G3p = ru(3 * P.D, 64);
+    auto tplace = [&](TLayer& T, int rows, int kp, int groups) {
+      LayerPlan tmp;
+      tmp.N = rows;
+      plan_nb(tmp);
+      T.RB = tmp.RB; T.NB = tmp.NB; T.kp = kp;
+      T.off = place(cur, static_cast<size_t>(groups) * T.NB * T.RB * kp * 2);
+    };
+    for (int l = 1; l < 5; ++l) tplace(P.t_head[l], P.Hd, ru(P.head[l].N, 64), P.G);
+    tplace(P.t_head[0], P.Dp + P.Sp, P.Gb * P.Hp, 1);
+    tplace(P.t_prior2, P.D, P.Sp, 1);
+    tplace(P.t_prior1, P.D, P.Dp, 1);
+    tplace(P.t_gru_x, P.D, P.G3p, 1);
+    tplace(P.t_gru_h, P.D, P.G3p, 1);
+    tplace(P.t_img_in, P.Sp + P.Ap, P.Dp, 1);
+  }
+  P.packed_bytes = rus(cur, 1024);
+  return 0;
+}
+
+// activation tape written by the forward rollout when rlsb_imagine_out::tape != NULL
+struct Tape {
+  size_t head_pre[4], head_rstd[4], x_pre, x_rstd, gru_scratch, gru_stats, y_pre, y_rstd;  // offsets inside a step
+  size_t step_bytes;
+  long long ld_scratch;
+  int m_pad;
+  size_t bytes;
+};
+
+inline void make_tape(const Plan& P, long long N, int H, Tape& T) {
+  const size_t m_pad = static_cast<size_t>(ru(static_cast<int>(N), 128));
+  T.m_pad = static_cast<int>(m_pad);
+  size_t cur = 0;
+  for (int l = 0; l < 4; ++l) {
+    T.head_pre[l] = place(cur, static_cast<size_t>(P.G) * m_pad * P.Hp * 2);
+    T.head_rstd[l] = place(cur, static_cast<size_t>(P.G) * m_pad * 4);
+  }
+  T.x_pre = place(cur, m_pad * P.Dp * 2);
+  T.x_rstd = place(cur, m_pad * 4);
+  T.ld_scratch = ru(3 * P.D, 4);
+  T.gru_scratch = place(cur, m_pad * T.ld_scratch * 4);
+  T.gru_stats = place(cur, static_cast<size_t>(P.gru.NB) * m_pad * 2 * 4);
+  T.y_pre = place(cur, m_pad * P.Dp * 2);
+  T.y_rstd = place(cur, m_pad * 4);
+  T.step_bytes = rus(cur, 1024);
+  T.bytes = T.step_bytes * static_cast<size_t>(H + 1);
+}
+
+struct Workspace {
+  size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
+  long long ld_scratch;
+  int m_pad;
+  size_t bytes;
+};
+
+inline void make_workspace(const Plan& P, long long N, Workspace& W) {
+  const int m_pad = ru(static_cast<int>(N), 128);
+  W.m_pad = m_pad;
+  size_t cur = 0;
+  for (int i = 0; i < 2; ++i) W.hbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
+  for (int i = 0; i < 2; ++i) W.zbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Sp * 2);
+  W.abf = place(cur, static_cast<size_t>(m_pad) * P.Ap * 2);
+  W.xbf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
+  W.ybf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
+  for (int i = 0; i < 2; ++i) W.hid[i] = place(cur, static_cast<size_t>(P.G) * m_pad * P.Hp * 2);
+  W.ld_scratch = ru(3 * P.D, 4);
+  W.scratch = place(cur, static_cast<size_t>(m_pad) * W.ld_scratch * 4);
+  int nbmax = P.gru.NB;
+  if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
+  W.stats = place(cur, static_cast<size_t>(nbmax) * m_pad * 2 * 4);
+  W.head_out = place(cur, static_cast<size_t>(P.G) * m_pad * 32 * 4);
+  W.bytes = rus(cur, 1024);
+}
+
+
+}  // namespace k1
+}  // namespace rlsb

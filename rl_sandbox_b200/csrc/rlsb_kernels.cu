@@ -64,22 +64,38 @@ __global__ void pack_kernel(const PackArgs a) {
   }
 }
 
-__global__ void pack_transposed_kernel(const float* __restrict__ src, long long ld_src, int cols, int rows,
-                                       __nv_bfloat16* __restrict__ dst, int RB, int rows_dst_pad, int k_pad) {
-  const long long chunks_per_row = k_pad >> 3;
-  const long long total = static_cast<long long>(rows_dst_pad) * chunks_per_row;
+struct PackTArgs {
+  const float* src;
+  long long ld_src;
+  int cols;                 // out-features of the Linear (columns of the transposed operand)
+  __nv_bfloat16* dst;
+  int RB, rows_dst_pad, k_pad;
+  int dst_k0, k_len;        // only the K range [dst_k0, dst_k0 + k_len) is written (k_len % 8 == 0)
+  int n_seg;
+  PackSeg seg[3];           // row segments: dst_k0 = first padded ROW, src_c0 = first in-feature, len
+};
+
+__global__ void pack_transposed_kernel(const PackTArgs a) {
+  const long long chunks = a.k_len >> 3;
+  const long long total = static_cast<long long>(a.rows_dst_pad) * chunks;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     // consecutive threads take consecutive ROWS of the same chunk: coalesced reads of src[c][r..]
-    const long long ch = i / rows_dst_pad;
-    const long long row = i - ch * rows_dst_pad;
-    const int k0 = static_cast<int>(ch) << 3;
+    const long long ch = i / a.rows_dst_pad;
+    const int row = static_cast<int>(i - ch * a.rows_dst_pad);
+    const int c0 = static_cast<int>(ch) << 3;   // column of the transposed operand relative to dst_k0
+    int src_col = -1;
+    for (int s = 0; s < a.n_seg; ++s) {
+      const int off = row - a.seg[s].dst_k0;
+      if (off >= 0 && off < a.seg[s].len) src_col = a.seg[s].src_c0 + off;
+    }
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      v[j] = (row < rows && k0 + j < cols) ? __ldg(src + static_cast<long long>(k0 + j) * ld_src + row) : 0.f;
-    const size_t idx = packed_index(static_cast<size_t>(row), static_cast<size_t>(k0), static_cast<size_t>(k_pad), RB);
-    *reinterpret_cast<uint4*>(dst + idx) = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+      v[j] = (src_col >= 0 && c0 + j < a.cols) ? __ldg(a.src + static_cast<long long>(c0 + j) * a.ld_src + src_col) : 0.f;
+    const size_t idx = packed_index(static_cast<size_t>(row), static_cast<size_t>(a.dst_k0 + c0),
+                                    static_cast<size_t>(a.k_pad), a.RB);
+    *reinterpret_cast<uint4*>(a.dst + idx) = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
   }
 }
 
@@ -649,15 +665,27 @@ int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16*
   return static_cast<int>(cudaGetLastError());
 }
 
-int launch_pack_transposed(const float* src, long long ld_src, int cols, int rows, __nv_bfloat16* dst, int RB,
-                           int rows_dst_pad, int k_pad, cudaStream_t stream) {
-  if (!src || !dst || (k_pad & 63) || (rows_dst_pad % RB) || cols > k_pad || rows > rows_dst_pad) return -1;
-  const long long total = static_cast<long long>(rows_dst_pad) * (k_pad >> 3);
+int launch_pack_transposed_seg(const float* src, long long ld_src, int cols, __nv_bfloat16* dst, int RB,
+                               int rows_dst_pad, int k_pad, int dst_k0, int k_len, int n_seg, const PackSeg* segs,
+                               cudaStream_t stream) {
+  if (!src || !dst || (k_pad & 63) || (rows_dst_pad % RB) || (k_len & 7) || (dst_k0 & 7) || dst_k0 + k_len > k_pad ||
+      cols > k_len || n_seg < 1 || n_seg > 3)
+    return -1;
+  PackTArgs a{src, ld_src, cols, dst, RB, rows_dst_pad, k_pad, dst_k0, k_len, n_seg, {}};
+  for (int i = 0; i < n_seg; ++i) a.seg[i] = segs[i];
+  const long long total = static_cast<long long>(rows_dst_pad) * (k_len >> 3);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_transposed_kernel<<<blocks, 256, 0, stream>>>(src, ld_src, cols, rows, dst, RB, rows_dst_pad, k_pad);
+  pack_transposed_kernel<<<blocks, 256, 0, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
+}
+
+int launch_pack_transposed(const float* src, long long ld_src, int cols, int rows, __nv_bfloat16* dst, int RB,
+                           int rows_dst_pad, int k_pad, cudaStream_t stream) {
+  if (rows > rows_dst_pad) return -1;
+  PackSeg seg{0, 0, rows};
+  return launch_pack_transposed_seg(src, ld_src, cols, dst, RB, rows_dst_pad, k_pad, 0, k_pad, 1, &seg, stream);
 }
 
 int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB, int RB, int M,

@@ -23,6 +23,13 @@ int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16*
 int launch_pack_transposed(const float* src, long long ld_src, int cols, int rows, __nv_bfloat16* dst, int RB,
                            int rows_dst_pad, int k_pad, cudaStream_t stream);
 
+// general form: the rows of the transposed operand are gathered from in-feature segments
+// (seg.dst_k0 = first padded row, seg.src_c0 = first in-feature, seg.len) and only the K range
+// [dst_k0, dst_k0 + k_len) is written (several Linears can share one K axis: K-concatenated groups)
+int launch_pack_transposed_seg(const float* src, long long ld_src, int cols, __nv_bfloat16* dst, int RB,
+                               int rows_dst_pad, int k_pad, int dst_k0, int k_len, int n_seg, const PackSeg* segs,
+                               cudaStream_t stream);
+
 // scratch fp32 [M_pad x ld] + per-block (mean, M2) partials -> [LayerNorm] -> act -> packed bf16
 int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB, int RB, int M,
                   int m_pad, int N, const float* gamma, const float* beta, float eps, int act,

@@ -225,11 +225,12 @@ class ImagineConfig:
     hidden: int = 400
     with_critic: bool = True
     discount_nan_on_tie: bool = True   # reference-exact Bernoulli.mode (NaN at p == 0.5)
+    with_backward: bool = False        # also pack the transposed images rlsb_imagine_bwd needs (D <= 512)
 
     def to_c(self) -> ImagineCfg:
         return ImagineCfg(self.D, self.groups, self.classes, self.A, self.hidden, int(self.discrete),
                           int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H,
-                          int(self.discount_nan_on_tie))
+                          int(self.discount_nan_on_tie), int(self.with_backward))
 
 
 def _mlp_params(sd: dict, prefix: str, keep: list) -> MlpParams:
@@ -311,7 +312,7 @@ class ImaginationEngine:
                 latent_uniforms: Optional[torch.Tensor] = None, action_noise: Optional[torch.Tensor] = None,
                 seed: int = 0, row_offset: int = 0, precomp_actions: Optional[torch.Tensor] = None,
                 horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
-                out: Optional[dict] = None, keep_packed: bool = False) -> dict:
+                out: Optional[dict] = None, keep_packed: bool = False, tape: bool = False) -> dict:
         cfg = self.cfg
         H = horizon if horizon is not None else cfg.H
         ccfg = cfg.to_c()
@@ -338,9 +339,15 @@ class ImaginationEngine:
             rows = round_up(n, 128)
             out["determ_packed"] = torch.empty((H + 1, rows, round_up(cfg.D, 64)), device=dev, dtype=torch.bfloat16)
             out["stoch_packed"] = torch.empty((H + 1, rows, round_up(S, 64)), device=dev, dtype=torch.bfloat16)
+        if tape and out.get("tape") is None:
+            nbytes = self.lib.rlsb_imagine_tape_bytes(C.byref(ccfg), n)
+            if nbytes == 0:
+                raise _lib.RlsbError("rollout(tape=True) needs ImagineConfig(with_backward=True) and D <= 512")
+            out["tape"] = torch.empty(nbytes, device=dev, dtype=torch.uint8)
         co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
                                                       "rewards", "discounts", "values", "actor_raw",
-                                                      "determ_packed", "stoch_packed")])
+                                                      "determ_packed", "stoch_packed", "tape")])
+        out["_horizon"] = H
         nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)),
                    _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
                    _ptr(None if precomp_actions is None else _f32c(precomp_actions)))
@@ -349,6 +356,30 @@ class ImaginationEngine:
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")
         return out
+
+    def backward(self, out: dict, g_rewards: torch.Tensor, g_values: torch.Tensor) -> torch.Tensor:
+        """d loss / d actions (H, N, A) from d loss / d rewards, d loss / d values (each (H+1, N)) through the
+        rollout recorded in ``out`` (made with tape=True): rlsb_imagine_bwd."""
+        if out.get("tape") is None:
+            raise _lib.RlsbError("ImaginationEngine.backward needs a rollout made with tape=True")
+        H = out["_horizon"]
+        ccfg = self.cfg.to_c()
+        ccfg.H = H
+        n = out["determ"].shape[1]
+        g_rewards, g_values = _f32c(g_rewards), _f32c(g_values)
+        if g_rewards.numel() != (H + 1) * n or g_values.numel() != (H + 1) * n:
+            raise _lib.RlsbError("backward: g_rewards / g_values must be (H+1, N)")
+        nbytes = self.lib.rlsb_imagine_bwd_workspace_bytes(C.byref(ccfg), n)
+        if getattr(self, "_bws", None) is None or self._bws.numel() < nbytes:
+            self._bws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        g_actions = torch.empty((H, n, self.cfg.A), device=self.device, dtype=torch.float32)
+        co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
+                                                      "rewards", "discounts", "values", "actor_raw",
+                                                      "determ_packed", "stoch_packed", "tape")])
+        check(self.lib.rlsb_imagine_bwd(C.byref(ccfg), self.packed.data_ptr(), n, C.byref(co), g_rewards.data_ptr(),
+                                        g_values.data_ptr(), g_actions.data_ptr(), self._bws.data_ptr(), _stream()),
+              "rlsb_imagine_bwd")
+        return g_actions
 
 
 # ------------------------------------------------------------------------------------------------
@@ -386,7 +417,7 @@ class ACUpdateEngine:
         self.device = torch.device(device)
         nbytes = self.lib.rlsb_ac_packed_bytes(C.byref(self.ccfg))
         if nbytes == 0:
-            raise _lib.RlsbError(f"unsupported actor-critic update config {cfg} (continuous actors need K1 backward)")
+            raise _lib.RlsbError(f"unsupported actor-critic update config {cfg}")
         self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
         self._ws, self._ws_rows = None, 0
         self.scalars = torch.zeros(_lib.AC_SCALARS, device=self.device, dtype=torch.float32)
@@ -400,7 +431,7 @@ class ACUpdateEngine:
         self._keep = keep
 
     def update(self, rollout: dict, vs: torch.Tensor, w: torch.Tensor, actor_seq, critic_seq, seed: int = 0,
-               horizon: Optional[int] = None) -> torch.Tensor:
+               horizon: Optional[int] = None, g_actions: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Writes .grad of every parameter of ``actor_seq`` / ``critic_seq`` (fc_nn Sequentials) and returns the
         RLSB_AC_SCALARS loss / metric vector (device tensor, see _lib.AC_SCALAR_NAMES)."""
         if rollout.get("determ_packed") is None:
@@ -421,7 +452,8 @@ class ACUpdateEngine:
             raise _lib.RlsbError(f"ACUpdateEngine.update: vs {tuple(vs.shape)} / w {tuple(w.shape)} for H={H}, N={n}")
         check(self.lib.rlsb_ac_update(C.byref(ccfg), self.packed.data_ptr(), n, rollout["determ_packed"].data_ptr(),
                                       rollout["stoch_packed"].data_ptr(), vs.data_ptr(), w.data_ptr(),
-                                      values.data_ptr(), actions.data_ptr(), seed, C.byref(ga), C.byref(gc),
+                                      values.data_ptr(), actions.data_ptr(),
+                                      _ptr(None if g_actions is None else _f32c(g_actions)), seed, C.byref(ga), C.byref(gc),
                                       self.scalars.data_ptr(), self._ws.data_ptr(), _stream()), "rlsb_ac_update")
         return self.scalars
 

@@ -108,3 +108,22 @@ def test_oracle_slot_attention_matches_reference():
     torch.testing.assert_close(out, torch.from_numpy(z["slots"]), rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(attn, torch.from_numpy(z["attn"]), rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(attn.sum(-1), torch.ones(3, 4), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["c2", "c2_ln"])
+def test_oracle_continuous_gradients_match_reference(name):
+    """The differentiable rollout of the port (imagine_st + ac_losses) reproduces the gradients the REFERENCE's
+    autograd produced (tests/golden: d loss_actor / d a_t, per-parameter norms and probed entries)."""
+    from oracle.gen_golden import grad_probe_indices
+    c = load_case(name)
+    m, gold = c["meta"], c["gold"]
+    r = orc.continuous_update_grads(c["wm"], c["actor"], c["critic"], c["h0"], c["z0"], c["lat"], c["act"], H=m["H"],
+                                    A=m["A"], lam=m["lam"], rho=m["rho"], eta=m["entropy_scale"])
+    assert torch.equal(r["traj"]["stoch_idx"].to(torch.uint8), gold["stoch_idx"])
+    torch.testing.assert_close(r["losses"]["loss_actor"], gold["loss_actor"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(r["g_actions"], gold["grad_actions"], rtol=2e-3, atol=1e-7)
+    for i, n in enumerate(m["grad_names"]):
+        g = r["grads"][n]
+        assert abs(g.norm().item() - gold["grad_norms"][i].item()) <= 1e-3 * gold["grad_norms"][i].item() + 1e-9, n
+        torch.testing.assert_close(g.flatten()[grad_probe_indices(g.numel())], gold["grad_probes"][i], rtol=5e-3,
+                                   atol=1e-6 * max(1.0, gold["grad_norms"][i].item()), msg=lambda s_: f"{n}: {s_}")
