@@ -14,7 +14,7 @@ Workloads (config.workload):
            i.e. 262144 = the top of the 16k-256k sweep at 8 GPUs), H=15.  This is the default: it is
            the configuration the metric ("at 1/2/4/8 B200") is quoted on.
   config1  the reference shape N = 16x50 = 800 (launch/latency bound; SURVEY hard part 8)
-  dino     config-2 dims (D=200, continuous A=12) at N = 800 — rollout only under no_grad
+  dino     config-2 dims (D=200, continuous A=12, rho = 0: dynamics back-propagation through K1 backward), N = 800
 One JSON line is printed by rank 0.
 """
 from __future__ import annotations
@@ -215,7 +215,7 @@ def main():
     def make_state(h, z):
         return State(h.unsqueeze(0), logits0, z.unsqueeze(0))
 
-    is_train = dims["discrete"]   # continuous actors need K1 backward (not built): time the rollout + K2 only
+    is_train = True   # discrete: K1 -> K2 -> K4; continuous: K1 (+tape) -> K2 -> K2 bwd -> K1 bwd -> K4
 
     def step(state, it):
         noise = {"seed": 1000 + it, "row_offset": rank * N}
@@ -329,8 +329,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {N} start states/GPU x H={H}, D={D}, 32x32 latents, A={dims['A']} "
                                    f"{'discrete' if dims['discrete'] else 'continuous'}, layer_norm={dims['layer_norm']}",
-                       "step": "imagine(K1) + lambda-return(K2) + critic/actor loss + backward + allreduce + AdamW x2"
-                               if is_train else "imagine(K1) + lambda-return(K2) [no_grad]",
+                       "step": "imagine(K1) + lambda-return(K2) + fused critic/actor loss fwd+bwd(K4) + allreduce + AdamW x2"
+                               if dims["discrete"] else
+                               "imagine(K1, tape) + lambda-return(K2) + K2 bwd + rollout backward(K1 bwd) + K4 + allreduce + AdamW x2",
                        "l2": "per-step working set (>= 2 GB of rollout outputs) exceeds the 126 MB L2; no explicit flush",
                        "metrics_samples": args.metrics_samples, "noise": "Philox4x32-10 on device"},
             "clocks": clk.summary(),

@@ -347,7 +347,6 @@ class ImaginationEngine:
         co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
                                                       "rewards", "discounts", "values", "actor_raw",
                                                       "determ_packed", "stoch_packed", "tape")])
-        out["_horizon"] = H
         nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)),
                    _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
                    _ptr(None if precomp_actions is None else _f32c(precomp_actions)))
@@ -362,7 +361,7 @@ class ImaginationEngine:
         rollout recorded in ``out`` (made with tape=True): rlsb_imagine_bwd."""
         if out.get("tape") is None:
             raise _lib.RlsbError("ImaginationEngine.backward needs a rollout made with tape=True")
-        H = out["_horizon"]
+        H = out["determ"].shape[0] - 1
         ccfg = self.cfg.to_c()
         ccfg.H = H
         n = out["determ"].shape[1]

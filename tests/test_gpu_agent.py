@@ -116,6 +116,31 @@ def test_train_step_end_to_end(cuda):
     assert st.determ.shape == (4, 1, 200) and rew.shape == (4, 1, 1)
 
 
+def test_train_step_continuous_actor_runs_fused(cuda):
+    """config_dino-shaped agent (continuous actions, rho = 0): train() drives K1 (+tape) -> K2 -> K2 bwd -> K1 bwd -> K4;
+    no torch autograd on the behaviour half.  Gradient parity is in test_gpu_ac_update.py."""
+    from rl_sandbox.utils.replay_buffer import RolloutChunks
+    import numpy as np
+    m = dict(D=200, A=12, discrete=False, layer_norm=False, predict_discount=False, entropy_scale=1e-4, gamma=0.99, H=5)
+    torch.manual_seed(0)
+    agent = make_agent(m, "cuda", batch_cluster_size=6)
+    assert agent._can_fuse_ac()
+    B, T = 3, 6
+    obs = agent.preprocess_obs(torch.randint(0, 255, (B * T, 64, 64, 3), dtype=torch.uint8)).cuda()
+    chunks = RolloutChunks(obs=obs, actions=torch.randn(B * T, 12).cuda(), rewards=torch.randn(B * T).cuda(),
+                           is_finished=torch.zeros(B * T).cuda(), is_first=torch.zeros(B * T).cuda(), additional_data={})
+    before = [p.detach().clone() for p in agent.actor.parameters()]
+    called = []
+    orig = agent._imagine_autograd
+    agent._imagine_autograd = lambda *a, **k: called.append(1) or orig(*a, **k)
+    out = agent.train(chunks)
+    assert not called, "the torch replay of the rollout must not run on the fused path"
+    assert all(np.isfinite(v).all() for v in out.values())
+    assert out["loss_actor_dynamics_backprop"] != 0
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, agent.actor.parameters()))
+    assert np.isfinite(agent.train(chunks)["total"]).all()
+
+
 def test_checkpoint_roundtrip_uses_reference_key_format(cuda, tmp_path, monkeypatch):
     m = dict(D=200, A=5, discrete=True, layer_norm=False, predict_discount=False, entropy_scale=3e-3, gamma=0.99, H=3)
     agent = make_agent(m, "cuda", batch_cluster_size=4)
