@@ -114,6 +114,14 @@ typedef struct {
   /* 1: the packed blob also holds the transposed weight images rlsb_imagine_bwd needs
    * (continuous actors, rho != 1: dynamics back-propagation, ac.py:121-123); requires D <= 512 */
   int32_t with_backward;
+  /* slotted RSSM (agents/dreamer/rssm_slots_attention.py:166-209): slots > 1 folds the slots into the
+   * row axis (row = n * slots + k, the reference's (batch, slots) order), runs `attention_blocks` mixer
+   * blocks on the GRU output before the prior logits, and feeds the heads cat_k[h_k, z_k] + pos_enc.
+   * 0 or 1 = the flat RSSM of rssm.py.  mixer_coeff = attention_scheduler.val (1.0 once warmed up). */
+  int32_t slots;
+  int32_t attention_blocks;
+  int32_t symmetric_qk;
+  float mixer_coeff;
 } rlsb_imagine_cfg;
 
 /* fp32 parameters in nn.Linear layout (weight = [out, in] row-major); NULL = absent.
@@ -138,6 +146,12 @@ typedef struct {
   rlsb_mlp_params reward;                            /* world_model.reward_predictor.*        */
   rlsb_mlp_params discount;                          /* world_model.discount_predictor.*      */
   rlsb_mlp_params critic;                            /* critic.target_critic.*                */
+  /* slotted RSSM only (NULL otherwise) */
+  const float* mix_qkv_w;                            /* hidden_attention_proj.weight (3D, D), no bias */
+  const float* mix_pre_norm_g; const float* mix_pre_norm_b;   /* pre_norm (D)                        */
+  const float* mix_fc_w; const float* mix_fc_b;      /* fc (D, D)                             */
+  const float* mix_fc_norm_g; const float* mix_fc_norm_b;     /* fc_norm (D)                          */
+  const float* pos_enc;                              /* world_model.pos_enc (slots, D + S)    */
 } rlsb_imagine_params;
 
 typedef struct {
@@ -176,7 +190,11 @@ size_t rlsb_imagine_workspace_bytes(const rlsb_imagine_cfg* cfg, int64_t N);
 /* fp32 nn.Linear parameters -> packed bf16 tile images + padded fp32 vectors */
 int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* params, void* packed,
                       void* stream);
-/* h0: (N, D) fp32; z0: (N, groups*classes) fp32 one-hot; logits0: (N, groups*classes) or NULL */
+/* h0: (N, D) fp32; z0: (N, groups*classes) fp32 one-hot; logits0: (N, groups*classes) or NULL.
+ * Slotted RSSM: every per-state tensor has slots times the rows, ordered (n, slot): h0 (N*slots, D),
+ * determ (H+1, N, slots, D), logits / stoch (H+1, N, slots, S), stoch_idx (H+1, N, slots, groups),
+ * latent_uniforms (H, N, slots, S); actions / rewards / discounts / values stay per start state.
+ * determ_packed / stoch_packed / tape are not available with slots > 1. */
 int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0,
                      const float* z0, const float* logits0, const rlsb_noise* noise,
                      const rlsb_imagine_out* out, void* workspace, void* stream);

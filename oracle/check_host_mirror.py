@@ -14,6 +14,56 @@ import torch
 from . import ref_harness as rh
 
 
+def check_slotted():
+    """world_model_slots_attention.WorldModel + rssm_slots_attention.RSSM mirrors vs the reference (config_slotted dims)."""
+    rh._import_reference()
+    from rl_sandbox.agents.dreamer.world_model_slots_attention import WorldModel as RefWM
+    from rl_sandbox_b200.agents.dreamer.world_model_slots_attention import WorldModel as MyWM
+    kw = dict(batch_cluster_size=4, latent_dim=32, latent_classes=32, rssm_dim=200, actions_num=1,
+              discount_loss_scale=1.0, kl_loss_scale=1000, kl_loss_balancing=0.8, kl_free_nats=5e-4,
+              discrete_rssm=False, predict_discount=False, layer_norm=True, encode_vit=False, decode_vit=False,
+              vit_l2_ratio=0.75, vit_img_size=224, slots_num=4, slots_iter_num=2, use_prev_slots=False)
+    torch.manual_seed(0)
+    ref, mine = RefWM(**kw), MyWM(**kw)
+    sd = ref.state_dict()
+    mk, rk = set(mine.state_dict()), set(sd)
+    ok = mk == rk and all(mine.state_dict()[k].shape == sd[k].shape for k in rk)
+    print(f"[slotted] state_dict keys/shapes world_model: {'ok' if ok else 'MISMATCH ' + str(sorted(mk ^ rk)[:8])} ({len(rk)} entries)")
+    if not ok:
+        return False
+    mine.load_state_dict(sd)
+    B, T = 2, 4
+    g = torch.Generator().manual_seed(1)
+    obs = torch.rand(B * T, 3, 64, 64, generator=g) - 0.5
+    a, r = torch.randn(B * T, 1, generator=g), torch.randn(B * T, generator=g)
+    disc, first = 0.99 * torch.ones(B * T), torch.zeros(B * T)
+    first[0] = 1
+    torch.manual_seed(5)
+    l_ref, post_ref, m_ref = ref.calculate_loss(obs, a, r, disc, first, {})
+    torch.manual_seed(5)
+    l_mine, post_mine, m_mine = mine.calculate_loss(obs, a, r, disc, first, {})
+    for k in l_ref:
+        same = torch.allclose(l_ref[k].float().reshape(-1), l_mine[k].float().reshape(-1), rtol=1e-5, atol=1e-6)
+        print(f"[slotted] calculate_loss {k}: ref {float(l_ref[k]):.6f} ours {float(l_mine[k]):.6f} {'ok' if same else 'MISMATCH'}")
+        ok &= same
+    for k in m_ref:
+        ok &= torch.allclose(torch.as_tensor(m_ref[k]).float(), torch.as_tensor(m_mine[k]).float(), rtol=1e-5, atol=1e-6)
+    same = torch.allclose(post_ref.determ, post_mine.determ, atol=1e-6) and torch.equal(post_ref.stoch, post_mine.stoch)
+    print(f"[slotted] posterior states: {'ok' if same else 'MISMATCH'}")
+    ok &= same
+    act = torch.randn(1, B * T, 1)
+    torch.manual_seed(6)
+    pr, rr, dr = ref.predict_next(post_ref.flatten().detach(), act)
+    torch.manual_seed(6)
+    pm, rm, dm = mine.predict_next(post_mine.flatten().detach(), act)
+    same = (torch.allclose(pr.determ, pm.determ, atol=1e-6) and torch.allclose(pr.stoch_logits, pm.stoch_logits, atol=1e-5)
+            and torch.allclose(rr, rm, atol=1e-6) and torch.allclose(pr.determ_updated, pm.determ_updated, atol=1e-6))
+    diffs = [(pr.determ - pm.determ).abs().max().item(), (pr.stoch_logits - pm.stoch_logits).abs().max().item(),
+             (pr.determ_updated - pm.determ_updated).abs().max().item(), (rr - rm).abs().max().item()]
+    print(f"[slotted] predict_next (determ, logits, determ_updated, reward) max abs diff {diffs}: {'ok' if same else 'MISMATCH'}")
+    return ok and same
+
+
 def main():
     ok = True
     for cfg in (dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True),
@@ -89,6 +139,7 @@ def main():
             same = torch.allclose(torch.as_tensor(x).float(), torch.as_tensor(y).float(), rtol=1e-5, atol=1e-6)
             print(f"[{cfg['D']}] {k}: ref {float(x):.6f} ours {float(y):.6f} {'ok' if same else 'MISMATCH'}")
             ok &= same
+    ok &= check_slotted()
     print("HOST MIRROR", "OK" if ok else "FAILED")
     sys.exit(0 if ok else 1)
 

@@ -167,6 +167,47 @@ def run_case(name, case):
     print(f"imagine_{name}.npz written:", {k: getattr(v, 'shape', None) for k, v in out.items() if k != 'meta'})
 
 
+SLOTTED_CASE = dict(D=200, A=1, K=4, discrete=False, layer_norm=True, predict_discount=False, N=5, H=3,
+                    entropy_scale=1e-4, gamma=0.999, param_seed=61, start_seed=62, noise_seed=63, blocks=3)
+
+
+def slotted_inputs(case=SLOTTED_CASE):
+    D, A, K, N, H = case["D"], case["A"], case["K"], case["N"], case["H"]
+    h0, z0 = orc.make_start(case["start_seed"], N * K, D)
+    g = torch.Generator().manual_seed(case["noise_seed"])
+    lat = torch.rand(H, N, K, 1024, generator=g)
+    act = torch.rand(H, N, A, generator=g) if case["discrete"] else torch.randn(H, N, A, generator=g)
+    return h0.view(N, K, D), z0.view(N, K, 1024), lat, act
+
+
+def run_slotted():
+    """config_slotted dims: DreamerV2.imagine_trajectory over world_model_slots_attention.WorldModel (reference)."""
+    c = SLOTTED_CASE
+    wm_sd, actor_sd, critic_sd = orc.make_params_slotted(c["param_seed"], D=c["D"], A=c["A"], K=c["K"],
+                                                         discrete=c["discrete"], layer_norm=c["layer_norm"],
+                                                         predict_discount=c["predict_discount"])
+    h0, z0, lat, act = slotted_inputs()
+    agent = rh.build_agent_slotted(D=c["D"], A=c["A"], K=c["K"], discrete=c["discrete"], layer_norm=c["layer_norm"],
+                                   predict_discount=c["predict_discount"], H=c["H"], entropy_scale=c["entropy_scale"],
+                                   gamma=c["gamma"], attention_block_num=c["blocks"])
+    rh.load_params(agent, {k: v for k, v in wm_sd.items() if k != "pos_enc"}, actor_sd, critic_sd)
+    wm = getattr(agent.world_model, "_orig_mod", agent.world_model)
+    assert torch.allclose(wm.pos_enc, wm_sd["pos_enc"], atol=1e-6), "pos_enc restatement differs"
+    state = rh.ref_state_slotted(agent, h0, z0)
+    q = rh.NoiseQueue(list(lat), list(act))
+    with rh.injected_noise(q), torch.no_grad():
+        states, actions, rewards, discounts = agent.imagine_trajectory(state)
+        values = agent.critic.target_critic(states.combined).mode
+    assert not q.latent and not q.action, "noise not fully consumed"
+    H, N, K = c["H"], c["N"], c["K"]
+    np.savez_compressed(
+        OUT / "imagine_slotted.npz", determ=states.determ.numpy(), logits=states.stoch_logits.reshape(H + 1, N, K, 1024).numpy(),
+        stoch_idx=states.stoch.reshape(H + 1, N, K, 32, 32).argmax(-1).numpy().astype(np.uint8), actions=actions.numpy(),
+        rewards=rewards.squeeze(-1).numpy(), discounts=discounts.squeeze(-1).numpy(), values=values.squeeze(-1).numpy(),
+        meta=json.dumps(c))
+    print("imagine_slotted.npz written:", states.determ.shape, states.stoch_logits.shape, actions.shape)
+
+
 SLOT_CASE = dict(B=3, tokens=196, dim=384, slots=4, iters=2, param_seed=41, input_seed=42)
 
 
@@ -198,6 +239,7 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     known_answers()
     run_slot_attention()
+    run_slotted()
     for name, case in CASES.items():
         run_case(name, case)
 

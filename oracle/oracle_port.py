@@ -259,6 +259,109 @@ def ac_losses(traj, actor_sd, critic_sd, *, lam, discrete, rho, eta, bf16=False)
                 loss_actor_reinforce=l_reinforce, loss_actor_dynamics_backprop=l_dyn, loss_actor_entropy=l_ent)
 
 
+# ------------------------------------------------------------------------------------------------
+# slotted RSSM (agents/dreamer/rssm_slots_attention.py:166-209, world_model_slots_attention.py:199-207)
+# ------------------------------------------------------------------------------------------------
+def position_encoding(seq_len, d, n=10000):
+    """agents/dreamer/common.py:8-15 (sin on even, cos on odd columns)."""
+    k = torch.arange(seq_len, dtype=torch.float64)[:, None]
+    i = torch.arange(d // 2, dtype=torch.float64)[None, :]
+    ang = k / torch.pow(torch.tensor(float(n), dtype=torch.float64), 2 * i / d)
+    P = torch.zeros(seq_len, d, dtype=torch.float64)
+    P[:, 0:2 * (d // 2):2] = torch.sin(ang)
+    P[:, 1:2 * (d // 2):2] = torch.cos(ang)
+    return P.float()
+
+
+def slot_mixer(h, sd, rp="recurrent_model.", blocks=3, coeff=1.0, symmetric_qk=False, bf16=False):
+    """rssm_slots_attention.py:186-203 on h (N, K, D): returns determ_post."""
+    D = h.shape[-1]
+    eye = torch.eye(h.shape[-2])
+    for _ in range(blocks):
+        x = layer_norm(h, sd[rp + "pre_norm.weight"], sd[rp + "pre_norm.bias"])
+        q, k, v = linear(x, sd[rp + "hidden_attention_proj.weight"], None, bf16).chunk(3, -1)
+        if symmetric_qk:
+            k = q
+        qk = torch.einsum('bih,bjh->bij', q, k)
+        attn = torch.softmax(D ** -0.5 * qk, -1) + 1e-8
+        attn = attn / attn.sum(-1, keepdim=True)
+        attn = coeff * attn + (1 - coeff) * eye
+        upd = torch.einsum('bjd,bij->bid', v, attn)
+        h = h + linear(layer_norm(upd, sd[rp + "fc_norm.weight"], sd[rp + "fc_norm.bias"]), sd[rp + "fc.weight"],
+                       sd[rp + "fc.bias"], bf16)
+    return h
+
+
+def imagine_slotted(wm_sd, actor_sd, critic_sd, h0, z0, *, H, A, K, discrete, predict_discount, latent_uniforms,
+                    action_noise, blocks=3, coeff=1.0, bf16=False, target_prefix="target_critic."):
+    """DreamerV2.imagine_trajectory (dreamer_v2.py:68-96) over the slotted world model: h0 (N,K,D), z0 (N,K,1024),
+    latent_uniforms (H,N,K,1024), action_noise (H,N,A).  Heads see cat_k([h_k, z_k] + pos_enc_k) with the UN-mixed h;
+    the mixer only shapes the prior logits (rssm_slots_attention.py:205-208)."""
+    N, D = h0.shape[0], h0.shape[-1]
+    S = 1024
+    pos = wm_sd["pos_enc"]
+    rp = "recurrent_model."
+    h, z = h0.clone(), z0.clone()
+    out = {k: [] for k in ("determ", "logits", "stoch_idx", "actions", "rewards", "discounts", "values")}
+    out["determ"].append(h); out["logits"].append(torch.zeros(N, K, S)); out["actions"].append(torch.zeros(N, A))
+    out["stoch_idx"].append(z.view(N, K, 32, 32).argmax(-1))
+    for t in range(H + 1):
+        s = (torch.cat([h, z], -1) + pos).flatten(1, 2)
+        out["rewards"].append(mlp(s, wm_sd, "reward_predictor.", bf16).squeeze(-1))
+        if t == 0 or not predict_discount:
+            out["discounts"].append(torch.ones(N))
+        else:
+            out["discounts"].append(bernoulli_mode(mlp(s, wm_sd, "discount_predictor.", bf16).squeeze(-1)))
+        out["values"].append(mlp(s, critic_sd, target_prefix, bf16).squeeze(-1))
+        if t == H:
+            break
+        raw = mlp(s, actor_sd, "actor.", bf16)
+        if discrete:
+            a = torch.nn.functional.one_hot(sample_categorical(raw, action_noise[t]), A).float()
+        else:
+            mu, sd_ = raw.chunk(2, -1)
+            a = torch.tanh(mu) + (2 * torch.sigmoid(sd_ / 2) + 0.1) * action_noise[t]
+        za = torch.cat([z, a.unsqueeze(1).expand(N, K, A)], -1).reshape(N * K, S + A)
+        x = linear(za, wm_sd[rp + "pre_determ_recurrent.0.weight"], wm_sd[rp + "pre_determ_recurrent.0.bias"], bf16)
+        if rp + "pre_determ_recurrent.1.weight" in wm_sd:
+            x = layer_norm(x, wm_sd[rp + "pre_determ_recurrent.1.weight"], wm_sd[rp + "pre_determ_recurrent.1.bias"])
+        x = elu(x)
+        h = gru_cell(x, h.reshape(N * K, D), wm_sd, rp + "determ_recurrent.", bf16).reshape(N, K, D)
+        hp = slot_mixer(h, wm_sd, rp, blocks, coeff, bf16=bf16).reshape(N * K, D)
+        y = linear(hp, wm_sd[rp + "ensemble_prior_estimator.0.weight"], wm_sd[rp + "ensemble_prior_estimator.0.bias"], bf16)
+        if rp + "ensemble_prior_estimator.1.weight" in wm_sd:
+            y = layer_norm(y, wm_sd[rp + "ensemble_prior_estimator.1.weight"], wm_sd[rp + "ensemble_prior_estimator.1.bias"])
+        logits = linear(elu(y), wm_sd[rp + "ensemble_prior_estimator.3.weight"],
+                        wm_sd[rp + "ensemble_prior_estimator.3.bias"], bf16).reshape(N, K, S)
+        idx = sample_categorical(logits.view(N, K, 32, 32), latent_uniforms[t].view(N, K, 32, 32))
+        z = torch.nn.functional.one_hot(idx, 32).float().view(N, K, S)
+        out["determ"].append(h); out["logits"].append(logits); out["stoch_idx"].append(idx); out["actions"].append(a)
+    return {k: torch.stack(v) for k, v in out.items()}
+
+
+def make_params_slotted(seed, *, D, A, K, discrete, layer_norm, predict_discount, hidden=400, S=1024):
+    """Random parameters of the slotted world model's hot-path modules + actor / critic on K*(D+S) inputs."""
+    gen = torch.Generator().manual_seed(seed)
+    wm, actor, critic = make_params(seed, D=D, A=A, discrete=discrete, layer_norm=layer_norm,
+                                    predict_discount=predict_discount, hidden=hidden, S=S)
+    rp = "recurrent_model."
+    wm = {k: v for k, v in wm.items() if k.startswith(rp)}
+    wm[rp + "hidden_attention_proj.weight"] = _lin(gen, 3 * D, D)[0]
+    wm[rp + "fc.weight"], wm[rp + "fc.bias"] = _lin(gen, D, D)
+    for name in ("pre_norm", "fc_norm"):
+        wm[rp + name + ".weight"] = 1 + 0.1 * torch.randn(D, generator=gen)
+        wm[rp + name + ".bias"] = 0.1 * torch.randn(D, generator=gen)
+    wm["pos_enc"] = position_encoding(K, D + S)
+    Z = K * (D + S)
+    wm.update(make_mlp_sd(gen, "reward_predictor.", Z, 1, hidden, layer_norm))
+    if predict_discount:
+        wm.update(make_mlp_sd(gen, "discount_predictor.", Z, 1, hidden, layer_norm))
+    actor = make_mlp_sd(gen, "actor.", Z, A if discrete else 2 * A, hidden, layer_norm)
+    critic = make_mlp_sd(gen, "critic.", Z, 1, hidden, layer_norm)
+    critic.update(make_mlp_sd(gen, "target_critic.", Z, 1, hidden, layer_norm))
+    return wm, actor, critic
+
+
 def imagine_st(wm, actor, critic, h0, z0, lat, act, *, H, A, bf16=False, keep_action_grads=False):
     """Differentiable rollout for a continuous actor (rho != 1): the autograd graph DreamerV2.imagine_trajectory
     builds (dreamer_v2.py:83-91) — actor on the DETACHED state, unclamped rsample, straight-through latents

@@ -125,6 +125,38 @@ def build_agent(*, D, A, discrete, layer_norm, predict_discount, H=15, entropy_s
     return agent
 
 
+def build_agent_slotted(*, D, A, K, discrete, layer_norm, predict_discount, H=15, entropy_scale=1e-4, lam=0.95,
+                        gamma=0.999, lr=8e-5, batch_cluster_size=50, attention_block_num=3):
+    """The reference DreamerV2 over world_model_slots_attention.WorldModel (config/agent/dreamer_v2_slotted_debug.yaml,
+    plus the two arguments that YAML forgets; decode_vit off: DINO only shapes the world-model loss)."""
+    ref = _import_reference()
+    from rl_sandbox.agents.dreamer.world_model_slots_attention import WorldModel
+    from rl_sandbox.agents.dreamer.ac import ImaginativeActor, ImaginativeCritic
+    from rl_sandbox.utils.optimizer import Optimizer
+    wm = partial(WorldModel, batch_cluster_size=batch_cluster_size, latent_dim=32, latent_classes=32, rssm_dim=D,
+                 discount_loss_scale=1.0, kl_loss_scale=1000, kl_loss_balancing=0.8, kl_free_nats=5e-4,
+                 discrete_rssm=False, predict_discount=predict_discount, layer_norm=layer_norm, encode_vit=False,
+                 decode_vit=False, vit_l2_ratio=0.75, vit_img_size=224, slots_num=K, slots_iter_num=2,
+                 use_prev_slots=False, attention_block_num=attention_block_num)
+    actor = partial(ImaginativeActor, layer_norm=layer_norm, reinforce_fraction=None, entropy_scale=entropy_scale)
+    critic = partial(ImaginativeCritic, discount_factor=gamma, update_interval=100, soft_update_fraction=1,
+                     value_target_lambda=lam, layer_norm=layer_norm)
+    opt = partial(Optimizer, lr=lr, eps=1e-5, weight_decay=1e-6, clip=100)
+    return ref.DreamerV2(obs_space_num=[64, 64, 3], clip_rewards="identity", actions_num=A, world_model=wm,
+                         actor=actor, critic=critic, action_type="discrete" if discrete else "continuous",
+                         imagination_horizon=H, wm_optim=opt, actor_optim=opt, critic_optim=opt, layer_norm=layer_norm,
+                         batch_cluster_size=batch_cluster_size, f16_precision=False, device_type="cpu")
+
+
+def ref_state_slotted(agent, h0, z0):
+    """h0 (N,K,D), z0 (N,K,1024) -> the reference's slotted State (1, N, K, .) carrying the world model's pos_enc."""
+    from rl_sandbox.agents.dreamer.rssm_slots_attention import State
+    N, K = h0.shape[:2]
+    wm = getattr(agent.world_model, "_orig_mod", agent.world_model)
+    return State(h0.unsqueeze(0).clone(), torch.zeros(1, N, K, 32, 32), z0.unsqueeze(0).clone(),
+                 wm.pos_enc.unsqueeze(0).unsqueeze(0))
+
+
 def load_params(agent, wm_sd, actor_sd, critic_sd):
     """Copy oracle_port.make_params tensors into the reference modules (same state-dict names)."""
     wm = getattr(agent.world_model, "_orig_mod", agent.world_model)

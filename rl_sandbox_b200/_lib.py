@@ -23,7 +23,8 @@ class RlsbError(RuntimeError):
 class ImagineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "predict_discount",
-        "with_critic", "H", "discount_nan_on_tie", "with_backward")]
+        "with_critic", "H", "discount_nan_on_tie", "with_backward", "slots", "attention_blocks",
+        "symmetric_qk")] + [("mixer_coeff", C.c_float)]
 
 
 class MlpParams(C.Structure):
@@ -35,7 +36,9 @@ class ImagineParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "img_in_w", "img_in_b", "img_in_ln_g", "img_in_ln_b", "gru_w", "gru_b", "gru_ln_g", "gru_ln_b",
         "prior1_w", "prior1_b", "prior1_ln_g", "prior1_ln_b", "prior2_w", "prior2_b")] + [
-        ("actor", MlpParams), ("reward", MlpParams), ("discount", MlpParams), ("critic", MlpParams)]
+        ("actor", MlpParams), ("reward", MlpParams), ("discount", MlpParams), ("critic", MlpParams)] + [
+        (n, C.c_void_p) for n in ("mix_qkv_w", "mix_pre_norm_g", "mix_pre_norm_b", "mix_fc_w", "mix_fc_b",
+                                  "mix_fc_norm_g", "mix_fc_norm_b", "pos_enc")]
 
 
 class Noise(C.Structure):

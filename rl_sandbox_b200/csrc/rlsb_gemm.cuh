@@ -9,7 +9,7 @@ namespace rlsb {
 
 constexpr int kTileM = 128;      // rows per M tile == TMEM lanes
 constexpr int kTileK = 64;       // bf16 elements per 128-byte swizzled row
-constexpr int kMaxSeg = 3;       // K segments (concatenated inputs, e.g. cat[x, h])
+constexpr int kMaxSeg = 8;       // K segments (concatenated inputs, e.g. cat[x, h]; slotted heads: 2 per slot)
 constexpr int kGemmThreads = 576;  // warp0 = bulk-copy producer, warp1 = MMA issuer, warps2-17 = epilogue
 
 enum GemmEpilogue : int {

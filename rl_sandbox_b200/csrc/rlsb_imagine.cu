@@ -10,6 +10,7 @@
 //   * every bf16 operand (activations and weights) is stored as SWIZZLE_128B tile images so a
 //     pipeline stage is one contiguous bulk copy (rlsb_ptx.cuh::packed_index).
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 
 #include "../../include/rlsb.h"
@@ -143,15 +144,28 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
       if (!hp->w[l]) return -20;
       const int n_out = (l == 4) ? ((g == P.g_actor) ? P.Aout : 1) : P.Hd;
       __nv_bfloat16* dst = wptr(L) + static_cast<size_t>(g) * L.NB * L.RB * L.kp;
-      if (l == 0) {  // input = cat[determ, stoch]  (rssm.py:29-31)
-        PackSeg segs[2] = {{0, 0, P.D}, {P.Dp, P.D, P.S}};
-        RLSB_TRY(launch_pack(hp->w[l], P.D + P.S, n_out, dst, L.RB, L.NB * L.RB, L.kp, 2, segs, s));
+      if (l == 0) {  // input = cat[determ, stoch]  (rssm.py:29-31), per slot when slotted
+        PackSeg segs[8];
+        for (int k = 0; k < P.K; ++k) {
+          segs[2 * k] = PackSeg{k * (P.Dp + P.Sp), k * (P.D + P.S), P.D};
+          segs[2 * k + 1] = PackSeg{k * (P.Dp + P.Sp) + P.Dp, k * (P.D + P.S) + P.D, P.S};
+        }
+        RLSB_TRY(launch_pack(hp->w[l], static_cast<long long>(P.K) * (P.D + P.S), n_out, dst, L.RB, L.NB * L.RB, L.kp,
+                             2 * P.K, segs, s));
       } else {
         PackSeg segs[1] = {{0, 0, P.Hd}};
         RLSB_TRY(launch_pack(hp->w[l], P.Hd, n_out, dst, L.RB, L.NB * L.RB, L.kp, 1, segs, s));
       }
-      RLSB_TRY(copy_pad(hp->b[l], n_out, fptr(L.bias_off) + static_cast<size_t>(g) * L.NB * L.RB,
-                        L.NB * L.RB, 0.f, s));
+      if (l == 0 && P.K > 1 && prm->pos_enc) {
+        // State.combined_slots adds the constant pos_enc to [h_k, z_k] (rssm_slots_attention.py:37-41):
+        // W (s + p) + b = W s + (b + W p)
+        RLSB_TRY(launch_bias_fold(hp->w[0], static_cast<long long>(P.K) * (P.D + P.S), n_out, P.K * (P.D + P.S),
+                                  prm->pos_enc, hp->b[0], fptr(L.bias_off) + static_cast<size_t>(g) * L.NB * L.RB,
+                                  L.NB * L.RB, s));
+      } else {
+        RLSB_TRY(copy_pad(hp->b[l], n_out, fptr(L.bias_off) + static_cast<size_t>(g) * L.NB * L.RB,
+                          L.NB * L.RB, 0.f, s));
+      }
       if (l < 4) {
         const int lnp = ru(L.N, 32);
         // fc_nn.py:15 — the first LayerNorm always exists; later ones only with layer_norm
@@ -173,6 +187,21 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
         }
       }
     }
+  }
+  if (P.K > 1) {   // slot mixer (rssm_slots_attention.py:141-145)
+    if (!prm->mix_qkv_w || !prm->mix_fc_w || !prm->mix_fc_b || !prm->mix_pre_norm_g || !prm->mix_pre_norm_b ||
+        !prm->mix_fc_norm_g || !prm->mix_fc_norm_b)
+      return -21;
+    PackSeg seg[1] = {{0, 0, P.D}};
+    RLSB_TRY(launch_pack(prm->mix_qkv_w, P.D, 3 * P.D, wptr(P.mix_qkv), P.mix_qkv.RB, P.mix_qkv.NB * P.mix_qkv.RB,
+                         P.mix_qkv.kp, 1, seg, s));
+    RLSB_TRY(launch_pack(prm->mix_fc_w, P.D, P.D, wptr(P.mix_fc), P.mix_fc.RB, P.mix_fc.NB * P.mix_fc.RB,
+                         P.mix_fc.kp, 1, seg, s));
+    RLSB_TRY(copy_pad(prm->mix_fc_b, P.D, fptr(P.mix_fc.bias_off), P.mix_fc.NB * P.mix_fc.RB, 0.f, s));
+    RLSB_TRY(copy_pad(prm->mix_pre_norm_g, P.D, fptr(P.mix_pre_g), P.D, 1.f, s));
+    RLSB_TRY(copy_pad(prm->mix_pre_norm_b, P.D, fptr(P.mix_pre_b), P.D, 0.f, s));
+    RLSB_TRY(copy_pad(prm->mix_fc_norm_g, P.D, fptr(P.mix_fcn_g), P.D, 1.f, s));
+    RLSB_TRY(copy_pad(prm->mix_fc_norm_b, P.D, fptr(P.mix_fcn_b), P.D, 0.f, s));
   }
   if (P.bwd) {
     auto tptr = [&](const TLayer& T) { return reinterpret_cast<__nv_bfloat16*>(base + T.off); };
@@ -208,9 +237,14 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   RLSB_TRY(make_plan(*cfg, P));
   Workspace W;
   make_workspace(P, N, W);
-  const int M = static_cast<int>(N);
+  const int M = static_cast<int>(N);          // start states: rows of the head operands
   const int m_pad = W.m_pad;
   const int m_tiles = m_pad / 128;
+  const int K = P.K;                           // slots (1 = flat RSSM)
+  if (N * K > (1LL << 30)) return -3;
+  const int Ms = M * K;                        // rows of the RSSM operands, ordered (n, slot)
+  const int ms_pad = W.ms_pad;
+  const int ms_tiles = ms_pad / 128;
   const int H = cfg->H;
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -222,7 +256,8 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   float* head_out = reinterpret_cast<float*>(ws + W.head_out);
   const bool ln = cfg->layer_norm != 0;
   const float eps = 1e-5f;
-  const size_t ND = static_cast<size_t>(N) * P.D, NS = static_cast<size_t>(N) * P.S;
+  const size_t ND = static_cast<size_t>(Ms) * P.D, NS = static_cast<size_t>(Ms) * P.S;
+  if (K > 1 && (out->determ_packed || out->stoch_packed || out->tape)) return -6;
 
   // packed bf16 state images: ping-pong in the workspace, or — when the caller keeps them for the
   // actor-critic update (rlsb_ac_update) — one slot per step in the caller's buffers
@@ -236,26 +271,26 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   const bool keep = out->determ_packed != nullptr && out->stoch_packed != nullptr;
   if ((out->determ_packed != nullptr) != (out->stoch_packed != nullptr)) return -4;
   auto himg = [&](int t) {
-    return keep ? static_cast<__nv_bfloat16*>(out->determ_packed) + static_cast<size_t>(t) * m_pad * P.Dp
+    return keep ? static_cast<__nv_bfloat16*>(out->determ_packed) + static_cast<size_t>(t) * ms_pad * P.Dp
                 : bf(W.hbf[t & 1]);
   };
   auto zimg = [&](int t) {
-    return keep ? static_cast<__nv_bfloat16*>(out->stoch_packed) + static_cast<size_t>(t) * m_pad * P.Sp
+    return keep ? static_cast<__nv_bfloat16*>(out->stoch_packed) + static_cast<size_t>(t) * ms_pad * P.Sp
                 : bf(W.zbf[t & 1]);
   };
 
   // ---- start state ---------------------------------------------------------------------------
   {
     PackSeg seg[1] = {{0, 0, P.D}};
-    RLSB_TRY(launch_pack(h0, P.D, M, himg(0), 128, m_pad, P.Dp, 1, seg, s));
+    RLSB_TRY(launch_pack(h0, P.D, Ms, himg(0), 128, ms_pad, P.Dp, 1, seg, s));
     PackSeg segz[1] = {{0, 0, P.S}};
-    RLSB_TRY(launch_pack(z0, P.S, M, zimg(0), 128, m_pad, P.Sp, 1, segz, s));
+    RLSB_TRY(launch_pack(z0, P.S, Ms, zimg(0), 128, ms_pad, P.Sp, 1, segz, s));
     // rows >= N of the other one-hot images are never written by the sampler: clear their last M tile
     const size_t tile_row_bytes = static_cast<size_t>(P.Sp / 64) * 128 * 64 * 2;
     cudaError_t e = cudaSuccess;
-    if (M != m_pad) {
+    if (Ms != ms_pad) {
       for (int t = 1; t <= (keep ? H : 1) && e == cudaSuccess; ++t)
-        e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(zimg(t)) + static_cast<size_t>(m_tiles - 1) * tile_row_bytes, 0,
+        e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(zimg(t)) + static_cast<size_t>(ms_tiles - 1) * tile_row_bytes, 0,
                             tile_row_bytes, s);
     }
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -270,18 +305,19 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     }
     e = cudaMemsetAsync(out->actions, 0, static_cast<size_t>(N) * P.A * 4, s);
     if (e != cudaSuccess) return static_cast<int>(e);
-    const long long tot = N * cfg->groups;
-    onehot_to_idx_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(z0, N, cfg->groups,
+    const long long tot = static_cast<long long>(Ms) * cfg->groups;
+    onehot_to_idx_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(z0, Ms, cfg->groups,
                                                                                   cfg->classes, out->stoch_idx);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
   }
 
-  auto base_gemm = [&](const LayerPlan& L) {
+  // heads work on M start states; RSSM layers on Ms = M * slots rows
+  auto base_gemm = [&](const LayerPlan& L, bool rssm_rows = true) {
     GemmParams g{};
     g.W = wbf(L); g.RB = L.RB; g.NB = L.NB; g.G = L.G;
-    g.M = M; g.m_tiles = m_tiles; g.N = L.N;
+    g.M = rssm_rows ? Ms : M; g.m_tiles = rssm_rows ? ms_tiles : m_tiles; g.N = L.N;
     g.bias = pf(L.bias_off);
     g.ln_eps = eps;
     return g;
@@ -301,7 +337,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     }
     g.out_f32 = scratch; g.ldo = W.ld_scratch; g.out_group_stride = 0; g.stats = stats;
     RLSB_TRY(launch_gemm(g, has_ln ? EPI_STATS : EPI_PLAIN, s));
-    return launch_ln_act(scratch, W.ld_scratch, stats, L.NB, L.RB, M, m_pad, L.N,
+    return launch_ln_act(scratch, W.ld_scratch, stats, L.NB, L.RB, Ms, ms_pad, L.N,
                          has_ln ? pf(L.g_off) : nullptr, has_ln ? pf(L.b_off) : nullptr, eps, ACT_ELU,
                          outp, P.Dp, s);
   };
@@ -312,8 +348,20 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     // ---- heads on s_t = cat[h_t, z_t]: actor, reward, discount, target critic -------------------
     for (int l = 0; l < 5; ++l) {
       const LayerPlan& L = P.head[l];
-      GemmParams g = base_gemm(L);
-      if (l == 0) {
+      GemmParams g = base_gemm(L, false);
+      if (l == 0 && K > 1) {
+        // slotted State.combined (rssm_slots_attention.py:33-43): cat over slots of [h_k, z_k]; the (n, slot)-ordered
+        // images are first gathered into one operand plane per slot (pos_enc is folded into the bias)
+        RLSB_TRY(launch_slot_gather(hb, M, K, P.Dp, bf(W.hplanes), m_pad, s));
+        RLSB_TRY(launch_slot_gather(zb, M, K, P.Sp, bf(W.zplanes), m_pad, s));
+        g.n_seg = 2 * K;
+        for (int k = 0; k < K; ++k) {
+          g.A[2 * k] = bf(W.hplanes) + static_cast<size_t>(k) * m_pad * P.Dp;
+          g.a_ktiles[2 * k] = P.Dp / 64; g.a_group_stride[2 * k] = 0;
+          g.A[2 * k + 1] = bf(W.zplanes) + static_cast<size_t>(k) * m_pad * P.Sp;
+          g.a_ktiles[2 * k + 1] = P.Sp / 64; g.a_group_stride[2 * k + 1] = 0;
+        }
+      } else if (l == 0) {
         g.n_seg = 2;
         g.A[0] = hb; g.a_ktiles[0] = P.Dp / 64; g.a_group_stride[0] = 0;
         g.A[1] = zb; g.a_ktiles[1] = P.Sp / 64; g.a_group_stride[1] = 0;
@@ -354,6 +402,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     hf.actor_raw_out = (out->actor_raw && t < H) ? out->actor_raw + static_cast<size_t>(t) * N * P.Aout : nullptr;
     hf.precomp = (noise->precomp_actions && t < H) ? noise->precomp_actions + static_cast<size_t>(t) * N * P.A : nullptr;
     hf.action_packed = bf(W.abf); hf.a_kpad = P.Ap;
+    hf.action_repeat = K; hf.action_rows_pad = ms_pad;
     RLSB_TRY(launch_head_finish(hf, s));
     if (t == H) break;
 
@@ -377,16 +426,51 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       float* gst = tape ? reinterpret_cast<float*>(tp(t + 1, TP.gru_stats)) : stats;
       g.out_f32 = gsc; g.ldo = W.ld_scratch; g.stats = gst;
       RLSB_TRY(launch_gemm(g, EPI_STATS, s));
-      RLSB_TRY(launch_gru_gate(gsc, W.ld_scratch, gst, P.gru.NB, P.gru.RB, M, m_pad, P.D,
+      RLSB_TRY(launch_gru_gate(gsc, W.ld_scratch, gst, P.gru.NB, P.gru.RB, Ms, ms_pad, P.D,
                                pf(P.gru.g_off), pf(P.gru.b_off), eps, -1.0f,
                                out->determ + static_cast<size_t>(t) * ND, P.D,
                                out->determ + static_cast<size_t>(t + 1) * ND, P.D, himg(t + 1), P.Dp, s));
     }
     // ---- prior logits = W2 ELU(LN?(W1 h' + b1)) + b2                      rssm.py:192 ----------
+    const __nv_bfloat16* prior_in = himg(t + 1);
+    if (K > 1) {
+      // ---- slot mixer (rssm_slots_attention.py:186-203): determ_post = h'; per block
+      //      q,k,v = W_qkv LN(determ_post); attn over slots; determ_post += W_fc LN(attn v) + b_fc.
+      //      Only the prior logits see determ_post; the state keeps the un-mixed h' (:207).
+      float* hpost = reinterpret_cast<float*>(ws + W.hpost);
+      float* qkv = reinterpret_cast<float*>(ws + W.mix_qkv);
+      float* fco = reinterpret_cast<float*>(ws + W.mix_fc);
+      cudaError_t e = cudaMemcpyAsync(hpost, out->determ + static_cast<size_t>(t + 1) * ND, ND * 4,
+                                      cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      for (int b = 0; b <= P.nblk; ++b) {
+        const bool last = b == P.nblk;
+        // determ_post += fc output of the previous block; then pre_norm (or, after the last block, a plain pack)
+        RLSB_TRY(launch_residual_ln_pack(hpost, P.D, b > 0 ? fco : nullptr, P.D, Ms, ms_pad, P.D,
+                                         last ? nullptr : pf(P.mix_pre_g), last ? nullptr : pf(P.mix_pre_b), eps,
+                                         bf(W.mix_ln), P.Dp, s));
+        if (last) break;
+        GemmParams gq = base_gemm(P.mix_qkv);
+        gq.bias = nullptr;
+        gq.n_seg = 1;
+        gq.A[0] = bf(W.mix_ln); gq.a_ktiles[0] = P.Dp / 64;
+        gq.out_f32 = qkv; gq.ldo = W.ld_qkv;
+        RLSB_TRY(launch_gemm(gq, EPI_PLAIN, s));
+        RLSB_TRY(launch_mixer_attn(qkv, W.ld_qkv, M, K, P.D, cfg->symmetric_qk, 1.0f / sqrtf(static_cast<float>(P.D)),
+                                   1e-8f, cfg->mixer_coeff, pf(P.mix_fcn_g), pf(P.mix_fcn_b), eps, bf(W.mix_upd),
+                                   P.Dp, ms_pad, s));
+        GemmParams gf = base_gemm(P.mix_fc);
+        gf.n_seg = 1;
+        gf.A[0] = bf(W.mix_upd); gf.a_ktiles[0] = P.Dp / 64;
+        gf.out_f32 = fco; gf.ldo = P.D;
+        RLSB_TRY(launch_gemm(gf, EPI_PLAIN, s));
+      }
+      prior_in = bf(W.mix_ln);
+    }
     {
       GemmParams g = base_gemm(P.prior1);
       g.n_seg = 1;
-      g.A[0] = himg(t + 1); g.a_ktiles[0] = P.Dp / 64;
+      g.A[0] = prior_in; g.a_ktiles[0] = P.Dp / 64;
       RLSB_TRY(rssm_layer(P.prior1, g, ln, bf(W.ybf), tape ? tp(t + 1, TP.y_pre) : nullptr,
                           tape ? tp(t + 1, TP.y_rstd) : nullptr));
       GemmParams g2 = base_gemm(P.prior2);
@@ -399,9 +483,10 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     {
       NoiseSpec ns{};
       ns.explicit_noise = noise->latent_uniforms ? noise->latent_uniforms + static_cast<size_t>(t) * NS : nullptr;
-      ns.ld = P.S; ns.seed = noise->seed; ns.step = static_cast<uint32_t>(t); ns.row_offset = noise->row_offset;
-      RLSB_TRY(launch_sample_latent(out->logits + static_cast<size_t>(t + 1) * NS, P.S, M, cfg->groups,
-                                    cfg->classes, ns, out->stoch_idx + static_cast<size_t>(t + 1) * N * cfg->groups,
+      ns.ld = P.S; ns.seed = noise->seed; ns.step = static_cast<uint32_t>(t);
+      ns.row_offset = noise->row_offset * static_cast<uint32_t>(K);   // rows are (global start state, slot)
+      RLSB_TRY(launch_sample_latent(out->logits + static_cast<size_t>(t + 1) * NS, P.S, Ms, cfg->groups,
+                                    cfg->classes, ns, out->stoch_idx + static_cast<size_t>(t + 1) * Ms * cfg->groups,
                                     zimg(t + 1), P.Sp,
                                     out->stoch ? out->stoch + static_cast<size_t>(t + 1) * NS : nullptr, P.S, s));
     }

@@ -45,6 +45,10 @@ struct Plan {
   int D, S, A, Hd, Dp, Sp, Ap, Hp, Aout, G;
   int g_actor, g_reward, g_discount, g_critic;
   LayerPlan img_in, gru, prior1, prior2, head[5];
+  // ---- slotted RSSM (cfg.slots > 1): mixer blocks between the GRU and the prior logits ----
+  int K = 1, nblk = 0;
+  LayerPlan mix_qkv, mix_fc;
+  size_t mix_pre_g = 0, mix_pre_b = 0, mix_fcn_g = 0, mix_fcn_b = 0;   // fp32 [D]
   // ---- backward (cfg.with_backward): dX operands ----
   bool bwd = false;
   int Gb = 0, gb0 = 0;       // head groups that carry gradient: gb0 .. gb0+Gb-1 (reward .. target critic)
@@ -69,6 +73,9 @@ inline int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
   P.Aout = c.discrete ? c.A : 2 * c.A;
   if (P.Aout > 32 || P.Ap > 64) return -12;
   if (ru(P.Hd, 32) > 512) return -13;
+  P.K = c.slots > 1 ? c.slots : 1;
+  P.nblk = P.K > 1 ? c.attention_blocks : 0;
+  if (P.K > 1 && (P.K > 4 || P.D > 512 || c.with_backward || P.nblk < 0)) return -16;
   int g = 0;
   P.g_actor = g++;
   P.g_reward = g++;
@@ -92,8 +99,16 @@ inline int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
     LayerPlan& L = P.head[l];
     L.G = P.G;
     L.N = (l == 4) ? P.Aout : P.Hd;
-    L.kp = (l == 0) ? (P.Dp + P.Sp) : P.Hp;
+    L.kp = (l == 0) ? P.K * (P.Dp + P.Sp) : P.Hp;
     finish(L, ru(L.N, 32));
+  }
+  if (P.K > 1) {
+    P.mix_qkv.N = 3 * P.D; P.mix_qkv.kp = P.Dp; finish(P.mix_qkv, 32);
+    P.mix_fc.N = P.D; P.mix_fc.kp = P.Dp;       finish(P.mix_fc, 32);
+    P.mix_pre_g = place(cur, static_cast<size_t>(P.D) * 4);
+    P.mix_pre_b = place(cur, static_cast<size_t>(P.D) * 4);
+    P.mix_fcn_g = place(cur, static_cast<size_t>(P.D) * 4);
+    P.mix_fcn_b = place(cur, static_cast<size_t>(P.D) * 4);
   }
   P.bwd = c.with_backward != 0;
   if (P.bwd) {
@@ -150,29 +165,46 @@ inline void make_tape(const Plan& P, long long N, int H, Tape& T) {
 
 struct Workspace {
   size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
-  long long ld_scratch;
-  int m_pad;
+  // slotted RSSM: per-slot operand planes for the heads and the mixer's buffers
+  size_t hplanes, zplanes, hpost, mix_ln, mix_qkv, mix_upd, mix_fc;
+  long long ld_scratch, ld_qkv;
+  int m_pad;    // rows of the head operands (start states, padded)
+  int ms_pad;   // rows of the RSSM operands (start states x slots, padded)
   size_t bytes;
 };
 
 inline void make_workspace(const Plan& P, long long N, Workspace& W) {
   const int m_pad = ru(static_cast<int>(N), 128);
+  const int ms_pad = ru(static_cast<int>(N) * P.K, 128);
   W.m_pad = m_pad;
+  W.ms_pad = ms_pad;
   size_t cur = 0;
-  for (int i = 0; i < 2; ++i) W.hbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
-  for (int i = 0; i < 2; ++i) W.zbf[i] = place(cur, static_cast<size_t>(m_pad) * P.Sp * 2);
-  W.abf = place(cur, static_cast<size_t>(m_pad) * P.Ap * 2);
-  W.xbf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
-  W.ybf = place(cur, static_cast<size_t>(m_pad) * P.Dp * 2);
+  for (int i = 0; i < 2; ++i) W.hbf[i] = place(cur, static_cast<size_t>(ms_pad) * P.Dp * 2);
+  for (int i = 0; i < 2; ++i) W.zbf[i] = place(cur, static_cast<size_t>(ms_pad) * P.Sp * 2);
+  W.abf = place(cur, static_cast<size_t>(ms_pad) * P.Ap * 2);
+  W.xbf = place(cur, static_cast<size_t>(ms_pad) * P.Dp * 2);
+  W.ybf = place(cur, static_cast<size_t>(ms_pad) * P.Dp * 2);
   for (int i = 0; i < 2; ++i) W.hid[i] = place(cur, static_cast<size_t>(P.G) * m_pad * P.Hp * 2);
   W.ld_scratch = ru(3 * P.D, 4);
-  W.scratch = place(cur, static_cast<size_t>(m_pad) * W.ld_scratch * 4);
+  W.scratch = place(cur, static_cast<size_t>(ms_pad) * W.ld_scratch * 4);
   int nbmax = P.gru.NB;
   if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
-  W.stats = place(cur, static_cast<size_t>(nbmax) * m_pad * 2 * 4);
+  W.stats = place(cur, static_cast<size_t>(nbmax) * ms_pad * 2 * 4);
   W.head_out = place(cur, static_cast<size_t>(P.G) * m_pad * 32 * 4);
+  W.ld_qkv = ru(3 * P.D, 4);
+  W.hplanes = W.zplanes = W.hpost = W.mix_ln = W.mix_qkv = W.mix_upd = W.mix_fc = 0;
+  if (P.K > 1) {
+    W.hplanes = place(cur, static_cast<size_t>(P.K) * m_pad * P.Dp * 2);
+    W.zplanes = place(cur, static_cast<size_t>(P.K) * m_pad * P.Sp * 2);
+    W.hpost = place(cur, static_cast<size_t>(ms_pad) * P.D * 4);
+    W.mix_ln = place(cur, static_cast<size_t>(ms_pad) * P.Dp * 2);
+    W.mix_qkv = place(cur, static_cast<size_t>(ms_pad) * W.ld_qkv * 4);
+    W.mix_upd = place(cur, static_cast<size_t>(ms_pad) * P.Dp * 2);
+    W.mix_fc = place(cur, static_cast<size_t>(ms_pad) * P.D * 4);
+  }
   W.bytes = rus(cur, 1024);
 }
+
 
 
 }  // namespace k1

@@ -33,7 +33,7 @@ struct PackArgs {
   int rows_src;
   __nv_bfloat16* dst;
   int RB, rows_dst_pad, k_pad, n_seg;
-  PackSeg seg[3];
+  PackSeg seg[8];
 };
 
 __global__ void pack_kernel(const PackArgs a) {
@@ -465,12 +465,18 @@ __global__ void head_finish_kernel(const HeadFinishParams p) {
       for (int k = 0; k < p.A; ++k) p.action_out[static_cast<size_t>(m) * p.A + k] = act[k];
   }
   if (p.action_packed) {
-    for (int c0 = 0; c0 < p.a_kpad; c0 += 8) {
-      uint4 pk = make_uint4(bf2(act[c0], act[c0 + 1]), bf2(act[c0 + 2], act[c0 + 3]),
-                            bf2(act[c0 + 4], act[c0 + 5]), bf2(act[c0 + 6], act[c0 + 7]));
-      const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0),
-                                      static_cast<size_t>(p.a_kpad), kTileM);
-      *reinterpret_cast<uint4*>(p.action_packed + idx) = pk;
+    // slotted RSSM: every slot row (n * K + k) of the img_in operand sees the same action
+    // (rssm_slots_attention.py:170: action.unsqueeze(2).repeat(...))
+    const int rep = p.action_repeat > 1 ? p.action_repeat : 1;
+    for (int r = 0; r < rep; ++r) {
+      const size_t row = static_cast<size_t>(m) * rep + r;
+      if (row >= static_cast<size_t>(p.action_rows_pad)) break;
+      for (int c0 = 0; c0 < p.a_kpad; c0 += 8) {
+        uint4 pk = make_uint4(bf2(act[c0], act[c0 + 1]), bf2(act[c0 + 2], act[c0 + 3]),
+                              bf2(act[c0 + 4], act[c0 + 5]), bf2(act[c0 + 6], act[c0 + 7]));
+        const size_t idx = packed_index(row, static_cast<size_t>(c0), static_cast<size_t>(p.a_kpad), kTileM);
+        *reinterpret_cast<uint4*>(p.action_packed + idx) = pk;
+      }
     }
   }
 }
@@ -654,7 +660,7 @@ inline int grid_for(long long total, int block, int cap = 148 * 16) {
 
 int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
                 int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream) {
-  if (n_seg < 0 || n_seg > 3 || (k_pad % 64) != 0 || RB <= 0 || (rows_dst_pad % RB) != 0) return -1;
+  if (n_seg < 0 || n_seg > 8 || (k_pad % 64) != 0 || RB <= 0 || (rows_dst_pad % RB) != 0) return -1;
   PackArgs a{};
   a.src = src; a.ld_src = ld_src; a.rows_src = rows_src; a.dst = dst; a.RB = RB;
   a.rows_dst_pad = rows_dst_pad; a.k_pad = k_pad; a.n_seg = n_seg;

@@ -77,8 +77,10 @@ struct HeadFinishParams {
   float* action_out;    // [M][A]   (actions[t+1])
   float* actor_raw_out; // [M][A or 2A] raw actor head output (logits / mean,std pre-activations) or nullptr
   const float* precomp; // [M][A] action to replay instead of sampling, or nullptr
-  __nv_bfloat16* action_packed;  // [m_pad x a_kpad]
+  __nv_bfloat16* action_packed;  // [action_rows_pad x a_kpad]
   int a_kpad;
+  int action_repeat;             // slots (each action row is written `action_repeat` times), 0/1 = flat
+  int action_rows_pad;           // rows of the action image
 };
 int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream);
 
@@ -90,4 +92,24 @@ int launch_lambda_return_bwd(const float* g_vs, const float* v, const float* d, 
                              int T, long long N, double lambda_, float* g_r, float* g_v, float* g_d,
                              cudaStream_t stream);
 
+}  // namespace rlsb
+
+namespace rlsb {
+// ---- slotted RSSM (rssm_slots_attention.py:166-209), D <= 512, slots <= 4 -------------------------------
+// x[m][:] += add[m][:] (add may be nullptr), then packed = LayerNorm(x) * gamma + beta (gamma nullptr: packed = x)
+int launch_residual_ln_pack(float* x, long long ld, const float* add, long long ld_add, int M, int m_pad, int D,
+                            const float* gamma, const float* beta, float eps, __nv_bfloat16* out, int kpad,
+                            cudaStream_t stream);
+// one warp per start state n: q_i, k_j, v_j = rows n*K+{i,j} of qkv (q | k | v, each D wide);
+// attn = softmax_j(scale q_i.k_j) + eps, renormalised, blended with the identity by `coeff`;
+// upd_i = sum_j attn_ij v_j; packed row n*K+i = LayerNorm(upd_i) * gamma + beta
+int launch_mixer_attn(const float* qkv, long long ld, int N, int K, int D, int symmetric_qk, float scale,
+                      float attn_eps, float coeff, const float* gamma, const float* beta, float ln_eps,
+                      __nv_bfloat16* out, int kpad, int rows_pad, cudaStream_t stream);
+// packed slot-minor image (row n*K+k) -> K plane images [K][m_pad x kpad] (row n), padding rows zeroed
+int launch_slot_gather(const __nv_bfloat16* src, int N, int K, int kpad, __nv_bfloat16* dst, int m_pad,
+                       cudaStream_t stream);
+// bias'[j] = bias[j] + sum_i W[j][i] * pos[i]  (the constant pos_enc added to the head input folds into the bias)
+int launch_bias_fold(const float* W, long long ld, int n_out, int n_in, const float* pos, const float* bias,
+                     float* out, int out_pad, cudaStream_t stream);
 }  // namespace rlsb

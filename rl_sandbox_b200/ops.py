@@ -226,11 +226,16 @@ class ImagineConfig:
     with_critic: bool = True
     discount_nan_on_tie: bool = True   # reference-exact Bernoulli.mode (NaN at p == 0.5)
     with_backward: bool = False        # also pack the transposed images rlsb_imagine_bwd needs (D <= 512)
+    slots: int = 1                     # > 1: slotted RSSM (rssm_slots_attention.py), rows ordered (n, slot)
+    attention_blocks: int = 3
+    symmetric_qk: bool = False
+    mixer_coeff: float = 1.0           # attention_scheduler.val
 
     def to_c(self) -> ImagineCfg:
         return ImagineCfg(self.D, self.groups, self.classes, self.A, self.hidden, int(self.discrete),
                           int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H,
-                          int(self.discount_nan_on_tie), int(self.with_backward))
+                          int(self.discount_nan_on_tie), int(self.with_backward), int(self.slots),
+                          int(self.attention_blocks), int(self.symmetric_qk), float(self.mixer_coeff))
 
 
 def _mlp_params(sd: dict, prefix: str, keep: list) -> MlpParams:
@@ -290,6 +295,12 @@ class ImaginationEngine:
         p.prior1_w, p.prior1_b = take(wm_sd, rp + "ensemble_prior_estimator.0.weight"), take(wm_sd, rp + "ensemble_prior_estimator.0.bias")
         p.prior1_ln_g, p.prior1_ln_b = take(wm_sd, rp + "ensemble_prior_estimator.1.weight"), take(wm_sd, rp + "ensemble_prior_estimator.1.bias")
         p.prior2_w, p.prior2_b = take(wm_sd, rp + "ensemble_prior_estimator.3.weight"), take(wm_sd, rp + "ensemble_prior_estimator.3.bias")
+        if self.cfg.slots > 1:   # slot mixer + positional encoding (rssm_slots_attention.py:141-145, world model pos_enc)
+            p.mix_qkv_w = take(wm_sd, rp + "hidden_attention_proj.weight")
+            p.mix_pre_norm_g, p.mix_pre_norm_b = take(wm_sd, rp + "pre_norm.weight"), take(wm_sd, rp + "pre_norm.bias")
+            p.mix_fc_w, p.mix_fc_b = take(wm_sd, rp + "fc.weight"), take(wm_sd, rp + "fc.bias")
+            p.mix_fc_norm_g, p.mix_fc_norm_b = take(wm_sd, rp + "fc_norm.weight"), take(wm_sd, rp + "fc_norm.bias")
+            p.pos_enc = take(wm_sd, "pos_enc")
         p.actor = _mlp_params(actor_sd, "actor.", keep)
         p.reward = _mlp_params(wm_sd, "reward_predictor.", keep)
         if self.cfg.predict_discount:
@@ -318,15 +329,21 @@ class ImaginationEngine:
         ccfg = cfg.to_c()
         ccfg.H = H
         h0, z0 = _f32c(h0), _f32c(z0)
-        n = h0.shape[0]
         S = cfg.groups * cfg.classes
+        K = max(1, cfg.slots)
+        # slotted: h0 (n, K, D) / (n*K, D), rows ordered (start state, slot)
+        h0, z0 = h0.reshape(-1, cfg.D), z0.reshape(-1, S)
+        if h0.shape[0] % K or z0.shape[0] != h0.shape[0]:
+            raise _lib.RlsbError(f"rollout: h0 {tuple(h0.shape)} / z0 {tuple(z0.shape)} for slots={K}")
+        n = h0.shape[0] // K
         dev = h0.device
+        sh = (n,) if K == 1 else (n, K)
         if out is None:
             out = {
-                "determ": torch.empty((H + 1, n, cfg.D), device=dev, dtype=torch.float32),
-                "logits": torch.empty((H + 1, n, S), device=dev, dtype=torch.float32),
-                "stoch_idx": torch.empty((H + 1, n, cfg.groups), device=dev, dtype=torch.uint8),
-                "stoch": torch.empty((H + 1, n, S), device=dev, dtype=torch.float32) if want_stoch else None,
+                "determ": torch.empty((H + 1,) + sh + (cfg.D,), device=dev, dtype=torch.float32),
+                "logits": torch.empty((H + 1,) + sh + (S,), device=dev, dtype=torch.float32),
+                "stoch_idx": torch.empty((H + 1,) + sh + (cfg.groups,), device=dev, dtype=torch.uint8),
+                "stoch": torch.empty((H + 1,) + sh + (S,), device=dev, dtype=torch.float32) if want_stoch else None,
                 "actions": torch.empty((H + 1, n, cfg.A), device=dev, dtype=torch.float32),
                 "rewards": torch.empty((H + 1, n), device=dev, dtype=torch.float32),
                 "discounts": torch.empty((H + 1, n), device=dev, dtype=torch.float32),

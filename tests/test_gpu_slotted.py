@@ -1,0 +1,79 @@
+"""GPU parity of the slotted imagination step (K1 with slots > 1: rlsb_imagine.cu + rlsb_mixer.cu) against the
+reference's slotted world model (tests/golden/imagine_slotted.npz) and against the oracle at a ragged size."""
+import pytest
+import torch
+
+from oracle import oracle_port as orc
+from tests.test_oracle import _load_slotted
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(m, H, blocks=3, coeff=1.0):
+    from rl_sandbox_b200 import ops
+    cfg = ops.ImagineConfig(D=m["D"], A=m["A"], discrete=m["discrete"], layer_norm=m["layer_norm"],
+                            predict_discount=m["predict_discount"], H=H, slots=m["K"], attention_blocks=blocks,
+                            mixer_coeff=coeff)
+    return ops.ImaginationEngine(cfg)
+
+
+def _rel(a, b):
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+def test_slotted_rollout_matches_reference(cuda):
+    m, gold, wm, actor, critic, h0, z0, lat, act = _load_slotted()
+    H, N, K = m["H"], m["N"], m["K"]
+    eng = _engine(m, H, m["blocks"])
+    to = lambda sd: {k: v.cuda() for k, v in sd.items()}
+    eng.pack(to(wm), to(actor), to(critic))
+    out = eng.rollout(h0.cuda(), z0.cuda(), None, lat.cuda(), act.cuda())
+    torch.cuda.synchronize()
+    assert out["determ"].shape == (H + 1, N, K, m["D"]) and out["logits"].shape == (H + 1, N, K, 1024)
+    assert out["stoch_idx"].shape == (H + 1, N, K, 32) and out["rewards"].shape == (H + 1, N)
+    # (1) indices are bit-exact given the kernel's own logits and the uniforms
+    own = orc.sample_categorical(out["logits"][1:].cpu().view(H, N, K, 32, 32), lat.view(H, N, K, 32, 32))
+    assert torch.equal(own, out["stoch_idx"][1:].cpu().long())
+    # (2) first transition from the reference's start state (no accumulated divergence)
+    for k, tol in (("determ", 3e-3), ("logits", 8e-3)):
+        e = _rel(out[k][1].cpu(), gold[k][1])
+        print(f"[parity] slotted step 1 {k}: rel-RMS vs reference {e:.3e}")
+        assert e < tol, (k, e)
+    for k in ("rewards", "values"):
+        e = _rel(out[k][:2].cpu(), gold[k][:2])
+        print(f"[parity] slotted {k}[0:2]: rel-RMS vs reference {e:.3e}")
+        assert e < 2e-2, (k, e)
+    # (3) whole trajectories where every draw coincides with the reference's
+    same = (out["stoch_idx"].cpu() == gold["stoch_idx"]).all(-1).all(-1).cumprod(0).bool()
+    frac = same[-1].float().mean().item()
+    print(f"[parity] slotted: start states with identical draws over all {H} steps: {frac:.2f}")
+    if same[-1].any():
+        e = _rel(out["determ"].cpu()[:, same[-1]], gold["determ"][:, same[-1]])
+        ea = _rel(out["actions"].cpu()[:, same[-1]], gold["actions"][:, same[-1]])
+        print(f"[parity] slotted trajectories: determ rel-RMS {e:.3e}, actions {ea:.3e}")
+        assert e < 5e-3 and ea < 2e-2
+
+
+@pytest.mark.parametrize("N,K,blocks,coeff", [(300, 4, 3, 1.0), (77, 2, 1, 0.4)])
+def test_slotted_rollout_matches_bf16_oracle(cuda, N, K, blocks, coeff):
+    """ragged sizes / other slot counts against the oracle with bf16-rounded contraction operands"""
+    m = dict(D=200, A=3, K=K, discrete=True, layer_norm=True, predict_discount=True)
+    H = 4
+    wm, actor, critic = orc.make_params_slotted(5, D=200, A=3, K=K, discrete=True, layer_norm=True, predict_discount=True)
+    h0, z0 = orc.make_start(6, N * K, 200)
+    h0, z0 = h0.view(N, K, 200), z0.view(N, K, 1024)
+    g = torch.Generator().manual_seed(7)
+    lat, act = torch.rand(H, N, K, 1024, generator=g), torch.rand(H, N, 3, generator=g)
+    ref = orc.imagine_slotted(wm, actor, critic, h0, z0, H=H, A=3, K=K, discrete=True, predict_discount=True,
+                              latent_uniforms=lat, action_noise=act, blocks=blocks, coeff=coeff, bf16=True)
+    eng = _engine(m, H, blocks, coeff)
+    to = lambda sd: {k: v.cuda() for k, v in sd.items()}
+    eng.pack(to(wm), to(actor), to(critic))
+    out = eng.rollout(h0.cuda(), z0.cuda(), None, lat.cuda(), act.cuda())
+    same = ((out["stoch_idx"].cpu().long() == ref["stoch_idx"]).all(-1).all(-1) &
+            (out["actions"].cpu().argmax(-1) == ref["actions"].argmax(-1))).cumprod(0).bool()
+    frac = same[-1].float().mean().item()
+    e = _rel(out["determ"].cpu()[:, same[-1]], ref["determ"][:, same[-1]])
+    el = _rel(out["logits"].cpu()[1:, same[-1]], ref["logits"][1:, same[-1]])
+    print(f"[parity] slotted N={N} K={K}: identical draws {frac:.3f}, determ rel-RMS {e:.2e}, logits {el:.2e}")
+    assert frac > 0.9 and e < 1e-3 and el < 3e-3

@@ -127,3 +127,30 @@ def test_oracle_continuous_gradients_match_reference(name):
         assert abs(g.norm().item() - gold["grad_norms"][i].item()) <= 1e-3 * gold["grad_norms"][i].item() + 1e-9, n
         torch.testing.assert_close(g.flatten()[grad_probe_indices(g.numel())], gold["grad_probes"][i], rtol=5e-3,
                                    atol=1e-6 * max(1.0, gold["grad_norms"][i].item()), msg=lambda s_: f"{n}: {s_}")
+
+
+def _load_slotted():
+    import json
+    import numpy as np
+    from oracle.gen_golden import SLOTTED_CASE, slotted_inputs
+    from tests._golden import GOLDEN
+    z = np.load(GOLDEN / "imagine_slotted.npz")
+    m = json.loads(str(z["meta"]))
+    assert m == SLOTTED_CASE, "fixture is stale: re-run python -m oracle.gen_golden"
+    gold = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files if k != "meta"}
+    wm, actor, critic = orc.make_params_slotted(m["param_seed"], D=m["D"], A=m["A"], K=m["K"], discrete=m["discrete"],
+                                                layer_norm=m["layer_norm"], predict_discount=m["predict_discount"])
+    h0, z0, lat, act = slotted_inputs()
+    return m, gold, wm, actor, critic, h0, z0, lat, act
+
+
+def test_oracle_slotted_rollout_matches_reference():
+    """oracle_port.imagine_slotted vs the reference's DreamerV2.imagine_trajectory over the slotted world model
+    (rssm_slots_attention.py:166-209: mixer blocks, un-mixed determ in the state, pos_enc on the head input)."""
+    m, gold, wm, actor, critic, h0, z0, lat, act = _load_slotted()
+    out = orc.imagine_slotted(wm, actor, critic, h0, z0, H=m["H"], A=m["A"], K=m["K"], discrete=m["discrete"],
+                              predict_discount=m["predict_discount"], latent_uniforms=lat, action_noise=act,
+                              blocks=m["blocks"])
+    assert torch.equal(out["stoch_idx"], gold["stoch_idx"].long()), "categorical indices must be bit-exact"
+    for k in ("determ", "logits", "actions", "rewards", "values"):
+        torch.testing.assert_close(out[k], gold[k], rtol=1e-4, atol=3e-5, msg=lambda s: f"{k}: {s}")
