@@ -89,11 +89,16 @@ class DreamerV2(RlAgent):
         from rl_sandbox_b200 import ops
         if self._engine is None:
             wm = self.world_model
+            slots = int(getattr(wm, 'slots_num', 0) or 1)
+            rm = wm.recurrent_model
             cfg = ops.ImagineConfig(D=wm.rssm_dim, A=self.actions_num, discrete=self.is_discrete,
                                     layer_norm=bool(wm.layer_norm), predict_discount=bool(wm.predict_discount),
                                     H=self.imagination_horizon, groups=wm.latent_dim, classes=wm.latent_classes,
                                     with_critic=True, discount_nan_on_tie=self.reference_exact_discount_nan,
-                                    with_backward=(not self.is_discrete) and wm.rssm_dim <= 512 and wm.rssm_dim % 8 == 0)
+                                    with_backward=(slots == 1 and not self.is_discrete and wm.rssm_dim <= 512
+                                                   and wm.rssm_dim % 8 == 0),
+                                    slots=slots, attention_blocks=int(getattr(rm, 'attention_block_num', 0)),
+                                    symmetric_qk=bool(getattr(rm, 'symmetric_qk', False)))
             self._engine = ops.ImaginationEngine(cfg, device=self.device)
         if self._packed_version != self._weights_version:
             self._engine.pack(self.world_model.state_dict(), self.actor.state_dict(), self.critic.state_dict())
@@ -142,9 +147,12 @@ class DreamerV2(RlAgent):
         eng = self._get_engine()
         N = init_state.determ.shape[1]
         S = self.world_model.latent_dim * self.world_model.latent_classes
+        slotted = eng.cfg.slots > 1
+        if slotted:   # (1, N, slots, .) states; the mixer coefficient follows the world model's scheduler
+            eng.cfg.mixer_coeff = float(self.world_model.recurrent_model.attention_scheduler.val)
         h0 = init_state.determ[0].detach().float()
         z0 = init_state.stoch[0].detach().float()
-        logits0 = init_state.stoch_logits[0].detach().float().reshape(N, S)
+        logits0 = init_state.stoch_logits[0].detach().float().reshape(-1, S)
         noise = dict(noise or {})
         if 'seed' not in noise and 'latent_uniforms' not in noise:
             noise['seed'] = (self._noise_seed << 20) + self._rollouts
@@ -159,6 +167,12 @@ class DreamerV2(RlAgent):
                           keep_packed=keep_packed, want_stoch=not keep_packed, tape=tape)
         self.last_rollout = out
         wm = self.world_model
+        if slotted:
+            from rl_sandbox_b200.agents.dreamer.rssm_slots_attention import State as SlotState
+            K = eng.cfg.slots
+            states = SlotState(out['determ'], out['logits'].view(horizon + 1, N, K, wm.latent_dim, wm.latent_classes),
+                               out['stoch'], init_state.pos_enc)
+            return states, out['actions'], out['rewards'].unsqueeze(-1), out['discounts'].unsqueeze(-1)
         states = State(out['determ'], out['logits'].view(horizon + 1, N, wm.latent_dim, wm.latent_classes),
                        out['stoch'])
         return states, out['actions'], out['rewards'].unsqueeze(-1), out['discounts'].unsqueeze(-1)
