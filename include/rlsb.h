@@ -32,6 +32,9 @@ int rlsb_check_device(void);
 const char* rlsb_error_string(int code);
 /* number of CUDA kernels this library has launched since load (or since the last reset != 0) */
 long long rlsb_launch_count(int reset);
+/* a CUDA-graph replay launches the kernels recorded at capture time without passing through the library:
+ * the caller that replays a graph adds the captured launch count here so the counter stays truthful */
+long long rlsb_launch_count_add(long long n);
 /* tuning: CTAs per thread-block cluster sharing one weight block via TMA multicast (1, 2 or 4;
  * default 2, env RLSB_CLUSTER).  Returns the value in effect. */
 int rlsb_set_cluster_size(int cs);
@@ -163,6 +166,9 @@ typedef struct {
   /* (H, N, A) actions to replay instead of sampling the actor (metrics caller of
    * imagine_trajectory(state, precomp_actions, horizon), dreamer_v2.py:83-84), or NULL */
   const float* precomp_actions;
+  /* device-resident Philox key; when non-NULL it overrides `seed`, so a CUDA graph that captured the call
+   * draws fresh noise on every replay (the caller rewrites the 8 bytes between replays) */
+  const uint64_t* seed_device;
 } rlsb_noise;
 
 typedef struct {
@@ -266,10 +272,11 @@ int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor, const rls
 /* vs: (H, N) lambda-returns; w: (H+1, N) cumprod weights; values: (H+1, N) target critic (baseline and
  * critic/avg_target_value); actions: (H+1, N, A) one-hot (row t+1 = action taken in state t);
  * g_actions: (H, N, A) d loss_actor / d a_t from rlsb_imagine_bwd when rho != 1 (continuous actor), else NULL;
- * scalars: RLSB_AC_SCALARS floats (device).  seed keys the Philox stream of the metric draws. */
+ * scalars: RLSB_AC_SCALARS floats (device).  seed (or the device-resident seed_device, if non-NULL) keys the
+ * Philox stream of the metric draws. */
 int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,
                    const void* stoch_packed, const float* vs, const float* w, const float* values,
-                   const float* actions, const float* g_actions, uint64_t seed,
+                   const float* actions, const float* g_actions, uint64_t seed, const uint64_t* seed_device,
                    const rlsb_mlp_grads* actor_grads,
                    const rlsb_mlp_grads* critic_grads, float* scalars, void* workspace, void* stream);
 

@@ -43,7 +43,7 @@ class ImagineParams(C.Structure):
 
 class Noise(C.Structure):
     _fields_ = [("latent_uniforms", C.c_void_p), ("action_noise", C.c_void_p), ("seed", C.c_uint64),
-                ("row_offset", C.c_uint32), ("precomp_actions", C.c_void_p)]
+                ("row_offset", C.c_uint32), ("precomp_actions", C.c_void_p), ("seed_device", C.c_void_p)]
 
 
 class ImagineOut(C.Structure):
@@ -101,6 +101,7 @@ def load() -> C.CDLL:
         "rlsb_check_device": (C.c_int, []),
         "rlsb_error_string": (C.c_char_p, [i32]),
         "rlsb_launch_count": (C.c_longlong, [i32]),
+        "rlsb_launch_count_add": (C.c_longlong, [C.c_longlong]),
         "rlsb_set_cluster_size": (C.c_int, [i32]),
         "rlsb_lambda_return_fwd": (C.c_int, [vp, vp, vp, i32, i64, C.c_double, vp, vp, vp, i32, vp]),
         "rlsb_lambda_return_bwd": (C.c_int, [vp, vp, vp, vp, i32, i64, C.c_double, vp, vp, vp, vp]),
@@ -128,7 +129,7 @@ def load() -> C.CDLL:
         "rlsb_ac_packed_bytes": (sz, [C.POINTER(AcCfg)]),
         "rlsb_ac_workspace_bytes": (sz, [C.POINTER(AcCfg), i64]),
         "rlsb_ac_pack": (C.c_int, [C.POINTER(AcCfg), C.POINTER(MlpParams), C.POINTER(MlpParams), vp, vp]),
-        "rlsb_ac_update": (C.c_int, [C.POINTER(AcCfg), vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(MlpGrads),
+        "rlsb_ac_update": (C.c_int, [C.POINTER(AcCfg), vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, vp, C.POINTER(MlpGrads),
                                      C.POINTER(MlpGrads), vp, vp, vp]),
         "rlsb_imagine_tape_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
         "rlsb_imagine_bwd_workspace_bytes": (sz, [C.POINTER(ImagineCfg), i64]),

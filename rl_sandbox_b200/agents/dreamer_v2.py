@@ -68,6 +68,11 @@ class DreamerV2(RlAgent):
         self._ac_engine = None       # lazily built ACUpdateEngine (K4: fused critic/actor losses + backward)
         self._ac_packed_version = -1
         self.fused_ac_update = True  # False: torch autograd on the K1 outputs (the reference's op sequence)
+        # launch-bound shapes (the configured N = 16 x 50 = 800): capture pack + K1 + K2 (+ bwd) + K4 once per shape
+        # in a CUDA graph and replay it; the Philox key lives in device memory so every replay draws fresh noise
+        self.cuda_graph = True
+        self.cuda_graph_max_rows = 8192
+        self._graphs: dict = {}
         self._weights_version = 0    # bumped whenever parameters change
         self._packed_version = -1
         self._noise_seed = 0x5EED    # Philox key; the step counter below is mixed in per rollout
@@ -268,23 +273,14 @@ class DreamerV2(RlAgent):
         """Discrete actor (rho == 1): K1 rollout keeping the packed state images -> K2 -> K4 (critic / actor
         forward, losses, backward to parameter gradients in librlsb) -> all-reduce, clip, AdamW."""
         from rl_sandbox_b200 import _lib, ops
-        with torch.no_grad():
-            dyn = self.actor.rho != 1.0   # dynamics back-propagation (ac.py:121-123): K2 bwd -> K1 bwd -> g_actions
-            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True, tape=dyn)
-            k1 = self.last_rollout
-            H, n = k1['determ'].shape[0] - 1, k1['determ'].shape[1]
-            # reward_normalizer is the identity (momentum 1.0, world_model.py:111; SURVEY hard part 7)
-            vs, w, _ = ops.lambda_return(k1['rewards'], k1['values'], k1['discounts'], self.critic.lambda_)
-            g_actions = None
-            if dyn:
-                # d/d vs of -mean((1 - rho) * vs[1:] * w[:-2]) (vs has H rows: V_0 .. V_{H-1})
-                g_vs = torch.zeros_like(vs)
-                g_vs[1:] = w[:H - 1] * (-(1.0 - float(self.actor.rho)) / ((H - 1) * n))
-                g_r, g_v, _ = ops.lambda_return_bwd(g_vs, k1['values'], k1['discounts'], vs, self.critic.lambda_)
-                g_actions = self._engine.backward(k1, g_r, g_v)
-            ac = self._get_ac_engine()
-            scal = ac.update(k1, vs, w, self.actor.actor, self.critic.critic, seed=self._noise_seed + self._rollouts,
-                             horizon=H, g_actions=g_actions)
+        noise = dict(noise or {})
+        n_rows = initial_states.determ.shape[1]
+        explicit = 'latent_uniforms' in noise or 'action_noise' in noise
+        if self.cuda_graph and not explicit and n_rows <= self.cuda_graph_max_rows:
+            scal = self._fused_step_graphed(initial_states, noise)
+        else:
+            with torch.no_grad():
+                scal = self._fused_step(initial_states, noise)
         metrics_a = self.actor_optimizer.step_with_grads()
         metrics_c = self.critic_optimizer.step_with_grads()
         self.critic.update_target()
@@ -295,6 +291,77 @@ class DreamerV2(RlAgent):
                                             'loss_actor_entropy', 'loss_actor', 'loss_critic')}
         metrics = {k: scal[i] for k, i in idx.items() if '/' in k}
         return losses, metrics | metrics_a | metrics_c
+
+    def _fused_step(self, initial_states: State, noise: dict, seed_device=None, static=None):
+        """pack (if stale) -> K1 -> K2 [-> K2 bwd -> K1 bwd] -> K4; returns the K4 scalar vector (device)."""
+        from rl_sandbox_b200 import ops
+        dyn = self.actor.rho != 1.0   # dynamics back-propagation (ac.py:121-123): K2 bwd -> K1 bwd -> g_actions
+        if static is None:
+            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True, tape=dyn)
+            k1 = self.last_rollout
+            ac = self._get_ac_engine()
+        else:   # graph body: always re-pack (the parameters change between replays), static buffers, device-resident key
+            eng, ac = static['eng'], static['ac']
+            eng.pack(self.world_model.state_dict(), self.actor.state_dict(), self.critic.state_dict())
+            ac.pack(self.actor.state_dict(), self.critic.state_dict())
+            k1 = eng.rollout(static['h0'], static['z0'], static['logits0'], seed_device=seed_device,
+                             row_offset=noise.get('row_offset', 0), keep_packed=True, tape=dyn, want_stoch=False,
+                             out=static.get('out'))
+            static['out'] = k1
+            self.last_rollout = k1
+        H, n = k1['determ'].shape[0] - 1, k1['determ'].shape[1]
+        # reward_normalizer is the identity (momentum 1.0, world_model.py:111; SURVEY hard part 7)
+        vs, w, _ = ops.lambda_return(k1['rewards'], k1['values'], k1['discounts'], self.critic.lambda_)
+        g_actions = None
+        if dyn:
+            # d/d vs of -mean((1 - rho) * vs[1:] * w[:-2]) (vs has H rows: V_0 .. V_{H-1})
+            g_vs = torch.zeros_like(vs)
+            g_vs[1:] = w[:H - 1] * (-(1.0 - float(self.actor.rho)) / ((H - 1) * n))
+            g_r, g_v, _ = ops.lambda_return_bwd(g_vs, k1['values'], k1['discounts'], vs, self.critic.lambda_)
+            g_actions = self._engine.backward(k1, g_r, g_v)
+        return ac.update(k1, vs, w, self.actor.actor, self.critic.critic, seed=self._noise_seed + self._rollouts,
+                         horizon=H, g_actions=g_actions, seed_device=seed_device)
+
+    def _fused_step_graphed(self, initial_states: State, noise: dict):
+        """CUDA-graph replay of ``_fused_step`` for one (rows, horizon, shard offset) shape."""
+        n = initial_states.determ.shape[1]
+        S = self.world_model.latent_dim * self.world_model.latent_classes
+        h0 = initial_states.determ[0].detach().float()
+        z0 = initial_states.stoch[0].detach().float()
+        logits0 = initial_states.stoch_logits[0].detach().float().reshape(n, S)
+        seed = noise.get('seed', (self._noise_seed << 20) + self._rollouts)
+        self._rollouts += 1
+        key = (n, self.imagination_horizon, int(noise.get('row_offset', 0)), self.metrics_samples)
+        st = self._graphs.get(key)
+        with torch.no_grad():
+            if st is None:
+                st = {'h0': h0.clone(), 'z0': z0.clone(), 'logits0': logits0.clone(),
+                      'seed': torch.zeros(1, device=h0.device, dtype=torch.int64),
+                      'eng': self._get_engine(), 'ac': self._get_ac_engine()}
+                st['seed'].fill_(seed)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):   # warm-up outside capture: workspaces, .grad buffers, kernel attributes
+                    for _ in range(2):
+                        self._fused_step(None, noise, seed_device=st['seed'], static=st)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                lib = st['eng'].lib
+                before = lib.rlsb_launch_count(0)
+                with torch.cuda.graph(graph):
+                    st['scal'] = self._fused_step(None, noise, seed_device=st['seed'], static=st)
+                st['launches'] = lib.rlsb_launch_count(0) - before   # kernels recorded in the graph
+                lib.rlsb_launch_count_add(-st['launches'])           # capture itself launched nothing
+                st['graph'] = graph
+                self._graphs[key] = st
+            st['h0'].copy_(h0)
+            st['z0'].copy_(z0)
+            st['logits0'].copy_(logits0)
+            st['seed'].fill_(seed)
+            st['graph'].replay()
+            st['eng'].lib.rlsb_launch_count_add(st['launches'])
+            self.last_rollout = st['out']
+        return st['scal']
 
     def train(self, rollout_chunks: RolloutChunks):
         obs, a, r, is_finished, is_first, additional = unpack(rollout_chunks)

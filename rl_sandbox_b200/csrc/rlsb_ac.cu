@@ -172,6 +172,7 @@ struct AcLossArgs {
   float rho, eta;
   int metrics_samples;
   uint64_t seed;
+  const uint64_t* seed_ptr;   // device-resident key overriding `seed` (CUDA-graph replays)
   __nv_bfloat16* dy4;      // packed [2][M x 64]
   double* accum;
 };
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(128) ac_loss_kernel(const AcLossArgs a) {
   float acc[ACC_COUNT];
 #pragma unroll
   for (int i = 0; i < ACC_COUNT; ++i) acc[i] = 0.f;
+  const uint64_t key = a.seed_ptr ? __ldg(a.seed_ptr) + 0x9E3779B97F4A7C15ull : a.seed;
   if (m < M) {
     const int t = static_cast<int>(m / a.m_pad);
     const int i = static_cast<int>(m - static_cast<long long>(t) * a.m_pad);
@@ -235,8 +237,8 @@ __global__ void __launch_bounds__(128) ac_loss_kernel(const AcLossArgs a) {
             for (int sidx = 0; sidx < a.metrics_samples; sidx += 4) {
               uint32_t o[4];
               rlsb_philox4x32(static_cast<uint32_t>(m), static_cast<uint32_t>(m >> 32) ^ (static_cast<uint32_t>(k) << 8), 7u,
-                              static_cast<uint32_t>(sidx >> 2), static_cast<uint32_t>(a.seed),
-                              static_cast<uint32_t>(a.seed >> 32), o);
+                              static_cast<uint32_t>(sidx >> 2), static_cast<uint32_t>(key),
+                              static_cast<uint32_t>(key >> 32), o);
               float z[4];
               const float r0 = sqrtf(-2.0f * __logf(rlsb_u32_to_uniform(o[0])));
               const float r1 = sqrtf(-2.0f * __logf(rlsb_u32_to_uniform(o[2])));
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(128) ac_loss_kernel(const AcLossArgs a) {
           for (int sidx = 0; sidx < a.metrics_samples; sidx += 4) {
             uint32_t o[4];
             rlsb_philox4x32(static_cast<uint32_t>(m), static_cast<uint32_t>(m >> 32), 7u, static_cast<uint32_t>(sidx >> 2),
-                            static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32), o);
+                            static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), o);
             for (int j = 0; j < 4 && sidx + j < a.metrics_samples; ++j) {
               const float u = rlsb_u32_to_uniform(o[j]) * run;
               int k = 0;
@@ -480,7 +482,7 @@ extern "C" int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor
 extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,
                               const void* stoch_packed, const float* vs, const float* w, const float* values,
                               const float* actions, const float* g_actions, uint64_t seed,
-                              const rlsb_mlp_grads* actor_grads,
+                              const uint64_t* seed_device, const rlsb_mlp_grads* actor_grads,
                               const rlsb_mlp_grads* critic_grads, float* scalars, void* workspace, void* stream_) {
   if (!cfg || !packed || !determ_packed || !stoch_packed || !vs || !w || !values || !actions || !actor_grads ||
       !critic_grads || !scalars || !workspace || N <= 0)
@@ -553,7 +555,7 @@ extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_
     a.m_pad = W.m_pad; a.N = static_cast<int>(N); a.H = P.H; a.A = P.A;
     a.vs = vs; a.w = w; a.values = values; a.actions = actions; a.g_actions = g_actions;
     a.discrete = cfg->discrete;
-    a.rho = cfg->rho; a.eta = cfg->eta; a.metrics_samples = cfg->metrics_samples; a.seed = seed;
+    a.rho = cfg->rho; a.eta = cfg->eta; a.metrics_samples = cfg->metrics_samples; a.seed = seed; a.seed_ptr = seed_device;
     a.dy4 = bfw(W.dy4); a.accum = accum;
     ac_loss_kernel<<<static_cast<unsigned>((W.M + 127) / 128), 128, 0, s>>>(a);
     count_launch();

@@ -33,6 +33,11 @@ extern "C" long long rlsb_launch_count(int reset) {
   return v;
 }
 
+extern "C" long long rlsb_launch_count_add(long long n) {
+  g_launches.fetch_add(n);
+  return g_launches.load();
+}
+
 extern "C" int rlsb_set_cluster_size(int cs) {
   set_gemm_cluster_size(cs);
   return gemm_cluster_size();

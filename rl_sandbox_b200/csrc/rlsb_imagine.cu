@@ -393,7 +393,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     hf.M = M; hf.m_pad = m_pad; hf.A = P.A; hf.discrete = cfg->discrete;
     hf.first_step = (t == 0); hf.want_action = (t < H); hf.nan_on_tie = cfg->discount_nan_on_tie;
     hf.noise.explicit_noise = noise->action_noise ? noise->action_noise + static_cast<size_t>(t) * N * P.A : nullptr;
-    hf.noise.ld = P.A; hf.noise.seed = noise->seed; hf.noise.step = static_cast<uint32_t>(t);
+    hf.noise.ld = P.A; hf.noise.seed = noise->seed; hf.noise.seed_ptr = noise->seed_device; hf.noise.step = static_cast<uint32_t>(t);
     hf.noise.row_offset = noise->row_offset;
     hf.reward_out = out->rewards + static_cast<size_t>(t) * N;
     hf.discount_out = out->discounts + static_cast<size_t>(t) * N;
@@ -483,7 +483,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     {
       NoiseSpec ns{};
       ns.explicit_noise = noise->latent_uniforms ? noise->latent_uniforms + static_cast<size_t>(t) * NS : nullptr;
-      ns.ld = P.S; ns.seed = noise->seed; ns.step = static_cast<uint32_t>(t);
+      ns.ld = P.S; ns.seed = noise->seed; ns.seed_ptr = noise->seed_device; ns.step = static_cast<uint32_t>(t);
       ns.row_offset = noise->row_offset * static_cast<uint32_t>(K);   // rows are (global start state, slot)
       RLSB_TRY(launch_sample_latent(out->logits + static_cast<size_t>(t + 1) * NS, P.S, Ms, cfg->groups,
                                     cfg->classes, ns, out->stoch_idx + static_cast<size_t>(t + 1) * Ms * cfg->groups,

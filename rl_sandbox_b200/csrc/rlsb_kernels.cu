@@ -288,14 +288,15 @@ __global__ void gru_gate_kernel(const GruArgs a) {
 __device__ __forceinline__ float noise_uniform(const NoiseSpec& ns, int m, uint32_t stream,
                                                uint32_t e) {
   if (ns.explicit_noise) return __ldg(ns.explicit_noise + static_cast<size_t>(m) * ns.ld + e);
-  return rlsb_noise_uniform(ns.seed, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, e);
+  return rlsb_noise_uniform(ns.seed_ptr ? __ldg(ns.seed_ptr) : ns.seed, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, e);
 }
 
 // Box-Muller on two Philox uniforms (device-only path; parity tests pass explicit normals)
 __device__ __forceinline__ float noise_normal(const NoiseSpec& ns, int m, uint32_t stream, uint32_t e) {
   if (ns.explicit_noise) return __ldg(ns.explicit_noise + static_cast<size_t>(m) * ns.ld + e);
-  const float u1 = rlsb_noise_uniform(ns.seed, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, 2 * e);
-  const float u2 = rlsb_noise_uniform(ns.seed, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, 2 * e + 1);
+  const uint64_t key = ns.seed_ptr ? __ldg(ns.seed_ptr) : ns.seed;
+  const float u1 = rlsb_noise_uniform(key, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, 2 * e);
+  const float u2 = rlsb_noise_uniform(key, ns.row_offset + static_cast<uint32_t>(m), ns.step, stream, 2 * e + 1);
   return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 
@@ -321,6 +322,7 @@ __global__ void sample_latent_kernel(const SampleLatentArgs a) {
   const int m = static_cast<int>(i / a.groups);
   const int g = static_cast<int>(i - static_cast<long long>(m) * a.groups);
   const float4* lp = reinterpret_cast<const float4*>(a.logits + static_cast<size_t>(m) * a.ld + g * 32);
+  const uint64_t key = a.noise.seed_ptr ? __ldg(a.noise.seed_ptr) : a.noise.seed;
   float best = 0.f;
   int best_k = 0;
 #pragma unroll
@@ -334,8 +336,8 @@ __global__ void sample_latent_kernel(const SampleLatentArgs a) {
     } else {
       uint32_t o[4];
       rlsb_philox4x32(a.noise.row_offset + static_cast<uint32_t>(m), a.noise.step, 0u,
-                      static_cast<uint32_t>(g * 8 + q), static_cast<uint32_t>(a.noise.seed),
-                      static_cast<uint32_t>(a.noise.seed >> 32), o);
+                      static_cast<uint32_t>(g * 8 + q), static_cast<uint32_t>(key),
+                      static_cast<uint32_t>(key >> 32), o);
 #pragma unroll
       for (int t = 0; t < 4; ++t) u[t] = rlsb_u32_to_uniform(o[t]);
     }
@@ -438,7 +440,8 @@ __global__ void head_finish_kernel(const HeadFinishParams p) {
       for (int k = 0; k < p.A; ++k) {
         const float u = p.noise.explicit_noise
                             ? __ldg(p.noise.explicit_noise + static_cast<size_t>(m) * p.noise.ld + k)
-                            : rlsb_noise_uniform(p.noise.seed, p.noise.row_offset + m, p.noise.step, 1u, k);
+                            : rlsb_noise_uniform(p.noise.seed_ptr ? __ldg(p.noise.seed_ptr) : p.noise.seed,
+                                                 p.noise.row_offset + m, p.noise.step, 1u, k);
         const float s = __fadd_rn(ao[k], rlsb_gumbel(u));
         if (k == 0 || s > best) {
           best = s;

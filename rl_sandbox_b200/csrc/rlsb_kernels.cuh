@@ -47,6 +47,7 @@ struct NoiseSpec {
   const float* explicit_noise;  // uniforms (categorical) / normals (continuous) or nullptr
   long long ld;                 // row stride of the explicit tensor (elements)
   uint64_t seed;                // Philox key when explicit_noise == nullptr
+  const uint64_t* seed_ptr;     // device-resident key overriding `seed` (CUDA-graph replays change it without re-capture)
   uint32_t step;                // imagination step (Philox counter word)
   uint32_t row_offset;          // global index of local row 0 (multi-GPU sharding)
 };

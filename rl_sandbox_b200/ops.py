@@ -323,7 +323,8 @@ class ImaginationEngine:
                 latent_uniforms: Optional[torch.Tensor] = None, action_noise: Optional[torch.Tensor] = None,
                 seed: int = 0, row_offset: int = 0, precomp_actions: Optional[torch.Tensor] = None,
                 horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
-                out: Optional[dict] = None, keep_packed: bool = False, tape: bool = False) -> dict:
+                out: Optional[dict] = None, keep_packed: bool = False, tape: bool = False,
+                seed_device: Optional[torch.Tensor] = None) -> dict:
         cfg = self.cfg
         H = horizon if horizon is not None else cfg.H
         ccfg = cfg.to_c()
@@ -366,7 +367,7 @@ class ImaginationEngine:
                                                       "determ_packed", "stoch_packed", "tape")])
         nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)),
                    _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
-                   _ptr(None if precomp_actions is None else _f32c(precomp_actions)))
+                   _ptr(None if precomp_actions is None else _f32c(precomp_actions)), _ptr(seed_device))
         ws = self.workspace(n)
         check(self.lib.rlsb_imagine_fwd(C.byref(ccfg), self.packed.data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
@@ -447,7 +448,8 @@ class ACUpdateEngine:
         self._keep = keep
 
     def update(self, rollout: dict, vs: torch.Tensor, w: torch.Tensor, actor_seq, critic_seq, seed: int = 0,
-               horizon: Optional[int] = None, g_actions: Optional[torch.Tensor] = None) -> torch.Tensor:
+               horizon: Optional[int] = None, g_actions: Optional[torch.Tensor] = None,
+               seed_device: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Writes .grad of every parameter of ``actor_seq`` / ``critic_seq`` (fc_nn Sequentials) and returns the
         RLSB_AC_SCALARS loss / metric vector (device tensor, see _lib.AC_SCALAR_NAMES)."""
         if rollout.get("determ_packed") is None:
@@ -469,7 +471,8 @@ class ACUpdateEngine:
         check(self.lib.rlsb_ac_update(C.byref(ccfg), self.packed.data_ptr(), n, rollout["determ_packed"].data_ptr(),
                                       rollout["stoch_packed"].data_ptr(), vs.data_ptr(), w.data_ptr(),
                                       values.data_ptr(), actions.data_ptr(),
-                                      _ptr(None if g_actions is None else _f32c(g_actions)), seed, C.byref(ga), C.byref(gc),
+                                      _ptr(None if g_actions is None else _f32c(g_actions)), seed, _ptr(seed_device),
+                                      C.byref(ga), C.byref(gc),
                                       self.scalars.data_ptr(), self._ws.data_ptr(), _stream()), "rlsb_ac_update")
         return self.scalars
 
