@@ -15,6 +15,11 @@ Workloads (config.workload):
            the configuration the metric ("at 1/2/4/8 B200") is quoted on.
   config1  the reference shape N = 16x50 = 800 (launch/latency bound; SURVEY hard part 8)
   dino     config-2 dims (D=200, continuous A=12, rho = 0: dynamics back-propagation through K1 backward), N = 800
+  crafter  configs[4]: the FULL DreamerV2.train() on a Crafter-shaped batch (16 x 50 frames of 64x64x3 uint8 per GPU):
+           world-model observe + losses + AdamW (torch / cuDNN, out of kernel scope) followed by the hot path
+  slotted  configs[2]: the full train() of config_slotted (slot-attention encoder, slotted RSSM, DINO-feature targets
+           supplied as synthetic d_features); imagination of this config runs K1 with slots = 4 under no_grad callers,
+           its (continuous-actor) training differentiates through the torch replay
 One JSON line is printed by rank 0.
 """
 from __future__ import annotations
@@ -41,6 +46,9 @@ DIMS = {
     "sweep": dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, eta=3e-3, lr=1e-4, fl="c1"),
     "config1": dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, eta=3e-3, lr=1e-4, fl="c1"),
     "dino": dict(D=200, A=12, discrete=False, layer_norm=False, predict_discount=False, eta=1e-5, lr=8e-5, fl="c2"),
+    "crafter": dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, eta=3e-3, lr=1e-4, fl="c1"),
+    "slotted": dict(D=200, A=1, discrete=False, layer_norm=True, predict_discount=False, eta=1e-4, lr=8e-5, fl="c2",
+                    slots=4),
 }
 
 
@@ -166,12 +174,20 @@ def build_agent(dims, H, device, metrics_samples):
     ln = dims["layer_norm"]
     torch.manual_seed(0)
     opt = partial(Optimizer, lr=dims["lr"], eps=1e-5, weight_decay=1e-6, clip=100)
+    if dims.get("slots"):
+        from rl_sandbox_b200.agents.dreamer.world_model_slots_attention import WorldModel as SlotWM
+        wm = partial(SlotWM, batch_cluster_size=50, latent_dim=32, latent_classes=32, rssm_dim=dims["D"],
+                     slots_num=dims["slots"], slots_iter_num=2, kl_loss_scale=1000, kl_loss_balancing=0.8,
+                     kl_free_nats=0.0005, discrete_rssm=False, decode_vit=True, vit_l2_ratio=0.75, use_prev_slots=False,
+                     encode_vit=False, predict_discount=False, layer_norm=ln, discount_loss_scale=1.0, vit_img_size=224)
+    else:
+        wm = partial(WorldModel, batch_cluster_size=50, latent_dim=32, latent_classes=32, rssm_dim=dims["D"],
+                     discount_loss_scale=1.0, kl_loss_scale=2, kl_loss_balancing=0.8, kl_free_nats=1.0,
+                     discrete_rssm=False, predict_discount=dims["predict_discount"], layer_norm=ln,
+                     encode_vit=False, decode_vit=False, vit_l2_ratio=0.5, vit_img_size=224)
     agent = DreamerV2(
         obs_space_num=[64, 64, 3], clip_rewards="tanh", actions_num=dims["A"],
-        world_model=partial(WorldModel, batch_cluster_size=50, latent_dim=32, latent_classes=32, rssm_dim=dims["D"],
-                            discount_loss_scale=1.0, kl_loss_scale=2, kl_loss_balancing=0.8, kl_free_nats=1.0,
-                            discrete_rssm=False, predict_discount=dims["predict_discount"], layer_norm=ln,
-                            encode_vit=False, decode_vit=False, vit_l2_ratio=0.5, vit_img_size=224),
+        world_model=wm,
         actor=partial(ImaginativeActor, layer_norm=ln, reinforce_fraction=None, entropy_scale=dims["eta"]),
         critic=partial(ImaginativeCritic, discount_factor=0.999, update_interval=100, soft_update_fraction=1,
                        value_target_lambda=0.95, layer_norm=ln),
@@ -182,11 +198,98 @@ def build_agent(dims, H, device, metrics_samples):
     return agent
 
 
+def full_train_main(args, dims):
+    """configs[4] / configs[2]: DreamerV2.train(RolloutChunks) end to end, host uint8 frames in, loss dict out."""
+    import torch.distributed as dist
+    from rl_sandbox_b200 import _lib
+    from rl_sandbox_b200.utils.replay_buffer import RolloutChunks
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    torch.backends.cuda.matmul.allow_tf32 = True   # reference train.py:40
+    lib = _lib.load()
+    H, B, T = args.horizon, 16, 50
+    N = B * T
+    agent = build_agent(dims, H, device, args.metrics_samples)
+    g = torch.Generator().manual_seed(1 + rank)
+    obs_host = torch.randint(0, 255, (N, 64, 64, 3), dtype=torch.uint8, generator=g).pin_memory()
+    A = dims["A"]
+    act_host = (torch.randint(0, A, (N, 1), generator=g) if dims["discrete"] else torch.randn(N, A, generator=g)).pin_memory()
+    rew_host = torch.randn(N, generator=g).pin_memory()
+    first = torch.zeros(N)
+    first[::T] = 1
+    first_host = first.pin_memory()
+    dfeat_host = torch.randn(N, 384, 196, generator=g).pin_memory() if dims.get("slots") else None
+
+    def step():
+        obs = agent.preprocess_obs(obs_host.to(device, non_blocking=True))
+        add = {"d_features": dfeat_host.to(device, non_blocking=True)} if dfeat_host is not None else {}
+        chunks = RolloutChunks(obs=obs, actions=act_host.to(device, non_blocking=True),
+                               rewards=torch.tanh(rew_host.to(device, non_blocking=True)),
+                               is_finished=torch.zeros(N, device=device), is_first=first_host.to(device, non_blocking=True),
+                               additional_data=add)
+        return agent.train(chunks)   # ends with the device->host read of every loss (dreamer_v2.py:216-217)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    lib.rlsb_launch_count(1)
+    flush = torch.empty(256 << 20, device=device, dtype=torch.uint8)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        barrier()
+        for e0, e1 in evs:
+            flush.zero_()          # > 126 MB L2
+            e0.record()
+            out = step()
+            e1.record()
+        barrier()
+    launches = lib.rlsb_launch_count(0)
+    ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    value = world * N * H / (ms_per_step * 1e-3)
+    if rank == 0:
+        h2d = obs_host.numel() + act_host.numel() * act_host.element_size() + 2 * N * 4 + (dfeat_host.numel() * 4 if dfeat_host is not None else 0)
+        line = {
+            "metric": "imagined_rssm_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: full DreamerV2.train() on {B} x {T} frames of 64x64x3 uint8 per GPU, H={H}, "
+                                   f"D={dims['D']}, A={A} {'discrete' if dims['discrete'] else 'continuous'}"
+                                   + (f", {dims['slots']} slots, slot attention 2 iterations, DINO-feature targets" if dims.get("slots") else ""),
+                       "step": "world-model observe + losses + AdamW (torch/cuDNN) -> imagination + lambda-return + actor-critic update",
+                       "l2": "256 MB flush buffer written between timed steps (per-step events)",
+                       "metrics_samples": args.metrics_samples},
+            "clocks": clk.summary(),
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * len(out),
+                    "ms_per_step": ms_per_step, "note": "the timed call takes pinned host buffers and returns host numpy losses"},
+            "gpu_launches": int(launches),
+            "losses": {k: float(out[k].reshape(-1)[0]) for k in ("loss_wm", "loss_actor", "loss_critic") if k in out},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     dims = DIMS[args.workload]
     if args.impl == "reference":
         return reference_arm(args, dims)
+    if args.workload in ("crafter", "slotted"):
+        return full_train_main(args, dims)
 
     import torch.distributed as dist
     from rl_sandbox_b200 import _lib, ops
@@ -238,30 +341,38 @@ def main():
     barrier()
     lib.rlsb_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # inputs + per-step outputs exceed the 126 MB L2 from N = 8192 start states up; below that an explicit flush
+    # buffer is written between timed steps (per-step events, so the flush itself is not timed)
+    flush = torch.empty(256 << 20, device=device, dtype=torch.uint8) if N < 8192 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
         barrier()
-        ev0.record()
-        for i in range(args.steps):
+        for i, (e0, e1) in enumerate(evs):
+            if flush is not None:
+                flush.zero_()
+            e0.record()
             out = step(state, args.warmup + i)
-        ev1.record()
+            e1.record()
         barrier()
     launches = lib.rlsb_launch_count(0)
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+    ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
     value = world * N * H / (ms_per_step * 1e-3)
 
-    # ---- imagination-only timing (K1 alone) -----------------------------------------------------
+    # ---- imagination-only timing (K1 alone): median of per-call CUDA-event times after 3 warm-up calls -------------
     with torch.no_grad():
-        agent.imagine_trajectory(state, noise={"seed": 1})
+        for i in range(3):
+            agent.imagine_trajectory(state, noise={"seed": 1 + i})
         torch.cuda.synchronize()
-        ev0.record()
-        for i in range(max(2, args.steps)):
-            agent.imagine_trajectory(state, noise={"seed": 2 + i})
-        ev1.record()
+        k1_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(3, args.steps))]
+        for i, (e0, e1) in enumerate(k1_evs):
+            e0.record()
+            agent.imagine_trajectory(state, noise={"seed": 10 + i})
+            e1.record()
         torch.cuda.synchronize()
-    k1_ms = ev0.elapsed_time(ev1) / max(2, args.steps)
+    k1_ms = statistics.median(e0.elapsed_time(e1) for e0, e1 in k1_evs)
     pk = peaks()
     k1_tflops = N * H * FLOP_PER_STEP[dims["fl"]] / (k1_ms * 1e-3) / 1e12
 
@@ -332,7 +443,8 @@ def main():
                        "step": "imagine(K1) + lambda-return(K2) + fused critic/actor loss fwd+bwd(K4) + allreduce + AdamW x2"
                                if dims["discrete"] else
                                "imagine(K1, tape) + lambda-return(K2) + K2 bwd + rollout backward(K1 bwd) + K4 + allreduce + AdamW x2",
-                       "l2": "per-step working set (>= 2 GB of rollout outputs) exceeds the 126 MB L2; no explicit flush",
+                       "l2": ("256 MB flush buffer written between timed steps (per-step events)" if flush is not None else
+                              "per-step working set (>= 2 GB of rollout outputs) exceeds the 126 MB L2; no explicit flush"),
                        "metrics_samples": args.metrics_samples, "noise": "Philox4x32-10 on device"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
