@@ -60,9 +60,35 @@ __device__ __forceinline__ float act_apply(float x) {
 
 // pass 2 of the full-row epilogue for one 8-column chunk: bias, [LayerNorm affine], activation,
 // bf16 pack, one 16-byte store into the packed operand image.
+// activation on a pair.  ELU is evaluated as max(a, exp(min(a, 0)) - 1): identical to the reference's
+// "a > 0 ? a : exp(a) - 1" (e^a - 1 >= a everywhere, and the exp argument never overflows), without predicates.
+template <int ACT>
+__device__ __forceinline__ void act_pair(f32x2 a2, float& y0, float& y1) {
+  float a0, a1;
+  unpk2(a2, a0, a1);
+  if (ACT == ACT_ELU) {
+    const f32x2 t = fmul2(pk2(fminf(a0, 0.f), fminf(a1, 0.f)), pk2(1.4426950408889634f, 1.4426950408889634f));
+    float t0, t1;
+    unpk2(t, t0, t1);
+    const f32x2 em = fadd2(pk2(ex2_approx(t0), ex2_approx(t1)), pk2(-1.0f, -1.0f));
+    float e0, e1;
+    unpk2(em, e0, e1);
+    y0 = fmaxf(a0, e0);
+    y1 = fmaxf(a1, e1);
+  } else if (ACT == ACT_RELU) {
+    y0 = fmaxf(a0, 0.f);
+    y1 = fmaxf(a1, 0.f);
+  } else {
+    y0 = a0;
+    y1 = a1;
+  }
+}
+
+// pass 2 of the full-row epilogue for one 8-column chunk: bias, [LayerNorm affine], activation,
+// bf16 pack, one 16-byte store into the packed operand image (packed fp32x2 arithmetic).
 template <int ACT, bool LN, bool SAVE>
 __device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int n_valid, uint32_t s_bias,
-                                             uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
+                                             uint32_t s_gam, uint32_t s_bet, f32x2 rstd2, f32x2 nmr2,
                                              __nv_bfloat16* dst, __nv_bfloat16* dst_pre, bool row_ok) {
   float y[8];
   float pre[8];
@@ -74,25 +100,28 @@ __device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int 
       for (int j = 0; j < 8; ++j) pre[j] = 0.f;
     }
   } else {
-    const float4 b0 = lds128(s_bias + 4u * c), b1 = lds128(s_bias + 4u * c + 16u);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    if (LN) {
-      const float4 g0 = lds128(s_gam + 4u * c), g1 = lds128(s_gam + 4u * c + 16u);
-      const float4 e0 = lds128(s_bet + 4u * c), e1 = lds128(s_bet + 4u * c + 16u);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    f32x2 b[4], v[4];
+    lds_2x2(s_bias + 4u * c, b[0], b[1]);
+    lds_2x2(s_bias + 4u * c + 16u, b[2], b[3]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = fmaf(__uint_as_float(r[j]) + bb[j], rstd, nmr);  // (x - mean) * rstd
-        if (SAVE) pre[j] = xh;
-        y[j] = act_apply<ACT>(fmaf(xh, gg[j], ee[j]));
+    for (int i = 0; i < 4; ++i) v[i] = fadd2(pk2u(r[2 * i], r[2 * i + 1]), b[i]);
+    if (LN) {
+      f32x2 g[4], e[4];
+      lds_2x2(s_gam + 4u * c, g[0], g[1]);
+      lds_2x2(s_gam + 4u * c + 16u, g[2], g[3]);
+      lds_2x2(s_bet + 4u * c, e[0], e[1]);
+      lds_2x2(s_bet + 4u * c + 16u, e[2], e[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = ffma2(v[i], rstd2, nmr2);  // (x - mean) * rstd
+        if (SAVE) unpk2(v[i], pre[2 * i], pre[2 * i + 1]);
+        act_pair<ACT>(ffma2(v[i], g[i], e[i]), y[2 * i], y[2 * i + 1]);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float a = __uint_as_float(r[j]) + bb[j];
-        if (SAVE) pre[j] = a;
-        y[j] = act_apply<ACT>(a);
+      for (int i = 0; i < 4; ++i) {
+        if (SAVE) unpk2(v[i], pre[2 * i], pre[2 * i + 1]);
+        act_pair<ACT>(v[i], y[2 * i], y[2 * i + 1]);
       }
     }
     if (c + 8 > n_valid) {  // partial chunk (N not a multiple of 8)
@@ -115,6 +144,7 @@ template <int ACT, bool LN, bool SAVE>
 __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chunks, int n_valid, int col0, int row,
                                              uint32_t s_bias, uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
                                              __nv_bfloat16* obase, __nv_bfloat16* pbase, bool row_ok) {
+  const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
   for (int i0 = 0; i0 < my_chunks; i0 += 2) {
     uint32_t r0[8], r1[8];
     const int c0 = (cq + 4 * i0) * 8, c1 = c0 + 32;
@@ -125,13 +155,13 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
     {
       const int oc = col0 + c0;
       const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
-      ln_act_chunk<ACT, LN, SAVE>(r0, c0, n_valid, s_bias, s_gam, s_bet, rstd, nmr, obase + off,
+      ln_act_chunk<ACT, LN, SAVE>(r0, c0, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, obase + off,
                                   SAVE ? pbase + off : nullptr, row_ok);
     }
     if (two) {
       const int oc = col0 + c1;
       const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
-      ln_act_chunk<ACT, LN, SAVE>(r1, c1, n_valid, s_bias, s_gam, s_bet, rstd, nmr, obase + off,
+      ln_act_chunk<ACT, LN, SAVE>(r1, c1, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, obase + off,
                                   SAVE ? pbase + off : nullptr, row_ok);
     }
   }
@@ -546,20 +576,23 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
         const bool vec_ok = (!kLnAct) && ((p.ldo & 3) == 0) && ((col0 & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0);
         const bool store = (!kLnAct) && row_ok;
+        f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
         auto pass1_chunk = [&](const uint32_t (&r)[8], int c) {
-          const float4 b0 = lds128(s_bias + 4u * c), b1 = lds128(s_bias + 4u * c + 16u);
-          float v[8];
-          v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
-          v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
-          v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
-          v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
+          f32x2 b[4], v2[4];
+          lds_2x2(s_bias + 4u * c, b[0], b[1]);
+          lds_2x2(s_bias + 4u * c + 16u, b[2], b[3]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v2[i] = fadd2(pk2u(r[2 * i], r[2 * i + 1]), b[i]);
           if (c + 8 <= n_valid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              sum += v[j];
-              sq = fmaf(v[j], v[j], sq);
+            for (int i = 0; i < 4; ++i) {
+              sum2 = fadd2(sum2, v2[i]);
+              sq2 = ffma2(v2[i], v2[i], sq2);
             }
             if (store) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) unpk2(v2[i], v[2 * i], v[2 * i + 1]);
               if (vec_ok) {
                 *reinterpret_cast<float4*>(orow + c) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(orow + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -569,6 +602,9 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
               }
             }
           } else if (c < n_valid) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) unpk2(v2[i], v[2 * i], v[2 * i + 1]);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (c + j < n_valid) {
@@ -588,6 +624,13 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           tmem_ld_wait();
           pass1_chunk(r0, c0);
           if (two) pass1_chunk(r1, c1);
+        }
+        {
+          float s0, s1, q0, q1;
+          unpk2(sum2, s0, s1);
+          unpk2(sq2, q0, q1);
+          sum += s0 + s1;
+          sq += q0 + q1;
         }
         if (EPI == EPI_STATS || has_ln) {
           sts64(s_part + 8u * (cq * kTileM + row), sum, sq);
