@@ -317,6 +317,32 @@ int rlsb_slot_attention_fwd(const rlsb_slot_cfg* cfg, const void* packed, int64_
                             const float* prev_slots, float* out_slots, float* out_attn,
                             void* workspace, void* stream);
 
+/* K3 with autograd: the forward records an activation tape (rlsb_slot_attention_tape_bytes bytes); the backward
+ * returns d loss / d X (B, tokens, dim), d loss / d prev_slots (B, slots, dim) and the gradient of every parameter of
+ * rlsb_slot_params (same field names, nn.Linear / nn.LayerNorm / nn.GRUCell layouts; all required) — the autograd of
+ * SlotAttention.forward (vision/slot_attention.py:52-77) inside the world-model loss.  `packed` is the blob of
+ * rlsb_slot_attention_pack (it also carries the transposed weight images). */
+typedef struct {
+  float* inputs_norm_g; float* inputs_norm_b;
+  float* inputs_proj_w;
+  float* slots_norm_g;  float* slots_norm_b;
+  float* slots_proj_w;
+  float* gru_w_ih; float* gru_w_hh;
+  float* gru_b_ih; float* gru_b_hh;
+  float* slots_norm2_g; float* slots_norm2_b;
+  float* mlp_w1; float* mlp_b1;
+  float* mlp_w2; float* mlp_b2;
+} rlsb_slot_grads;
+
+size_t rlsb_slot_attention_tape_bytes(const rlsb_slot_cfg* cfg, int64_t B);
+size_t rlsb_slot_attention_bwd_workspace_bytes(const rlsb_slot_cfg* cfg, int64_t B);
+int rlsb_slot_attention_fwd_tape(const rlsb_slot_cfg* cfg, const void* packed, int64_t B, const float* X,
+                                 const float* prev_slots, float* out_slots, float* out_attn, void* tape,
+                                 void* workspace, void* stream);
+int rlsb_slot_attention_bwd(const rlsb_slot_cfg* cfg, const void* packed, int64_t B, const float* X, const void* tape,
+                            const float* d_out_slots, const rlsb_slot_grads* grads, float* dX, float* d_prev_slots,
+                            void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

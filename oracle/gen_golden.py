@@ -218,6 +218,11 @@ def slot_inputs(case=SLOT_CASE):
     return X, prev
 
 
+def slot_grad_weights(case=SLOT_CASE):
+    g = torch.Generator().manual_seed(case["input_seed"] + 1)
+    return torch.randn(case["B"], case["slots"], case["dim"], generator=g)
+
+
 def run_slot_attention():
     """SlotAttention.forward of the reference (vision/slot_attention.py:52-77) with explicit prev_slots."""
     rh._import_reference()
@@ -229,9 +234,19 @@ def run_slot_attention():
     X, prev = slot_inputs()
     with torch.no_grad():
         out = mod(X, prev)
-    np.savez_compressed(OUT / "slot_attention.npz", slots=out.numpy(), attn=mod.last_attention.numpy(),
-                        meta=json.dumps(c))
-    print("slot_attention.npz written:", out.shape, mod.last_attention.shape)
+    # gradients of the reference's autograd for the scalar sum(out * G), G seeded (pins rlsb_slot_attention_bwd)
+    Xg, pg = X.clone().requires_grad_(), prev.clone().requires_grad_()
+    G = slot_grad_weights()
+    (mod(Xg, pg) * G).sum().backward()
+    names = [n for n, _ in mod.named_parameters() if not n.startswith("slots_mu") and not n.startswith("slots_logsigma")]
+    params = dict(mod.named_parameters())
+    np.savez_compressed(OUT / "slot_attention.npz", slots=out.numpy(), attn=mod.last_attention.detach().numpy(),
+                        grad_X=Xg.grad.numpy(), grad_prev=pg.grad.numpy(),
+                        grad_norms=np.asarray([params[n].grad.norm().item() for n in names], np.float32),
+                        grad_probes=np.stack([params[n].grad.flatten()[grad_probe_indices(params[n].numel())].numpy()
+                                              for n in names]).astype(np.float32),
+                        meta=json.dumps({**c, "grad_names": names}))
+    print("slot_attention.npz written:", out.shape, mod.last_attention.shape, len(names), "parameter gradients")
 
 
 def main():

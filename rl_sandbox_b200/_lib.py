@@ -81,6 +81,10 @@ class SlotParams(C.Structure):
         "mlp_w1", "mlp_b1", "mlp_w2", "mlp_b2")]
 
 
+class SlotGrads(C.Structure):
+    _fields_ = SlotParams._fields_
+
+
 _lib = None
 
 
@@ -121,6 +125,10 @@ def load() -> C.CDLL:
         "rlsb_slot_attention_workspace_bytes": (sz, [C.POINTER(SlotCfg), i64]),
         "rlsb_slot_attention_pack": (C.c_int, [C.POINTER(SlotCfg), C.POINTER(SlotParams), vp, vp]),
         "rlsb_slot_attention_fwd": (C.c_int, [C.POINTER(SlotCfg), vp, i64, vp, vp, vp, vp, vp, vp]),
+        "rlsb_slot_attention_tape_bytes": (sz, [C.POINTER(SlotCfg), i64]),
+        "rlsb_slot_attention_bwd_workspace_bytes": (sz, [C.POINTER(SlotCfg), i64]),
+        "rlsb_slot_attention_fwd_tape": (C.c_int, [C.POINTER(SlotCfg), vp, i64, vp, vp, vp, vp, vp, vp, vp]),
+        "rlsb_slot_attention_bwd": (C.c_int, [C.POINTER(SlotCfg), vp, i64, vp, vp, vp, C.POINTER(SlotGrads), vp, vp, vp, vp]),
     })
     sig.update({
         "rlsb_packed_rows": (sz, [i64]),

@@ -271,7 +271,7 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[8], const uint4& p
 // the whole EPI_BWD epilogue of one tile (see GemmParams); returns nothing, writes out_bf16 / smem column sums
 template <int ACT, bool LN>
 __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, int cq, int my_chunks, int n_valid,
-                                         int row, int lane, bool row_ok, uint32_t s_gam, uint32_t s_bet,
+                                         int col0, int row, int lane, bool row_ok, uint32_t s_gam, uint32_t s_bet,
                                          uint32_t s_part, uint32_t s_acc, float rstd,
                                          const __nv_bfloat16* pbase, __nv_bfloat16* obase) {
   float s1 = 0.f, s2 = 0.f;
@@ -281,7 +281,8 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     if (c >= n_valid) break;   // warp-uniform
     uint32_t r[8];
     tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);
-    const size_t off = static_cast<size_t>(c >> 6) * (kTileM * kTileK) + ((((c & 63) >> 3) ^ (row & 7)) << 3);
+    const int oc = col0 + c;   // column inside the whole row (col0 != 0 only without LayerNorm)
+    const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
     const uint4 pb = *reinterpret_cast<const uint4*>(pbase + off);
     tmem_ld_wait();
     float da[8], dxh[8], pre[8];
@@ -322,7 +323,8 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
       if (c >= n_valid) break;
       uint32_t r[8];
       tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);
-      const size_t off = static_cast<size_t>(c >> 6) * (kTileM * kTileK) + ((((c & 63) >> 3) ^ (row & 7)) << 3);
+      const int oc = col0 + c;
+      const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
       const uint4 pb = *reinterpret_cast<const uint4*>(pbase + off);
       tmem_ld_wait();
       float da[8], dxh[8], pre[8], o[8];
@@ -543,21 +545,25 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
                              static_cast<size_t>(row) * kTileK;
           const float rs = (has_ln && row_ok) ? __ldg(p.bwd_rstd + static_cast<size_t>(g) * m_pad + m) : 0.f;
 #define RLSB_B(ACT, LN) \
-  bwd_tile<ACT, LN>(p, tmem_d, cq, my_chunks, n_valid, row, lane, row_ok, s_gam, s_bet, s_part, s_acc, rs, \
+  bwd_tile<ACT, LN>(p, tmem_d, cq, my_chunks, n_valid, col0, row, lane, row_ok, s_gam, s_bet, s_part, s_acc, rs, \
                     p.bwd_pre + img, p.out_bf16 + img)
           if (has_ln) {
             if (p.act == ACT_ELU) RLSB_B(ACT_ELU, true);
             else RLSB_B(ACT_NONE, true);
           } else {
             if (p.act == ACT_ELU) RLSB_B(ACT_ELU, false);
+            else if (p.act == ACT_RELU) RLSB_B(ACT_RELU, false);
             else RLSB_B(ACT_NONE, false);
           }
 #undef RLSB_B
-          // zero the padding columns [n_valid rounded down to a chunk .. out_kpad) of the packed image
-          for (int ch = (n_valid >> 3) + cq; ch < (p.out_kpad >> 3); ch += 4) {
-            if (ch * 8 < n_valid) continue;   // partial chunk was written above
-            __nv_bfloat16* trow = p.out_bf16 + img + static_cast<size_t>(ch >> 3) * (kTileM * kTileK);
-            *reinterpret_cast<uint4*>(trow + (((ch & 7) ^ (row & 7)) << 3)) = make_uint4(0u, 0u, 0u, 0u);
+          // zero the padding columns [N rounded down to a chunk .. out_kpad) of the packed image (last block)
+          if (nb == p.NB - 1) {
+            const int n_end = col0 + n_valid;
+            for (int ch = (n_end >> 3) + cq; ch < (p.out_kpad >> 3); ch += 4) {
+              if (ch * 8 < n_end) continue;   // partial chunk was written above
+              __nv_bfloat16* trow = p.out_bf16 + img + static_cast<size_t>(ch >> 3) * (kTileM * kTileK);
+              *reinterpret_cast<uint4*>(trow + (((ch & 7) ^ (row & 7)) << 3)) = make_uint4(0u, 0u, 0u, 0u);
+            }
           }
         }
         tc_fence_before();
@@ -748,8 +754,8 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB != 1 && p.ln_gamma != nullptr) return -3;  // LayerNorm needs the whole row
   if (p.M <= 0 || p.m_tiles != (p.M + kTileM - 1) / kTileM) return -4;
   if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE || epilogue == EPI_BWD) && ((p.out_kpad % 64) != 0 || p.out_kpad < p.N)) return -5;
-  if (epilogue == EPI_BWD && (p.NB != 1 || !p.bwd_pre || !p.out_bf16 || !p.group_major ||
-                              (p.ln_gamma && !p.bwd_rstd) || (p.act != ACT_ELU && p.act != ACT_NONE)))
+  if (epilogue == EPI_BWD && ((p.NB != 1 && p.ln_gamma) || !p.bwd_pre || !p.out_bf16 || !p.group_major ||
+                              (p.ln_gamma && !p.bwd_rstd) || (p.ln_gamma && p.act == ACT_RELU)))
     return -8;
   if (epilogue == EPI_LN_ACT_SAVE && (p.act != ACT_ELU || p.NB != 1)) return -9;
   {

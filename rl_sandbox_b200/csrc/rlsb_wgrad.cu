@@ -201,7 +201,7 @@ __global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
     const size_t stride = static_cast<size_t>(p.G) * p.rows_pad * p.ld;
     const float* src = p.partial + i;
     for (int s = 0; s < p.splits; ++s) acc += __ldg(src + s * stride);
-    *dst = acc;
+    *dst = p.accumulate ? *dst + acc : acc;
   }
 }
 

@@ -53,6 +53,7 @@ struct WgradReduceParams {
   int n_seg;
   PackSeg seg[3];                // dst_k0 = first padded column, src_c0 = first weight column, len
   int ones_col;                  // padded column that holds the bias gradient, or -1
+  int accumulate;                // 1: dst += sum (contributions of several launches, e.g. slot-attention iterations)
 };
 int launch_wgrad_reduce(const WgradReduceParams& p, cudaStream_t stream);
 

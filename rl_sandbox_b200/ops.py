@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (AcCfg, ImagineCfg, ImagineOut, ImagineParams, MlpGrads, MlpParams, Noise, SlotCfg,
-                   SlotParams, check)
+                   SlotGrads, SlotParams, check)
 
 
 def _stream() -> int:
@@ -529,3 +529,67 @@ class SlotAttentionEngine:
                                                prev_slots.data_ptr(), out.data_ptr(), _ptr(attn), self._ws.data_ptr(),
                                                _stream()), "rlsb_slot_attention_fwd")
         return out, attn
+
+
+    # ---- training: forward with an activation tape + backward (rlsb_slot_attention_fwd_tape / _bwd) ----
+    def forward_tape(self, X: torch.Tensor, prev_slots: torch.Tensor):
+        X, prev_slots = _f32c(X), _f32c(prev_slots)
+        B = X.shape[0]
+        if X.shape[1:] != (self.tokens, self.dim) or prev_slots.shape != (B, self.slots, self.dim):
+            raise _lib.RlsbError(f"slot attention: X {tuple(X.shape)} prev_slots {tuple(prev_slots.shape)}")
+        if self._ws is None or self._ws_b < B:
+            self._ws = torch.zeros(self.lib.rlsb_slot_attention_workspace_bytes(C.byref(self.cfg), B),
+                                   device=self.device, dtype=torch.uint8)
+            self._ws_b = B
+        # zero-initialised: padding rows of the operand images on the tape enter weight-gradient contractions
+        tape = torch.zeros(self.lib.rlsb_slot_attention_tape_bytes(C.byref(self.cfg), B), device=self.device,
+                           dtype=torch.uint8)
+        out = torch.empty_like(prev_slots)
+        attn = torch.empty((B, self.slots, self.tokens), device=X.device, dtype=torch.float32)
+        check(self.lib.rlsb_slot_attention_fwd_tape(C.byref(self.cfg), self.packed.data_ptr(), B, X.data_ptr(),
+                                                    prev_slots.data_ptr(), out.data_ptr(), attn.data_ptr(),
+                                                    tape.data_ptr(), self._ws.data_ptr(), _stream()),
+              "rlsb_slot_attention_fwd_tape")
+        return out, attn, tape
+
+    def backward(self, X: torch.Tensor, tape: torch.Tensor, d_out: torch.Tensor):
+        """-> (dX, d_prev_slots, {state-dict key: gradient})"""
+        X, d_out = _f32c(X), _f32c(d_out)
+        B = X.shape[0]
+        nbytes = self.lib.rlsb_slot_attention_bwd_workspace_bytes(C.byref(self.cfg), B)
+        if getattr(self, "_bws", None) is None or self._bws.numel() < nbytes:
+            self._bws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        d, K = self.dim, self.slots
+        shapes = {"inputs_norm_g": (d,), "inputs_norm_b": (d,), "inputs_proj_w": (2 * d, d), "slots_norm_g": (d,),
+                  "slots_norm_b": (d,), "slots_proj_w": (d, d), "gru_w_ih": (3 * d, d), "gru_w_hh": (3 * d, d),
+                  "gru_b_ih": (3 * d,), "gru_b_hh": (3 * d,), "slots_norm2_g": (d,), "slots_norm2_b": (d,),
+                  "mlp_w1": (4 * d, d), "mlp_b1": (4 * d,), "mlp_w2": (d, 4 * d), "mlp_b2": (d,)}
+        g, grads = SlotGrads(), {}
+        for field, shp in shapes.items():
+            t = torch.zeros(shp, device=self.device, dtype=torch.float32)
+            grads[self.KEYS[field]] = t
+            setattr(g, field, t.data_ptr())
+        dX = torch.empty_like(X)
+        dprev = torch.empty((B, K, d), device=self.device, dtype=torch.float32)
+        check(self.lib.rlsb_slot_attention_bwd(C.byref(self.cfg), self.packed.data_ptr(), B, X.data_ptr(), tape.data_ptr(),
+                                               d_out.data_ptr(), C.byref(g), dX.data_ptr(), dprev.data_ptr(),
+                                               self._bws.data_ptr(), _stream()), "rlsb_slot_attention_bwd")
+        return dX, dprev, grads
+
+
+class SlotAttentionFn(torch.autograd.Function):
+    """SlotAttention.forward (vision/slot_attention.py:52-77) with both directions in librlsb (K3)."""
+
+    @staticmethod
+    def forward(ctx, engine, names, X, prev_slots, *params):
+        out, attn, tape = engine.forward_tape(X.detach(), prev_slots.detach())
+        ctx.engine, ctx.names = engine, names
+        ctx.save_for_backward(X.detach(), tape)
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, d_out, _d_attn):
+        X, tape = ctx.saved_tensors
+        dX, dprev, grads = ctx.engine.backward(X, tape, d_out.contiguous())
+        return (None, None, dX, dprev) + tuple(grads[n] for n in ctx.names)

@@ -45,7 +45,7 @@ class SlotAttention(nn.Module):
     def mark_weights_changed(self):
         self._engine_key = None
 
-    def _kernel_forward(self, X, slots):
+    def _kernel_forward_prepare(self, X):
         from rl_sandbox_b200 import ops
         key = (X.shape[1], tuple(p._version for p in self.parameters()))
         if self._engine is None or self._engine.tokens != X.shape[1]:
@@ -54,6 +54,9 @@ class SlotAttention(nn.Module):
         if self._engine_key != key:
             self._engine.pack(self.state_dict())
             self._engine_key = key
+
+    def _kernel_forward(self, X, slots):
+        self._kernel_forward_prepare(X)
         return self._engine.forward(X.float(), slots.float())
 
     def forward(self, X: torch.Tensor, prev_slots: t.Optional[torch.Tensor]) -> torch.Tensor:
@@ -72,10 +75,24 @@ class SlotAttention(nn.Module):
         if not X.is_cuda and not needs_grad:
             raise RuntimeError("SlotAttention.forward runs on the B200 kernels: tensors must be on CUDA "
                                "(rl_sandbox_b200 has no CPU fallback)")
+        if X.is_cuda and self.kernel_backward:
+            return self._kernel_autograd_forward(X, slots)
         return self._autograd_forward(X, slots)
 
+    kernel_backward = True   # False: differentiate through the torch-op restatement below
+
+    def _kernel_autograd_forward(self, X, slots):
+        """Training: K3 forward with an activation tape, K3 backward (rlsb_slot_attention_bwd) under torch autograd."""
+        from rl_sandbox_b200 import ops
+        self._kernel_forward_prepare(X)
+        names = list(ops.SlotAttentionEngine.KEYS.values())
+        sd = dict(self.named_parameters())
+        out, attn = ops.SlotAttentionFn.apply(self._engine, names, X.float(), slots.float(), *[sd[n] for n in names])
+        self.last_attention = attn
+        return out
+
     def _autograd_forward(self, X, slots):
-        """Differentiable evaluation (training only; K3 backward is not built yet)."""
+        """Differentiable evaluation with torch ops (the reference's op sequence; CPU checks and kernel_backward=False)."""
         k, v = self.inputs_proj(self.inputs_norm(X)).chunk(2, dim=-1)
         self.last_attention = None
         for _ in range(self.n_iter):
