@@ -317,6 +317,61 @@ int rlsb_slot_attention_fwd(const rlsb_slot_cfg* cfg, const void* packed, int64_
                             const float* prev_slots, float* out_slots, float* out_attn,
                             void* workspace, void* stream);
 
+/* ---- K5: world-model observe scan ------------------------------------------------
+ * replaces the T sequential RSSM.forward calls of WorldModel.calculate_loss
+ * (agents/dreamer/world_model.py:187-202 -> agents/dreamer/rssm.py:176-209: predict_next + update_current,
+ * posterior sampled straight-through) and, with rlsb_observe_bwd, their autograd (BPTT over the T steps with
+ * parameter gradients).  Time-major tensors: embed (T, B, E) encoder output, actions (T, B, A) already
+ * multiplied by (1 - is_first) (world_model.py:191); the initial state is zero (get_initial_state).
+ * The tape (rlsb_observe_tape_bytes) must be ZERO-INITIALISED by the caller. */
+typedef struct {
+  int32_t D, groups, classes, A;
+  int32_t E;            /* encoder embedding width (4 * 384 for the conv encoder, rssm.py:156) */
+  int32_t layer_norm;
+  int32_t T;            /* steps (batch_cluster_size) */
+} rlsb_observe_cfg;
+
+typedef struct {
+  const float* img_in_w;  const float* img_in_b;  const float* img_in_ln_g; const float* img_in_ln_b;  /* pre_determ_recurrent */
+  const float* gru_w;     const float* gru_b;     const float* gru_ln_g;    const float* gru_ln_b;     /* determ_recurrent    */
+  const float* prior1_w;  const float* prior1_b;  const float* prior1_ln_g; const float* prior1_ln_b;  /* ensemble_prior_estimator.0/.1 */
+  const float* prior2_w;  const float* prior2_b;                                                         /* ensemble_prior_estimator.3    */
+  const float* post1_w;   const float* post1_b;   const float* post1_ln_g;  const float* post1_ln_b;   /* stoch_net.0/.1 (D + E inputs) */
+  const float* post2_w;   const float* post2_b;                                                          /* stoch_net.3                   */
+} rlsb_observe_params;
+
+typedef struct {
+  float* img_in_w;  float* img_in_b;  float* img_in_ln_g; float* img_in_ln_b;
+  float* gru_w;     float* gru_b;     float* gru_ln_g;    float* gru_ln_b;
+  float* prior1_w;  float* prior1_b;  float* prior1_ln_g; float* prior1_ln_b;
+  float* prior2_w;  float* prior2_b;
+  float* post1_w;   float* post1_b;   float* post1_ln_g;  float* post1_ln_b;
+  float* post2_w;   float* post2_b;
+} rlsb_observe_grads;
+
+typedef struct {
+  float* prior_logits;  /* (T, B, groups*classes) */
+  float* post_logits;   /* (T, B, groups*classes) */
+  float* determ;        /* (T, B, D) */
+  uint8_t* stoch_idx;   /* (T, B, groups) posterior sample */
+  float* stoch;         /* (T, B, groups*classes) one-hot, or NULL */
+} rlsb_observe_out;
+
+size_t rlsb_observe_packed_bytes(const rlsb_observe_cfg* cfg);
+size_t rlsb_observe_tape_bytes(const rlsb_observe_cfg* cfg, int64_t B);
+size_t rlsb_observe_bwd_workspace_bytes(const rlsb_observe_cfg* cfg, int64_t B);
+int rlsb_observe_pack(const rlsb_observe_cfg* cfg, const rlsb_observe_params* params, void* packed, void* stream);
+/* noise: latent_uniforms (T, B, groups*classes) or the Philox key (stream 0, step t, row = row_offset + b) */
+int rlsb_observe_fwd(const rlsb_observe_cfg* cfg, const void* packed, int64_t B, const float* embed, const float* actions,
+                     const rlsb_noise* noise, const rlsb_observe_out* out, void* tape, void* stream);
+/* g_* : d loss / d (the four forward outputs), each may be NULL; the straight-through gradient of `stoch` is routed
+ * into the posterior logits inside.  grads: every parameter gradient (LayerNorm entries may be NULL without
+ * layer_norm); g_embed: (T, B, E). */
+int rlsb_observe_bwd(const rlsb_observe_cfg* cfg, const void* packed, int64_t B, const void* tape,
+                     const rlsb_observe_out* fwd, const float* g_prior_logits, const float* g_post_logits,
+                     const float* g_determ, const float* g_stoch, const rlsb_observe_grads* grads, float* g_embed,
+                     void* workspace, void* stream);
+
 /* K3 with autograd: the forward records an activation tape (rlsb_slot_attention_tape_bytes bytes); the backward
  * returns d loss / d X (B, tokens, dim), d loss / d prev_slots (B, slots, dim) and the gradient of every parameter of
  * rlsb_slot_params (same field names, nn.Linear / nn.LayerNorm / nn.GRUCell layouts; all required) — the autograd of

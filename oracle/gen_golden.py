@@ -208,6 +208,62 @@ def run_slotted():
     print("imagine_slotted.npz written:", states.determ.shape, states.stoch_logits.shape, actions.shape)
 
 
+OBSERVE_CASE = dict(D=200, A=5, layer_norm=True, B=3, T=4, E=1536, param_seed=71, input_seed=72)
+
+
+def observe_inputs(case=OBSERVE_CASE):
+    g = torch.Generator().manual_seed(case["input_seed"])
+    T, B = case["T"], case["B"]
+    embed = torch.randn(T, B, case["E"], generator=g)
+    actions = torch.randn(T, B, case["A"], generator=g)
+    uniforms = torch.rand(T, B, 1024, generator=g)
+    weights = {k: torch.randn(T, B, n, generator=g) / n ** 0.5
+               for k, n in (("prior_logits", 1024), ("post_logits", 1024), ("determ", case["D"]), ("stoch", 1024))}
+    return embed, actions, uniforms, weights
+
+
+def run_observe():
+    """The observe loop of WorldModel.calculate_loss (world_model.py:187-202) run with the reference's RSSM.forward and
+    State objects; outputs + the reference autograd's gradients of a seeded probe loss (pins rlsb_observe_fwd / _bwd)."""
+    c = OBSERVE_CASE
+    wm_sd, actor_sd, critic_sd = orc.make_params(c["param_seed"], D=c["D"], A=c["A"], discrete=False,
+                                                 layer_norm=c["layer_norm"], predict_discount=False)
+    agent = rh.build_agent(D=c["D"], A=c["A"], discrete=False, layer_norm=c["layer_norm"], predict_discount=False, H=3)
+    rh.load_params(agent, wm_sd, actor_sd, critic_sd)
+    wm = getattr(agent.world_model, "_orig_mod", agent.world_model)
+    embed, actions, uniforms, weights = observe_inputs()
+    embed = embed.clone().requires_grad_()
+    from rl_sandbox.agents.dreamer.rssm import State
+    q = rh.NoiseQueue(list(uniforms), [])
+    for p_ in wm.parameters():
+        p_.grad = None
+    with rh.injected_noise(q):
+        prev = wm.get_initial_state(c["B"])
+        priors, posts = [], []
+        for t in range(c["T"]):
+            prior, post, _ = wm.recurrent_model.forward(prev, embed[t].unsqueeze(0), actions[t].unsqueeze(0))
+            prev = post
+            priors.append(prior)
+            posts.append(post)
+        posterior, prior = State.stack(posts), State.stack(priors)
+        o = dict(prior_logits=prior.stoch_logits.reshape(c["T"], c["B"], 1024),
+                 post_logits=posterior.stoch_logits.reshape(c["T"], c["B"], 1024), determ=posterior.determ,
+                 stoch=posterior.stoch)
+        orc.observe_probe_loss(o, weights).backward()
+    assert not q.latent, "noise not fully consumed"
+    names = [n for n in orc.OBSERVE_PARAM_KEYS if "recurrent_model." + n in dict(wm.named_parameters())]
+    params = dict(wm.named_parameters())
+    np.savez_compressed(
+        OUT / "observe.npz", prior_logits=o["prior_logits"].detach().numpy(), post_logits=o["post_logits"].detach().numpy(),
+        determ=o["determ"].detach().numpy(), stoch_idx=o["stoch"].detach().reshape(c["T"], c["B"], 32, 32).argmax(-1).numpy().astype(np.uint8),
+        grad_embed=embed.grad.numpy(),
+        grad_norms=np.asarray([params["recurrent_model." + n].grad.norm().item() for n in names], np.float32),
+        grad_probes=np.stack([params["recurrent_model." + n].grad.flatten()[grad_probe_indices(params["recurrent_model." + n].numel())].numpy()
+                              for n in names]).astype(np.float32),
+        meta=json.dumps({**c, "grad_names": names}))
+    print("observe.npz written:", o["determ"].shape, len(names), "parameter gradients")
+
+
 SLOT_CASE = dict(B=3, tokens=196, dim=384, slots=4, iters=2, param_seed=41, input_seed=42)
 
 
@@ -255,6 +311,7 @@ def main():
     known_answers()
     run_slot_attention()
     run_slotted()
+    run_observe()
     for name, case in CASES.items():
         run_case(name, case)
 

@@ -260,6 +260,44 @@ def ac_losses(traj, actor_sd, critic_sd, *, lam, discrete, rho, eta, bf16=False)
 
 
 # ------------------------------------------------------------------------------------------------
+# world-model observe loop (agents/dreamer/world_model.py:187-202 -> rssm.py:176-209), differentiable
+# ------------------------------------------------------------------------------------------------
+OBSERVE_PARAM_KEYS = [
+    "pre_determ_recurrent.0.weight", "pre_determ_recurrent.0.bias", "pre_determ_recurrent.1.weight", "pre_determ_recurrent.1.bias",
+    "determ_recurrent._layer.weight", "determ_recurrent._layer.bias", "determ_recurrent._norm.weight", "determ_recurrent._norm.bias",
+    "ensemble_prior_estimator.0.weight", "ensemble_prior_estimator.0.bias", "ensemble_prior_estimator.1.weight",
+    "ensemble_prior_estimator.1.bias", "ensemble_prior_estimator.3.weight", "ensemble_prior_estimator.3.bias",
+    "stoch_net.0.weight", "stoch_net.0.bias", "stoch_net.1.weight", "stoch_net.1.bias", "stoch_net.3.weight", "stoch_net.3.bias"]
+
+
+def observe_scan(wm_sd, embed, actions, uniforms, *, bf16=False, rp="recurrent_model."):
+    """embed (T,B,E), actions (T,B,A) (already masked by is_first), uniforms (T,B,1024) for the posterior draws.
+    Returns prior_logits, post_logits (T,B,1024), determ (T,B,D), stoch (T,B,1024) straight-through, stoch_idx."""
+    T, B = embed.shape[:2]
+    D = wm_sd[rp + "ensemble_prior_estimator.0.weight"].shape[0]
+    h, z = torch.zeros(B, D), torch.zeros(B, 1024)
+    outs = {k: [] for k in ("prior_logits", "post_logits", "determ", "stoch", "stoch_idx")}
+    for t in range(T):
+        h, prior_logits = rssm_predict_next(h, z, actions[t], wm_sd, rp, bf16)
+        y = linear(torch.cat([h, embed[t]], -1), wm_sd[rp + "stoch_net.0.weight"], wm_sd[rp + "stoch_net.0.bias"], bf16)
+        if rp + "stoch_net.1.weight" in wm_sd:
+            y = layer_norm(y, wm_sd[rp + "stoch_net.1.weight"], wm_sd[rp + "stoch_net.1.bias"])
+        post_logits = linear(elu(y), wm_sd[rp + "stoch_net.3.weight"], wm_sd[rp + "stoch_net.3.bias"], bf16)
+        lg = post_logits.view(B, 32, 32)
+        idx = sample_categorical(lg.detach(), uniforms[t].view(B, 32, 32))
+        probs = torch.softmax(lg, -1)
+        z = (torch.nn.functional.one_hot(idx, 32).float() + probs - probs.detach()).view(B, 1024)
+        for k, v in (("prior_logits", prior_logits), ("post_logits", post_logits), ("determ", h), ("stoch", z), ("stoch_idx", idx)):
+            outs[k].append(v)
+    return {k: torch.stack(v) for k, v in outs.items()}
+
+
+def observe_probe_loss(o, weights):
+    """a scalar that touches every output of the observe scan (used to compare gradients): weights = dict of tensors"""
+    return sum((o[k] * weights[k]).sum() for k in ("prior_logits", "post_logits", "determ", "stoch"))
+
+
+# ------------------------------------------------------------------------------------------------
 # slotted RSSM (agents/dreamer/rssm_slots_attention.py:166-209, world_model_slots_attention.py:199-207)
 # ------------------------------------------------------------------------------------------------
 def position_encoding(seq_len, d, n=10000):
@@ -345,7 +383,7 @@ def make_params_slotted(seed, *, D, A, K, discrete, layer_norm, predict_discount
     wm, actor, critic = make_params(seed, D=D, A=A, discrete=discrete, layer_norm=layer_norm,
                                     predict_discount=predict_discount, hidden=hidden, S=S)
     rp = "recurrent_model."
-    wm = {k: v for k, v in wm.items() if k.startswith(rp)}
+    wm = {k: v for k, v in wm.items() if k.startswith(rp) and "stoch_net" not in k}   # slotted posterior net: other width
     wm[rp + "hidden_attention_proj.weight"] = _lin(gen, 3 * D, D)[0]
     wm[rp + "fc.weight"], wm[rp + "fc.bias"] = _lin(gen, D, D)
     for name in ("pre_norm", "fc_norm"):
@@ -447,6 +485,13 @@ def make_params(seed, *, D, A, discrete, layer_norm, predict_discount, hidden=40
         for name in ("pre_determ_recurrent.1", "ensemble_prior_estimator.1"):
             wm[rp + name + ".weight"] = 1 + 0.1 * torch.randn(D, generator=gen)
             wm[rp + name + ".bias"] = 0.1 * torch.randn(D, generator=gen)
+    # posterior net (rssm.py:156-165), drawn from its own generator so that older fixtures keep their parameters
+    gen_post = torch.Generator().manual_seed(seed + 7919)
+    wm[rp + "stoch_net.0.weight"], wm[rp + "stoch_net.0.bias"] = _lin(gen_post, D, D + 1536)
+    wm[rp + "stoch_net.3.weight"], wm[rp + "stoch_net.3.bias"] = _lin(gen_post, S, D)
+    if layer_norm:
+        wm[rp + "stoch_net.1.weight"] = 1 + 0.1 * torch.randn(D, generator=gen_post)
+        wm[rp + "stoch_net.1.bias"] = 0.1 * torch.randn(D, generator=gen_post)
     wm.update(make_mlp_sd(gen, "reward_predictor.", D + S, 1, hidden, layer_norm))
     if predict_discount:
         wm.update(make_mlp_sd(gen, "discount_predictor.", D + S, 1, hidden, layer_norm))

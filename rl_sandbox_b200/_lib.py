@@ -81,6 +81,40 @@ class SlotParams(C.Structure):
         "mlp_w1", "mlp_b1", "mlp_w2", "mlp_b2")]
 
 
+class ObserveCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("D", "groups", "classes", "A", "E", "layer_norm", "T")]
+
+
+_OBS_FIELDS = ("img_in_w", "img_in_b", "img_in_ln_g", "img_in_ln_b", "gru_w", "gru_b", "gru_ln_g", "gru_ln_b",
+               "prior1_w", "prior1_b", "prior1_ln_g", "prior1_ln_b", "prior2_w", "prior2_b",
+               "post1_w", "post1_b", "post1_ln_g", "post1_ln_b", "post2_w", "post2_b")
+
+
+class ObserveParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _OBS_FIELDS]
+
+
+class ObserveGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _OBS_FIELDS]
+
+
+class ObserveOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("prior_logits", "post_logits", "determ", "stoch_idx", "stoch")]
+
+
+# rlsb_observe_params field -> state-dict key below `recurrent_model.` (reference: agents/dreamer/rssm.py:136-165)
+OBS_KEYS = {"img_in_w": "pre_determ_recurrent.0.weight", "img_in_b": "pre_determ_recurrent.0.bias",
+            "img_in_ln_g": "pre_determ_recurrent.1.weight", "img_in_ln_b": "pre_determ_recurrent.1.bias",
+            "gru_w": "determ_recurrent._layer.weight", "gru_b": "determ_recurrent._layer.bias",
+            "gru_ln_g": "determ_recurrent._norm.weight", "gru_ln_b": "determ_recurrent._norm.bias",
+            "prior1_w": "ensemble_prior_estimator.0.weight", "prior1_b": "ensemble_prior_estimator.0.bias",
+            "prior1_ln_g": "ensemble_prior_estimator.1.weight", "prior1_ln_b": "ensemble_prior_estimator.1.bias",
+            "prior2_w": "ensemble_prior_estimator.3.weight", "prior2_b": "ensemble_prior_estimator.3.bias",
+            "post1_w": "stoch_net.0.weight", "post1_b": "stoch_net.0.bias",
+            "post1_ln_g": "stoch_net.1.weight", "post1_ln_b": "stoch_net.1.bias",
+            "post2_w": "stoch_net.3.weight", "post2_b": "stoch_net.3.bias"}
+
+
 class SlotGrads(C.Structure):
     _fields_ = SlotParams._fields_
 
@@ -142,6 +176,15 @@ def load() -> C.CDLL:
         "rlsb_imagine_tape_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
         "rlsb_imagine_bwd_workspace_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
         "rlsb_imagine_bwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, C.POINTER(ImagineOut), vp, vp, vp, vp, vp]),
+    })
+    sig.update({
+        "rlsb_observe_packed_bytes": (sz, [C.POINTER(ObserveCfg)]),
+        "rlsb_observe_tape_bytes": (sz, [C.POINTER(ObserveCfg), i64]),
+        "rlsb_observe_bwd_workspace_bytes": (sz, [C.POINTER(ObserveCfg), i64]),
+        "rlsb_observe_pack": (C.c_int, [C.POINTER(ObserveCfg), C.POINTER(ObserveParams), vp, vp]),
+        "rlsb_observe_fwd": (C.c_int, [C.POINTER(ObserveCfg), vp, i64, vp, vp, C.POINTER(Noise), C.POINTER(ObserveOut), vp, vp]),
+        "rlsb_observe_bwd": (C.c_int, [C.POINTER(ObserveCfg), vp, i64, vp, C.POINTER(ObserveOut), vp, vp, vp, vp,
+                                       C.POINTER(ObserveGrads), vp, vp, vp]),
     })
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -593,3 +593,101 @@ class SlotAttentionFn(torch.autograd.Function):
         X, tape = ctx.saved_tensors
         dX, dprev, grads = ctx.engine.backward(X, tape, d_out.contiguous())
         return (None, None, dX, dprev) + tuple(grads[n] for n in ctx.names)
+
+
+# ------------------------------------------------------------------------------------------------
+# K5: world-model observe scan
+# ------------------------------------------------------------------------------------------------
+class ObserveEngine:
+    """Packed RSSM weights of K5 (the T-step observe loop of WorldModel.calculate_loss, world_model.py:187-202)."""
+
+    def __init__(self, D: int, A: int, E: int, layer_norm: bool, T: int, groups: int = 32, classes: int = 32, device="cuda"):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.cfg = _lib.ObserveCfg(D, groups, classes, A, E, int(layer_norm), T)
+        self.D, self.A, self.E, self.T, self.S, self.groups, self.layer_norm = D, A, E, T, groups * classes, groups, layer_norm
+        self.device = torch.device(device)
+        nbytes = self.lib.rlsb_observe_packed_bytes(C.byref(self.cfg))
+        if nbytes == 0:
+            raise _lib.RlsbError(f"unsupported observe config D={D} A={A} E={E} T={T}")
+        self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+        self._bws = None
+
+    def names(self) -> list:
+        """state-dict keys (below `recurrent_model.`) in the order of rlsb_observe_params, LayerNorm entries only if present"""
+        return [k for f, k in _lib.OBS_KEYS.items() if self.layer_norm or not f.endswith(("1_ln_g", "1_ln_b", "in_ln_g", "in_ln_b"))]
+
+    def pack(self, rssm_sd: dict) -> None:
+        p, keep = _lib.ObserveParams(), []
+        for field, key in _lib.OBS_KEYS.items():
+            if key in rssm_sd and key in self.names():
+                t = _f32c(rssm_sd[key])
+                keep.append(t)
+                setattr(p, field, t.data_ptr())
+        check(self.lib.rlsb_observe_pack(C.byref(self.cfg), C.byref(p), self.packed.data_ptr(), _stream()), "rlsb_observe_pack")
+        self._keep = keep
+
+    def forward(self, embed: torch.Tensor, actions: torch.Tensor, latent_uniforms: Optional[torch.Tensor] = None,
+                seed: int = 0, row_offset: int = 0):
+        """embed (T, B, E), actions (T, B, A) -> dict(prior_logits, post_logits, determ, stoch_idx, stoch, tape)"""
+        embed, actions = _f32c(embed), _f32c(actions)
+        T, B = embed.shape[0], embed.shape[1]
+        if T != self.T or embed.shape[2] != self.E or actions.shape != (T, B, self.A):
+            raise _lib.RlsbError(f"observe: embed {tuple(embed.shape)} actions {tuple(actions.shape)} for T={self.T}")
+        dev = embed.device
+        out = {"prior_logits": torch.empty((T, B, self.S), device=dev), "post_logits": torch.empty((T, B, self.S), device=dev),
+               "determ": torch.empty((T, B, self.D), device=dev),
+               "stoch_idx": torch.empty((T, B, self.groups), device=dev, dtype=torch.uint8),
+               "stoch": torch.empty((T, B, self.S), device=dev)}
+        # zero-initialised: slot 0 of the state images is the zero initial state, padding rows enter weight gradients
+        out["tape"] = torch.zeros(self.lib.rlsb_observe_tape_bytes(C.byref(self.cfg), B), device=dev, dtype=torch.uint8)
+        co = _lib.ObserveOut(*[out[k].data_ptr() for k in ("prior_logits", "post_logits", "determ", "stoch_idx", "stoch")])
+        nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)), None, seed, row_offset, None, None)
+        check(self.lib.rlsb_observe_fwd(C.byref(self.cfg), self.packed.data_ptr(), B, embed.data_ptr(), actions.data_ptr(),
+                                        C.byref(nz), C.byref(co), out["tape"].data_ptr(), _stream()), "rlsb_observe_fwd")
+        return out
+
+    def backward(self, out: dict, g_prior, g_post, g_determ, g_stoch):
+        """-> (g_embed (T, B, E), {state-dict key: gradient})"""
+        T, B = out["determ"].shape[0], out["determ"].shape[1]
+        nbytes = self.lib.rlsb_observe_bwd_workspace_bytes(C.byref(self.cfg), B)
+        if self._bws is None or self._bws.numel() < nbytes:
+            self._bws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        D, S, A, E = self.D, self.S, self.A, self.E
+        shapes = {"img_in_w": (D, S + A), "img_in_b": (D,), "img_in_ln_g": (D,), "img_in_ln_b": (D,),
+                  "gru_w": (3 * D, 2 * D), "gru_b": (3 * D,), "gru_ln_g": (3 * D,), "gru_ln_b": (3 * D,),
+                  "prior1_w": (D, D), "prior1_b": (D,), "prior1_ln_g": (D,), "prior1_ln_b": (D,),
+                  "prior2_w": (S, D), "prior2_b": (S,), "post1_w": (D, D + E), "post1_b": (D,),
+                  "post1_ln_g": (D,), "post1_ln_b": (D,), "post2_w": (S, D), "post2_b": (S,)}
+        g, grads = _lib.ObserveGrads(), {}
+        names = set(self.names())
+        for field, key in _lib.OBS_KEYS.items():
+            if key in names:
+                t = torch.zeros(shapes[field], device=self.device, dtype=torch.float32)
+                grads[key] = t
+                setattr(g, field, t.data_ptr())
+        g_embed = torch.empty((T, B, E), device=self.device, dtype=torch.float32)
+        co = _lib.ObserveOut(*[out[k].data_ptr() for k in ("prior_logits", "post_logits", "determ", "stoch_idx", "stoch")])
+        f = lambda t: None if t is None else _f32c(t).data_ptr()
+        check(self.lib.rlsb_observe_bwd(C.byref(self.cfg), self.packed.data_ptr(), B, out["tape"].data_ptr(), C.byref(co),
+                                        f(g_prior), f(g_post), f(g_determ), f(g_stoch), C.byref(g), g_embed.data_ptr(),
+                                        self._bws.data_ptr(), _stream()), "rlsb_observe_bwd")
+        return g_embed, grads
+
+
+class ObserveScanFn(torch.autograd.Function):
+    """The observe loop under torch autograd: forward = rlsb_observe_fwd, backward = rlsb_observe_bwd."""
+
+    @staticmethod
+    def forward(ctx, engine, names, noise, embed, actions, *params):
+        out = engine.forward(embed.detach(), actions.detach(), **noise)
+        ctx.engine, ctx.names, ctx.out = engine, names, out
+        ctx.mark_non_differentiable(out["stoch_idx"])
+        return out["prior_logits"], out["post_logits"], out["determ"], out["stoch"], out["stoch_idx"]
+
+    @staticmethod
+    def backward(ctx, g_prior, g_post, g_determ, g_stoch, _g_idx):
+        c = lambda t: None if t is None else t.contiguous()
+        g_embed, grads = ctx.engine.backward(ctx.out, c(g_prior), c(g_post), c(g_determ), c(g_stoch))
+        ctx.out = None
+        return (None, None, None, g_embed, None) + tuple(grads[n] for n in ctx.names)

@@ -303,3 +303,46 @@ def test_cuda_graph_replay_matches_eager(cuda, name):
             for k in ("determ", "stoch_idx", "actions", "rewards", "values"):
                 assert torch.equal(outs[0][1][k], outs[1][1][k]), (step, k)
     print(f"[parity] {name}: graph replays track eager steps (step 0 bit-identical; later steps to fp32 rounding)")
+
+
+def test_ac_update_full_size_properties(cuda):
+    """BASELINE sweep size (32768 start states x H = 15), size-independent properties of K4:
+    weight / bias gradients are bitwise reproducible run to run (fixed-order split reductions), everything is finite,
+    and the actor's last-layer bias gradient sums to zero (sum_k d loss / d logit_k = 0 for both the reinforce and
+    the entropy term of a softmax policy)."""
+    from rl_sandbox.agents.dreamer.rssm import State
+    c = load_case("c1")
+    m = c["meta"]
+    agent = make_agent(m, "cuda", H=15)
+    load_params(agent, c)
+    torch.manual_seed(1)
+    with torch.no_grad():
+        for p in list(agent.actor.parameters()) + list(agent.critic.critic.parameters()):
+            p.add_(0.05 * torch.randn_like(p))
+    agent.mark_weights_changed()
+    N = 32768
+    g = torch.Generator(device="cuda").manual_seed(3)
+    h0 = 0.5 * torch.randn(N, m["D"], device="cuda", generator=g)
+    z0 = torch.nn.functional.one_hot(torch.randint(0, 32, (N, 32), device="cuda", generator=g), 32).float().view(N, 1024)
+    init = State(h0.unsqueeze(0), torch.zeros(1, N, 32, 32, device="cuda"), z0.unsqueeze(0))
+    from rl_sandbox_b200 import ops
+    with torch.no_grad():
+        agent.imagine_trajectory(init, noise={"seed": 5}, keep_packed=True)
+    k1 = agent.last_rollout
+    vs, w, _ = ops.lambda_return(k1["rewards"], k1["values"], k1["discounts"], agent.critic.lambda_)
+    eng = agent._get_ac_engine()
+    runs = []
+    for _ in range(2):
+        for p in list(agent.actor.parameters()) + list(agent.critic.parameters()):
+            p.grad = None
+        scal = eng.update(k1, vs, w, agent.actor.actor, agent.critic.critic, seed=1, horizon=15).clone()
+        runs.append((scal, {n: p.grad.clone() for n, p in list(agent.actor.actor.named_parameters()) +
+                            [("c." + n, p) for n, p in agent.critic.critic.named_parameters()]}))
+    assert torch.isfinite(runs[0][0]).all()
+    for n, g0 in runs[0][1].items():
+        assert torch.isfinite(g0).all(), n
+        if int(n.split(".")[-2]) in (0, 3, 6, 9, 12):   # nn.Linear weights / biases (LayerNorm sits at 1, 4, 7, 10)
+            assert torch.equal(g0, runs[1][1][n]), f"{n}: weight / bias gradients must be bitwise reproducible"
+    gb = runs[0][1]["12.bias"]
+    assert gb.sum().abs().item() < 2e-2 * gb.norm().item(), (gb.sum().item(), gb.norm().item())
+    print(f"[parity] K4 full size: actor last-bias gradient sum {gb.sum().item():.3e} vs norm {gb.norm().item():.3e}")

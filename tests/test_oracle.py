@@ -100,14 +100,21 @@ def test_oracle_slot_attention_matches_reference():
     import json
     from tests._golden import GOLDEN
     from oracle.gen_golden import SLOT_CASE, slot_inputs
+    from oracle.gen_golden import slot_grad_weights
     z = np.load(GOLDEN / "slot_attention.npz")
-    assert json.loads(str(z["meta"])) == SLOT_CASE
+    meta = json.loads(str(z["meta"]))
+    assert {k: meta[k] for k in SLOT_CASE} == SLOT_CASE, "fixture is stale: re-run python -m oracle.gen_golden"
     sd = orc.make_slot_params(SLOT_CASE["param_seed"], SLOT_CASE["dim"], SLOT_CASE["slots"])
     X, prev = slot_inputs()
     out, attn = orc.slot_attention(X, prev, sd, SLOT_CASE["iters"])
     torch.testing.assert_close(out, torch.from_numpy(z["slots"]), rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(attn, torch.from_numpy(z["attn"]), rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(attn.sum(-1), torch.ones(3, 4), rtol=1e-5, atol=1e-5)
+    # the port's autograd reproduces the reference's gradients of sum(out * G) w.r.t. the inputs
+    Xg, pg = X.clone().requires_grad_(), prev.clone().requires_grad_()
+    (orc.slot_attention(Xg, pg, sd, SLOT_CASE["iters"])[0] * slot_grad_weights()).sum().backward()
+    torch.testing.assert_close(Xg.grad, torch.from_numpy(z["grad_X"]), rtol=2e-3, atol=1e-5)
+    torch.testing.assert_close(pg.grad, torch.from_numpy(z["grad_prev"]), rtol=2e-3, atol=1e-5)
 
 
 @pytest.mark.parametrize("name", ["c2", "c2_ln"])
@@ -154,3 +161,38 @@ def test_oracle_slotted_rollout_matches_reference():
     assert torch.equal(out["stoch_idx"], gold["stoch_idx"].long()), "categorical indices must be bit-exact"
     for k in ("determ", "logits", "actions", "rewards", "values"):
         torch.testing.assert_close(out[k], gold[k], rtol=1e-4, atol=3e-5, msg=lambda s: f"{k}: {s}")
+
+
+def _load_observe():
+    import json
+    from oracle.gen_golden import OBSERVE_CASE, observe_inputs
+    from tests._golden import GOLDEN
+    z = np.load(GOLDEN / "observe.npz")
+    meta = json.loads(str(z["meta"]))
+    assert {k: meta[k] for k in OBSERVE_CASE} == OBSERVE_CASE, "fixture is stale: re-run python -m oracle.gen_golden"
+    gold = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files if k != "meta"}
+    wm, _, _ = orc.make_params(meta["param_seed"], D=meta["D"], A=meta["A"], discrete=False, layer_norm=meta["layer_norm"],
+                               predict_discount=False)
+    return meta, gold, wm, observe_inputs()
+
+
+def test_oracle_observe_scan_matches_reference():
+    """oracle_port.observe_scan (+ autograd) vs the reference's observe loop (RSSM.forward x T, world_model.py:187-202)
+    and the gradients its autograd produced for the seeded probe loss."""
+    from oracle.gen_golden import grad_probe_indices
+    meta, gold, wm, (embed, actions, uniforms, weights) = _load_observe()
+    rp = "recurrent_model."
+    wm = {k: (v.clone().requires_grad_() if k.startswith(rp) else v) for k, v in wm.items()}
+    embed = embed.clone().requires_grad_()
+    o = orc.observe_scan(wm, embed, actions, uniforms)
+    assert torch.equal(o["stoch_idx"].to(torch.uint8), gold["stoch_idx"])
+    for k in ("prior_logits", "post_logits", "determ"):
+        torch.testing.assert_close(o[k], gold[k], rtol=1e-4, atol=2e-5, msg=lambda s: f"{k}: {s}")
+    orc.observe_probe_loss(o, weights).backward()
+    torch.testing.assert_close(embed.grad, gold["grad_embed"], rtol=2e-3, atol=1e-6)
+    for i, n in enumerate(meta["grad_names"]):
+        g = wm[rp + n].grad
+        nref = gold["grad_norms"][i].item()
+        assert abs(g.norm().item() - nref) <= 1e-3 * nref + 1e-8, n
+        torch.testing.assert_close(g.flatten()[grad_probe_indices(g.numel())], gold["grad_probes"][i], rtol=5e-3,
+                                   atol=1e-5 * max(1.0, nref), msg=lambda s: f"{n}: {s}")
