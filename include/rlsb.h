@@ -374,7 +374,7 @@ int rlsb_observe_bwd(const rlsb_observe_cfg* cfg, const void* packed, int64_t B,
 
 /* K3 with autograd: the forward records an activation tape (rlsb_slot_attention_tape_bytes bytes); the backward
  * returns d loss / d X (B, tokens, dim), d loss / d prev_slots (B, slots, dim) and the gradient of every parameter of
- * rlsb_slot_params (same field names, nn.Linear / nn.LayerNorm / nn.GRUCell layouts; all required) — the autograd of
+ * rlsb_slot_params -- same field names, nn.Linear / nn.LayerNorm / nn.GRUCell layouts; all required -- the autograd of
  * SlotAttention.forward (vision/slot_attention.py:52-77) inside the world-model loss.  `packed` is the blob of
  * rlsb_slot_attention_pack (it also carries the transposed weight images). */
 typedef struct {

@@ -105,6 +105,31 @@ class WorldModel(nn.Module):
         rhs = torch.maximum(kl(Dist(post_logits), Dist(prior_logits.detach())).mean(), floor)
         return self.alpha * lhs + (1 - self.alpha) * rhs
 
+    kernel_observe = True   # False: the reference's op sequence (T torch RSSM.forward calls under autograd)
+    _observe_engine = None
+    _observe_calls = 0
+
+    def _observe_scan(self, embed, actions):
+        """The T-step observe loop in librlsb (K5, rlsb_observe_fwd / _bwd under torch autograd).
+        embed (B, T, E), actions (B, T, A) already masked by is_first -> posterior, prior States (T, B, .)."""
+        from rl_sandbox_b200 import ops
+        B, T, E = embed.shape
+        rm = self.recurrent_model
+        eng = self._observe_engine
+        if eng is None or (eng.T, eng.E) != (T, E):
+            eng = ops.ObserveEngine(self.rssm_dim, self.actions_num, E, bool(self.layer_norm), T, groups=self.latent_dim,
+                                    classes=self.latent_classes, device=embed.device)
+            self._observe_engine = eng
+        sd = dict(rm.named_parameters())
+        eng.pack({k: v.detach() for k, v in sd.items()})   # the parameters change every optimizer step
+        names = eng.names()
+        noise = {"seed": 0x0B5E0000 + self._observe_calls}
+        self._observe_calls += 1
+        prior_l, post_l, determ, stoch, _idx = ops.ObserveScanFn.apply(
+            eng, names, noise, embed.transpose(0, 1).float(), actions.transpose(0, 1).float(), *[sd[n] for n in names])
+        shape = (T, B, self.latent_dim, self.latent_classes)
+        return State(determ, post_l.view(shape), stoch), State(determ, prior_l.view(shape))
+
     def calculate_loss(self, obs, a, r, discount, first, additional):
         self.recurrent_model.on_train_step()
         b = obs.shape[0]
@@ -114,15 +139,18 @@ class WorldModel(nn.Module):
         a_c = a.reshape(B, T, self.actions_num)
         r_c, d_c, first_c = r.reshape(B, T, 1), discount.reshape(B, T, 1), first.reshape(B, T, 1)
 
-        priors, posts = [], []
-        state = self.get_initial_state(B)
-        for step in range(T):
-            a_t = (a_c[:, step] * (1 - first_c[:, step])).unsqueeze(0)
-            prior, post, _ = self.recurrent_model.forward(state, embed[:, step].unsqueeze(0), a_t)
-            priors.append(prior)
-            posts.append(post)
-            state = post
-        posterior, prior = State.stack(posts), State.stack(priors)
+        if self.kernel_observe and embed.is_cuda and not self.recurrent_model.discrete_rssm:
+            posterior, prior = self._observe_scan(embed, a_c * (1 - first_c))
+        else:
+            priors, posts = [], []
+            state = self.get_initial_state(B)
+            for step in range(T):
+                a_t = (a_c[:, step] * (1 - first_c[:, step])).unsqueeze(0)
+                prior, post, _ = self.recurrent_model.forward(state, embed[:, step].unsqueeze(0), a_t)
+                priors.append(prior)
+                posts.append(post)
+                state = post
+            posterior, prior = State.stack(posts), State.stack(priors)
         feat = posterior.combined.transpose(0, 1)  # (B, T, Z)
 
         losses, metrics = {}, {}

@@ -63,3 +63,38 @@ def run2():
     return e0.elapsed_time(e1)
 for _ in range(2): run2()
 print("observe loop backward alone %.2f ms" % statistics.median(run2() for _ in range(5)))
+
+# ---- the same with the observe loop in librlsb (K5) ----
+from rl_sandbox_b200.agents.dreamer.rssm import State
+def run3():
+    e = [ev() for _ in range(5)]
+    e[0].record()
+    embed = wm.encoder(obs).reshape(B, T, -1)
+    e[1].record()
+    posterior, prior = wm._observe_scan(embed, a.reshape(B, T, -1))
+    e[2].record()
+    feat = posterior.combined.transpose(0, 1)
+    flat = feat.flatten(0, 1)
+    loss = -wm.image_predictor(flat).log_prob(obs).float().mean() - wm.reward_predictor(feat).log_prob(r.reshape(B, T, 1)).float().mean() \
+        - wm.discount_predictor(feat).log_prob(disc.reshape(B, T, 1)).float().mean() + 2 * wm._kl(prior.stoch_logits, posterior.stoch_logits)
+    e[3].record()
+    for p in wm.parameters(): p.grad = None
+    loss.backward()
+    e[4].record()
+    torch.cuda.synchronize()
+    return [e[i].elapsed_time(e[i + 1]) for i in range(4)]
+for _ in range(3): run3()
+ts = [run3() for _ in range(5)]
+med = [statistics.median(t[i] for t in ts) for i in range(4)]
+print("K5 path: encoder %.2f ms | observe scan fwd %.2f ms | heads+decoder+losses fwd %.2f ms | backward (all) %.2f ms" % tuple(med))
+eng = wm._observe_engine
+emb = wm.encoder(obs).reshape(B, T, -1).transpose(0, 1).contiguous().detach()
+act = a.reshape(B, T, -1).transpose(0, 1).contiguous()
+def t_fwd():
+    e0, e1 = ev(), ev(); e0.record(); out = eng.forward(emb, act, seed=1); e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1), out
+def t_bwd(out):
+    gp = torch.randn_like(out["prior_logits"]); gd = torch.randn_like(out["determ"])
+    e0, e1 = ev(), ev(); e0.record(); eng.backward(out, gp, gp, gd, gp); e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)
+for _ in range(2): t_bwd(t_fwd()[1])
+f = [t_fwd() for _ in range(5)]
+print("K5 alone: fwd %.2f ms, bwd %.2f ms" % (statistics.median(x[0] for x in f), statistics.median(t_bwd(x[1]) for x in f)))
