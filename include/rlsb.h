@@ -64,6 +64,14 @@ int rlsb_lambda_return_bwd(const float* g_vs, const float* v, const float* d, co
  *   logits, uniforms : (rows, classes) fp32;  idx : (rows) int32 */
 int rlsb_sample_categorical(const float* logits, const float* uniforms, int64_t rows, int classes,
                             int32_t* idx, void* stream);
+/* The latent draw of K1 / K5 on its own (rssm.py:34-37: State.stoch over groups x 32 classes), as the rollout
+ * launches it: screening pass with fast logs, every group whose winner is not separated from the runner-up by more
+ * than the screening error is redrawn in the reference order with the bit-reproducible transform, so idx equals
+ * rlsb_sample_categorical's on the same logits and uniforms, always.
+ *   logits : (rows, groups*32) fp32;  uniforms : same shape, or NULL -> Philox(seed; row_offset + row, step, 0, e/4);
+ *   idx : (rows, groups) uint8;  onehot_f32 : (rows, groups*32) fp32 or NULL */
+int rlsb_sample_latent(const float* logits, int64_t rows, int groups, const float* uniforms, uint64_t seed,
+                       uint32_t row_offset, uint32_t step, uint8_t* idx, float* onehot_f32, void* stream);
 /* Philox4x32-10 uniforms exactly as the imagination kernels draw them (for RNG parity tests):
  * out[i] = uniform(seed, n = n0 + i / per_row, t, stream_id, e = i % per_row) */
 int rlsb_philox_uniform(uint64_t seed, uint32_t n0, uint32_t t, uint32_t stream_id, int per_row,

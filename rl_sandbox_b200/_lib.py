@@ -145,6 +145,7 @@ def load() -> C.CDLL:
         "rlsb_lambda_return_bwd": (C.c_int, [vp, vp, vp, vp, i32, i64, C.c_double, vp, vp, vp, vp]),
         "rlsb_sample_categorical": (C.c_int, [vp, vp, i64, i32, vp, vp]),
         "rlsb_philox_uniform": (C.c_int, [u64, u32, u32, u32, i32, i64, vp, vp]),
+        "rlsb_sample_latent": (C.c_int, [vp, i64, i32, vp, u64, u32, u32, vp, vp, vp]),
         "rlsb_pack_rows": (C.c_int, [vp, i64, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
         "rlsb_gemm_bias": (C.c_int, [vp, i32, vp, i32, i32, vp, i32, i32, vp, i64, vp, vp]),
         "rlsb_gemm_ln_act": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, f32, i32, vp, i32, vp]),

@@ -49,4 +49,4 @@ class Decoder(nn.Module):
 
     def forward(self, X):
         y = self.net(self.convin(X).view(-1, self.in_channels, 1, 1))
-        return td.Independent(td.Normal(y, 1.0), 3) if self.return_dist else y
+        return td.Independent(td.Normal(y, torch.ones((), device=y.device, dtype=y.dtype)), 3) if self.return_dist else y

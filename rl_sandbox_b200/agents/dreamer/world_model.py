@@ -108,6 +108,7 @@ class WorldModel(nn.Module):
     kernel_observe = True   # False: the reference's op sequence (T torch RSSM.forward calls under autograd)
     _observe_engine = None
     _observe_calls = 0
+    _observe_seed_device = None   # int64 device tensor holding the Philox key (CUDA-graph replays change it in place)
 
     def _observe_scan(self, embed, actions):
         """The T-step observe loop in librlsb (K5, rlsb_observe_fwd / _bwd under torch autograd).
@@ -124,6 +125,8 @@ class WorldModel(nn.Module):
         eng.pack({k: v.detach() for k, v in sd.items()})   # the parameters change every optimizer step
         names = eng.names()
         noise = {"seed": 0x0B5E0000 + self._observe_calls}
+        if self._observe_seed_device is not None:
+            noise = {"seed_device": self._observe_seed_device}
         self._observe_calls += 1
         prior_l, post_l, determ, stoch, _idx = ops.ObserveScanFn.apply(
             eng, names, noise, embed.transpose(0, 1).float(), actions.transpose(0, 1).float(), *[sd[n] for n in names])
@@ -163,7 +166,7 @@ class WorldModel(nn.Module):
             if self.vit_l2_ratio != 1.0:
                 img_rec = -self.image_predictor(flat).log_prob(obs).float().mean()
             else:
-                img_rec = torch.tensor(0, device=obs.device)
+                img_rec = torch.zeros((), device=obs.device, dtype=torch.long)
                 losses['loss_reconstruction_img'] = -self.image_predictor(flat.detach()).log_prob(obs).float().mean()
             d_obs = additional['d_features'].reshape(b, self.vit_feat_dim, self.vit_size, self.vit_size)
             d_rec = -self.dino_predictor(flat).log_prob(d_obs).float().mean()

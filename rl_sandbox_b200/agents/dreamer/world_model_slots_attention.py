@@ -139,7 +139,8 @@ class WorldModel(nn.Module):
             l2 = (mask * ((decoded - target.unsqueeze(1)) ** 2)).sum(dim=[2, 3, 4])
             norm = torch.prod(torch.tensor(target.shape)[-3:]) / mask.sum(dim=[2, 3, 4]).clamp(min=1)
             return l2, norm
-        dist = td.Independent(td.Normal(torch.sum(decoded, dim=1), 1.0), 3)
+        mean = torch.sum(decoded, dim=1)
+        dist = td.Independent(td.Normal(mean, torch.ones((), device=mean.device, dtype=mean.dtype)), 3)
         return -dist.log_prob(target).float().mean(), None
 
     def calculate_loss(self, obs, a, r, discount, first, additional):
@@ -176,7 +177,7 @@ class WorldModel(nn.Module):
         posterior, prior = State.stack(posteriors), State.stack(priors)
         r_pred = self.reward_predictor(posterior.combined.transpose(0, 1))
         f_pred = self.discount_predictor(posterior.combined.transpose(0, 1))
-        losses['loss_reconstruction_img'] = torch.tensor(0, device=obs.device)
+        losses['loss_reconstruction_img'] = torch.zeros((), device=obs.device, dtype=torch.long)
 
         def image_rec(post):
             imgs, masks = self._decode(self.image_predictor, post, b, 3, h, w, 2)
@@ -189,7 +190,7 @@ class WorldModel(nn.Module):
             if self.vit_l2_ratio != 1.0:
                 img_rec = image_rec(posterior)
             else:
-                img_rec = torch.tensor(0, device=obs.device)
+                img_rec = torch.zeros((), device=obs.device, dtype=torch.long)
                 losses['loss_reconstruction_img'] = image_rec(posterior.detach())
             d_features = additional['d_features']
             feats_dec, masks = self._decode(self.dino_predictor, posterior, b, self.vit_feat_dim, self.vit_size,

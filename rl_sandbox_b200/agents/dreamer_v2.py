@@ -36,6 +36,11 @@ def _strip_compile_prefix(sd: dict) -> dict:
     return {k.removeprefix('_orig_mod.'): v for k, v in sd.items()}
 
 
+def _lib_handle():
+    from rl_sandbox_b200 import _lib
+    return _lib.load()
+
+
 class DreamerV2(RlAgent):
 
     def __init__(self, obs_space_num: list[int], clip_rewards: str, actions_num: int, world_model: t.Any,
@@ -72,6 +77,11 @@ class DreamerV2(RlAgent):
         # in a CUDA graph and replay it; the Philox key lives in device memory so every replay draws fresh noise
         self.cuda_graph = True
         self.cuda_graph_max_rows = 8192
+        # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
+        # T sequential steps of small kernels — thousands of launches whose CPU dispatch cost exceeds their GPU time)
+        self.cuda_graph_wm = True
+        self._wm_graphs: dict = {}
+        self._wm_sched_prev = None
         self._graphs: dict = {}
         self._weights_version = 0    # bumped whenever parameters change
         self._packed_version = -1
@@ -363,6 +373,101 @@ class DreamerV2(RlAgent):
             self.last_rollout = st['out']
         return st['scal']
 
+    # ------------------------------------------------------------------------------------------
+    # world-model half of train() (dreamer_v2.py:172-177)
+    # ------------------------------------------------------------------------------------------
+    def _world_model_update(self, obs, a, r, discount_factors, first_flags, additional):
+        sched = getattr(self.world_model.recurrent_model, 'attention_scheduler', None)
+        sched_val = float(sched.val) if sched is not None else None
+        # a Python-side schedule that is still moving would be frozen into the graph: stay eager until it settles
+        stable = sched is None or sched_val == self._wm_sched_prev
+        self._wm_sched_prev = sched_val
+        if self.cuda_graph_wm and obs.is_cuda and not self.is_f16 and stable and torch.is_grad_enabled():
+            return self._world_model_update_graphed(obs, a, r, discount_factors, first_flags, additional, sched_val)
+        with torch.autocast(device_type='cuda', enabled=self.is_f16):
+            losses_wm, discovered_states, metrics_wm = self.world_model.calculate_loss(
+                obs, a, r, discount_factors, first_flags, additional)
+        metrics_wm |= self.world_model_optimizer.step(losses_wm['loss_wm'])
+        return losses_wm, discovered_states, metrics_wm
+
+    def _world_model_update_graphed(self, obs, a, r, discount_factors, first_flags, additional, sched_val):
+        """calculate_loss + loss_wm.backward() replayed from a CUDA graph (static inputs, gradients in static .grad
+        buffers, device-resident noise key for the observe scan); all-reduce, clipping and AdamW run eagerly after."""
+        import torch.distributions as td
+        wm, opt = self.world_model, self.world_model_optimizer
+        ins = {'obs': obs, 'a': a.float(), 'r': r, 'disc': discount_factors, 'first': first_flags}
+        ins |= {f'add.{k}': v for k, v in additional.items() if torch.is_tensor(v)}
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in ins.items()) + (sched_val,)
+        st = self._wm_graphs.get(key)
+
+        named = [(n, p) for n, p in wm.named_parameters() if p.requires_grad]
+        params = [p for _, p in named]
+
+        def body(static):
+            from torch.nn.utils.stateless import _reparametrize_module
+            add = {k[4:]: v for k, v in static.items() if k.startswith('add.')}
+            # Fresh leaves aliasing the parameters: their gradient edges are created on the current (capturing) stream.
+            # The parameters' own AccumulateGrad nodes live on whatever stream first used them — the default stream after
+            # an eager step or get_action() — and a capture cannot synchronise with that stream.
+            leaves = {n: p.detach().requires_grad_(True) for n, p in named}
+            for m in wm.modules():   # engines that re-pack only when a parameter version changed: always inside the graph
+                if hasattr(m, 'mark_weights_changed'):
+                    m.mark_weights_changed()
+            with _reparametrize_module(wm, leaves):
+                losses, states, metrics = wm.calculate_loss(static['obs'], static['a'], static['r'], static['disc'],
+                                                            static['first'], add)
+            grads = torch.autograd.grad(losses['loss_wm'], list(leaves.values()), allow_unused=True)
+            return losses, states, metrics, grads
+
+        if st is None:
+            st = {'in': {k: v.detach().clone() for k, v in ins.items()},
+                  'seed': torch.zeros(1, device=obs.device, dtype=torch.int64)}
+            validate = td.Distribution._validate_args
+            td.Distribution.set_default_validate_args(False)   # argument checks read tensors back on the host
+            wm._observe_seed_device = st['seed']
+            sched = getattr(wm.recurrent_model, 'attention_scheduler', None)
+            t0 = sched._curr_t if sched is not None else None
+            calls0 = getattr(wm, '_observe_calls', 0)
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):   # warm-up outside capture: cuDNN plans, workspaces, kernel attributes
+                    for _ in range(2):
+                        body(st['in'])
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                lib = _lib_handle()
+                before = lib.rlsb_launch_count(0)
+                with torch.cuda.graph(graph):
+                    st['out'] = body(st['in'])
+                st['launches'] = lib.rlsb_launch_count(0) - before
+                lib.rlsb_launch_count_add(-st['launches'])
+            finally:
+                td.Distribution.set_default_validate_args(validate)
+                wm._observe_seed_device = None
+                if sched is not None:
+                    sched._curr_t = t0 + 1   # the warm-up passes do not count as training steps
+                if hasattr(wm, '_observe_calls'):
+                    wm._observe_calls = calls0
+            st['graph'] = graph
+            st['grads'] = [(p, g) for p, g in zip(params, st['out'][3])]
+            self._wm_graphs[key] = st
+        else:
+            wm.recurrent_model.on_train_step()   # the Python-side bookkeeping calculate_loss does per call
+        for k, v in ins.items():
+            st['in'][k].copy_(v)
+        # the observe scan's Philox key: the same sequence the eager path uses (world_model.py::_observe_scan)
+        st['seed'].fill_(0x0B5E0000 + getattr(wm, '_observe_calls', 0))
+        if hasattr(wm, '_observe_calls'):
+            wm._observe_calls += 1
+        st['graph'].replay()
+        _lib_handle().rlsb_launch_count_add(st['launches'])
+        for p, gbuf in st['grads']:   # the graph's static gradient buffers (None: parameter not on the loss path)
+            p.grad = gbuf
+        losses, states, metrics, _ = st['out']
+        metrics = dict(metrics) | opt.step_with_grads()
+        return dict(losses), states, metrics
+
     def train(self, rollout_chunks: RolloutChunks):
         obs, a, r, is_finished, is_first, additional = unpack(rollout_chunks)
         if self.is_discrete:
@@ -370,10 +475,8 @@ class DreamerV2(RlAgent):
         discount_factors = self.critic.gamma * (1 - is_finished).float()
         first_flags = is_first.float()
 
-        with torch.autocast(device_type='cuda', enabled=self.is_f16):
-            losses_wm, discovered_states, metrics_wm = self.world_model.calculate_loss(
-                obs, a, r, discount_factors, first_flags, additional)
-        metrics_wm |= self.world_model_optimizer.step(losses_wm['loss_wm'])
+        losses_wm, discovered_states, metrics_wm = self._world_model_update(obs, a, r, discount_factors, first_flags,
+                                                                          additional)
         self.mark_weights_changed()
 
         initial_states = discovered_states.flatten().detach()

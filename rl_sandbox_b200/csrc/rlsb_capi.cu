@@ -86,6 +86,17 @@ extern "C" int rlsb_sample_categorical(const float* logits, const float* uniform
   return launch_sample_categorical(logits, uniforms, rows, classes, idx, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int rlsb_sample_latent(const float* logits, int64_t rows, int groups, const float* uniforms, uint64_t seed,
+                                  uint32_t row_offset, uint32_t step, uint8_t* idx, float* onehot_f32, void* stream) {
+  if (!logits || !idx || rows <= 0 || rows > (1LL << 30) || groups <= 0 || groups > 64) return -1;
+  NoiseSpec ns{};
+  ns.explicit_noise = uniforms; ns.ld = static_cast<long long>(groups) * 32; ns.seed = seed; ns.seed_ptr = nullptr;
+  ns.step = step; ns.row_offset = row_offset;
+  return launch_sample_latent(logits, static_cast<long long>(groups) * 32, static_cast<int>(rows), groups, 32, ns, idx,
+                              nullptr, 0, onehot_f32, static_cast<long long>(groups) * 32,
+                              static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int rlsb_philox_uniform(uint64_t seed, uint32_t n0, uint32_t t, uint32_t stream_id, int per_row,
                                    int64_t count, float* out, void* stream) {
   if (!out || per_row <= 0 || count <= 0) return -1;

@@ -123,11 +123,26 @@ __device__ __forceinline__ void row_stats_warp(const float* stats, int NB, int m
   rstd = 1.0f / sqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + eps);
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid / tanh from MUFU.EX2 + MUFU.RCP (2 ulp each; no IEEE division sequence): |error| < 3e-7 absolute
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
-  const float e = __expf(-2.0f * fabsf(x));
-  const float t = (1.0f - e) / (1.0f + e);
-  return copysignf(t, x);
+  // 1 - 2 / (1 + e^{2x}); e^{2x} -> inf gives 1, -> 0 gives -1
+  return fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * x)), 1.0f);
 }
 
 struct LnActArgs {
@@ -143,53 +158,89 @@ struct LnActArgs {
   int out_kpad;
 };
 
-// one warp per (row, group of 32 eight-column chunks)
-__global__ void ln_act_kernel(const LnActArgs a) {
-  const int chunks_per_row = a.out_kpad >> 3;
-  const int gpr = (chunks_per_row + 31) >> 5;
-  const long long total = static_cast<long long>(a.m_pad) * gpr;
+__device__ __forceinline__ void load8(const float* p, bool vec, int valid, float (&v)[8]) {
+  if (vec && valid >= 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < valid ? p[j] : 0.f;
+  }
+}
+__device__ __forceinline__ void load8_ro(const float* p, bool vec, int valid, float (&v)[8]) {
+  if (vec && valid >= 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < valid ? __ldg(p + j) : 0.f;
+  }
+}
+
+// LayerNorm + activation over the fp32 pre-activations a split-row GEMM left in `scratch`: one warp per row.
+// A lane owns the 8-column chunks lane, lane + 32, ... (one 16-byte store each into the packed operand image); up
+// to four chunks (eight 16-byte loads) are in flight per lane before the row statistics are reduced — HBM-bound:
+// 4 B read + 2 B written per element.
+__global__ void __launch_bounds__(256, 4) ln_act_kernel(const LnActArgs a) {
+  const int cpr = a.out_kpad >> 3;
   const int lane = threadIdx.x & 31;
-  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long wi = warp0; wi < total; wi += nwarps) {
-    const int m = static_cast<int>(wi / gpr);
-    const int chunk = static_cast<int>(wi - static_cast<long long>(m) * gpr) * 32 + lane;
-    const int c0 = chunk << 3;
-    float mean = 0.f, rstd = 1.f;
+  const int warp0 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = static_cast<int>((gridDim.x * blockDim.x) >> 5);
+  const bool vec = ((a.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0);
+  const bool pvec = a.gamma && ((reinterpret_cast<uintptr_t>(a.gamma) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(a.beta) & 15) == 0);
+  for (int m = warp0; m < a.m_pad; m += nwarps) {
     const bool row_ok = m < a.M;
-    const bool act = row_ok && chunk < chunks_per_row && c0 < a.N;
-    float v[8];
-    if (act) {
-      const float* src = a.scratch + static_cast<size_t>(m) * a.ld + c0;
-      if (c0 + 8 <= a.N && (a.ld & 3) == 0) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
-        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-      } else {
+    const float* src = a.scratch + static_cast<size_t>(m) * a.ld;
+    float mean = 0.f, rstd = 1.f;
+    for (int cb = 0; cb < cpr; cb += 128) {   // batches of 4 chunks per lane
+      float v[4][8];
+      int valid[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < a.N) ? src[j] : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const int c0 = (cb + 32 * i + lane) << 3;
+        valid[i] = (row_ok && cb + 32 * i + lane < cpr) ? max(0, min(8, a.N - c0)) : 0;
+        if (valid[i] > 0) load8(src + c0, vec, valid[i], v[i]);
       }
-    }
-    if (row_ok && a.gamma) row_stats_warp(a.stats, a.NB, a.m_pad, m, a.N, a.eps, mean, rstd);
-    if (chunk >= chunks_per_row) continue;
-    float y[8];
+      if (cb == 0 && row_ok && a.gamma) row_stats_warp(a.stats, a.NB, a.m_pad, m, a.N, a.eps, mean, rstd);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) y[j] = 0.f;
-    if (act) {
+      for (int i = 0; i < 4; ++i) {
+        const int chunk = cb + 32 * i + lane;
+        if (chunk >= cpr) continue;
+        const int c0 = chunk << 3;
+        float y[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (c0 + j < a.N) {
-          float t = v[j];
-          if (a.gamma) t = (t - mean) * rstd * __ldg(a.gamma + c0 + j) + __ldg(a.beta + c0 + j);
-          if (a.act == ACT_ELU) t = t > 0.f ? t : __expf(t) - 1.0f;
-          else if (a.act == ACT_RELU) t = fmaxf(t, 0.f);
-          y[j] = t;
+        for (int j = 0; j < 8; ++j) y[j] = 0.f;
+        if (valid[i] > 0) {
+          float g[8], b[8];
+          if (a.gamma) {
+            load8_ro(a.gamma + c0, pvec, valid[i], g);
+            load8_ro(a.beta + c0, pvec, valid[i], b);
+            const float nmr = -mean * rstd;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(fmaf(v[i][j], rstd, nmr), g[j], b[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = v[i][j];
+          }
+          if (a.act == ACT_ELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], ex2_approx(1.4426950408889634f * fminf(y[j], 0.f)) - 1.0f);
+          } else if (a.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+          }
+          if (valid[i] < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j >= valid[i]) y[j] = 0.f;
+          }
         }
+        const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0),
+                                        static_cast<size_t>(a.out_kpad), kTileM);
+        *reinterpret_cast<uint4*>(a.out + idx) = make_uint4(bf2(y[0], y[1]), bf2(y[2], y[3]), bf2(y[4], y[5]), bf2(y[6], y[7]));
       }
     }
-    uint4 pk = make_uint4(bf2(y[0], y[1]), bf2(y[2], y[3]), bf2(y[4], y[5]), bf2(y[6], y[7]));
-    const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0),
-                                    static_cast<size_t>(a.out_kpad), kTileM);
-    *reinterpret_cast<uint4*>(a.out + idx) = pk;
   }
 }
 
@@ -209,17 +260,8 @@ struct GruArgs {
   int kpad;
 };
 
-__device__ __forceinline__ void load8(const float* p, bool vec, int valid, float (&v)[8]) {
-  if (vec && valid >= 8) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = j < valid ? p[j] : 0.f;
-  }
-}
-
-__global__ void gru_gate_kernel(const GruArgs a) {
+// generic path (D or a leading dimension not a multiple of 4): one warp per (row, 32 eight-column chunks)
+__global__ void gru_gate_kernel_generic(const GruArgs a) {
   const int chunks_per_row = a.kpad >> 3;
   const int gpr = (chunks_per_row + 31) >> 5;
   const long long total = static_cast<long long>(a.m_pad) * gpr;
@@ -227,7 +269,6 @@ __global__ void gru_gate_kernel(const GruArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const bool vec = ((a.ld & 3) == 0) && ((D & 3) == 0) && ((a.ld_h & 3) == 0) && ((a.ld_hn & 3) == 0);
   for (long long wi = warp0; wi < total; wi += nwarps) {
     const int m = static_cast<int>(wi / gpr);
     const int chunk = static_cast<int>(wi - static_cast<long long>(m) * gpr) * 32 + lane;
@@ -236,18 +277,18 @@ __global__ void gru_gate_kernel(const GruArgs a) {
     const bool act = row_ok && chunk < chunks_per_row && c0 < D;
     const int valid = act ? min(8, D - c0) : 0;
     float pr[8], pc[8], pu[8], hp[8], gr[8], gc[8], gu[8], br[8], bc[8], bu[8];
-    if (act) {  // all loads in flight before the shuffle-synchronised statistics
+    if (act) {
       const float* src = a.scratch + static_cast<size_t>(m) * a.ld + c0;
-      load8(src, vec, valid, pr);
-      load8(src + D, vec, valid, pc);
-      load8(src + 2 * D, vec, valid, pu);
-      load8(a.h_prev + static_cast<size_t>(m) * a.ld_h + c0, vec, valid, hp);
-      load8(a.gamma + c0, vec, valid, gr);
-      load8(a.gamma + D + c0, vec, valid, gc);
-      load8(a.gamma + 2 * D + c0, vec, valid, gu);
-      load8(a.beta + c0, vec, valid, br);
-      load8(a.beta + D + c0, vec, valid, bc);
-      load8(a.beta + 2 * D + c0, vec, valid, bu);
+      load8(src, false, valid, pr);
+      load8(src + D, false, valid, pc);
+      load8(src + 2 * D, false, valid, pu);
+      load8(a.h_prev + static_cast<size_t>(m) * a.ld_h + c0, false, valid, hp);
+      load8(a.gamma + c0, false, valid, gr);
+      load8(a.gamma + D + c0, false, valid, gc);
+      load8(a.gamma + 2 * D + c0, false, valid, gu);
+      load8(a.beta + c0, false, valid, br);
+      load8(a.beta + D + c0, false, valid, bc);
+      load8(a.beta + 2 * D + c0, false, valid, bu);
     }
     float mean = 0.f, rstd = 1.f;
     if (row_ok) row_stats_warp(a.stats, a.NB, a.m_pad, m, 3 * D, a.eps, mean, rstd);
@@ -256,6 +297,7 @@ __global__ void gru_gate_kernel(const GruArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = 0.f;
     if (act) {
+      float* hn = a.h_next + static_cast<size_t>(m) * a.ld_hn + c0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (j < valid) {
@@ -263,22 +305,76 @@ __global__ void gru_gate_kernel(const GruArgs a) {
           const float cand = fast_tanh(r * ((pc[j] - mean) * rstd * gc[j] + bc[j]));
           const float u = fast_sigmoid((pu[j] - mean) * rstd * gu[j] + bu[j] + a.update_bias);
           y[j] = u * cand + (1.0f - u) * hp[j];
+          hn[j] = y[j];
         }
       }
-      float* hn = a.h_next + static_cast<size_t>(m) * a.ld_hn + c0;
-      if (vec && valid == 8) {
-        *reinterpret_cast<float4*>(hn) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(hn + 4) = make_float4(y[4], y[5], y[6], y[7]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < valid) hn[j] = y[j];
-      }
     }
-    uint4 pk = make_uint4(bf2(y[0], y[1]), bf2(y[2], y[3]), bf2(y[4], y[5]), bf2(y[6], y[7]));
     const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0),
                                     static_cast<size_t>(a.kpad), kTileM);
-    *reinterpret_cast<uint4*>(a.h_packed + idx) = pk;
+    *reinterpret_cast<uint4*>(a.h_packed + idx) = make_uint4(bf2(y[0], y[1]), bf2(y[2], y[3]), bf2(y[4], y[5]), bf2(y[6], y[7]));
+  }
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// GRU gates (common.py:69-81) on the fp32 pre-activations of the split-row GRU contraction: one warp per row, a lane
+// owns the float4 column groups lane, lane + 32, ...; two groups (eight streaming 16-byte loads) are in flight per lane
+// before the row statistics are reduced.  HBM-bound: 3·4 + 4 B read, 4 + 2 B written per hidden unit.
+__global__ void __launch_bounds__(256) gru_gate_kernel(const GruArgs a) {
+  const int D = a.D;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = static_cast<int>((gridDim.x * blockDim.x) >> 5);
+  const int quads = a.kpad >> 2;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int m = warp0; m < a.m_pad; m += nwarps) {
+    const bool row_ok = m < a.M;
+    const float* src = a.scratch + static_cast<size_t>(m) * a.ld;
+    const float* hp = a.h_prev + static_cast<size_t>(m) * a.ld_h;
+    float* hn = a.h_next + static_cast<size_t>(m) * a.ld_hn;
+    float mean = 0.f, rstd = 1.f;
+    for (int qb = 0; qb < quads; qb += 64) {
+      float4 pr[2], pc[2], pu[2], hv[2];
+      bool ok[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = (qb + 32 * i + lane) << 2;
+        ok[i] = row_ok && c < D;
+        pr[i] = pc[i] = pu[i] = hv[i] = zero4;
+        if (ok[i]) {
+          pr[i] = *reinterpret_cast<const float4*>(src + c);
+          pc[i] = *reinterpret_cast<const float4*>(src + D + c);
+          pu[i] = *reinterpret_cast<const float4*>(src + 2 * D + c);
+          hv[i] = *reinterpret_cast<const float4*>(hp + c);
+        }
+      }
+      if (qb == 0 && row_ok) row_stats_warp(a.stats, a.NB, a.m_pad, m, 3 * D, a.eps, mean, rstd);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = qb + 32 * i + lane;
+        if (q >= quads) continue;
+        const int c = q << 2;
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ok[i]) {
+          const float4 gr = ldg4(a.gamma + c), gc = ldg4(a.gamma + D + c), gu = ldg4(a.gamma + 2 * D + c);
+          const float4 br = ldg4(a.beta + c), bc = ldg4(a.beta + D + c), bu = ldg4(a.beta + 2 * D + c);
+          const float vr[4] = {pr[i].x, pr[i].y, pr[i].z, pr[i].w}, vc[4] = {pc[i].x, pc[i].y, pc[i].z, pc[i].w};
+          const float vu[4] = {pu[i].x, pu[i].y, pu[i].z, pu[i].w}, vh[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
+          const float wgr[4] = {gr.x, gr.y, gr.z, gr.w}, wgc[4] = {gc.x, gc.y, gc.z, gc.w}, wgu[4] = {gu.x, gu.y, gu.z, gu.w};
+          const float wbr[4] = {br.x, br.y, br.z, br.w}, wbc[4] = {bc.x, bc.y, bc.z, bc.w}, wbu[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float r = fast_sigmoid((vr[j] - mean) * rstd * wgr[j] + wbr[j]);
+            const float cand = fast_tanh(r * ((vc[j] - mean) * rstd * wgc[j] + wbc[j]));
+            const float u = fast_sigmoid((vu[j] - mean) * rstd * wgu[j] + wbu[j] + a.update_bias);
+            y[j] = u * cand + (1.0f - u) * vh[j];
+          }
+          *reinterpret_cast<float4*>(hn + c) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+        const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c), static_cast<size_t>(a.kpad), kTileM);
+        *reinterpret_cast<uint2*>(a.h_packed + idx) = make_uint2(bf2(y[0], y[1]), bf2(y[2], y[3]));
+      }
+    }
   }
 }
 
@@ -315,17 +411,38 @@ struct SampleLatentArgs {
   long long ld_f32;
 };
 
-__global__ void sample_latent_kernel(const SampleLatentArgs a) {
-  const long long total = static_cast<long long>(a.M) * a.groups;
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int m = static_cast<int>(i / a.groups);
-  const int g = static_cast<int>(i - static_cast<long long>(m) * a.groups);
+// Fast standard Gumbel for the screening pass of sample_latent_kernel.  |result - rlsb_gumbel(u)| < 2e-5 for every
+// representable u: -log(u) by MUFU.LG2 (abs. error 2^-21.4 on [0.5, 1)) where it is >= 0.03, by its series in
+// d = 1 - u (exact subtraction; truncation < 2e-10 relative) closer to 1; the outer log is MUFU.LG2 again
+// (arguments are never subnormal: u >= 1e-20, -log(u) >= 5.9e-8).
+__device__ __forceinline__ float fast_gumbel(float u) {
+  u = rlsb_clamp_uniform(u);
+  const float d = 1.0f - u;
+  float t = -0.6931471805599453f * lg2_approx(u);
+  const float ser = d * fmaf(d, fmaf(d, fmaf(d, fmaf(d, fmaf(d, 0.16666667f, 0.2f), 0.25f), 0.33333334f), 0.5f), 1.0f);
+  t = u > 0.96875f ? ser : t;
+  return -0.6931471805599453f * lg2_approx(t);
+}
+
+// order-preserving float -> uint32 key whose low 5 bits carry (31 - class): one unsigned max then finds the largest
+// score AND, among scores equal in the upper 27 bits, the lowest class.  Dropping 5 mantissa bits moves a score by at
+// most 32 ulp (3.8e-6 relative), which the screening margin covers.
+__device__ __forceinline__ uint32_t score_key(float s, int k) {
+  const uint32_t b = __float_as_uint(s);
+  const uint32_t o = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+  return (o & ~31u) | static_cast<uint32_t>(31 - k);
+}
+__device__ __forceinline__ float key_score(uint32_t key) {
+  const uint32_t o = key & ~31u;
+  return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// the reference-order draw of one (row, group): argmax_k fl(logit_k + G(u_k)), lowest index on ties; G is the
+// bit-reproducible Gumbel transform the C oracle restates (rlsb_detmath.h)
+__device__ __noinline__ int sample_group_exact(const SampleLatentArgs& a, int m, int g, uint64_t key) {
   const float4* lp = reinterpret_cast<const float4*>(a.logits + static_cast<size_t>(m) * a.ld + g * 32);
-  const uint64_t key = a.noise.seed_ptr ? __ldg(a.noise.seed_ptr) : a.noise.seed;
   float best = 0.f;
   int best_k = 0;
-#pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 l4 = __ldg(lp + q);
     float u[4];
@@ -352,31 +469,90 @@ __global__ void sample_latent_kernel(const SampleLatentArgs a) {
       }
     }
   }
-  a.idx_out[static_cast<size_t>(m) * a.groups + g] = static_cast<uint8_t>(best_k);
-  if (a.onehot_packed) {
-    // group g occupies columns [32g, 32g+32): 4 chunks of 8 bf16
-    const int c0 = g * 32;
+  return best_k;
+}
+
+// Latent sampling, classes == 32.  Eight lanes share one (row, group): a lane holds four classes (one float4 of
+// logits, one Philox block of uniforms), so a warp instruction reads 512 contiguous bytes.  Screening pass: the
+// Gumbel-max with fast_gumbel and a top-2 butterfly over the eight lanes; the winner is final when it leads the
+// runner-up by more than the worst-case difference between the fast and the bit-reproducible scores (2 x 2.5e-5 +
+// one rounding of the sum).  Otherwise (about 1 group in 10^4, and whenever a score is NaN / infinite) the group is
+// redrawn in the reference order with the bit-reproducible transform — the indices are those of the oracle, always.
+__global__ void __launch_bounds__(256, 4) sample_latent_kernel(const SampleLatentArgs a) {
+  const long long total = static_cast<long long>(a.M) * a.groups;
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const uint64_t key = a.noise.seed_ptr ? __ldg(a.noise.seed_ptr) : a.noise.seed;
+  const int gshift = (a.groups & (a.groups - 1)) == 0 ? __ffs(a.groups) - 1 : -1;
+  const long long iters = (total + 3) >> 2;
+  for (long long it = warp0; it < iters; it += nwarps) {
+    long long item = it * 4 + (lane >> 3);
+    const bool live = item < total;
+    if (!live) item = total - 1;
+    int m, g;
+    if (gshift >= 0) {
+      m = static_cast<int>(item >> gshift);
+      g = static_cast<int>(item) & (a.groups - 1);
+    } else {
+      m = static_cast<int>(item / a.groups);
+      g = static_cast<int>(item - static_cast<long long>(m) * a.groups);
+    }
+    const float4 l4 = __ldg(reinterpret_cast<const float4*>(a.logits + static_cast<size_t>(m) * a.ld + g * 32) + q);
+    float u[4];
+    if (a.noise.explicit_noise) {
+      const float4 u4 = __ldg(reinterpret_cast<const float4*>(a.noise.explicit_noise +
+                                                              static_cast<size_t>(m) * a.noise.ld + g * 32) + q);
+      u[0] = u4.x; u[1] = u4.y; u[2] = u4.z; u[3] = u4.w;
+    } else {
+      uint32_t o[4];
+      rlsb_philox4x32(a.noise.row_offset + static_cast<uint32_t>(m), a.noise.step, 0u,
+                      static_cast<uint32_t>(g * 8 + q), static_cast<uint32_t>(key),
+                      static_cast<uint32_t>(key >> 32), o);
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
+      for (int t = 0; t < 4; ++t) u[t] = rlsb_u32_to_uniform(o[t]);
+    }
+    const float sc[4] = {l4.x + fast_gumbel(u[0]), l4.y + fast_gumbel(u[1]), l4.z + fast_gumbel(u[2]),
+                         l4.w + fast_gumbel(u[3])};
+    // a NaN / infinite score anywhere in the group: let the reference-order draw decide
+    const bool odd = !(fabsf((sc[0] + sc[1]) + (sc[2] + sc[3])) < 3.0e38f);
+    const uint32_t k0 = score_key(sc[0], q * 4), k1 = score_key(sc[1], q * 4 + 1), k2 = score_key(sc[2], q * 4 + 2),
+                   k3 = score_key(sc[3], q * 4 + 3);
+    const uint32_t hi01 = max(k0, k1), lo01 = min(k0, k1), hi23 = max(k2, k3), lo23 = min(k2, k3);
+    uint32_t b1 = max(hi01, hi23);                                  // largest key of the lane
+    uint32_t b2 = max(min(hi01, hi23), hi01 > hi23 ? lo01 : lo23);  // second largest
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const uint32_t ob1 = __shfl_xor_sync(0xffffffffu, b1, o);
+      const uint32_t ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
+      b2 = max(min(b1, ob1), max(b2, ob2));
+      b1 = max(b1, ob1);
+    }
+    const unsigned oddmask = __ballot_sync(0xffffffffu, odd);
+    const bool group_odd = ((oddmask >> (lane & 24)) & 0xffu) != 0u;
+    const float f1 = key_score(b1), f2 = key_score(b2);
+    const float margin = 1.0e-4f + 8.0e-6f * fabsf(f1);
+    const bool unsure = group_odd || !(f1 - f2 > margin);
+    const int i1 = 31 - static_cast<int>(b1 & 31u);
+    int best_k = i1;
+    if (unsure && q == 0) best_k = sample_group_exact(a, m, g, key);
+    best_k = __shfl_sync(0xffffffffu, best_k, lane & 24);
+    if (!live) continue;
+    if (q == 0) a.idx_out[static_cast<size_t>(m) * a.groups + g] = static_cast<uint8_t>(best_k);
+    if (a.onehot_packed && q < 4) {
+      // group g occupies columns [32g, 32g+32): 4 chunks of 8 bf16, one per lane q = 0..3
       uint32_t w[4] = {0u, 0u, 0u, 0u};
-      const int rel = best_k - ch * 8;
+      const int rel = best_k - q * 8;
       if (rel >= 0 && rel < 8) w[rel >> 1] = (rel & 1) ? 0x3F800000u : 0x00003F80u;  // bf16 1.0
-      const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(c0 + ch * 8),
+      const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(g * 32 + q * 8),
                                       static_cast<size_t>(a.kpad), kTileM);
       *reinterpret_cast<uint4*>(a.onehot_packed + idx) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-  }
-  if (a.onehot_f32) {
-    float4* op = reinterpret_cast<float4*>(a.onehot_f32 + static_cast<size_t>(m) * a.ld_f32 + g * 32);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.onehot_f32) {
       const int rel = best_k - q * 4;
-      if (rel == 0) o.x = 1.f;
-      if (rel == 1) o.y = 1.f;
-      if (rel == 2) o.z = 1.f;
-      if (rel == 3) o.w = 1.f;
-      op[q] = o;
+      reinterpret_cast<float4*>(a.onehot_f32 + static_cast<size_t>(m) * a.ld_f32 + g * 32)[q] =
+          make_float4(rel == 0 ? 1.f : 0.f, rel == 1 ? 1.f : 0.f, rel == 2 ? 1.f : 0.f, rel == 3 ? 1.f : 0.f);
     }
   }
 }
@@ -701,8 +877,9 @@ int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB
                   int m_pad, int N, const float* gamma, const float* beta, float eps, int act,
                   __nv_bfloat16* out, int out_kpad, cudaStream_t stream) {
   LnActArgs a{scratch, ld, stats, NB, RB, M, m_pad, N, gamma, beta, eps, act, out, out_kpad};
-  const long long total = static_cast<long long>(m_pad) * ((out_kpad / 8 + 31) / 32) * 32;
-  ln_act_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
+  // one warp per row; small row counts still spread over every SM (one warp per block)
+  const int block = m_pad >= 148 * 8 ? 256 : 32;
+  ln_act_kernel<<<grid_for(static_cast<long long>(m_pad) * 32, block, 148 * 8), block, 0, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -713,8 +890,17 @@ int launch_gru_gate(const float* scratch, long long ld, const float* stats, int 
                     long long ld_hn, __nv_bfloat16* h_next_packed, int kpad, cudaStream_t stream) {
   GruArgs a{scratch, ld, stats, NB, RB, M, m_pad, D, gamma, beta, eps, update_bias,
             h_prev, ld_h, h_next, ld_hn, h_next_packed, kpad};
-  const long long total = static_cast<long long>(m_pad) * ((kpad / 8 + 31) / 32) * 32;
-  gru_gate_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
+  const bool vec = ((ld & 3) == 0) && ((D & 3) == 0) && ((ld_h & 3) == 0) && ((ld_hn & 3) == 0) &&
+                   (((reinterpret_cast<uintptr_t>(scratch) | reinterpret_cast<uintptr_t>(h_prev) |
+                      reinterpret_cast<uintptr_t>(h_next) | reinterpret_cast<uintptr_t>(gamma) |
+                      reinterpret_cast<uintptr_t>(beta)) & 15) == 0);
+  if (vec) {
+    const int block = m_pad >= 148 * 8 ? 256 : 32;
+    gru_gate_kernel<<<grid_for(static_cast<long long>(m_pad) * 32, block, 148 * 8), block, 0, stream>>>(a);
+  } else {
+    const long long total = static_cast<long long>(m_pad) * ((kpad / 8 + 31) / 32) * 32;
+    gru_gate_kernel_generic<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
+  }
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -725,8 +911,11 @@ int launch_sample_latent(const float* logits, long long ld, int M, int groups, i
   if (classes != 32) return -1;
   SampleLatentArgs a{logits, ld, M, groups, noise, idx_out, onehot_packed, kpad, onehot_f32, ld_f32};
   const long long total = static_cast<long long>(M) * groups;
-  const int block = 128;
-  sample_latent_kernel<<<static_cast<unsigned>((total + block - 1) / block), block, 0, stream>>>(a);
+  if (total <= 0) return 0;
+  // eight lanes per (row, group): four groups per warp iteration
+  const long long warps = (total + 3) / 4;
+  const int block = warps >= 148 * 8 ? 256 : 32;
+  sample_latent_kernel<<<grid_for(warps * 32, block, 148 * 64), block, 0, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

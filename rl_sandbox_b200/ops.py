@@ -116,6 +116,26 @@ def sample_categorical(logits: torch.Tensor, uniforms: torch.Tensor) -> torch.Te
     return idx
 
 
+def sample_latent(logits: torch.Tensor, uniforms: Optional[torch.Tensor] = None, seed: int = 0, row_offset: int = 0,
+                  step: int = 0, want_onehot: bool = False):
+    """The rollout's latent draw on its own (rssm.py:34-37): logits (rows, groups, 32) -> uint8 indices (rows, groups)
+    [, fp32 one-hot (rows, groups*32)].  uniforms=None draws Philox noise exactly as K1 does."""
+    _lib.require_device()
+    lib = _lib.load()
+    logits = _f32c(logits)
+    rows, groups, classes = logits.shape
+    assert classes == 32
+    if uniforms is not None:
+        uniforms = _f32c(uniforms)
+        assert uniforms.numel() == logits.numel()
+    idx = torch.empty((rows, groups), device=logits.device, dtype=torch.uint8)
+    onehot = torch.empty((rows, groups * 32), device=logits.device) if want_onehot else None
+    check(lib.rlsb_sample_latent(logits.data_ptr(), rows, groups, uniforms.data_ptr() if uniforms is not None else None,
+                                 seed, row_offset, step, idx.data_ptr(), onehot.data_ptr() if want_onehot else None,
+                                 _stream()), "rlsb_sample_latent")
+    return (idx, onehot) if want_onehot else idx
+
+
 def philox_uniform(seed: int, n0: int, t: int, stream_id: int, per_row: int, rows: int,
                    device="cuda") -> torch.Tensor:
     _lib.require_device()
@@ -628,8 +648,9 @@ class ObserveEngine:
         self._keep = keep
 
     def forward(self, embed: torch.Tensor, actions: torch.Tensor, latent_uniforms: Optional[torch.Tensor] = None,
-                seed: int = 0, row_offset: int = 0):
-        """embed (T, B, E), actions (T, B, A) -> dict(prior_logits, post_logits, determ, stoch_idx, stoch, tape)"""
+                seed: int = 0, row_offset: int = 0, seed_device: Optional[torch.Tensor] = None):
+        """embed (T, B, E), actions (T, B, A) -> dict(prior_logits, post_logits, determ, stoch_idx, stoch, tape).
+        seed_device: int64 device tensor holding the Philox key (read by the kernels; lets a CUDA graph change it)."""
         embed, actions = _f32c(embed), _f32c(actions)
         T, B = embed.shape[0], embed.shape[1]
         if T != self.T or embed.shape[2] != self.E or actions.shape != (T, B, self.A):
@@ -642,7 +663,8 @@ class ObserveEngine:
         # zero-initialised: slot 0 of the state images is the zero initial state, padding rows enter weight gradients
         out["tape"] = torch.zeros(self.lib.rlsb_observe_tape_bytes(C.byref(self.cfg), B), device=dev, dtype=torch.uint8)
         co = _lib.ObserveOut(*[out[k].data_ptr() for k in ("prior_logits", "post_logits", "determ", "stoch_idx", "stoch")])
-        nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)), None, seed, row_offset, None, None)
+        nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)), None, seed, row_offset, None,
+                   None if seed_device is None else seed_device.data_ptr())
         check(self.lib.rlsb_observe_fwd(C.byref(self.cfg), self.packed.data_ptr(), B, embed.data_ptr(), actions.data_ptr(),
                                         C.byref(nz), C.byref(co), out["tape"].data_ptr(), _stream()), "rlsb_observe_fwd")
         return out

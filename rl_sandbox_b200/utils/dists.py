@@ -50,7 +50,7 @@ class DistLayer(nn.Module):
         if self._dist == 'onehot':
             return td.OneHotCategoricalStraightThrough(logits=x.float(), validate_args=False)
         if self._dist == 'mse':
-            base = td.Normal(x.float(), 1.0, validate_args=False)
+            base = td.Normal(x.float(), torch.ones((), device=x.device), validate_args=False)
         elif self._dist == 'binary':
             base = td.Bernoulli(logits=x.float(), validate_args=False)  # targets are gamma*(1-done), not {0,1}
         else:

@@ -116,6 +116,54 @@ def test_train_step_end_to_end(cuda):
     assert st.determ.shape == (4, 1, 200) and rew.shape == (4, 1, 1)
 
 
+def test_world_model_update_graph_replay_matches_eager(cuda):
+    """The world-model half of train() replayed from a CUDA graph (forward + backward captured; clip + AdamW eager)
+    is the eager computation: same Philox keys for the observe scan -> same losses and gradients on the first step,
+    the same parameters after it, and the same loss trajectory over the following steps."""
+    from rl_sandbox.utils.replay_buffer import RolloutChunks
+    import numpy as np
+    m = dict(D=200, A=5, discrete=True, layer_norm=True, predict_discount=True, entropy_scale=3e-3, gamma=0.999, H=5)
+    B, T = 3, 6
+    g = torch.Generator().manual_seed(5)
+    obs = (torch.randint(0, 255, (B * T, 64, 64, 3), dtype=torch.uint8, generator=g).float() / 255 - 0.5).permute(0, 3, 1, 2).cuda()
+    first = torch.zeros(B * T)
+    first[::T] = 1
+    chunks = RolloutChunks(obs=obs, actions=torch.randint(0, 5, (B * T, 1), generator=g).cuda(),
+                           rewards=torch.randn(B * T, generator=g).cuda(), is_finished=torch.zeros(B * T).cuda(),
+                           is_first=first.cuda(), additional_data={})
+    runs = {}
+    for graphed in (True, False):
+        torch.manual_seed(0)
+        agent = make_agent(m, "cuda", batch_cluster_size=T)
+        agent.cuda_graph_wm = graphed
+        p_init = torch.cat([p.detach().flatten() for p in agent.world_model.parameters()]).clone()
+        out0 = agent.train(chunks)
+        grads = {n: p.grad.detach().clone() for n, p in agent.world_model.named_parameters() if p.grad is not None}
+        params = torch.cat([p.detach().flatten() for p in agent.world_model.parameters()]).clone()
+        outs = [out0] + [agent.train(chunks) for _ in range(4)]
+        assert bool(agent._wm_graphs) == graphed
+        assert all(np.isfinite(v).all() for o in outs for v in o.values())
+        runs[graphed] = (outs, grads, params)
+    (og, gg, pg), (oe, ge, pe) = runs[True], runs[False]
+    for k in ("loss_wm", "loss_reconstruction", "loss_reward_pred", "loss_kl_reg", "loss_discount_pred"):
+        a, b = float(og[0][k]), float(oe[0][k])
+        print(f"[parity] wm graph vs eager, step 1 {k}: {a:.6f} vs {b:.6f}")
+        assert abs(a - b) <= 1e-4 * abs(b) + 1e-5, k
+    assert set(gg) == set(ge)
+    worst = max(((gg[n] - ge[n]).norm() / (ge[n].norm() + 1e-12)).item() for n in ge)
+    print(f"[parity] wm graph vs eager, step 1 gradients: worst rel-L2 over {len(ge)} tensors {worst:.3e}")
+    assert worst < 1e-2   # cuDNN / float-atomics reduction order only
+    cos = torch.nn.functional.cosine_similarity(pg - p_init, pe - p_init, dim=0).item()
+    print(f"[parity] wm graph vs eager, step 1 parameter displacement: cos {cos:.5f}")
+    assert cos > 0.98 and (pg - pe).abs().max().item() <= 2.1e-4   # one AdamW step of lr 1e-4
+    for k in ("loss_wm", "loss_kl_reg"):
+        a = np.array([float(o[k]) for o in og])
+        b = np.array([float(o[k]) for o in oe])
+        print(f"[parity] wm graph vs eager {k}: {a.round(4).tolist()} vs {b.round(4).tolist()}")
+        assert np.all(np.abs(a - b) <= 0.02 * np.abs(b)), k
+    assert float(og[-1]["loss_wm"]) < float(og[0]["loss_wm"])
+
+
 def test_train_step_continuous_actor_runs_fused(cuda):
     """config_dino-shaped agent (continuous actions, rho = 0): train() drives K1 (+tape) -> K2 -> K2 bwd -> K1 bwd -> K4;
     no torch autograd on the behaviour half.  Gradient parity is in test_gpu_ac_update.py."""

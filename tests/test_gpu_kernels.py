@@ -117,6 +117,61 @@ def test_sampler_edge_uniforms_and_ties(ops, cuda):
     assert same.tolist() == [0] * 5  # ties -> lowest index, like torch.argmax
 
 
+def test_latent_sampler_bit_exact(ops, cuda):
+    """The rollout's own latent draw (fast screening pass + reference-order redraw of unsure groups) gives the oracle's
+    indices, bit for bit: random logits, explicit uniforms and Philox noise, ragged row counts, groups not a power of 2."""
+    g = torch.Generator().manual_seed(12)
+    for rows, groups, scale in [(20000, 32, 3.0), (4097, 32, 0.05), (333, 5, 10.0), (1, 32, 1.0), (129, 64, 1.0)]:
+        logits = torch.randn(rows, groups, 32, generator=g) * scale
+        un = torch.rand(rows, groups, 32, generator=g)
+        idx, onehot = ops.sample_latent(logits.to(cuda), un.to(cuda), want_onehot=True)
+        want = orc.sample_categorical(logits, un)
+        assert torch.equal(idx.cpu().long(), want)
+        assert torch.equal(onehot.cpu().view(rows, groups, 32).argmax(-1), want)
+        assert torch.equal(onehot.cpu().sum(), torch.tensor(float(rows * groups)))
+    rows, groups = 5000, 32
+    logits = torch.randn(rows, groups, 32, generator=g)
+    idx = ops.sample_latent(logits.to(cuda), None, seed=2 ** 41 + 77, row_offset=123456, step=9)
+    un = torch.from_numpy(orc.philox_uniform(2 ** 41 + 77, 123456, 9, 0, groups * 32, rows)).view(rows, groups, 32)
+    assert torch.equal(idx.cpu().long(), orc.sample_categorical(logits, un))
+
+
+def test_latent_sampler_near_ties_take_the_exact_path(ops, cuda):
+    """Scores engineered so that the runner-up sits within a few ulp of the winner (below the screening pass's error):
+    only the bit-reproducible redraw can order them; plus exact ties, edge uniforms and non-finite logits."""
+    g = torch.Generator().manual_seed(13)
+    rows, groups = 3000, 32
+    logits = torch.randn(rows, groups, 32, generator=g) * 2
+    un = torch.rand(rows, groups, 32, generator=g)
+    gum = orc.gumbel(un).view(rows, groups, 32)
+    score = logits + gum
+    best = score.max(-1, keepdim=True).values
+    j = torch.randint(0, 32, (rows, groups, 1), generator=g)
+    ulps = torch.randint(-3, 4, (rows, groups, 1), generator=g).float()
+    target = best + ulps * torch.finfo(torch.float32).eps * best.abs()
+    logits.scatter_(-1, j, target - gum.gather(-1, j))       # class j now scores within 3 ulp of the winner
+    want = orc.sample_categorical(logits, un)
+    got = ops.sample_latent(logits.to(cuda), un.to(cuda)).cpu().long()
+    assert torch.equal(got, want)
+    frac = (want == j.squeeze(-1)).float().mean().item()
+    assert 0.2 < frac < 0.9   # the planted class wins some and loses some: the order really is decided at ulp level
+    # exact ties -> lowest index; edge uniforms; -inf / +inf / NaN logits follow the reference-order scan
+    lg = torch.zeros(4, 32, 32)
+    u2 = torch.full((4, 32, 32), 0.25)
+    u2[1, :, 5] = 0.0
+    u2[1, :, 9] = 1.0
+    u2[2, :, 3] = 0.99999994
+    u2[2, :, 30] = 0.99999994
+    u2[3] = torch.rand(32, 32, generator=g)
+    lg[3, :, 4] = float("-inf")
+    lg[3, 1, 7] = float("inf")
+    lg[3, 2, 0] = float("nan")
+    lg[3, 3, 11] = float("nan")
+    got = ops.sample_latent(lg.to(cuda), u2.to(cuda)).cpu().long()
+    assert torch.equal(got, orc.sample_categorical(lg, u2))
+    assert got[0].tolist() == [0] * 32
+
+
 def test_philox_bit_exact(ops, cuda):
     for seed, n0, t, stream, per_row, rows in [(0, 0, 0, 0, 1024, 64), (2 ** 40 + 12345, 1000000, 14, 1, 17, 300)]:
         u = ops.philox_uniform(seed, n0, t, stream, per_row, rows).cpu().numpy()
