@@ -41,7 +41,9 @@ class Normalizer(nn.Module):
         self.register_buffer('mag', torch.ones(1, dtype=torch.float32))
 
     def update(self, x):
-        self.mag = self.momentum * self.mag + (1 - self.momentum) * x.abs().mean().detach()
+        # in place: the buffer keeps its address (a CUDA-graph replay of the caller reads and writes this tensor)
+        with torch.no_grad():
+            self.mag.mul_(self.momentum).add_((1 - self.momentum) * x.abs().mean())
 
     def forward(self, x):
         self.update(x)

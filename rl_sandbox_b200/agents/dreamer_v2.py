@@ -252,6 +252,22 @@ class DreamerV2(RlAgent):
         from rl_sandbox_b200 import ops
         if self._can_fuse_ac():
             return self._behaviour_update_fused(initial_states, noise)
+        # torch-replay rollouts only (rho != 1): their noise comes from torch's graph-safe generator
+        graphable = (self.cuda_graph_wm and noise is None and not self.is_f16 and initial_states.determ.is_cuda
+                     and torch.is_grad_enabled() and self.actor.rho != 1.0)
+        if graphable:
+            return self._behaviour_update_graphed_torch(initial_states)
+        losses_a, losses_c, metrics_a, metrics_c = self._behaviour_losses(initial_states, noise)
+        metrics_a |= self.actor_optimizer.step(losses_a['loss_actor'])
+        metrics_c |= self.critic_optimizer.step(losses_c['loss_critic'])
+        self.critic.update_target()
+        self.mark_weights_changed()
+        return losses_a | losses_c, metrics_a | metrics_c
+
+    def _behaviour_losses(self, initial_states: State, noise: t.Optional[dict] = None):
+        """imagination -> lambda-return -> critic / actor losses under torch autograd (dreamer_v2.py:179-207): the path of
+        configurations the fused update does not cover (slotted world model, D > 512 with a continuous actor)."""
+        from rl_sandbox_b200 import ops
         with torch.autocast(device_type='cuda', enabled=self.is_f16):
             no_grad_rollout = self.actor.rho == 1.0
             with (torch.no_grad() if no_grad_rollout else torch.enable_grad()):
@@ -273,11 +289,70 @@ class DreamerV2(RlAgent):
             losses_c, metrics_c = self.critic.calculate_loss(zs[:-1], vs, w[:-1], target_values=values[:-1])
             losses_a, metrics_a = self.actor.calculate_loss(zs[:-2], vs[1:], values[:-2].detach(), w[:-2],
                                                             actions[1:-1], metrics_samples=self.metrics_samples)
-        metrics_a |= self.actor_optimizer.step(losses_a['loss_actor'])
-        metrics_c |= self.critic_optimizer.step(losses_c['loss_critic'])
+        return losses_a, losses_c, metrics_a, metrics_c
+
+    def _behaviour_update_graphed_torch(self, initial_states: State):
+        """``_behaviour_losses`` + both backward passes replayed from a CUDA graph (static start states; the gradients of
+        loss_actor w.r.t. the actor and of loss_critic w.r.t. the critic land in static buffers); all-reduce, clipping,
+        AdamW and the target update run eagerly after the replay."""
+        import dataclasses
+        import torch.distributions as td
+        from torch.nn.utils.stateless import _reparametrize_module
+        fields = {f.name: getattr(initial_states, f.name) for f in dataclasses.fields(initial_states)}
+        tens = {k: v for k, v in fields.items() if torch.is_tensor(v)}
+        key = (type(initial_states).__name__,) + tuple((k, tuple(v.shape), v.dtype) for k, v in tens.items()) + (
+            self.metrics_samples, float(getattr(getattr(self.world_model.recurrent_model, 'attention_scheduler', None), 'val', 0.0)))
+        st = self._wm_graphs.get(key)
+        named_a = [(n, p) for n, p in self.actor.named_parameters() if p.requires_grad]
+        named_c = [(n, p) for n, p in self.critic.named_parameters() if p.requires_grad]
+
+        def body(static):
+            state = type(initial_states)(**{k: static.get(k, v) for k, v in fields.items()})
+            la = {n: p.detach().requires_grad_(True) for n, p in named_a}   # see _world_model_update_graphed
+            lc = {n: p.detach().requires_grad_(True) for n, p in named_c}
+            with _reparametrize_module(self.actor, la), _reparametrize_module(self.critic, lc):
+                losses_a, losses_c, metrics_a, metrics_c = self._behaviour_losses(state, None)
+            ga = torch.autograd.grad(losses_a['loss_actor'], list(la.values()), allow_unused=True, retain_graph=True)
+            gc = torch.autograd.grad(losses_c['loss_critic'], list(lc.values()), allow_unused=True)
+            return losses_a | losses_c, metrics_a | metrics_c, ga, gc
+
+        if st is None:
+            st = {'in': {k: v.detach().clone() for k, v in tens.items()}}
+            validate = td.Distribution._validate_args
+            td.Distribution.set_default_validate_args(False)
+            rollouts0 = self._rollouts
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        body(st['in'])
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                lib = _lib_handle()
+                before = lib.rlsb_launch_count(0)
+                with torch.cuda.graph(graph):
+                    st['out'] = body(st['in'])
+                st['launches'] = lib.rlsb_launch_count(0) - before
+                lib.rlsb_launch_count_add(-st['launches'])
+            finally:
+                td.Distribution.set_default_validate_args(validate)
+                self._rollouts = rollouts0
+            st['graph'] = graph
+            st['grads'] = [(p, g) for (_, p), g in zip(named_a, st['out'][2])] + \
+                          [(p, g) for (_, p), g in zip(named_c, st['out'][3])]
+            self._wm_graphs[key] = st
+        for k, v in tens.items():
+            st['in'][k].copy_(v)
+        st['graph'].replay()
+        _lib_handle().rlsb_launch_count_add(st['launches'])
+        for p, gbuf in st['grads']:
+            p.grad = gbuf
+        losses, metrics, _, _ = st['out']
+        metrics = dict(metrics) | self.actor_optimizer.step_with_grads() | self.critic_optimizer.step_with_grads()
         self.critic.update_target()
         self.mark_weights_changed()
-        return losses_a | losses_c, metrics_a | metrics_c
+        return dict(losses), metrics
 
     def _behaviour_update_fused(self, initial_states: State, noise: t.Optional[dict]):
         """Discrete actor (rho == 1): K1 rollout keeping the packed state images -> K2 -> K4 (critic / actor

@@ -110,6 +110,23 @@ def test_slotted_agent_end_to_end(cuda):
     out = agent.train(chunks)
     assert all(np.isfinite(v).all() for v in out.values()), {k: v for k, v in out.items() if not np.isfinite(v).all()}
     assert out["loss_actor_dynamics_backprop"] != 0
+    # both halves of train() replay from CUDA graphs once the mixer schedule has settled (the first step is eager):
+    # losses stay finite, the world-model loss falls, actor and critic keep moving, and the graphed steps agree with
+    # eager ones on the same batch to within the step-to-step change
+    before = [p.detach().clone() for p in list(agent.actor.parameters()) + list(agent.critic.critic.parameters())]
+    outs = [agent.train(chunks) for _ in range(4)]
+    assert len(agent._wm_graphs) == 2, list(agent._wm_graphs)
+    assert all(np.isfinite(v).all() for o in outs for v in o.values())
+    assert float(outs[-1]["loss_wm"]) < float(out["loss_wm"])
+    after = list(agent.actor.parameters()) + list(agent.critic.critic.parameters())
+    assert all(not torch.equal(a, b.detach()) for a, b in zip(before, after))
+    agent.cuda_graph_wm = False
+    eager = agent.train(chunks)
+    for k in ("loss_wm", "loss_critic", "loss_actor_dynamics_backprop"):
+        a, b, c = float(outs[-2][k]), float(outs[-1][k]), float(eager[k])
+        print(f"[parity] slotted train() {k}: graphed {a:.5f}, {b:.5f} -> eager {c:.5f}")
+        assert abs(c - b) <= 3 * abs(b - a) + 0.05 * abs(b) + 1e-3, k
+    agent.cuda_graph_wm = True
     # K1 (slots = 4) behind the reference's method surface
     state, _ = agent.world_model.get_initial_state(batch_size=6)
     with torch.no_grad():
