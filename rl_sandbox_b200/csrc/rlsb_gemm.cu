@@ -145,26 +145,13 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
                                              uint32_t s_bias, uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
                                              __nv_bfloat16* obase, __nv_bfloat16* pbase, bool row_ok) {
   const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
-  for (int i0 = 0; i0 < my_chunks; i0 += 2) {
-    uint32_t r0[8], r1[8];
-    const int c0 = (cq + 4 * i0) * 8, c1 = c0 + 32;
-    const bool two = i0 + 1 < my_chunks;
-    tmem_ld8(tmem_d + static_cast<uint32_t>(c0), r0);
-    if (two) tmem_ld8(tmem_d + static_cast<uint32_t>(c1), r1);
-    tmem_ld_wait();
-    {
-      const int oc = col0 + c0;
-      const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
-      ln_act_chunk<ACT, LN, SAVE>(r0, c0, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, obase + off,
-                                  SAVE ? pbase + off : nullptr, row_ok);
-    }
-    if (two) {
-      const int oc = col0 + c1;
-      const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
-      ln_act_chunk<ACT, LN, SAVE>(r1, c1, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, obase + off,
-                                  SAVE ? pbase + off : nullptr, row_ok);
-    }
-  }
+  tmem_sweep(tmem_d, cq, my_chunks, [&](const uint32_t (&r)[8], int i) {
+    const int c = (cq + 4 * i) * 8;
+    const int oc = col0 + c;
+    const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
+    ln_act_chunk<ACT, LN, SAVE>(r, c, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, obase + off,
+                                SAVE ? pbase + off : nullptr, row_ok);
+  });
 }
 
 
@@ -621,16 +608,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             }
           }
         };
-        for (int i0 = 0; i0 < my_chunks; i0 += 2) {
-          uint32_t r0[8], r1[8];
-          const int c0 = (cq + 4 * i0) * 8, c1 = c0 + 32;
-          const bool two = i0 + 1 < my_chunks;
-          tmem_ld8(tmem_d + static_cast<uint32_t>(c0), r0);
-          if (two) tmem_ld8(tmem_d + static_cast<uint32_t>(c1), r1);
-          tmem_ld_wait();
-          pass1_chunk(r0, c0);
-          if (two) pass1_chunk(r1, c1);
-        }
+        tmem_sweep(tmem_d, cq, my_chunks, [&](const uint32_t (&r)[8], int i) { pass1_chunk(r, (cq + 4 * i) * 8); });
         {
           float s0, s1, q0, q1;
           unpk2(sum2, s0, s1);

@@ -262,6 +262,37 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same wait, with the destination registers of the loads it completes tied to it: nothing that reads them can be
+// scheduled above the wait while OTHER loads (issued after it, into other registers) are in flight
+__device__ __forceinline__ void tmem_ld_wait2(uint32_t (&a)[8], uint32_t (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                 "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+               :
+               : "memory");
+}
+// software-pipelined sweep over the 8-column chunks cq, cq + 4, ... of a thread's TMEM row: two chunks are processed
+// while the next two are in flight (the wait then finds its loads complete).  f(r, i) handles chunk index cq + 4 i.
+template <class F>
+__device__ __forceinline__ void tmem_sweep(uint32_t tmem_d, int cq, int n_chunks, F&& f) {
+  uint32_t a0[8] = {}, a1[8] = {}, b0[8] = {}, b1[8] = {};
+  auto issue = [&](int i, uint32_t (&x)[8], uint32_t (&y)[8]) {
+    if (i < n_chunks) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * i) * 8), x);
+    if (i + 1 < n_chunks) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * (i + 1)) * 8), y);
+  };
+  issue(0, a0, a1);
+  for (int i = 0; i < n_chunks; i += 4) {
+    tmem_ld_wait2(a0, a1);
+    issue(i + 2, b0, b1);
+    f(a0, i);
+    if (i + 1 < n_chunks) f(a1, i + 1);
+    if (i + 2 >= n_chunks) break;
+    tmem_ld_wait2(b0, b1);
+    issue(i + 4, a0, a1);
+    f(b0, i + 2);
+    if (i + 3 < n_chunks) f(b1, i + 3);
+  }
+}
 
 // ----------------------------------------------------------------------------------------
 // descriptors
