@@ -13,6 +13,8 @@
 // groups are 4 KB apart (LBO) and 8-row groups 1 KB apart (SBO).
 #include "rlsb_wgrad.cuh"
 
+#include <cstdlib>
+
 #include "rlsb_count.cuh"
 #include "rlsb_gemm.cuh"
 #include "rlsb_ptx.cuh"
@@ -34,7 +36,10 @@ struct WgCtl {
   uint32_t pad;
 };
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams p, const int stages) {
+// cs > 1: a cluster of cs CTAs works on cs consecutive n-slices of the same (group, k chunk, split).  They contract
+// the same X pieces, so CTA r fetches pieces r, r + cs, ... and multicasts them into every CTA of the cluster (the
+// dY pieces are private): the L2 -> SM traffic per 32-row stage drops from (2 + 8) to (2 + 8 / cs) pieces.
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams p, const int stages, const int cs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -45,9 +50,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
   const int items = p.G * p.n_slices * p.n_chunks;
   const int item = static_cast<int>(blockIdx.x) % items;
   const int split = static_cast<int>(blockIdx.x) / items;
-  const int kc = item % p.n_chunks;
-  const int ns = (item / p.n_chunks) % p.n_slices;
+  const int ns = item % p.n_slices;                      // n-slice fastest: the CTAs of a cluster differ in ns only
+  const int kc = (item / p.n_slices) % p.n_chunks;
   const int g = item / (p.n_chunks * p.n_slices);
+  const int rank = cs > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const uint16_t cta_mask = static_cast<uint16_t>((1u << cs) - 1u);
   const int m0 = static_cast<int>(static_cast<long long>(split) * p.m_tiles / p.splits);
   const int m1 = static_cast<int>(static_cast<long long>(split + 1) * p.m_tiles / p.splits);
   const int kt0 = kc * p.kc_tiles;
@@ -60,7 +67,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(&ctl->full[s], 1);
-        mbar_init(&ctl->empty[s], 1);
+        mbar_init(&ctl->empty[s], static_cast<uint32_t>(cs));   // every CTA of the cluster releases the slot
       }
       mbar_init(&ctl->tmem_full, 1);
       fence_mbar_init();
@@ -72,6 +79,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
@@ -103,8 +111,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
           for (int a = 0; a < na; ++a)
             bulk_g2s(sa + a * kPiece, ysrc + mt * ystride + static_cast<size_t>(a) * (kTileM * kTileK) + roff, kPiece,
                      &ctl->full[stage]);
-          for (int j = 0; j < nkt; ++j)
-            bulk_g2s(sa + (2 + j) * kPiece, xsrc[j] + mt * xstride[j] + roff, kPiece, &ctl->full[stage]);
+          if (cs == 1) {
+            for (int j = 0; j < nkt; ++j)
+              bulk_g2s(sa + (2 + j) * kPiece, xsrc[j] + mt * xstride[j] + roff, kPiece, &ctl->full[stage]);
+          } else {
+            for (int j = rank; j < nkt; j += cs)
+              bulk_g2s_multicast(sa + (2 + j) * kPiece, xsrc[j] + mt * xstride[j] + roff, kPiece, &ctl->full[stage],
+                                 cta_mask);
+          }
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -137,7 +151,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
             if (n1 > 0) umma_bf16(tmem_base + 256u, adesc + adv, bdesc1 + adv, idesc1, acc);
           }
           first = false;
-          umma_commit(&ctl->empty[stage]);
+          if (cs == 1) umma_commit(&ctl->empty[stage]);
+          else umma_commit_multicast(&ctl->empty[stage], cta_mask);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -173,6 +188,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // nobody leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -221,6 +237,19 @@ __global__ void colsum_reduce_kernel(const ColsumReduceParams p) {
 }
 
 int g_wg_sms = 0;
+int g_wg_cluster = 4;          // max CTAs per cluster (1, 2 or 4); RLSB_WGRAD_CLUSTER overrides
+int g_wg_max_ctas[5] = {0, 0, 0, 0, 0};   // co-resident CTAs for cluster size 1 / 2 / 4 (148 / 148 / 132 on B200)
+
+int wg_stage_bytes(const WgradParams& p) { return (2 + p.kc_tiles) * static_cast<int>(kPiece); }
+int wg_stages(const WgradParams& p) {
+  int stages = (227 * 1024 - 1024 - static_cast<int>(sizeof(WgCtl)) - 256) / wg_stage_bytes(p);
+  return stages > kWgMaxStages ? kWgMaxStages : stages;
+}
+int wg_cluster(const WgradParams& p) {
+  int cs = g_wg_cluster;
+  while (cs > 1 && (p.n_slices % cs) != 0) cs >>= 1;
+  return cs;
+}
 
 }  // namespace
 
@@ -232,6 +261,33 @@ int plan_wgrad(WgradParams& p) {
     if (e != cudaSuccess) return static_cast<int>(e);
     e = cudaDeviceGetAttribute(&g_wg_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return static_cast<int>(e);
+    if (const char* env = getenv("RLSB_WGRAD_CLUSTER")) {
+      const int v = atoi(env);
+      if (v == 1 || v == 2 || v == 4) g_wg_cluster = v;
+    }
+    g_wg_max_ctas[1] = g_wg_sms;
+    e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    for (int cs = 2; cs <= 4; cs *= 2) {   // how many clusters of this size the device holds at once
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(static_cast<unsigned>(g_wg_sms / cs * cs));
+      cfg.blockDim = dim3(kWgThreads);
+      cfg.dynamicSmemBytes = 200 * 1024;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = static_cast<unsigned>(cs);
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, wgrad_kernel, &cfg);
+      if (e != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = g_wg_sms / cs / 2;   // conservative
+      }
+      g_wg_max_ctas[cs] = n * cs;
+    }
   }
   p.kt_total = 0;
   for (int s = 0; s < p.n_seg; ++s) p.kt_total += p.x_ktiles[s];
@@ -240,7 +296,7 @@ int plan_wgrad(WgradParams& p) {
   p.n_chunks = (p.kt_total + p.kc_tiles - 1) / p.kc_tiles;
   p.n_slices = (p.n_tiles + 1) / 2;
   const int items = p.G * p.n_slices * p.n_chunks;
-  int splits = g_wg_sms / items;
+  int splits = g_wg_max_ctas[wg_cluster(p)] / items;   // one wave of co-resident CTAs (clusters)
   if (splits < 1) splits = 1;
   if (splits > p.m_tiles) splits = p.m_tiles;
   p.splits = splits;
@@ -253,20 +309,26 @@ size_t wgrad_partial_bytes(const WgradParams& p) {
 
 int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
   if (!p.dY || !p.partial || p.splits < 1 || p.kc_tiles < 1 || p.kc_tiles > 8) return -1;
-  const int stage_bytes = (2 + p.kc_tiles) * static_cast<int>(kPiece);
-  int stages = (227 * 1024 - 1024 - static_cast<int>(sizeof(WgCtl)) - 256) / stage_bytes;
-  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  const int stage_bytes = wg_stage_bytes(p);
+  const int stages = wg_stages(p);
   if (stages < 2) return -2;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + sizeof(WgCtl) + 1024;
-  static bool attr_done = false;
-  cudaError_t e;
-  if (!attr_done) {
-    e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_done = true;
-  }
+  const int cs = wg_cluster(p);
   const int grid = p.G * p.n_slices * p.n_chunks * p.splits;
-  wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(p, stages);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cs);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_kernel, p, stages, cs);
+  if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
