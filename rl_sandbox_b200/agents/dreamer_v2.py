@@ -80,6 +80,8 @@ class DreamerV2(RlAgent):
         # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
         # T sequential steps of small kernels — thousands of launches whose CPU dispatch cost exceeds their GPU time)
         self.cuda_graph_wm = True
+        self.cuda_graph_act = True    # get_action(): the batch-1 acting step replays from a CUDA graph (flat world model)
+        self._act_graph = None
         self._wm_graphs: dict = {}
         self._wm_sched_prev = None
         self._graphs: dict = {}
@@ -230,6 +232,8 @@ class DreamerV2(RlAgent):
         return ((obs + 0.5).clamp(0, 1) * 255).cpu().to(dtype=torch.uint8)
 
     def get_action(self, obs: Observation) -> Action:
+        if self.cuda_graph_act and self._flat_wm() and str(self.device).startswith('cuda') and not self.is_f16:
+            return self._get_action_graphed(obs)
         obs = self.preprocess_obs(torch.from_numpy(obs).to(self.device))
         self._state = self.world_model.get_latent(obs, self._last_action, self._state)
         dist = self.actor.get_action(self._state)
@@ -238,6 +242,70 @@ class DreamerV2(RlAgent):
             self._action_probs += dist.probs.squeeze()
             return self._last_action.argmax()
         return self._last_action.squeeze().detach().cpu()
+
+    def _get_action_graphed(self, obs: Observation) -> Action:
+        """The acting step (dreamer_v2.py:139-154: encoder on one frame, one RSSM observe step, actor, action draw)
+        replayed from a CUDA graph: ~60 batch-1 kernels whose launch cost dominates an eager call.  The recurrent state,
+        the previous action and the action statistics live in static buffers the graph updates in place."""
+        import torch.distributions as td
+        frame = torch.from_numpy(np.ascontiguousarray(obs))
+        st = self._act_graph
+        if st is None or st['obs'].shape != frame.shape or st['obs'].dtype != frame.dtype:
+            dev = self.device
+            init = self.world_model.get_initial_state()
+            st = {'obs': torch.zeros(frame.shape, dtype=frame.dtype, device=dev),
+                  'state': State(init.determ.clone(), init.stoch_logits.clone(), init.stoch.clone()),
+                  'action': torch.zeros((1, 1, self.actions_num), device=dev),
+                  'probs': torch.zeros((self.actions_num), device=dev)}
+
+            def body():
+                x = self.preprocess_obs(st['obs'])
+                new = self.world_model.get_latent(x, st['action'], st['state'])
+                dist = self.actor.get_action(new)
+                a = dist.sample()
+                st['state'].determ.copy_(new.determ)
+                st['state'].stoch_logits.copy_(new.stoch_logits)
+                st['state'].stoch_.copy_(new.stoch)
+                st['action'].copy_(a.reshape(st['action'].shape))
+                if self.is_discrete:
+                    st['probs'].add_(dist.probs.reshape(-1))
+                    return a.argmax()
+                return a.reshape(-1).clone()
+
+            validate = td.Distribution._validate_args
+            td.Distribution.set_default_validate_args(False)
+            try:
+                with torch.no_grad():
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            body()
+                    torch.cuda.current_stream().wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        st['out'] = body()
+            finally:
+                td.Distribution.set_default_validate_args(validate)
+            st['graph'] = graph
+            self._act_graph = st   # self._state is not the static State yet: the block below loads it (the warm-up
+            #                        passes advanced the static buffers)
+        if self._state is not st['state']:   # reset() (or a state set from outside): load it into the static buffers
+            src = self._state if self._state is not None else self.world_model.get_initial_state()
+            with torch.no_grad():
+                st['state'].determ.copy_(src.determ)
+                st['state'].stoch_logits.copy_(src.stoch_logits)
+                st['state'].stoch_.copy_(src.stoch)
+                st['action'].copy_(self._last_action.reshape(st['action'].shape))
+                st['probs'].copy_(self._action_probs.reshape(-1))
+            self._state = st['state']
+        st['obs'].copy_(frame, non_blocking=False)
+        st['graph'].replay()
+        self._last_action = st['action']
+        self._action_probs = st['probs']
+        if self.is_discrete:
+            return st['out'].clone()
+        return st['out'].detach().cpu()
 
     def from_np(self, arr: np.ndarray):
         arr = torch.from_numpy(arr) if isinstance(arr, np.ndarray) else arr

@@ -164,6 +164,42 @@ def test_world_model_update_graph_replay_matches_eager(cuda):
     assert float(og[-1]["loss_wm"]) < float(og[0]["loss_wm"])
 
 
+def test_acting_path_graph_replay(cuda):
+    """get_action(): the batch-1 acting step replayed from a CUDA graph follows the eager op sequence — the first step
+    after reset() (zero state, zero action: no randomness upstream of the posterior logits) gives the same recurrent
+    state; actions stay valid, reset() reloads the static state, and the replay is several times faster."""
+    import time
+    m = dict(D=200, A=5, discrete=True, layer_norm=True, predict_discount=True, entropy_scale=3e-3, gamma=0.999, H=5)
+    torch.manual_seed(0)
+    agent = make_agent(m, "cuda", batch_cluster_size=6)
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.randint(0, 255, (64, 64, 3), dtype=torch.uint8, generator=g).numpy() for _ in range(6)]
+    res, times = {}, {}
+    for graphed in (False, True):
+        agent.cuda_graph_act = graphed
+        agent.reset()
+        a0 = agent.get_action(frames[0])
+        res[graphed] = (agent._state.determ.clone(), agent._state.stoch_logits.clone())
+        acts = [int(a0)] + [int(agent.get_action(f)) for f in frames[1:]]
+        assert all(0 <= a < 5 for a in acts)
+        assert torch.isfinite(agent._state.determ).all() and abs(agent._action_probs.sum().item() - 6) < 1e-3
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for f in frames * 5:
+            agent.get_action(f)
+        torch.cuda.synchronize()
+        times[graphed] = (time.perf_counter() - t0) / 30 * 1e3
+    assert agent._act_graph is not None
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-4, atol=1e-4)
+    print(f"[perf] get_action: eager {times[False]:.3f} ms, graph replay {times[True]:.3f} ms per call")
+    assert times[True] < times[False]
+    # reset() reloads the zero state into the static buffers
+    agent.reset()
+    agent.get_action(frames[0])
+    torch.testing.assert_close(agent._state.determ, res[True][0], rtol=1e-4, atol=1e-5)
+
+
 def test_train_step_continuous_actor_runs_fused(cuda):
     """config_dino-shaped agent (continuous actions, rho = 0): train() drives K1 (+tape) -> K2 -> K2 bwd -> K1 bwd -> K4;
     no torch autograd on the behaviour half.  Gradient parity is in test_gpu_ac_update.py."""
