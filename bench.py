@@ -379,14 +379,37 @@ def main():
     # ---- end to end through the public API with HOST buffers ------------------------------------
     h_host = h0.cpu().pin_memory()
     i_host = idx0.to(torch.uint8).cpu().pin_memory()
+    # Every step uploads its start states from pinned host memory and its result is read back on the host.  The upload
+    # of step i+1 runs on a copy stream while step i computes (two device buffer sets), and the host reads the result
+    # of step i-1 after it has enqueued step i — the input pipeline a training loop with a prefetching loader has.
+    copy_stream = torch.cuda.Stream()
+    dbuf = [(torch.empty_like(h0), torch.empty((N, 32), device=device, dtype=torch.uint8)) for _ in range(2)]
+    up_ev = [torch.cuda.Event() for _ in range(2)]
+    done_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done_ev[i % 2])      # the step that last read this buffer set has finished
+            dbuf[i % 2][0].copy_(h_host, non_blocking=True)
+            dbuf[i % 2][1].copy_(i_host, non_blocking=True)
+            up_ev[i % 2].record(copy_stream)
+
     barrier()
     ev0.record()
+    upload(0)
+    prev = None
     for i in range(args.steps):
-        h_dev = h_host.to(device, non_blocking=True)
-        i_dev = i_host.to(device, non_blocking=True)
+        torch.cuda.current_stream().wait_event(up_ev[i % 2])
+        if i + 1 < args.steps:
+            upload(i + 1)
+        h_dev, i_dev = dbuf[i % 2]
         z_dev = torch.nn.functional.one_hot(i_dev.long(), 32).float().view(N, 1024)
         res = step(make_state(h_dev, z_dev), 5000 + i)
-        res_host = res.detach().cpu()   # device->host read of the step's result (blocks, like dreamer_v2.py:216)
+        done_ev[i % 2].record()
+        if prev is not None:
+            res_host = prev.detach().cpu()   # device->host read of the previous step's result (blocks the host only)
+        prev = res
+    res_host = prev.detach().cpu()
     ev1.record()
     barrier()
     e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
@@ -458,7 +481,7 @@ def main():
                               "per-step working set (>= 2 GB of rollout outputs) exceeds the 126 MB L2; no explicit flush"),
                        "metrics_samples": args.metrics_samples, "noise": "Philox4x32-10 on device"},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"note": "pinned host start states uploaded on a copy stream one step ahead, result read back every step", "value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms.item() / args.steps},
             "gpu_launches": int(launches),
             "imagination_only": {"steps_per_sec": world * N * H / (k1_ms * 1e-3), "ms": k1_ms},
