@@ -32,6 +32,7 @@ struct SmemCtl {
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t peer_full[8];   // CTA pair: the odd CTA's stage is filled (signalled across the pair by its relay thread)
   uint32_t tmem_base;
   uint32_t pad;
   alignas(16) float bias[2][kMaxRB];    // double-buffered per-tile epilogue parameters
@@ -327,16 +328,23 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
   }
 }
 
-template <int EPI>
+template <int EPI, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) {
+  constexpr bool pair = PAIR;   // compile-time: a kernel that contains cta_group::2 instructions can only be launched
+                                // with an even cluster size
+  // pair != 0 (cs == 2, RB <= 256): the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per k-step over their two
+  // M tiles: each stages its own A tile and HALF of the weight block (rows [rank RB/2, (rank+1) RB/2)), so an SM receives
+  // 16 + RB/4 KB per k-step instead of 16 + RB/8 ... 16 + RB/4 x 2 with multicast — the L2 -> SM delivery is what bounds
+  // the wide contractions.  Rank 0 issues the MMAs and owns the barriers the issue depends on; rank 1's MMA warp relays
+  // "my stage is full" across the pair.
   constexpr bool kLnAct = (EPI == EPI_LN_ACT || EPI == EPI_LN_ACT_SAVE);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t a_bytes = kTileM * kTileK * 2;                 // 16 KB
-  const uint32_t b_bytes = static_cast<uint32_t>(p.RB) * kTileK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.RB) * kTileK * 2 / (pair ? 2u : 1u);   // bytes staged per CTA
   const uint32_t stage_bytes = a_bytes + b_bytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + static_cast<size_t>(stages) * stage_bytes);
 
@@ -356,17 +364,24 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(&ctl->full[s], 1);
-        mbar_init(&ctl->empty[s], static_cast<uint32_t>(cs));   // released by every CTA of the cluster
+        // multicast: released by the MMA warp of every CTA of the cluster; pair: by the one issuing CTA
+        mbar_init(&ctl->empty[s], pair ? 1u : static_cast<uint32_t>(cs));
+        mbar_init(&ctl->peer_full[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&ctl->tmem_full[b], 1);
-        mbar_init(&ctl->tmem_empty[b], kEpiWarps);
+        mbar_init(&ctl->tmem_empty[b], pair ? 2 * kEpiWarps : kEpiWarps);   // pair: both CTAs' epilogues drain
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(&ctl->tmem_base, 512);
-    tmem_relinquish();
+    if constexpr (pair) {
+      tmem_alloc2(&ctl->tmem_base, 512);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(&ctl->tmem_base, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -400,7 +415,11 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             bulk_g2s(sa, asrc + static_cast<size_t>(kt) * (kTileM * kTileK), a_bytes,
                      &ctl->full[stage]);
             const __nv_bfloat16* wtile = wsrc + static_cast<size_t>(kt_glob) * (static_cast<size_t>(p.RB) * kTileK);
-            if (cs == 1) {
+            if (pair) {
+              // this CTA's half of the block's rows, at the same offset in both CTAs
+              bulk_g2s(sb, reinterpret_cast<const uint8_t*>(wtile) + static_cast<size_t>(rank) * b_bytes, b_bytes,
+                       &ctl->full[stage]);
+            } else if (cs == 1) {
               bulk_g2s(sb, wtile, b_bytes, &ctl->full[stage]);
             } else {
               // this CTA fetches rows [rank*RB/cs, (rank+1)*RB/cs) of the block for the whole cluster
@@ -418,10 +437,24 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================================
-    if (lane == 0) {
+    if (lane == 0 && pair && rank == 1) {
+      // odd CTA of a pair: no MMAs to issue; tell the even CTA when each of MY stages has landed
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        for (int kt = 0; kt < kt_total; ++kt) {
+          mbar_wait(&ctl->full[stage], phase);
+          mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->peer_full[stage]), 0u));
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else if (lane == 0) {
       const int n_chunk0 = p.RB > 256 ? 256 : p.RB;
       const int n_chunk1 = p.RB - n_chunk0;
-      const uint32_t idesc0 = make_idesc_bf16(kTileM, static_cast<uint32_t>(n_chunk0));
+      const uint32_t idesc0 = make_idesc_bf16(pair ? 2 * kTileM : kTileM, static_cast<uint32_t>(n_chunk0));
       const uint32_t idesc1 = n_chunk1 > 0 ? make_idesc_bf16(kTileM, static_cast<uint32_t>(n_chunk1)) : 0u;
       int stage = 0;
       uint32_t phase = 0;
@@ -434,6 +467,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * buf_cols);
         for (int kt = 0; kt < kt_total; ++kt) {
           mbar_wait(&ctl->full[stage], phase);
+          if (pair) mbar_wait(&ctl->peer_full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sb = sa + a_bytes;
@@ -444,21 +478,29 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           for (int kk = 0; kk < kTileK / 16; ++kk) {
             const uint32_t acc = (kt > 0 || kk > 0) ? 1u : 0u;
             // +32 bytes per 16-element K step == +2 in the (addr >> 4) start-address field
-            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
-                      idesc0, acc);
-            if (n_chunk1 > 0)
-              umma_bf16(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
-                        bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
+            if constexpr (pair) {
+              umma_bf16_2cta(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
+                             idesc0, acc);
+            } else {
+              umma_bf16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
+                        idesc0, acc);
+              if (n_chunk1 > 0)
+                umma_bf16(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
+                          bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
+            }
           }
           // frees the smem stage (in every CTA of the cluster: peers multicast into it) when these MMAs retire
-          if (cs == 1) umma_commit(&ctl->empty[stage]);
+          if constexpr (pair) umma_commit2_multicast(&ctl->empty[stage], cta_mask);
+          else if (cs == 1) umma_commit(&ctl->empty[stage]);
           else umma_commit_multicast(&ctl->empty[stage], cta_mask);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&ctl->tmem_full[buf]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: of both CTAs)
+        if constexpr (pair) umma_commit2_multicast(&ctl->tmem_full[buf], cta_mask);
+        else umma_commit(&ctl->tmem_full[buf]);
       }
     }
   } else {
@@ -555,7 +597,10 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+        if (lane == 0) {
+          if (pair && rank == 1) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->tmem_empty[buf]), 0u));
+          else mbar_arrive(&ctl->tmem_empty[buf]);
+        }
         continue;
       }
 
@@ -673,7 +718,10 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl->tmem_empty[buf]);
+      if (lane == 0) {
+        if (pair && rank == 1) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->tmem_empty[buf]), 0u));
+        else mbar_arrive(&ctl->tmem_empty[buf]);
+      }
     }
     if (bwd_colsum) flush_colsum(g_acc);
   }
@@ -683,11 +731,13 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
   if (cs > 1) cluster_sync_all();   // nobody leaves while a peer may still write its smem / barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (pair) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
 int g_num_sms = 0;
+int g_pair = 1;   // cta_group::2 for clusters of 2 with RB <= 256; RLSB_PAIR=0 falls back to multicast
 int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
 
 }  // namespace
@@ -706,6 +756,7 @@ int init_device_info() {
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return static_cast<int>(e);
     if (const char* env = getenv("RLSB_CLUSTER")) set_gemm_cluster_size(atoi(env));
+    if (const char* env = getenv("RLSB_PAIR")) g_pair = atoi(env) != 0;
   }
   return 0;
 }
@@ -740,7 +791,10 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
     const int ie = init_device_info();
     if (ie != 0) return ie;
   }
-  const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2;
+  // cluster size along M: CTAs of a cluster share the weight block (TMA multicast, or one MMA over the CTA pair)
+  const int cs = pick_cluster(p);
+  const int pair = (g_pair && cs == 2 && p.RB <= 256 && (p.RB % 16) == 0) ? 1 : 0;
+  const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2 / (pair ? 2 : 1);
   const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256;
   static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
   int stages = budget / stage_bytes;
@@ -748,8 +802,6 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   if (stages < 2) return -6;
   const int nbuf = p.RB <= 256 ? 2 : 1;
   const size_t smem = static_cast<size_t>(stages) * stage_bytes + sizeof(SmemCtl) + 1024;
-  // cluster size along M: CTAs of a cluster share the weight block (TMA multicast)
-  const int cs = pick_cluster(p);
   const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
   int clusters = g_num_sms / cs;
   if (total_work < clusters) clusters = total_work;
@@ -776,12 +828,16 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   do {                                                                                           \
     static bool attr_done = false;                                                               \
     if (!attr_done) {                                                                            \
-      e = cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+      e = cudaFuncSetAttribute(gemm_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               227 * 1024);                                                      \
+      if (e != cudaSuccess) return static_cast<int>(e);                                          \
+      e = cudaFuncSetAttribute(gemm_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                227 * 1024);                                                      \
       if (e != cudaSuccess) return static_cast<int>(e);                                          \
       attr_done = true;                                                                          \
     }                                                                                            \
-    e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI>, p, stages, nbuf, cs);                         \
+    if (pair) e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, true>, p, stages, nbuf, cs);         \
+    else e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, false>, p, stages, nbuf, cs);             \
     if (e != cudaSuccess) return static_cast<int>(e);                                            \
   } while (0)
   switch (epilogue) {

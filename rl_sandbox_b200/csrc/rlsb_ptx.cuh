@@ -219,6 +219,52 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
       "h"(cta_mask)
       : "memory");
 }
+// ---- CTA pair (cta_group::2): one MMA over two SMs; the even CTA of the pair (cluster rank 0) issues it ----------
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {   // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D (256 x N: rows 0-127 in this CTA's TMEM, 128-255 in the peer's) (+)= A * B with A = 128 rows per CTA and
+// B = N/2 rows per CTA, each read from the SAME shared-memory offset in both CTAs.
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrive (once the pair's MMAs issued so far have completed) on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit2_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// A local barrier whose arrivals come from the peer CTA is waited on with the plain (CTA-scope) mbar_wait: what the
+// waiter goes on to touch is the peer's shared memory through the tensor core (async proxy) or TMEM, never its own L1,
+// and a cluster-scope acquire per k-step in the MMA issue loop costs more than the four MMAs it guards.
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -33,6 +33,7 @@ def test_no_torch_types_in_abi():
 def test_sass_contains_blackwell_instructions():
     sass = subprocess.check_output(["cuobjdump", "-sass", str(_lib.LIB_PATH)], text=True)
     assert "UTCHMMA" in sass, "tcgen05.mma missing from SASS"
+    assert "UTCHMMA.2CTA" in sass, "tcgen05.mma.cta_group::2 (CTA-pair MMA of the wide contractions) missing from SASS"
     assert "UBLKCP" in sass, "bulk (TMA engine) copies missing from SASS"
     assert "LDTM" in sass, "tcgen05.ld missing from SASS"
     assert "sm_100a" in subprocess.check_output(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], text=True)
