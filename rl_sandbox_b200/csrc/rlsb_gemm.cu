@@ -416,9 +416,14 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
                      &ctl->full[stage]);
             const __nv_bfloat16* wtile = wsrc + static_cast<size_t>(kt_glob) * (static_cast<size_t>(p.RB) * kTileK);
             if (pair) {
-              // this CTA's half of the block's rows, at the same offset in both CTAs
-              bulk_g2s(sb, reinterpret_cast<const uint8_t*>(wtile) + static_cast<size_t>(rank) * b_bytes, b_bytes,
-                       &ctl->full[stage]);
+              // this CTA's half of the rows of each MMA's column range (<= 256 columns per instruction), at the same
+              // offsets in both CTAs: rows [rank n0/2, +n0/2) and, for blocks wider than 256, [n0 + rank n1/2, +n1/2)
+              const uint32_t n0 = p.RB > 256 ? 256u : static_cast<uint32_t>(p.RB), n1 = static_cast<uint32_t>(p.RB) - n0;
+              const uint32_t h0 = n0 / 2u * 128u, h1 = n1 / 2u * 128u;   // bytes
+              const uint8_t* wb = reinterpret_cast<const uint8_t*>(wtile);
+              bulk_g2s(sb, wb + static_cast<size_t>(rank) * h0, h0, &ctl->full[stage]);
+              if (n1 > 0) bulk_g2s(sb + h0, wb + static_cast<size_t>(n0) * 128u + static_cast<size_t>(rank) * h1, h1,
+                                   &ctl->full[stage]);
             } else if (cs == 1) {
               bulk_g2s(sb, wtile, b_bytes, &ctl->full[stage]);
             } else {
@@ -454,8 +459,11 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
     } else if (lane == 0) {
       const int n_chunk0 = p.RB > 256 ? 256 : p.RB;
       const int n_chunk1 = p.RB - n_chunk0;
-      const uint32_t idesc0 = make_idesc_bf16(pair ? 2 * kTileM : kTileM, static_cast<uint32_t>(n_chunk0));
-      const uint32_t idesc1 = n_chunk1 > 0 ? make_idesc_bf16(kTileM, static_cast<uint32_t>(n_chunk1)) : 0u;
+      const uint32_t mma_m = pair ? 2 * kTileM : kTileM;
+      const uint32_t idesc0 = make_idesc_bf16(mma_m, static_cast<uint32_t>(n_chunk0));
+      const uint32_t idesc1 = n_chunk1 > 0 ? make_idesc_bf16(mma_m, static_cast<uint32_t>(n_chunk1)) : 0u;
+      // rows of the first column range staged per CTA (pair: half of them)
+      const uint32_t b1_off = static_cast<uint32_t>(n_chunk0) / (pair ? 2u : 1u) * 128u;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -473,7 +481,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           const uint32_t sb = sa + a_bytes;
           const uint64_t adesc = make_smem_desc_sw128(sa);
           const uint64_t bdesc0 = make_smem_desc_sw128(sb);
-          const uint64_t bdesc1 = make_smem_desc_sw128(sb + 256u * 128u);
+          const uint64_t bdesc1 = make_smem_desc_sw128(sb + b1_off);
 #pragma unroll
           for (int kk = 0; kk < kTileK / 16; ++kk) {
             const uint32_t acc = (kt > 0 || kk > 0) ? 1u : 0u;
@@ -481,6 +489,9 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             if constexpr (pair) {
               umma_bf16_2cta(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
                              idesc0, acc);
+              if (n_chunk1 > 0)
+                umma_bf16_2cta(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
+                               bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
             } else {
               umma_bf16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
                         idesc0, acc);
@@ -737,7 +748,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
 }
 
 int g_num_sms = 0;
-int g_pair = 1;   // cta_group::2 for clusters of 2 with RB <= 256; RLSB_PAIR=0 falls back to multicast
+int g_pair = 2;   // cta_group::2 for clusters of 2 (1: only n-blocks <= 256 columns, 0: multicast only); RLSB_PAIR overrides
 int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
 
 }  // namespace
@@ -756,7 +767,7 @@ int init_device_info() {
     e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return static_cast<int>(e);
     if (const char* env = getenv("RLSB_CLUSTER")) set_gemm_cluster_size(atoi(env));
-    if (const char* env = getenv("RLSB_PAIR")) g_pair = atoi(env) != 0;
+    if (const char* env = getenv("RLSB_PAIR")) g_pair = atoi(env);   // 0: multicast only, 1: pairs for RB <= 256, 2: all
   }
   return 0;
 }
@@ -793,7 +804,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   }
   // cluster size along M: CTAs of a cluster share the weight block (TMA multicast, or one MMA over the CTA pair)
   const int cs = pick_cluster(p);
-  const int pair = (g_pair && cs == 2 && p.RB <= 256 && (p.RB % 16) == 0) ? 1 : 0;
+  const int pair = (g_pair && cs == 2 && (p.RB % 32) == 0 && (p.RB <= 256 || g_pair > 1)) ? 1 : 0;
   const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2 / (pair ? 2 : 1);
   const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256;
   static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
