@@ -276,6 +276,12 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     float da[8], dxh[8], pre[8];
     bwd_chunk<ACT, LN>(r, pb, c, n_valid, s_gam, s_bet, row_ok, da, dxh, pre);
     if (LN) {
+      {   // park dxh in the accumulator's columns: pass 2 then needs neither gamma / beta nor the activation derivative
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = __float_as_uint(dxh[j]);
+        tmem_st8(tmem_d + static_cast<uint32_t>(c), w);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s1 += dxh[j];
@@ -299,6 +305,7 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     }
   }
   if (LN) {
+    tmem_st_wait();
     sts64(s_part + 8u * (cq * kTileM + row), s1, s2);
     epi_bar(2);
     const float2 a0 = lds64(s_part + 8u * row), a1 = lds64(s_part + 8u * (kTileM + row)),
@@ -306,21 +313,23 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     const float inv_n = 1.0f / static_cast<float>(n_valid);
     const float m1 = ((a0.x + a1.x) + (a2.x + a3.x)) * inv_n;
     const float m2 = ((a0.y + a1.y) + (a2.y + a3.y)) * inv_n;
+    const float nm1r = -m1 * rstd, nm2r = -m2 * rstd;
     for (int i = 0; i < my_chunks; ++i) {
       const int c = (cq + 4 * i) * 8;
       if (c >= n_valid) break;
       uint32_t r[8];
-      tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);
+      tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);   // dxh (0 in invalid rows / columns)
       const int oc = col0 + c;
       const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
       const uint4 pb = *reinterpret_cast<const uint4*>(pbase + off);
       tmem_ld_wait();
-      float da[8], dxh[8], pre[8], o[8];
-      bwd_chunk<ACT, LN>(r, pb, c, n_valid, s_gam, s_bet, row_ok, da, dxh, pre);
+      float pre[8], o[8];
+      unpack_bf16x8(pb, pre);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const bool ok = row_ok && (c + j < n_valid);
-        o[j] = ok ? rstd * (dxh[j] - m1 - pre[j] * m2) : 0.f;
+        // rstd * (dxh - m1 - pre * m2)
+        o[j] = ok ? fmaf(pre[j], nm2r, fmaf(__uint_as_float(r[j]), rstd, nm1r)) : 0.f;
       }
       *reinterpret_cast<uint4*>(obase + off) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
                                                           pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
