@@ -1,5 +1,7 @@
 // rlsb_capi.cu — extern "C" surface declared in include/rlsb.h (everything except the K1
 // entry points, which live next to their planner in rlsb_imagine.cu, and K3 in rlsb_slot.cu).
+#include <cstdlib>
+
 #include "../../include/rlsb.h"
 
 #include "rlsb_count.cuh"
@@ -12,6 +14,10 @@ using namespace rlsb;
 
 namespace rlsb {
 std::atomic<long long> g_launches{0};
+int g_pdl = [] {
+  const char* env = getenv("RLSB_PDL");
+  return (env && atoi(env) == 0) ? 0 : 1;
+}();
 }
 
 namespace {

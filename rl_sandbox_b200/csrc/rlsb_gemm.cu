@@ -348,6 +348,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
   // the wide contractions.  Rank 0 issues the MMAs and owns the barriers the issue depends on; rank 1's MMA warp relays
   // "my stage is full" across the pair.
   constexpr bool kLnAct = (EPI == EPI_LN_ACT || EPI == EPI_LN_ACT_SAVE);
+  pdl_launch_dependents();   // the next kernel of the stream may be scheduled now (it waits before reading memory)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atom
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -397,6 +398,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
   tc_fence_after();
   if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   const uint32_t tmem_base = ctl->tmem_base;
+  pdl_wait();   // everything above (barriers, TMEM) overlapped the predecessor's tail; its results are visible from here
 
   if (warp == 0) {
     // ===================== producer: bulk copies into the stage ring =====================
@@ -837,13 +839,15 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(cs);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
 #define RLSB_LAUNCH(EPI)                                                                         \
   do {                                                                                           \
     static bool attr_done = false;                                                               \

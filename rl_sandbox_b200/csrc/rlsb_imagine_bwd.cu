@@ -66,6 +66,8 @@ void make_bwd_workspace(const Plan& P, long long N, BwdWorkspace& W) {
 // d loss / d (head outputs) of the reward head and the target critic -> packed [Gb][m_pad x 64]
 __global__ void head_grad_kernel(const float* __restrict__ g_r, const float* __restrict__ g_v, int M, int m_pad,
                                  int Gb, int gb_reward, int gb_critic, __nv_bfloat16* __restrict__ dy4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= m_pad) return;
   const size_t tile = static_cast<size_t>(m >> 7) * (kTileM * kTileK);
@@ -91,6 +93,8 @@ __global__ void head_grad_kernel(const float* __restrict__ g_r, const float* __r
 __global__ void st_softmax_bwd_kernel(const float* __restrict__ logits, long long ld_l, const float* __restrict__ ga,
                                       long long ld_a, const float* __restrict__ gb, long long ld_b, int M, int groups,
                                       __nv_bfloat16* __restrict__ out, int kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(M) * groups) return;
   const int m = static_cast<int>(i / groups);
@@ -151,6 +155,8 @@ struct GruBwdArgs {
 
 // one warp per row, lane -> chunks of 8 consecutive j (D % 8 == 0)
 __global__ void gru_gate_bwd_kernel(const GruBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   if (warp >= a.m_pad) return;
@@ -251,6 +257,8 @@ __global__ void gru_gate_bwd_kernel(const GruBwdArgs a) {
 
 __global__ void extract_cols_kernel(const float* __restrict__ src, long long ld, int col0, int M, int n,
                                     float* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(M) * n) return;
   const int m = static_cast<int>(i / n), k = static_cast<int>(i % n);
@@ -324,9 +332,9 @@ extern "C" int rlsb_imagine_bwd(const rlsb_imagine_cfg* cfg, const void* packed,
 
   for (int t = H; t >= 1; --t) {
     // ---- reward head + target critic at state t: d loss / d [h_t, z_t] -> g_s -------------------------
-    head_grad_kernel<<<(m_pad + 127) / 128, 128, 0, s>>>(g_rewards + static_cast<size_t>(t) * N,
+    if (launch_pdl(head_grad_kernel, static_cast<unsigned>((m_pad + 127) / 128), 128, 0, s, g_rewards + static_cast<size_t>(t) * N,
                                                           g_values + static_cast<size_t>(t) * N, M, m_pad, P.Gb,
-                                                          P.g_reward - P.gb0, P.g_critic - P.gb0, bf(W.dy4));
+                                                          P.g_reward - P.gb0, P.g_critic - P.gb0, bf(W.dy4)) != cudaSuccess) return static_cast<int>(cudaGetLastError());
     count_launch();
     RLSB_CUDA_OK();
     const __nv_bfloat16* dy = bf(W.dy4);
@@ -367,9 +375,9 @@ extern "C" int rlsb_imagine_bwd(const rlsb_imagine_cfg* cfg, const void* packed,
     // ---- z_t -> prior logits -> prior MLP -> h_t ---------------------------------------------------------
     {
       const long long tot = static_cast<long long>(M) * cfg->groups;
-      st_softmax_bwd_kernel<<<static_cast<unsigned>((tot + 127) / 128), 128, 0, s>>>(
+      if (launch_pdl(st_softmax_bwd_kernel, static_cast<unsigned>(static_cast<unsigned>((tot + 127) / 128)), 128, 0, s, 
           fwd->logits + static_cast<size_t>(t) * NS, P.S, f32(W.g_s) + P.Dp, W.ldS,
-          t < H ? f32(W.g_za) : nullptr, W.ldZA, M, cfg->groups, bf(W.g_logits), P.Sp);
+          t < H ? f32(W.g_za) : nullptr, W.ldZA, M, cfg->groups, bf(W.g_logits), P.Sp) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       count_launch();
       RLSB_CUDA_OK();
       GemmParams g = base();
@@ -408,7 +416,7 @@ extern "C" int rlsb_imagine_bwd(const rlsb_imagine_cfg* cfg, const void* packed,
       }
       a.g_pre = bf(W.g_pre); a.kpad = P.G3p;
       a.g_hdirect = f32(W.g_hdirect);
-      gru_gate_bwd_kernel<<<(m_pad * 32 + 255) / 256, 256, 0, s>>>(a);
+      if (launch_pdl(gru_gate_bwd_kernel, static_cast<unsigned>((m_pad * 32 + 255) / 256), 256, 0, s, a) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       count_launch();
       RLSB_CUDA_OK();
       // d loss / d x_t with the ELU' / LayerNorm backward of the img_in layer fused
@@ -438,8 +446,8 @@ extern "C" int rlsb_imagine_bwd(const rlsb_imagine_cfg* cfg, const void* packed,
       g.out_f32 = f32(W.g_za); g.ldo = W.ldZA;
       RLSB_TRY(launch_gemm(g, EPI_PLAIN, s));
       const long long tot = static_cast<long long>(M) * P.A;
-      extract_cols_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(
-          f32(W.g_za), W.ldZA, P.Sp, M, P.A, g_actions + static_cast<size_t>(t - 1) * N * P.A);
+      if (launch_pdl(extract_cols_kernel, static_cast<unsigned>(static_cast<unsigned>((tot + 255) / 256)), 256, 0, s, 
+          f32(W.g_za), W.ldZA, P.Sp, M, P.A, g_actions + static_cast<size_t>(t - 1) * N * P.A) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       count_launch();
       RLSB_CUDA_OK();
     }

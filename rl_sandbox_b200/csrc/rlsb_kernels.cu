@@ -182,6 +182,8 @@ __device__ __forceinline__ void load8_ro(const float* p, bool vec, int valid, fl
 // to four chunks (eight 16-byte loads) are in flight per lane before the row statistics are reduced — HBM-bound:
 // 4 B read + 2 B written per element.
 __global__ void __launch_bounds__(256, 4) ln_act_kernel(const LnActArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cpr = a.out_kpad >> 3;
   const int lane = threadIdx.x & 31;
   const int warp0 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -321,6 +323,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // owns the float4 column groups lane, lane + 32, ...; two groups (eight streaming 16-byte loads) are in flight per lane
 // before the row statistics are reduced.  HBM-bound: 3·4 + 4 B read, 4 + 2 B written per hidden unit.
 __global__ void __launch_bounds__(256) gru_gate_kernel(const GruArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int D = a.D;
   const int lane = threadIdx.x & 31;
   const int warp0 = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -479,6 +483,8 @@ __device__ __noinline__ int sample_group_exact(const SampleLatentArgs& a, int m,
 // one rounding of the sum).  Otherwise (about 1 group in 10^4, and whenever a score is NaN / infinite) the group is
 // redrawn in the reference order with the bit-reproducible transform — the indices are those of the oracle, always.
 __global__ void __launch_bounds__(256, 4) sample_latent_kernel(const SampleLatentArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(a.M) * a.groups;
   const int lane = threadIdx.x & 31;
   const int q = lane & 7;
@@ -581,6 +587,8 @@ __global__ void sample_categorical_kernel(const float* __restrict__ logits,
 // head post-processing: reward / value / discount read-out + action draw (one thread per row)
 // ------------------------------------------------------------------------------------------
 __global__ void head_finish_kernel(const HeadFinishParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= p.m_pad) return;
   const bool valid = m < p.M;
@@ -879,7 +887,9 @@ int launch_ln_act(const float* scratch, long long ld, const float* stats, int NB
   LnActArgs a{scratch, ld, stats, NB, RB, M, m_pad, N, gamma, beta, eps, act, out, out_kpad};
   // one warp per row; small row counts still spread over every SM (one warp per block)
   const int block = m_pad >= 148 * 8 ? 256 : 32;
-  ln_act_kernel<<<grid_for(static_cast<long long>(m_pad) * 32, block, 148 * 8), block, 0, stream>>>(a);
+  const cudaError_t le = launch_pdl(ln_act_kernel, grid_for(static_cast<long long>(m_pad) * 32, block, 148 * 8), block, 0,
+                                    stream, a);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -896,7 +906,9 @@ int launch_gru_gate(const float* scratch, long long ld, const float* stats, int 
                       reinterpret_cast<uintptr_t>(beta)) & 15) == 0);
   if (vec) {
     const int block = m_pad >= 148 * 8 ? 256 : 32;
-    gru_gate_kernel<<<grid_for(static_cast<long long>(m_pad) * 32, block, 148 * 8), block, 0, stream>>>(a);
+    const cudaError_t le = launch_pdl(gru_gate_kernel, grid_for(static_cast<long long>(m_pad) * 32, block, 148 * 8), block,
+                                      0, stream, a);
+    if (le != cudaSuccess) return static_cast<int>(le);
   } else {
     const long long total = static_cast<long long>(m_pad) * ((kpad / 8 + 31) / 32) * 32;
     gru_gate_kernel_generic<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(a);
@@ -915,7 +927,8 @@ int launch_sample_latent(const float* logits, long long ld, int M, int groups, i
   // eight lanes per (row, group): four groups per warp iteration
   const long long warps = (total + 3) / 4;
   const int block = warps >= 148 * 8 ? 256 : 32;
-  sample_latent_kernel<<<grid_for(warps * 32, block, 148 * 64), block, 0, stream>>>(a);
+  const cudaError_t le = launch_pdl(sample_latent_kernel, grid_for(warps * 32, block, 148 * 64), block, 0, stream, a);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -933,7 +946,8 @@ int launch_sample_categorical(const float* logits, const float* uniforms, long l
 int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream) {
   if (p.a_kpad > 64 || (p.a_kpad % 8) != 0) return -1;
   const int block = 128;
-  head_finish_kernel<<<(p.m_pad + block - 1) / block, block, 0, stream>>>(p);
+  const cudaError_t le = launch_pdl(head_finish_kernel, (p.m_pad + block - 1) / block, block, 0, stream, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }

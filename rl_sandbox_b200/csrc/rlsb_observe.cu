@@ -230,6 +230,8 @@ __global__ void pack_steps_kernel(const float* __restrict__ src, int T, int B, i
 __global__ void st_softmax_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ g_ext,
                                       const float* __restrict__ gz_a, const float* __restrict__ gz_b, long long ld_b,
                                       int M, int m_pad, int groups, __nv_bfloat16* __restrict__ out, int kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(m_pad) * groups) return;
   const int m = static_cast<int>(i / groups);
@@ -285,6 +287,8 @@ __global__ void ln_act_bwd_kernel(const float* __restrict__ g, long long ld_g, c
                                   const float* __restrict__ stats, int NB, int M, int m_pad, int D,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                   __nv_bfloat16* __restrict__ dp, int kpad, float* __restrict__ da_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   if (row >= m_pad) return;
@@ -363,6 +367,8 @@ struct GruBwdArgs {
 };
 
 __global__ void gru_gate_bwd_kernel(const GruBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   if (warp >= a.m_pad) return;
@@ -455,6 +461,8 @@ __global__ void ln_param_grad_kernel(const float* __restrict__ da, const float* 
 
 __global__ void extract_steps_kernel(const float* __restrict__ src, long long ld, int col0, int B, int n,
                                      float* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n) return;
   const int m = i / n, k = i % n;
@@ -723,9 +731,9 @@ extern "C" int rlsb_observe_bwd(const rlsb_observe_cfg* cfg, const void* packed,
   };
   auto ln_bwd = [&](const float* g, long long ld_g, const float* pre, const float* st, const LayerPlan& L,
                     __nv_bfloat16* dp, float* da) -> int {
-    ln_act_bwd_kernel<<<(m_pad * 32 + 255) / 256, 256, 0, s>>>(g, ld_g, pre, st, L.NB, B, m_pad, P.D,
+    if (launch_pdl(ln_act_bwd_kernel, static_cast<unsigned>((m_pad * 32 + 255) / 256), 256, 0, s, g, ld_g, pre, st, L.NB, B, m_pad, P.D,
                                                                 P.ln ? pf(L.g_off) : nullptr, P.ln ? pf(L.b_off) : nullptr,
-                                                                eps, dp, P.Dp, da);
+                                                                eps, dp, P.Dp, da) != cudaSuccess) return static_cast<int>(cudaGetLastError());
     count_launch();
     return static_cast<int>(cudaGetLastError());
   };
@@ -735,27 +743,27 @@ extern "C" int rlsb_observe_bwd(const rlsb_observe_cfg* cfg, const void* packed,
     // ---- posterior logits: external gradient + the straight-through sample's gradient --------------------
     {
       const long long tot = static_cast<long long>(m_pad) * cfg->groups;
-      st_softmax_bwd_kernel<<<static_cast<unsigned>((tot + 127) / 128), 128, 0, s>>>(
+      if (launch_pdl(st_softmax_bwd_kernel, static_cast<unsigned>(static_cast<unsigned>((tot + 127) / 128)), 128, 0, s, 
           fwd->post_logits + static_cast<size_t>(t) * BS, g_post_logits ? g_post_logits + static_cast<size_t>(t) * BS : nullptr,
           g_stoch ? g_stoch + static_cast<size_t>(t) * BS : nullptr, last ? nullptr : f32(W.g_za), W.ld_za, B, m_pad,
-          cfg->groups, wimg(W.gl_post, t, P.Sp), P.Sp);
+          cfg->groups, wimg(W.gl_post, t, P.Sp), P.Sp) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       count_launch();
       RLSB_CUDA_OK();
       RLSB_TRY(dx(P.t_post2, wimg(W.gl_post, t, P.Sp), P.D, f32(W.g_y2), P.D));
       RLSB_TRY(ln_bwd(f32(W.g_y2), P.D, tfb(TP.sc_y2, t, mD), tfb(TP.st_y2, t, static_cast<size_t>(P.post1.NB) * m_pad * 2),
                       P.post1, wimg(W.dp2, t, P.Dp), wfb(W.da_y2, t, mD)));
       RLSB_TRY(dx(P.t_post1, wimg(W.dp2, t, P.Dp), P.Dp + P.Ep, f32(W.g_he), W.ld_he));
-      extract_steps_kernel<<<(B * P.E + 255) / 256, 256, 0, s>>>(f32(W.g_he), W.ld_he, P.Dp, B, P.E,
-                                                                 g_embed + static_cast<size_t>(t) * B * P.E);
+      if (launch_pdl(extract_steps_kernel, static_cast<unsigned>((B * P.E + 255) / 256), 256, 0, s, f32(W.g_he), W.ld_he, P.Dp, B, P.E,
+                                                                 g_embed + static_cast<size_t>(t) * B * P.E) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       count_launch();
       RLSB_CUDA_OK();
     }
     // ---- prior logits -----------------------------------------------------------------------------------------
     {
       const long long tot = static_cast<long long>(m_pad) * cfg->groups;
-      st_softmax_bwd_kernel<<<static_cast<unsigned>((tot + 127) / 128), 128, 0, s>>>(
+      if (launch_pdl(st_softmax_bwd_kernel, static_cast<unsigned>(static_cast<unsigned>((tot + 127) / 128)), 128, 0, s, 
           nullptr, g_prior_logits ? g_prior_logits + static_cast<size_t>(t) * BS : nullptr, nullptr, nullptr, 0, B, m_pad,
-          cfg->groups, wimg(W.gl_prior, t, P.Sp), P.Sp);
+          cfg->groups, wimg(W.gl_prior, t, P.Sp), P.Sp) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       count_launch();
       RLSB_CUDA_OK();
       RLSB_TRY(dx(P.t_prior2, wimg(W.gl_prior, t, P.Sp), P.D, f32(W.g_y), P.D));
@@ -783,7 +791,7 @@ extern "C" int rlsb_observe_bwd(const rlsb_observe_cfg* cfg, const void* packed,
       a.g_pre = wimg(W.g_pre, t, P.G3p); a.kpad = P.G3p;
       a.g_hdirect = f32(W.g_hdirect);
       a.da_out = wfb(W.da_g, t, static_cast<size_t>(m_pad) * TP.ld3);
-      gru_gate_bwd_kernel<<<(m_pad * 32 + 255) / 256, 256, 0, s>>>(a);
+      if (launch_pdl(gru_gate_bwd_kernel, static_cast<unsigned>((m_pad * 32 + 255) / 256), 256, 0, s, a) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       count_launch();
       RLSB_CUDA_OK();
       RLSB_TRY(dx(P.t_gru_x, wimg(W.g_pre, t, P.G3p), P.D, f32(W.g_x), P.D));
