@@ -77,6 +77,7 @@ class DreamerV2(RlAgent):
         # in a CUDA graph and replay it; the Philox key lives in device memory so every replay draws fresh noise
         self.cuda_graph = True
         self.cuda_graph_max_rows = 8192
+        self.max_rows_per_pass = 131072   # start states per pass of the fused update (HBM sizing, _fused_step_chunked)
         # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
         # T sequential steps of small kernels — thousands of launches whose CPU dispatch cost exceeds their GPU time)
         self.cuda_graph_wm = True
@@ -431,6 +432,9 @@ class DreamerV2(RlAgent):
         explicit = 'latent_uniforms' in noise or 'action_noise' in noise
         if self.cuda_graph and not explicit and n_rows <= self.cuda_graph_max_rows:
             scal = self._fused_step_graphed(initial_states, noise)
+        elif n_rows > self.max_rows_per_pass and not explicit:
+            with torch.no_grad():
+                scal = self._fused_step_chunked(initial_states, noise)
         else:
             with torch.no_grad():
                 scal = self._fused_step(initial_states, noise)
@@ -444,6 +448,40 @@ class DreamerV2(RlAgent):
                                             'loss_actor_entropy', 'loss_actor', 'loss_critic')}
         metrics = {k: scal[i] for k, i in idx.items() if '/' in k}
         return losses, metrics | metrics_a | metrics_c
+
+    def _fused_step_chunked(self, initial_states: State, noise: dict):
+        """More start states than one pass holds in HBM (the rollout outputs and the K4 activation images of 131 072 start
+        states x H = 15 take ~100 GB): passes over contiguous chunks, parameter gradients and scalars combined with the
+        chunks' weights.  The Philox counters are global start-state indices, so the result does not depend on the split."""
+        from rl_sandbox_b200 import _lib
+        n = initial_states.determ.shape[1]
+        chunks = -(-n // self.max_rows_per_pass)
+        per = -(-n // chunks)
+        per = -(-per // 128) * 128
+        params = list(self.actor.actor.parameters()) + list(self.critic.critic.parameters())
+        seed = noise.get('seed', (self._noise_seed << 20) + self._rollouts)
+        off0 = int(noise.get('row_offset', 0))
+        idx = _lib.AC_SCALAR_NAMES
+        acc, scal = None, None
+        for a in range(0, n, per):
+            b = min(n, a + per)
+            w = (b - a) / n
+            sub = type(initial_states)(initial_states.determ[:, a:b], initial_states.stoch_logits[:, a:b],
+                                       initial_states.stoch[:, a:b])
+            s = self._fused_step(sub, {'seed': seed, 'row_offset': off0 + a}).clone()
+            grads = [p.grad for p in params]
+            if acc is None:
+                acc = [g * w for g in grads]
+                scal = s * w
+                lo, hi = s[idx['actor/min_val']].clone(), s[idx['actor/max_val']].clone()
+            else:
+                torch._foreach_add_(acc, grads, alpha=w)
+                scal += s * w
+                lo, hi = torch.minimum(lo, s[idx['actor/min_val']]), torch.maximum(hi, s[idx['actor/max_val']])
+        for p, g in zip(params, acc):
+            p.grad.copy_(g)
+        scal[idx['actor/min_val']], scal[idx['actor/max_val']] = lo, hi
+        return scal
 
     def _fused_step(self, initial_states: State, noise: dict, seed_device=None, static=None):
         """pack (if stale) -> K1 -> K2 [-> K2 bwd -> K1 bwd] -> K4; returns the K4 scalar vector (device)."""
