@@ -17,6 +17,7 @@ continuous actor (rho == 0) the dynamics-backprop loss needs d(rollout)/d(actor)
 yet, so that configuration differentiates through a torch replay of the rollout (``_imagine_autograd``,
 CUDA tensors, same modules) — recorded in DESIGN.md as the open item of this round.
 """
+import os
 import typing as t
 from pathlib import Path
 
@@ -76,7 +77,7 @@ class DreamerV2(RlAgent):
         # launch-bound shapes (the configured N = 16 x 50 = 800): capture pack + K1 + K2 (+ bwd) + K4 once per shape
         # in a CUDA graph and replay it; the Philox key lives in device memory so every replay draws fresh noise
         self.cuda_graph = True
-        self.cuda_graph_max_rows = 8192
+        self.cuda_graph_max_rows = int(os.environ.get('RLSB_GRAPH_MAX_ROWS', 32768))
         self.max_rows_per_pass = 131072   # start states per pass of the fused update (HBM sizing, _fused_step_chunked)
         # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
         # T sequential steps of small kernels — thousands of launches whose CPU dispatch cost exceeds their GPU time)

@@ -123,14 +123,8 @@ int make_ac_workspace(const AcPlan& P, long long N, AcWorkspace& W) {
   return 0;
 }
 
-__global__ void copy_pad_kernel2(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad, float fill) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) dst[i] = (src && i < n) ? src[i] : fill;
-}
 int copy_pad2(const float* src, int n, float* dst, int n_pad, float fill, cudaStream_t s) {
-  copy_pad_kernel2<<<(n_pad + 255) / 256, 256, 0, s>>>(src, n, dst, n_pad, fill);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_copy_pad(src, n, dst, n_pad, fill, s);
 }
 
 // the "ones" K tile: element (row, 0) = 1, everything else 0 (bias gradient = dY^T * 1)
@@ -445,6 +439,7 @@ extern "C" int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   AcPlan P;
   RLSB_TRY(make_ac_plan(*cfg, P));
+  LaunchBatchScope batch(s);   // the small pack / pad launches below are queued and issued as multi-job kernels
   uint8_t* base = static_cast<uint8_t*>(packed);
   for (int l = 0; l < 5; ++l) {
     const AcLayer& L = P.L[l];
@@ -476,7 +471,9 @@ extern "C" int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor
   }
   ones_tile_kernel<<<8, 128, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(base + P.ones_off));
   count_launch();
-  return static_cast<int>(cudaGetLastError());
+  const int e = static_cast<int>(cudaGetLastError());
+  if (e != 0) return e;
+  return batch.end();
 }
 
 extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,

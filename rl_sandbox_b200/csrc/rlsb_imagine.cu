@@ -25,16 +25,8 @@ using namespace k1;
 
 namespace {
 
-__global__ void copy_pad_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad,
-                                float fill) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) dst[i] = (src && i < n) ? src[i] : fill;
-}
-
 int copy_pad(const float* src, int n, float* dst, int n_pad, float fill, cudaStream_t s) {
-  copy_pad_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(src, n, dst, n_pad, fill);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_copy_pad(src, n, dst, n_pad, fill, s);
 }
 
 // one-hot fp32 rows -> uint8 class index per group (start state only)
@@ -97,6 +89,7 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   Plan P;
   RLSB_TRY(make_plan(*cfg, P));
+  LaunchBatchScope batch(s);   // the small pack / pad launches below are queued and issued as multi-job kernels
   uint8_t* base = static_cast<uint8_t*>(packed);
   auto wptr = [&](const LayerPlan& L) { return reinterpret_cast<__nv_bfloat16*>(base + L.w_off); };
   auto fptr = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
@@ -222,7 +215,7 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
                                           P.t_img_in.NB * P.t_img_in.RB, P.t_img_in.kp, 0, P.t_img_in.kp, 2, ri, s));
     }
   }
-  return 0;
+  return batch.end();
 }
 
 extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0,

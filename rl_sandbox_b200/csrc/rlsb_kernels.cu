@@ -1,5 +1,6 @@
 // rlsb_kernels.cu — HBM-bound kernels of the imagination path: operand packing, LayerNorm /
 // GRU-gate application, categorical sampling, head post-processing and the lambda-return scan.
+#include <cstdlib>
 #include "rlsb_kernels.cuh"
 
 #include "rlsb_count.cuh"
@@ -64,6 +65,73 @@ __global__ void pack_kernel(const PackArgs a) {
   }
 }
 
+// ---- multi-job variants (see batch_begin / batch_end) -----------------------------------------------------------
+constexpr int kPackJobs = 20;
+struct PackJobs {
+  int n;
+  long long first[kPackJobs + 1];   // prefix sums of 16-byte destination chunks
+  PackArgs job[kPackJobs];
+};
+__global__ void pack_multi_kernel(const __grid_constant__ PackJobs J) {
+  const long long total = J.first[J.n];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int j = 0;
+    while (j + 1 < J.n && i >= J.first[j + 1]) ++j;
+    const PackArgs& a = J.job[j];
+    const long long li = i - J.first[j];
+    const long long chunks_per_row = a.k_pad >> 3;
+    const long long row = li / chunks_per_row;
+    const int k0 = static_cast<int>(li - row * chunks_per_row) << 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float x = 0.f;
+      if (row < a.rows_src) {
+        const int k = k0 + e;
+        for (int s = 0; s < a.n_seg; ++s) {
+          const int off = k - a.seg[s].dst_k0;
+          if (off >= 0 && off < a.seg[s].len) x = __ldg(a.src + row * a.ld_src + a.seg[s].src_c0 + off);
+        }
+      }
+      v[e] = x;
+    }
+    const size_t idx = packed_index(static_cast<size_t>(row), static_cast<size_t>(k0), static_cast<size_t>(a.k_pad), a.RB);
+    *reinterpret_cast<uint4*>(a.dst + idx) = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+  }
+}
+
+constexpr int kPadJobs = 96;
+struct PadJob {
+  const float* src;
+  float* dst;
+  int n, n_pad;
+  float fill;
+};
+struct PadJobs {
+  int n;
+  int first[kPadJobs + 1];   // prefix sums of n_pad
+  PadJob job[kPadJobs];
+};
+__global__ void copy_pad_multi_kernel(const __grid_constant__ PadJobs J) {
+  const int total = J.first[J.n];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = J.n;   // job j with first[j] <= i < first[j + 1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (i >= J.first[mid]) lo = mid;
+      else hi = mid;
+    }
+    const PadJob& a = J.job[lo];
+    const int li = i - J.first[lo];
+    a.dst[li] = (a.src && li < a.n) ? a.src[li] : a.fill;
+  }
+}
+__global__ void copy_pad_single_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad, float fill) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = (src && i < n) ? src[i] : fill;
+}
+
 struct PackTArgs {
   const float* src;
   long long ld_src;
@@ -98,6 +166,47 @@ __global__ void pack_transposed_kernel(const PackTArgs a) {
     *reinterpret_cast<uint4*>(a.dst + idx) = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
   }
 }
+
+constexpr int kPackTJobs = 28;
+struct PackTJobs {
+  int n;
+  long long first[kPackTJobs + 1];   // prefix sums of 16-byte destination chunks
+  PackTArgs job[kPackTJobs];
+};
+__global__ void pack_transposed_multi_kernel(const __grid_constant__ PackTJobs J) {
+  const long long total = J.first[J.n];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int j = 0;
+    while (j + 1 < J.n && i >= J.first[j + 1]) ++j;
+    const PackTArgs& a = J.job[j];
+    const long long li = i - J.first[j];
+    const long long ch = li / a.rows_dst_pad;
+    const int row = static_cast<int>(li - ch * a.rows_dst_pad);
+    const int c0 = static_cast<int>(ch) << 3;
+    int src_col = -1;
+    for (int s = 0; s < a.n_seg; ++s) {
+      const int off = row - a.seg[s].dst_k0;
+      if (off >= 0 && off < a.seg[s].len) src_col = a.seg[s].src_c0 + off;
+    }
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      v[e] = (src_col >= 0 && c0 + e < a.cols) ? __ldg(a.src + static_cast<long long>(c0 + e) * a.ld_src + src_col) : 0.f;
+    const size_t idx = packed_index(static_cast<size_t>(row), static_cast<size_t>(a.dst_k0 + c0),
+                                    static_cast<size_t>(a.k_pad), a.RB);
+    *reinterpret_cast<uint4*>(a.dst + idx) = make_uint4(bf2(v[0], v[1]), bf2(v[2], v[3]), bf2(v[4], v[5]), bf2(v[6], v[7]));
+  }
+}
+
+struct LaunchBatch {
+  bool active = false;
+  cudaStream_t stream = nullptr;
+  PackJobs packs{};
+  PackTJobs packts{};
+  PadJobs pads{};
+};
+thread_local LaunchBatch t_batch;
 
 // ------------------------------------------------------------------------------------------
 // LayerNorm statistics from the per-(row, n-block) partials (sum, sum of squares) the GEMM
@@ -845,6 +954,33 @@ inline int grid_for(long long total, int block, int cap = 148 * 16) {
 
 }  // namespace
 
+namespace {
+int flush_packs() {
+  PackJobs& J = t_batch.packs;
+  if (J.n == 0) return 0;
+  pack_multi_kernel<<<grid_for(J.first[J.n], 256), 256, 0, t_batch.stream>>>(J);
+  count_launch();
+  J.n = 0;
+  return static_cast<int>(cudaGetLastError());
+}
+int flush_packts() {
+  PackTJobs& J = t_batch.packts;
+  if (J.n == 0) return 0;
+  pack_transposed_multi_kernel<<<grid_for(J.first[J.n], 256, 148 * 8), 256, 0, t_batch.stream>>>(J);
+  count_launch();
+  J.n = 0;
+  return static_cast<int>(cudaGetLastError());
+}
+int flush_pads() {
+  PadJobs& J = t_batch.pads;
+  if (J.n == 0) return 0;
+  copy_pad_multi_kernel<<<grid_for(J.first[J.n], 256, 148 * 4), 256, 0, t_batch.stream>>>(J);
+  count_launch();
+  J.n = 0;
+  return static_cast<int>(cudaGetLastError());
+}
+}  // namespace
+
 int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
                 int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream) {
   if (n_seg < 0 || n_seg > 8 || (k_pad % 64) != 0 || RB <= 0 || (rows_dst_pad % RB) != 0) return -1;
@@ -853,9 +989,60 @@ int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16*
   a.rows_dst_pad = rows_dst_pad; a.k_pad = k_pad; a.n_seg = n_seg;
   for (int s = 0; s < n_seg; ++s) a.seg[s] = segs[s];
   const long long total = static_cast<long long>(rows_dst_pad) * (k_pad / 8);
+  if (t_batch.active && t_batch.stream == stream) {
+    if (t_batch.packs.n == kPackJobs) {
+      const int e = flush_packs();
+      if (e != 0) return e;
+    }
+    PackJobs& J = t_batch.packs;
+    if (J.n == 0) J.first[0] = 0;
+    J.job[J.n] = a;
+    J.first[J.n + 1] = J.first[J.n] + total;
+    ++J.n;
+    return 0;
+  }
   pack_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
   count_launch();
   return static_cast<int>(cudaGetLastError());
+}
+
+int launch_copy_pad(const float* src, int n, float* dst, int n_pad, float fill, cudaStream_t stream) {
+  if (n_pad <= 0) return 0;
+  if (t_batch.active && t_batch.stream == stream) {
+    PadJobs& J = t_batch.pads;
+    if (J.n == kPadJobs || (J.n > 0 && J.first[J.n] > (1 << 30) - n_pad)) {
+      const int e = flush_pads();
+      if (e != 0) return e;
+    }
+    if (J.n == 0) J.first[0] = 0;
+    J.job[J.n] = PadJob{src, dst, n, n_pad, fill};
+    J.first[J.n + 1] = J.first[J.n] + n_pad;
+    ++J.n;
+    return 0;
+  }
+  copy_pad_single_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(src, n, dst, n_pad, fill);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+void batch_begin(cudaStream_t stream) {
+  static const bool enabled = [] {
+    const char* e = getenv("RLSB_PACK_BATCH");   // RLSB_PACK_BATCH=0: one launch per pack / pad job (A/B runs)
+    return !(e && e[0] == '0');
+  }();
+  t_batch.active = enabled;
+  t_batch.stream = stream;
+  t_batch.packs.n = 0;
+  t_batch.packts.n = 0;
+  t_batch.pads.n = 0;
+}
+
+int batch_end() {
+  const int e = flush_packs();
+  const int e1 = flush_packts();
+  const int e2 = flush_pads();
+  t_batch.active = false;
+  return e != 0 ? e : (e1 != 0 ? e1 : e2);
 }
 
 int launch_pack_transposed_seg(const float* src, long long ld_src, int cols, __nv_bfloat16* dst, int RB,
@@ -867,6 +1054,18 @@ int launch_pack_transposed_seg(const float* src, long long ld_src, int cols, __n
   PackTArgs a{src, ld_src, cols, dst, RB, rows_dst_pad, k_pad, dst_k0, k_len, n_seg, {}};
   for (int i = 0; i < n_seg; ++i) a.seg[i] = segs[i];
   const long long total = static_cast<long long>(rows_dst_pad) * (k_len >> 3);
+  if (t_batch.active && t_batch.stream == stream) {
+    if (t_batch.packts.n == kPackTJobs) {
+      const int e = flush_packts();
+      if (e != 0) return e;
+    }
+    PackTJobs& J = t_batch.packts;
+    if (J.n == 0) J.first[0] = 0;
+    J.job[J.n] = a;
+    J.first[J.n + 1] = J.first[J.n] + total;
+    ++J.n;
+    return 0;
+  }
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_transposed_kernel<<<blocks, 256, 0, stream>>>(a);

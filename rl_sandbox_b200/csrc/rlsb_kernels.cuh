@@ -15,6 +15,24 @@ struct PackSeg {
 
 // fp32 row-major [rows_src x *] (leading dim ld_src) -> packed bf16 [rows_dst_pad x k_pad] with
 // row block RB; everything not covered by a segment (and rows >= rows_src) is written as zero.
+// Batching of the small launches of a weight (re-)pack: between batch_begin(stream) and batch_end() every launch_pack and
+// launch_copy_pad on that stream is queued instead of launched; batch_end() issues them as a handful of multi-job kernels
+// (the job table travels in the kernel parameters).  The queued jobs must be independent of each other and of anything
+// launched in between — they are: each writes its own region of a packed blob from fp32 parameters.  A pack is ~140 tiny
+// launches per optimizer step otherwise, a third of all launches of the step at 800 start states.
+void batch_begin(cudaStream_t stream);
+int batch_end();
+// dst[i] = i < n ? src[i] : fill for i < n_pad (src may be nullptr: all fill)
+int launch_copy_pad(const float* src, int n, float* dst, int n_pad, float fill, cudaStream_t stream);
+// scope guard: an early error return inside a pack function must not leave the thread's batch open
+struct LaunchBatchScope {
+  explicit LaunchBatchScope(cudaStream_t stream) { batch_begin(stream); }
+  ~LaunchBatchScope() { if (!done_) batch_end(); }
+  int end() { done_ = true; return batch_end(); }
+ private:
+  bool done_ = false;
+};
+
 int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
                 int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream);
 

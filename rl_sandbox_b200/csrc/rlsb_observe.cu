@@ -478,10 +478,6 @@ __global__ void obs_ones_tile_kernel(__nv_bfloat16* dst) {
   reinterpret_cast<uint4*>(dst)[i] = v;
 }
 
-__global__ void obs_copy_pad_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad, float fill) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) dst[i] = (src && i < n) ? src[i] : fill;
-}
 
 #define RLSB_TRY(expr)            \
   do {                            \
@@ -495,9 +491,7 @@ __global__ void obs_copy_pad_kernel(const float* __restrict__ src, int n, float*
   } while (0)
 
 int copy_pad(const float* src, int n, float* dst, int n_pad, float fill, cudaStream_t s) {
-  obs_copy_pad_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(src, n, dst, n_pad, fill);
-  count_launch();
-  return static_cast<int>(cudaGetLastError());
+  return launch_copy_pad(src, n, dst, n_pad, fill, s);
 }
 
 }  // namespace
@@ -532,6 +526,7 @@ extern "C" int rlsb_observe_pack(const rlsb_observe_cfg* cfg, const rlsb_observe
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   ObsPlan P;
   RLSB_TRY(make_obs_plan(*cfg, P));
+  LaunchBatchScope batch(s);   // the small pack / pad launches below are queued and issued as multi-job kernels
   uint8_t* base = static_cast<uint8_t*>(packed);
   auto wptr = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
   auto fptr = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
@@ -578,7 +573,8 @@ extern "C" int rlsb_observe_pack(const rlsb_observe_cfg* cfg, const rlsb_observe
   }
   obs_ones_tile_kernel<<<8, 128, 0, s>>>(wptr(P.ones_off));
   count_launch();
-  return static_cast<int>(cudaGetLastError());
+  RLSB_CUDA_OK();
+  return batch.end();
 }
 
 extern "C" int rlsb_observe_fwd(const rlsb_observe_cfg* cfg, const void* packed, int64_t B_, const float* embed,
