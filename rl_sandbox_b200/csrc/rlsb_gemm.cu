@@ -141,18 +141,98 @@ __device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int 
                                                     pack_bf16x2(pre[4], pre[5]), pack_bf16x2(pre[6], pre[7]));
 }
 
+// the same for a chunk known to be complete (all 8 columns valid): no bounds checks, parameter addresses = base + immediate
+template <int ACT, bool LN, bool SAVE>
+__device__ __forceinline__ void ln_act_chunk_full(const uint32_t (&r)[8], uint32_t s_bias, uint32_t s_gam, uint32_t s_bet,
+                                                  f32x2 rstd2, f32x2 nmr2, __nv_bfloat16* dst, __nv_bfloat16* dst_pre,
+                                                  bool row_ok) {
+  float y[8];
+  float pre[8];
+  f32x2 b[4], v[4];
+  lds_2x2(s_bias, b[0], b[1]);
+  lds_2x2(s_bias + 16u, b[2], b[3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = fadd2(pk2u(r[2 * i], r[2 * i + 1]), b[i]);
+  if (LN) {
+    f32x2 g[4], e[4];
+    lds_2x2(s_gam, g[0], g[1]);
+    lds_2x2(s_gam + 16u, g[2], g[3]);
+    lds_2x2(s_bet, e[0], e[1]);
+    lds_2x2(s_bet + 16u, e[2], e[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = ffma2(v[i], rstd2, nmr2);  // (x - mean) * rstd
+      if (SAVE) unpk2(v[i], pre[2 * i], pre[2 * i + 1]);
+      act_pair<ACT>(ffma2(v[i], g[i], e[i]), y[2 * i], y[2 * i + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (SAVE) unpk2(v[i], pre[2 * i], pre[2 * i + 1]);
+      act_pair<ACT>(v[i], y[2 * i], y[2 * i + 1]);
+    }
+  }
+  uint4 o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  if (SAVE) {   // invalid rows of the training forward stay zero (they are contraction indices of the weight gradient)
+    uint4 q = make_uint4(pack_bf16x2(pre[0], pre[1]), pack_bf16x2(pre[2], pre[3]), pack_bf16x2(pre[4], pre[5]),
+                         pack_bf16x2(pre[6], pre[7]));
+    if (!row_ok) {
+      o = make_uint4(0u, 0u, 0u, 0u);
+      q = make_uint4(0u, 0u, 0u, 0u);
+    }
+    *reinterpret_cast<uint4*>(dst_pre) = q;
+  }
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
 template <int ACT, bool LN, bool SAVE>
 __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chunks, int n_valid, int col0, int row,
                                              uint32_t s_bias, uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
-                                             __nv_bfloat16* obase, __nv_bfloat16* pbase, bool row_ok) {
+                                             __nv_bfloat16* obase, __nv_bfloat16* pbase, bool row_ok, int n_fast) {
   const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
-  tmem_sweep(tmem_d, cq, my_chunks, [&](const uint32_t (&r)[8], int i) {
+  int done = 0;
+  if (n_fast >= 4) {
+    // chunk i of this warp = columns (cq + 4 i) * 8 ..: k-tile (col0 >> 6) + (i >> 1), 16-byte position cq or cq + 4 inside
+    // the tile's 128-byte row (XOR-swizzled by the row) — two fixed offsets and a tile pointer that moves every other chunk
+    const int sw = row & 7;
+    const int pos0 = (cq ^ sw) << 3, pos1 = ((cq + 4) ^ sw) << 3;
+    __nv_bfloat16* o = obase + static_cast<size_t>(col0 >> 6) * (kTileM * kTileK);
+    __nv_bfloat16* q = SAVE ? pbase + static_cast<size_t>(col0 >> 6) * (kTileM * kTileK) : nullptr;
+    uint32_t sb = s_bias + 32u * cq, sg = s_gam + 32u * cq, se = s_bet + 32u * cq;
+    done = tmem_sweep_groups(
+        tmem_d + static_cast<uint32_t>(cq * 8), n_fast,
+        [&](const uint32_t (&r)[8], auto J) {
+          constexpr int j = decltype(J)::value;
+          constexpr int tile_off = (j >> 1) * (kTileM * kTileK);
+          const int pos = (j & 1) ? pos1 : pos0;
+          ln_act_chunk_full<ACT, LN, SAVE>(r, sb + 128u * j, sg + 128u * j, se + 128u * j, rstd2, nmr2,
+                                           o + tile_off + pos, SAVE ? q + tile_off + pos : nullptr, row_ok);
+        },
+        [&]() {
+          o += 2 * (kTileM * kTileK);
+          if (SAVE) q += 2 * (kTileM * kTileK);
+          sb += 512u;
+          sg += 512u;
+          se += 512u;
+        });
+  }
+  auto checked = [&](const uint32_t (&r)[8], int i) {   // bounds-checked (partial / padding chunks, odd shapes)
     const int c = (cq + 4 * i) * 8;
     const int oc = col0 + c;
     const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
     ln_act_chunk<ACT, LN, SAVE>(r, c, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, obase + off,
                                 SAVE ? pbase + off : nullptr, row_ok);
-  });
+  };
+  if (done == 0) {
+    tmem_sweep(tmem_d, cq, my_chunks, checked);
+    return;
+  }
+  for (int i = done; i < my_chunks; ++i) {   // at most three chunks left
+    uint32_t r[8];
+    tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * i) * 8), r);
+    tmem_ld_wait();
+    checked(r, i);
+  }
 }
 
 
@@ -256,15 +336,146 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[8], const uint4& p
   }
 }
 
+// bwd_chunk for a complete chunk of a valid row: no predicates, packed fp32x2 arithmetic, parameters at base + immediate
+template <int ACT, bool LN>
+__device__ __forceinline__ void bwd_chunk_full(const uint32_t (&r)[8], const uint4& pre_bits, uint32_t s_gam, uint32_t s_bet,
+                                               f32x2 (&da)[4], f32x2 (&dxh)[4], f32x2 (&pre)[4]) {
+  {
+    float f[8];
+    unpack_bf16x8(pre_bits, f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pre[i] = pk2(f[2 * i], f[2 * i + 1]);
+  }
+  f32x2 g[4];
+  if (LN) {
+    f32x2 e[4];
+    lds_2x2(s_gam, g[0], g[1]);
+    lds_2x2(s_gam + 16u, g[2], g[3]);
+    lds_2x2(s_bet, e[0], e[1]);
+    lds_2x2(s_bet + 16u, e[2], e[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[i] = ffma2(pre[i], g[i], e[i]);   // a = x_hat * gamma + beta
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f32x2 d = pk2(1.0f, 1.0f);
+      if (ACT == ACT_ELU) {   // act'(a) = a > 0 ? 1 : exp(a) = exp(min(a, 0))
+        float a0, a1;
+        unpk2(e[i], a0, a1);
+        const f32x2 t = fmul2(pk2(fminf(a0, 0.f), fminf(a1, 0.f)), pk2(1.4426950408889634f, 1.4426950408889634f));
+        float t0, t1;
+        unpk2(t, t0, t1);
+        d = pk2(ex2_approx(t0), ex2_approx(t1));
+      } else if (ACT == ACT_RELU) {
+        float a0, a1;
+        unpk2(e[i], a0, a1);
+        d = pk2(a0 > 0.f ? 1.0f : 0.f, a1 > 0.f ? 1.0f : 0.f);
+      }
+      da[i] = fmul2(pk2u(r[2 * i], r[2 * i + 1]), d);
+      dxh[i] = fmul2(da[i], g[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f32x2 d = pk2(1.0f, 1.0f);
+      float a0, a1;
+      unpk2(pre[i], a0, a1);
+      if (ACT == ACT_ELU) {
+        const f32x2 t = fmul2(pk2(fminf(a0, 0.f), fminf(a1, 0.f)), pk2(1.4426950408889634f, 1.4426950408889634f));
+        float t0, t1;
+        unpk2(t, t0, t1);
+        d = pk2(ex2_approx(t0), ex2_approx(t1));
+      } else if (ACT == ACT_RELU) {
+        d = pk2(a0 > 0.f ? 1.0f : 0.f, a1 > 0.f ? 1.0f : 0.f);
+      }
+      da[i] = fmul2(pk2u(r[2 * i], r[2 * i + 1]), d);
+      dxh[i] = da[i];
+    }
+  }
+}
+
 // the whole EPI_BWD epilogue of one tile (see GemmParams); returns nothing, writes out_bf16 / smem column sums
 template <int ACT, bool LN>
 __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, int cq, int my_chunks, int n_valid,
                                          int col0, int row, int lane, bool row_ok, uint32_t s_gam, uint32_t s_bet,
                                          uint32_t s_part, uint32_t s_acc, float rstd,
-                                         const __nv_bfloat16* pbase, __nv_bfloat16* obase) {
+                                         const __nv_bfloat16* pbase, __nv_bfloat16* obase, int n_fast) {
   float s1 = 0.f, s2 = 0.f;
   const bool colsum = LN && p.col_part != nullptr;
-  for (int i = 0; i < my_chunks; ++i) {
+  // ---- complete chunks of a warp whose 32 rows are all valid: software-pipelined sweep (TMEM and the saved x_hat of a
+  // chunk are fetched two chunks ahead), no predicates, per-chunk addresses = group base + immediate ------------------
+  int done = 0;
+  const int sw = row & 7;
+  const int pos0 = (cq ^ sw) << 3, pos1 = ((cq + 4) ^ sw) << 3;   // see ln_act_pass2
+  const size_t tile0 = static_cast<size_t>(col0 >> 6) * (kTileM * kTileK);
+  if (n_fast >= 4 && __all_sync(0xffffffffu, row_ok)) {
+    const __nv_bfloat16* q = pbase + tile0;
+    __nv_bfloat16* o = obase + tile0;
+    uint32_t sg = s_gam + 32u * cq, se = s_bet + 32u * cq, sa = s_acc + 32u * cq;
+    f32x2 s1a = pk2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
+    done = tmem_sweep_groups_g(
+        tmem_d + static_cast<uint32_t>(cq * 8), n_fast,
+        [&](int j) { return *reinterpret_cast<const uint4*>(q + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0)); },
+        [&](const uint32_t (&r)[8], const uint4& pb, auto J, uint32_t t) {
+          constexpr int j = decltype(J)::value;
+          f32x2 da[4], dxh[4], pre[4];
+          bwd_chunk_full<ACT, LN>(r, pb, sg + 128u * j, se + 128u * j, da, dxh, pre);
+          if (LN) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float x0, x1;
+              unpk2(dxh[i], x0, x1);
+              w[2 * i] = __float_as_uint(x0);
+              w[2 * i + 1] = __float_as_uint(x1);
+            }
+            tmem_st8(t + 32u * j, w);
+            s1a = fadd2(s1a, dxh[0]);
+            s1b = fadd2(s1b, dxh[1]);
+            s2a = ffma2(dxh[0], pre[0], s2a);
+            s2b = ffma2(dxh[1], pre[1], s2b);
+            s1a = fadd2(s1a, dxh[2]);
+            s1b = fadd2(s1b, dxh[3]);
+            s2a = ffma2(dxh[2], pre[2], s2a);
+            s2b = ffma2(dxh[3], pre[3], s2b);
+            if (colsum) {
+              float dg[8], db[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                unpk2(fmul2(da[i], pre[i]), dg[2 * i], dg[2 * i + 1]);
+                unpk2(da[i], db[2 * i], db[2 * i + 1]);
+              }
+              const float cg = colsum8(dg, lane);
+              const float cb = colsum8(db, lane);
+              if ((lane & 3) == 0) {
+                const uint32_t col4 = 4u * (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
+                red_shared_add(sa + 128u * j + col4, cg);
+                red_shared_add(sa + 128u * j + col4 + 4u * p.RB, cb);
+              }
+            }
+          } else {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) unpk2(dxh[i], y[2 * i], y[2 * i + 1]);
+            *reinterpret_cast<uint4*>(o + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0)) =
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          }
+        },
+        [&]() {
+          q += 2 * (kTileM * kTileK);
+          o += 2 * (kTileM * kTileK);
+          sg += 512u;
+          se += 512u;
+          sa += 512u;
+        });
+    if (LN) {
+      float a, b;
+      unpk2(fadd2(s1a, s1b), a, b);
+      s1 = a + b;
+      unpk2(fadd2(s2a, s2b), a, b);
+      s2 = a + b;
+    }
+  }
+  for (int i = done; i < my_chunks; ++i) {
     const int c = (cq + 4 * i) * 8;
     if (c >= n_valid) break;   // warp-uniform
     uint32_t r[8];
@@ -314,7 +525,30 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     const float m1 = ((a0.x + a1.x) + (a2.x + a3.x)) * inv_n;
     const float m2 = ((a0.y + a1.y) + (a2.y + a3.y)) * inv_n;
     const float nm1r = -m1 * rstd, nm2r = -m2 * rstd;
-    for (int i = 0; i < my_chunks; ++i) {
+    if (done > 0) {   // rstd * (dxh - m1 - x_hat * m2) over the complete chunks, pipelined as pass 1
+      const __nv_bfloat16* q = pbase + tile0;
+      __nv_bfloat16* o = obase + tile0;
+      const f32x2 rstd2 = pk2(rstd, rstd), nm1r2 = pk2(nm1r, nm1r), nm2r2 = pk2(nm2r, nm2r);
+      tmem_sweep_groups_g(
+          tmem_d + static_cast<uint32_t>(cq * 8), done,
+          [&](int j) { return *reinterpret_cast<const uint4*>(q + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0)); },
+          [&](const uint32_t (&r)[8], const uint4& pb, auto J, uint32_t) {
+            constexpr int j = decltype(J)::value;
+            float f[8], y[8];
+            unpack_bf16x8(pb, f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              unpk2(ffma2(pk2(f[2 * i], f[2 * i + 1]), nm2r2, ffma2(pk2u(r[2 * i], r[2 * i + 1]), rstd2, nm1r2)), y[2 * i],
+                    y[2 * i + 1]);
+            *reinterpret_cast<uint4*>(o + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0)) =
+                make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          },
+          [&]() {
+            q += 2 * (kTileM * kTileK);
+            o += 2 * (kTileM * kTileK);
+          });
+    }
+    for (int i = done; i < my_chunks; ++i) {
       const int c = (cq + 4 * i) * 8;
       if (c >= n_valid) break;
       uint32_t r[8];
@@ -566,6 +800,9 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       const uint32_t use = (nbuf == 2) ? static_cast<uint32_t>(it >> 1) : static_cast<uint32_t>(it);
       const int col0 = nb * p.RB;                   // first column of this block inside the group
       const int n_valid = min(p.RB, p.N - col0);    // valid columns in this block (may be <= 0)
+      // chunks of this warp that are complete and need no bounds checks (full-row LayerNorm epilogues)
+      const int n_fast = ((kLnAct || EPI == EPI_BWD) && (n_valid & 7) == 0 && (col0 & 63) == 0 && (n_valid >> 3) > cq)
+                             ? min(my_chunks, ((n_valid >> 3) - cq + 3) >> 2) : 0;
       const int pb = it & 1;
       const uint32_t s_bias = smem_u32(&ctl->bias[pb][0]);
       const uint32_t s_gam = smem_u32(&ctl->gamma[pb][0]);
@@ -597,7 +834,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           const float rs = (has_ln && row_ok) ? __ldg(p.bwd_rstd + static_cast<size_t>(g) * m_pad + m) : 0.f;
 #define RLSB_B(ACT, LN) \
   bwd_tile<ACT, LN>(p, tmem_d, cq, my_chunks, n_valid, col0, row, lane, row_ok, s_gam, s_bet, s_part, s_acc, rs, \
-                    p.bwd_pre + img, p.out_bf16 + img)
+                    p.bwd_pre + img, p.out_bf16 + img, n_fast)
           if (has_ln) {
             if (p.act == ACT_ELU) RLSB_B(ACT_ELU, true);
             else RLSB_B(ACT_NONE, true);
@@ -675,7 +912,42 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             }
           }
         };
-        tmem_sweep(tmem_d, cq, my_chunks, [&](const uint32_t (&r)[8], int i) { pass1_chunk(r, (cq + 4 * i) * 8); });
+        int done1 = 0;
+        if (kLnAct && n_fast >= 4) {   // complete chunks: statistics only, two independent accumulator pairs
+          f32x2 sumb = pk2(0.f, 0.f), sqb = pk2(0.f, 0.f);
+          uint32_t sb = s_bias + 32u * cq;
+          done1 = tmem_sweep_groups(
+              tmem_d + static_cast<uint32_t>(cq * 8), n_fast,
+              [&](const uint32_t (&r)[8], auto J) {
+                constexpr int j = decltype(J)::value;
+                f32x2 b[4], v2[4];
+                lds_2x2(sb + 128u * j, b[0], b[1]);
+                lds_2x2(sb + 128u * j + 16u, b[2], b[3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v2[i] = fadd2(pk2u(r[2 * i], r[2 * i + 1]), b[i]);
+                sum2 = fadd2(sum2, v2[0]);
+                sumb = fadd2(sumb, v2[1]);
+                sq2 = ffma2(v2[0], v2[0], sq2);
+                sqb = ffma2(v2[1], v2[1], sqb);
+                sum2 = fadd2(sum2, v2[2]);
+                sumb = fadd2(sumb, v2[3]);
+                sq2 = ffma2(v2[2], v2[2], sq2);
+                sqb = ffma2(v2[3], v2[3], sqb);
+              },
+              [&]() { sb += 512u; });
+          sum2 = fadd2(sum2, sumb);
+          sq2 = fadd2(sq2, sqb);
+        }
+        if (done1 == 0) {
+          tmem_sweep(tmem_d, cq, my_chunks, [&](const uint32_t (&r)[8], int i) { pass1_chunk(r, (cq + 4 * i) * 8); });
+        } else {
+          for (int i = done1; i < my_chunks; ++i) {
+            uint32_t r[8];
+            tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * i) * 8), r);
+            tmem_ld_wait();
+            pass1_chunk(r, (cq + 4 * i) * 8);
+          }
+        }
         {
           float s0, s1, q0, q1;
           unpk2(sum2, s0, s1);
@@ -714,7 +986,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
         __nv_bfloat16* pbase = p.save_pre ? p.save_pre + (obase - p.out_bf16) : nullptr;
 #define RLSB_P2(ACT, LN, SAVE) \
   ln_act_pass2<ACT, LN, SAVE>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase, \
-                              pbase, row_ok)
+                              pbase, row_ok, n_fast)
         if (EPI == EPI_LN_ACT_SAVE) {   // training forward (ELU only): also keep x_hat / the pre-activation
           if (has_ln) RLSB_P2(ACT_ELU, true, EPI == EPI_LN_ACT_SAVE);
           else RLSB_P2(ACT_ELU, false, EPI == EPI_LN_ACT_SAVE);

@@ -349,6 +349,80 @@ __device__ __forceinline__ void tmem_sweep(uint32_t tmem_d, int cq, int n_chunks
   }
 }
 
+// the same sweep for a run of chunks that needs no bounds checks: groups of four chunks with their position inside the
+// group known at compile time (f(r, std::integral_constant<int, J>) handles chunk 4 g + J of this warp, next_group() moves
+// the caller's pointers on), so that all per-chunk addresses are a base register plus an immediate.  t0 = TMEM address of
+// the warp's first chunk; consecutive chunks of a warp are 32 columns apart.  Returns the number of chunks handled
+// (a multiple of four); the caller finishes the remaining n % 4 chunks.
+template <int J>
+struct ChunkPos { static constexpr int value = J; };
+template <class F, class G>
+__device__ __forceinline__ int tmem_sweep_groups(uint32_t t0, int n, F&& f, G&& next_group) {
+  uint32_t a0[8] = {}, a1[8] = {}, b0[8] = {}, b1[8] = {};
+  const int groups = n >> 2;
+  if (groups > 0) {
+    tmem_ld8(t0, a0);
+    tmem_ld8(t0 + 32u, a1);
+  }
+  uint32_t t = t0;
+  for (int g = 0; g < groups; ++g) {
+    tmem_ld_wait2(a0, a1);
+    tmem_ld8(t + 64u, b0);
+    tmem_ld8(t + 96u, b1);
+    f(a0, ChunkPos<0>{});
+    f(a1, ChunkPos<1>{});
+    tmem_ld_wait2(b0, b1);
+    if (g + 1 < groups) {
+      tmem_ld8(t + 128u, a0);
+      tmem_ld8(t + 160u, a1);
+    }
+    f(b0, ChunkPos<2>{});
+    f(b1, ChunkPos<3>{});
+    t += 128u;
+    next_group();
+  }
+  return groups << 2;
+}
+
+// tmem_sweep_groups with a second, global-memory operand per chunk (16 bytes per thread): gload(j) fetches the operand of
+// chunk 4 g + j of the current group (j = 4, 5: first pair of the next group) two chunks ahead of its use, next to the TMEM
+// load of the same chunk, so that neither latency is exposed per chunk.  f(r, bits, ChunkPos<J>, t): t = TMEM address of
+// the group's first chunk.
+template <class P, class F, class G>
+__device__ __forceinline__ int tmem_sweep_groups_g(uint32_t t0, int n, P&& gload, F&& f, G&& next_group) {
+  uint32_t a0[8] = {}, a1[8] = {}, b0[8] = {}, b1[8] = {};
+  uint4 pa0 = make_uint4(0u, 0u, 0u, 0u), pa1 = pa0, pb0 = pa0, pb1 = pa0;
+  const int groups = n >> 2;
+  if (groups > 0) {
+    tmem_ld8(t0, a0);
+    tmem_ld8(t0 + 32u, a1);
+    pa0 = gload(0);
+    pa1 = gload(1);
+  }
+  uint32_t t = t0;
+  for (int g = 0; g < groups; ++g) {
+    tmem_ld_wait2(a0, a1);
+    tmem_ld8(t + 64u, b0);
+    tmem_ld8(t + 96u, b1);
+    pb0 = gload(2);
+    pb1 = gload(3);
+    f(a0, pa0, ChunkPos<0>{}, t);
+    f(a1, pa1, ChunkPos<1>{}, t);
+    tmem_ld_wait2(b0, b1);
+    if (g + 1 < groups) {
+      tmem_ld8(t + 128u, a0);
+      tmem_ld8(t + 160u, a1);
+      pa0 = gload(4);
+      pa1 = gload(5);
+    }
+    f(b0, pb0, ChunkPos<2>{}, t);
+    f(b1, pb1, ChunkPos<3>{}, t);
+    t += 128u;
+    next_group();
+  }
+  return groups << 2;
+}
+
 // ----------------------------------------------------------------------------------------
 // descriptors
 // ----------------------------------------------------------------------------------------

@@ -1,0 +1,11 @@
+# fast LN epilogue: parity tests, per-layer GEMM timings, sweep bench
+TAG=${1:-v12}
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo pytest_exit=$?
+tail -3 gpurun_out/pytest_gpu_$TAG.log
+timeout 300 python scripts/gemm_sweep.py 32768 2>&1 | tail -7
+timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_sweep_$TAG.json 2> gpurun_out/bench_sweep_$TAG.err; echo bench_exit=$?
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_sweep_$TAG.json"))
+print("sweep", d["ms_per_step"], d["e2e"]["ms_per_step"], d["gpu_launches"], d.get("imagination_only"), d["roofline"]["achieved"])
+PY
