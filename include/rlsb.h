@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RLSB_ABI_VERSION 2
+#define RLSB_ABI_VERSION 3
 
 /* ---- library / device ------------------------------------------------------------------- */
 int rlsb_abi_version(void);
@@ -179,6 +179,20 @@ typedef struct {
   const uint64_t* seed_device;
 } rlsb_noise;
 
+/* Slices of the rlsb_ac_update workspace that hold the ACTOR's forward activations (group 0 of the update's
+ * actor | critic images): the rollout evaluates ImaginativeActor.forward (agents/dreamer/ac.py:103-104) on every
+ * state anyway (agents/dreamer_v2.py:86), with the same weights and on the same packed state images the update
+ * reads, so it can leave layer outputs, x_hat and 1/std where ImaginativeActor.calculate_loss's backward pass
+ * (ac.py:113-146 under optimizer.py:55-57) expects them, and the update skips that half of its forward. */
+typedef struct rlsb_actor_slots {
+  void* x[4];        /* packed bf16 output of hidden layer l, step t at row t * m_pad: [H][m_pad x Hp] */
+  void* pre[4];      /* packed bf16 x_hat (LayerNorm) or pre-activation of layer l, same geometry */
+  float* rstd[4];    /* [H][m_pad] 1/sqrt(var + eps) of layer l */
+  int64_t m_pad;     /* rows per step image = rlsb_packed_rows(N) */
+  int32_t Hp;        /* padded hidden width */
+  int32_t steps;     /* H */
+} rlsb_actor_slots;
+
 typedef struct {
   float* determ;        /* (H+1, N, D)              row 0 = start state (written by the call)   */
   float* logits;        /* (H+1, N, groups*classes)  row 0 = start logits (copied)               */
@@ -196,6 +210,9 @@ typedef struct {
   void* stoch_packed;
   /* activation tape for rlsb_imagine_bwd (rlsb_imagine_tape_bytes bytes), or NULL */
   void* tape;
+  /* where the actor head's activations of steps 0..H-1 are kept for rlsb_ac_update (filled by rlsb_ac_actor_slots;
+   * needs determ_packed / stoch_packed, no tape, a flat RSSM), or NULL: the update then recomputes the actor forward */
+  const struct rlsb_actor_slots* actor_slots;
 } rlsb_imagine_out;
 
 /* bytes needed for packed weights / activation workspace for N start states */
@@ -244,6 +261,7 @@ typedef struct {
   float rho;               /* reinforce fraction (1 for discrete actors) */
   float eta;               /* entropy scale */
   int32_t metrics_samples; /* draws per element behind actor/avg_val, avg_sd, min_val, max_val (ac.py:137); 0 = skip */
+  int32_t actor_fwd_in_rollout; /* 1: rlsb_imagine_fwd filled the actor's slots (rlsb_imagine_out::actor_slots) */
 } rlsb_ac_cfg;
 
 typedef struct {
@@ -282,6 +300,8 @@ int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor, const rls
  * g_actions: (H, N, A) d loss_actor / d a_t from rlsb_imagine_bwd when rho != 1 (continuous actor), else NULL;
  * scalars: RLSB_AC_SCALARS floats (device).  seed (or the device-resident seed_device, if non-NULL) keys the
  * Philox stream of the metric draws. */
+/* the actor's slices of `workspace` (rlsb_ac_workspace_bytes(cfg, N) bytes) for rlsb_imagine_out::actor_slots */
+int rlsb_ac_actor_slots(const rlsb_ac_cfg* cfg, int64_t N, void* workspace, rlsb_actor_slots* slots);
 int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,
                    const void* stoch_packed, const float* vs, const float* w, const float* values,
                    const float* actions, const float* g_actions, uint64_t seed, const uint64_t* seed_device,

@@ -46,15 +46,21 @@ class Noise(C.Structure):
                 ("row_offset", C.c_uint32), ("precomp_actions", C.c_void_p), ("seed_device", C.c_void_p)]
 
 
+class ActorSlots(C.Structure):
+    """rlsb_actor_slots: the actor's slices of the rlsb_ac_update workspace that rlsb_imagine_fwd fills."""
+    _fields_ = [("x", C.c_void_p * 4), ("pre", C.c_void_p * 4), ("rstd", C.c_void_p * 4), ("m_pad", C.c_int64),
+                ("Hp", C.c_int32), ("steps", C.c_int32)]
+
+
 class ImagineOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "determ", "logits", "stoch_idx", "stoch", "actions", "rewards", "discounts", "values",
-        "actor_raw", "determ_packed", "stoch_packed", "tape")]
+        "actor_raw", "determ_packed", "stoch_packed", "tape")] + [("actor_slots", C.POINTER(ActorSlots))]
 
 
 class AcCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "H")] + [
-        ("rho", C.c_float), ("eta", C.c_float), ("metrics_samples", C.c_int32)]
+        ("rho", C.c_float), ("eta", C.c_float), ("metrics_samples", C.c_int32), ("actor_fwd_in_rollout", C.c_int32)]
 
 
 class MlpGrads(C.Structure):
@@ -67,7 +73,7 @@ AC_SCALAR_NAMES = {
     "loss_actor": 4, "critic/avg_target_value": 5, "critic/avg_lambda_value": 6, "critic/avg_predicted_value": 7,
     "actor/avg_val": 8, "actor/mean_val": 9, "actor/avg_sd": 10, "actor/min_val": 11, "actor/max_val": 12}
 AC_SCALARS = 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class SlotCfg(C.Structure):
@@ -172,6 +178,7 @@ def load() -> C.CDLL:
         "rlsb_ac_packed_bytes": (sz, [C.POINTER(AcCfg)]),
         "rlsb_ac_workspace_bytes": (sz, [C.POINTER(AcCfg), i64]),
         "rlsb_ac_pack": (C.c_int, [C.POINTER(AcCfg), C.POINTER(MlpParams), C.POINTER(MlpParams), vp, vp]),
+        "rlsb_ac_actor_slots": (C.c_int, [C.POINTER(AcCfg), i64, vp, C.POINTER(ActorSlots)]),
         "rlsb_ac_update": (C.c_int, [C.POINTER(AcCfg), vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, vp, C.POINTER(MlpGrads),
                                      C.POINTER(MlpGrads), vp, vp, vp]),
         "rlsb_imagine_tape_bytes": (sz, [C.POINTER(ImagineCfg), i64]),

@@ -78,6 +78,7 @@ class DreamerV2(RlAgent):
         # in a CUDA graph and replay it; the Philox key lives in device memory so every replay draws fresh noise
         self.cuda_graph = True
         self.cuda_graph_max_rows = int(os.environ.get('RLSB_GRAPH_MAX_ROWS', 32768))
+        self.reuse_actor_forward = os.environ.get('RLSB_ACTOR_REUSE', '1') != '0'   # K1's actor activations feed K4
         self.max_rows_per_pass = 131072   # start states per pass of the fused update (HBM sizing, _fused_step_chunked)
         # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
         # T sequential steps of small kernels — thousands of launches whose CPU dispatch cost exceeds their GPU time)
@@ -149,7 +150,7 @@ class DreamerV2(RlAgent):
 
     def imagine_trajectory(self, init_state: State, precomp_actions: t.Optional[list[Action]] = None,
                            horizon: t.Optional[int] = None, noise: t.Optional[dict] = None,
-                           keep_packed: bool = False, tape: bool = False
+                           keep_packed: bool = False, tape: bool = False, actor_slots=None
                            ) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
         """H-step closed-loop rollout from (1, N, .) start states (dreamer_v2.py:68-96).
 
@@ -183,7 +184,7 @@ class DreamerV2(RlAgent):
         out = eng.rollout(h0, z0, logits0, latent_uniforms=noise.get('latent_uniforms'),
                           action_noise=noise.get('action_noise'), seed=noise.get('seed', 0),
                           row_offset=noise.get('row_offset', 0), precomp_actions=pre, horizon=horizon,
-                          keep_packed=keep_packed, want_stoch=not keep_packed, tape=tape)
+                          keep_packed=keep_packed, want_stoch=not keep_packed, tape=tape, actor_slots=actor_slots)
         self.last_rollout = out
         wm = self.world_model
         if slotted:
@@ -488,17 +489,22 @@ class DreamerV2(RlAgent):
         """pack (if stale) -> K1 -> K2 [-> K2 bwd -> K1 bwd] -> K4; returns the K4 scalar vector (device)."""
         from rl_sandbox_b200 import ops
         dyn = self.actor.rho != 1.0   # dynamics back-propagation (ac.py:121-123): K2 bwd -> K1 bwd -> g_actions
+        # the rollout evaluates the actor on every state with the weights the update differentiates: it leaves the
+        # actor's activations in the update's workspace and K4 runs the critic's forward only
+        reuse = self.reuse_actor_forward and not dyn
         if static is None:
-            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True, tape=dyn)
-            k1 = self.last_rollout
             ac = self._get_ac_engine()
+            slots = ac.actor_slots(initial_states.determ.shape[1], self.imagination_horizon) if reuse else None
+            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True, tape=dyn, actor_slots=slots)
+            k1 = self.last_rollout
         else:   # graph body: always re-pack (the parameters change between replays), static buffers, device-resident key
             eng, ac = static['eng'], static['ac']
             eng.pack(self.world_model.state_dict(), self.actor.state_dict(), self.critic.state_dict())
             ac.pack(self.actor.state_dict(), self.critic.state_dict())
+            slots = ac.actor_slots(static['h0'].shape[0], self.imagination_horizon) if reuse else None
             k1 = eng.rollout(static['h0'], static['z0'], static['logits0'], seed_device=seed_device,
                              row_offset=noise.get('row_offset', 0), keep_packed=True, tape=dyn, want_stoch=False,
-                             out=static.get('out'))
+                             out=static.get('out'), actor_slots=slots)
             static['out'] = k1
             self.last_rollout = k1
         H, n = k1['determ'].shape[0] - 1, k1['determ'].shape[1]
@@ -512,7 +518,7 @@ class DreamerV2(RlAgent):
             g_r, g_v, _ = ops.lambda_return_bwd(g_vs, k1['values'], k1['discounts'], vs, self.critic.lambda_)
             g_actions = self._engine.backward(k1, g_r, g_v)
         return ac.update(k1, vs, w, self.actor.actor, self.critic.critic, seed=self._noise_seed + self._rollouts,
-                         horizon=H, g_actions=g_actions, seed_device=seed_device)
+                         horizon=H, g_actions=g_actions, seed_device=seed_device, actor_forward_done=reuse)
 
     def _fused_step_graphed(self, initial_states: State, noise: dict):
         """CUDA-graph replay of ``_fused_step`` for one (rows, horizon, shard offset) shape."""

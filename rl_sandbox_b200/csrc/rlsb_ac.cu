@@ -476,6 +476,24 @@ extern "C" int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor
   return batch.end();
 }
 
+extern "C" int rlsb_ac_actor_slots(const rlsb_ac_cfg* cfg, int64_t N, void* workspace, rlsb_actor_slots* slots) {
+  if (!cfg || !workspace || !slots || N <= 0) return -1;
+  AcPlan P;
+  RLSB_TRY(make_ac_plan(*cfg, P));
+  AcWorkspace W;
+  RLSB_TRY(make_ac_workspace(P, N, W));
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  for (int l = 0; l < 4; ++l) {   // group 0 (actor) comes first in every [actor | critic] image
+    slots->x[l] = ws + W.x[l];
+    slots->pre[l] = ws + W.pre[l];
+    slots->rstd[l] = reinterpret_cast<float*>(ws + W.rstd[l]);
+  }
+  slots->m_pad = W.m_pad;
+  slots->Hp = P.Hp;
+  slots->steps = P.H;
+  return 0;
+}
+
 extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,
                               const void* stoch_packed, const float* vs, const float* w, const float* values,
                               const float* actions, const float* g_actions, uint64_t seed,
@@ -507,12 +525,16 @@ extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_
   const __nv_bfloat16* ones = pbf(P.ones_off);
 
   // ---- forward: actor | critic on every state of steps 0..H-1 -----------------------------------
+  // (the hidden layers of the actor — group 0 — are already in place when the rollout filled its slots: only the
+  //  critic — group 1 — runs them; the small last layer runs for both)
+  const bool actor_done = cfg->actor_fwd_in_rollout != 0;
   for (int l = 0; l < 5; ++l) {
     const AcLayer& L = P.L[l];
+    const int g0 = (actor_done && l < 4) ? 1 : 0;   // first group of this launch
     GemmParams g{};
-    g.W = pbf(L.w_off); g.RB = L.RB; g.NB = 1; g.G = kG;
+    g.W = pbf(L.w_off) + static_cast<size_t>(g0) * L.RB * L.kp; g.RB = L.RB; g.NB = 1; g.G = kG - g0;
     g.M = M; g.m_tiles = m_tiles; g.N = L.N;
-    g.bias = pf(L.bias_off);
+    g.bias = pf(L.bias_off) + static_cast<size_t>(g0) * L.RB;
     g.ln_eps = eps;
     g.row_period = W.m_pad; g.row_valid = static_cast<int>(N);
     if (l == 0) {
@@ -521,16 +543,16 @@ extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_
       g.A[1] = zimg; g.a_ktiles[1] = P.Sp / 64; g.a_group_stride[1] = 0;
     } else {
       g.n_seg = 1;
-      g.A[0] = bfw(W.x[l - 1]); g.a_ktiles[0] = P.Hp / 64; g.a_group_stride[0] = act_gs;
+      g.A[0] = bfw(W.x[l - 1]) + static_cast<size_t>(g0) * act_gs; g.a_ktiles[0] = P.Hp / 64; g.a_group_stride[0] = act_gs;
     }
     if (l < 4) {
       const bool has_ln = (l == 0) || ln;
-      g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
-      g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
+      g.ln_gamma = has_ln ? pf(L.g_off) + static_cast<size_t>(g0) * L.RB : nullptr;
+      g.ln_beta = has_ln ? pf(L.b_off) + static_cast<size_t>(g0) * L.RB : nullptr;
       g.act = ACT_ELU;
-      g.out_bf16 = bfw(W.x[l]); g.out_kpad = P.Hp; g.out_bf16_group_stride = act_gs;
-      g.save_pre = bfw(W.pre[l]);
-      g.save_rstd = has_ln ? reinterpret_cast<float*>(ws + W.rstd[l]) : nullptr;
+      g.out_bf16 = bfw(W.x[l]) + static_cast<size_t>(g0) * act_gs; g.out_kpad = P.Hp; g.out_bf16_group_stride = act_gs;
+      g.save_pre = bfw(W.pre[l]) + static_cast<size_t>(g0) * act_gs;
+      g.save_rstd = has_ln ? reinterpret_cast<float*>(ws + W.rstd[l]) + static_cast<size_t>(g0) * M : nullptr;
       RLSB_TRY(launch_gemm(g, EPI_LN_ACT, s));
     } else {
       g.out_f32 = head_out; g.ldo = 32; g.out_group_stride = static_cast<long long>(M) * 32;

@@ -136,7 +136,7 @@ __device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int 
   }
   *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
                                               pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-  if (SAVE)
+  if (SAVE && dst_pre)
     *reinterpret_cast<uint4*>(dst_pre) = make_uint4(pack_bf16x2(pre[0], pre[1]), pack_bf16x2(pre[2], pre[3]),
                                                     pack_bf16x2(pre[4], pre[5]), pack_bf16x2(pre[6], pre[7]));
 }
@@ -180,7 +180,7 @@ __device__ __forceinline__ void ln_act_chunk_full(const uint32_t (&r)[8], uint32
       o = make_uint4(0u, 0u, 0u, 0u);
       q = make_uint4(0u, 0u, 0u, 0u);
     }
-    *reinterpret_cast<uint4*>(dst_pre) = q;
+    if (dst_pre) *reinterpret_cast<uint4*>(dst_pre) = q;
   }
   *reinterpret_cast<uint4*>(dst) = o;
 }
@@ -197,7 +197,7 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
     const int sw = row & 7;
     const int pos0 = (cq ^ sw) << 3, pos1 = ((cq + 4) ^ sw) << 3;
     __nv_bfloat16* o = obase + static_cast<size_t>(col0 >> 6) * (kTileM * kTileK);
-    __nv_bfloat16* q = SAVE ? pbase + static_cast<size_t>(col0 >> 6) * (kTileM * kTileK) : nullptr;
+    __nv_bfloat16* q = (SAVE && pbase) ? pbase + static_cast<size_t>(col0 >> 6) * (kTileM * kTileK) : nullptr;
     uint32_t sb = s_bias + 32u * cq, sg = s_gam + 32u * cq, se = s_bet + 32u * cq;
     done = tmem_sweep_groups(
         tmem_d + static_cast<uint32_t>(cq * 8), n_fast,
@@ -206,11 +206,11 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
           constexpr int tile_off = (j >> 1) * (kTileM * kTileK);
           const int pos = (j & 1) ? pos1 : pos0;
           ln_act_chunk_full<ACT, LN, SAVE>(r, sb + 128u * j, sg + 128u * j, se + 128u * j, rstd2, nmr2,
-                                           o + tile_off + pos, SAVE ? q + tile_off + pos : nullptr, row_ok);
+                                           o + tile_off + pos, (SAVE && q) ? q + tile_off + pos : nullptr, row_ok);
         },
         [&]() {
           o += 2 * (kTileM * kTileK);
-          if (SAVE) q += 2 * (kTileM * kTileK);
+          if (SAVE && q) q += 2 * (kTileM * kTileK);
           sb += 512u;
           sg += 512u;
           se += 512u;
@@ -221,7 +221,7 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
     const int oc = col0 + c;
     const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
     ln_act_chunk<ACT, LN, SAVE>(r, c, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, obase + off,
-                                SAVE ? pbase + off : nullptr, row_ok);
+                                (SAVE && pbase) ? pbase + off : nullptr, row_ok);
   };
   if (done == 0) {
     tmem_sweep(tmem_d, cq, my_chunks, checked);
@@ -649,9 +649,9 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             p.W + static_cast<size_t>(gnb) * kt_total * (static_cast<size_t>(p.RB) * kTileK);
         int kt_glob = 0;
         for (int s = 0; s < p.n_seg; ++s) {
-          const __nv_bfloat16* asrc = p.A[s] + static_cast<size_t>(g) * p.a_group_stride[s] +
-                                      static_cast<size_t>(m_tile) * p.a_ktiles[s] *
-                                          (kTileM * kTileK);
+          const __nv_bfloat16* abase = (s == 0 && p.alt_A != nullptr && g + 1 == p.alt_group_p1)
+                                           ? p.alt_A : p.A[s] + static_cast<size_t>(g) * p.a_group_stride[s];
+          const __nv_bfloat16* asrc = abase + static_cast<size_t>(m_tile) * p.a_ktiles[s] * (kTileM * kTileK);
           for (int kt = 0; kt < p.a_ktiles[s]; ++kt, ++kt_glob) {
             mbar_wait(&ctl->empty[stage], phase ^ 1u);
             uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
@@ -971,7 +971,10 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             mean = tsum * inv_n;
             const float var = fmaxf(tsq * inv_n - mean * mean, 0.f);
             rstd = 1.0f / sqrtf(var + p.ln_eps);
-            if (p.save_rstd && cq == 0 && tile_ok) p.save_rstd[static_cast<size_t>(g) * m_pad + m] = rstd;
+            if (p.save_rstd && cq == 0 && tile_ok) {
+              if (p.alt_group_p1 == 0) p.save_rstd[static_cast<size_t>(g) * m_pad + m] = rstd;
+              else if (g + 1 == p.alt_group_p1) p.save_rstd[m] = rstd;
+            }
           }
         }
       }
@@ -979,11 +982,16 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       // ---- pass 2 (EPI_LN_ACT): normalise, activate, write the packed bf16 operand image --------
       if (kLnAct && tile_ok) {
         const float nmr = -mean * rstd;
-        __nv_bfloat16* obase = p.out_bf16 + static_cast<size_t>(g) * p.out_bf16_group_stride +
-                               static_cast<size_t>(m_tile) * (p.out_kpad >> 6) * (kTileM * kTileK) +
-                               static_cast<size_t>(row) * kTileK;
+        const bool alt = (g + 1 == p.alt_group_p1);
+        const size_t tile_off = static_cast<size_t>(m_tile) * (p.out_kpad >> 6) * (kTileM * kTileK) +
+                                static_cast<size_t>(row) * kTileK;
+        const size_t goff = static_cast<size_t>(g) * p.out_bf16_group_stride;
+        __nv_bfloat16* obase = (alt ? p.alt_out_bf16 : p.out_bf16 + goff) + tile_off;
         const int tot_chunks = p.RB >> 3;
-        __nv_bfloat16* pbase = p.save_pre ? p.save_pre + (obase - p.out_bf16) : nullptr;
+        // saves: every group (training forward of rlsb_ac_update) or, with an alt group, that group alone
+        __nv_bfloat16* pbase = !p.save_pre ? nullptr
+                               : (p.alt_group_p1 == 0 ? p.save_pre + goff + tile_off
+                                                      : (alt ? p.save_pre + tile_off : nullptr));
 #define RLSB_P2(ACT, LN, SAVE) \
   ln_act_pass2<ACT, LN, SAVE>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase, \
                               pbase, row_ok, n_fast)

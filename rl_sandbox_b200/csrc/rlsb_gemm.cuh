@@ -65,6 +65,13 @@ struct GemmParams {
   const float* bwd_rstd;         // [G][M_pad] or nullptr
   float* col_part;               // [gridDim.x][G][2][RB] (zeroed by the launcher) or nullptr
   int group_major;               // work order: all M tiles of group 0, then group 1, ... (EPI_BWD)
+  // ---- one group of a grouped launch living in other buffers (K1's actor head, whose activations rlsb_ac_update reuses
+  //      instead of recomputing them): group alt_group_p1 - 1 (0 = none) reads its segment-0 A operand from alt_A (if
+  //      non-null), writes its packed output to alt_out_bf16, and is the only group that stores save_pre / save_rstd
+  //      (both then point at that group's image: no group stride is applied)
+  int alt_group_p1;
+  const __nv_bfloat16* alt_A;
+  __nv_bfloat16* alt_out_bf16;
 };
 
 // Launch on `stream`; returns cudaError_t as int (0 = ok) or a negative argument error.

@@ -262,6 +262,12 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   }
   auto tp = [&](int t, size_t off) { return tape + static_cast<size_t>(t) * TP.step_bytes + off; };
   const bool keep = out->determ_packed != nullptr && out->stoch_packed != nullptr;
+  // the actor head's activations of steps 0..H-1 go straight into the update's workspace (rlsb_ac_actor_slots)
+  const rlsb_actor_slots* slots = out->actor_slots;
+  if (slots && (tape || !keep || K > 1 || slots->steps != H || slots->m_pad != m_pad || slots->Hp != P.Hp)) return -7;
+  auto slot_img = [&](void* const* base, int l, int t) {
+    return static_cast<__nv_bfloat16*>(base[l]) + static_cast<size_t>(t) * m_pad * P.Hp;
+  };
   if ((out->determ_packed != nullptr) != (out->stoch_packed != nullptr)) return -4;
   auto himg = [&](int t) {
     return keep ? static_cast<__nv_bfloat16*>(out->determ_packed) + static_cast<size_t>(t) * ms_pad * P.Dp
@@ -374,9 +380,20 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
           g.save_pre = reinterpret_cast<__nv_bfloat16*>(tp(t, TP.head_pre[l]));
           g.save_rstd = has_ln ? reinterpret_cast<float*>(tp(t, TP.head_rstd[l])) : nullptr;
         }
+        if (slots && t < H) {   // the actor group reads / writes its slot of the update's images and keeps x_hat, rstd
+          g.alt_group_p1 = P.g_actor + 1;
+          g.alt_A = l > 0 ? slot_img(slots->x, l - 1, t) : nullptr;
+          g.alt_out_bf16 = slot_img(slots->x, l, t);
+          g.save_pre = slot_img(slots->pre, l, t);
+          g.save_rstd = has_ln ? slots->rstd[l] + static_cast<size_t>(t) * m_pad : nullptr;
+        }
         RLSB_TRY(launch_gemm(g, EPI_LN_ACT, s));
       } else {
         g.out_f32 = head_out; g.ldo = 32; g.out_group_stride = static_cast<long long>(m_pad) * 32;
+        if (slots && t < H) {
+          g.alt_group_p1 = P.g_actor + 1;
+          g.alt_A = slot_img(slots->x, 3, t);
+        }
         RLSB_TRY(launch_gemm(g, EPI_PLAIN, s));
       }
     }

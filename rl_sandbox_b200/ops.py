@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (AcCfg, ImagineCfg, ImagineOut, ImagineParams, MlpGrads, MlpParams, Noise, SlotCfg,
+from ._lib import (AcCfg, ActorSlots, ImagineCfg, ImagineOut, ImagineParams, MlpGrads, MlpParams, Noise, SlotCfg,
                    SlotGrads, SlotParams, check)
 
 
@@ -344,7 +344,9 @@ class ImaginationEngine:
                 seed: int = 0, row_offset: int = 0, precomp_actions: Optional[torch.Tensor] = None,
                 horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
                 out: Optional[dict] = None, keep_packed: bool = False, tape: bool = False,
-                seed_device: Optional[torch.Tensor] = None) -> dict:
+                seed_device: Optional[torch.Tensor] = None, actor_slots=None) -> dict:
+        """``actor_slots`` (``ACUpdateEngine.actor_slots(n)``): the actor head's activations of steps 0..H-1 are written
+        into the update's workspace, so that ``ACUpdateEngine.update(..., actor_forward_done=True)`` skips that forward."""
         cfg = self.cfg
         H = horizon if horizon is not None else cfg.H
         ccfg = cfg.to_c()
@@ -385,6 +387,8 @@ class ImaginationEngine:
         co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
                                                       "rewards", "discounts", "values", "actor_raw",
                                                       "determ_packed", "stoch_packed", "tape")])
+        if actor_slots is not None:
+            co.actor_slots = C.pointer(actor_slots)
         nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)),
                    _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
                    _ptr(None if precomp_actions is None else _f32c(precomp_actions)), _ptr(seed_device))
@@ -467,9 +471,25 @@ class ACUpdateEngine:
               "rlsb_ac_pack")
         self._keep = keep
 
+    def _workspace(self, ccfg, n: int) -> torch.Tensor:
+        if self._ws is None or self._ws_rows < n:
+            nbytes = self.lib.rlsb_ac_workspace_bytes(C.byref(ccfg), n)
+            self._ws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+            self._ws_rows = n
+        return self._ws
+
+    def actor_slots(self, n: int, horizon: Optional[int] = None) -> ActorSlots:
+        """Where ``ImaginationEngine.rollout(..., actor_slots=...)`` leaves the actor's activations for ``update``."""
+        ccfg = AcCfg.from_buffer_copy(self.ccfg)
+        ccfg.H = horizon if horizon is not None else self.cfg.H
+        ws = self._workspace(ccfg, n)   # the slices are laid out for n rows; update(n) uses the same layout
+        slots = ActorSlots()
+        check(self.lib.rlsb_ac_actor_slots(C.byref(ccfg), n, ws.data_ptr(), C.byref(slots)), "rlsb_ac_actor_slots")
+        return slots
+
     def update(self, rollout: dict, vs: torch.Tensor, w: torch.Tensor, actor_seq, critic_seq, seed: int = 0,
                horizon: Optional[int] = None, g_actions: Optional[torch.Tensor] = None,
-               seed_device: Optional[torch.Tensor] = None) -> torch.Tensor:
+               seed_device: Optional[torch.Tensor] = None, actor_forward_done: bool = False) -> torch.Tensor:
         """Writes .grad of every parameter of ``actor_seq`` / ``critic_seq`` (fc_nn Sequentials) and returns the
         RLSB_AC_SCALARS loss / metric vector (device tensor, see _lib.AC_SCALAR_NAMES)."""
         if rollout.get("determ_packed") is None:
@@ -478,10 +498,10 @@ class ACUpdateEngine:
         H = horizon if horizon is not None else self.cfg.H
         ccfg = AcCfg.from_buffer_copy(self.ccfg)
         ccfg.H = H
-        if self._ws is None or self._ws_rows < n:
-            nbytes = self.lib.rlsb_ac_workspace_bytes(C.byref(ccfg), n)
-            self._ws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
-            self._ws_rows = n
+        ccfg.actor_fwd_in_rollout = int(actor_forward_done)
+        if actor_forward_done and (self._ws is None or self._ws_rows < n):
+            raise _lib.RlsbError("update(actor_forward_done=True): the rollout must have been given actor_slots(n) of this engine")
+        self._workspace(ccfg, n)
         keep: list = []
         ga, gc = _mlp_grads(actor_seq, keep), _mlp_grads(critic_seq, keep)
         vs, w = _f32c(vs), _f32c(w)

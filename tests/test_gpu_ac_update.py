@@ -305,6 +305,42 @@ def test_cuda_graph_replay_matches_eager(cuda, name):
     print(f"[parity] {name}: graph replays track eager steps (step 0 bit-identical; later steps to fp32 rounding)")
 
 
+@pytest.mark.parametrize("graphed", [False, True])
+def test_actor_forward_reuse_matches_recompute(cuda, graphed):
+    """K1 leaves the actor head's activations (layer outputs, x_hat, 1/std of steps 0..H-1) in the update's workspace
+    (rlsb_imagine_out::actor_slots) and K4 skips the actor's forward: same kernel, same operands -> the losses and the
+    weight / bias gradients are bit-identical to the update that recomputes the actor forward itself."""
+    from rl_sandbox.agents.dreamer.rssm import State
+    c = load_case("c1")
+    m = c["meta"]
+    N = 300   # not a multiple of 128: padding rows of the last tile stay zero in the reused images too
+    g = torch.Generator(device="cuda").manual_seed(5)
+    h0 = 0.5 * torch.randn(N, m["D"], device="cuda", generator=g)
+    z0 = torch.nn.functional.one_hot(torch.randint(0, 32, (N, 32), device="cuda", generator=g), 32).float().view(N, 1024)
+    res = []
+    for reuse in (True, False):
+        a = make_agent(m, "cuda", H=5)
+        load_params(a, c)
+        a.cuda_graph = graphed
+        a.reuse_actor_forward = reuse
+        init = State(h0.unsqueeze(0), torch.zeros(1, N, 32, 32, device="cuda"), z0.unsqueeze(0))
+        from rl_sandbox_b200 import _lib
+        before = _lib.load().rlsb_launch_count(0)
+        losses, _ = a.behaviour_update(init, noise={"seed": 91})
+        launches = _lib.load().rlsb_launch_count(0) - before
+        grads = {n: p.grad.clone() for n, p in list(a.actor.named_parameters()) + list(a.critic.critic.named_parameters())}
+        res.append((losses, grads, launches))
+    for k in res[0][0]:
+        assert torch.equal(res[0][0][k], res[1][0][k]), k
+    for n, ga in res[0][1].items():
+        gb = res[1][1][n]
+        if ga.dim() == 2:
+            assert torch.equal(ga, gb), n
+        else:   # biases through the ones tile are deterministic too; LayerNorm gamma / beta use smem float atomics
+            torch.testing.assert_close(ga, gb, rtol=1e-4, atol=1e-7, msg=lambda s_: f"{n}: {s_}")
+    print(f"[parity] actor forward reuse (graphed={graphed}): losses and weight gradients bit-identical")
+
+
 def test_ac_update_full_size_properties(cuda):
     """BASELINE sweep size (32768 start states x H = 15), size-independent properties of K4:
     weight / bias gradients are bitwise reproducible run to run (fixed-order split reductions), everything is finite,
