@@ -79,6 +79,7 @@ class DreamerV2(RlAgent):
         self.cuda_graph = True
         self.cuda_graph_max_rows = int(os.environ.get('RLSB_GRAPH_MAX_ROWS', 32768))
         self.reuse_actor_forward = os.environ.get('RLSB_ACTOR_REUSE', '1') != '0'   # K1's actor activations feed K4
+        self.reuse_actor_min_rows = 2048   # below: launch-latency bound, the extra stores of the rollout cost more (800 rows: +2 %)
         self.max_rows_per_pass = 131072   # start states per pass of the fused update (HBM sizing, _fused_step_chunked)
         # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
         # T sequential steps of small kernels — thousands of launches whose CPU dispatch cost exceeds their GPU time)
@@ -491,7 +492,8 @@ class DreamerV2(RlAgent):
         dyn = self.actor.rho != 1.0   # dynamics back-propagation (ac.py:121-123): K2 bwd -> K1 bwd -> g_actions
         # the rollout evaluates the actor on every state with the weights the update differentiates: it leaves the
         # actor's activations in the update's workspace and K4 runs the critic's forward only
-        reuse = self.reuse_actor_forward and not dyn
+        n_rows = initial_states.determ.shape[1] if static is None else static['h0'].shape[0]
+        reuse = self.reuse_actor_forward and not dyn and n_rows >= self.reuse_actor_min_rows
         if static is None:
             ac = self._get_ac_engine()
             slots = ac.actor_slots(initial_states.determ.shape[1], self.imagination_horizon) if reuse else None

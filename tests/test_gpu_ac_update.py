@@ -323,6 +323,7 @@ def test_actor_forward_reuse_matches_recompute(cuda, graphed):
         load_params(a, c)
         a.cuda_graph = graphed
         a.reuse_actor_forward = reuse
+        a.reuse_actor_min_rows = 0
         init = State(h0.unsqueeze(0), torch.zeros(1, N, 32, 32, device="cuda"), z0.unsqueeze(0))
         from rl_sandbox_b200 import _lib
         before = _lib.load().rlsb_launch_count(0)
