@@ -88,9 +88,9 @@ __device__ __forceinline__ void act_pair(f32x2 a2, float& y0, float& y1) {
 // pass 2 of the full-row epilogue for one 8-column chunk: bias, [LayerNorm affine], activation,
 // bf16 pack, one 16-byte store into the packed operand image (packed fp32x2 arithmetic).
 template <int ACT, bool LN, bool SAVE>
-__device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int n_valid, uint32_t s_bias,
-                                             uint32_t s_gam, uint32_t s_bet, f32x2 rstd2, f32x2 nmr2,
-                                             __nv_bfloat16* dst, __nv_bfloat16* dst_pre, bool row_ok) {
+__device__ __forceinline__ void ln_act_chunk_words(const uint32_t (&r)[8], int c, int n_valid, uint32_t s_bias,
+                                                   uint32_t s_gam, uint32_t s_bet, f32x2 rstd2, f32x2 nmr2, bool row_ok,
+                                                   uint4& o, uint4& q) {
   float y[8];
   float pre[8];
   if (c >= n_valid || (SAVE && !row_ok)) {  // padding columns of the block / invalid row (training forward)
@@ -134,18 +134,26 @@ __device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int 
         }
     }
   }
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                              pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-  if (SAVE && dst_pre)
-    *reinterpret_cast<uint4*>(dst_pre) = make_uint4(pack_bf16x2(pre[0], pre[1]), pack_bf16x2(pre[2], pre[3]),
-                                                    pack_bf16x2(pre[4], pre[5]), pack_bf16x2(pre[6], pre[7]));
+  o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  if (SAVE)
+    q = make_uint4(pack_bf16x2(pre[0], pre[1]), pack_bf16x2(pre[2], pre[3]), pack_bf16x2(pre[4], pre[5]),
+                   pack_bf16x2(pre[6], pre[7]));
+}
+template <int ACT, bool LN, bool SAVE>
+__device__ __forceinline__ void ln_act_chunk(const uint32_t (&r)[8], int c, int n_valid, uint32_t s_bias,
+                                             uint32_t s_gam, uint32_t s_bet, f32x2 rstd2, f32x2 nmr2,
+                                             __nv_bfloat16* dst, __nv_bfloat16* dst_pre, bool row_ok) {
+  uint4 o, q = make_uint4(0u, 0u, 0u, 0u);
+  ln_act_chunk_words<ACT, LN, SAVE>(r, c, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, row_ok, o, q);
+  *reinterpret_cast<uint4*>(dst) = o;
+  if (SAVE && dst_pre) *reinterpret_cast<uint4*>(dst_pre) = q;
 }
 
 // the same for a chunk known to be complete (all 8 columns valid): no bounds checks, parameter addresses = base + immediate
 template <int ACT, bool LN, bool SAVE>
-__device__ __forceinline__ void ln_act_chunk_full(const uint32_t (&r)[8], uint32_t s_bias, uint32_t s_gam, uint32_t s_bet,
-                                                  f32x2 rstd2, f32x2 nmr2, __nv_bfloat16* dst, __nv_bfloat16* dst_pre,
-                                                  bool row_ok) {
+__device__ __forceinline__ void ln_act_chunk_full_words(const uint32_t (&r)[8], uint32_t s_bias, uint32_t s_gam,
+                                                        uint32_t s_bet, f32x2 rstd2, f32x2 nmr2, bool row_ok, uint4& o,
+                                                        uint4& q) {
   float y[8];
   float pre[8];
   f32x2 b[4], v[4];
@@ -172,16 +180,23 @@ __device__ __forceinline__ void ln_act_chunk_full(const uint32_t (&r)[8], uint32
       act_pair<ACT>(v[i], y[2 * i], y[2 * i + 1]);
     }
   }
-  uint4 o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  o = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
   if (SAVE) {   // invalid rows of the training forward stay zero (they are contraction indices of the weight gradient)
-    uint4 q = make_uint4(pack_bf16x2(pre[0], pre[1]), pack_bf16x2(pre[2], pre[3]), pack_bf16x2(pre[4], pre[5]),
-                         pack_bf16x2(pre[6], pre[7]));
+    q = make_uint4(pack_bf16x2(pre[0], pre[1]), pack_bf16x2(pre[2], pre[3]), pack_bf16x2(pre[4], pre[5]),
+                   pack_bf16x2(pre[6], pre[7]));
     if (!row_ok) {
       o = make_uint4(0u, 0u, 0u, 0u);
       q = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (dst_pre) *reinterpret_cast<uint4*>(dst_pre) = q;
   }
+}
+template <int ACT, bool LN, bool SAVE>
+__device__ __forceinline__ void ln_act_chunk_full(const uint32_t (&r)[8], uint32_t s_bias, uint32_t s_gam, uint32_t s_bet,
+                                                  f32x2 rstd2, f32x2 nmr2, __nv_bfloat16* dst, __nv_bfloat16* dst_pre,
+                                                  bool row_ok) {
+  uint4 o, q = make_uint4(0u, 0u, 0u, 0u);
+  ln_act_chunk_full_words<ACT, LN, SAVE>(r, s_bias, s_gam, s_bet, rstd2, nmr2, row_ok, o, q);
+  if (SAVE && dst_pre) *reinterpret_cast<uint4*>(dst_pre) = q;
   *reinterpret_cast<uint4*>(dst) = o;
 }
 
@@ -238,6 +253,58 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
 
 __device__ __forceinline__ void epi_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
+}
+
+// Pass 2 of the full-row epilogue with the output assembled in shared memory.  A thread owns one row, so its 16-byte
+// chunks land in 32 different 128-byte lines per warp store — the LSU then bounds the whole kernel (a bias-only epilogue
+// took 77 us where the main loop needs 24).  A 128 x 64 tile of the packed image is 16 KB of contiguous global memory in
+// exactly the layout it has here, so the 16 epilogue warps write their two chunks of k-tile kt into a 16 KB slot with
+// conflict-free STS.128 and one thread sends the slot with a single bulk copy (two slots: the copy of k-tile kt - 1 drains
+// while kt is assembled).  ph / pending carry the slot parity and "a copy is in flight" across tiles.
+template <int ACT, bool LN, bool SAVE>
+__device__ __forceinline__ void ln_act_pass2_staged(uint32_t tmem_d, int cq, int n_valid, int kt_out, int row, int tid_e,
+                                                    uint32_t s_bias, uint32_t s_gam, uint32_t s_bet, float rstd, float nmr,
+                                                    bool row_ok, uint8_t* stage_out, uint8_t* stage_pre,
+                                                    __nv_bfloat16* gout, __nv_bfloat16* gpre, uint32_t& ph, bool& pending) {
+  const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(nmr, nmr);
+  const uint32_t sw = static_cast<uint32_t>(row & 7);
+  const uint32_t so0 = smem_u32(stage_out) + static_cast<uint32_t>(row) * 128u;
+  const uint32_t sp0 = smem_u32(stage_pre) + static_cast<uint32_t>(row) * 128u;
+  const bool save_here = SAVE && gpre != nullptr;
+  for (int kt = 0; kt < kt_out; ++kt) {
+    const uint32_t slot = ph & 1u;
+    uint32_t r0[8] = {}, r1[8] = {};
+    const int ch0 = kt * 8 + cq, ch1 = ch0 + 4;
+    const int c0 = ch0 * 8, c1 = ch1 * 8;
+    if (c0 < n_valid) tmem_ld8(tmem_d + static_cast<uint32_t>(c0), r0);
+    if (c1 < n_valid) tmem_ld8(tmem_d + static_cast<uint32_t>(c1), r1);
+    tmem_ld_wait2(r0, r1);
+    uint4 o, q = make_uint4(0u, 0u, 0u, 0u);
+    if (c0 + 8 <= n_valid)
+      ln_act_chunk_full_words<ACT, LN, SAVE>(r0, s_bias + 4u * c0, s_gam + 4u * c0, s_bet + 4u * c0, rstd2, nmr2, row_ok, o, q);
+    else
+      ln_act_chunk_words<ACT, LN, SAVE>(r0, c0, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, row_ok, o, q);
+    sts128(so0 + slot * 16384u + ((static_cast<uint32_t>(cq) ^ sw) << 4), o);
+    if (save_here) sts128(sp0 + slot * 16384u + ((static_cast<uint32_t>(cq) ^ sw) << 4), q);
+    if (c1 + 8 <= n_valid)
+      ln_act_chunk_full_words<ACT, LN, SAVE>(r1, s_bias + 4u * c1, s_gam + 4u * c1, s_bet + 4u * c1, rstd2, nmr2, row_ok, o, q);
+    else
+      ln_act_chunk_words<ACT, LN, SAVE>(r1, c1, n_valid, s_bias, s_gam, s_bet, rstd2, nmr2, row_ok, o, q);
+    sts128(so0 + slot * 16384u + ((static_cast<uint32_t>(cq + 4) ^ sw) << 4), o);
+    if (save_here) sts128(sp0 + slot * 16384u + ((static_cast<uint32_t>(cq + 4) ^ sw) << 4), q);
+    // the copy of the previous k-tile has finished reading the other slot before anybody passes the barrier and
+    // starts to overwrite it
+    if (tid_e == 0 && pending) bulk_wait_read<0>();
+    fence_proxy_async_smem();   // this thread's slot writes are visible to the bulk-copy engine
+    epi_bar(4);
+    if (tid_e == 0) {
+      bulk_s2g(gout + static_cast<size_t>(kt) * (kTileM * kTileK), stage_out + slot * 16384u, 16384u);
+      if (save_here) bulk_s2g(gpre + static_cast<size_t>(kt) * (kTileM * kTileK), stage_pre + slot * 16384u, 16384u);
+      bulk_commit();
+    }
+    pending = true;
+    ph ^= 1u;
+  }
 }
 
 // work item -> (m_tile, g, nb).  The n-block index runs fastest so that the CTAs resident at any
@@ -590,7 +657,11 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
   const uint32_t a_bytes = kTileM * kTileK * 2;                 // 16 KB
   const uint32_t b_bytes = static_cast<uint32_t>(p.RB) * kTileK * 2 / (pair ? 2u : 1u);   // bytes staged per CTA
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  // staged output (ln_act_pass2_staged): two 16 KB slots for the output image (+ two for x_hat in the saving variant)
+  uint8_t* stage_out = smem + static_cast<size_t>(stages) * stage_bytes;
+  uint8_t* stage_pre = stage_out + 32768;
+  const uint32_t staging_bytes = (kLnAct && p.staged_out) ? (EPI == EPI_LN_ACT_SAVE ? 65536u : 32768u) : 0u;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(stage_out + staging_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -786,6 +857,8 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       epi_bar(3);
     };
     int it = 0;
+    uint32_t out_ph = 0;        // staged output: slot parity, carried across tiles
+    bool out_pending = false;   //                a bulk store of this CTA is in flight
     for (int w = cluster_id; w < total_work; w += num_clusters, ++it) {
       int m_tile, gnb;
       decode_work(p, w, cs, rank, m_tile, gnb);
@@ -992,9 +1065,18 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
         __nv_bfloat16* pbase = !p.save_pre ? nullptr
                                : (p.alt_group_p1 == 0 ? p.save_pre + goff + tile_off
                                                       : (alt ? p.save_pre + tile_off : nullptr));
-#define RLSB_P2(ACT, LN, SAVE) \
-  ln_act_pass2<ACT, LN, SAVE>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase, \
-                              pbase, row_ok, n_fast)
+        // staged: tile pointers without the row term (the slot already is the 128-row tile)
+        __nv_bfloat16* gout = obase - static_cast<size_t>(row) * kTileK;
+        __nv_bfloat16* gpre = pbase ? pbase - static_cast<size_t>(row) * kTileK : nullptr;
+#define RLSB_P2(ACT, LN, SAVE)                                                                                            \
+  do {                                                                                                                    \
+    if (p.staged_out)                                                                                                     \
+      ln_act_pass2_staged<ACT, LN, SAVE>(tmem_d, cq, n_valid, p.out_kpad >> 6, row, tid_e, s_bias, s_gam, s_bet, rstd, nmr, \
+                                         row_ok, stage_out, stage_pre, gout, gpre, out_ph, out_pending);                  \
+    else                                                                                                                  \
+      ln_act_pass2<ACT, LN, SAVE>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase,      \
+                                  pbase, row_ok, n_fast);                                                                 \
+  } while (0)
         if (EPI == EPI_LN_ACT_SAVE) {   // training forward (ELU only): also keep x_hat / the pre-activation
           if (has_ln) RLSB_P2(ACT_ELU, true, EPI == EPI_LN_ACT_SAVE);
           else RLSB_P2(ACT_ELU, false, EPI == EPI_LN_ACT_SAVE);
@@ -1008,8 +1090,8 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           else RLSB_P2(ACT_NONE, false, false);
         }
 #undef RLSB_P2
-        // zero the padding columns [RB, out_kpad) of the packed image (last block only)
-        if (nb == p.NB - 1) {
+        // zero the padding columns [RB, out_kpad) of the packed image (last block only; the staged path wrote them)
+        if (nb == p.NB - 1 && !p.staged_out) {
           for (int ch = tot_chunks + cq; ch < ((p.out_kpad - col0) >> 3); ch += 4) {
             const int oc = col0 + ch * 8;
             __nv_bfloat16* trow = obase + static_cast<size_t>(oc >> 6) * (kTileM * kTileK);
@@ -1026,6 +1108,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       }
     }
     if (bwd_colsum) flush_colsum(g_acc);
+    if (kLnAct && tid_e == 0 && out_pending) bulk_wait<0>();   // staged output: every bulk store has landed
   }
 
   tc_fence_before();
@@ -1041,6 +1124,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
 int g_num_sms = 0;
 int g_pair = 2;   // cta_group::2 for clusters of 2 (1: only n-blocks <= 256 columns, 0: multicast only); RLSB_PAIR overrides
 int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
+int g_staged = 1;         // full-row epilogues write their output through shared memory + bulk copies (RLSB_STAGED=0: 16-byte stores)
 
 }  // namespace
 
@@ -1059,6 +1143,7 @@ int init_device_info() {
     if (e != cudaSuccess) return static_cast<int>(e);
     if (const char* env = getenv("RLSB_CLUSTER")) set_gemm_cluster_size(atoi(env));
     if (const char* env = getenv("RLSB_PAIR")) g_pair = atoi(env);   // 0: multicast only, 1: pairs for RB <= 256, 2: all
+    if (const char* env = getenv("RLSB_STAGED")) g_staged = atoi(env);
   }
   return 0;
 }
@@ -1097,13 +1182,18 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   const int cs = pick_cluster(p);
   const int pair = (g_pair && cs == 2 && (p.RB % 32) == 0 && (p.RB <= 256 || g_pair > 1)) ? 1 : 0;
   const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2 / (pair ? 2 : 1);
-  const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256;
+  // full-row epilogues that own whole output tiles assemble them in shared memory (ln_act_pass2_staged)
+  const bool staged = g_staged && (epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB == 1;
+  const int staging_bytes = staged ? (epilogue == EPI_LN_ACT_SAVE ? 65536 : 32768) : 0;
+  const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256 - staging_bytes;
   static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return -6;
   const int nbuf = p.RB <= 256 ? 2 : 1;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + sizeof(SmemCtl) + 1024;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + staging_bytes + sizeof(SmemCtl) + 1024;
+  GemmParams q = p;
+  q.staged_out = staged ? 1 : 0;
   const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
   int clusters = g_num_sms / cs;
   if (total_work < clusters) clusters = total_work;
@@ -1140,8 +1230,8 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
       if (e != cudaSuccess) return static_cast<int>(e);                                          \
       attr_done = true;                                                                          \
     }                                                                                            \
-    if (pair) e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, true>, p, stages, nbuf, cs);         \
-    else e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, false>, p, stages, nbuf, cs);             \
+    if (pair) e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, true>, q, stages, nbuf, cs);         \
+    else e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, false>, q, stages, nbuf, cs);             \
     if (e != cudaSuccess) return static_cast<int>(e);                                            \
   } while (0)
   switch (epilogue) {

@@ -72,6 +72,9 @@ struct GemmParams {
   int alt_group_p1;
   const __nv_bfloat16* alt_A;
   __nv_bfloat16* alt_out_bf16;
+  // ---- set by launch_gemm (callers leave it 0): the full-row epilogue assembles each 128 x 64 output tile (16 KB, contiguous
+  //      in the packed image) in shared memory and writes it with one bulk copy instead of 16-byte stores scattered over 32 rows
+  int staged_out;
 };
 
 // Launch on `stream`; returns cudaError_t as int (0 = ok) or a negative argument error.

@@ -51,6 +51,9 @@ __device__ __forceinline__ float lds32(uint32_t a) {
 __device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t a, float x) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
 }
