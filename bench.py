@@ -209,6 +209,7 @@ def full_train_main(args, dims):
     device = f"cuda:{local}"
     _lib.require_device()
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device(device))
     torch.backends.cuda.matmul.allow_tf32 = True   # reference train.py:40
     lib = _lib.load()
@@ -301,6 +302,8 @@ def main():
     device = f"cuda:{local}"
     _lib.require_device()
     if world > 1:
+        # stdout carries the one JSON line only: NCCL's version / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(device))
     torch.backends.cuda.matmul.allow_tf32 = True   # as the reference's train.py:40 (loss MLPs run in torch)
     lib = _lib.load()
