@@ -38,6 +38,10 @@ long long rlsb_launch_count_add(long long n);
 /* tuning: CTAs per thread-block cluster sharing one weight block via TMA multicast (1, 2 or 4;
  * default 2, env RLSB_CLUSTER).  Returns the value in effect. */
 int rlsb_set_cluster_size(int cs);
+/* tuning: the full-row GEMM epilogues (LayerNorm / activation -> packed bf16 image) assemble each 128 x 64 output tile in
+ * shared memory and write it with one bulk copy (1, default; env RLSB_STAGED) or store 16 bytes per thread (0) — same
+ * bits either way.  Any other value only queries.  Returns the value in effect. */
+int rlsb_set_staged_output(int on);
 
 /* ---- K2: lambda-return + shifted-cumprod weights + advantage --------------------------------
  * replaces ImaginativeCritic._lambda_return (agents/dreamer/ac.py:52-62), the discount

@@ -49,6 +49,8 @@ extern "C" int rlsb_set_cluster_size(int cs) {
   return gemm_cluster_size();
 }
 
+extern "C" int rlsb_set_staged_output(int on) { return set_gemm_staged_output(on); }
+
 extern "C" int rlsb_check_device(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -1128,6 +1128,10 @@ int g_staged = 1;         // full-row epilogues write their output through share
 
 }  // namespace
 
+int set_gemm_staged_output(int on) {
+  if (on == 0 || on == 1) g_staged = on;
+  return g_staged;
+}
 void set_gemm_cluster_size(int cs) {
   if (cs == 1 || cs == 2 || cs == 4) g_cluster_size = cs;
 }

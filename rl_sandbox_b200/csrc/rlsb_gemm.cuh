@@ -85,5 +85,8 @@ int gemm_grid_size(const GemmParams& p);
 // CTAs per thread-block cluster that share one weight block through TMA multicast (1, 2 or 4)
 void set_gemm_cluster_size(int cs);
 int gemm_cluster_size();
+// full-row epilogues write their output tiles through shared memory + bulk copies (1, default) or with 16-byte stores (0);
+// any other value only queries.  Returns the value in effect.
+int set_gemm_staged_output(int on);
 
 }  // namespace rlsb

@@ -657,12 +657,13 @@ __global__ void __launch_bounds__(256, 4) sample_latent_kernel(const SampleLaten
     if (q == 0) a.idx_out[static_cast<size_t>(m) * a.groups + g] = static_cast<uint8_t>(best_k);
     if (a.onehot_packed && q < 4) {
       // group g occupies columns [32g, 32g+32): 4 chunks of 8 bf16, one per lane q = 0..3
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
       const int rel = best_k - q * 8;
-      if (rel >= 0 && rel < 8) w[rel >> 1] = (rel & 1) ? 0x3F800000u : 0x00003F80u;  // bf16 1.0
+      const uint32_t one = (rel & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+      const int word = (rel >= 0 && rel < 8) ? (rel >> 1) : -1;     // selects, not an indexed local array
       const size_t idx = packed_index(static_cast<size_t>(m), static_cast<size_t>(g * 32 + q * 8),
                                       static_cast<size_t>(a.kpad), kTileM);
-      *reinterpret_cast<uint4*>(a.onehot_packed + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(a.onehot_packed + idx) =
+          make_uint4(word == 0 ? one : 0u, word == 1 ? one : 0u, word == 2 ? one : 0u, word == 3 ? one : 0u);
     }
     if (a.onehot_f32) {
       const int rel = best_k - q * 4;

@@ -217,6 +217,35 @@ def test_tcgen05_gemm_vs_fp32_reference(ops, cuda, cluster, M, K, N):
     torch.testing.assert_close(var, ref.var(-1, unbiased=False), rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("M,K,N,use_ln,act", [(300, 448, 400, True, 1), (1000, 2048, 400, True, 1), (300, 256, 200, False, 1),
+                                              (260, 448, 17, False, 0), (5000, 448, 400, True, 1)])
+def test_staged_epilogue_output_is_bit_identical(ops, cuda, M, K, N, use_ln, act):
+    """The full-row epilogue writes its 128 x 64 output tiles through shared memory + one bulk copy per tile (default) or with
+    16-byte stores per thread: only the path to HBM differs, every bit of the packed image (padding included) is the same."""
+    from rl_sandbox_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    gam = (1 + 0.1 * torch.randn(N, generator=g)).to(cuda)
+    bet = (0.1 * torch.randn(N, generator=g)).to(cuda)
+    rb, nb = ops.plan_blocks(N)
+    kp, okp = ops.round_up(K, 64), ops.round_up(N, 64)
+    xp, wp = ops.pack_rows(x), ops.pack_rows(w, row_block=rb, rows_pad=rb, k_pad=kp)
+    outs = []
+    try:
+        for staged in (1, 0):
+            assert lib.rlsb_set_staged_output(staged) == staged
+            outs.append(ops.gemm_ln_act(xp, kp, wp, rb, b, M, N, gam if use_ln else None, bet if use_ln else None, 1e-5, act,
+                                        okp).clone())
+    finally:
+        lib.rlsb_set_staged_output(1)
+    rows = ops.round_up(M, 128)
+    a0, a1 = (ops.unpack_rows(o, rows, okp, k_pad=okp) for o in outs)
+    assert torch.equal(a0[:M], a1[:M])
+
+
 @pytest.mark.parametrize("M,K,N,use_ln,act", [(300, 448, 400, True, 1), (1000, 2048, 400, True, 1),
                                               (300, 256, 200, False, 1), (260, 448, 17, False, 0),
                                               (130, 384, 384, True, 2), (33000, 448, 400, True, 1)])
