@@ -131,53 +131,96 @@ struct AttnArgs {
 };
 
 template <int K>
-__global__ void __launch_bounds__(kAttnThreads) slot_attn_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kAttnThreads, 2) slot_attn_kernel(const AttnArgs a) {
+  // HBM-bound: k and v of the frame (2 x T x dim bf16) are streamed once each.  Two token rows per warp iteration keep four
+  // 16-byte loads per lane in flight; q is read from shared memory as float4 vectors; the cross-warp reduction of the
+  // updates is a three-round tree over a half-size buffer, so that six CTAs fit on an SM.
   extern __shared__ float sm[];
   const int dim = a.dim, T = a.T;
   const int chunks = dim >> 3;  // 16-byte chunks per k (or v) row
   float* sq = sm;                      // [K][dim]
   float* sattn = sq + K * dim;         // [K][T]
-  float* sred = sattn + K * T;         // [warps][K][dim]
-  float* srs = sred + kAttnWarps * K * dim;  // [K] row sums
+  float* sred = sattn + ((K * T + 3) & ~3);   // [warps / 2][K][dim], 16-byte aligned
+  float* srs = sred + (kAttnWarps / 2) * K * dim;  // [K] row sums
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < K * dim; i += kAttnThreads) sq[i] = a.q[static_cast<size_t>(b) * K * dim + i];
   __syncthreads();
   const int kpad = 2 * dim;
+  const int c0 = lane, c1 = lane + 32;
+  const bool has1 = c1 < chunks;
+  auto kv_chunk = [&](size_t row, int col) {
+    return __ldg(reinterpret_cast<const uint4*>(
+        a.kv + packed_index(row, static_cast<size_t>(col), static_cast<size_t>(kpad), kTileM)));
+  };
   // ---- logits, softmax over slots -------------------------------------------------------------
-  for (int j = warp; j < T; j += kAttnWarps) {
+  // the four 16-byte pieces of token rows j, j + 1 (column offset `col`: 0 = k, dim = v); zero beyond the frame
+  auto fetch = [&](int j, int col, uint4 (&u)[2][2]) {
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     const size_t row = static_cast<size_t>(b) * T + j;
-    float acc[K];
+    const bool one = j < T, two = j + 1 < T;
+    u[0][0] = (one && c0 < chunks) ? kv_chunk(row, col + c0 * 8) : zero;
+    u[0][1] = (one && has1) ? kv_chunk(row, col + c1 * 8) : zero;
+    u[1][0] = (two && c0 < chunks) ? kv_chunk(row + 1, col + c0 * 8) : zero;
+    u[1][1] = (two && has1) ? kv_chunk(row + 1, col + c1 * 8) : zero;
+  };
+  uint4 nxt[2][2];
+  fetch(2 * warp, 0, nxt);
+  for (int j = 2 * warp; j < T; j += 2 * kAttnWarps) {
+    const bool two = j + 1 < T;
+    uint4 u[2][2];
 #pragma unroll
-    for (int i = 0; i < K; ++i) acc[i] = 0.f;
-    for (int c = lane; c < chunks; c += 32) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(
-          a.kv + packed_index(row, static_cast<size_t>(c * 8), static_cast<size_t>(kpad), kTileM)));
-      float kf[8];
-      unpack8(u, kf);
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const float* qi = sq + i * dim + c * 8;
+      for (int h = 0; h < 2; ++h) u[t][h] = nxt[t][h];
+    fetch(j + 2 * kAttnWarps, 0, nxt);   // the next pair of rows is in flight while this one is reduced
+    float acc[2][K];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i] = fmaf(qi[e], kf[e], acc[i]);
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < K; ++i) acc[t][i] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = h ? c1 : c0;
+      if (c < chunks) {
+        float kf[2][8];
+        unpack8(u[0][h], kf[0]);
+        unpack8(u[1][h], kf[1]);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          const float4 q0 = *reinterpret_cast<const float4*>(sq + i * dim + c * 8);
+          const float4 q1 = *reinterpret_cast<const float4*>(sq + i * dim + c * 8 + 4);
+          const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[0][i] = fmaf(qv[e], kf[0][e], acc[0][i]);
+            acc[1][i] = fmaf(qv[e], kf[1][e], acc[1][i]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < K; ++i)
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-    if (lane == 0) {
-      float mx = acc[0] * a.scale;
+      for (int i = 0; i < K; ++i)
 #pragma unroll
-      for (int i = 1; i < K; ++i) mx = fmaxf(mx, acc[i] * a.scale);
+        for (int o = 16; o > 0; o >>= 1) acc[t][i] += __shfl_xor_sync(0xffffffffu, acc[t][i], o);
+    if (lane < 2 && (lane == 0 || two)) {
+      const int t = lane;
+      float lg[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) lg[i] = (t ? acc[1][i] : acc[0][i]) * a.scale;
+      float mx = lg[0];
+#pragma unroll
+      for (int i = 1; i < K; ++i) mx = fmaxf(mx, lg[i]);
       float e[K], den = 0.f;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
-        e[i] = __expf(acc[i] * a.scale - mx);
+        e[i] = __expf(lg[i] - mx);
         den += e[i];
       }
 #pragma unroll
-      for (int i = 0; i < K; ++i) sattn[i * T + j] = e[i] / den + a.eps;
+      for (int i = 0; i < K; ++i) sattn[i * T + j + t] = e[i] / den + a.eps;
     }
   }
   __syncthreads();
@@ -196,63 +239,90 @@ __global__ void __launch_bounds__(kAttnThreads) slot_attn_kernel(const AttnArgs 
     if (a.attn_out) a.attn_out[static_cast<size_t>(b) * K * T + i] = v;
   }
   __syncthreads();
-  // ---- updates = attn . v  (each warp accumulates a token subset, then a block reduction) ----------
-  {
-    float acc[K][2][8];
+  // ---- updates = attn . v  (each warp accumulates a token subset, then a tree reduction over the warps) --------
+  float acc[K][2][8];
 #pragma unroll
-    for (int i = 0; i < K; ++i)
+  for (int i = 0; i < K; ++i)
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][u][e] = 0.f;
-    for (int j = warp; j < T; j += kAttnWarps) {
-      const size_t row = static_cast<size_t>(b) * T + j;
-      float w[K];
+      for (int e = 0; e < 8; ++e) acc[i][h][e] = 0.f;
+  fetch(2 * warp, dim, nxt);
+  for (int j = 2 * warp; j < T; j += 2 * kAttnWarps) {
+    const bool two = j + 1 < T;
+    uint4 x[2][2];
 #pragma unroll
-      for (int i = 0; i < K; ++i) w[i] = sattn[i * T + j];
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = lane + 32 * u;
-        if (c < chunks) {
-          const uint4 x = __ldg(reinterpret_cast<const uint4*>(
-              a.kv + packed_index(row, static_cast<size_t>(dim + c * 8), static_cast<size_t>(kpad), kTileM)));
-          float vf[8];
-          unpack8(x, vf);
+      for (int h = 0; h < 2; ++h) x[t][h] = nxt[t][h];
+    fetch(j + 2 * kAttnWarps, dim, nxt);
+    float w[2][K];
 #pragma unroll
-          for (int i = 0; i < K; ++i)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[i][u][e] = fmaf(w[i], vf[e], acc[i][u][e]);
-        }
-      }
+    for (int i = 0; i < K; ++i) {
+      w[0][i] = sattn[i * T + j];
+      w[1][i] = two ? sattn[i * T + j + 1] : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < K; ++i)
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = lane + 32 * u;
-        if (c < chunks) {
+      for (int h = 0; h < 2; ++h) {
+        float vf[8];
+        unpack8(x[t][h], vf);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) sred[(warp * K + i) * dim + c * 8 + e] = acc[i][u][e];
-        }
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[i][h][e] = fmaf(w[t][i], vf[e], acc[i][h][e]);
       }
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < K * chunks; idx += kAttnThreads) {
-    const int i = idx / chunks, c = idx - i * chunks;
-    float s[8];
+  // tree over the 8 warps: the upper half of the active warps hands its partial sums to the lower half
+  for (int half = kAttnWarps / 2; half >= 1; half >>= 1) {
+    if (warp >= half && warp < 2 * half) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s[e] = 0.f;
-    for (int wv = 0; wv < kAttnWarps; ++wv) {
-      const float* p = sred + (wv * K + i) * dim + c * 8;
+      for (int i = 0; i < K; ++i)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] += p[e];
+        for (int h = 0; h < 2; ++h) {
+          const int c = h ? c1 : c0;
+          if (c < chunks) {
+            float4* dst = reinterpret_cast<float4*>(sred + ((warp - half) * K + i) * dim + c * 8);
+            dst[0] = make_float4(acc[i][h][0], acc[i][h][1], acc[i][h][2], acc[i][h][3]);
+            dst[1] = make_float4(acc[i][h][4], acc[i][h][5], acc[i][h][6], acc[i][h][7]);
+          }
+        }
     }
-    const size_t r = static_cast<size_t>(b) * K + i;
-    float4* po = reinterpret_cast<float4*>(a.upd_out + r * dim + c * 8);
-    po[0] = make_float4(s[0], s[1], s[2], s[3]);
-    po[1] = make_float4(s[4], s[5], s[6], s[7]);
-    *reinterpret_cast<uint4*>(a.upd_packed + packed_index(r, static_cast<size_t>(c * 8), static_cast<size_t>(dim), kTileM)) =
-        make_uint4(bf2(s[0], s[1]), bf2(s[2], s[3]), bf2(s[4], s[5]), bf2(s[6], s[7]));
+    __syncthreads();
+    if (warp < half) {
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = h ? c1 : c0;
+          if (c < chunks) {
+            const float4* src = reinterpret_cast<const float4*>(sred + (warp * K + i) * dim + c * 8);
+            const float4 s0 = src[0], s1 = src[1];
+            acc[i][h][0] += s0.x; acc[i][h][1] += s0.y; acc[i][h][2] += s0.z; acc[i][h][3] += s0.w;
+            acc[i][h][4] += s1.x; acc[i][h][5] += s1.y; acc[i][h][6] += s1.z; acc[i][h][7] += s1.w;
+          }
+        }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = h ? c1 : c0;
+        if (c < chunks) {
+          const float* sv = acc[i][h];
+          const size_t r = static_cast<size_t>(b) * K + i;
+          float4* po = reinterpret_cast<float4*>(a.upd_out + r * dim + c * 8);
+          po[0] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+          po[1] = make_float4(sv[4], sv[5], sv[6], sv[7]);
+          *reinterpret_cast<uint4*>(a.upd_packed +
+                                    packed_index(r, static_cast<size_t>(c * 8), static_cast<size_t>(dim), kTileM)) =
+              make_uint4(bf2(sv[0], sv[1]), bf2(sv[2], sv[3]), bf2(sv[4], sv[5]), bf2(sv[6], sv[7]));
+        }
+      }
   }
 }
 
@@ -531,8 +601,8 @@ static int slot_fwd_impl(const rlsb_slot_cfg* cfg, const void* packed, int64_t B
   }
   RLSB_CUDA(cudaMemcpyAsync(f32(W.cur[0]), prev_slots, static_cast<size_t>(BK) * dim * 4, cudaMemcpyDeviceToDevice, s));
   static bool attr_done[kMaxSlots + 1] = {};
-  const size_t attn_smem = (static_cast<size_t>(P.K) * dim + static_cast<size_t>(P.K) * P.T +
-                            static_cast<size_t>(kAttnWarps) * P.K * dim + kMaxSlots) * sizeof(float);
+  const size_t attn_smem = (static_cast<size_t>(P.K) * dim + ((static_cast<size_t>(P.K) * P.T + 3) & ~static_cast<size_t>(3)) +
+                            static_cast<size_t>(kAttnWarps / 2) * P.K * dim + kMaxSlots) * sizeof(float);
   int cur = 0;
   for (int it = 0; it < P.iters; ++it) {
     float* s_prev = f32(W.cur[cur]);
