@@ -76,6 +76,23 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def init_nccl_quietly(dist, device):
+    """stdout carries the one JSON line only: NCCL prints its version banner to the C-level stdout when the first
+    communicator comes up, so file descriptor 1 points at stderr while the process group and its communicator are created."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+        t = torch.zeros(1, device=device)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -209,8 +226,7 @@ def full_train_main(args, dims):
     device = f"cuda:{local}"
     _lib.require_device()
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device(device))
+        init_nccl_quietly(dist, device)
     torch.backends.cuda.matmul.allow_tf32 = True   # reference train.py:40
     lib = _lib.load()
     H, B, T = args.horizon, 16, 50
@@ -302,9 +318,7 @@ def main():
     device = f"cuda:{local}"
     _lib.require_device()
     if world > 1:
-        # stdout carries the one JSON line only: NCCL's version / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device(device))
+        init_nccl_quietly(dist, device)
     torch.backends.cuda.matmul.allow_tf32 = True   # as the reference's train.py:40 (loss MLPs run in torch)
     lib = _lib.load()
 
