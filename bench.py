@@ -153,6 +153,13 @@ def cpu_hot_path(dims, H, rows, steps, warmup, metrics_samples):
     return rows * H / sec, sec, threads
 
 
+def workload_name(args, dims, rows):
+    if args.workload in ("crafter", "slotted"):
+        return f"{args.workload}: full DreamerV2.train() on 16 x 50 frames of 64x64x3 uint8 per GPU, H={args.horizon}"
+    return (f"{args.workload}: {rows} start states/GPU x H={args.horizon}, D={dims['D']}, 32x32 latents, A={dims['A']} "
+            f"{'discrete' if dims['discrete'] else 'continuous'}, layer_norm={dims['layer_norm']}")
+
+
 def reference_arm(args, dims):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,8 +176,9 @@ def reference_arm(args, dims):
         "impl": "reference", "metric": "imagined_rssm_steps_per_sec", "value": val, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: bounded sample of {rows} start states x H={args.horizon} "
-                               f"(dims D={dims['D']} A={dims['A']} discrete={dims['discrete']})",
+        # the b200 arm's workload (same dims, same hot path); each timed step is a bounded sample of it
+        "config": {"workload": workload_name(args, dims, args.rows or (32768 if args.workload == "sweep" else 800)),
+                   "sample": f"bounded sample: {rows} start states x H={args.horizon} per step on the host cores",
                    "impl_note": "reference's PyTorch-CPU hot path restated in oracle/oracle_port.py "
                                 "(HotPathCPU: imagine + lambda-return + AC losses + backward + AdamW); "
                                 "the reference is pure Python and is not present on the GPU box"},
@@ -489,8 +497,7 @@ def main():
             "metric": "imagined_rssm_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {N} start states/GPU x H={H}, D={D}, 32x32 latents, A={dims['A']} "
-                                   f"{'discrete' if dims['discrete'] else 'continuous'}, layer_norm={dims['layer_norm']}",
+            "config": {"workload": workload_name(args, dims, N),
                        "step": "imagine(K1) + lambda-return(K2) + fused critic/actor loss fwd+bwd(K4) + allreduce + AdamW x2"
                                if dims["discrete"] else
                                "imagine(K1, tape) + lambda-return(K2) + K2 bwd + rollout backward(K1 bwd) + K4 + allreduce + AdamW x2",
