@@ -660,7 +660,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
   // staged output (ln_act_pass2_staged): two 16 KB slots for the output image (+ two for x_hat in the saving variant)
   uint8_t* stage_out = smem + static_cast<size_t>(stages) * stage_bytes;
   uint8_t* stage_pre = stage_out + 32768;
-  const uint32_t staging_bytes = (kLnAct && p.staged_out) ? (EPI == EPI_LN_ACT_SAVE ? 65536u : 32768u) : 0u;
+  const uint32_t staging_bytes = p.staged_out ? (EPI == EPI_LN_ACT_SAVE ? 65536u : 32768u) : 0u;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(stage_out + staging_bytes);
 
   const int warp = threadIdx.x >> 5;
@@ -986,6 +986,65 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           }
         };
         int done1 = 0;
+        if ((EPI == EPI_PLAIN || EPI == EPI_STATS) && p.staged_out) {
+          // fp32 row-major output through shared memory: a thread owns a row, so its 32 bytes per chunk would go to a
+          // different 128-byte line per lane (32 partial lines per warp store).  The sixteen warps instead write one chunk
+          // each of a 128 x 32 slab (16 KB, rows of 128 bytes with the 16-byte slots XOR-swizzled by the row), and after a
+          // barrier every warp stores eight rows of the slab as full 128-byte lines.  Two slabs alternate: the barrier of
+          // slab s + 1 also says that everybody has finished reading slab s - 1's buffer.
+          const uint32_t sbuf0 = smem_u32(stage_out);
+          const int wq = warp - 2;                       // 0..15: rows [8 wq, 8 wq + 8) of a slab on the way out
+          const uint32_t swz = static_cast<uint32_t>(row & 7);
+          float* gbase = p.out_f32 + static_cast<size_t>(g) * p.out_group_stride + col0;
+          uint32_t ra[8] = {}, rb[8] = {};
+          const int nsl = my_chunks;                     // chunk i of this warp lies in slab i (columns [32 i, 32 i + 32))
+          tmem_ld8(tmem_d + static_cast<uint32_t>(cq * 8), ra);
+          for (int i = 0; i < nsl; ++i) {
+            const int c = (cq + 4 * i) * 8;
+            if (i & 1) tmem_ld_wait2(rb, ra); else tmem_ld_wait2(ra, rb);
+            if (i + 1 < nsl) {
+              if (i & 1) tmem_ld8(tmem_d + static_cast<uint32_t>(c + 32), ra);
+              else tmem_ld8(tmem_d + static_cast<uint32_t>(c + 32), rb);
+            }
+            f32x2 b[4], v2[4];
+            lds_2x2(s_bias + 4u * c, b[0], b[1]);
+            lds_2x2(s_bias + 4u * c + 16u, b[2], b[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              v2[e] = fadd2((i & 1) ? pk2u(rb[2 * e], rb[2 * e + 1]) : pk2u(ra[2 * e], ra[2 * e + 1]), b[e]);
+            if (c + 8 <= n_valid) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                sum2 = fadd2(sum2, v2[e]);
+                sq2 = ffma2(v2[e], v2[e], sq2);
+              }
+            }
+            const uint32_t sbuf = sbuf0 + static_cast<uint32_t>(i & 1) * 16384u;
+            {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) unpk2(v2[e], f[2 * e], f[2 * e + 1]);
+              const uint32_t rowa = sbuf + static_cast<uint32_t>(row) * 128u;
+              sts128(rowa + ((static_cast<uint32_t>(2 * cq) ^ swz) << 4),
+                     make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+              sts128(rowa + ((static_cast<uint32_t>(2 * cq + 1) ^ swz) << 4),
+                     make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+            }
+            epi_bar(4);
+            if (tile_ok && col0 + 32 * i < p.N) {   // (N is a multiple of 32 in this mode: a slab is valid or padding)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int rr = wq * 8 + h * 4 + (lane >> 3);
+                const uint32_t slot = static_cast<uint32_t>(lane & 7);
+                const float4 v = lds128(sbuf + static_cast<uint32_t>(rr) * 128u + ((slot ^ static_cast<uint32_t>(rr & 7)) << 4));
+                const int mm = m_tile * kTileM + rr;
+                if (row_is_valid(p, mm))
+                  *reinterpret_cast<float4*>(gbase + static_cast<size_t>(mm) * p.ldo + 32 * i + 4 * static_cast<int>(slot)) = v;
+              }
+            }
+          }
+          done1 = my_chunks;
+        }
         if (kLnAct && n_fast >= 4) {   // complete chunks: statistics only, two independent accumulator pairs
           f32x2 sumb = pk2(0.f, 0.f), sqb = pk2(0.f, 0.f);
           uint32_t sb = s_bias + 32u * cq;
@@ -1011,7 +1070,9 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           sum2 = fadd2(sum2, sumb);
           sq2 = fadd2(sq2, sqb);
         }
-        if (done1 == 0) {
+        if (done1 >= my_chunks) {
+          // everything went through the staged sweep
+        } else if (done1 == 0) {
           tmem_sweep(tmem_d, cq, my_chunks, [&](const uint32_t (&r)[8], int i) { pass1_chunk(r, (cq + 4 * i) * 8); });
         } else {
           for (int i = done1; i < my_chunks; ++i) {
@@ -1125,6 +1186,7 @@ int g_num_sms = 0;
 int g_pair = 2;   // cta_group::2 for clusters of 2 (1: only n-blocks <= 256 columns, 0: multicast only); RLSB_PAIR overrides
 int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
 int g_staged = 1;         // full-row epilogues write their output through shared memory + bulk copies (RLSB_STAGED=0: 16-byte stores)
+int g_staged_f32 = 1;     // fp32 row-major outputs go through shared-memory slabs and leave as full lines (RLSB_STAGED_F32=0)
 
 }  // namespace
 
@@ -1148,6 +1210,7 @@ int init_device_info() {
     if (const char* env = getenv("RLSB_CLUSTER")) set_gemm_cluster_size(atoi(env));
     if (const char* env = getenv("RLSB_PAIR")) g_pair = atoi(env);   // 0: multicast only, 1: pairs for RB <= 256, 2: all
     if (const char* env = getenv("RLSB_STAGED")) g_staged = atoi(env);
+    if (const char* env = getenv("RLSB_STAGED_F32")) g_staged_f32 = atoi(env);
   }
   return 0;
 }
@@ -1187,7 +1250,10 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   const int pair = (g_pair && cs == 2 && (p.RB % 32) == 0 && (p.RB <= 256 || g_pair > 1)) ? 1 : 0;
   const int stage_bytes = kTileM * kTileK * 2 + p.RB * kTileK * 2 / (pair ? 2 : 1);
   // full-row epilogues that own whole output tiles assemble them in shared memory (ln_act_pass2_staged)
-  const bool staged = g_staged && (epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB == 1;
+  const bool staged_f32 = g_staged_f32 && (epilogue == EPI_PLAIN || epilogue == EPI_STATS) && (p.N % 32) == 0 &&
+                          (p.ldo % 4) == 0 && p.out_f32 != nullptr && (reinterpret_cast<uintptr_t>(p.out_f32) % 16) == 0 &&
+                          (p.out_group_stride % 4) == 0;
+  const bool staged = staged_f32 || (g_staged && (epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB == 1);
   const int staging_bytes = staged ? (epilogue == EPI_LN_ACT_SAVE ? 65536 : 32768) : 0;
   const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256 - staging_bytes;
   static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
