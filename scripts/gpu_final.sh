@@ -1,5 +1,5 @@
 # round-end batch: tests, smoke, every bench workload, reference arm, launch list, full capture of the roofline kernel
-TAG=${1:-v19}
+TAG=${1:-v25}
 make -C oracle >/dev/null 2>&1
 timeout 900 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo pytest_exit=$?
 tail -2 gpurun_out/pytest_gpu_$TAG.log
