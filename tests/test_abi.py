@@ -57,3 +57,35 @@ def test_argument_errors_are_negative_codes():
     cfg = _lib.ImagineCfg(1024, 32, 32, 17, 400, 1, 1, 1, 1, 15, 1)
     assert lib.rlsb_imagine_packed_bytes(C.byref(cfg)) > 20_000_000
     assert lib.rlsb_imagine_workspace_bytes(C.byref(cfg), 800) > 0
+
+
+@pytest.mark.gpu   # the workspace plan sizes the weight-gradient partials by the SM count of the device
+def test_actor_slots_lie_inside_the_update_workspace():
+    """rlsb_ac_actor_slots is pointer arithmetic over the K4 workspace plan: the twelve slices the rollout fills (layer outputs,
+    x_hat, 1/std of the actor's four hidden layers) are disjoint, ordered and inside rlsb_ac_workspace_bytes."""
+    lib = _lib.load()
+    H, N = 15, 800
+    cfg = _lib.AcCfg(1024, 32, 32, 17, 400, 1, 1, H, 1.0, 3e-3, 128, 0)
+    total = lib.rlsb_ac_workspace_bytes(C.byref(cfg), N)
+    assert total > 0
+    base = 1 << 40   # a made-up device address: nothing is dereferenced
+    slots = _lib.ActorSlots()
+    assert lib.rlsb_ac_actor_slots(C.byref(cfg), N, C.c_void_p(base), C.byref(slots)) == 0
+    assert slots.m_pad == 896 and slots.Hp == 448 and slots.steps == H
+    img = H * slots.m_pad * slots.Hp * 2        # one group's packed bf16 image of a layer
+    spans = []
+    for l in range(4):
+        spans += [(slots.x[l], img), (slots.pre[l], img), (slots.rstd[l], H * slots.m_pad * 4)]
+    spans.sort()
+    for (a, n), (b, _) in zip(spans, spans[1:]):
+        assert a + n <= b, "actor slices overlap"
+    assert spans[0][0] >= base and spans[-1][0] + spans[-1][1] <= base + total
+    assert lib.rlsb_ac_actor_slots(None, N, C.c_void_p(base), C.byref(slots)) < 0
+
+
+def test_staged_output_switch_is_queryable_without_a_device():
+    lib = _lib.load()
+    cur = lib.rlsb_set_staged_output(-1)
+    assert cur in (0, 1)
+    assert lib.rlsb_set_staged_output(0) == 0 and lib.rlsb_set_staged_output(1) == 1
+    lib.rlsb_set_staged_output(cur)
