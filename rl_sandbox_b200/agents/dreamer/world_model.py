@@ -12,9 +12,10 @@ from torch import nn
 
 from rl_sandbox_b200.agents.dreamer.common import Dist, Normalizer
 from rl_sandbox_b200.agents.dreamer.rssm import RSSM, State
-from rl_sandbox_b200.agents.dreamer.vision import Decoder, Encoder
+from rl_sandbox_b200.agents.dreamer.vision import Decoder, Encoder, SpatialBroadcastDecoder
 from rl_sandbox_b200.utils.dists import DistLayer
 from rl_sandbox_b200.utils.fc_nn import fc_nn_generator
+from rl_sandbox_b200.vision.dino import ViTFeat
 
 
 class WorldModel(nn.Module):
@@ -42,21 +43,26 @@ class WorldModel(nn.Module):
         self.recurrent_model = RSSM(latent_dim, rssm_dim, actions_num, latent_classes, discrete_rssm,
                                     norm_layer=nn.LayerNorm if layer_norm else nn.Identity)
         if decode_vit:
-            from rl_sandbox_b200.vision.dino import ViTFeat
-            from rl_sandbox_b200.vision.decoders import SpatialBroadcastDecoder
+            # frozen DINO ViT-S supplying the `d_features` loss targets (world_model.py:44-59)
             if vit_img_size == 224:
-                patch, self.vit_size = 16, 14
+                self.dino_vit = ViTFeat("/dino/dino_deitsmall16_pretrain/dino_deitsmall16_pretrain.pth",
+                                        feat_dim=384, vit_arch='small', patch_size=16)
+                self.decoder_kernels, self.vit_size = [3, 3, 2], 14
             elif vit_img_size == 64:
-                patch, self.vit_size = 8, 8
+                self.dino_vit = ViTFeat("/dino/dino_deitsmall8_pretrain/dino_deitsmall8_pretrain.pth",
+                                        feat_dim=384, vit_arch='small', patch_size=8)
+                self.decoder_kernels, self.vit_size = [3, 4], 8
             else:
                 raise RuntimeError("Unknown vit img size")
-            self.dino_vit = ViTFeat(None, feat_dim=384, vit_arch='small', patch_size=patch)
             self.vit_feat_dim = self.dino_vit.feat_dim
             self.dino_vit.requires_grad_(False)
+        # submodules are registered in the reference's order (recurrent_model, dino_vit, encoder, dino_predictor,
+        # image_predictor, heads): optimizer state dicts are keyed by parameter index (checkpoint round trip)
+        self.encoder = Encoder(norm_layer=norm2d, kernel_sizes=[4, 4, 4, 4], channel_step=48)
+        if decode_vit:
             self.dino_predictor = SpatialBroadcastDecoder(self.state_size, norm_layer=norm2d, out_image=(14, 14),
                                                           kernel_sizes=[5, 5, 5, 5], channel_step=self.vit_feat_dim,
                                                           output_channels=self.vit_feat_dim, return_dist=True)
-        self.encoder = Encoder(norm_layer=norm2d, kernel_sizes=[4, 4, 4, 4], channel_step=48)
         self.image_predictor = Decoder(self.state_size, norm_layer=norm2d)
         head = lambda kind: fc_nn_generator(self.state_size, 1, hidden_size=400, num_layers=5,
                                             intermediate_activation=nn.ELU, layer_norm=layer_norm,

@@ -5,8 +5,8 @@ Same constructor kwargs (incl. the two the shipped YAML forgets, ``discount_loss
 (``get_initial_state`` / ``get_latent`` return ``(State, slots)`` tuples).  Hot-path pieces:
 ``predict_next`` chains run in librlsb (K1, slots > 1) when driven by DreamerV2.imagine_trajectory;
 ``SlotAttention.forward`` is K3.  The observe loop, the conv encoder / decoders and the losses are torch
-ops (out of scope as kernel targets).  DINO targets are taken from
-``additional['d_features']``; computing them (precalc_data) needs the reference's ViT and is not mirrored.
+ops (out of scope as kernel targets).  DINO targets ``additional['d_features']`` come from
+the frozen ``dino_vit`` (``precalc_data``, world_model_slots_attention.py:160-173).
 """
 import typing as t
 
@@ -17,9 +17,10 @@ from torch.nn import functional as F
 
 from rl_sandbox_b200.agents.dreamer.common import Dist, Normalizer, get_position_encoding
 from rl_sandbox_b200.agents.dreamer.rssm_slots_attention import RSSM, State
-from rl_sandbox_b200.agents.dreamer.vision import Decoder, Encoder
+from rl_sandbox_b200.agents.dreamer.vision import Decoder, Encoder, SpatialBroadcastDecoder
 from rl_sandbox_b200.utils.dists import DistLayer
 from rl_sandbox_b200.utils.fc_nn import fc_nn_generator
+from rl_sandbox_b200.vision.dino import ViTFeat
 from rl_sandbox_b200.vision.slot_attention import PositionalEmbedding, SlotAttention
 
 
@@ -33,9 +34,9 @@ class WorldModel(nn.Module):
                  per_slot_rec_loss: bool = False, spatial_decoder: bool = False):
         super().__init__()
         if encode_vit:
-            raise NotImplementedError("encode_vit needs the reference's DINO ViT (not part of the B200 hot path)")
-        if spatial_decoder:
-            raise NotImplementedError("spatial_decoder=True is not mirrored")
+            # the reference's encode_vit branch feeds raw ViT features of the wrong rank into slot attention
+            # (hard part 6): not a working configuration there either
+            raise NotImplementedError("encode_vit=true is not supported (it is broken in the reference too)")
         self.use_prev_slots = use_prev_slots
         self.register_buffer('kl_free_nats', kl_free_nats * torch.ones(1))
         self.discount_scale, self.kl_beta, self.alpha = discount_loss_scale, kl_loss_scale, kl_loss_balancing
@@ -55,13 +56,20 @@ class WorldModel(nn.Module):
                                     full_qk_from=full_qk_from, symmetric_qk=symmetric_qk,
                                     attention_block_num=attention_block_num)
         if decode_vit:
+            # frozen DINO ViT-S (world_model_slots_attention.py:66-82); registered right after recurrent_model as in
+            # the reference so that parameter indices (optimizer state) and checkpoint keys `dino_vit.*` line up
             if vit_img_size == 224:
+                self.dino_vit = ViTFeat("/dino/dino_deitsmall16_pretrain/dino_deitsmall16_pretrain.pth",
+                                        feat_dim=384, vit_arch='small', patch_size=16)
                 self.decoder_kernels, self.vit_size = [3, 3, 2], 14
             elif vit_img_size == 64:
+                self.dino_vit = ViTFeat("/dino/dino_deitsmall8_pretrain/dino_deitsmall8_pretrain.pth",
+                                        feat_dim=384, vit_arch='small', patch_size=8)
                 self.decoder_kernels, self.vit_size = [3, 4], 8
             else:
                 raise RuntimeError("Unknown vit img size")
-            self.vit_feat_dim = 384
+            self.vit_feat_dim = self.dino_vit.feat_dim
+            self.dino_vit.requires_grad_(False)
         self.encoder = Encoder(norm_layer=norm2d, kernel_sizes=[4, 4], channel_step=48 * (self.n_dim // 192) * 2,
                                post_conv_num=2, flatten_output=False)
         self.slot_attention = SlotAttention(slots_num, self.n_dim, slots_iter_num, use_prev_slots)
@@ -71,7 +79,11 @@ class WorldModel(nn.Module):
         self.slot_mlp = nn.Sequential(nn.Linear(self.n_dim, self.n_dim), nn.ReLU(inplace=True),
                                       nn.Linear(self.n_dim, self.n_dim))
         z = rssm_dim + latent_dim * latent_classes
-        if decode_vit:
+        if decode_vit and spatial_decoder:
+            self.dino_predictor = SpatialBroadcastDecoder(z, norm_layer=norm2d, out_image=(14, 14), kernel_sizes=[5, 5, 5],
+                                                          channel_step=self.vit_feat_dim,
+                                                          output_channels=self.vit_feat_dim + 1, return_dist=False)
+        elif decode_vit:
             self.dino_predictor = Decoder(z, norm_layer=norm2d, conv_kernel_sizes=[3], channel_step=self.vit_feat_dim,
                                           kernel_sizes=self.decoder_kernels, output_channels=self.vit_feat_dim + 1,
                                           return_dist=False)
@@ -96,7 +108,10 @@ class WorldModel(nn.Module):
     def precalc_data(self, obs: torch.Tensor) -> dict[str, torch.Tensor]:
         if not self.decode_vit:
             return {}
-        raise NotImplementedError("DINO feature extraction is not mirrored: pass additional_data['d_features']")
+        import torchvision as tv
+        prep = tv.transforms.Compose([tv.transforms.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)),
+                                      tv.transforms.Resize(self.vit_img_size, antialias=True)])
+        return {'d_features': self.dino_vit(prep(obs + 0.5)).squeeze()}
 
     def get_initial_state(self, batch_size: int = 1, seq_size: int = 1):
         dev = next(self.parameters()).device
