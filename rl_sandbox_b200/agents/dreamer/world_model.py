@@ -112,7 +112,8 @@ class WorldModel(nn.Module):
         return self.alpha * lhs + (1 - self.alpha) * rhs
 
     kernel_observe = True   # False: the reference's op sequence (T torch RSSM.forward calls under autograd)
-    _observe_engine = None
+    _observe_engine = None    # the engine of the last call
+    _observe_engines = None   # {(T, E, B): ObserveEngine}
     _observe_calls = 0
     _observe_seed_device = None   # int64 device tensor holding the Philox key (CUDA-graph replays change it in place)
 
@@ -122,17 +123,24 @@ class WorldModel(nn.Module):
         from rl_sandbox_b200 import ops
         B, T, E = embed.shape
         rm = self.recurrent_model
-        eng = self._observe_engine
-        if eng is None or (eng.T, eng.E) != (T, E):
+        # one engine per input shape, kept alive: a captured CUDA graph of the world-model update replays the raw
+        # pointers of its engine's packed weights / backward workspace, which therefore must never be freed or resized
+        if self._observe_engines is None:
+            self._observe_engines = {}
+        eng = self._observe_engines.get((T, E, B))
+        if eng is None:
             eng = ops.ObserveEngine(self.rssm_dim, self.actions_num, E, bool(self.layer_norm), T, groups=self.latent_dim,
                                     classes=self.latent_classes, device=embed.device)
-            self._observe_engine = eng
+            self._observe_engines[(T, E, B)] = eng
+        self._observe_engine = eng
         sd = dict(rm.named_parameters())
         eng.pack({k: v.detach() for k, v in sd.items()})   # the parameters change every optimizer step
         names = eng.names()
         noise = {"seed": 0x0B5E0000 + self._observe_calls}
         if self._observe_seed_device is not None:
             noise = {"seed_device": self._observe_seed_device}
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            noise["row_offset"] = torch.distributed.get_rank() * B   # global sequence index: ranks draw distinct noise
         self._observe_calls += 1
         prior_l, post_l, determ, stoch, _idx = ops.ObserveScanFn.apply(
             eng, names, noise, embed.transpose(0, 1).float(), actions.transpose(0, 1).float(), *[sd[n] for n in names])

@@ -325,7 +325,8 @@ class DreamerV2(RlAgent):
         if self._can_fuse_ac():
             return self._behaviour_update_fused(initial_states, noise)
         # torch-replay rollouts only (rho != 1): their noise comes from torch's graph-safe generator
-        graphable = (self.cuda_graph_wm and noise is None and not self.is_f16 and initial_states.determ.is_cuda
+        only_offset = noise is None or set(noise) <= {'row_offset'}   # (the torch replay draws from torch's generator)
+        graphable = (self.cuda_graph_wm and only_offset and not self.is_f16 and initial_states.determ.is_cuda
                      and torch.is_grad_enabled() and self.actor.rho != 1.0)
         if graphable:
             return self._behaviour_update_graphed_torch(initial_states)
@@ -501,12 +502,13 @@ class DreamerV2(RlAgent):
             k1 = self.last_rollout
         else:   # graph body: always re-pack (the parameters change between replays), static buffers, device-resident key
             eng, ac = static['eng'], static['ac']
+            pin = static['pin']   # this graph's own workspaces (ops.ImaginationEngine.workspace)
             eng.pack(self.world_model.state_dict(), self.actor.state_dict(), self.critic.state_dict())
             ac.pack(self.actor.state_dict(), self.critic.state_dict())
-            slots = ac.actor_slots(static['h0'].shape[0], self.imagination_horizon) if reuse else None
+            slots = ac.actor_slots(static['h0'].shape[0], self.imagination_horizon, pin=pin) if reuse else None
             k1 = eng.rollout(static['h0'], static['z0'], static['logits0'], seed_device=seed_device,
                              row_offset=noise.get('row_offset', 0), keep_packed=True, tape=dyn, want_stoch=False,
-                             out=static.get('out'), actor_slots=slots)
+                             out=static.get('out'), actor_slots=slots, pin=pin)
             static['out'] = k1
             self.last_rollout = k1
         H, n = k1['determ'].shape[0] - 1, k1['determ'].shape[1]
@@ -518,9 +520,10 @@ class DreamerV2(RlAgent):
             g_vs = torch.zeros_like(vs)
             g_vs[1:] = w[:H - 1] * (-(1.0 - float(self.actor.rho)) / ((H - 1) * n))
             g_r, g_v, _ = ops.lambda_return_bwd(g_vs, k1['values'], k1['discounts'], vs, self.critic.lambda_)
-            g_actions = self._engine.backward(k1, g_r, g_v)
+            g_actions = self._engine.backward(k1, g_r, g_v, pin=None if static is None else static['pin'])
         return ac.update(k1, vs, w, self.actor.actor, self.critic.critic, seed=self._noise_seed + self._rollouts,
-                         horizon=H, g_actions=g_actions, seed_device=seed_device, actor_forward_done=reuse)
+                         horizon=H, g_actions=g_actions, seed_device=seed_device, actor_forward_done=reuse,
+                         pin=None if static is None else static['pin'])
 
     def _fused_step_graphed(self, initial_states: State, noise: dict):
         """CUDA-graph replay of ``_fused_step`` for one (rows, horizon, shard offset) shape."""
@@ -537,7 +540,7 @@ class DreamerV2(RlAgent):
             if st is None:
                 st = {'h0': h0.clone(), 'z0': z0.clone(), 'logits0': logits0.clone(),
                       'seed': torch.zeros(1, device=h0.device, dtype=torch.int64),
-                      'eng': self._get_engine(), 'ac': self._get_ac_engine()}
+                      'eng': self._get_engine(), 'ac': self._get_ac_engine(), 'pin': key}
                 st['seed'].fill_(seed)
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -670,7 +673,12 @@ class DreamerV2(RlAgent):
         self.mark_weights_changed()
 
         initial_states = discovered_states.flatten().detach()
-        losses_ac, metrics_ac = self.behaviour_update(initial_states)
+        # data-parallel ranks hold different start states: their Philox counters are global start-state indices
+        # (rank * rows per rank), so no two ranks draw the same noise and the result does not depend on the split
+        noise = None
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            noise = {'row_offset': torch.distributed.get_rank() * initial_states.determ.shape[1]}
+        losses_ac, metrics_ac = self.behaviour_update(initial_states, noise)
 
         losses = losses_wm | losses_ac
         metrics = metrics_wm | metrics_ac

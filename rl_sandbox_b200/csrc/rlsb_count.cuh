@@ -33,5 +33,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// "done once per device" flag for per-device function attributes (cudaFuncSetAttribute applies to the current device
+// only: one process driving several GPUs must set it on each).  Setting an attribute twice is harmless, so a race between
+// two first callers is benign; the flag itself is atomic.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  // true if the caller still has to initialise the current device; `bit` receives the device's flag for done()
+  bool need(unsigned long long& bit) const {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    bit = 1ull << (dev & 63);
+    return (mask.load(std::memory_order_acquire) & bit) == 0;
+  }
+  void done(unsigned long long bit) { mask.fetch_or(bit, std::memory_order_release); }
+};
 }  // namespace rlsb
 #endif

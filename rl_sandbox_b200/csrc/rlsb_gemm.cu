@@ -1290,15 +1290,16 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   cfg.numAttrs = 2;
 #define RLSB_LAUNCH(EPI)                                                                         \
   do {                                                                                           \
-    static bool attr_done = false;                                                               \
-    if (!attr_done) {                                                                            \
+    static PerDeviceOnce attr_once;                                                              \
+    unsigned long long dev_bit = 0;                                                              \
+    if (attr_once.need(dev_bit)) {                                                               \
       e = cudaFuncSetAttribute(gemm_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                227 * 1024);                                                      \
       if (e != cudaSuccess) return static_cast<int>(e);                                          \
       e = cudaFuncSetAttribute(gemm_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                227 * 1024);                                                      \
       if (e != cudaSuccess) return static_cast<int>(e);                                          \
-      attr_done = true;                                                                          \
+      attr_once.done(dev_bit);                                                                   \
     }                                                                                            \
     if (pair) e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, true>, q, stages, nbuf, cs);         \
     else e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, false>, q, stages, nbuf, cs);             \

@@ -600,7 +600,8 @@ static int slot_fwd_impl(const rlsb_slot_cfg* cfg, const void* packed, int64_t B
     RLSB_TRY(launch_gemm(g, EPI_LN_ACT, s));
   }
   RLSB_CUDA(cudaMemcpyAsync(f32(W.cur[0]), prev_slots, static_cast<size_t>(BK) * dim * 4, cudaMemcpyDeviceToDevice, s));
-  static bool attr_done[kMaxSlots + 1] = {};
+  static PerDeviceOnce attr_once[kMaxSlots + 1];
+  unsigned long long dev_bit = 0;
   const size_t attn_smem = (static_cast<size_t>(P.K) * dim + ((static_cast<size_t>(P.K) * P.T + 3) & ~static_cast<size_t>(3)) +
                             static_cast<size_t>(kAttnWarps / 2) * P.K * dim + kMaxSlots) * sizeof(float);
   int cur = 0;
@@ -633,10 +634,11 @@ static int slot_fwd_impl(const rlsb_slot_cfg* cfg, const void* packed, int64_t B
                  (it == P.iters - 1) ? out_attn : nullptr, f32(W.upd), updp_img};
 #define RLSB_ATTN(KK)                                                                                   \
   case KK:                                                                                              \
-    if (!attr_done[KK])                                                                                 \
+    if (attr_once[KK].need(dev_bit)) {                                                                  \
       RLSB_CUDA(cudaFuncSetAttribute(slot_attn_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      200 * 1024));                                                      \
-    attr_done[KK] = true;                                                                               \
+      attr_once[KK].done(dev_bit);                                                                      \
+    }                                                                                                   \
     slot_attn_kernel<KK><<<static_cast<unsigned>(B), kAttnThreads, attn_smem, s>>>(a);                  \
     break;
       switch (P.K) {
@@ -1209,7 +1211,8 @@ extern "C" int rlsb_slot_attention_bwd(const rlsb_slot_cfg* cfg, const void* pac
   };
 
   RLSB_CUDA(cudaMemsetAsync(ws + S.dkv, 0, static_cast<size_t>(BT) * 2 * dim * 4, s));
-  static bool attr_done[kMaxSlots + 1] = {};
+  static PerDeviceOnce attr_once[kMaxSlots + 1];
+  unsigned long long dev_bit = 0;
   const size_t attn_smem = (2 * static_cast<size_t>(P.K) * dim + 3 * static_cast<size_t>(P.K) * P.T +
                             static_cast<size_t>(kAttnWarps) * P.K * dim + 2 * kMaxSlots) * sizeof(float);
   const float* ds = d_out_slots;   // d loss / d (slots leaving iteration it)
@@ -1257,10 +1260,11 @@ extern "C" int rlsb_slot_attention_bwd(const rlsb_slot_cfg* cfg, const void* pac
                                   static_cast<size_t>(128) * dim * 2, s));
 #define RLSB_ATTNB(KK)                                                                                      \
   case KK:                                                                                                  \
-    if (!attr_done[KK])                                                                                     \
+    if (attr_once[KK].need(dev_bit)) {                                                                      \
       RLSB_CUDA(cudaFuncSetAttribute(slot_attn_bwd_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      200 * 1024));                                                          \
-    attr_done[KK] = true;                                                                                   \
+      attr_once[KK].done(dev_bit);                                                                          \
+    }                                                                                                       \
     slot_attn_bwd_kernel<KK><<<static_cast<unsigned>(B), kAttnThreads, attn_smem, s>>>(a);                  \
     break;
       switch (P.K) {

@@ -236,6 +236,7 @@ __global__ void colsum_reduce_kernel(const ColsumReduceParams p) {
   dst[col] = acc;
 }
 
+PerDeviceOnce g_wg_attr_once;
 int g_wg_sms = 0;
 int g_wg_cluster = 4;          // max CTAs per cluster (1, 2 or 4); RLSB_WGRAD_CLUSTER overrides
 int g_wg_max_ctas[5] = {0, 0, 0, 0, 0};   // co-resident CTAs for cluster size 1 / 2 / 4 (148 / 148 / 132 on B200)
@@ -266,8 +267,13 @@ int plan_wgrad(WgradParams& p) {
       if (v == 1 || v == 2 || v == 4) g_wg_cluster = v;
     }
     g_wg_max_ctas[1] = g_wg_sms;
-    e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    {   // also the first device's attribute: the occupancy query below needs it
+      unsigned long long bit = 0;
+      g_wg_attr_once.need(bit);
+      e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      g_wg_attr_once.done(bit);
+    }
     for (int cs = 2; cs <= 4; cs *= 2) {   // how many clusters of this size the device holds at once
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(static_cast<unsigned>(g_wg_sms / cs * cs));
@@ -287,6 +293,14 @@ int plan_wgrad(WgradParams& p) {
         n = g_wg_sms / cs / 2;   // conservative
       }
       g_wg_max_ctas[cs] = n * cs;
+    }
+  }
+  {   // the shared-memory attribute is per device: a process that moved to another GPU sets it there too
+    unsigned long long bit = 0;
+    if (g_wg_attr_once.need(bit)) {
+      const cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      g_wg_attr_once.done(bit);
     }
   }
   p.kt_total = 0;

@@ -292,7 +292,11 @@ class ImaginationEngine:
             raise _lib.RlsbError(f"unsupported imagination config {cfg}")
         self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
         self._ws = None
-        self._ws_rows = 0
+        self._ws_bytes = 0
+        # workspaces owned by a captured CUDA graph (key = the graph's identity): a graph replays raw pointers, so its
+        # buffers are allocated once per key and never resized or freed while the engine lives; eager calls use the
+        # growable buffers above, which no graph ever references
+        self._pinned: dict = {}
 
     # state-dict keys follow SURVEY Appendix A.1 / A.2 (reference module attribute names)
     def pack(self, wm_sd: dict, actor_sd: dict, critic_sd: Optional[dict],
@@ -332,11 +336,19 @@ class ImaginationEngine:
         # `keep` tensors must outlive the enqueued pack kernels: stream-ordered frees make that safe
         self._keep = keep
 
-    def workspace(self, n: int) -> torch.Tensor:
-        if self._ws is None or self._ws_rows < n:
-            nbytes = self.lib.rlsb_imagine_workspace_bytes(C.byref(self.ccfg), n)
+    def workspace(self, n: int, pin=None) -> torch.Tensor:
+        nbytes = self.lib.rlsb_imagine_workspace_bytes(C.byref(self.ccfg), n)
+        if pin is not None:
+            key = ("ws", pin)
+            buf = self._pinned.get(key)
+            if buf is None:
+                buf = self._pinned[key] = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+            elif buf.numel() < nbytes:
+                raise _lib.RlsbError("a pinned (graph-owned) workspace cannot grow: capture a new graph for the new shape")
+            return buf
+        if self._ws is None or self._ws_bytes < nbytes:
             self._ws = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
-            self._ws_rows = n
+            self._ws_bytes = nbytes
         return self._ws
 
     def rollout(self, h0: torch.Tensor, z0: torch.Tensor, logits0: Optional[torch.Tensor] = None,
@@ -344,8 +356,8 @@ class ImaginationEngine:
                 seed: int = 0, row_offset: int = 0, precomp_actions: Optional[torch.Tensor] = None,
                 horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
                 out: Optional[dict] = None, keep_packed: bool = False, tape: bool = False,
-                seed_device: Optional[torch.Tensor] = None, actor_slots=None) -> dict:
-        """``actor_slots`` (``ACUpdateEngine.actor_slots(n)``): the actor head's activations of steps 0..H-1 are written
+                seed_device: Optional[torch.Tensor] = None, actor_slots=None, pin=None) -> dict:
+        """``pin``: identity of the CUDA graph this call is captured into (see ``workspace``).  ``actor_slots`` (``ACUpdateEngine.actor_slots(n)``): the actor head's activations of steps 0..H-1 are written
         into the update's workspace, so that ``ACUpdateEngine.update(..., actor_forward_done=True)`` skips that forward."""
         cfg = self.cfg
         H = horizon if horizon is not None else cfg.H
@@ -392,13 +404,13 @@ class ImaginationEngine:
         nz = Noise(_ptr(None if latent_uniforms is None else _f32c(latent_uniforms)),
                    _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
                    _ptr(None if precomp_actions is None else _f32c(precomp_actions)), _ptr(seed_device))
-        ws = self.workspace(n)
+        ws = self.workspace(n, pin)
         check(self.lib.rlsb_imagine_fwd(C.byref(ccfg), self.packed.data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")
         return out
 
-    def backward(self, out: dict, g_rewards: torch.Tensor, g_values: torch.Tensor) -> torch.Tensor:
+    def backward(self, out: dict, g_rewards: torch.Tensor, g_values: torch.Tensor, pin=None) -> torch.Tensor:
         """d loss / d actions (H, N, A) from d loss / d rewards, d loss / d values (each (H+1, N)) through the
         rollout recorded in ``out`` (made with tape=True): rlsb_imagine_bwd."""
         if out.get("tape") is None:
@@ -411,14 +423,22 @@ class ImaginationEngine:
         if g_rewards.numel() != (H + 1) * n or g_values.numel() != (H + 1) * n:
             raise _lib.RlsbError("backward: g_rewards / g_values must be (H+1, N)")
         nbytes = self.lib.rlsb_imagine_bwd_workspace_bytes(C.byref(ccfg), n)
-        if getattr(self, "_bws", None) is None or self._bws.numel() < nbytes:
-            self._bws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        if pin is not None:
+            bws = self._pinned.get(("bws", pin))
+            if bws is None or bws.numel() < nbytes:
+                if bws is not None:
+                    raise _lib.RlsbError("a pinned (graph-owned) backward workspace cannot grow")
+                bws = self._pinned[("bws", pin)] = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        else:
+            if getattr(self, "_bws", None) is None or self._bws.numel() < nbytes:
+                self._bws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+            bws = self._bws
         g_actions = torch.empty((H, n, self.cfg.A), device=self.device, dtype=torch.float32)
         co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
                                                       "rewards", "discounts", "values", "actor_raw",
                                                       "determ_packed", "stoch_packed", "tape")])
         check(self.lib.rlsb_imagine_bwd(C.byref(ccfg), self.packed.data_ptr(), n, C.byref(co), g_rewards.data_ptr(),
-                                        g_values.data_ptr(), g_actions.data_ptr(), self._bws.data_ptr(), _stream()),
+                                        g_values.data_ptr(), g_actions.data_ptr(), bws.data_ptr(), _stream()),
               "rlsb_imagine_bwd")
         return g_actions
 
@@ -460,7 +480,8 @@ class ACUpdateEngine:
         if nbytes == 0:
             raise _lib.RlsbError(f"unsupported actor-critic update config {cfg}")
         self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
-        self._ws, self._ws_rows = None, 0
+        self._ws, self._ws_bytes = None, 0
+        self._pinned: dict = {}   # graph-owned workspaces, see ImaginationEngine.workspace
         self.scalars = torch.zeros(_lib.AC_SCALARS, device=self.device, dtype=torch.float32)
 
     def pack(self, actor_sd: dict, critic_sd: dict, actor_prefix="actor.", critic_prefix="critic.") -> None:
@@ -471,25 +492,36 @@ class ACUpdateEngine:
               "rlsb_ac_pack")
         self._keep = keep
 
-    def _workspace(self, ccfg, n: int) -> torch.Tensor:
-        if self._ws is None or self._ws_rows < n:
-            nbytes = self.lib.rlsb_ac_workspace_bytes(C.byref(ccfg), n)
+    def _workspace(self, ccfg, n: int, pin=None) -> torch.Tensor:
+        """The size depends on the rows AND the horizon (rlsb_ac_workspace_bytes): tracked in bytes."""
+        nbytes = self.lib.rlsb_ac_workspace_bytes(C.byref(ccfg), n)
+        if pin is not None:
+            buf = self._pinned.get(pin)
+            if buf is None:
+                buf = self._pinned[pin] = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+            elif buf.numel() < nbytes:
+                raise _lib.RlsbError("a pinned (graph-owned) workspace cannot grow: capture a new graph for the new shape")
+            return buf
+        if self._ws is None or self._ws_bytes < nbytes:
             self._ws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
-            self._ws_rows = n
+            self._ws_bytes = nbytes
+            self._ws_layout = None
         return self._ws
 
-    def actor_slots(self, n: int, horizon: Optional[int] = None) -> ActorSlots:
+    def actor_slots(self, n: int, horizon: Optional[int] = None, pin=None) -> ActorSlots:
         """Where ``ImaginationEngine.rollout(..., actor_slots=...)`` leaves the actor's activations for ``update``."""
         ccfg = AcCfg.from_buffer_copy(self.ccfg)
         ccfg.H = horizon if horizon is not None else self.cfg.H
-        ws = self._workspace(ccfg, n)   # the slices are laid out for n rows; update(n) uses the same layout
+        ws = self._workspace(ccfg, n, pin)   # the slices are laid out for (n rows, H); update(n, H) uses the same layout
+        if pin is None:
+            self._ws_layout = (n, ccfg.H, ws.data_ptr())
         slots = ActorSlots()
         check(self.lib.rlsb_ac_actor_slots(C.byref(ccfg), n, ws.data_ptr(), C.byref(slots)), "rlsb_ac_actor_slots")
         return slots
 
     def update(self, rollout: dict, vs: torch.Tensor, w: torch.Tensor, actor_seq, critic_seq, seed: int = 0,
                horizon: Optional[int] = None, g_actions: Optional[torch.Tensor] = None,
-               seed_device: Optional[torch.Tensor] = None, actor_forward_done: bool = False) -> torch.Tensor:
+               seed_device: Optional[torch.Tensor] = None, actor_forward_done: bool = False, pin=None) -> torch.Tensor:
         """Writes .grad of every parameter of ``actor_seq`` / ``critic_seq`` (fc_nn Sequentials) and returns the
         RLSB_AC_SCALARS loss / metric vector (device tensor, see _lib.AC_SCALAR_NAMES)."""
         if rollout.get("determ_packed") is None:
@@ -499,9 +531,13 @@ class ACUpdateEngine:
         ccfg = AcCfg.from_buffer_copy(self.ccfg)
         ccfg.H = H
         ccfg.actor_fwd_in_rollout = int(actor_forward_done)
-        if actor_forward_done and (self._ws is None or self._ws_rows < n):
+        if actor_forward_done and pin is None and getattr(self, "_ws_layout", None) is None:
             raise _lib.RlsbError("update(actor_forward_done=True): the rollout must have been given actor_slots(n) of this engine")
-        self._workspace(ccfg, n)
+        if actor_forward_done and pin is not None and pin not in self._pinned:
+            raise _lib.RlsbError("update(actor_forward_done=True, pin=...): actor_slots(n, pin=...) was not called for this graph")
+        ws = self._workspace(ccfg, n, pin)
+        if actor_forward_done and pin is None and self._ws_layout != (n, H, ws.data_ptr()):
+            raise _lib.RlsbError("update(actor_forward_done=True): the workspace changed since actor_slots(n, H) was taken")
         keep: list = []
         ga, gc = _mlp_grads(actor_seq, keep), _mlp_grads(critic_seq, keep)
         vs, w = _f32c(vs), _f32c(w)
@@ -513,7 +549,7 @@ class ACUpdateEngine:
                                       values.data_ptr(), actions.data_ptr(),
                                       _ptr(None if g_actions is None else _f32c(g_actions)), seed, _ptr(seed_device),
                                       C.byref(ga), C.byref(gc),
-                                      self.scalars.data_ptr(), self._ws.data_ptr(), _stream()), "rlsb_ac_update")
+                                      self.scalars.data_ptr(), ws.data_ptr(), _stream()), "rlsb_ac_update")
         return self.scalars
 
 

@@ -35,6 +35,7 @@ class SlotAttention(nn.Module):
         self.prev_slots = None
         self.last_attention = None
         self._engine = None
+        self._engines = None
         self._engine_key = None
 
     def generate_initial(self, batch: int):
@@ -47,9 +48,15 @@ class SlotAttention(nn.Module):
 
     def _kernel_forward_prepare(self, X):
         from rl_sandbox_b200 import ops
-        key = (X.shape[1], tuple(p._version for p in self.parameters()))
-        if self._engine is None or self._engine.tokens != X.shape[1]:
-            self._engine = ops.SlotAttentionEngine(self.n_slots, self.n_dim, X.shape[1], self.n_iter, device=X.device)
+        key = (X.shape[0], X.shape[1], tuple(p._version for p in self.parameters()))
+        # one engine per (frames, tokens), kept alive: CUDA graphs captured around a call replay its raw workspace pointers
+        shape = (X.shape[0], X.shape[1])
+        if self._engines is None:
+            self._engines = {}
+        if shape not in self._engines:
+            self._engines[shape] = ops.SlotAttentionEngine(self.n_slots, self.n_dim, X.shape[1], self.n_iter, device=X.device)
+        if self._engine is not self._engines[shape]:
+            self._engine = self._engines[shape]
             self._engine_key = None
         if self._engine_key != key:
             self._engine.pack(self.state_dict())
