@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RLSB_ABI_VERSION 3
+#define RLSB_ABI_VERSION 4
 
 /* ---- library / device ------------------------------------------------------------------- */
 int rlsb_abi_version(void);
@@ -137,6 +137,11 @@ typedef struct {
   int32_t attention_blocks;
   int32_t symmetric_qk;
   float mixer_coeff;
+  /* 1: split-operand ("bf16 x 3") contractions — every operand x travels as bf16(x) and bf16(x - bf16(x)), a Linear is
+   * one tcgen05 contraction over [hi.Whi | hi.Wlo | lo.Whi] with fp32 accumulation: results within ~1e-5 of the
+   * reference's fp32 path (north star: rtol 1e-3) at 3x the tensor work.  The verification mode of the parity tests;
+   * flat RSSM, forward only (no tape, no actor_slots).  The packed blob depends on it: pack with the same cfg. */
+  int32_t parity;
 } rlsb_imagine_cfg;
 
 /* fp32 parameters in nn.Linear layout (weight = [out, in] row-major); NULL = absent.
@@ -304,6 +309,15 @@ int rlsb_ac_pack(const rlsb_ac_cfg* cfg, const rlsb_mlp_params* actor, const rls
  * g_actions: (H, N, A) d loss_actor / d a_t from rlsb_imagine_bwd when rho != 1 (continuous actor), else NULL;
  * scalars: RLSB_AC_SCALARS floats (device).  seed (or the device-resident seed_device, if non-NULL) keys the
  * Philox stream of the metric draws. */
+/* The loss half of rlsb_ac_update on its own: head_out is (2, H * rlsb_packed_rows(N), 32) fp32 — group 0 the actor's
+ * raw outputs (logits, or mean | std pre-activations) of states 0..H-1 in columns [0, A or 2A), group 1 the critic's
+ * value in column 0; step t occupies rows [t * rlsb_packed_rows(N), ... + N).  Writes the RLSB_AC_SCALARS losses /
+ * metrics of ImaginativeCritic.calculate_loss / ImaginativeActor.calculate_loss (ac.py:68-81,113-146); the dynamics
+ * term is reported, gradients are not formed.  With head outputs from a rollout in the split-operand mode
+ * (rlsb_imagine_cfg::parity) this is the fp32-grade evaluation of the losses. */
+int rlsb_ac_losses(const rlsb_ac_cfg* cfg, int64_t N, const float* head_out, const float* vs, const float* w,
+                   const float* values, const float* actions, uint64_t seed, float* scalars, void* workspace,
+                   void* stream);
 /* the actor's slices of `workspace` (rlsb_ac_workspace_bytes(cfg, N) bytes) for rlsb_imagine_out::actor_slots */
 int rlsb_ac_actor_slots(const rlsb_ac_cfg* cfg, int64_t N, void* workspace, rlsb_actor_slots* slots);
 int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_t N, const void* determ_packed,

@@ -24,7 +24,7 @@ class ImagineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "predict_discount",
         "with_critic", "H", "discount_nan_on_tie", "with_backward", "slots", "attention_blocks",
-        "symmetric_qk")] + [("mixer_coeff", C.c_float)]
+        "symmetric_qk")] + [("mixer_coeff", C.c_float), ("parity", C.c_int32)]
 
 
 class MlpParams(C.Structure):
@@ -73,7 +73,7 @@ AC_SCALAR_NAMES = {
     "loss_actor": 4, "critic/avg_target_value": 5, "critic/avg_lambda_value": 6, "critic/avg_predicted_value": 7,
     "actor/avg_val": 8, "actor/mean_val": 9, "actor/avg_sd": 10, "actor/min_val": 11, "actor/max_val": 12}
 AC_SCALARS = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class SlotCfg(C.Structure):
@@ -182,6 +182,7 @@ def load() -> C.CDLL:
         "rlsb_ac_actor_slots": (C.c_int, [C.POINTER(AcCfg), i64, vp, C.POINTER(ActorSlots)]),
         "rlsb_ac_update": (C.c_int, [C.POINTER(AcCfg), vp, i64, vp, vp, vp, vp, vp, vp, vp, u64, vp, C.POINTER(MlpGrads),
                                      C.POINTER(MlpGrads), vp, vp, vp]),
+        "rlsb_ac_losses": (C.c_int, [C.POINTER(AcCfg), i64, vp, vp, vp, vp, vp, u64, vp, vp, vp]),
         "rlsb_imagine_tape_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
         "rlsb_imagine_bwd_workspace_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
         "rlsb_imagine_bwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, C.POINTER(ImagineOut), vp, vp, vp, vp, vp]),

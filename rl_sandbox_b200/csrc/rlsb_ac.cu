@@ -662,3 +662,40 @@ extern "C" int rlsb_ac_update(const rlsb_ac_cfg* cfg, const void* packed, int64_
   }
   return 0;
 }
+
+// Loss / metric scalars from caller-supplied head outputs: the loss kernel of rlsb_ac_update on its own.  Used with the
+// head outputs of a rollout in the split-operand contraction mode (rlsb_imagine_cfg::parity) it evaluates
+// ImaginativeCritic.calculate_loss / ImaginativeActor.calculate_loss (ac.py:68-81,113-146) at fp32-grade precision.
+extern "C" int rlsb_ac_losses(const rlsb_ac_cfg* cfg, int64_t N, const float* head_out, const float* vs, const float* w,
+                              const float* values, const float* actions, uint64_t seed, float* scalars, void* workspace,
+                              void* stream_) {
+  if (!cfg || !head_out || !vs || !w || !values || !actions || !scalars || !workspace || N <= 0) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  AcPlan P;
+  RLSB_TRY(make_ac_plan(*cfg, P));
+  AcWorkspace W;
+  RLSB_TRY(make_ac_workspace(P, N, W));
+  if (W.M > (1LL << 30)) return -3;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  double* accum = reinterpret_cast<double*>(ws + W.accum);
+  cudaError_t ce = cudaMemsetAsync(accum, 0, kScalars * sizeof(double), s);
+  if (ce != cudaSuccess) return static_cast<int>(ce);
+  ce = cudaMemsetAsync(accum + kAccMinKey, 0x7f, sizeof(double), s);
+  if (ce != cudaSuccess) return static_cast<int>(ce);
+  ce = cudaMemsetAsync(accum + kAccMaxKey, 0x80, sizeof(double), s);
+  if (ce != cudaSuccess) return static_cast<int>(ce);
+  AcLossArgs a{};
+  a.head_out = head_out; a.group_stride = W.M * 32;
+  a.m_pad = W.m_pad; a.N = static_cast<int>(N); a.H = P.H; a.A = P.A;
+  a.vs = vs; a.w = w; a.values = values; a.actions = actions; a.g_actions = nullptr;
+  a.discrete = cfg->discrete;
+  a.rho = cfg->rho; a.eta = cfg->eta; a.metrics_samples = cfg->metrics_samples; a.seed = seed; a.seed_ptr = nullptr;
+  a.dy4 = reinterpret_cast<__nv_bfloat16*>(ws + W.dy4); a.accum = accum;
+  ac_loss_kernel<<<static_cast<unsigned>((W.M + 127) / 128), 128, 0, s>>>(a);
+  count_launch();
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return static_cast<int>(ce);
+  ac_finalize_kernel<<<1, 32, 0, s>>>(accum, P.H, N, P.A, cfg->metrics_samples, cfg->discrete, scalars);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}

@@ -48,6 +48,21 @@ __global__ void onehot_to_idx_kernel(const float* __restrict__ z, long long N, i
     if (_e != 0) return _e;       \
   } while (0)
 
+// weight image of one Linear: plain, or — Plan::parity — the split layout [Whi | Wlo | Whi] per input segment (each
+// block as wide as the segment's padded width; LayerPlan::kp is already three times the padded input width)
+int pack_weight(const Plan& P, const float* src, long long ld, int rows, __nv_bfloat16* dst, const LayerPlan& L, int n,
+                const PackSeg* segs, cudaStream_t s) {
+  if (!P.parity) return launch_pack(src, ld, rows, dst, L.RB, L.NB * L.RB, L.kp, n, segs, s);
+  if (3 * n > 8) return -22;
+  PackSeg ex[8];
+  const int kp0 = L.kp / 3;
+  for (int i = 0; i < n; ++i) {
+    const int w = (i + 1 < n ? segs[i + 1].dst_k0 : kp0) - segs[i].dst_k0;
+    for (int j = 0; j < 3; ++j) ex[3 * i + j] = PackSeg{3 * segs[i].dst_k0 + j * w, segs[i].src_c0, segs[i].len, j == 1 ? 1 : 0};
+  }
+  return launch_pack(src, ld, rows, dst, L.RB, L.NB * L.RB, L.kp, 3 * n, ex, s);
+}
+
 const rlsb_mlp_params* head_params(const rlsb_imagine_params& p, const Plan& P, int g) {
   if (g == P.g_actor) return &p.actor;
   if (g == P.g_reward) return &p.reward;
@@ -56,6 +71,13 @@ const rlsb_mlp_params* head_params(const rlsb_imagine_params& p, const Plan& P, 
 }
 
 }  // namespace
+
+int launch_onehot_to_idx(const float* z, long long rows, int groups, int classes, uint8_t* idx, cudaStream_t s) {
+  const long long tot = rows * groups;
+  onehot_to_idx_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(z, rows, groups, classes, idx);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
 
 }  // namespace rlsb
 
@@ -98,7 +120,7 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
   {
     const LayerPlan& L = P.img_in;  // input = cat[stoch, action]
     PackSeg segs[2] = {{0, 0, P.S}, {P.Sp, P.S, P.A}};
-    RLSB_TRY(launch_pack(prm->img_in_w, P.S + P.A, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 2, segs, s));
+    RLSB_TRY(pack_weight(P, prm->img_in_w, P.S + P.A, L.N, wptr(L), L, 2, segs, s));
     RLSB_TRY(copy_pad(prm->img_in_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
     if (prm->img_in_ln_g) {
       RLSB_TRY(copy_pad(prm->img_in_ln_g, L.N, fptr(L.g_off), ru(L.N, 32), 1.f, s));
@@ -108,7 +130,7 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
   {
     const LayerPlan& L = P.gru;  // input = cat[x, h]
     PackSeg segs[2] = {{0, 0, P.D}, {P.Dp, P.D, P.D}};
-    RLSB_TRY(launch_pack(prm->gru_w, 2 * P.D, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 2, segs, s));
+    RLSB_TRY(pack_weight(P, prm->gru_w, 2 * P.D, L.N, wptr(L), L, 2, segs, s));
     RLSB_TRY(copy_pad(prm->gru_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
     RLSB_TRY(copy_pad(prm->gru_ln_g, L.N, fptr(L.g_off), L.N, 1.f, s));
     RLSB_TRY(copy_pad(prm->gru_ln_b, L.N, fptr(L.b_off), L.N, 0.f, s));
@@ -116,7 +138,7 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
   {
     const LayerPlan& L = P.prior1;
     PackSeg segs[1] = {{0, 0, P.D}};
-    RLSB_TRY(launch_pack(prm->prior1_w, P.D, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 1, segs, s));
+    RLSB_TRY(pack_weight(P, prm->prior1_w, P.D, L.N, wptr(L), L, 1, segs, s));
     RLSB_TRY(copy_pad(prm->prior1_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
     if (prm->prior1_ln_g) {
       RLSB_TRY(copy_pad(prm->prior1_ln_g, L.N, fptr(L.g_off), ru(L.N, 32), 1.f, s));
@@ -126,7 +148,7 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
   {
     const LayerPlan& L = P.prior2;
     PackSeg segs[1] = {{0, 0, P.D}};
-    RLSB_TRY(launch_pack(prm->prior2_w, P.D, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 1, segs, s));
+    RLSB_TRY(pack_weight(P, prm->prior2_w, P.D, L.N, wptr(L), L, 1, segs, s));
     RLSB_TRY(copy_pad(prm->prior2_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
   }
   // ---- heads (fc_nn.py:4-23): groups share one launch per layer ----
@@ -143,11 +165,10 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
           segs[2 * k] = PackSeg{k * (P.Dp + P.Sp), k * (P.D + P.S), P.D};
           segs[2 * k + 1] = PackSeg{k * (P.Dp + P.Sp) + P.Dp, k * (P.D + P.S) + P.D, P.S};
         }
-        RLSB_TRY(launch_pack(hp->w[l], static_cast<long long>(P.K) * (P.D + P.S), n_out, dst, L.RB, L.NB * L.RB, L.kp,
-                             2 * P.K, segs, s));
+        RLSB_TRY(pack_weight(P, hp->w[l], static_cast<long long>(P.K) * (P.D + P.S), n_out, dst, L, 2 * P.K, segs, s));
       } else {
         PackSeg segs[1] = {{0, 0, P.Hd}};
-        RLSB_TRY(launch_pack(hp->w[l], P.Hd, n_out, dst, L.RB, L.NB * L.RB, L.kp, 1, segs, s));
+        RLSB_TRY(pack_weight(P, hp->w[l], P.Hd, n_out, dst, L, 1, segs, s));
       }
       if (l == 0 && P.K > 1 && prm->pos_enc) {
         // State.combined_slots adds the constant pos_enc to [h_k, z_k] (rssm_slots_attention.py:37-41):
@@ -228,6 +249,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   Plan P;
   RLSB_TRY(make_plan(*cfg, P));
+  if (P.parity) return imagine_fwd_parity(cfg, P, packed, N, h0, z0, logits0, noise, out, workspace, s);
   Workspace W;
   make_workspace(P, N, W);
   const int M = static_cast<int>(N);          // start states: rows of the head operands
@@ -304,12 +326,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     }
     e = cudaMemsetAsync(out->actions, 0, static_cast<size_t>(N) * P.A * 4, s);
     if (e != cudaSuccess) return static_cast<int>(e);
-    const long long tot = static_cast<long long>(Ms) * cfg->groups;
-    onehot_to_idx_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(z0, Ms, cfg->groups,
-                                                                                  cfg->classes, out->stoch_idx);
-    count_launch();
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return static_cast<int>(e);
+    RLSB_TRY(launch_onehot_to_idx(z0, Ms, cfg->groups, cfg->classes, out->stoch_idx, s));
   }
 
   // heads work on M start states; RSSM layers on Ms = M * slots rows

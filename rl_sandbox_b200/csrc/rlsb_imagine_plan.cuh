@@ -5,6 +5,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <cuda_runtime.h>
+
 #include "../../include/rlsb.h"
 
 namespace rlsb {
@@ -49,6 +51,9 @@ struct Plan {
   int K = 1, nblk = 0;
   LayerPlan mix_qkv, mix_fc;
   size_t mix_pre_g = 0, mix_pre_b = 0, mix_fcn_g = 0, mix_fcn_b = 0;   // fp32 [D]
+  // ---- split-operand contraction mode (cfg.parity): every weight image carries [Whi | Wlo | Whi] per input segment,
+  //      i.e. LayerPlan::kp is three times the padded input width (rlsb_imagine_parity.cu)
+  bool parity = false;
   // ---- backward (cfg.with_backward): dX operands ----
   bool bwd = false;
   int Gb = 0, gb0 = 0;       // head groups that carry gradient: gb0 .. gb0+Gb-1 (reward .. target critic)
@@ -76,6 +81,9 @@ inline int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
   P.K = c.slots > 1 ? c.slots : 1;
   P.nblk = P.K > 1 ? c.attention_blocks : 0;
   if (P.K > 1 && (P.K > 4 || P.D > 512 || c.with_backward || P.nblk < 0)) return -16;
+  P.parity = c.parity != 0;
+  if (P.parity && (P.K > 1 || c.with_backward)) return -17;   // verification mode: flat RSSM, forward only
+  const int kmul = P.parity ? 3 : 1;
   int g = 0;
   P.g_actor = g++;
   P.g_reward = g++;
@@ -91,15 +99,15 @@ inline int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
     L.g_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
     L.b_off = place(cur, static_cast<size_t>(L.G) * ln_len_per_group * 4);
   };
-  P.img_in.N = P.D; P.img_in.kp = P.Sp + P.Ap; finish(P.img_in, ru(P.D, 32));
-  P.gru.N = 3 * P.D; P.gru.kp = 2 * P.Dp;      finish(P.gru, 3 * P.D);
-  P.prior1.N = P.D; P.prior1.kp = P.Dp;        finish(P.prior1, ru(P.D, 32));
-  P.prior2.N = P.S; P.prior2.kp = P.Dp;        finish(P.prior2, 32);
+  P.img_in.N = P.D; P.img_in.kp = kmul * (P.Sp + P.Ap); finish(P.img_in, ru(P.D, 32));
+  P.gru.N = 3 * P.D; P.gru.kp = kmul * 2 * P.Dp; finish(P.gru, 3 * P.D);
+  P.prior1.N = P.D; P.prior1.kp = kmul * P.Dp;   finish(P.prior1, ru(P.D, 32));
+  P.prior2.N = P.S; P.prior2.kp = kmul * P.Dp;   finish(P.prior2, 32);
   for (int l = 0; l < 5; ++l) {
     LayerPlan& L = P.head[l];
     L.G = P.G;
     L.N = (l == 4) ? P.Aout : P.Hd;
-    L.kp = (l == 0) ? P.K * (P.Dp + P.Sp) : P.Hp;
+    L.kp = kmul * ((l == 0) ? P.K * (P.Dp + P.Sp) : P.Hp);
     finish(L, ru(L.N, 32));
   }
   if (P.K > 1) {
@@ -167,6 +175,10 @@ struct Workspace {
   size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
   // slotted RSSM: per-slot operand planes for the heads and the mixer's buffers
   size_t hplanes, zplanes, hpost, mix_ln, mix_qkv, mix_upd, mix_fc;
+  // split-operand mode (Plan::parity): fp32 pre-activation buffers, the residual ("lo") images and a zero image
+  size_t p_pre = 0, p_head_pre = 0, p_hlo[2] = {0, 0}, p_zero = 0, p_zero_bytes = 0, p_hid_lo[2] = {0, 0}, p_alo = 0,
+         p_xlo = 0, p_ylo = 0;
+  long long p_ld = 0, p_ld_head = 0;
   long long ld_scratch, ld_qkv;
   int m_pad;    // rows of the head operands (start states, padded)
   int ms_pad;   // rows of the RSSM operands (start states x slots, padded)
@@ -202,10 +214,31 @@ inline void make_workspace(const Plan& P, long long N, Workspace& W) {
     W.mix_upd = place(cur, static_cast<size_t>(ms_pad) * P.Dp * 2);
     W.mix_fc = place(cur, static_cast<size_t>(ms_pad) * P.D * 4);
   }
+  if (P.parity) {
+    const size_t mp = static_cast<size_t>(m_pad);
+    W.p_ld = ru(3 * P.D, 4);
+    W.p_ld_head = ru(P.Hd, 4);
+    W.p_pre = place(cur, mp * W.p_ld * 4);
+    W.p_head_pre = place(cur, static_cast<size_t>(P.G) * mp * W.p_ld_head * 4);
+    for (int i = 0; i < 2; ++i) W.p_hlo[i] = place(cur, mp * P.Dp * 2);
+    W.p_zero_bytes = mp * P.Sp * 2;
+    W.p_zero = place(cur, W.p_zero_bytes);
+    for (int i = 0; i < 2; ++i) W.p_hid_lo[i] = place(cur, static_cast<size_t>(P.G) * mp * P.Hp * 2);
+    W.p_alo = place(cur, mp * P.Ap * 2);
+    W.p_xlo = place(cur, mp * P.Dp * 2);
+    W.p_ylo = place(cur, mp * P.Dp * 2);
+  }
   W.bytes = rus(cur, 1024);
 }
 
 
 
 }  // namespace k1
+
+// start-state one-hot rows -> uint8 class indices (rlsb_imagine.cu)
+int launch_onehot_to_idx(const float* z, long long rows, int groups, int classes, uint8_t* idx, cudaStream_t s);
+// the rollout in the split-operand contraction mode (rlsb_imagine_parity.cu)
+int imagine_fwd_parity(const rlsb_imagine_cfg* cfg, const k1::Plan& P, const void* packed, int64_t N, const float* h0,
+                       const float* z0, const float* logits0, const rlsb_noise* noise, const rlsb_imagine_out* out,
+                       void* workspace, cudaStream_t s);
 }  // namespace rlsb

@@ -17,6 +17,9 @@ __device__ __forceinline__ uint32_t bf2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// x - float(bf16(x)): what the "lo" image of the split-operand contraction mode carries (exact in fp32)
+__device__ __forceinline__ float bf16_residual(float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); }
+
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == ACT_ELU) return x > 0.f ? x : expm1f(x);
   if (act == ACT_RELU) return fmaxf(x, 0.f);
@@ -52,8 +55,10 @@ __global__ void pack_kernel(const PackArgs a) {
         const int k = k0 + j;
         for (int s = 0; s < a.n_seg; ++s) {
           const int off = k - a.seg[s].dst_k0;
-          if (off >= 0 && off < a.seg[s].len)
+          if (off >= 0 && off < a.seg[s].len) {
             x = __ldg(a.src + row * a.ld_src + a.seg[s].src_c0 + off);
+            if (a.seg[s].part) x = bf16_residual(x);
+          }
         }
       }
       v[j] = x;
@@ -91,7 +96,10 @@ __global__ void pack_multi_kernel(const __grid_constant__ PackJobs J) {
         const int k = k0 + e;
         for (int s = 0; s < a.n_seg; ++s) {
           const int off = k - a.seg[s].dst_k0;
-          if (off >= 0 && off < a.seg[s].len) x = __ldg(a.src + row * a.ld_src + a.seg[s].src_c0 + off);
+          if (off >= 0 && off < a.seg[s].len) {
+            x = __ldg(a.src + row * a.ld_src + a.seg[s].src_c0 + off);
+            if (a.seg[s].part) x = bf16_residual(x);
+          }
         }
       }
       v[e] = x;
@@ -773,6 +781,13 @@ __global__ void head_finish_kernel(const HeadFinishParams p) {
                               bf2(act[c0 + 4], act[c0 + 5]), bf2(act[c0 + 6], act[c0 + 7]));
         const size_t idx = packed_index(row, static_cast<size_t>(c0), static_cast<size_t>(p.a_kpad), kTileM);
         *reinterpret_cast<uint4*>(p.action_packed + idx) = pk;
+        if (p.action_packed_lo) {
+          float l[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) l[j] = bf16_residual(act[c0 + j]);
+          *reinterpret_cast<uint4*>(p.action_packed_lo + idx) =
+              make_uint4(bf2(l[0], l[1]), bf2(l[2], l[3]), bf2(l[4], l[5]), bf2(l[6], l[7]));
+        }
       }
     }
   }

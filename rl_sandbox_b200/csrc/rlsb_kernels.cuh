@@ -11,6 +11,8 @@ struct PackSeg {
   int dst_k0;  // first destination column (inside the padded K axis)
   int src_c0;  // first source column
   int len;     // columns
+  int part = 0;  // 0: bf16(x); 1: the residual bf16(x - float(bf16(x))) — the "lo" image of the split-operand
+                 // (bf16 x 3) contraction mode, rlsb_imagine_cfg::parity (launch_pack only)
 };
 
 // fp32 row-major [rows_src x *] (leading dim ld_src) -> packed bf16 [rows_dst_pad x k_pad] with
@@ -97,6 +99,7 @@ struct HeadFinishParams {
   float* actor_raw_out; // [M][A or 2A] raw actor head output (logits / mean,std pre-activations) or nullptr
   const float* precomp; // [M][A] action to replay instead of sampling, or nullptr
   __nv_bfloat16* action_packed;  // [action_rows_pad x a_kpad]
+  __nv_bfloat16* action_packed_lo;  // residual image of the action (split-operand mode) or nullptr
   int a_kpad;
   int action_repeat;             // slots (each action row is written `action_repeat` times), 0/1 = flat
   int action_rows_pad;           // rows of the action image
@@ -104,6 +107,20 @@ struct HeadFinishParams {
 int launch_head_finish(const HeadFinishParams& p, cudaStream_t stream);
 
 // K2 (reference: ac.py:52-66 + dreamer_v2.py:192-197 + ac.py:118)
+// ---- split-operand ("bf16 x 3") contraction mode: rlsb_imagine_cfg::parity ------------------------------------------
+// Every activation x is carried as two packed bf16 images, hi = bf16(x) and lo = bf16(x - hi); with the weights split the
+// same way, x.w = hi.Whi + hi.Wlo + lo.Whi + O(2^-17 |x||w|) — three K segments of the tcgen05 contraction, fp32
+// accumulation, i.e. fp32-grade results from the bf16 tensor-core path.
+// fp32 pre-activations [G][m_pad x ld] (bias already added) -> [LayerNorm over N columns] -> act -> hi / lo images
+int launch_ln_act_split(const float* pre, long long ld, long long group_stride, int G, int M, int m_pad, int N,
+                        const float* gamma, const float* beta, int ln_group_stride, float eps, int act,
+                        __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int out_kpad, long long out_group_stride,
+                        cudaStream_t stream);
+// GRU gates (common.py:69-81) with its own two-pass LayerNorm statistics and libm-grade sigmoid / tanh
+int launch_gru_gate_split(const float* pre, long long ld, int M, int m_pad, int D, const float* gamma, const float* beta,
+                          float eps, float update_bias, const float* h_prev, long long ld_h, float* h_next, long long ld_hn,
+                          __nv_bfloat16* h_hi, __nv_bfloat16* h_lo, int kpad, cudaStream_t stream);
+
 int launch_lambda_return(const float* r, const float* v, const float* d, int T, long long N,
                          double lambda_, float* vs, float* w, float* adv, int layout_batch_major,
                          cudaStream_t stream);

@@ -250,12 +250,13 @@ class ImagineConfig:
     attention_blocks: int = 3
     symmetric_qk: bool = False
     mixer_coeff: float = 1.0           # attention_scheduler.val
+    parity: bool = False               # split-operand ("bf16 x 3") contractions: fp32-grade results, 3x tensor work
 
     def to_c(self) -> ImagineCfg:
         return ImagineCfg(self.D, self.groups, self.classes, self.A, self.hidden, int(self.discrete),
                           int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H,
                           int(self.discount_nan_on_tie), int(self.with_backward), int(self.slots),
-                          int(self.attention_blocks), int(self.symmetric_qk), float(self.mixer_coeff))
+                          int(self.attention_blocks), int(self.symmetric_qk), float(self.mixer_coeff), int(self.parity))
 
 
 def _mlp_params(sd: dict, prefix: str, keep: list) -> MlpParams:
@@ -551,6 +552,36 @@ class ACUpdateEngine:
                                       C.byref(ga), C.byref(gc),
                                       self.scalars.data_ptr(), ws.data_ptr(), _stream()), "rlsb_ac_update")
         return self.scalars
+
+
+    def losses_from_heads(self, actor_raw: torch.Tensor, critic_values: torch.Tensor, vs: torch.Tensor, w: torch.Tensor,
+                          values: torch.Tensor, actions: torch.Tensor, seed: int = 0,
+                          horizon: Optional[int] = None) -> torch.Tensor:
+        """rlsb_ac_losses: the loss kernel of the update on caller-supplied head outputs — ``actor_raw`` (H, N, A or 2A)
+        the actor's raw outputs and ``critic_values`` (H, N) the critic's values on states 0..H-1 (e.g. from a rollout in
+        the split-operand mode, ``ImagineConfig(parity=True)``); vs (H, N), w / values (H+1, N), actions (H+1, N, A).
+        Returns a copy of the RLSB_AC_SCALARS vector."""
+        H = horizon if horizon is not None else self.cfg.H
+        ccfg = AcCfg.from_buffer_copy(self.ccfg)
+        ccfg.H = H
+        n = critic_values.shape[1]
+        rows = round_up(n, 128)
+        actor_raw, critic_values = _f32c(actor_raw), _f32c(critic_values)
+        if actor_raw.shape[:2] != (H, n) or critic_values.shape[0] != H:
+            raise _lib.RlsbError(f"losses_from_heads: actor_raw {tuple(actor_raw.shape)} / critic_values "
+                                 f"{tuple(critic_values.shape)} for H={H}")
+        head = torch.zeros((2, H, rows, 32), device=self.device, dtype=torch.float32)
+        head[0, :, :n, :actor_raw.shape[-1]] = actor_raw
+        head[1, :, :n, 0] = critic_values.reshape(H, n)
+        vs, w, values, actions = _f32c(vs), _f32c(w), _f32c(values), _f32c(actions)
+        if vs.numel() != H * n or w.numel() != (H + 1) * n or values.numel() != (H + 1) * n:
+            raise _lib.RlsbError("losses_from_heads: vs must be (H, N), w / values (H+1, N)")
+        ws = torch.empty(self.lib.rlsb_ac_workspace_bytes(C.byref(ccfg), n), device=self.device, dtype=torch.uint8)
+        scal = torch.zeros(_lib.AC_SCALARS, device=self.device, dtype=torch.float32)
+        check(self.lib.rlsb_ac_losses(C.byref(ccfg), n, head.data_ptr(), vs.data_ptr(), w.data_ptr(), values.data_ptr(),
+                                      actions.data_ptr(), seed, scal.data_ptr(), ws.data_ptr(), _stream()),
+              "rlsb_ac_losses")
+        return scal
 
 
 # ------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     missing = [n for n in names if n not in exported]
     assert not missing, f"declared in include/rlsb.h but not exported: {missing}"
-    assert lib.rlsb_abi_version() == 3
+    assert lib.rlsb_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_no_torch_types_in_abi():
@@ -57,6 +57,14 @@ def test_argument_errors_are_negative_codes():
     cfg = _lib.ImagineCfg(1024, 32, 32, 17, 400, 1, 1, 1, 1, 15, 1)
     assert lib.rlsb_imagine_packed_bytes(C.byref(cfg)) > 20_000_000
     assert lib.rlsb_imagine_workspace_bytes(C.byref(cfg), 800) > 0
+    # split-operand mode (cfg.parity): three weight blocks per input segment, extra residual images in the workspace;
+    # flat RSSM and forward only
+    plain = lib.rlsb_imagine_packed_bytes(C.byref(cfg))
+    par = _lib.ImagineCfg(1024, 32, 32, 17, 400, 1, 1, 1, 1, 15, 1, parity=1)
+    assert 2.9 * plain < lib.rlsb_imagine_packed_bytes(C.byref(par)) < 3.1 * plain
+    assert lib.rlsb_imagine_workspace_bytes(C.byref(par), 800) > lib.rlsb_imagine_workspace_bytes(C.byref(cfg), 800)
+    assert lib.rlsb_imagine_packed_bytes(C.byref(_lib.ImagineCfg(200, 32, 32, 1, 400, 0, 1, 0, 1, 15, 1, slots=4, parity=1))) == 0
+    assert lib.rlsb_imagine_packed_bytes(C.byref(_lib.ImagineCfg(200, 32, 32, 12, 400, 0, 0, 0, 1, 15, 1, with_backward=1, parity=1))) == 0
 
 
 @pytest.mark.gpu   # the workspace plan sizes the weight-gradient partials by the SM count of the device

@@ -29,7 +29,7 @@ def test_wgrad_contraction(cuda, M, n, k):
     assert (out[:, k:] == 0).all()
 
 
-def _reference_grads(agent, k1, vs, w):
+def _reference_grads(agent, k1, vs, w, metrics_samples=128):
     """critic.calculate_loss / actor.calculate_loss + backward with torch autograd (the reference's op sequence)."""
     zs = torch.cat([k1["determ"], torch.nn.functional.one_hot(k1["stoch_idx"].long(), 32).float().flatten(-2)], -1)
     values = k1["values"].unsqueeze(-1)
@@ -38,7 +38,7 @@ def _reference_grads(agent, k1, vs, w):
     for p in list(agent.actor.parameters()) + list(agent.critic.parameters()):
         p.grad = None
     lc, mc = agent.critic.calculate_loss(zs[:-1], vs3, w3[:-1], target_values=values[:-1])
-    la, ma = agent.actor.calculate_loss(zs[:-2], vs3[1:], values[:-2], w3[:-2], actions[1:-1], metrics_samples=128)
+    la, ma = agent.actor.calculate_loss(zs[:-2], vs3[1:], values[:-2], w3[:-2], actions[1:-1], metrics_samples=metrics_samples)
     lc["loss_critic"].backward()
     la["loss_actor"].backward()
     grads = {"actor." + n: p.grad.clone() for n, p in agent.actor.actor.named_parameters()}
@@ -195,30 +195,88 @@ def _fused_update(m, wm, actor_sd, critic_sd, h0, z0, lat, act, H):
     return k1, vs, g_actions, scal, grads
 
 
-@pytest.mark.parametrize("name", ["c1", "c2_long", "c2", "c2_ln"])
+def _teacher_forced_update(m, c, gold, H):
+    """K4 on the REFERENCE's own trajectory: the state images are packed from the fixture's determ / stoch, the
+    lambda-returns, weights, values and actions are the reference's — nothing depends on the rollout's draws."""
+    from rl_sandbox_b200 import ops
+    dev = "cuda"
+    N = m["N"]
+    rows = ops.round_up(N, 128)
+    z = torch.nn.functional.one_hot(gold["stoch_idx"].long(), 32).float().reshape(H + 1, N, 1024)
+    k1 = {"determ": gold["determ"].to(dev), "values": gold["values"].to(dev), "actions": gold["actions"].to(dev),
+          "determ_packed": torch.stack([ops.pack_rows(gold["determ"][t].to(dev), rows_pad=rows) for t in range(H + 1)]),
+          "stoch_packed": torch.stack([ops.pack_rows(z[t].to(dev), rows_pad=rows) for t in range(H + 1)])}
+    _, cfg = _engine_for(m, H, with_backward=False)
+    actor, critic = _modules_for(m, c["actor"], c["critic"])
+    ac = ops.ACUpdateEngine(cfg, rho=m["rho"], eta=m["entropy_scale"], metrics_samples=128)
+    ac.pack(actor.state_dict(), critic.state_dict())
+    scal = ac.update(k1, gold["vs"].to(dev), gold["w"].to(dev), actor.actor, critic.critic, seed=3, horizon=H).cpu()
+    grads = {"actor." + k: p.grad for k, p in actor.actor.named_parameters()}
+    grads |= {"critic." + k: p.grad for k, p in critic.critic.named_parameters()}
+    torch.cuda.synchronize()
+    return scal, grads
+
+
+def _parity_rollout_update(m, c, H):
+    """K4 on the states of a rollout in the split-operand mode (within ~1e-5 of the reference's trajectory)."""
+    from rl_sandbox_b200 import ops
+    dev = "cuda"
+    to = lambda sd: {k: v.to(dev) for k, v in sd.items()}
+    cfg = ops.ImagineConfig(D=m["D"], A=m["A"], discrete=True, layer_norm=m["layer_norm"],
+                            predict_discount=m["predict_discount"], H=H, parity=True)
+    eng = ops.ImaginationEngine(cfg)
+    eng.pack(to(c["wm"]), to(c["actor"]), to(c["critic"]))
+    k1 = eng.rollout(c["h0"].to(dev), c["z0"].to(dev), None, c["lat"].to(dev), c["act"].to(dev), keep_packed=True,
+                     want_stoch=False)
+    vs, w, _ = ops.lambda_return(k1["rewards"], k1["values"], k1["discounts"], m["lam"])
+    actor, critic = _modules_for(m, c["actor"], c["critic"])
+    ac = ops.ACUpdateEngine(cfg, rho=m["rho"], eta=m["entropy_scale"], metrics_samples=128)
+    ac.pack(actor.state_dict(), critic.state_dict())
+    scal = ac.update(k1, vs, w, actor.actor, critic.critic, seed=3, horizon=H).cpu()
+    grads = {"actor." + k: p.grad for k, p in actor.actor.named_parameters()}
+    grads |= {"critic." + k: p.grad for k, p in critic.critic.named_parameters()}
+    torch.cuda.synchronize()
+    return k1, scal, grads
+
+
+@pytest.mark.parametrize("name", ["c1", "c2_long", "c1_long", "c2", "c2_ln"])
 def test_fused_update_matches_reference_gradients(cuda, name):
-    """Whole fused chain vs the gradients the REFERENCE's autograd produced on the same parameters, start states and
-    noise (tests/golden: norms + 64 probed entries per tensor; d loss_actor / d a_t for the continuous cases)."""
+    """The fused update vs the gradients the REFERENCE's autograd produced on the same parameters, start states and
+    noise (tests/golden: norms + 64 probed entries per tensor; d loss_actor / d a_t for the continuous cases).
+
+    Discrete actors (rho = 1: nothing differentiates through the rollout): K4 is driven from the reference's own
+    trajectory (teacher-forced; c1_long, whose fixture stores the states of 40 of its 128 rows, from a split-operand
+    rollout that reproduces the reference's trajectory), so a draw the bf16 rollout would flip cannot make the
+    comparison vacuous.  Continuous actors: the whole chain K1 (tape) -> K2 -> K2 bwd -> K1 bwd -> K4; their fixtures
+    (6 rows x 3 steps) are reproduced draw for draw, which is asserted."""
     from oracle.gen_golden import grad_probe_indices
     from rl_sandbox_b200 import _lib
     c = load_case(name)
     m, gold = c["meta"], c["gold"]
-    H = m["H"]
-    k1, vs, g_actions, scal, grads = _fused_update(m, c["wm"], c["actor"], c["critic"], c["h0"], c["z0"], c["lat"],
-                                                   c["act"], H)
-    same = (k1["stoch_idx"].cpu() == gold["stoch_idx"]).all(-1)
-    if m["discrete"]:
-        same &= k1["actions"].argmax(-1).cpu() == gold["actions"].argmax(-1)
-    frac = same.all(0).float().mean().item()
-    print(f"[parity] {name}: trajectories with identical draws {frac:.3f}")
-    if frac < 1.0:
-        pytest.skip("bf16 flipped a categorical draw on this fixture: gradients of different trajectories are not comparable")
+    H, N = m["H"], m["N"]
+    g_actions = None
+    tol_rows = 0
+    if m["discrete"] and gold["determ"].shape[1] == N:
+        scal, grads = _teacher_forced_update(m, c, gold, H)
+    elif m["discrete"]:
+        k1, scal, grads = _parity_rollout_update(m, c, H)
+        same = ((k1["stoch_idx"].cpu() == gold["stoch_idx"]).all(-1) &
+                (k1["actions"].argmax(-1).cpu() == gold["actions"].argmax(-1))).all(0)
+        tol_rows = int((~same).sum())
+        print(f"[parity] {name}: rows of the split-operand rollout that left the reference's trajectory: {tol_rows} of {N}")
+        assert tol_rows <= 2
+    else:
+        k1, vs, g_actions, scal, grads = _fused_update(m, c["wm"], c["actor"], c["critic"], c["h0"], c["z0"], c["lat"],
+                                                       c["act"], H)
+        same = (k1["stoch_idx"].cpu() == gold["stoch_idx"]).all(-1)
+        assert bool(same.all()), f"{name}: the rollout no longer reproduces the fixture's draws: regenerate it with another seed"
     idx = _lib.AC_SCALAR_NAMES
     for k in ("loss_critic", "loss_actor", "loss_actor_dynamics_backprop", "loss_actor_entropy"):
         got, ref = scal[idx[k]].item(), gold[k].item()
         print(f"[parity] {name}.{k}: fused {got:.6f} reference {ref:.6f}")
-        # means over only H x N = 18 head outputs, each a 5-deep bf16 contraction chain (4-9e-3 per element)
-        assert abs(got - ref) <= 1e-2 * abs(ref) + 2e-4, (k, got, ref)
+        # means over H x N head outputs (18 for the small fixtures), each a 5-deep bf16 contraction chain (4-9e-3 per
+        # element); a diverged row moves a mean by at most its share
+        assert abs(got - ref) <= (1e-2 + 2.0 * tol_rows / N) * abs(ref) + 2e-4, (k, got, ref)
     if not m["discrete"]:
         ga, gref = g_actions.cpu(), gold["grad_actions"]
         rel = ((ga - gref).norm() / gref.norm()).item()
@@ -232,7 +290,7 @@ def test_fused_update_matches_reference_gradients(cuda, name):
         perr = ((probe - gold["grad_probes"][i]).norm() / gold["grad_probes"][i].norm().clamp_min(1e-12)).item()
         nerr = abs(g.norm().item() - nref) / max(nref, 1e-12)
         worst = max(worst, perr)
-        assert nerr < 3e-2 and perr < 6e-2, (n, nerr, perr)
+        assert nerr < 3e-2 + 2.0 * tol_rows / N and perr < 6e-2 + 2.0 * tol_rows / N, (n, nerr, perr)
     print(f"[parity] {name}: worst probed-gradient rel-L2 vs reference {worst:.3e}")
 
 

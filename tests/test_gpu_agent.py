@@ -4,6 +4,7 @@ from functools import partial
 import pytest
 import torch
 
+from oracle import oracle_port as orc
 from tests._golden import load_case
 
 pytestmark = pytest.mark.gpu
@@ -66,21 +67,35 @@ def test_losses_match_reference(cuda, name):
     vs = agent.critic.lambda_return(zs, rewards[:-1], ts, vs=values)
     vs2, w, adv = ops.lambda_return(rewards, values, ts, agent.critic.lambda_)
     assert torch.equal(vs, vs2)
-    losses_c, metrics_c = agent.critic.calculate_loss(zs[:-1], vs, w[:-1], target_values=values[:-1])
-    losses_a, metrics_a = agent.actor.calculate_loss(zs[:-2], vs[1:], values[:-2], w[:-2], actions[1:-1])
-    if frac == 1.0:
-        # losses are means over (H x N) rows; bf16 contraction error averages down: rtol 1e-3 of the north star
-        for k, ref in [("loss_critic", gold["loss_critic"]), ("loss_actor", gold["loss_actor"]),
-                       ("loss_actor_reinforce", gold["loss_actor_reinforce"]),
-                       ("loss_actor_dynamics_backprop", gold["loss_actor_dynamics_backprop"]),
-                       ("loss_actor_entropy", gold["loss_actor_entropy"])]:
-            got = (losses_c | losses_a)[k].float().cpu()
-            print(f"[parity] {name}.{k}: ours {got.item():.6f} reference {ref.item():.6f}")
-            torch.testing.assert_close(got, ref, rtol=5e-3, atol=2e-4, msg=lambda s: f"{name}.{k}: {s}")
-        e = ((vs.squeeze(-1).cpu() - gold["vs"]).pow(2).mean().sqrt() / gold["vs"].pow(2).mean().sqrt()).item()
-        print(f"[parity] {name}.lambda_returns rel-RMS vs reference: {e:.3e}")
-        assert e < 2e-2
-        assert torch.equal(w.squeeze(-1).cpu(), gold["w"])
+    # bf16 contractions flip a near-tie draw now and then, after which that row imagines another trajectory: every
+    # comparison runs on the rows whose draws equal the reference's over all H steps — against the oracle port re-run on
+    # exactly those rows (the port is pinned to the reference on the whole fixture, tests/test_oracle.py) and, when no row
+    # diverged, against the reference's own scalars.  The 1e-3 north-star bound is asserted in the split-operand mode
+    # (tests/test_gpu_parity_mode.py); this is the default bf16 mode, whose band DESIGN.md derives.
+    rows = same.all(0)
+    sub = rows.nonzero().flatten()
+    assert sub.numel() >= 0.4 * N, f"{name}: only {sub.numel()} of {N} rows follow the reference's draws"
+    dsub = sub.cuda()
+    pk = lambda t: t.index_select(1, dsub)
+    losses_c, metrics_c = agent.critic.calculate_loss(pk(zs[:-1]), pk(vs), pk(w[:-1]), target_values=pk(values[:-1]))
+    losses_a, metrics_a = agent.actor.calculate_loss(pk(zs[:-2]), pk(vs[1:]), pk(values[:-2]), pk(w[:-2]), pk(actions[1:-1]))
+    ref_traj = orc.imagine(c["wm"], c["actor"], c["critic"], c["h0"][sub], c["z0"][sub], H=H, A=m["A"],
+                           discrete=m["discrete"], predict_discount=m["predict_discount"],
+                           latent_uniforms=c["lat"][:, sub], action_noise=c["act"][:, sub])
+    ref = orc.ac_losses(ref_traj, c["actor"], c["critic"], lam=m["lam"], discrete=m["discrete"], rho=m["rho"],
+                        eta=m["entropy_scale"])
+    for k in ("loss_critic", "loss_actor", "loss_actor_reinforce", "loss_actor_dynamics_backprop", "loss_actor_entropy"):
+        got = float((losses_c | losses_a)[k])
+        want = float(ref[k])
+        print(f"[parity] {name}.{k} on {sub.numel()}/{N} rows: ours {got:.6f} oracle {want:.6f}")
+        # losses are means over (H x rows) terms; the reinforce term is a signed sum in which advantages cancel
+        assert abs(got - want) <= 5e-3 * abs(want) + 2e-4, (name, k, got, want)
+        if sub.numel() == N:
+            assert abs(got - gold[k].item()) <= 5e-3 * abs(gold[k].item()) + 2e-4, (name, k, got, gold[k].item())
+    e = ((pk(vs).squeeze(-1).cpu() - gold["vs"][:, sub]).pow(2).mean().sqrt() / gold["vs"][:, sub].pow(2).mean().sqrt()).item()
+    print(f"[parity] {name}.lambda_returns rel-RMS vs reference on alive rows: {e:.3e}")
+    assert e < 2e-2
+    assert torch.equal(pk(w).squeeze(-1).cpu(), gold["w"][:, sub])
 
 
 def test_train_step_end_to_end(cuda):

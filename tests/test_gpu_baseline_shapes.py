@@ -1,0 +1,140 @@
+"""Rollout and update parity AT THE BASELINE SHAPES (BASELINE.json configs[0] / configs[3]), not only on the small
+fixtures: N = 800 x H = 15 x D = 1024 (the configured 16 x 50 start states) and the benched 32 768 start states per GPU
+driven through ``DreamerV2.behaviour_update`` — CTA-pair multi-wave GEMMs, CUDA-graph replay, Philox noise from a
+device-resident key, the actor's activations handed from the rollout to the update.
+
+Start states are independent, so a slice of rows of a large run is checked against the oracle (bf16-rounded operands:
+the tensor cores' arithmetic) re-run on just those rows with the same Philox counters — seconds on the CPU.  The update's
+gradients (sums over all rows) are checked against torch fp32 autograd of the mirror modules on the identical trajectory.
+"""
+import copy
+
+import pytest
+import torch
+
+from oracle import oracle_port as orc
+from tests.test_gpu_agent import make_agent
+
+pytestmark = pytest.mark.gpu
+
+C1 = dict(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, entropy_scale=3e-3, gamma=0.999, H=15)
+
+
+def rel_rms(x, r):
+    x, r = x.double().cpu(), r.double().cpu()
+    return ((x - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+def philox_noise(seed, a, b, H, A):
+    """the uniforms rlsb_imagine_fwd draws for global start states [a, b): streams 0 (latents) and 1 (actions)"""
+    lat = torch.stack([torch.from_numpy(orc.philox_uniform(seed, a, t, 0, 1024, b - a)) for t in range(H)])
+    act = torch.stack([torch.from_numpy(orc.philox_uniform(seed, a, t, 1, A, b - a)) for t in range(H)])
+    return lat, act
+
+
+def check_slice(tag, k1, a, b, wm, actor, critic, h0, z0, seed, H, A, row_offset=0):
+    """rows [a, b) of the rollout `k1` vs the bf16-operand oracle on the same start states and Philox counters"""
+    lat, act = philox_noise(seed, row_offset + a, row_offset + b, H, A)
+    ref = orc.imagine(wm, actor, critic, h0[a:b].cpu(), z0[a:b].cpu(), H=H, A=A, discrete=True, predict_discount=True,
+                      latent_uniforms=lat, action_noise=act, bf16=True)
+    idx = k1["stoch_idx"][:, a:b].cpu().long()
+    # (1) exact: the sampler on the kernel's own logits and the regenerated uniforms
+    own = orc.sample_categorical(k1["logits"][1:, a:b].cpu().view(H, b - a, 32, 32), lat.view(H, b - a, 32, 32))
+    assert torch.equal(own, idx[1:]), f"{tag}: categorical indices differ from the oracle sampler"
+    same = (idx == ref["stoch_idx"]).all(-1) & (k1["actions"][:, a:b].cpu().argmax(-1) == ref["actions"].argmax(-1))
+    alive = same.cumprod(0).bool()
+    frac = alive[-1].float().mean().item()
+    print(f"[shape] {tag}: rows [{a}, {b}) alive after {H} steps: {frac:.3f}")
+    assert frac > 0.85, f"{tag}: {frac:.3f} of the rows follow the bf16 oracle's draws"
+    for k, lim in (("determ", 1e-3), ("logits", 2e-3), ("rewards", 1e-2), ("values", 1e-2)):
+        e = rel_rms(k1[k][:, a:b].cpu()[alive], ref[k][alive])
+        print(f"[shape] {tag}.{k}: rel-RMS vs bf16 oracle {e:.3e}")
+        assert e < lim, f"{tag}.{k}: {e:.2e}"
+    d = k1["discounts"][:, a:b].cpu()[alive]
+    assert torch.equal(torch.nan_to_num(d, nan=-1.0), torch.nan_to_num(ref["discounts"][alive], nan=-1.0))
+    return alive
+
+
+def start_states(n, D, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    h0 = 0.5 * torch.randn(n, D, device="cuda", generator=g)
+    z0 = torch.nn.functional.one_hot(torch.randint(0, 32, (n, 32), device="cuda", generator=g), 32).float().view(n, 1024)
+    return h0, z0
+
+
+def test_configured_shape_rollout_matches_oracle(cuda):
+    """N = 16 x 50 = 800 start states, H = 15, config-1 dims: the whole rollout against the oracle (all 800 rows)."""
+    from rl_sandbox_b200 import ops
+    m = C1
+    wm, actor, critic = orc.make_params(101, D=m["D"], A=m["A"], discrete=True, layer_norm=True, predict_discount=True)
+    eng = ops.ImaginationEngine(ops.ImagineConfig(D=m["D"], A=m["A"], discrete=True, layer_norm=True, predict_discount=True, H=15))
+    to = lambda sd: {k: v.cuda() for k, v in sd.items()}
+    eng.pack(to(wm), to(actor), to(critic))
+    h0, z0 = start_states(800, m["D"], 7)
+    k1 = eng.rollout(h0, z0, None, None, None, seed=1234, row_offset=0)
+    torch.cuda.synchronize()
+    check_slice("config1 N=800", k1, 0, 800, wm, actor, critic, h0, z0, 1234, 15, m["A"])
+    vs, w, adv = ops.lambda_return(k1["rewards"], k1["values"], k1["discounts"], 0.95)
+    vs_o, w_o, adv_o = orc.lambda_return_c(k1["rewards"].cpu().numpy(), k1["values"].cpu().numpy(),
+                                           k1["discounts"].cpu().numpy(), 0.95)
+    assert (vs.cpu().numpy() == vs_o).all() and (w.cpu().numpy() == w_o).all() and (adv.cpu().numpy() == adv_o).all()
+
+
+def test_benched_shape_graph_replayed_update(cuda):
+    """32 768 start states through DreamerV2.behaviour_update (what bench.py times): the second call replays the CUDA
+    graph.  A 256-row slice of its rollout vs the oracle; the update's losses and parameter gradients vs torch fp32
+    autograd of the mirror modules on the identical trajectory; the parameters move."""
+    from rl_sandbox.agents.dreamer.rssm import State
+    from rl_sandbox_b200 import _lib, ops
+    from tests.test_gpu_ac_update import _reference_grads
+    m = C1
+    N = 32768
+    torch.manual_seed(0)
+    agent = make_agent(m, "cuda")
+    wm, actor, critic = orc.make_params(102, D=m["D"], A=m["A"], discrete=True, layer_norm=True, predict_discount=True)
+    agent.world_model.load_state_dict(wm, strict=False)
+    agent.actor.load_state_dict(actor)
+    agent.critic.load_state_dict(critic)
+    agent.mark_weights_changed()
+    assert agent._can_fuse_ac() and agent.cuda_graph and N <= agent.cuda_graph_max_rows
+    h0, z0 = start_states(N, m["D"], 8)
+    init = State(h0.unsqueeze(0), torch.zeros(1, N, 32, 32, device="cuda"), z0.unsqueeze(0))
+    agent.behaviour_update(init, noise={"seed": 900})        # captures the graph (and trains one step)
+    assert len(agent._graphs) == 1
+    # the parameters the SECOND (replayed) step uses
+    sd = lambda mod: {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
+    wm_sd, actor_sd, critic_sd = sd(agent.world_model), sd(agent.actor), sd(agent.critic)
+    ref_agent_actor, ref_agent_critic = copy.deepcopy(agent.actor), copy.deepcopy(agent.critic)
+    before = [p.detach().clone() for p in agent.actor.parameters()]
+    launches0 = _lib.load().rlsb_launch_count(0)
+    losses, metrics = agent.behaviour_update(init, noise={"seed": 901})   # graph replay
+    torch.cuda.synchronize()
+    assert len(agent._graphs) == 1 and _lib.load().rlsb_launch_count(0) - launches0 > 300
+    k1 = agent.last_rollout
+    a, b = 20000, 20256          # a slice in the middle: a different CTA pair / wave than rows 0..255
+    check_slice("sweep N=32768 replay", k1, a, b, wm_sd, actor_sd, critic_sd, h0, z0, 901, 15, m["A"])
+    check_slice("sweep N=32768 replay (last rows)", k1, N - 128, N, wm_sd, actor_sd, critic_sd, h0, z0, 901, 15, m["A"])
+    # K2 + K4 on the whole batch vs torch fp32 autograd on the identical trajectory
+    vs, w, _ = ops.lambda_return(k1["rewards"], k1["values"], k1["discounts"], agent.critic.lambda_)
+
+    class Ref:   # _reference_grads reads .actor / .critic
+        pass
+    ref = Ref()
+    ref.actor, ref.critic = ref_agent_actor, ref_agent_critic
+    ref_losses, _, ref_grads = _reference_grads(ref, k1, vs, w, metrics_samples=2)
+    for k in ("loss_critic", "loss_actor_reinforce", "loss_actor_entropy", "loss_actor"):
+        got, want = float(losses[k]), float(ref_losses[k])
+        print(f"[shape] sweep {k}: fused {got:.6f} torch fp32 {want:.6f}")
+        assert abs(got - want) <= 2e-3 * abs(want) + 1e-4, (k, got, want)     # means over 491 520 rows
+    ours = {"actor." + n: p.grad for n, p in agent.actor.actor.named_parameters()}
+    ours |= {"critic." + n: p.grad for n, p in agent.critic.critic.named_parameters()}
+    worst = 0.0
+    for n, gref in ref_grads.items():
+        g = ours[n]
+        rel = ((g - gref).norm() / gref.norm().clamp_min(1e-12)).item()
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
+        worst = max(worst, rel)
+        assert rel < 3e-2 and cos > 0.999, (n, rel, cos)
+    print(f"[shape] sweep N=32768: worst parameter-gradient rel-L2 vs torch fp32 autograd {worst:.3e}")
+    assert any(not torch.equal(x, y.detach()) for x, y in zip(before, agent.actor.parameters()))
+    assert all(torch.isfinite(v).all() for v in list(losses.values()) + list(metrics.values()))

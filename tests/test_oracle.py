@@ -76,7 +76,7 @@ def test_lambda_c_oracle_is_bit_identical_to_reference_loop():
                                rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("name", ["c1", "c2", "c2_long"])
+@pytest.mark.parametrize("name", ["c1", "c2", "c2_long", "c1_long"])
 def test_oracle_port_matches_reference_rollout(name):
     """oracle_port.imagine / ac_losses vs the tensors the reference's modules produced."""
     c = load_case(name)
@@ -85,7 +85,8 @@ def test_oracle_port_matches_reference_rollout(name):
                       predict_discount=m["predict_discount"], latent_uniforms=c["lat"], action_noise=c["act"])
     assert torch.equal(out["stoch_idx"], gold["stoch_idx"].long()), "categorical indices must be bit-exact"
     for k in ("determ", "logits", "actions", "rewards", "values"):
-        torch.testing.assert_close(out[k], gold[k], rtol=1e-4, atol=2e-5, msg=lambda s: f"{k}: {s}")
+        R = gold[k].shape[1]   # the large tensors of some fixtures cover the first `store_rows` start states only
+        torch.testing.assert_close(out[k][:, :R], gold[k], rtol=1e-4, atol=2e-5, msg=lambda s: f"{k}: {s}")
     assert torch.equal(torch.nan_to_num(out["discounts"], nan=-1), torch.nan_to_num(gold["discounts"], nan=-1))
     losses = orc.ac_losses(out, c["actor"], c["critic"], lam=m["lam"], discrete=m["discrete"], rho=m["rho"],
                            eta=m["entropy_scale"])
