@@ -6,7 +6,8 @@ of synthetic start states: imagination rollout (K1) -> lambda-return / weights /
 critic + actor losses -> backward -> [gradient all-reduce] -> clip -> AdamW x2 -> target update.
 
   python bench.py --gpus N --steps K --warmup W            # the B200 arm (this repo)
-  python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+  python bench.py --impl reference --gpus N ...            # the reference's own CPU path (the unmodified reference
+                                                           # staged under oracle/_ref/; the oracle port if it is absent)
 
 Workloads (config.workload):
   sweep    configs[3] of BASELINE.json: config-1 dims (D=1024, 32x32 latents, A=17 discrete,
@@ -20,7 +21,10 @@ Workloads (config.workload):
   slotted  configs[2]: the full train() of config_slotted (slot-attention encoder, slotted RSSM, DINO-feature targets
            supplied as synthetic d_features); imagination of this config runs K1 with slots = 4 under no_grad callers,
            its (continuous-actor) training differentiates through the torch replay
-One JSON line is printed by rank 0.
+One JSON line is printed by rank 0.  Besides the contract's keys it carries `roofline`, `cpu_baseline`, and (sweep /
+config1 / dino workloads) `sweep_strong` (BASELINE configs[3]: N_total in {16 384, 65 536, 262 144} start states split
+over the launched GPUs), `torch_gpu_baseline` (the reference's eager PyTorch path on the same B200, TF32 as its
+train.py:40) and `parity_mode` (cost of the split-operand contraction mode the 1e-3 parity tests run in).
 """
 from __future__ import annotations
 
@@ -64,6 +68,9 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=None, help="start states of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--metrics-samples", type=int, default=128)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip sweep_strong / torch_gpu_baseline / parity_mode (the default line's keys are unchanged)")
+    ap.add_argument("--strong-totals", default="16384,65536,262144", help="N_total values of the strong-scaling sweep")
     return ap.parse_args()
 
 
@@ -131,26 +138,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_hot_path(dims, H, rows, steps, warmup, metrics_samples):
-    """The reference's CPU path (oracle port; the reference itself is Python and cannot travel to the
-    GPU box).  Returns (steps/s, seconds per step, threads)."""
+def reference_available() -> bool:
+    """the unmodified reference: /root/reference (build container) or the copy oracle/make_ref.py stages in oracle/_ref/"""
+    try:
+        from oracle import ref_runner
+        return ref_runner.available()
+    except Exception:
+        return False
+
+
+def cpu_hot_path(dims, H, rows, steps, warmup, metrics_samples, device="cpu"):
+    """The hot path on the host cores (or, device='cuda', the reference's eager PyTorch path on the GPU).
+    kind 'reference': the UNMODIFIED reference's modules executing agents/dreamer_v2.py:179-217 (oracle/ref_runner.py);
+    kind 'port': oracle/oracle_port.py::HotPathCPU when no copy of the reference is present (host only).
+    Returns (steps/s, seconds per step, threads, kind)."""
     from oracle import oracle_port as orc
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    hp = orc.HotPathCPU(D=dims["D"], A=dims["A"], discrete=dims["discrete"], layer_norm=dims["layer_norm"],
-                        predict_discount=dims["predict_discount"], H=H, eta=dims["eta"], lr=dims["lr"],
-                        metrics_samples=metrics_samples)
     h0, z0 = orc.make_start(1, rows, dims["D"])
-    gen = torch.Generator().manual_seed(2)
+    if reference_available():
+        from oracle import ref_runner
+        hp = ref_runner.ReferenceHotPath(D=dims["D"], A=dims["A"], discrete=dims["discrete"], layer_norm=dims["layer_norm"],
+                                         predict_discount=dims["predict_discount"], H=H, eta=dims["eta"], lr=dims["lr"],
+                                         device=device)
+        state = hp.state(h0, z0)
+        run = lambda: hp.step(state)
+        kind = "reference"
+    else:
+        if device != "cpu":
+            raise RuntimeError("torch-on-GPU baseline needs the staged reference (oracle/_ref)")
+        hp = orc.HotPathCPU(D=dims["D"], A=dims["A"], discrete=dims["discrete"], layer_norm=dims["layer_norm"],
+                            predict_discount=dims["predict_discount"], H=H, eta=dims["eta"], lr=dims["lr"],
+                            metrics_samples=metrics_samples)
+        gen = torch.Generator().manual_seed(2)
+        run = lambda: hp.step(h0, z0, gen)
+        kind = "port"
+    sync = (lambda: torch.cuda.synchronize()) if device != "cpu" else (lambda: None)
     for _ in range(warmup):
-        hp.step(h0, z0, gen)
+        run()
     ts = []
     for _ in range(steps):
+        sync()
         t0 = time.perf_counter()
-        hp.step(h0, z0, gen)
+        run()            # ends with the host read of every loss / metric (dreamer_v2.py:216-217)
+        sync()
         ts.append(time.perf_counter() - t0)
     sec = statistics.median(ts)
-    return rows * H / sec, sec, threads
+    return rows * H / sec, sec, threads, kind
 
 
 def workload_name(args, dims, rows):
@@ -165,13 +199,21 @@ def reference_arm(args, dims):
     if rank != 0:
         return
     rows = args.cpu_rows or 256
-    val, sec, threads = cpu_hot_path(dims, args.horizon, rows, args.steps, max(1, min(args.warmup, 2)),
-                                     args.metrics_samples)
+    val, sec, threads, kind = cpu_hot_path(dims, args.horizon, rows, args.steps, max(1, min(args.warmup, 2)),
+                                           args.metrics_samples)
+    # the same path at 8x the rows: steps/s of the host path must be (about) flat in the number of start states for the
+    # bounded sample to stand for the b200 arm's workload
+    rows_big = 8 * rows
+    val_big, sec_big, _, _ = cpu_hot_path(dims, args.horizon, rows_big, min(args.steps, 2), 1, args.metrics_samples)
     cpu_model = "unknown"
     try:
         cpu_model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
     except Exception:
         pass
+    note = ("the UNMODIFIED reference (Midren/rl_sandbox) executing agents/dreamer_v2.py:179-217 through oracle/ref_runner.py "
+            "(imagine_trajectory + lambda_return + calculate_loss x2 + Optimizer.step x2 + update_target + host read)"
+            if kind == "reference" else
+            "reference's PyTorch-CPU hot path restated in oracle/oracle_port.py (HotPathCPU); no copy of the reference present")
     line = {
         "impl": "reference", "metric": "imagined_rssm_steps_per_sec", "value": val, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -179,11 +221,11 @@ def reference_arm(args, dims):
         # the b200 arm's workload (same dims, same hot path); each timed step is a bounded sample of it
         "config": {"workload": workload_name(args, dims, args.rows or (32768 if args.workload == "sweep" else 800)),
                    "sample": f"bounded sample: {rows} start states x H={args.horizon} per step on the host cores",
-                   "impl_note": "reference's PyTorch-CPU hot path restated in oracle/oracle_port.py "
-                                "(HotPathCPU: imagine + lambda-return + AC losses + backward + AdamW); "
-                                "the reference is pure Python and is not present on the GPU box"},
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{rows} start states x H={args.horizon}, median of {args.steps} steps", "cpu": cpu_model},
+                   "impl_note": note},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": kind,
+                         "sample": f"{rows} start states x H={args.horizon}, median of {args.steps} steps", "cpu": cpu_model,
+                         "flatness": {"rows": rows_big, "value": val_big, "ms_per_step": sec_big * 1e3,
+                                      "note": f"same path at {rows_big} start states: steps/s vs the {rows}-row sample"}},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -349,7 +391,8 @@ def main():
         noise = {"seed": 1000 + it, "row_offset": rank * N}
         if is_train:
             losses, metrics = agent.behaviour_update(state, noise=noise)
-            return losses["loss_actor"] + losses["loss_critic"]
+            # every loss and metric the reference's train() hands to the host (dreamer_v2.py:216-217)
+            return torch.stack([v.reshape(-1)[0].float() for v in list(losses.values()) + list(metrics.values())])
         with torch.no_grad():
             states, actions, rewards, discounts = agent.imagine_trajectory(state, noise=noise)
             vs, w, adv = ops.lambda_return(rewards, agent.last_rollout["values"].unsqueeze(-1), discounts, 0.95)
@@ -444,6 +487,11 @@ def main():
     h2d = h_host.numel() * 4 + i_host.numel()
     d2h = res_host.numel() * 4
 
+    # ---- extras: every rank takes part in the strong sweep (its all-reduce is collective); the rest is rank 0's ------
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, dims, agent, world, rank, device, H, N, k1_ms, barrier, make_state)
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel: the GRU contraction (tcgen05 GEMM, EPI_STATS) ------
@@ -484,14 +532,17 @@ def main():
                     "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)",
                     "frac_of_sustained": achieved / pk["tf_sus"], "peak_sustained": pk["tf_sus"],
                     "ms_per_launch": gemm_ms, "traffic": traffic,
-                    "algorithmic_bytes": N * (2 * D * 2 + 3 * D * 4) + 3 * D * 2 * D * 2,
+                    # the GRU CELL's bytes (common.py:69-81): x, h in (bf16) + h' out (fp32 + packed bf16) + the weights;
+                    # the contraction as executed also writes its fp32 pre-activations + statistics for the gate kernel
+                    "algorithmic_bytes": N * (2 * D * 2 + D * 4 + D * 2) + 3 * D * 2 * D * 2,
+                    "executed_bytes_unfused": N * (2 * D * 2 + 3 * D * 4) + 3 * D * 2 * D * 2,
                     "whole_rollout": {"tflops": k1_tflops, "frac": k1_tflops / pk["tf_sus"], "ms": k1_ms,
                                       "note": "reference-equivalent FLOPs of all layers / K1 time, vs sustained bf16"}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rows = args.cpu_rows or 256
-            v, sec, threads = cpu_hot_path(dims, H, rows, 3, 1, args.metrics_samples)
-            cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+            v, sec, threads, kind = cpu_hot_path(dims, H, rows, 3, 1, args.metrics_samples)
+            cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": kind,
                    "sample": f"{rows} start states x H={H} (same dims, same hot path), median of 3 steps, {sec:.2f} s/step"}
         line = {
             "metric": "imagined_rssm_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world,
@@ -513,10 +564,104 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_extras(args, dims, agent, world, rank, device, H, N, k1_ms, barrier, make_state):
+    """sweep_strong / torch_gpu_baseline / parity_mode — measured after the headline numbers, never inside their timed
+    regions.  Failures are reported as strings: an extra must not take the default line down."""
+    import torch.distributed as dist
+    from rl_sandbox_b200 import ops
+    out = {}
+    D = dims["D"]
+
+    # ---- strong scaling (BASELINE configs[3]): N_total start states split into contiguous shards of N_total / G ------
+    try:
+        totals = [int(x) for x in args.strong_totals.split(",") if x]
+        rows_list = []
+        for n_total in totals:
+            rows = n_total // world
+            if rows < 128 or rows * world != n_total:
+                rows_list.append(None)
+                continue
+            rows_list.append(rows)
+        strong = []
+        agent.max_rows_per_pass = 65536            # bounded HBM footprint for the 262 144-row point on one GPU
+        for n_total, rows in zip(totals, rows_list):
+            if rows is None:
+                strong.append({"n_total": n_total, "skipped": "not divisible into shards of >= 128 rows"})
+                continue
+            g = torch.Generator(device=device).manual_seed(77 + rank)
+            h = 0.5 * torch.randn(rows, D, device=device, generator=g)
+            z = torch.nn.functional.one_hot(torch.randint(0, 32, (rows, 32), device=device, generator=g), 32).float().view(rows, 1024)
+            st = type(make_state(h[:1], z[:1]))(h.unsqueeze(0), torch.zeros(1, rows, 32, 32, device=device), z.unsqueeze(0))
+            steps = 3
+            for i in range(2):
+                agent.behaviour_update(st, noise={"seed": 7000 + i, "row_offset": rank * rows})
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for i, (e0, e1) in enumerate(evs):
+                e0.record()
+                agent.behaviour_update(st, noise={"seed": 7100 + i, "row_offset": rank * rows})
+                e1.record()
+            barrier()
+            ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs) / steps], device=device)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            strong.append({"n_total": n_total, "rows_per_gpu": rows, "ms_per_step": ms.item(),
+                           "steps_per_sec": n_total * H / (ms.item() * 1e-3)})
+            del st, h, z
+        out["sweep_strong"] = {"n_gpus": world, "points": strong,
+                               "note": "same step as `value`; total start states fixed, contiguous shards of N_total / n_gpus; "
+                                       "efficiency = steps_per_sec(G) / (G x steps_per_sec(1)) across runs of this bench"}
+    except Exception as exc:   # noqa: BLE001
+        out["sweep_strong"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if rank != 0:
+        return out
+
+    # ---- cost of the split-operand ("bf16 x 3") contraction mode the 1e-3 parity tests run in (K1 only) --------------
+    try:
+        cfg = ops.ImagineConfig(D=D, A=dims["A"], discrete=dims["discrete"], layer_norm=dims["layer_norm"],
+                                predict_discount=dims["predict_discount"], H=H, parity=True)
+        eng = ops.ImaginationEngine(cfg, device=device)
+        eng.pack(agent.world_model.state_dict(), agent.actor.state_dict(), agent.critic.state_dict())
+        g = torch.Generator(device=device).manual_seed(5)
+        h = 0.5 * torch.randn(N, D, device=device, generator=g)
+        z = torch.nn.functional.one_hot(torch.randint(0, 32, (N, 32), device=device, generator=g), 32).float().view(N, 1024)
+        res = eng.rollout(h, z, None, None, None, seed=1, want_stoch=False)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for i, (e0, e1) in enumerate(evs):
+            e0.record()
+            eng.rollout(h, z, None, None, None, seed=2 + i, want_stoch=False, out=res)
+            e1.record()
+        torch.cuda.synchronize()
+        pm = statistics.median(e0.elapsed_time(e1) for e0, e1 in evs)
+        out["parity_mode"] = {"k1_ms": pm, "k1_fast_ms": k1_ms, "cost_ratio": pm / k1_ms,
+                              "note": "imagination rollout with every contraction as hi.Whi + hi.Wlo + lo.Whi (fp32-grade: "
+                                      "<= 2e-5 of the reference on the golden fixtures, tests/test_gpu_parity_mode.py)"}
+        del eng, res, h, z
+    except Exception as exc:   # noqa: BLE001
+        out["parity_mode"] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- the reference's eager PyTorch path on this B200 (TF32 allowed, reference train.py:40) -----------------------
+    try:
+        if reference_available():
+            torch.cuda.empty_cache()
+            rows = min(N, 32768)
+            v, sec, _, kind = cpu_hot_path(dims, H, rows, 3, 1, args.metrics_samples, device=device)
+            out["torch_gpu_baseline"] = {"value": v, "unit": "steps/s", "ms_per_step": sec * 1e3, "rows": rows, "kind": kind,
+                                         "note": "the unmodified reference's modules (oracle/ref_runner.py) on cuda: eager PyTorch, "
+                                                 "TF32 matmuls, host read of the losses every step"}
+        else:
+            out["torch_gpu_baseline"] = {"unavailable": "no staged copy of the reference (oracle/_ref) on this box"}
+    except Exception as exc:   # noqa: BLE001
+        out["torch_gpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
+    return out
 
 
 if __name__ == "__main__":

@@ -23,7 +23,21 @@ import torch
 import torch.distributions as td
 
 _HERE = Path(__file__).resolve().parent
-REFERENCE_ROOT = Path(os.environ.get("RLSB_REFERENCE_ROOT", "/root/reference"))
+
+
+def _find_reference() -> Path:
+    """RLSB_REFERENCE_ROOT, else the read-only checkout of the build container, else the copy oracle/make_ref.py
+    stages under oracle/_ref/ (git-ignored; what the GPU box has)."""
+    env = os.environ.get("RLSB_REFERENCE_ROOT")
+    if env:
+        return Path(env)
+    for cand in (Path("/root/reference"), _HERE / "_ref"):
+        if (cand / "rl_sandbox" / "agents" / "dreamer_v2.py").exists():
+            return cand
+    return Path("/root/reference")
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def available() -> bool:
@@ -103,7 +117,7 @@ def injected_noise(queue: NoiseQueue):
 
 
 def build_agent(*, D, A, discrete, layer_norm, predict_discount, H=15, entropy_scale=1e-5, lam=0.95,
-                gamma=0.99, lr=1e-4, batch_cluster_size=50, clip_rewards="identity"):
+                gamma=0.99, lr=1e-4, batch_cluster_size=50, clip_rewards="identity", device_type="cpu"):
     """The reference DreamerV2 with the kwargs of config/agent/dreamer_v2*.yaml."""
     ref = _import_reference()
     from rl_sandbox.agents.dreamer.world_model import WorldModel
@@ -121,7 +135,7 @@ def build_agent(*, D, A, discrete, layer_norm, predict_discount, H=15, entropy_s
                           world_model=wm, actor=actor, critic=critic,
                           action_type="discrete" if discrete else "continuous", imagination_horizon=H,
                           wm_optim=opt, actor_optim=opt, critic_optim=opt, layer_norm=layer_norm,
-                          batch_cluster_size=batch_cluster_size, f16_precision=False, device_type="cpu")
+                          batch_cluster_size=batch_cluster_size, f16_precision=False, device_type=device_type)
     return agent
 
 

@@ -89,6 +89,7 @@ class DreamerV2(RlAgent):
         self._wm_graphs: dict = {}
         self._wm_sched_prev = None
         self._graphs: dict = {}
+        self._ac_bucket = None       # GradBucket over actor + critic: their .grad are views of one flat fp32 buffer
         self._weights_version = 0    # bumped whenever parameters change
         self._packed_version = -1
         self._noise_seed = 0x5EED    # Philox key; the step counter below is mixed in per rollout
@@ -434,6 +435,13 @@ class DreamerV2(RlAgent):
         noise = dict(noise or {})
         n_rows = initial_states.determ.shape[1]
         explicit = 'latent_uniforms' in noise or 'action_noise' in noise
+        # K4 writes both networks' gradients into views of ONE flat buffer (stable addresses for the captured graph);
+        # data-parallel: a single all-reduce of that buffer after both backward passes, before either clip
+        if self._ac_bucket is None:
+            from rl_sandbox_b200.utils.optimizer import GradBucket
+            self._ac_bucket = GradBucket(list(self.actor.actor.parameters()) + list(self.critic.critic.parameters()))
+        elif not self._ac_bucket.attached():
+            self._ac_bucket.attach()
         if self.cuda_graph and not explicit and n_rows <= self.cuda_graph_max_rows:
             scal = self._fused_step_graphed(initial_states, noise)
         elif n_rows > self.max_rows_per_pass and not explicit:
@@ -442,8 +450,9 @@ class DreamerV2(RlAgent):
         else:
             with torch.no_grad():
                 scal = self._fused_step(initial_states, noise)
-        metrics_a = self.actor_optimizer.step_with_grads()
-        metrics_c = self.critic_optimizer.step_with_grads()
+        reduced = self._ac_bucket.all_reduce()
+        metrics_a = self.actor_optimizer.step_with_grads(reduced=reduced)
+        metrics_c = self.critic_optimizer.step_with_grads(reduced=reduced)
         self.critic.update_target()
         self.mark_weights_changed()
         idx = _lib.AC_SCALAR_NAMES

@@ -40,6 +40,52 @@ def allreduce_grads_(params: t.Iterable[torch.Tensor]) -> None:
         off += n
 
 
+class GradBucket:
+    """One persistent flat fp32 buffer holding the gradients of several modules, each ``p.grad`` a VIEW into it
+    ("one ncclAllReduce(sum) over a flat fp32 bucket of actor+critic grads").
+
+    rlsb_ac_update writes the actor's and the critic's gradients straight into these views (ops._mlp_grads hands the
+    kernels ``p.grad.data_ptr()``), so the data-parallel step is a single all-reduce of ``flat`` — no torch.cat, no
+    copy-back — issued after both backward passes and before either ``clip_grad_norm_``.  The views are stable
+    addresses, which is what a captured CUDA graph of the update needs."""
+
+    def __init__(self, params: t.Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucket needs at least one trainable parameter")
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        self.attach()
+
+    def attach(self) -> None:
+        """(Re-)install the views as ``.grad``; a gradient somebody else put there meanwhile is copied in first."""
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+            p.grad = v
+
+    def attached(self) -> bool:
+        return all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(self.params, self.views))
+
+    def all_reduce(self) -> bool:
+        """Average the bucket over the ranks with ONE collective; returns False when there is nothing to do (no
+        process group / a single rank)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return False
+        if not self.attached():
+            self.attach()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.flat.div_(dist.get_world_size())
+        return True
+
+
 class Optimizer:
     def __init__(self, model, lr=1e-4, eps=1e-8, weight_decay=0.01,
                  lr_scheduler: t.Optional[t.Type[LRScheduler] | t.Iterable[t.Type[LRScheduler]]] = None,
@@ -63,14 +109,16 @@ class Optimizer:
             self.scaler.unscale_(self.optimizer)
         return self._apply()
 
-    def step_with_grads(self):
+    def step_with_grads(self, reduced: bool = False):
         """Same as ``step`` from the all-reduce on, for gradients a kernel already wrote into ``.grad``
-        (rlsb_ac_update replaces zero_grad + loss.backward(), optimizer.py:55-57)."""
-        return self._apply()
+        (rlsb_ac_update replaces zero_grad + loss.backward(), optimizer.py:55-57).  ``reduced``: the caller has
+        already averaged the gradients over the ranks (GradBucket.all_reduce)."""
+        return self._apply(reduced)
 
-    def _apply(self):
+    def _apply(self, reduced: bool = False):
         metrics = {}
-        allreduce_grads_(self.model.parameters())
+        if not reduced:
+            allreduce_grads_(self.model.parameters())
         if self.log_grad:
             for tag, value in self.model.named_parameters():
                 metrics[f"grad/{tag.replace('.', '/')}"] = value.detach()

@@ -60,6 +60,8 @@ def test_losses_match_reference(cuda, name):
     same = (idx == gold["stoch_idx"].long()).all(-1)
     if m["discrete"]:
         same &= actions.argmax(-1).cpu() == gold["actions"].argmax(-1)
+    # a discount is a Bernoulli MODE (0 / 1): a head output within the bf16 band of 0 flips it, and with it the weights
+    same &= torch.nan_to_num(ts.squeeze(-1).cpu(), nan=-1.0) == torch.nan_to_num(gold["discounts"], nan=-1.0)
     frac = same.all(0).float().mean().item()
     print(f"[parity] {name}: trajectories with identical draws over all {H} steps: {frac:.3f}")
     zs = states.combined
