@@ -142,6 +142,10 @@ typedef struct {
    * reference's fp32 path (north star: rtol 1e-3) at 3x the tensor work.  The verification mode of the parity tests;
    * flat RSSM, forward only (no tape, no actor_slots).  The packed blob depends on it: pack with the same cfg. */
   int32_t parity;
+  /* 1: at step H evaluate the target-critic head only — values[H] is the bootstrap of the lambda-return, while
+   * rewards[H] / discounts[H] are never read by the update (ac.py:57-58, dreamer_v2.py:192-197) and are written as 0 / 1.
+   * For the training path; imagine_trajectory's public result keeps the reference's rewards[H] (flag 0). */
+  int32_t last_step_value_only;
 } rlsb_imagine_cfg;
 
 /* fp32 parameters in nn.Linear layout (weight = [out, in] row-major); NULL = absent.

@@ -24,7 +24,7 @@ class ImagineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "predict_discount",
         "with_critic", "H", "discount_nan_on_tie", "with_backward", "slots", "attention_blocks",
-        "symmetric_qk")] + [("mixer_coeff", C.c_float), ("parity", C.c_int32)]
+        "symmetric_qk")] + [("mixer_coeff", C.c_float), ("parity", C.c_int32), ("last_step_value_only", C.c_int32)]
 
 
 class MlpParams(C.Structure):

@@ -152,8 +152,8 @@ class DreamerV2(RlAgent):
 
     def imagine_trajectory(self, init_state: State, precomp_actions: t.Optional[list[Action]] = None,
                            horizon: t.Optional[int] = None, noise: t.Optional[dict] = None,
-                           keep_packed: bool = False, tape: bool = False, actor_slots=None
-                           ) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
+                           keep_packed: bool = False, tape: bool = False, actor_slots=None,
+                           last_step_value_only: bool = False) -> tuple[State, torch.Tensor, torch.Tensor, torch.Tensor]:
         """H-step closed-loop rollout from (1, N, .) start states (dreamer_v2.py:68-96).
 
         ``noise`` (extension, optional): {'latent_uniforms': (H,N,1024), 'action_noise': (H,N,A)} to
@@ -186,7 +186,8 @@ class DreamerV2(RlAgent):
         out = eng.rollout(h0, z0, logits0, latent_uniforms=noise.get('latent_uniforms'),
                           action_noise=noise.get('action_noise'), seed=noise.get('seed', 0),
                           row_offset=noise.get('row_offset', 0), precomp_actions=pre, horizon=horizon,
-                          keep_packed=keep_packed, want_stoch=not keep_packed, tape=tape, actor_slots=actor_slots)
+                          keep_packed=keep_packed, want_stoch=not keep_packed, tape=tape, actor_slots=actor_slots,
+                          last_step_value_only=last_step_value_only)
         self.last_rollout = out
         wm = self.world_model
         if slotted:
@@ -507,7 +508,9 @@ class DreamerV2(RlAgent):
         if static is None:
             ac = self._get_ac_engine()
             slots = ac.actor_slots(initial_states.determ.shape[1], self.imagination_horizon) if reuse else None
-            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True, tape=dyn, actor_slots=slots)
+            # (the update reads rewards / discounts of steps 0..H-1 only: step H evaluates the target critic alone)
+            self.imagine_trajectory(initial_states, noise=noise, keep_packed=True, tape=dyn, actor_slots=slots,
+                                    last_step_value_only=not dyn)
             k1 = self.last_rollout
         else:   # graph body: always re-pack (the parameters change between replays), static buffers, device-resident key
             eng, ac = static['eng'], static['ac']
@@ -517,7 +520,7 @@ class DreamerV2(RlAgent):
             slots = ac.actor_slots(static['h0'].shape[0], self.imagination_horizon, pin=pin) if reuse else None
             k1 = eng.rollout(static['h0'], static['z0'], static['logits0'], seed_device=seed_device,
                              row_offset=noise.get('row_offset', 0), keep_packed=True, tape=dyn, want_stoch=False,
-                             out=static.get('out'), actor_slots=slots, pin=pin)
+                             out=static.get('out'), actor_slots=slots, pin=pin, last_step_value_only=not dyn)
             static['out'] = k1
             self.last_rollout = k1
         H, n = k1['determ'].shape[0] - 1, k1['determ'].shape[1]

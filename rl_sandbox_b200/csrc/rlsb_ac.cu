@@ -290,37 +290,55 @@ __global__ void __launch_bounds__(128) ac_loss_kernel(const AcLossArgs a) {
         acc[ACC_REINFORCE] = -a.rho * logp_a * wt * adv;
         acc[ACC_ENTROPY] = -a.eta * ent * wt;
         const float inv_cnt = 1.0f / (static_cast<float>(a.H - 1) * static_cast<float>(a.N));
+        // cumulative probabilities in registers: every loop over the classes below is fully unrolled over 32 with a
+        // uniform (k < A) guard, so no array is indexed dynamically (no local memory)
         float cdf[32];
         float run = 0.f;
-        for (int k = 0; k < a.A; ++k) {
-          const float lp = lg[k] - lse;
-          const float pk = expf(lp);
-          dya[k] = (-a.rho * wt * adv * ((k == a_idx ? 1.0f : 0.f) - pk) + a.eta * wt * pk * (lp + ent)) * inv_cnt;
-          run += pk;
-          cdf[k] = run;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          cdf[k] = 3.0e38f;
+          if (k < a.A) {
+            const float lp = lg[k] - lse;
+            const float pk = expf(lp);
+            dya[k] = (-a.rho * wt * adv * ((k == a_idx ? 1.0f : 0.f) - pk) + a.eta * wt * pk * (lp + ent)) * inv_cnt;
+            run += pk;
+            cdf[k] = run;
+          }
         }
         acc[ACC_MEAN_VAL] = run;   // sum_k p_k (dist.mean summed over the action axis)
         // ---- statistics of `metrics_samples` draws per element (ac.py:137-143): the empirical class
-        //      frequencies f_k decide avg_val (= sum f_k / A) and avg_sd (= mean sqrt(f_k (1 - f_k)))
+        //      frequencies f_k decide avg_val (= sum f_k / A) and avg_sd (= mean sqrt(f_k (1 - f_k))).
+        //      A draw u falls into class k iff cdf[k-1] <= u < cdf[k] (the last class takes the rest), so the class
+        //      counts are differences of the cumulative counts below[k] = #{u < cdf[k]} — branch-free compare-and-add.
         if (a.metrics_samples > 0) {
-          int cnt[32];
-          for (int k = 0; k < a.A; ++k) cnt[k] = 0;
+          int below[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) below[k] = 0;
           for (int sidx = 0; sidx < a.metrics_samples; sidx += 4) {
             uint32_t o[4];
             rlsb_philox4x32(static_cast<uint32_t>(m), static_cast<uint32_t>(m >> 32), 7u, static_cast<uint32_t>(sidx >> 2),
                             static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), o);
-            for (int j = 0; j < 4 && sidx + j < a.metrics_samples; ++j) {
-              const float u = rlsb_u32_to_uniform(o[j]) * run;
-              int k = 0;
-              while (k < a.A - 1 && u >= cdf[k]) ++k;
-              ++cnt[k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (sidx + j < a.metrics_samples) {
+                const float u = rlsb_u32_to_uniform(o[j]) * run;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                  if (k < a.A - 1) below[k] += (u < cdf[k]) ? 1 : 0;
+              }
             }
           }
           float sd = 0.f;
           const float inv_s = 1.0f / static_cast<float>(a.metrics_samples);
-          for (int k = 0; k < a.A; ++k) {
-            const float f = static_cast<float>(cnt[k]) * inv_s;
-            sd += sqrtf(f * (1.0f - f));
+          int prev = 0;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            if (k < a.A) {
+              const int upto = (k < a.A - 1) ? below[k] : a.metrics_samples;
+              const float f = static_cast<float>(upto - prev) * inv_s;
+              prev = upto;
+              sd += sqrtf(f * (1.0f - f));
+            }
           }
           acc[ACC_AVG_SD] = sd;
         }

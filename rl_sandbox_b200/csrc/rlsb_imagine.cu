@@ -362,9 +362,20 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     const __nv_bfloat16* hb = himg(t);
     const __nv_bfloat16* zb = zimg(t);
     // ---- heads on s_t = cat[h_t, z_t]: actor, reward, discount, target critic -------------------
+    // Training callers (cfg.last_step_value_only) read rows 0..H-1 of rewards / discounts (ac.py:57-58,
+    // dreamer_v2.py:192-197) and only the bootstrap value of state H: at t == H the target-critic group runs alone
+    // (a quarter of that step's head work); rewards[H] := 0, discounts[H] := 1.
+    const bool crit_only = cfg->last_step_value_only != 0 && t == H && !tape && K == 1 && P.g_critic >= 0;
+    const int g0 = crit_only ? P.g_critic : 0;
     for (int l = 0; l < 5; ++l) {
       const LayerPlan& L = P.head[l];
       GemmParams g = base_gemm(L, false);
+      if (crit_only) {   // group g0 only: every per-group base pointer moves to that group's slot
+        g.G = 1;
+        g.W = wbf(L) + static_cast<size_t>(g0) * L.NB * L.RB * L.kp;
+        g.bias = pf(L.bias_off) + static_cast<size_t>(g0) * L.NB * L.RB;
+      }
+      const size_t hid_g0 = static_cast<size_t>(g0) * m_pad * P.Hp;
       if (l == 0 && K > 1) {
         // slotted State.combined (rssm_slots_attention.py:33-43): cat over slots of [h_k, z_k]; the (n, slot)-ordered
         // images are first gathered into one operand plane per slot (pos_enc is folded into the bias)
@@ -383,15 +394,16 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
         g.A[1] = zb; g.a_ktiles[1] = P.Sp / 64; g.a_group_stride[1] = 0;
       } else {
         g.n_seg = 1;
-        g.A[0] = bf(W.hid[(l - 1) & 1]); g.a_ktiles[0] = P.Hp / 64;
+        g.A[0] = bf(W.hid[(l - 1) & 1]) + hid_g0; g.a_ktiles[0] = P.Hp / 64;
         g.a_group_stride[0] = static_cast<long long>(m_pad) * P.Hp;
       }
       if (l < 4) {
         const bool has_ln = (l == 0) || ln;
-        g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
-        g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
+        const size_t ln_g0 = static_cast<size_t>(g0) * ru(L.N, 32);
+        g.ln_gamma = has_ln ? pf(L.g_off) + ln_g0 : nullptr;
+        g.ln_beta = has_ln ? pf(L.b_off) + ln_g0 : nullptr;
         g.act = ACT_ELU;
-        g.out_bf16 = bf(W.hid[l & 1]); g.out_kpad = P.Hp;
+        g.out_bf16 = bf(W.hid[l & 1]) + hid_g0; g.out_kpad = P.Hp;
         g.out_bf16_group_stride = static_cast<long long>(m_pad) * P.Hp;
         if (tape) {
           g.save_pre = reinterpret_cast<__nv_bfloat16*>(tp(t, TP.head_pre[l]));
@@ -406,7 +418,8 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
         }
         RLSB_TRY(launch_gemm(g, EPI_LN_ACT, s));
       } else {
-        g.out_f32 = head_out; g.ldo = 32; g.out_group_stride = static_cast<long long>(m_pad) * 32;
+        g.out_f32 = head_out + static_cast<size_t>(g0) * m_pad * 32; g.ldo = 32;
+        g.out_group_stride = static_cast<long long>(m_pad) * 32;
         if (slots && t < H) {
           g.alt_group_p1 = P.g_actor + 1;
           g.alt_A = slot_img(slots->x, 3, t);
@@ -417,6 +430,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     HeadFinishParams hf{};
     hf.head_out = head_out; hf.ldo = 32; hf.group_stride = static_cast<long long>(m_pad) * 32;
     hf.g_actor = P.g_actor; hf.g_reward = P.g_reward; hf.g_discount = P.g_discount; hf.g_critic = P.g_critic;
+    if (crit_only) hf.g_actor = hf.g_reward = hf.g_discount = -1;   // not evaluated: reward := 0, discount := 1
     hf.M = M; hf.m_pad = m_pad; hf.A = P.A; hf.discrete = cfg->discrete;
     hf.first_step = (t == 0); hf.want_action = (t < H); hf.nan_on_tie = cfg->discount_nan_on_tie;
     hf.noise.explicit_noise = noise->action_noise ? noise->action_noise + static_cast<size_t>(t) * N * P.A : nullptr;

