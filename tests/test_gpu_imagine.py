@@ -221,6 +221,6 @@ def test_last_step_value_only_matches_full_rollout(ops, cuda):
     for k in ("rewards", "discounts"):
         assert torch.equal(lean[k][:H], full[k][:H]), k
     assert not lean["rewards"][H].any() and bool((lean["discounts"][H] == 1).all())
-    a, b = ops.lambda_return(lean["rewards"], lean["values"], lean["discounts"], 0.95), \\
-        ops.lambda_return(full["rewards"], full["values"], full["discounts"], 0.95)
+    a = ops.lambda_return(lean["rewards"], lean["values"], lean["discounts"], 0.95)
+    b = ops.lambda_return(full["rewards"], full["values"], full["discounts"], 0.95)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
