@@ -96,6 +96,7 @@ class Optimizer:
         # 20 us each — 10 % of the step at the configured 800 start states); same update rule, same state_dict layout
         fused = bool(params) and all(p.is_cuda and p.dtype == torch.float32 for p in params)
         self.optimizer = torch.optim.AdamW(params, lr=lr, eps=eps, weight_decay=weight_decay, **({"fused": True} if fused else {}))
+        self._fused = fused
         if isinstance(lr_scheduler, Iterable):
             lr_scheduler = torch.optim.lr_scheduler.ChainedScheduler(
                 [make(optimizer=self.optimizer) for make in lr_scheduler])
@@ -128,6 +129,13 @@ class Optimizer:
                 metrics[f"grad/{tag.replace('.', '/')}"] = value.detach()
         if self.clip:
             nn.utils.clip_grad_norm_(self.model.parameters(), self.clip)
+        if self._fused:
+            # the fused kernel wants every gradient in its parameter's dtype and strides (autograd hands conv-weight
+            # gradients back in whatever memory format cuDNN chose; the optimizer state follows the parameter)
+            for p in self.model.parameters():
+                g = p.grad
+                if g is not None and (g.stride() != p.stride() or g.dtype != p.dtype):
+                    p.grad = torch.empty_like(p).copy_(g)
         if self.scaler:
             self.scaler.step(self.optimizer)
             self.scaler.update()

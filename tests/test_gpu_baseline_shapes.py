@@ -32,8 +32,10 @@ def philox_noise(seed, a, b, H, A):
     return lat, act
 
 
-def check_slice(tag, k1, a, b, wm, actor, critic, h0, z0, seed, H, A, row_offset=0):
-    """rows [a, b) of the rollout `k1` vs the bf16-operand oracle on the same start states and Philox counters"""
+def check_slice(tag, k1, a, b, wm, actor, critic, h0, z0, seed, H, A, row_offset=0, training=False):
+    """rows [a, b) of the rollout `k1` vs the bf16-operand oracle on the same start states and Philox counters.
+    ``training``: the rollout came from ``behaviour_update``, which evaluates only the target critic on state H
+    (rlsb_imagine_cfg::last_step_value_only: rewards[H] := 0, discounts[H] := 1 — neither is read by the update)."""
     lat, act = philox_noise(seed, row_offset + a, row_offset + b, H, A)
     ref = orc.imagine(wm, actor, critic, h0[a:b].cpu(), z0[a:b].cpu(), H=H, A=A, discrete=True, predict_discount=True,
                       latent_uniforms=lat, action_noise=act, bf16=True)
@@ -54,10 +56,16 @@ def check_slice(tag, k1, a, b, wm, actor, critic, h0, z0, seed, H, A, row_offset
     # 13-16 % of the rows over the horizon (measured: 0.87 / 0.84).  What must hold always is (1) above.
     assert frac > 0.7, f"{tag}: {frac:.3f} of the rows follow the bf16 oracle's draws"
     for k, lim in (("determ", 1e-3), ("logits", 2e-3), ("rewards", 1e-2), ("values", 1e-2)):
-        e = rel_rms(k1[k][:, a:b].cpu()[alive], ref[k][alive])
+        rows = slice(0, H) if (training and k == "rewards") else slice(None)
+        e = rel_rms(k1[k][rows, a:b].cpu()[alive[rows]], ref[k][rows][alive[rows]])
         print(f"[shape] {tag}.{k}: rel-RMS vs bf16 oracle {e:.3e}")
         assert e < lim, f"{tag}.{k}: {e:.2e}"
-    flips = (d_ours[alive] != d_ref[alive]).float().mean().item()
+    if training:
+        assert not k1["rewards"][H, a:b].any() and bool((k1["discounts"][H, a:b] == 1).all())
+        d_ours, d_ref, alive_d = d_ours[:H], d_ref[:H], alive[:H]
+    else:
+        alive_d = alive
+    flips = (d_ours[alive_d] != d_ref[alive_d]).float().mean().item()
     print(f"[shape] {tag}: discount modes that differ from the bf16 oracle's on alive rows: {flips:.2e}")
     assert flips < 5e-3, f"{tag}: {flips:.2e} of the discount modes differ"
     return alive
@@ -120,8 +128,8 @@ def test_benched_shape_graph_replayed_update(cuda):
     assert len(agent._graphs) == 1 and _lib.load().rlsb_launch_count(0) - launches0 > 150
     k1 = agent.last_rollout
     a, b = 20000, 20256          # a slice in the middle: a different CTA pair / wave than rows 0..255
-    check_slice("sweep N=32768 replay", k1, a, b, wm_sd, actor_sd, critic_sd, h0, z0, 901, 15, m["A"])
-    check_slice("sweep N=32768 replay (last rows)", k1, N - 128, N, wm_sd, actor_sd, critic_sd, h0, z0, 901, 15, m["A"])
+    check_slice("sweep N=32768 replay", k1, a, b, wm_sd, actor_sd, critic_sd, h0, z0, 901, 15, m["A"], training=True)
+    check_slice("sweep N=32768 replay (last rows)", k1, N - 128, N, wm_sd, actor_sd, critic_sd, h0, z0, 901, 15, m["A"], training=True)
     # K2 + K4 on the whole batch vs torch fp32 autograd on the identical trajectory
     vs, w, _ = ops.lambda_return(k1["rewards"], k1["values"], k1["discounts"], agent.critic.lambda_)
 
