@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RLSB_ABI_VERSION 4
+#define RLSB_ABI_VERSION 5
 
 /* ---- library / device ------------------------------------------------------------------- */
 int rlsb_abi_version(void);
@@ -146,6 +146,9 @@ typedef struct {
    * rewards[H] / discounts[H] are never read by the update (ac.py:57-58, dreamer_v2.py:192-197) and are written as 0 / 1.
    * For the training path; imagine_trajectory's public result keeps the reference's rewards[H] (flag 0). */
   int32_t last_step_value_only;
+  /* rlsb_rollout_* only: CTAs per thread-block cluster (one cluster carries 128 start states): 4, 8 or 16; 0 = the
+   * library default (rlsb_rollout_cluster_size()).  The packed blob depends on it: pack with the same value. */
+  int32_t rollout_cluster;
 } rlsb_imagine_cfg;
 
 /* fp32 parameters in nn.Linear layout (weight = [out, in] row-major); NULL = absent.
@@ -242,6 +245,28 @@ int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* pa
 int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0,
                      const float* z0, const float* logits0, const rlsb_noise* noise,
                      const rlsb_imagine_out* out, void* workspace, void* stream);
+
+/* ---- K1 as ONE persistent kernel (csrc/rlsb_rollout.cu) ------------------------------------------------------------
+ * The same rollout — DreamerV2.imagine_trajectory's loop (agents/dreamer_v2.py:68-96) with everything it calls, see
+ * rlsb_imagine_fwd — executed by a single kernel launch: each 128-row block of start states is carried through all H
+ * steps by one thread-block cluster (rlsb_rollout_cluster_size() CTAs, env RLSB_ROLLOUT_CLUSTER = 4 | 8 | 16); layers are
+ * split by output columns over the CTAs, LayerNorm statistics travel through distributed shared memory, the GRU gates
+ * (agents/dreamer/common.py:69-81) are fused into their contraction's epilogue, and the only synchronisation between
+ * layers is the hardware cluster barrier.  For the launch-bound sizes (the configured 16 x 50 = 800 start states); the
+ * chained rlsb_imagine_fwd stays the path of the 16 k - 256 k sweep.
+ * Same cfg / noise / out / workspace (rlsb_imagine_workspace_bytes) / tape contract as rlsb_imagine_fwd for the flat
+ * RSSM (slots <= 1, parity == 0, out->actor_slots == NULL); the packed weights are this kernel's own. */
+int rlsb_rollout_cluster_size(void);
+/* profiling aid: a device buffer of (H + 1) x 11 x 8 uint64 that the next rlsb_rollout_fwd launches fill with
+ * %globaltimer stamps of cluster 0 — per step the 11 phases head layers 0-4, read-out / action draw, img_in, GRU, prior 1,
+ * prior 2, latent draw; per phase 0 producer starts, 1 first stage landed, 2 MMAs issued, 3 accumulator ready,
+ * 4 statistics pass done, 5 statistics exchanged, 6 outputs stored, 7 phase finished — or NULL to switch it off */
+void rlsb_rollout_set_trace(void* device_buffer);
+size_t rlsb_rollout_packed_bytes(const rlsb_imagine_cfg* cfg);
+int rlsb_rollout_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* params, void* packed, void* stream);
+int rlsb_rollout_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0, const float* z0,
+                     const float* logits0, const rlsb_noise* noise, const rlsb_imagine_out* out, void* workspace,
+                     void* stream);
 
 /* backward of the rollout w.r.t. the sampled actions (activation gradients only: the world model and the
  * target critic receive no parameter update from the actor loss, dreamer_v2.py:199-207):

@@ -24,7 +24,8 @@ class ImagineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "D", "groups", "classes", "A", "hidden", "discrete", "layer_norm", "predict_discount",
         "with_critic", "H", "discount_nan_on_tie", "with_backward", "slots", "attention_blocks",
-        "symmetric_qk")] + [("mixer_coeff", C.c_float), ("parity", C.c_int32), ("last_step_value_only", C.c_int32)]
+        "symmetric_qk")] + [("mixer_coeff", C.c_float), ("parity", C.c_int32), ("last_step_value_only", C.c_int32),
+                                  ("rollout_cluster", C.c_int32)]
 
 
 class MlpParams(C.Structure):
@@ -73,7 +74,7 @@ AC_SCALAR_NAMES = {
     "loss_actor": 4, "critic/avg_target_value": 5, "critic/avg_lambda_value": 6, "critic/avg_predicted_value": 7,
     "actor/avg_val": 8, "actor/mean_val": 9, "actor/avg_sd": 10, "actor/min_val": 11, "actor/max_val": 12}
 AC_SCALARS = 16
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class SlotCfg(C.Structure):
@@ -160,6 +161,12 @@ def load() -> C.CDLL:
         "rlsb_imagine_workspace_bytes": (sz, [C.POINTER(ImagineCfg), i64]),
         "rlsb_imagine_pack": (C.c_int, [C.POINTER(ImagineCfg), C.POINTER(ImagineParams), vp, vp]),
         "rlsb_imagine_fwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, vp, vp, vp, C.POINTER(Noise),
+                                       C.POINTER(ImagineOut), vp, vp]),
+        "rlsb_rollout_cluster_size": (C.c_int, []),
+        "rlsb_rollout_set_trace": (None, [vp]),
+        "rlsb_rollout_packed_bytes": (sz, [C.POINTER(ImagineCfg)]),
+        "rlsb_rollout_pack": (C.c_int, [C.POINTER(ImagineCfg), C.POINTER(ImagineParams), vp, vp]),
+        "rlsb_rollout_fwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, vp, vp, vp, C.POINTER(Noise),
                                        C.POINTER(ImagineOut), vp, vp]),
     }
     sig.update({

@@ -41,6 +41,7 @@ namespace rlsb {
 namespace ro {
 
 constexpr int kMaxC = 16;
+constexpr int kGruChunksHost = 5;   // == kGruChunks of the kernel
 constexpr int kThreads = kGemmThreads;   // warp 0 producer, warp 1 MMA issuer, warps 2-17 epilogue / row phases
 constexpr int kEpiThreads = 512;
 
@@ -82,6 +83,11 @@ struct RolloutParams {
   uint8_t* tape; size_t tape_step;
   size_t tp_head_pre[4], tp_head_rstd[4], tp_x_pre, tp_x_rstd, tp_gru_scratch, tp_gru_stats, tp_y_pre, tp_y_rstd;
   long long tape_ld_scratch; int tape_gru_nb;
+  // profiling aid (rlsb_rollout_set_trace): [H+1][11 phases][8] globaltimer stamps of cluster 0, see `trp` in the kernel;
+  // nullptr = off
+  unsigned long long* trace;
+  int kg_max;   // k tiles per pipeline stage, at most (RLSB_ROLLOUT_KG, default 4)
+  int dbg;   // timing experiments only (RLSB_ROLLOUT_DEBUG; results are garbage): 1 = no MMAs, 2 = no weight copies, 4 = no A copies
 };
 
 // split n columns into `parts` slices whose boundaries are multiples of 8 (16-byte chunks of the packed images)
@@ -158,6 +164,7 @@ inline int make_rplan(const rlsb_imagine_cfg& cfg, int C, RPlan& R) {
     int maxw = 0;
     for (int i = 0; i < parts; ++i) maxw = L.width[i] > maxw ? L.width[i] : maxw;
     L.wpad = k1::ru(maxw, 16);
+    if (L.wpad > 8 * 4 * kGruChunksHost) return -36;
     if ((e = finish(L)) != 0) return e;
   }
   if ((e = rssm(R.prior1, P.D, P.Dp / 64)) != 0) return e;
@@ -263,11 +270,38 @@ struct RCtl {
   float2 xstat[2][kTileM];   // this CTA's per-row (sum, sumsq) of the current LayerNorm layer, read by its peers (DSMEM)
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// profiling stamps: `p` = this phase's 8 slots (nullptr unless this thread is one of cluster 0's tracer threads)
+__device__ __forceinline__ void tr(unsigned long long* p, int slot) {
+  if (p) p[slot] = globaltimer_ns();
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// (volatile, no memory clobber: a run of these loads is issued back to back and their latencies overlap; they stay below
+// the cluster barrier, which is a volatile asm with a memory clobber)
 __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
   float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr));
   return v;
+}
+// sum over the CTAs [g0, g0 + cpg) of the float2 each keeps at shared-memory offset `mine`
+__device__ __forceinline__ float2 dsmem_sum(uint32_t mine, int g0, int cpg) {
+  float s = 0.f, q = 0.f;
+  for (int b = 0; b < cpg; b += 8) {   // eight loads in flight at a time
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      v[r] = b + r < cpg ? ld_dsmem_f2(mapa_cluster(mine, static_cast<uint32_t>(g0 + b + r))) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      s += v[r].x;
+      q += v[r].y;
+    }
+  }
+  return make_float2(s, q);
 }
 __device__ __forceinline__ void epi_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
@@ -293,60 +327,93 @@ struct Roles {
   uint32_t tf;   // epilogue: parity to wait for on tmem_full
 };
 
+// A pipeline stage holds a GROUP of up to `kg` consecutive k tiles of one K segment (their A tiles are contiguous in the
+// packed image, and so are the slab's): one "full" barrier, one tcgen05.commit per group instead of per k tile — the
+// commit is what paces a main loop of small MMAs (it is not overlapped with the MMAs that follow it).
+struct Ring {
+  int kg;            // k tiles per stage
+  int stages;
+  uint32_t a_bytes;  // bytes reserved for the A tiles of a stage (kg x 16 KB)
+  uint32_t stage_bytes;
+};
+__device__ __forceinline__ Ring make_ring(int ring_bytes, int NC, int kg_max) {
+  const int per_kt = 16384 + NC * 128;
+  int kg = ring_bytes / (2 * per_kt);   // at least two stages
+  if (kg > kg_max) kg = kg_max;
+  if (kg < 1) kg = 1;
+  Ring r;
+  r.kg = kg;
+  r.a_bytes = static_cast<uint32_t>(kg) * 16384u;
+  r.stage_bytes = static_cast<uint32_t>(kg * per_kt);
+  r.stages = ring_bytes / static_cast<int>(r.stage_bytes);
+  if (r.stages > 8) r.stages = 8;
+  return r;
+}
+
 // producer thread: stream the A tiles of this row block and this CTA's weight slab through the stage ring
 __device__ __forceinline__ void produce(RCtl* ctl, uint8_t* ring, int ring_bytes, const RLayer& L, int rank, const OpA& a,
-                                        Roles& st) {
-  const uint32_t b_bytes = static_cast<uint32_t>(L.NC) * 128u;
-  const uint32_t stage_bytes = 16384u + b_bytes;
-  int stages = ring_bytes / static_cast<int>(stage_bytes);
-  if (stages > 8) stages = 8;
+                                        Roles& st, int dbg, int kg_max, unsigned long long* trp) {
+  const Ring R = make_ring(ring_bytes, L.NC, kg_max);
+  const uint32_t b_kt = static_cast<uint32_t>(L.NC) * 128u;
+  tr(trp, 0);
   const __nv_bfloat16* w = L.W + static_cast<size_t>(rank) * L.kt * L.NC * 64;
   fence_proxy_async_all();   // the images were written with ordinary stores by other CTAs before the cluster barrier
   int s = 0, ktg = 0;
   for (int sg = 0; sg < a.nseg; ++sg) {
-    for (int kt = 0; kt < a.kt[sg]; ++kt, ++ktg) {
+    for (int kt = 0; kt < a.kt[sg]; kt += R.kg) {
+      const int g = min(R.kg, a.kt[sg] - kt);
       mbar_wait(&ctl->empty[s], (st.pe >> s) & 1u);
       st.pe ^= 1u << s;
-      uint8_t* sa = ring + static_cast<size_t>(s) * stage_bytes;
-      mbar_expect_tx(&ctl->full[s], stage_bytes);
-      bulk_g2s(sa, a.A[sg] + static_cast<size_t>(kt) * (kTileM * kTileK), 16384u, &ctl->full[s]);
-      bulk_g2s(sa + 16384, w + static_cast<size_t>(ktg) * L.NC * 64, b_bytes, &ctl->full[s]);
-      if (++s == stages) s = 0;
+      uint8_t* sa = ring + static_cast<size_t>(s) * R.stage_bytes;
+      const uint32_t ab = static_cast<uint32_t>(g) * 16384u, bb = static_cast<uint32_t>(g) * b_kt;
+      mbar_expect_tx(&ctl->full[s], ((dbg & 4) ? 0u : ab) + ((dbg & 2) ? 0u : bb));
+      if (!(dbg & 4)) bulk_g2s(sa, a.A[sg] + static_cast<size_t>(kt) * (kTileM * kTileK), ab, &ctl->full[s]);
+      if (!(dbg & 2)) bulk_g2s(sa + R.a_bytes, w + static_cast<size_t>(ktg) * L.NC * 64, bb, &ctl->full[s]);
+      ktg += g;
+      if (++s == R.stages) s = 0;
     }
   }
 }
 
 // MMA thread: acc[128 x NC] (TMEM columns 0..NC) = sum over k tiles of A_tile * W_tile^T
 __device__ __forceinline__ void issue_mma(RCtl* ctl, uint8_t* ring, int ring_bytes, const RLayer& L, uint32_t tmem_base,
-                                          Roles& st) {
-  const uint32_t b_bytes = static_cast<uint32_t>(L.NC) * 128u;
-  const uint32_t stage_bytes = 16384u + b_bytes;
-  int stages = ring_bytes / static_cast<int>(stage_bytes);
-  if (stages > 8) stages = 8;
+                                          const OpA& a, Roles& st, int dbg, int kg_max, unsigned long long* trp) {
+  const Ring R = make_ring(ring_bytes, L.NC, kg_max);
+  const uint32_t b_kt = static_cast<uint32_t>(L.NC) * 128u;
   const int n0 = L.NC > 256 ? 256 : L.NC, n1 = L.NC - n0;
   const uint32_t idesc0 = make_idesc_bf16(kTileM, static_cast<uint32_t>(n0));
   const uint32_t idesc1 = n1 > 0 ? make_idesc_bf16(kTileM, static_cast<uint32_t>(n1)) : 0u;
   tc_fence_after();   // the previous layer's epilogue has drained TMEM (cluster barrier in between)
   int s = 0;
-  for (int kt = 0; kt < L.kt; ++kt) {
-    mbar_wait(&ctl->full[s], (st.pf >> s) & 1u);
-    st.pf ^= 1u << s;
-    tc_fence_after();
-    const uint32_t sa = smem_u32(ring + static_cast<size_t>(s) * stage_bytes);
-    const uint64_t adesc = make_smem_desc_sw128(sa);
-    const uint64_t bdesc0 = make_smem_desc_sw128(sa + 16384u);
-    const uint64_t bdesc1 = make_smem_desc_sw128(sa + 16384u + static_cast<uint32_t>(n0) * 128u);
+  uint32_t acc = 0u;
+  for (int sg = 0; sg < a.nseg; ++sg) {
+    for (int kt = 0; kt < a.kt[sg]; kt += R.kg) {
+      const int g = min(R.kg, a.kt[sg] - kt);
+      mbar_wait(&ctl->full[s], (st.pf >> s) & 1u);
+      st.pf ^= 1u << s;
+      tc_fence_after();
+      if (acc == 0u) tr(trp, 1);
+      const uint32_t sa = smem_u32(ring + static_cast<size_t>(s) * R.stage_bytes);
+      for (int j = 0; j < g; ++j) {
+        const uint64_t adesc = make_smem_desc_sw128(sa + static_cast<uint32_t>(j) * 16384u);
+        const uint32_t sb = sa + R.a_bytes + static_cast<uint32_t>(j) * b_kt;
+        const uint64_t bdesc0 = make_smem_desc_sw128(sb);
+        const uint64_t bdesc1 = make_smem_desc_sw128(sb + static_cast<uint32_t>(n0) * 128u);
 #pragma unroll
-    for (int kk = 0; kk < kTileK / 16; ++kk) {
-      const uint32_t acc = (kt > 0 || kk > 0) ? 1u : 0u;
-      umma_bf16(tmem_base, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2), idesc0, acc);
-      if (n1 > 0)
-        umma_bf16(tmem_base + 256u, adesc + static_cast<uint64_t>(kk * 2), bdesc1 + static_cast<uint64_t>(kk * 2), idesc1,
-                  acc);
+        for (int kk = 0; kk < kTileK / 16; ++kk) {
+          if (dbg & 1) break;
+          umma_bf16(tmem_base, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2), idesc0, acc);
+          if (n1 > 0)
+            umma_bf16(tmem_base + 256u, adesc + static_cast<uint64_t>(kk * 2), bdesc1 + static_cast<uint64_t>(kk * 2), idesc1,
+                      acc);
+          acc = 1u;
+        }
+      }
+      umma_commit(&ctl->empty[s]);
+      if (++s == R.stages) s = 0;
     }
-    umma_commit(&ctl->empty[s]);
-    if (++s == stages) s = 0;
   }
+  tr(trp, 2);
   umma_commit(&ctl->tmem_full);
 }
 
@@ -393,17 +460,11 @@ __device__ __forceinline__ RowStat ln_exchange(RCtl* ctl, int cq, int row, float
   }
   __syncwarp();
   cluster_sync_all();
-  float s = 0.f, q = 0.f;
-  const uint32_t mine = smem_u32(&ctl->xstat[par][row]);
-  for (int r = 0; r < cpg; ++r) {
-    const float2 v = ld_dsmem_f2(mapa_cluster(mine, static_cast<uint32_t>(g0 + r)));
-    s += v.x;
-    q += v.y;
-  }
+  const float2 tot = dsmem_sum(smem_u32(&ctl->xstat[par][row]), g0, cpg);
   RowStat st;
   const float inv_n = 1.0f / static_cast<float>(n);
-  st.mean = s * inv_n;
-  st.rstd = 1.0f / sqrtf(fmaxf(q * inv_n - st.mean * st.mean, 0.f) + eps);
+  st.mean = tot.x * inv_n;
+  st.rstd = 1.0f / sqrtf(fmaxf(tot.y * inv_n - st.mean * st.mean, 0.f) + eps);
   return st;
 }
 
@@ -423,7 +484,7 @@ struct LnActOut {
 };
 
 __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank, bool ln, const LnActOut& o, uint32_t tmem_d,
-                                           int cq, int row, bool row_ok, float eps, int par) {
+                                           int cq, int row, bool row_ok, float eps, int par, unsigned long long* trp) {
   const int gi = rank % L.cpg, g0 = rank - gi;
   const int width = L.width[gi], col0 = L.col0[gi];
   const int n_chunks = L.NC >> 3;
@@ -442,7 +503,9 @@ __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank,
         }
       }
     });
+    tr(trp, 4);
     st = ln_exchange(ctl, cq, row, sum, sq, g0, L.cpg, L.n, eps, par);
+    tr(trp, 5);
   }
   const float nmr = -st.mean * st.rstd;
   const bool save = o.save_pre != nullptr;
@@ -478,6 +541,108 @@ __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank,
     }
   }
   if (ln && o.save_rstd && cq == 0 && gi == 0) o.save_rstd[row] = st.rstd;
+  tr(trp, 6);
+}
+
+// the compiler must not move a read of freshly loaded TMEM registers above the tcgen05.wait::ld that completes them
+__device__ __forceinline__ void tie8(uint32_t (&r)[8]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+}
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {   // 32-byte aligned shared-memory parameters
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// epi_ln_act with the thread's accumulator columns held in registers between the statistics and the output pass: every
+// TMEM load of the thread is in flight at once and TMEM is read once (MAXCH = 8-column chunks per thread, at most)
+template <int MAXCH>
+__device__ __forceinline__ void epi_ln_act_reg(RCtl* ctl, const RLayer& L, int rank, bool ln, const LnActOut& o, uint32_t tmem_d,
+                                               int cq, int row, bool row_ok, float eps, int par, unsigned long long* trp) {
+  const int gi = rank % L.cpg, g0 = rank - gi;
+  const int width = L.width[gi], col0 = L.col0[gi];
+  const int n_chunks = L.NC >> 3;
+  const int mine = n_chunks > cq ? (n_chunks - cq + 3) >> 2 : 0;
+  uint32_t r[MAXCH][8];
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i)
+    if (i < mine) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * i) * 8), r[i]);
+  tmem_ld_wait();
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (i < mine && c < width) {
+      tie8(r[i]);
+      float b[8];
+      ld8f(&ctl->bias[c], b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = __uint_as_float(r[i][j]) + b[j];
+        r[i][j] = __float_as_uint(v);   // the pre-activation stays in the register the accumulator arrived in
+        if (c + j < width) {
+          sum += v;
+          sq = fmaf(v, v, sq);
+        }
+      }
+    }
+  }
+  RowStat st{0.f, 1.f};
+  if (ln) {
+    tr(trp, 4);
+    st = ln_exchange(ctl, cq, row, sum, sq, g0, L.cpg, L.n, eps, par);
+    tr(trp, 5);
+  }
+  const float nmr = -st.mean * st.rstd;
+  const bool save = o.save_pre != nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (i < mine && c < width) {
+      float y[8], x[8], g[8], be[8];
+      if (ln) {
+        ld8f(&ctl->gamma[c], g);
+        ld8f(&ctl->beta[c], be);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = __uint_as_float(r[i][j]);
+        if (ln) {
+          a = fmaf(a, st.rstd, nmr);
+          x[j] = a;
+          a = fmaf(a, g[j], be[j]);
+        } else {
+          x[j] = a;
+        }
+        y[j] = elu1(a);
+        if (c + j >= width || (save && !row_ok)) {
+          y[j] = 0.f;
+          x[j] = 0.f;
+        }
+      }
+      const size_t off = pk_off(row, col0 + c);
+      *reinterpret_cast<uint4*>(o.out + off) = pack8(y);
+      if (save) *reinterpret_cast<uint4*>(o.save_pre + off) = pack8(x);
+    }
+  }
+  if (gi == L.cpg - 1) {   // padding columns of the image: zeros (they meet zero weights, but must be finite)
+    for (int ch = ((col0 + width + 7) >> 3) + cq; ch < (o.out_kpad >> 3); ch += 4) {
+      const size_t off = pk_off(row, ch * 8);
+      *reinterpret_cast<uint4*>(o.out + off) = make_uint4(0u, 0u, 0u, 0u);
+      if (save) *reinterpret_cast<uint4*>(o.save_pre + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if (ln && o.save_rstd && cq == 0 && gi == 0) o.save_rstd[row] = st.rstd;
+  tr(trp, 6);
+}
+// size dispatch: chunks per thread = ceil(NC / 32)
+__device__ __forceinline__ void epi_ln_act_any(RCtl* ctl, const RLayer& L, int rank, bool ln, const LnActOut& o, uint32_t tmem_d,
+                                               int cq, int row, bool row_ok, float eps, int par, unsigned long long* trp) {
+  // (the register-resident variant costs more in spills than it saves in TMEM reads while the whole rollout is one
+  // function compiled for 96 registers per thread: kept for reference, switched off)
+  constexpr bool kRegEpilogue = false;
+  const int per_thread = (L.NC + 31) >> 5;
+  if (kRegEpilogue && per_thread <= 4) epi_ln_act_reg<4>(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, eps, par, trp);
+  else epi_ln_act(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, eps, par, trp);
 }
 
 // Linear -> fp32 row-major (fc_nn.py:21 head outputs; rssm.py:192 prior logits)
@@ -511,8 +676,29 @@ struct GruOut {
   float2* tape_stats;    // tape: [nb][m_pad] partial statistics, this row block's first row, or nullptr
   int tape_nb, m_pad;
 };
+constexpr int kGruChunks = 5;   // 8-column chunks of hidden units per epilogue thread (wpad <= 160)
+// h_prev of this thread's hidden units, fetched while the contraction is still running
+template <int NCH>
+__device__ __forceinline__ void gru_prefetch_h(const RLayer& L, int rank, const float* h_prev, int cq, bool row_ok,
+                                               float (&hp)[NCH][8]) {
+  const int width = L.width[rank], col0 = L.col0[rank];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (row_ok && c + 8 <= width) {
+      const float4 h0 = __ldcg(reinterpret_cast<const float4*>(h_prev + col0 + c));
+      const float4 h1 = __ldcg(reinterpret_cast<const float4*>(h_prev + col0 + c + 4));
+      hp[i][0] = h0.x; hp[i][1] = h0.y; hp[i][2] = h0.z; hp[i][3] = h0.w;
+      hp[i][4] = h1.x; hp[i][5] = h1.y; hp[i][6] = h1.z; hp[i][7] = h1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hp[i][j] = (row_ok && c + j < width) ? __ldcg(h_prev + col0 + c + j) : 0.f;
+    }
+  }
+}
 __device__ __forceinline__ void epi_gru(RCtl* ctl, const RLayer& L, int rank, int D, int Dp, const GruOut& o, uint32_t tmem_d,
-                                        int cq, int row, bool row_ok, float eps, int par) {
+                                        int cq, int row, bool row_ok, float eps, int par, const float (&hpre)[kGruChunks][8],
+                                        unsigned long long* trp) {
   const int width = L.width[rank], col0 = L.col0[rank], wpad = L.wpad;
   const int n_chunks = wpad >> 3;
   float sum = 0.f, sq = 0.f;
@@ -535,36 +721,24 @@ __device__ __forceinline__ void epi_gru(RCtl* ctl, const RLayer& L, int rank, in
       }
     }
   }
+  tr(trp, 4);
   const RowStat st = ln_exchange(ctl, cq, row, sum, sq, 0, L.cpg, L.n, eps, par);
+  tr(trp, 5);
   if (o.tape_stats && cq == 0 && rank == 0) {
     // the backward pass sums the per-block partials of the chained rollout: hand it the total in block 0
-    const uint32_t mine = smem_u32(&ctl->xstat[par][row]);
-    float s = 0.f, q = 0.f;
-    for (int r = 0; r < L.cpg; ++r) {
-      const float2 v = ld_dsmem_f2(mapa_cluster(mine, static_cast<uint32_t>(r)));
-      s += v.x;
-      q += v.y;
-    }
-    o.tape_stats[row] = make_float2(s, q);
+    o.tape_stats[row] = dsmem_sum(smem_u32(&ctl->xstat[par][row]), 0, L.cpg);
     for (int b = 1; b < o.tape_nb; ++b) o.tape_stats[static_cast<size_t>(b) * o.m_pad + row] = make_float2(0.f, 0.f);
   }
   const float nmr = -st.mean * st.rstd;
-  for (int jc = cq; jc < n_chunks; jc += 4) {
-    const int c = jc * 8;
-    if (c >= width) break;
+#pragma unroll
+  for (int i = 0; i < kGruChunks; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (c >= width || c >= wpad) break;
+    const float (&hp)[8] = hpre[i];
     uint32_t r0[8], r1[8], r2[8];
     tmem_ld8(tmem_d + static_cast<uint32_t>(c), r0);
     tmem_ld8(tmem_d + static_cast<uint32_t>(wpad + c), r1);
     tmem_ld8(tmem_d + static_cast<uint32_t>(2 * wpad + c), r2);
-    float hp[8];
-    if (row_ok && c + 8 <= width) {
-      const float4 h0 = __ldcg(reinterpret_cast<const float4*>(o.h_prev + col0 + c));
-      const float4 h1 = __ldcg(reinterpret_cast<const float4*>(o.h_prev + col0 + c + 4));
-      hp[0] = h0.x; hp[1] = h0.y; hp[2] = h0.z; hp[3] = h0.w; hp[4] = h1.x; hp[5] = h1.y; hp[6] = h1.z; hp[7] = h1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) hp[j] = (row_ok && c + j < width) ? __ldcg(o.h_prev + col0 + c + j) : 0.f;
-    }
     tmem_ld_wait();
     float y[8];
 #pragma unroll
@@ -598,6 +772,98 @@ __device__ __forceinline__ void epi_gru(RCtl* ctl, const RLayer& L, int rank, in
     for (int ch = ((D + 7) >> 3) + cq; ch < (Dp >> 3); ch += 4)
       *reinterpret_cast<uint4*>(o.himg + pk_off(row, ch * 8)) = make_uint4(0u, 0u, 0u, 0u);
   }
+  tr(trp, 6);
+}
+
+// epi_gru for slices of at most 64 hidden units (two 8-column chunks per thread): the 3 x 2 accumulator chunks stay in
+// registers between the statistics and the gate pass
+__device__ __forceinline__ void epi_gru_reg(RCtl* ctl, const RLayer& L, int rank, int D, int Dp, const GruOut& o, uint32_t tmem_d,
+                                            int cq, int row, bool row_ok, float eps, int par, const float (&hpre)[2][8],
+                                            unsigned long long* trp) {
+  constexpr int MJ = 2;
+  const int width = L.width[rank], col0 = L.col0[rank], wpad = L.wpad;
+  uint32_t r[3][MJ][8];
+#pragma unroll
+  for (int i = 0; i < MJ; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (c < width) {
+#pragma unroll
+      for (int gt = 0; gt < 3; ++gt) tmem_ld8(tmem_d + static_cast<uint32_t>(gt * wpad + c), r[gt][i]);
+    }
+  }
+  tmem_ld_wait();
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MJ; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (c < width) {
+#pragma unroll
+      for (int gt = 0; gt < 3; ++gt) {
+        tie8(r[gt][i]);
+        float b[8];
+        ld8f(&ctl->bias[gt * wpad + c], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = __uint_as_float(r[gt][i][j]) + b[j];
+          r[gt][i][j] = __float_as_uint(v);
+          if (c + j < width) {
+            sum += v;
+            sq = fmaf(v, v, sq);
+          }
+        }
+      }
+    }
+  }
+  tr(trp, 4);
+  const RowStat st = ln_exchange(ctl, cq, row, sum, sq, 0, L.cpg, L.n, eps, par);
+  tr(trp, 5);
+  if (o.tape_stats && cq == 0 && rank == 0) {
+    o.tape_stats[row] = dsmem_sum(smem_u32(&ctl->xstat[par][row]), 0, L.cpg);
+    for (int b = 1; b < o.tape_nb; ++b) o.tape_stats[static_cast<size_t>(b) * o.m_pad + row] = make_float2(0.f, 0.f);
+  }
+  const float nmr = -st.mean * st.rstd;
+#pragma unroll
+  for (int i = 0; i < MJ; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (c < width) {
+      float gr[8], gc[8], gu[8], br[8], bc[8], bu[8], y[8];
+      ld8f(&ctl->gamma[c], gr);
+      ld8f(&ctl->gamma[wpad + c], gc);
+      ld8f(&ctl->gamma[2 * wpad + c], gu);
+      ld8f(&ctl->beta[c], br);
+      ld8f(&ctl->beta[wpad + c], bc);
+      ld8f(&ctl->beta[2 * wpad + c], bu);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pr = __uint_as_float(r[0][i][j]), pc = __uint_as_float(r[1][i][j]), pu = __uint_as_float(r[2][i][j]);
+        if (o.tape_pre && row_ok && c + j < width) {
+          o.tape_pre[col0 + c + j] = pr;
+          o.tape_pre[D + col0 + c + j] = pc;
+          o.tape_pre[2 * D + col0 + c + j] = pu;
+        }
+        const float rg = rowops::fast_sigmoid(fmaf(fmaf(pr, st.rstd, nmr), gr[j], br[j]));
+        const float cand = rowops::fast_tanh(rg * fmaf(fmaf(pc, st.rstd, nmr), gc[j], bc[j]));
+        const float u = rowops::fast_sigmoid(fmaf(fmaf(pu, st.rstd, nmr), gu[j], bu[j]) - 1.0f);
+        y[j] = (row_ok && c + j < width) ? u * cand + (1.0f - u) * hpre[i][j] : 0.f;
+      }
+      if (row_ok) {
+        if (c + 8 <= width) {
+          *reinterpret_cast<float4*>(o.h_next + col0 + c) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(o.h_next + col0 + c + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c + j < width) o.h_next[col0 + c + j] = y[j];
+        }
+      }
+      *reinterpret_cast<uint4*>(o.himg + pk_off(row, col0 + c)) = pack8(y);
+    }
+  }
+  if (rank == L.cpg - 1) {   // padding columns [D rounded up to 8, Dp) of the h image
+    for (int ch = ((D + 7) >> 3) + cq; ch < (Dp >> 3); ch += 4)
+      *reinterpret_cast<uint4*>(o.himg + pk_off(row, ch * 8)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  tr(trp, 6);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -655,21 +921,30 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
   auto zimg = [&](int t) { return P.zimg + static_cast<size_t>(P.zimg_pingpong ? (t & 1) : t) * P.zimg_step + blk_S; };
   auto tp = [&](int t, size_t off) { return P.tape + static_cast<size_t>(t) * P.tape_step + off; };
 
+  int phase = 0;   // phase index inside the step (profiling stamps)
+  const bool tracer = P.trace != nullptr && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64);
+  unsigned long long* trp = nullptr;   // this phase's stamps: 0 producer starts, 1 first stage landed, 2 MMAs issued, 3 accumulator
+                                       // ready, 4 statistics pass done, 5 statistics exchanged, 6 outputs stored, 7 phase finished
+  auto stamp = [&](int t, int ph) {    // call at the top of phase `ph` of step t
+    trp = tracer ? P.trace + (static_cast<size_t>(t) * 11 + ph) * 8 : nullptr;
+  };
   // one contraction layer, every role: `active` = this CTA has a slab in it
   auto run_mainloop = [&](const RLayer& L, const OpA& a, bool active) {
     if (warp == 0) {
-      if (active && lane == 0) produce(ctl, ring, ring_bytes, L, rank, a, st);
+      if (active && lane == 0) produce(ctl, ring, ring_bytes, L, rank, a, st, P.dbg, P.kg_max, trp);
       __syncwarp();
     } else if (warp == 1) {
-      if (active && lane == 0) issue_mma(ctl, ring, ring_bytes, L, tmem_base, st);
+      if (active && lane == 0) issue_mma(ctl, ring, ring_bytes, L, tmem_base, a, st, P.dbg, P.kg_max, trp);
       __syncwarp();
     }
   };
 
   for (int t = 0; t <= P.H; ++t) {
+    phase = 0;
     // ================= heads on s_t = cat[h_t, z_t]: actor, reward, discount, target critic =================
     const bool crit_only = P.last_step_value_only != 0 && t == P.H && !P.tape && P.g_critic >= 0;
     for (int l = 0; l < 5; ++l) {
+      stamp(t, phase);
       const RLayer& L = P.head[l];
       const int grp = rank / L.cpg;
       const bool active = rank < L.ranks && (!crit_only || grp == P.g_critic);
@@ -688,6 +963,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
         const bool ln = (l == 0) || P.layer_norm;
         if (warp >= 2 && active) {
           epi_begin(ctl, L, rank, tid_e, ln, st);
+          tr(trp, 3);
           LnActOut o;
           o.out = P.hid[l & 1] + static_cast<size_t>(grp) * hid_gs + blk_H;
           o.out_kpad = P.Hp;
@@ -696,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
           o.save_rstd = (P.tape && ln) ? reinterpret_cast<float*>(tp(t, P.tp_head_rstd[l])) + static_cast<size_t>(grp) * P.m_pad +
                                              rb * kTileM
                                        : nullptr;
-          epi_ln_act(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, P.eps, lnpar);
+          epi_ln_act_any(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, P.eps, lnpar, trp);
         } else if (ln) {
           __syncwarp();
           cluster_sync_all();   // the statistics exchange of the CTAs that do have work
@@ -704,12 +980,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
         if (ln) lnpar ^= 1;
       } else if (warp >= 2 && active) {
         epi_begin(ctl, L, rank, tid_e, false, st);
+        tr(trp, 3);
         float* orow = P.head_out + (static_cast<size_t>(grp) * P.m_pad + m) * 32;
         epi_plain(ctl, L, rank, orow, grp == P.g_actor ? P.Aout : 1, tmem_d, cq, row_ok);
       }
       layer_end(warp >= 2 && active);
+      tr(trp, 7);
+      ++phase;
     }
     // ---- reward / value / discount read-out and the action draw: one warp per row, rows split over the cluster ----
+    stamp(t, phase);
     if (warp >= 2) {
       const int rpc = kTileM / C;
       const bool want_action = t < P.H && !crit_only;
@@ -788,10 +1068,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
       }
     }
     layer_end(warp >= 2);
+    tr(trp, 7);
+    ++phase;
     if (t == P.H) break;
 
     // ================= x = ELU(LN?(W_in [z, a] + b))                                    rssm.py:179 =================
     {
+      stamp(t, phase);
       const RLayer& L = P.img_in;
       const bool active = rank < L.ranks;
       OpA a;
@@ -802,21 +1085,25 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
       const bool ln = P.layer_norm != 0;
       if (warp >= 2 && active) {
         epi_begin(ctl, L, rank, tid_e, ln, st);
+          tr(trp, 3);
         LnActOut o;
         o.out = P.xbf + blk_D;
         o.out_kpad = P.Dp;
         o.save_pre = P.tape ? reinterpret_cast<__nv_bfloat16*>(tp(t + 1, P.tp_x_pre)) + blk_D : nullptr;
         o.save_rstd = (P.tape && ln) ? reinterpret_cast<float*>(tp(t + 1, P.tp_x_rstd)) + rb * kTileM : nullptr;
-        epi_ln_act(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, P.eps, lnpar);
+        epi_ln_act_any(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, P.eps, lnpar, trp);
       } else if (ln) {
         __syncwarp();
         cluster_sync_all();
       }
       if (ln) lnpar ^= 1;
       layer_end(warp >= 2 && active);
+      tr(trp, 7);
+      ++phase;
     }
     // ================= h' = GRU(x, h)                                      rssm.py:181, common.py:69-81 =================
     {
+      stamp(t, phase);
       const RLayer& L = P.gru;
       const bool active = rank < L.ranks;
       OpA a;
@@ -825,9 +1112,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
       a.A[1] = himg(t); a.kt[1] = P.Dp >> 6;
       run_mainloop(L, a, active);
       if (warp >= 2 && active) {
-        epi_begin(ctl, L, rank, tid_e, true, st);
+        const float* hprev = P.determ + static_cast<size_t>(t) * ND + static_cast<size_t>(m) * P.D;
         GruOut o;
-        o.h_prev = P.determ + static_cast<size_t>(t) * ND + static_cast<size_t>(m) * P.D;
+        o.h_prev = hprev;
         o.h_next = P.determ + static_cast<size_t>(t + 1) * ND + static_cast<size_t>(m) * P.D;
         o.himg = himg(t + 1);
         o.tape_pre = P.tape ? reinterpret_cast<float*>(tp(t + 1, P.tp_gru_scratch)) + static_cast<size_t>(m) * P.tape_ld_scratch
@@ -835,16 +1122,31 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
         o.tape_stats = P.tape ? reinterpret_cast<float2*>(tp(t + 1, P.tp_gru_stats)) + rb * kTileM : nullptr;
         o.tape_nb = P.tape_gru_nb;
         o.m_pad = P.m_pad;
-        epi_gru(ctl, L, rank, P.D, P.Dp, o, tmem_d, cq, row, row_ok, P.eps, lnpar);
+        if (false && L.wpad <= 64) {
+          float hp[2][8];
+          gru_prefetch_h<2>(L, rank, hprev, cq, row_ok, hp);
+          epi_begin(ctl, L, rank, tid_e, true, st);
+          tr(trp, 3);
+          epi_gru_reg(ctl, L, rank, P.D, P.Dp, o, tmem_d, cq, row, row_ok, P.eps, lnpar, hp, trp);
+        } else {
+          float hp[kGruChunks][8];
+          gru_prefetch_h<kGruChunks>(L, rank, hprev, cq, row_ok, hp);
+          epi_begin(ctl, L, rank, tid_e, true, st);
+          tr(trp, 3);
+          epi_gru(ctl, L, rank, P.D, P.Dp, o, tmem_d, cq, row, row_ok, P.eps, lnpar, hp, trp);
+        }
       } else {
         __syncwarp();
         cluster_sync_all();
       }
       lnpar ^= 1;
       layer_end(warp >= 2 && active);
+      tr(trp, 7);
+      ++phase;
     }
     // ================= prior logits = W2 ELU(LN?(W1 h' + b1)) + b2                         rssm.py:192 =================
     {
+      stamp(t, phase);
       const RLayer& L = P.prior1;
       const bool active = rank < L.ranks;
       OpA a;
@@ -855,20 +1157,24 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
       const bool ln = P.layer_norm != 0;
       if (warp >= 2 && active) {
         epi_begin(ctl, L, rank, tid_e, ln, st);
+          tr(trp, 3);
         LnActOut o;
         o.out = P.ybf + blk_D;
         o.out_kpad = P.Dp;
         o.save_pre = P.tape ? reinterpret_cast<__nv_bfloat16*>(tp(t + 1, P.tp_y_pre)) + blk_D : nullptr;
         o.save_rstd = (P.tape && ln) ? reinterpret_cast<float*>(tp(t + 1, P.tp_y_rstd)) + rb * kTileM : nullptr;
-        epi_ln_act(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, P.eps, lnpar);
+        epi_ln_act_any(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, P.eps, lnpar, trp);
       } else if (ln) {
         __syncwarp();
         cluster_sync_all();
       }
       if (ln) lnpar ^= 1;
       layer_end(warp >= 2 && active);
+      tr(trp, 7);
+      ++phase;
     }
     {
+      stamp(t, phase);
       const RLayer& L = P.prior2;
       const bool active = rank < L.ranks;
       OpA a;
@@ -878,12 +1184,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
       run_mainloop(L, a, active);
       if (warp >= 2 && active) {
         epi_begin(ctl, L, rank, tid_e, false, st);
+        tr(trp, 3);
         float* orow = P.logits + static_cast<size_t>(t + 1) * NS + static_cast<size_t>(m) * P.S + L.col0[rank];
         epi_plain(ctl, L, rank, orow, L.width[rank], tmem_d, cq, row_ok);
       }
       layer_end(warp >= 2 && active);
+      tr(trp, 7);
+      ++phase;
     }
     // ================= z' ~ OneHotCategoricalST(logits)                                     rssm.py:34-37 =================
+    stamp(t, phase);
     if (warp >= 2) {
       const int rpc = kTileM / C;
       const long long row0 = static_cast<long long>(rb) * kTileM + rank * rpc;
@@ -910,6 +1220,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
       }
     }
     layer_end(warp >= 2);
+    tr(trp, 7);
+    ++phase;
   }
 
   tc_fence_before();
@@ -922,6 +1234,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
 }
 
 int g_rollout_cluster = 0;   // 0: not read yet
+unsigned long long* g_rollout_trace = nullptr;
 
 int rollout_cluster_size() {
   if (g_rollout_cluster == 0) {
@@ -961,9 +1274,18 @@ using namespace rlsb::ro;
 
 extern "C" int rlsb_rollout_cluster_size(void) { return rollout_cluster_size(); }
 
+extern "C" void rlsb_rollout_set_trace(void* device_buffer) { g_rollout_trace = static_cast<unsigned long long*>(device_buffer); }
+
+namespace {
+int cluster_of(const rlsb_imagine_cfg& cfg) {
+  const int c = cfg.rollout_cluster;
+  return (c == 4 || c == 8 || c == 16) ? c : rollout_cluster_size();
+}
+}  // namespace
+
 extern "C" size_t rlsb_rollout_packed_bytes(const rlsb_imagine_cfg* cfg) {
   RPlan R;
-  if (!cfg || make_rplan(*cfg, rollout_cluster_size(), R) != 0) return 0;
+  if (!cfg || make_rplan(*cfg, cluster_of(*cfg), R) != 0) return 0;
   return R.bytes;
 }
 
@@ -971,7 +1293,7 @@ extern "C" int rlsb_rollout_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
   if (!cfg || !prm || !packed) return -1;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   RPlan R;
-  RLSB_TRY(make_rplan(*cfg, rollout_cluster_size(), R));
+  RLSB_TRY(make_rplan(*cfg, cluster_of(*cfg), R));
   const k1::Plan& P = R.P;
   uint8_t* base = static_cast<uint8_t*>(packed);
   RPackJobs J{};
@@ -1042,7 +1364,7 @@ extern "C" int rlsb_rollout_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   if (out->actor_slots) return -7;   // the update recomputes the actor forward at these sizes
   if ((out->determ_packed != nullptr) != (out->stoch_packed != nullptr)) return -4;
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  const int C = rollout_cluster_size();
+  const int C = cluster_of(*cfg);
   RPlan R;
   RLSB_TRY(make_rplan(*cfg, C, R));
   const k1::Plan& P = R.P;
@@ -1101,6 +1423,10 @@ extern "C" int rlsb_rollout_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     rp.tape_ld_scratch = TP.ld_scratch;
     rp.tape_gru_nb = P.gru.NB;
   }
+  rp.trace = g_rollout_trace;
+  if (const char* env = getenv("RLSB_ROLLOUT_DEBUG")) rp.dbg = atoi(env);
+  rp.kg_max = 4;
+  if (const char* env = getenv("RLSB_ROLLOUT_KG")) rp.kg_max = atoi(env) >= 1 ? atoi(env) : 1;
   auto himg = [&](int t) { return rp.himg + static_cast<size_t>(rp.himg_pingpong ? (t & 1) : t) * rp.himg_step; };
   auto zimg = [&](int t) { return rp.zimg + static_cast<size_t>(rp.zimg_pingpong ? (t & 1) : t) * rp.zimg_step; };
 

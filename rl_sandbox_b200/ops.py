@@ -6,6 +6,7 @@ Every function raises if the library or a B200 device is missing — there is no
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -252,13 +253,14 @@ class ImagineConfig:
     mixer_coeff: float = 1.0           # attention_scheduler.val
     parity: bool = False               # split-operand ("bf16 x 3") contractions: fp32-grade results, 3x tensor work
     last_step_value_only: bool = False  # training path: at step H only the target critic's head runs (values[H])
+    rollout_cluster: int = 0           # persistent rollout: CTAs per cluster (4 | 8 | 16); 0 = chosen per call from the rows
 
     def to_c(self) -> ImagineCfg:
         return ImagineCfg(self.D, self.groups, self.classes, self.A, self.hidden, int(self.discrete),
                           int(self.layer_norm), int(self.predict_discount), int(self.with_critic), self.H,
                           int(self.discount_nan_on_tie), int(self.with_backward), int(self.slots),
                           int(self.attention_blocks), int(self.symmetric_qk), float(self.mixer_coeff), int(self.parity),
-                          int(self.last_step_value_only))
+                          int(self.last_step_value_only), int(self.rollout_cluster))
 
 
 def _mlp_params(sd: dict, prefix: str, keep: list) -> MlpParams:
@@ -294,6 +296,18 @@ class ImaginationEngine:
         if nbytes == 0:
             raise _lib.RlsbError(f"unsupported imagination config {cfg}")
         self.packed = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+        # The persistent rollout kernel (rlsb_rollout_fwd: the whole H-step rollout in ONE launch, a thread-block cluster
+        # per 128 start states) takes over below `persistent_max_rows` start states, where the chained rollout is bound
+        # by the latency of its ~230 dependent launches.  RLSB_PERSISTENT=0 disables it, =1 forces it for any size.
+        env = os.environ.get("RLSB_PERSISTENT", "")
+        self.persistent_max_rows = {"0": 0, "1": 1 << 30}.get(env, 2048)
+        ro_bytes = self.lib.rlsb_rollout_packed_bytes(C.byref(self.ccfg)) if self.persistent_max_rows > 0 else 0
+        # its weights are re-ordered per CTA of the cluster, i.e. they depend on the cluster size: packed on first use
+        # after every `pack` (one blob per cluster size seen)
+        self.packed_ro: Optional[dict] = {} if ro_bytes else None
+        self._ro_version: dict = {}
+        self._pack_version = 0
+        self._params = None
         self._ws = None
         self._ws_bytes = 0
         # workspaces owned by a captured CUDA graph (key = the graph's identity): a graph replays raw pointers, so its
@@ -336,8 +350,40 @@ class ImaginationEngine:
             p.critic = _mlp_params(critic_sd, target_prefix, keep)
         check(self.lib.rlsb_imagine_pack(C.byref(self.ccfg), C.byref(p), self.packed.data_ptr(), _stream()),
               "rlsb_imagine_pack")
+        self._params = p
+        self._pack_version += 1
         # `keep` tensors must outlive the enqueued pack kernels: stream-ordered frees make that safe
         self._keep = keep
+
+    def rollout_cluster_for(self, n: int) -> int:
+        """CTAs per cluster of the persistent rollout for n start states: the configured / RLSB_ROLLOUT_CLUSTER value, else
+        16 while every 128-row block still gets its own GPC (a cluster of 16 fills one; B200 has 8), else 8."""
+        if self.cfg.rollout_cluster:
+            return int(self.cfg.rollout_cluster)
+        if os.environ.get("RLSB_ROLLOUT_CLUSTER"):
+            return int(self.lib.rlsb_rollout_cluster_size())
+        c = 16 if (n + 127) // 128 <= 8 else 8
+        if self.cfg.D > 640 and c == 4:
+            c = 8
+        return c
+
+    def _packed_rollout(self, ccfg) -> torch.Tensor:
+        """the persistent kernel's weight blob for ccfg.rollout_cluster, re-packed when `pack` ran since it was made"""
+        if self._params is None:
+            raise _lib.RlsbError("ImaginationEngine.rollout before pack")
+        c = int(ccfg.rollout_cluster)
+        blob = self.packed_ro.get(c)
+        if blob is None:
+            nbytes = self.lib.rlsb_rollout_packed_bytes(C.byref(ccfg))
+            if nbytes == 0:
+                raise _lib.RlsbError(f"persistent rollout: unsupported config {self.cfg} with a cluster of {c}")
+            blob = self.packed_ro[c] = torch.zeros(nbytes, device=self.device, dtype=torch.uint8)
+        if self._ro_version.get(c) != self._pack_version:
+            pc = self.cfg.to_c()
+            pc.rollout_cluster = c
+            check(self.lib.rlsb_rollout_pack(C.byref(pc), C.byref(self._params), blob.data_ptr(), _stream()), "rlsb_rollout_pack")
+            self._ro_version[c] = self._pack_version
+        return blob
 
     def workspace(self, n: int, pin=None) -> torch.Tensor:
         nbytes = self.lib.rlsb_imagine_workspace_bytes(C.byref(self.ccfg), n)
@@ -360,7 +406,7 @@ class ImaginationEngine:
                 horizon: Optional[int] = None, want_stoch: bool = True, want_actor_raw: bool = False,
                 out: Optional[dict] = None, keep_packed: bool = False, tape: bool = False,
                 seed_device: Optional[torch.Tensor] = None, actor_slots=None, pin=None,
-                last_step_value_only: bool = False) -> dict:
+                last_step_value_only: bool = False, persistent: Optional[bool] = None) -> dict:
         """``pin``: identity of the CUDA graph this call is captured into (see ``workspace``).  ``actor_slots`` (``ACUpdateEngine.actor_slots(n)``): the actor head's activations of steps 0..H-1 are written
         into the update's workspace, so that ``ACUpdateEngine.update(..., actor_forward_done=True)`` skips that forward."""
         cfg = self.cfg
@@ -410,6 +456,18 @@ class ImaginationEngine:
                    _ptr(None if action_noise is None else _f32c(action_noise)), seed, row_offset,
                    _ptr(None if precomp_actions is None else _f32c(precomp_actions)), _ptr(seed_device))
         ws = self.workspace(n, pin)
+        if persistent is None:
+            persistent = self.packed_ro is not None and actor_slots is None and n <= self.persistent_max_rows
+        elif persistent and (self.packed_ro is None or actor_slots is not None):
+            raise _lib.RlsbError("rollout(persistent=True): flat RSSM without parity mode / actor_slots only")
+        self.last_rollout_persistent = bool(persistent)
+        if persistent:
+            ccfg.rollout_cluster = self.rollout_cluster_for(n)
+            blob = self._packed_rollout(ccfg)
+            check(self.lib.rlsb_rollout_fwd(C.byref(ccfg), blob.data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
+                                            _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
+                                            C.byref(co), ws.data_ptr(), _stream()), "rlsb_rollout_fwd")
+            return out
         check(self.lib.rlsb_imagine_fwd(C.byref(ccfg), self.packed.data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")

@@ -382,6 +382,7 @@ def test_actor_forward_reuse_matches_recompute(cuda, graphed):
         a.cuda_graph = graphed
         a.reuse_actor_forward = reuse
         a.reuse_actor_min_rows = 0
+        a._get_engine().persistent_max_rows = 0   # both runs through the chained rollout (the persistent kernel has no actor slots)
         init = State(h0.unsqueeze(0), torch.zeros(1, N, 32, 32, device="cuda"), z0.unsqueeze(0))
         from rl_sandbox_b200 import _lib
         before = _lib.load().rlsb_launch_count(0)

@@ -39,10 +39,14 @@ def rel_rms(x, r, tag=None):
     return e
 
 
-def engine(ops, meta, cuda, case, H):
+def engine(ops, meta, cuda, case, H, mode=None):
+    """mode: "chained" (rlsb_imagine_fwd, one launch per layer), "persistent" (rlsb_rollout_fwd, one launch per rollout)
+    or None = the engine's own choice by size."""
     cfg = ops.ImagineConfig(D=meta["D"], A=meta["A"], discrete=meta["discrete"], layer_norm=meta["layer_norm"],
                             predict_discount=meta["predict_discount"], H=H)
     eng = ops.ImaginationEngine(cfg)
+    if mode is not None:
+        eng.persistent_max_rows = (1 << 30) if mode == "persistent" else 0
     to = lambda sd: {k: v.to(cuda) for k, v in sd.items()}
     eng.pack(to(case["wm"]), to(case["actor"]), to(case["critic"]))
     return eng
@@ -54,21 +58,26 @@ def ops(cuda):
     return _ops
 
 
+MODES = ["chained", "persistent"]
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["c1", "c2", "c2_long", "c1_long"])
-def test_one_step_teacher_forced_vs_reference(ops, cuda, name):
+def test_one_step_teacher_forced_vs_reference(ops, cuda, name, mode):
     c = load_case(name)
     m, gold = c["meta"], c["gold"]
     H, A = m["H"], m["A"]
     N = gold["determ"].shape[1]            # rows whose states the fixture stores (all of them, or the first store_rows)
     gold = {k: (v[:, :N] if v.dim() >= 2 and v.shape[1] == m["N"] else v) for k, v in gold.items()}
     lat, act = c["lat"][:, :N], c["act"][:, :N]
-    eng = engine(ops, m, cuda, c, 1)
+    eng = engine(ops, m, cuda, c, 1, mode)
     # rows = (t, n): start from the reference's state t, use step t's noise
     h = gold["determ"][:H].reshape(H * N, -1)
     z = torch.nn.functional.one_hot(gold["stoch_idx"][:H].long(), 32).float().reshape(H * N, 1024)
     out = eng.rollout(h.to(cuda), z.to(cuda), None, lat.reshape(1, H * N, 1024).to(cuda),
                       act.reshape(1, H * N, A).to(cuda), want_actor_raw=True)
     torch.cuda.synchronize()
+    assert eng.last_rollout_persistent == (mode == "persistent")
     nxt = lambda k: gold[k][1:H + 1].reshape((H * N,) + tuple(gold[k].shape[2:]))
     # (1) exact: sampler on the kernel's own logits
     own = orc.sample_categorical(out["logits"][1].cpu().view(H * N, 32, 32), lat.reshape(H * N, 32, 32))
@@ -96,12 +105,13 @@ def test_one_step_teacher_forced_vs_reference(ops, cuda, name):
     assert torch.equal(out["discounts"][0].cpu(), torch.ones(H * N))   # ts[0] = 1 (dreamer_v2.py:80)
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["c1", "c2", "c2_long", "c1_long"])
-def test_free_running_vs_bf16_oracle(ops, cuda, name):
+def test_free_running_vs_bf16_oracle(ops, cuda, name, mode):
     c = load_case(name)
     m = c["meta"]
     H, N, A = m["H"], m["N"], m["A"]
-    eng = engine(ops, m, cuda, c, H)
+    eng = engine(ops, m, cuda, c, H, mode)
     out = eng.rollout(c["h0"].to(cuda), c["z0"].to(cuda), None, c["lat"].to(cuda), c["act"].to(cuda),
                       want_actor_raw=True)
     ref = orc.imagine(c["wm"], c["actor"], c["critic"], c["h0"], c["z0"], H=H, A=A, discrete=m["discrete"],
