@@ -707,7 +707,8 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
 
   if (warp == 0) {
     // ===================== producer: bulk copies into the stage ring =====================
-    if (lane == 0) {
+    // (whole warp in uniform control flow, one elected lane issues: see the MMA warp)
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t b_slice = b_bytes / static_cast<uint32_t>(cs);
@@ -727,10 +728,11 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             mbar_wait(&ctl->empty[stage], phase ^ 1u);
             uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
             uint8_t* sb = sa + a_bytes;
+            const __nv_bfloat16* wtile = wsrc + static_cast<size_t>(kt_glob) * (static_cast<size_t>(p.RB) * kTileK);
+            if (elect_one()) {
             mbar_expect_tx(&ctl->full[stage], stage_bytes);
             bulk_g2s(sa, asrc + static_cast<size_t>(kt) * (kTileM * kTileK), a_bytes,
                      &ctl->full[stage]);
-            const __nv_bfloat16* wtile = wsrc + static_cast<size_t>(kt_glob) * (static_cast<size_t>(p.RB) * kTileK);
             if (pair) {
               // this CTA's half of the rows of each MMA's column range (<= 256 columns per instruction), at the same
               // offsets in both CTAs: rows [rank n0/2, +n0/2) and, for blocks wider than 256, [n0 + rank n1/2, +n1/2)
@@ -748,6 +750,8 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
                                  reinterpret_cast<const uint8_t*>(wtile) + static_cast<size_t>(rank) * b_slice,
                                  b_slice, &ctl->full[stage], cta_mask);
             }
+            }
+            __syncwarp();
             if (++stage == stages) {
               stage = 0;
               phase ^= 1u;
@@ -757,22 +761,27 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================================
-    if (lane == 0 && pair && rank == 1) {
+    // ===================== MMA issuer =====================================================
+    // The WHOLE warp walks the issue loop in uniform control flow and one elected lane executes the tcgen05 instructions:
+    // descriptors, TMEM addresses and predicates then live in uniform registers.  With the loop inside `if (lane == 0)`
+    // the compiler cannot prove them warp-uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+    // "waterfall" (5 R2UR per MMA) — ~2x the 128-cycle floor of a 128 x 256 x 16 MMA per issue.
+    if (pair && rank == 1) {
       // odd CTA of a pair: no MMAs to issue; tell the even CTA when each of MY stages has landed
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < total_work; w += num_clusters) {
         for (int kt = 0; kt < kt_total; ++kt) {
           mbar_wait(&ctl->full[stage], phase);
-          mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->peer_full[stage]), 0u));
+          if (elect_one()) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->peer_full[stage]), 0u));
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
       }
-    } else if (lane == 0) {
+    } else {
       const int n_chunk0 = p.RB > 256 ? 256 : p.RB;
       const int n_chunk1 = p.RB - n_chunk0;
       const uint32_t mma_m = pair ? 2 * kTileM : kTileM;
@@ -798,36 +807,42 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           const uint64_t adesc = make_smem_desc_sw128(sa);
           const uint64_t bdesc0 = make_smem_desc_sw128(sb);
           const uint64_t bdesc1 = make_smem_desc_sw128(sb + b1_off);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kTileK / 16; ++kk) {
-            const uint32_t acc = (kt > 0 || kk > 0) ? 1u : 0u;
-            // +32 bytes per 16-element K step == +2 in the (addr >> 4) start-address field
-            if constexpr (pair) {
-              umma_bf16_2cta(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
-                             idesc0, acc);
-              if (n_chunk1 > 0)
-                umma_bf16_2cta(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
-                               bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
-            } else {
-              umma_bf16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
-                        idesc0, acc);
-              if (n_chunk1 > 0)
-                umma_bf16(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
-                          bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
+            for (int kk = 0; kk < kTileK / 16; ++kk) {
+              const uint32_t acc = (kt > 0 || kk > 0) ? 1u : 0u;
+              // +32 bytes per 16-element K step == +2 in the (addr >> 4) start-address field
+              if constexpr (pair) {
+                umma_bf16_2cta(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
+                               idesc0, acc);
+                if (n_chunk1 > 0)
+                  umma_bf16_2cta(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
+                                 bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
+              } else {
+                umma_bf16(tmem_d, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2),
+                          idesc0, acc);
+                if (n_chunk1 > 0)
+                  umma_bf16(tmem_d + 256u, adesc + static_cast<uint64_t>(kk * 2),
+                            bdesc1 + static_cast<uint64_t>(kk * 2), idesc1, acc);
+              }
             }
+            // frees the smem stage (in every CTA of the cluster: peers multicast into it) when these MMAs retire
+            if constexpr (pair) umma_commit2_multicast(&ctl->empty[stage], cta_mask);
+            else if (cs == 1) umma_commit(&ctl->empty[stage]);
+            else umma_commit_multicast(&ctl->empty[stage], cta_mask);
           }
-          // frees the smem stage (in every CTA of the cluster: peers multicast into it) when these MMAs retire
-          if constexpr (pair) umma_commit2_multicast(&ctl->empty[stage], cta_mask);
-          else if (cs == 1) umma_commit(&ctl->empty[stage]);
-          else umma_commit_multicast(&ctl->empty[stage], cta_mask);
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
         // accumulator complete -> epilogue (pair: of both CTAs)
-        if constexpr (pair) umma_commit2_multicast(&ctl->tmem_full[buf], cta_mask);
-        else umma_commit(&ctl->tmem_full[buf]);
+        if (elect_one()) {
+          if constexpr (pair) umma_commit2_multicast(&ctl->tmem_full[buf], cta_mask);
+          else umma_commit(&ctl->tmem_full[buf]);
+        }
+        __syncwarp();
       }
     }
   } else {

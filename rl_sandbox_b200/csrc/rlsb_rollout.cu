@@ -267,7 +267,10 @@ struct RCtl {
   float gamma[512];
   float beta[512];
   float2 part[4][kTileM];    // per column-quarter partial (sum, sumsq) of each row
-  float2 xstat[2][kTileM];   // this CTA's per-row (sum, sumsq) of the current LayerNorm layer, read by its peers (DSMEM)
+  // per-row (sum, sumsq) of the current LayerNorm layer from every CTA of this CTA's LayerNorm group: each CTA PUSHES its
+  // partial into slot [its index in the group] of all its peers (st.shared::cluster) before the cluster barrier and reads
+  // only its own shared memory after it (two sets: a fast peer may already push the next layer's)
+  float2 xstat[2][kMaxC][kTileM];
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -280,28 +283,8 @@ __device__ __forceinline__ void tr(unsigned long long* p, int slot) {
   if (p) p[slot] = globaltimer_ns();
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// (volatile, no memory clobber: a run of these loads is issued back to back and their latencies overlap; they stay below
-// the cluster barrier, which is a volatile asm with a memory clobber)
-__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr));
-  return v;
-}
-// sum over the CTAs [g0, g0 + cpg) of the float2 each keeps at shared-memory offset `mine`
-__device__ __forceinline__ float2 dsmem_sum(uint32_t mine, int g0, int cpg) {
-  float s = 0.f, q = 0.f;
-  for (int b = 0; b < cpg; b += 8) {   // eight loads in flight at a time
-    float2 v[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-      v[r] = b + r < cpg ? ld_dsmem_f2(mapa_cluster(mine, static_cast<uint32_t>(g0 + b + r))) : make_float2(0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      s += v[r].x;
-      q += v[r].y;
-    }
-  }
-  return make_float2(s, q);
+__device__ __forceinline__ void st_dsmem_f2(uint32_t cluster_addr, float2 v) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y) : "memory");
 }
 __device__ __forceinline__ void epi_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
@@ -366,9 +349,12 @@ __device__ __forceinline__ void produce(RCtl* ctl, uint8_t* ring, int ring_bytes
       st.pe ^= 1u << s;
       uint8_t* sa = ring + static_cast<size_t>(s) * R.stage_bytes;
       const uint32_t ab = static_cast<uint32_t>(g) * 16384u, bb = static_cast<uint32_t>(g) * b_kt;
-      mbar_expect_tx(&ctl->full[s], ((dbg & 4) ? 0u : ab) + ((dbg & 2) ? 0u : bb));
-      if (!(dbg & 4)) bulk_g2s(sa, a.A[sg] + static_cast<size_t>(kt) * (kTileM * kTileK), ab, &ctl->full[s]);
-      if (!(dbg & 2)) bulk_g2s(sa + R.a_bytes, w + static_cast<size_t>(ktg) * L.NC * 64, bb, &ctl->full[s]);
+      if (elect_one()) {
+        mbar_expect_tx(&ctl->full[s], ((dbg & 4) ? 0u : ab) + ((dbg & 2) ? 0u : bb));
+        if (!(dbg & 4)) bulk_g2s(sa, a.A[sg] + static_cast<size_t>(kt) * (kTileM * kTileK), ab, &ctl->full[s]);
+        if (!(dbg & 2)) bulk_g2s(sa + R.a_bytes, w + static_cast<size_t>(ktg) * L.NC * 64, bb, &ctl->full[s]);
+      }
+      __syncwarp();
       ktg += g;
       if (++s == R.stages) s = 0;
     }
@@ -394,27 +380,32 @@ __device__ __forceinline__ void issue_mma(RCtl* ctl, uint8_t* ring, int ring_byt
       tc_fence_after();
       if (acc == 0u) tr(trp, 1);
       const uint32_t sa = smem_u32(ring + static_cast<size_t>(s) * R.stage_bytes);
-      for (int j = 0; j < g; ++j) {
-        const uint64_t adesc = make_smem_desc_sw128(sa + static_cast<uint32_t>(j) * 16384u);
-        const uint32_t sb = sa + R.a_bytes + static_cast<uint32_t>(j) * b_kt;
-        const uint64_t bdesc0 = make_smem_desc_sw128(sb);
-        const uint64_t bdesc1 = make_smem_desc_sw128(sb + static_cast<uint32_t>(n0) * 128u);
+      if (elect_one()) {
+        for (int j = 0; j < g; ++j) {
+          const uint64_t adesc = make_smem_desc_sw128(sa + static_cast<uint32_t>(j) * 16384u);
+          const uint32_t sb = sa + R.a_bytes + static_cast<uint32_t>(j) * b_kt;
+          const uint64_t bdesc0 = make_smem_desc_sw128(sb);
+          const uint64_t bdesc1 = make_smem_desc_sw128(sb + static_cast<uint32_t>(n0) * 128u);
 #pragma unroll
-        for (int kk = 0; kk < kTileK / 16; ++kk) {
-          if (dbg & 1) break;
-          umma_bf16(tmem_base, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2), idesc0, acc);
-          if (n1 > 0)
-            umma_bf16(tmem_base + 256u, adesc + static_cast<uint64_t>(kk * 2), bdesc1 + static_cast<uint64_t>(kk * 2), idesc1,
-                      acc);
-          acc = 1u;
+          for (int kk = 0; kk < kTileK / 16; ++kk) {
+            if (dbg & 1) break;
+            umma_bf16(tmem_base, adesc + static_cast<uint64_t>(kk * 2), bdesc0 + static_cast<uint64_t>(kk * 2), idesc0, acc);
+            if (n1 > 0)
+              umma_bf16(tmem_base + 256u, adesc + static_cast<uint64_t>(kk * 2), bdesc1 + static_cast<uint64_t>(kk * 2),
+                        idesc1, acc);
+            acc = 1u;
+          }
         }
+        umma_commit(&ctl->empty[s]);
       }
-      umma_commit(&ctl->empty[s]);
+      __syncwarp();
+      acc = 1u;
       if (++s == R.stages) s = 0;
     }
   }
   tr(trp, 2);
-  umma_commit(&ctl->tmem_full);
+  if (elect_one()) umma_commit(&ctl->tmem_full);
+  __syncwarp();
 }
 
 // epilogue warps: bring this rank's bias / gamma / beta into shared memory, then wait for the accumulator
@@ -450,21 +441,29 @@ struct RowStat {
 // LayerNorm statistics of a row whose columns are spread over the 4 column-quarter warps of this CTA and over the
 // `cpg` CTAs [g0, g0 + cpg) of the cluster.  Called by all 512 epilogue threads; contains the cluster barrier that the
 // other warps of the CTA (and the CTAs without work in this layer) match with a bare cluster_sync_all().
-__device__ __forceinline__ RowStat ln_exchange(RCtl* ctl, int cq, int row, float sum, float sq, int g0, int cpg, int n,
-                                               float eps, int par) {
+__device__ __forceinline__ RowStat ln_exchange(RCtl* ctl, int cq, int row, float sum, float sq, int g0, int cpg, int gi,
+                                               int n, float eps, int par, float2* total = nullptr) {
   ctl->part[cq][row] = make_float2(sum, sq);
   epi_bar(2);
   if (cq == 0) {
     const float2 a0 = ctl->part[0][row], a1 = ctl->part[1][row], a2 = ctl->part[2][row], a3 = ctl->part[3][row];
-    ctl->xstat[par][row] = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+    const float2 mine = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+    const uint32_t slot = smem_u32(&ctl->xstat[par][gi][row]);
+    for (int r = 0; r < cpg; ++r) st_dsmem_f2(mapa_cluster(slot, static_cast<uint32_t>(g0 + r)), mine);
   }
   __syncwarp();
   cluster_sync_all();
-  const float2 tot = dsmem_sum(smem_u32(&ctl->xstat[par][row]), g0, cpg);
+  float s = 0.f, q = 0.f;
+  for (int r = 0; r < cpg; ++r) {   // same order in every CTA: identical statistics everywhere
+    const float2 v = ctl->xstat[par][r][row];
+    s += v.x;
+    q += v.y;
+  }
+  if (total) *total = make_float2(s, q);
   RowStat st;
   const float inv_n = 1.0f / static_cast<float>(n);
-  st.mean = tot.x * inv_n;
-  st.rstd = 1.0f / sqrtf(fmaxf(tot.y * inv_n - st.mean * st.mean, 0.f) + eps);
+  st.mean = s * inv_n;
+  st.rstd = 1.0f / sqrtf(fmaxf(q * inv_n - st.mean * st.mean, 0.f) + eps);
   return st;
 }
 
@@ -504,7 +503,7 @@ __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank,
       }
     });
     tr(trp, 4);
-    st = ln_exchange(ctl, cq, row, sum, sq, g0, L.cpg, L.n, eps, par);
+    st = ln_exchange(ctl, cq, row, sum, sq, g0, L.cpg, gi, L.n, eps, par);
     tr(trp, 5);
   }
   const float nmr = -st.mean * st.rstd;
@@ -589,7 +588,7 @@ __device__ __forceinline__ void epi_ln_act_reg(RCtl* ctl, const RLayer& L, int r
   RowStat st{0.f, 1.f};
   if (ln) {
     tr(trp, 4);
-    st = ln_exchange(ctl, cq, row, sum, sq, g0, L.cpg, L.n, eps, par);
+    st = ln_exchange(ctl, cq, row, sum, sq, g0, L.cpg, gi, L.n, eps, par);
     tr(trp, 5);
   }
   const float nmr = -st.mean * st.rstd;
@@ -722,11 +721,12 @@ __device__ __forceinline__ void epi_gru(RCtl* ctl, const RLayer& L, int rank, in
     }
   }
   tr(trp, 4);
-  const RowStat st = ln_exchange(ctl, cq, row, sum, sq, 0, L.cpg, L.n, eps, par);
+  float2 total;
+  const RowStat st = ln_exchange(ctl, cq, row, sum, sq, 0, L.cpg, rank, L.n, eps, par, &total);
   tr(trp, 5);
   if (o.tape_stats && cq == 0 && rank == 0) {
     // the backward pass sums the per-block partials of the chained rollout: hand it the total in block 0
-    o.tape_stats[row] = dsmem_sum(smem_u32(&ctl->xstat[par][row]), 0, L.cpg);
+    o.tape_stats[row] = total;
     for (int b = 1; b < o.tape_nb; ++b) o.tape_stats[static_cast<size_t>(b) * o.m_pad + row] = make_float2(0.f, 0.f);
   }
   const float nmr = -st.mean * st.rstd;
@@ -815,10 +815,11 @@ __device__ __forceinline__ void epi_gru_reg(RCtl* ctl, const RLayer& L, int rank
     }
   }
   tr(trp, 4);
-  const RowStat st = ln_exchange(ctl, cq, row, sum, sq, 0, L.cpg, L.n, eps, par);
+  float2 total;
+  const RowStat st = ln_exchange(ctl, cq, row, sum, sq, 0, L.cpg, rank, L.n, eps, par, &total);
   tr(trp, 5);
   if (o.tape_stats && cq == 0 && rank == 0) {
-    o.tape_stats[row] = dsmem_sum(smem_u32(&ctl->xstat[par][row]), 0, L.cpg);
+    o.tape_stats[row] = total;
     for (int b = 1; b < o.tape_nb; ++b) o.tape_stats[static_cast<size_t>(b) * o.m_pad + row] = make_float2(0.f, 0.f);
   }
   const float nmr = -st.mean * st.rstd;
@@ -930,12 +931,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
   };
   // one contraction layer, every role: `active` = this CTA has a slab in it
   auto run_mainloop = [&](const RLayer& L, const OpA& a, bool active) {
+    // whole warps in uniform control flow; one elected lane issues the bulk copies / tcgen05 instructions (their operands
+    // then live in uniform registers: no ELECT / R2UR.BROADCAST loop around every UBLKCP / UTCHMMA)
     if (warp == 0) {
-      if (active && lane == 0) produce(ctl, ring, ring_bytes, L, rank, a, st, P.dbg, P.kg_max, trp);
-      __syncwarp();
+      if (active) produce(ctl, ring, ring_bytes, L, rank, a, st, P.dbg, P.kg_max, trp);
     } else if (warp == 1) {
-      if (active && lane == 0) issue_mma(ctl, ring, ring_bytes, L, tmem_base, a, st, P.dbg, P.kg_max, trp);
-      __syncwarp();
+      if (active) issue_mma(ctl, ring, ring_bytes, L, tmem_base, a, st, P.dbg, P.kg_max, trp);
     }
   };
 

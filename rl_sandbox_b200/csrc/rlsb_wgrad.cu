@@ -82,8 +82,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
   if (cs > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   const uint32_t tmem_base = ctl->tmem_base;
 
+  // Producer and MMA warp walk their loops as whole warps in uniform control flow; one elected lane issues the bulk
+  // copies / tcgen05 instructions, whose operands then sit in uniform registers (inside `if (lane == 0)` the compiler wraps
+  // every UBLKCP / UTCHMMA in an ELECT + R2UR.BROADCAST loop, several times the cost of the two MMAs a 32-row stage holds).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // resolve the source of every k tile of this chunk once
       const __nv_bfloat16* xsrc[8];
       long long xstride[8];
@@ -106,8 +109,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
         for (int sub = 0; sub < kTileM / kWgRows; ++sub) {
           mbar_wait(&ctl->empty[stage], phase ^ 1u);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
-          mbar_expect_tx(&ctl->full[stage], tx);
           const size_t roff = static_cast<size_t>(sub) * kWgRows * kTileK;   // elements
+          if (elect_one()) {
+          mbar_expect_tx(&ctl->full[stage], tx);
           for (int a = 0; a < na; ++a)
             bulk_g2s(sa + a * kPiece, ysrc + mt * ystride + static_cast<size_t>(a) * (kTileM * kTileK) + roff, kPiece,
                      &ctl->full[stage]);
@@ -119,6 +123,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
               bulk_g2s_multicast(sa + (2 + j) * kPiece, xsrc[j] + mt * xstride[j] + roff, kPiece, &ctl->full[stage],
                                  cta_mask);
           }
+          }
+          __syncwarp();
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const int n0 = nkt > 4 ? 256 : nkt * 64;
       const int n1 = nkt * 64 - n0;
       const uint32_t idesc0 = make_idesc_bf16_mn(128, static_cast<uint32_t>(n0));
@@ -143,23 +149,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
           const uint64_t adesc = make_smem_desc_mn_sw128(sa, kPiece);
           const uint64_t bdesc0 = make_smem_desc_mn_sw128(sa + 2 * kPiece, kPiece);
           const uint64_t bdesc1 = make_smem_desc_mn_sw128(sa + 6 * kPiece, kPiece);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kWgRows / 16; ++kk) {
-            const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-            const uint64_t adv = static_cast<uint64_t>(kk) * (2048u >> 4);   // 16 rows of 128 bytes
-            umma_bf16(tmem_base, adesc + adv, bdesc0 + adv, idesc0, acc);
-            if (n1 > 0) umma_bf16(tmem_base + 256u, adesc + adv, bdesc1 + adv, idesc1, acc);
+            for (int kk = 0; kk < kWgRows / 16; ++kk) {
+              const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+              const uint64_t adv = static_cast<uint64_t>(kk) * (2048u >> 4);   // 16 rows of 128 bytes
+              umma_bf16(tmem_base, adesc + adv, bdesc0 + adv, idesc0, acc);
+              if (n1 > 0) umma_bf16(tmem_base + 256u, adesc + adv, bdesc1 + adv, idesc1, acc);
+            }
+            if (cs == 1) umma_commit(&ctl->empty[stage]);
+            else umma_commit_multicast(&ctl->empty[stage], cta_mask);
           }
+          __syncwarp();
           first = false;
-          if (cs == 1) umma_commit(&ctl->empty[stage]);
-          else umma_commit_multicast(&ctl->empty[stage], cta_mask);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
       }
-      umma_commit(&ctl->tmem_full);
+      if (elect_one()) umma_commit(&ctl->tmem_full);
+      __syncwarp();
     }
   } else {
     // ---- epilogue: TMEM -> fp32 partial tile ---------------------------------------------------
