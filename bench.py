@@ -554,7 +554,11 @@ def main():
                                "imagine(K1, tape) + lambda-return(K2) + K2 bwd + rollout backward(K1 bwd) + K4 + allreduce + AdamW x2",
                        "l2": ("256 MB flush buffer written between timed steps (per-step events)" if flush is not None else
                               "per-step working set (>= 2 GB of rollout outputs) exceeds the 126 MB L2; no explicit flush"),
-                       "metrics_samples": args.metrics_samples, "noise": "Philox4x32-10 on device"},
+                       "metrics_samples": args.metrics_samples, "noise": "Philox4x32-10 on device",
+                       "rollout_kernel": (f"persistent: rlsb_rollout_fwd, one launch per rollout, thread-block clusters of "
+                                          f"{agent._get_engine().rollout_cluster_for(N)} per 128 start states"
+                                          if getattr(agent._get_engine(), "last_rollout_persistent", False) else
+                                          "chained: rlsb_imagine_fwd, one tcgen05 GEMM launch per layer (CTA pairs)")},
             "clocks": clk.summary(),
             "e2e": {"note": "pinned host start states uploaded on a copy stream one step ahead, result read back every step", "value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms.item() / args.steps},

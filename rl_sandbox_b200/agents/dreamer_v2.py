@@ -2,20 +2,24 @@
 
 Same constructor kwargs (the Hydra `_target_`/`_partial_` contract of config/agent/dreamer_v2*.yaml),
 same methods and the same keys in the dict ``train`` returns.  What differs is where the second half
-of ``train`` (dreamer_v2.py:179-211) executes:
+of ``train`` (dreamer_v2.py:179-211) executes, for the flat RSSM (configs 1 and 2):
 
-  imagine_trajectory   -> ONE C-ABI call, rlsb_imagine_fwd (K1: tcgen05 GEMM chain + sampling)
+  imagine_trajectory   -> K1: rlsb_rollout_fwd (ONE persistent kernel, a thread-block cluster per 128 start states;
+                          up to 2048 start states) or rlsb_imagine_fwd (one tcgen05 GEMM launch per layer; the 16 k - 256 k
+                          sweep), with the actor, the RSSM step, the reward / discount / target-critic heads and all draws
   lambda_return,
   cumprod weights,
-  advantage            -> ONE kernel, rlsb_lambda_return_fwd (K2)
-  critic / actor loss  -> torch autograd on the K1 outputs ("next")
-  optimizer steps      -> AdamW with a flat-bucket gradient all-reduce when torch.distributed is up
+  advantage            -> K2: ONE kernel, rlsb_lambda_return_fwd
+  critic / actor loss,
+  both backward passes -> K4: rlsb_ac_update (forward, losses, metrics, backward to parameter gradients); a continuous
+                          actor (rho == 0) adds rlsb_lambda_return_bwd + rlsb_imagine_bwd for d loss / d actions
+  optimizer steps      -> fused AdamW on one flat actor + critic gradient bucket (a single all-reduce when
+                          torch.distributed is up)
 
-Gradient flow: with a discrete actor rho == 1 and nothing differentiates through the rollout
-(hard part 3), so K1 runs under no_grad exactly like the reference's values.  With a
-continuous actor (rho == 0) the dynamics-backprop loss needs d(rollout)/d(actor); K1 has no backward
-yet, so that configuration differentiates through a torch replay of the rollout (``_imagine_autograd``,
-CUDA tensors, same modules) — recorded in DESIGN.md as the open item of this round.
+No torch autograd runs on that path.  The slotted world model (config 3) has K1's forward (mixer blocks included) but not
+its backward / K4: its behaviour half differentiates through ``_imagine_autograd`` / ``_behaviour_losses`` — the reference's
+op sequence on CUDA tensors, replayed from a CUDA graph — as does a continuous actor with rssm_dim > 512 (no shipped
+config).  Everything raises without a CUDA device and librlsb.so: there is no CPU path.
 """
 import os
 import typing as t
