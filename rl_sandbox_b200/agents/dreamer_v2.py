@@ -83,7 +83,9 @@ class DreamerV2(RlAgent):
         self.cuda_graph = True
         self.cuda_graph_max_rows = int(os.environ.get('RLSB_GRAPH_MAX_ROWS', 32768))
         self.reuse_actor_forward = os.environ.get('RLSB_ACTOR_REUSE', '1') != '0'   # K1's actor activations feed K4
-        self.reuse_actor_min_rows = 2048   # below: launch-latency bound, the extra stores of the rollout cost more (800 rows: +2 %)
+        # below: launch-latency bound — the persistent rollout kernel (up to ImaginationEngine.persistent_max_rows = 2048
+        # start states; it has no actor slots) is the faster path, and the update recomputes the actor forward
+        self.reuse_actor_min_rows = 2049
         self.max_rows_per_pass = 131072   # start states per pass of the fused update (HBM sizing, _fused_step_chunked)
         # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
         # T sequential steps of small kernels — thousands of launches whose CPU dispatch cost exceeds their GPU time)
