@@ -332,6 +332,14 @@ class DreamerV2(RlAgent):
         from rl_sandbox_b200 import ops
         if self._can_fuse_ac():
             return self._behaviour_update_fused(initial_states, noise)
+        if not getattr(self, '_warned_torch_behaviour', False):
+            import warnings
+            self._warned_torch_behaviour = True
+            why = ("the slotted world model has no rollout backward / fused update kernels" if not self._flat_wm() else
+                   "fused_ac_update / f16 / device settings" if (not self.fused_ac_update or self.is_f16) else
+                   f"a continuous actor with rssm_dim = {self.world_model.rssm_dim} > 512 has no rollout backward kernel")
+            warnings.warn(f"DreamerV2.behaviour_update: critic / actor losses and their backward pass run as torch autograd on "
+                          f"CUDA tensors ({why}); the librlsb kernels cover the rollout forward only", stacklevel=2)
         # torch-replay rollouts only (rho != 1): their noise comes from torch's graph-safe generator
         only_offset = noise is None or set(noise) <= {'row_offset'}   # (the torch replay draws from torch's generator)
         graphable = (self.cuda_graph_wm and only_offset and not self.is_f16 and initial_states.determ.is_cuda

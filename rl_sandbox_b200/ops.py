@@ -28,6 +28,11 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32 or not t.is_cuda:
         raise _lib.RlsbError(f"expected a CUDA float32 tensor, got {t.dtype} on {t.device}")
+    # the kernels are enqueued on the CURRENT device's stream (_stream) with per-device function attributes: a tensor
+    # living on another GPU of the process would be a silent cross-device launch
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise _lib.RlsbError(f"tensor on {t.device} while the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                             f"wrap the call in torch.cuda.device({t.device.index})")
     return t.contiguous()
 
 

@@ -11,6 +11,8 @@ WANT = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct"]
 
 rows = list(csv.reader(l for l in open(sys.argv[1]) if not l.startswith("==")))
+if len(rows) < 3:
+    sys.exit(f"{sys.argv[1]}: no kernel was captured (empty ncu export)")
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 for r in rows[2:]:

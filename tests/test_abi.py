@@ -97,3 +97,26 @@ def test_staged_output_switch_is_queryable_without_a_device():
     assert cur in (0, 1)
     assert lib.rlsb_set_staged_output(0) == 0 and lib.rlsb_set_staged_output(1) == 1
     lib.rlsb_set_staged_output(cur)
+
+
+def test_persistent_rollout_plan_sizes_without_a_device():
+    """rlsb_rollout_packed_bytes is host arithmetic (per-CTA weight slabs of the persistent rollout kernel): every cluster
+    size yields a blob close to the chained one's weights (same matrices, re-ordered and padded per CTA); unsupported
+    combinations are refused with 0 — slotted RSSM, split-operand mode, GRU slices wider than the epilogue's register plan."""
+    lib = _lib.load()
+    assert lib.rlsb_rollout_cluster_size() in (4, 8, 16)
+    c1 = dict(D=1024, groups=32, classes=32, A=17, hidden=400, discrete=1, layer_norm=1, predict_discount=1, with_critic=1, H=15,
+              discount_nan_on_tie=1)
+    c2 = dict(D=200, groups=32, classes=32, A=12, hidden=400, discrete=0, layer_norm=0, predict_discount=0, with_critic=1, H=15,
+              discount_nan_on_tie=1, with_backward=1)
+    chained = lib.rlsb_imagine_packed_bytes(C.byref(_lib.ImagineCfg(**c1)))
+    for cs in (8, 16):
+        n = lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, rollout_cluster=cs)))
+        assert 0.95 * chained < n < 1.15 * chained, (cs, n, chained)
+    assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, rollout_cluster=4))) == 0   # 256 hidden units per CTA
+    sizes = [lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c2, rollout_cluster=cs))) for cs in (4, 8, 16)]
+    assert all(s > 7_000_000 for s in sizes) and max(sizes) < 1.1 * min(sizes)         # same matrices, a little padding
+    assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, rollout_cluster=0))) > 0  # 0 = library default
+    assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, parity=1))) == 0
+    assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**dict(c2, with_backward=0), slots=4, attention_blocks=3))) == 0
+    assert lib.rlsb_rollout_fwd(None, None, 0, None, None, None, None, None, None, None) < 0
