@@ -465,7 +465,8 @@ template <int ACT, bool LN>
 __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, int cq, int my_chunks, int n_valid,
                                          int col0, int row, int lane, bool row_ok, uint32_t s_gam, uint32_t s_bet,
                                          uint32_t s_part, uint32_t s_acc, float rstd,
-                                         const __nv_bfloat16* pbase, __nv_bfloat16* obase, int n_fast) {
+                                         const __nv_bfloat16* pbase, __nv_bfloat16* obase, int n_fast, uint32_t xs) {
+  // xs != 0: this thread's chunk i of the saved image was prefetched to shared memory at xs + i * 8192 (see the kernel)
   float s1 = 0.f, s2 = 0.f;
   const bool colsum = LN && p.col_part != nullptr;
   // ---- complete chunks of a warp whose 32 rows are all valid: software-pipelined sweep (TMEM and the saved x_hat of a
@@ -478,10 +479,14 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     const __nv_bfloat16* q = pbase + tile0;
     __nv_bfloat16* o = obase + tile0;
     uint32_t sg = s_gam + 32u * cq, se = s_bet + 32u * cq, sa = s_acc + 32u * cq;
+    uint32_t xg = xs;
     f32x2 s1a = pk2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
     done = tmem_sweep_groups_g(
         tmem_d + static_cast<uint32_t>(cq * 8), n_fast,
-        [&](int j) { return *reinterpret_cast<const uint4*>(q + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0)); },
+        [&](int j) {
+          return xs ? lds128u(xg + 8192u * static_cast<uint32_t>(j))
+                    : *reinterpret_cast<const uint4*>(q + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0));
+        },
         [&](const uint32_t (&r)[8], const uint4& pb, auto J, uint32_t t) {
           constexpr int j = decltype(J)::value;
           f32x2 da[4], dxh[4], pre[4];
@@ -533,6 +538,7 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
           sg += 512u;
           se += 512u;
           sa += 512u;
+          xg += 4u * 8192u;
         });
     if (LN) {
       float a, b;
@@ -549,7 +555,7 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);
     const int oc = col0 + c;   // column inside the whole row (col0 != 0 only without LayerNorm)
     const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
-    const uint4 pb = *reinterpret_cast<const uint4*>(pbase + off);
+    const uint4 pb = xs ? lds128u(xs + 8192u * static_cast<uint32_t>(i)) : *reinterpret_cast<const uint4*>(pbase + off);
     tmem_ld_wait();
     float da[8], dxh[8], pre[8];
     bwd_chunk<ACT, LN>(r, pb, c, n_valid, s_gam, s_bet, row_ok, da, dxh, pre);
@@ -588,7 +594,7 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
     epi_bar(2);
     const float2 a0 = lds64(s_part + 8u * row), a1 = lds64(s_part + 8u * (kTileM + row)),
                  a2 = lds64(s_part + 8u * (2 * kTileM + row)), a3 = lds64(s_part + 8u * (3 * kTileM + row));
-    const float inv_n = 1.0f / static_cast<float>(n_valid);
+    const float inv_n = n_valid == p.N ? p.inv_n : 1.0f / static_cast<float>(n_valid);
     const float m1 = ((a0.x + a1.x) + (a2.x + a3.x)) * inv_n;
     const float m2 = ((a0.y + a1.y) + (a2.y + a3.y)) * inv_n;
     const float nm1r = -m1 * rstd, nm2r = -m2 * rstd;
@@ -596,9 +602,13 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
       const __nv_bfloat16* q = pbase + tile0;
       __nv_bfloat16* o = obase + tile0;
       const f32x2 rstd2 = pk2(rstd, rstd), nm1r2 = pk2(nm1r, nm1r), nm2r2 = pk2(nm2r, nm2r);
+      uint32_t xg = xs;
       tmem_sweep_groups_g(
           tmem_d + static_cast<uint32_t>(cq * 8), done,
-          [&](int j) { return *reinterpret_cast<const uint4*>(q + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0)); },
+          [&](int j) {
+            return xs ? lds128u(xg + 8192u * static_cast<uint32_t>(j))
+                      : *reinterpret_cast<const uint4*>(q + (j >> 1) * (kTileM * kTileK) + ((j & 1) ? pos1 : pos0));
+          },
           [&](const uint32_t (&r)[8], const uint4& pb, auto J, uint32_t) {
             constexpr int j = decltype(J)::value;
             float f[8], y[8];
@@ -613,6 +623,7 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
           [&]() {
             q += 2 * (kTileM * kTileK);
             o += 2 * (kTileM * kTileK);
+            xg += 4u * 8192u;
           });
     }
     for (int i = done; i < my_chunks; ++i) {
@@ -622,7 +633,7 @@ __device__ __forceinline__ void bwd_tile(const GemmParams& p, uint32_t tmem_d, i
       tmem_ld8(tmem_d + static_cast<uint32_t>(c), r);   // dxh (0 in invalid rows / columns)
       const int oc = col0 + c;
       const size_t off = static_cast<size_t>(oc >> 6) * (kTileM * kTileK) + ((((oc & 63) >> 3) ^ (row & 7)) << 3);
-      const uint4 pb = *reinterpret_cast<const uint4*>(pbase + off);
+      const uint4 pb = xs ? lds128u(xs + 8192u * static_cast<uint32_t>(i)) : *reinterpret_cast<const uint4*>(pbase + off);
       tmem_ld_wait();
       float pre[8], o[8];
       unpack_bf16x8(pb, pre);
@@ -661,7 +672,8 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
   uint8_t* stage_out = smem + static_cast<size_t>(stages) * stage_bytes;
   uint8_t* stage_pre = stage_out + 32768;
   const uint32_t staging_bytes = p.staged_out ? (EPI == EPI_LN_ACT_SAVE ? 65536u : 32768u) : 0u;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(stage_out + staging_bytes);
+  uint8_t* xbuf = stage_out + staging_bytes;   // EPI_BWD: per-thread slots of the saved image (GemmParams::xbuf_bytes)
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(xbuf + (EPI == EPI_BWD ? static_cast<uint32_t>(p.xbuf_bytes) : 0u));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -871,6 +883,28 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       for (int i = tid_e; i < 2 * p.RB; i += kEpiThreads) sts32(s_acc + 4u * i, 0.f);
       epi_bar(3);
     };
+    // EPI_BWD: the saved x_hat / pre-activation chunks this thread needs (both passes) arrive in shared memory by cp.async,
+    // issued one tile ahead — their latency (52 % of the epilogue warps' stall samples were long-scoreboard waits on these
+    // 16-byte loads, profiles/r02_d_bwd_*) hides behind the previous tile's pass 2 and this tile's main loop
+    const uint32_t xs = (EPI == EPI_BWD && p.xbuf_bytes > 0) ? smem_u32(xbuf) + static_cast<uint32_t>(tid_e) * 16u : 0u;
+    auto prefetch_saved = [&](int wn) {
+      if (xs == 0u || wn >= total_work) return;
+      int mt, gn;
+      decode_work(p, wn, cs, rank, mt, gn);
+      if (mt >= p.m_tiles) return;
+      const int gg = gn / p.NB;
+      const int nv = min(p.RB, p.N);
+      const __nv_bfloat16* src = p.bwd_pre + static_cast<size_t>(gg) * p.out_bf16_group_stride +
+                                 static_cast<size_t>(mt) * (p.out_kpad >> 6) * (kTileM * kTileK) + static_cast<size_t>(row) * kTileK;
+      for (int i = 0; i < my_chunks; ++i) {
+        const int c = (cq + 4 * i) * 8;
+        if (c >= nv) break;
+        cp_async16(xs + 8192u * static_cast<uint32_t>(i),
+                   src + static_cast<size_t>(c >> 6) * (kTileM * kTileK) + ((((c & 63) >> 3) ^ (row & 7)) << 3));
+      }
+      cp_async_commit();
+    };
+    if (EPI == EPI_BWD) prefetch_saved(cluster_id);
     int it = 0;
     uint32_t out_ph = 0;        // staged output: slot parity, carried across tiles
     bool out_pending = false;   //                a bulk store of this CTA is in flight
@@ -920,9 +954,10 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
                              static_cast<size_t>(m_tile) * (p.out_kpad >> 6) * (kTileM * kTileK) +
                              static_cast<size_t>(row) * kTileK;
           const float rs = (has_ln && row_ok) ? __ldg(p.bwd_rstd + static_cast<size_t>(g) * m_pad + m) : 0.f;
+          if (xs) cp_async_wait_all();
 #define RLSB_B(ACT, LN) \
   bwd_tile<ACT, LN>(p, tmem_d, cq, my_chunks, n_valid, col0, row, lane, row_ok, s_gam, s_bet, s_part, s_acc, rs, \
-                    p.bwd_pre + img, p.out_bf16 + img, n_fast)
+                    p.bwd_pre + img, p.out_bf16 + img, n_fast, xs)
           if (has_ln) {
             if (p.act == ACT_ELU) RLSB_B(ACT_ELU, true);
             else RLSB_B(ACT_NONE, true);
@@ -948,6 +983,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           if (pair && rank == 1) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->tmem_empty[buf]), 0u));
           else mbar_arrive(&ctl->tmem_empty[buf]);
         }
+        prefetch_saved(w + num_clusters);
         continue;
       }
 
@@ -1116,7 +1152,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             if (cq == 0 && tile_ok)
               reinterpret_cast<float2*>(p.stats)[static_cast<size_t>(gnb) * m_pad + m] = make_float2(tsum, tsq);
           } else {
-            const float inv_n = 1.0f / static_cast<float>(n_valid);
+            const float inv_n = n_valid == p.N ? p.inv_n : 1.0f / static_cast<float>(n_valid);
             mean = tsum * inv_n;
             const float var = fmaxf(tsq * inv_n - mean * mean, 0.f);
             rstd = 1.0f / sqrtf(var + p.ln_eps);
@@ -1202,6 +1238,7 @@ int g_pair = 2;   // cta_group::2 for clusters of 2 (1: only n-blocks <= 256 col
 int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
 int g_staged = 1;         // full-row epilogues write their output through shared memory + bulk copies (RLSB_STAGED=0: 16-byte stores)
 int g_staged_f32 = 1;     // fp32 row-major outputs go through shared-memory slabs and leave as full lines (RLSB_STAGED_F32=0)
+int g_bwd_xbuf = 1;       // EPI_BWD prefetches its saved x_hat chunks into shared memory with cp.async (RLSB_BWD_XBUF=0: global loads)
 
 }  // namespace
 
@@ -1226,6 +1263,7 @@ int init_device_info() {
     if (const char* env = getenv("RLSB_PAIR")) g_pair = atoi(env);   // 0: multicast only, 1: pairs for RB <= 256, 2: all
     if (const char* env = getenv("RLSB_STAGED")) g_staged = atoi(env);
     if (const char* env = getenv("RLSB_STAGED_F32")) g_staged_f32 = atoi(env);
+    if (const char* env = getenv("RLSB_BWD_XBUF")) g_bwd_xbuf = atoi(env);
   }
   return 0;
 }
@@ -1270,15 +1308,24 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
                           (p.out_group_stride % 4) == 0;
   const bool staged = staged_f32 || (g_staged && (epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB == 1);
   const int staging_bytes = staged ? (epilogue == EPI_LN_ACT_SAVE ? 65536 : 32768) : 0;
-  const int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256 - staging_bytes;
+  int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256 - staging_bytes;
   static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
+  // EPI_BWD: a 16-byte slot per epilogue thread and chunk for the saved image (two stages must still fit)
+  // (latency-bound launches only — a tile or two per CTA: dino step 5.52 -> 5.30 ms; with many tiles per CTA the loads of
+  // the next tile already overlap and the deeper stage ring is worth more: sweep step 33.5 vs 34.0 ms; RLSB_BWD_XBUF=2 forces it)
+  int xbuf_bytes = (epilogue == EPI_BWD && p.NB == 1 && g_bwd_xbuf &&
+                    (g_bwd_xbuf > 1 || p.m_tiles * p.G <= 2 * g_num_sms)) ? (p.RB >> 5) * kEpiThreads * 16 : 0;
+  if (xbuf_bytes > 0 && (budget - xbuf_bytes) / stage_bytes < 2) xbuf_bytes = 0;
+  budget -= xbuf_bytes;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return -6;
   const int nbuf = p.RB <= 256 ? 2 : 1;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + staging_bytes + sizeof(SmemCtl) + 1024;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + staging_bytes + xbuf_bytes + sizeof(SmemCtl) + 1024;
   GemmParams q = p;
   q.staged_out = staged ? 1 : 0;
+  q.xbuf_bytes = xbuf_bytes;
+  q.inv_n = 1.0f / static_cast<float>(p.N);
   const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
   int clusters = g_num_sms / cs;
   if (total_work < clusters) clusters = total_work;

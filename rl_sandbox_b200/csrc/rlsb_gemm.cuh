@@ -75,6 +75,12 @@ struct GemmParams {
   // ---- set by launch_gemm (callers leave it 0): the full-row epilogue assembles each 128 x 64 output tile (16 KB, contiguous
   //      in the packed image) in shared memory and writes it with one bulk copy instead of 16-byte stores scattered over 32 rows
   int staged_out;
+  // ---- set by launch_gemm: 1 / N as the host's correctly rounded fp32 quotient (== the device's IEEE division, without the
+  //      FCHK + MUFU.RCP + Newton sequence every epilogue thread would run per tile); used when a block holds all N columns
+  float inv_n;
+  // ---- set by launch_gemm (EPI_BWD): bytes of the shared-memory buffer the epilogue threads prefetch their saved x_hat /
+  //      pre-activation chunks into with cp.async (0 = the epilogue reads them from global memory, twice)
+  int xbuf_bytes;
 };
 
 // Launch on `stream`; returns cudaError_t as int (0 = ok) or a negative argument error.

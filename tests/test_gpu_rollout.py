@@ -82,9 +82,10 @@ def test_persistent_matches_chained(ops, cuda, name):
         assert rel_rms(pers["actor_raw"][0], chained["actor_raw"][0]) < 2e-3
 
 
-@pytest.mark.parametrize("n", [1, 127, 129, 800])
+@pytest.mark.parametrize("n", [1, 127, 129, 800, 1024, 2048])
 def test_persistent_ragged_row_counts_vs_oracle(ops, cuda, n):
-    """row blocks with padding rows, a single row, the configured 16 x 50 = 800 start states (7 clusters)"""
+    """row blocks with padding rows, a single row, the configured 16 x 50 = 800 start states (7 clusters of 16), the last size
+    with clusters of 16 (1024: 8 row blocks) and the engine's upper limit (2048: 16 clusters of 8)"""
     c = load_case("c2")
     m = c["meta"]
     H = 3
@@ -93,7 +94,7 @@ def test_persistent_ragged_row_counts_vs_oracle(ops, cuda, n):
     g = torch.Generator().manual_seed(n)
     lat, act = torch.rand(H, n, 1024, generator=g), torch.randn(H, n, m["A"], generator=g)
     out = eng.rollout(h0.to(cuda), z0.to(cuda), None, lat.to(cuda), act.to(cuda), horizon=H)
-    assert eng.last_rollout_persistent
+    assert eng.last_rollout_persistent and eng.rollout_cluster_for(n) == (16 if n <= 1024 else 8)
     ref = orc.imagine(c["wm"], c["actor"], c["critic"], h0, z0, H=H, A=m["A"], discrete=False, predict_discount=False,
                       latent_uniforms=lat, action_noise=act, bf16=True)
     same = (out["stoch_idx"].cpu().long() == ref["stoch_idx"]).all(-1).cumprod(0).bool()
