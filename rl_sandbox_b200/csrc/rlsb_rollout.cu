@@ -333,6 +333,13 @@ __device__ __forceinline__ Ring make_ring(int ring_bytes, int NC, int kg_max) {
   return r;
 }
 
+// k tiles of the n-th group of a K segment of `left` remaining tiles: the first two groups of a layer are single tiles (the
+// first MMA starts after one tile's transfer, not after four), later ones fill the stage
+__device__ __forceinline__ int group_tiles(int n, int kg, int left) {
+  const int g = n < 2 ? 1 : kg;
+  return g < left ? g : left;
+}
+
 // producer thread: stream the A tiles of this row block and this CTA's weight slab through the stage ring
 __device__ __forceinline__ void produce(RCtl* ctl, uint8_t* ring, int ring_bytes, const RLayer& L, int rank, const OpA& a,
                                         Roles& st, int dbg, int kg_max, unsigned long long* trp) {
@@ -341,10 +348,10 @@ __device__ __forceinline__ void produce(RCtl* ctl, uint8_t* ring, int ring_bytes
   tr(trp, 0);
   const __nv_bfloat16* w = L.W + static_cast<size_t>(rank) * L.kt * L.NC * 64;
   fence_proxy_async_all();   // the images were written with ordinary stores by other CTAs before the cluster barrier
-  int s = 0, ktg = 0;
+  int s = 0, ktg = 0, ng = 0;
   for (int sg = 0; sg < a.nseg; ++sg) {
-    for (int kt = 0; kt < a.kt[sg]; kt += R.kg) {
-      const int g = min(R.kg, a.kt[sg] - kt);
+    for (int kt = 0, g = 0; kt < a.kt[sg]; kt += g, ++ng) {
+      g = group_tiles(ng, R.kg, a.kt[sg] - kt);
       mbar_wait(&ctl->empty[s], (st.pe >> s) & 1u);
       st.pe ^= 1u << s;
       uint8_t* sa = ring + static_cast<size_t>(s) * R.stage_bytes;
@@ -370,11 +377,11 @@ __device__ __forceinline__ void issue_mma(RCtl* ctl, uint8_t* ring, int ring_byt
   const uint32_t idesc0 = make_idesc_bf16(kTileM, static_cast<uint32_t>(n0));
   const uint32_t idesc1 = n1 > 0 ? make_idesc_bf16(kTileM, static_cast<uint32_t>(n1)) : 0u;
   tc_fence_after();   // the previous layer's epilogue has drained TMEM (cluster barrier in between)
-  int s = 0;
+  int s = 0, ng = 0;
   uint32_t acc = 0u;
   for (int sg = 0; sg < a.nseg; ++sg) {
-    for (int kt = 0; kt < a.kt[sg]; kt += R.kg) {
-      const int g = min(R.kg, a.kt[sg] - kt);
+    for (int kt = 0, g = 0; kt < a.kt[sg]; kt += g, ++ng) {
+      g = group_tiles(ng, R.kg, a.kt[sg] - kt);
       mbar_wait(&ctl->full[s], (st.pf >> s) & 1u);
       st.pf ^= 1u << s;
       tc_fence_after();
@@ -482,6 +489,11 @@ struct LnActOut {
   int out_kpad;
 };
 
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {   // 32-byte aligned shared-memory parameters
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank, bool ln, const LnActOut& o, uint32_t tmem_d,
                                            int cq, int row, bool row_ok, float eps, int par, unsigned long long* trp) {
   const int gi = rank % L.cpg, g0 = rank - gi;
@@ -490,20 +502,34 @@ __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank,
   const int mine = n_chunks > cq ? (n_chunks - cq + 3) >> 2 : 0;
   RowStat st{0.f, 1.f};
   if (ln) {
-    float sum = 0.f, sq = 0.f;
+    float sum = 0.f, sq = 0.f, sumb = 0.f, sqb = 0.f;
     tmem_sweep(tmem_d, cq, mine, [&](const uint32_t (&r)[8], int i) {
       const int c = (cq + 4 * i) * 8;
+      if (c >= width) return;
+      float b[8];
+      ld8f(&ctl->bias[c], b);
+      if (c + 8 <= width) {   // complete chunk: no per-element predicates, two accumulator pairs
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (c + j < width) {
-          const float v = __uint_as_float(r[j]) + ctl->bias[c + j];
-          sum += v;
-          sq = fmaf(v, v, sq);
+        for (int j = 0; j < 8; j += 2) {
+          const float v0 = __uint_as_float(r[j]) + b[j], v1 = __uint_as_float(r[j + 1]) + b[j + 1];
+          sum += v0;
+          sumb += v1;
+          sq = fmaf(v0, v0, sq);
+          sqb = fmaf(v1, v1, sqb);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (c + j < width) {
+            const float v = __uint_as_float(r[j]) + b[j];
+            sum += v;
+            sq = fmaf(v, v, sq);
+          }
         }
       }
     });
     tr(trp, 4);
-    st = ln_exchange(ctl, cq, row, sum, sq, g0, L.cpg, gi, L.n, eps, par);
+    st = ln_exchange(ctl, cq, row, sum + sumb, sq + sqb, g0, L.cpg, gi, L.n, eps, par);
     tr(trp, 5);
   }
   const float nmr = -st.mean * st.rstd;
@@ -511,21 +537,31 @@ __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank,
   tmem_sweep(tmem_d, cq, mine, [&](const uint32_t (&r)[8], int i) {
     const int c = (cq + 4 * i) * 8;
     if (c >= width) return;
-    float y[8], x[8];
+    float y[8], x[8], b[8];
+    ld8f(&ctl->bias[c], b);
+    if (ln) {
+      float g[8], be[8];
+      ld8f(&ctl->gamma[c], g);
+      ld8f(&ctl->beta[c], be);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = __uint_as_float(r[j]) + ctl->bias[c + j];
-      if (ln) {
-        v = fmaf(v, st.rstd, nmr);
-        x[j] = v;
-        v = fmaf(v, ctl->gamma[c + j], ctl->beta[c + j]);
-      } else {
-        x[j] = v;
+      for (int j = 0; j < 8; ++j) {
+        x[j] = fmaf(__uint_as_float(r[j]) + b[j], st.rstd, nmr);
+        y[j] = elu1(fmaf(x[j], g[j], be[j]));
       }
-      y[j] = elu1(v);
-      if (c + j >= width || (save && !row_ok)) {
-        y[j] = 0.f;
-        x[j] = 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[j] = __uint_as_float(r[j]) + b[j];
+        y[j] = elu1(x[j]);
+      }
+    }
+    if (c + 8 > width || (save && !row_ok)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c + j >= width || (save && !row_ok)) {
+          y[j] = 0.f;
+          x[j] = 0.f;
+        }
       }
     }
     const size_t off = pk_off(row, col0 + c);
@@ -547,11 +583,6 @@ __device__ __forceinline__ void epi_ln_act(RCtl* ctl, const RLayer& L, int rank,
 __device__ __forceinline__ void tie8(uint32_t (&r)[8]) {
   asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
 }
-__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {   // 32-byte aligned shared-memory parameters
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
-
 // epi_ln_act with the thread's accumulator columns held in registers between the statistics and the output pass: every
 // TMEM load of the thread is in flight at once and TMEM is read once (MAXCH = 8-column chunks per thread, at most)
 template <int MAXCH>
@@ -708,13 +739,17 @@ __device__ __forceinline__ void epi_gru(RCtl* ctl, const RLayer& L, int rank, in
     tmem_ld8(tmem_d + static_cast<uint32_t>(c), r0);
     tmem_ld8(tmem_d + static_cast<uint32_t>(wpad + c), r1);
     tmem_ld8(tmem_d + static_cast<uint32_t>(2 * wpad + c), r2);
+    float b0[8], b1[8], b2[8];
+    ld8f(&ctl->bias[c], b0);
+    ld8f(&ctl->bias[wpad + c], b1);
+    ld8f(&ctl->bias[2 * wpad + c], b2);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (c + j < width) {
-        const float a = __uint_as_float(r0[j]) + ctl->bias[c + j];
-        const float b = __uint_as_float(r1[j]) + ctl->bias[wpad + c + j];
-        const float u = __uint_as_float(r2[j]) + ctl->bias[2 * wpad + c + j];
+        const float a = __uint_as_float(r0[j]) + b0[j];
+        const float b = __uint_as_float(r1[j]) + b1[j];
+        const float u = __uint_as_float(r2[j]) + b2[j];
         sum += (a + b) + u;
         sq = fmaf(a, a, fmaf(b, b, fmaf(u, u, sq)));
       }
@@ -740,21 +775,44 @@ __device__ __forceinline__ void epi_gru(RCtl* ctl, const RLayer& L, int rank, in
     tmem_ld8(tmem_d + static_cast<uint32_t>(wpad + c), r1);
     tmem_ld8(tmem_d + static_cast<uint32_t>(2 * wpad + c), r2);
     tmem_ld_wait();
-    float y[8];
+    const bool tape = o.tape_pre != nullptr && row_ok;
+    float gate[8], y[8];
+    {   // reset gate
+      float b[8], g[8], be[8];
+      ld8f(&ctl->bias[c], b);
+      ld8f(&ctl->gamma[c], g);
+      ld8f(&ctl->beta[c], be);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float pr = __uint_as_float(r0[j]) + ctl->bias[c + j];
-      const float pc = __uint_as_float(r1[j]) + ctl->bias[wpad + c + j];
-      const float pu = __uint_as_float(r2[j]) + ctl->bias[2 * wpad + c + j];
-      if (o.tape_pre && row_ok && c + j < width) {
-        o.tape_pre[col0 + c + j] = pr;
-        o.tape_pre[D + col0 + c + j] = pc;
-        o.tape_pre[2 * D + col0 + c + j] = pu;
+      for (int j = 0; j < 8; ++j) {
+        const float p = __uint_as_float(r0[j]) + b[j];
+        if (tape && c + j < width) o.tape_pre[col0 + c + j] = p;
+        gate[j] = rowops::fast_sigmoid(fmaf(fmaf(p, st.rstd, nmr), g[j], be[j]));
       }
-      const float r = rowops::fast_sigmoid(fmaf(fmaf(pr, st.rstd, nmr), ctl->gamma[c + j], ctl->beta[c + j]));
-      const float cand = rowops::fast_tanh(r * fmaf(fmaf(pc, st.rstd, nmr), ctl->gamma[wpad + c + j], ctl->beta[wpad + c + j]));
-      const float u = rowops::fast_sigmoid(fmaf(fmaf(pu, st.rstd, nmr), ctl->gamma[2 * wpad + c + j], ctl->beta[2 * wpad + c + j]) - 1.0f);
-      y[j] = (row_ok && c + j < width) ? u * cand + (1.0f - u) * hp[j] : 0.f;
+    }
+    {   // candidate
+      float b[8], g[8], be[8];
+      ld8f(&ctl->bias[wpad + c], b);
+      ld8f(&ctl->gamma[wpad + c], g);
+      ld8f(&ctl->beta[wpad + c], be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p = __uint_as_float(r1[j]) + b[j];
+        if (tape && c + j < width) o.tape_pre[D + col0 + c + j] = p;
+        gate[j] = rowops::fast_tanh(gate[j] * fmaf(fmaf(p, st.rstd, nmr), g[j], be[j]));
+      }
+    }
+    {   // update gate and the convex update
+      float b[8], g[8], be[8];
+      ld8f(&ctl->bias[2 * wpad + c], b);
+      ld8f(&ctl->gamma[2 * wpad + c], g);
+      ld8f(&ctl->beta[2 * wpad + c], be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p = __uint_as_float(r2[j]) + b[j];
+        if (tape && c + j < width) o.tape_pre[2 * D + col0 + c + j] = p;
+        const float u = rowops::fast_sigmoid(fmaf(fmaf(p, st.rstd, nmr), g[j], be[j]) - 1.0f);
+        y[j] = (row_ok && c + j < width) ? u * gate[j] + (1.0f - u) * hp[j] : 0.f;
+      }
     }
     if (row_ok) {
       if (c + 8 <= width) {
