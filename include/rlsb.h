@@ -267,6 +267,15 @@ int rlsb_rollout_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* pa
 int rlsb_rollout_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const float* h0, const float* z0,
                      const float* logits0, const rlsb_noise* noise, const rlsb_imagine_out* out, void* workspace,
                      void* stream);
+/* rlsb_imagine_bwd (the backward of the rollout w.r.t. the sampled actions: agents/dreamer_v2.py:199-207 through
+ * agents/dreamer/rssm.py:176-193, common.py:69-81, rssm.py:34-37) as ONE persistent kernel on the same cluster machinery:
+ * 12 phases per step (head gradients, four dX contractions with the ELU' / LayerNorm backward in the epilogue — row sums over
+ * DSMEM —, head layer 0, straight-through softmax backward, prior MLP, GRU gate backward, the two GRU dX contractions as one
+ * phase, img_in).  Same arguments and workspace (rlsb_imagine_bwd_workspace_bytes) as rlsb_imagine_bwd; `packed` is the
+ * rlsb_rollout_pack blob of a cfg with with_backward = 1; `fwd->tape` may come from either forward kernel. */
+int rlsb_rollout_bwd_supported(const rlsb_imagine_cfg* cfg);   /* 1: with_backward and the cluster size fits the kernel's plan */
+int rlsb_rollout_bwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const rlsb_imagine_out* fwd,
+                     const float* g_rewards, const float* g_values, float* g_actions, void* workspace, void* stream);
 
 /* backward of the rollout w.r.t. the sampled actions (activation gradients only: the world model and the
  * target critic receive no parameter update from the actor loss, dreamer_v2.py:199-207):

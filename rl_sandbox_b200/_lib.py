@@ -168,6 +168,8 @@ def load() -> C.CDLL:
         "rlsb_rollout_pack": (C.c_int, [C.POINTER(ImagineCfg), C.POINTER(ImagineParams), vp, vp]),
         "rlsb_rollout_fwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, vp, vp, vp, C.POINTER(Noise),
                                        C.POINTER(ImagineOut), vp, vp]),
+        "rlsb_rollout_bwd_supported": (C.c_int, [C.POINTER(ImagineCfg)]),
+        "rlsb_rollout_bwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, C.POINTER(ImagineOut), vp, vp, vp, vp, vp]),
     }
     sig.update({
         "rlsb_slot_attention_packed_bytes": (sz, [C.POINTER(SlotCfg)]),

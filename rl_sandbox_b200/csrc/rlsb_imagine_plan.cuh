@@ -233,6 +233,34 @@ inline void make_workspace(const Plan& P, long long N, Workspace& W) {
 
 
 
+// workspace of the backward rollout (rlsb_imagine_bwd / rlsb_rollout_bwd)
+struct BwdWorkspace {
+  size_t dy4, dh[2], g_s, g_logits, dp1, g_hprior, g_pre, g_hdirect, dp_in, g_hgru, g_za;
+  int m_pad;
+  long long ldS, ldZA;
+  size_t bytes;
+};
+
+inline void make_bwd_workspace(const Plan& P, long long N, BwdWorkspace& W) {
+  const size_t m_pad = static_cast<size_t>(ru(static_cast<int>(N), 128));
+  W.m_pad = static_cast<int>(m_pad);
+  W.ldS = P.Dp + P.Sp;
+  W.ldZA = P.Sp + P.Ap;
+  size_t cur = 0;
+  W.dy4 = place(cur, static_cast<size_t>(P.Gb) * m_pad * 64 * 2);
+  for (int i = 0; i < 2; ++i) W.dh[i] = place(cur, static_cast<size_t>(P.Gb) * m_pad * P.Hp * 2);
+  W.g_s = place(cur, m_pad * W.ldS * 4);
+  W.g_logits = place(cur, m_pad * P.Sp * 2);
+  W.dp1 = place(cur, m_pad * P.Dp * 2);
+  W.g_hprior = place(cur, m_pad * P.D * 4);
+  W.g_pre = place(cur, m_pad * P.G3p * 2);
+  W.g_hdirect = place(cur, m_pad * P.D * 4);
+  W.dp_in = place(cur, m_pad * P.Dp * 2);
+  W.g_hgru = place(cur, m_pad * P.D * 4);
+  W.g_za = place(cur, m_pad * W.ldZA * 4);
+  W.bytes = rus(cur, 1024);
+}
+
 }  // namespace k1
 
 // start-state one-hot rows -> uint8 class indices (rlsb_imagine.cu)

@@ -36,6 +36,7 @@
 #include "rlsb_kernels.cuh"
 #include "rlsb_ptx.cuh"
 #include "rlsb_rowops.cuh"
+#include "rlsb_bwd_rowops.cuh"
 
 namespace rlsb {
 namespace ro {
@@ -115,6 +116,10 @@ struct RPlan {
   int C = 8;
   k1::Plan P;
   HLayer head[5], img_in, gru, prior1, prior2;
+  // transposed layers of the backward rollout (cfg.with_backward): slab rows = in-features
+  bool bwd = false;
+  HLayer t_head[5], t_prior2, t_prior1, t_gru, t_img_in;
+  size_t gru_ln_off = 0;   // fp32 [2][3D]: determ_recurrent._norm gamma | beta in the reference's order (gate backward row code)
   size_t bytes = 0;
 };
 
@@ -186,20 +191,60 @@ inline int make_rplan(const rlsb_imagine_cfg& cfg, int C, RPlan& R) {
     }
     if ((e = finish(L)) != 0) return e;
   }
+  // ---- backward rollout (rlsb_rollout_bwd): dX contractions against the transposed weights ------------------
+  R.bwd = P.bwd;
+  if (R.bwd) {
+    // (a cluster size whose slices do not fit the LayerNorm-backward epilogue's register plan — at most 4 chunks = 128
+    // accumulator columns per CTA — leaves the forward kernel available: R.bwd = false, rlsb_rollout_bwd refuses)
+    const size_t cur0 = cur;
+    auto tlayer = [&](HLayer& L, int groups, int n_rows, int kt, int cpg) {
+      L.groups = groups; L.n = n_rows; L.kt = kt; L.cpg = cpg;
+      while (L.cpg > 1 && (n_rows + 7) / 8 < L.cpg) --L.cpg;
+      split8(n_rows, L.cpg, L.col0, L.width);
+      return finish(L);
+    };
+    const int cpg_h = C / P.Gb > 0 ? C / P.Gb : 1;
+    int eb = 0;
+    for (int l = 1; l < 5 && eb == 0; ++l) eb = tlayer(R.t_head[l], P.Gb, P.Hd, k1::ru(P.head[l].N, 64) / 64, cpg_h);
+    if (eb == 0) eb = tlayer(R.t_head[0], 1, P.Dp + P.Sp, P.Gb * P.Hp / 64, C);
+    if (eb == 0) eb = tlayer(R.t_prior2, 1, P.D, P.Sp / 64, C);
+    if (eb == 0) eb = tlayer(R.t_prior1, 1, P.D, P.Dp / 64, C);
+    if (eb == 0) eb = tlayer(R.t_gru, 2, P.D, P.G3p / 64, C / 2);
+    if (eb == 0) eb = tlayer(R.t_img_in, 1, P.Sp + P.Ap, P.Dp / 64, C);
+    for (int l = 1; l < 5 && eb == 0; ++l)
+      if (R.t_head[l].NC > 128) eb = -37;
+    if (eb == 0 && (R.t_prior2.NC > 128 || R.t_gru.NC > 128 || P.Gb > 4)) eb = -37;
+    if (eb == 0) {
+      R.gru_ln_off = k1::place(cur, static_cast<size_t>(2) * 3 * P.D * 4);
+    } else {
+      R.bwd = false;
+      cur = cur0;
+    }
+  }
   R.bytes = k1::rus(cur, 1024);
   return 0;
 }
 
 // ---- weight re-pack: nn.Linear fp32 (out, in) -> per-CTA slabs --------------------------------------------------------
+struct RowSeg {
+  int dst_r0, src_i0, len;   // rows [dst_r0, dst_r0 + len) of the (padded) slab row axis <- in-features src_i0 ...
+};
 struct RPackJob {
   const float* w; long long ld;
-  const float* b; const float* g; const float* be;   // bias / LayerNorm gamma / beta by out-feature (nullable)
+  const float* b; const float* g; const float* be;   // bias / LayerNorm gamma / beta by slab row (nullable)
   __nv_bfloat16* W; float* bias; float* gamma; float* beta;   // destinations of this job's first rank
+  // mode 0: slab rows = out-features (a contiguous slice per rank), K = in-features through `seg`
+  // mode 1: GRU triplets [r | c | u] of a slice of hidden units
+  // mode 2: TRANSPOSED (the dX contractions of the backward rollout): slab rows = in-features through `rseg` (the padded row
+  //         axis is sliced per rank), K = out-features through `seg`; only the K range [k_lo, k_hi) is written (several
+  //         Linears can share one K axis: K-concatenated head groups)
   int ranks, NC, kt, n_out, mode, D, wpad, n_seg;
   PackSeg seg[4];
+  int n_rseg, k_lo, k_hi;
+  RowSeg rseg[2];
   short col0[kMaxC], width[kMaxC];
 };
-constexpr int kMaxJobs = 24;
+constexpr int kMaxJobs = 48;
 struct RPackJobs {
   int n;
   int first_block[kMaxJobs + 1];
@@ -210,6 +255,13 @@ namespace {
 
 __device__ __forceinline__ int rpack_src_row(const RPackJob& j, int rank, int r) {
   if (j.mode == 0) return (r < j.width[rank] && j.col0[rank] + r < j.n_out) ? j.col0[rank] + r : -1;
+  if (j.mode == 2) {
+    if (r >= j.width[rank]) return -1;
+    const int rg = j.col0[rank] + r;
+    for (int i = 0; i < j.n_rseg; ++i)
+      if (rg >= j.rseg[i].dst_r0 && rg < j.rseg[i].dst_r0 + j.rseg[i].len) return j.rseg[i].src_i0 + rg - j.rseg[i].dst_r0;
+    return -1;
+  }
   const int gate = r / j.wpad, u = r - gate * j.wpad;
   return (gate < 3 && u < j.width[rank]) ? gate * j.D + j.col0[rank] + u : -1;
 }
@@ -236,18 +288,20 @@ __global__ void __launch_bounds__(256) rpack_kernel(const __grid_constant__ RPac
   const int kt = static_cast<int>(t2 % j.kt);
   const int rank = static_cast<int>(t2 / j.kt);
   const int src = rpack_src_row(j, rank, r);
+  const int k0 = kt * 64 + ch * 8;
+  if (j.mode == 2 && (k0 < j.k_lo || k0 >= j.k_hi)) return;   // another job's share of the K axis
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = 0.f;
   if (src >= 0) {
-    const int k0 = kt * 64 + ch * 8;
     const float* row = j.w + static_cast<long long>(src) * j.ld;
     for (int s = 0; s < j.n_seg; ++s) {
       const PackSeg& sg = j.seg[s];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = k0 + e - sg.dst_k0;
-        if (k >= 0 && k < sg.len) v[e] = row[sg.src_c0 + k];
+        if (k >= 0 && k < sg.len)
+          v[e] = j.mode == 2 ? j.w[static_cast<long long>(sg.src_c0 + k) * j.ld + src] : row[sg.src_c0 + k];
       }
     }
   }
@@ -298,9 +352,9 @@ __device__ __forceinline__ size_t pk_off(int r, int col) {
          static_cast<size_t>((((col & 63) >> 3) ^ (r & 7)) << 3) + (col & 7);
 }
 
-struct OpA {   // A operand of a layer for this row block: up to two K segments (concatenated inputs)
-  const __nv_bfloat16* A[2];
-  int kt[2];
+struct OpA {   // A operand of a layer for this row block: up to four K segments (concatenated inputs)
+  const __nv_bfloat16* A[4];
+  int kt[4];
   int nseg;
 };
 
@@ -1292,6 +1346,378 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// the backward rollout as ONE persistent kernel (rlsb_rollout_bwd): d loss / d actions through the chain of
+// rlsb_imagine_bwd.cu, a thread-block cluster per 128 start states, the same layer machinery as the forward kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct RolloutBwdParams {
+  RLayer t_head[5], t_prior2, t_prior1, t_gru, t_img_in;
+  int C, M, m_pad, H;
+  int D, S, A, Dp, Sp, Ap, Hp, G3p, Gb, gb0, gb_reward, gb_critic, groups, layer_norm, gru_nb;
+  float eps;
+  // forward results
+  const float *determ, *logits;
+  const uint8_t* tape; size_t tape_step;
+  size_t tp_head_pre[4], tp_head_rstd[4], tp_x_pre, tp_x_rstd, tp_gru_scratch, tp_gru_stats, tp_y_pre, tp_y_rstd;
+  long long tape_ld_scratch;
+  const float *gru_gamma, *gru_beta;   // determ_recurrent._norm (3D), un-permuted (the gate kernel's row code reads them)
+  // gradients in / out
+  const float *g_rewards, *g_values;
+  float* g_actions;
+  // workspace (k1::BwdWorkspace)
+  __nv_bfloat16 *dy4, *dh[2], *g_logits, *dp1, *g_pre, *dp_in;
+  float *g_s, *g_hprior, *g_hdirect, *g_hgru, *g_za;
+  long long ldS, ldZA;
+  int kg_max;
+};
+
+struct BwdEpi {
+  const __nv_bfloat16* pre;   // row block of the saved x_hat / pre-activation image (pk_off geometry)
+  const float* rstd;          // [128] of this row block (LayerNorm) or nullptr
+  __nv_bfloat16* out;         // row block of the output image
+  int out_kpad;
+};
+// (the register-hungry row phases are separate functions: the 64 live values of a softmax group or the gate gradients of a row
+// must not inflate the register allocation of the contraction phases around them)
+__device__ __noinline__ void bwd_softmax_phase(const float* logits, int S, const float* g_s_z, long long ldS, const float* g_za,
+                                               long long ldZA, __nv_bfloat16* g_logits, int Sp, int row0, int rows, int M, int groups,
+                                               int tid_e) {
+  for (int i = tid_e; i < rows * groups; i += kEpiThreads) {
+    const int mm = row0 + i / groups, g = i % groups;
+    if (mm < M) bwdops::st_softmax_bwd_item<true>(mm, g, logits, S, g_s_z, ldS, g_za, ldZA, g_logits, Sp);
+  }
+}
+__device__ __noinline__ void bwd_gate_phase(const bwdops::GruBwdArgs& ga, int row0, int rows, int we, int lane) {
+  for (int r = we; r < rows; r += 16) bwdops::gru_gate_bwd_row<true>(ga, row0 + r, lane);
+}
+
+// dX epilogue: acc = d loss / d y, y = ELU(LN?(pre)); ELU' and the LayerNorm backward (row sums over the group's CTAs through
+// the DSMEM exchange) -> packed bf16 d loss / d (pre-LayerNorm activation).  The thread's chunks stay in registers.
+template <int kBwdChunks>   // 8-column chunks per epilogue thread, at most: 2 (NC <= 64) or 4 (NC <= 128)
+__device__ __forceinline__ void epi_bwd_n(RCtl* ctl, const RLayer& L, int rank, bool ln, const BwdEpi& o, uint32_t tmem_d, int cq,
+                                          int row, bool row_ok, int tid_e, int par, Roles& st) {
+  const int gi = rank % L.cpg, g0 = rank - gi;
+  const int width = L.width[gi], col0 = L.col0[gi];
+  const int n_chunks = L.NC >> 3;
+  const int mine = n_chunks > cq ? (n_chunks - cq + 3) >> 2 : 0;
+  // the saved image and 1/std come from the forward pass: fetch them while the contraction is still running
+  uint4 pb[kBwdChunks];
+#pragma unroll
+  for (int i = 0; i < kBwdChunks; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    pb[i] = (i < mine && c < width) ? __ldg(reinterpret_cast<const uint4*>(o.pre + pk_off(row, col0 + c))) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  const float rstd = (ln && o.rstd) ? __ldg(o.rstd + row) : 1.0f;
+  epi_begin(ctl, L, rank, tid_e, ln, st);
+  uint32_t r[kBwdChunks][8];
+#pragma unroll
+  for (int i = 0; i < kBwdChunks; ++i)
+    if (i < mine) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * i) * 8), r[i]);
+  tmem_ld_wait();
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kBwdChunks; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (i < mine && c < width) {
+      tie8(r[i]);
+      float x[8], g[8], be[8];
+      const uint32_t w[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[2 * j] = __uint_as_float(w[j] << 16);
+        x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+      }
+      if (ln) {
+        ld8f(&ctl->gamma[c], g);
+        ld8f(&ctl->beta[c], be);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = ln ? fmaf(x[j], g[j], be[j]) : x[j];
+        const float d = a > 0.f ? 1.0f : rowops::ex2_approx(a * 1.4426950408889634f);   // ELU'
+        float dxh = (row_ok && c + j < width) ? __uint_as_float(r[i][j]) * d : 0.f;
+        if (ln) dxh *= g[j];
+        s1 += dxh;
+        s2 = fmaf(dxh, x[j], s2);
+        r[i][j] = __float_as_uint(dxh);
+      }
+    }
+  }
+  float m1r = 0.f, m2r = 0.f;
+  if (ln) {
+    float2 total;
+    ln_exchange(ctl, cq, row, s1, s2, g0, L.cpg, gi, L.n, 0.f, par, &total);
+    const float inv_n = 1.0f / static_cast<float>(L.n);
+    m1r = -total.x * inv_n * rstd;
+    m2r = -total.y * inv_n * rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < kBwdChunks; ++i) {
+    const int c = (cq + 4 * i) * 8;
+    if (i < mine && c < width) {
+      float y[8];
+      const uint32_t w[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dxh = __uint_as_float(r[i][j]);
+        const float xh = (j & 1) ? __uint_as_float(w[j >> 1] & 0xffff0000u) : __uint_as_float(w[j >> 1] << 16);
+        // rstd * (dxh - mean(dxh) - x_hat * mean(dxh * x_hat))
+        y[j] = ln ? ((row_ok && c + j < width) ? fmaf(xh, m2r, fmaf(dxh, rstd, m1r)) : 0.f) : dxh;
+      }
+      *reinterpret_cast<uint4*>(o.out + pk_off(row, col0 + c)) = pack8(y);
+    }
+  }
+  if (gi == L.cpg - 1) {
+    for (int ch = ((col0 + width + 7) >> 3) + cq; ch < (o.out_kpad >> 3); ch += 4)
+      *reinterpret_cast<uint4*>(o.out + pk_off(row, ch * 8)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__device__ __noinline__ void epi_bwd(RCtl* ctl, const RLayer& L, int rank, bool ln, const BwdEpi& o, uint32_t tmem_d, int cq,
+                                     int row, bool row_ok, int tid_e, int par, Roles& st) {
+  if (L.NC <= 64) epi_bwd_n<2>(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, par, st);
+  else epi_bwd_n<4>(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, par, st);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_constant__ RolloutBwdParams P, const int ring_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  RCtl* ctl = reinterpret_cast<RCtl*>(ring + ring_bytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int C = P.C;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int rb = static_cast<int>(blockIdx.x) / C;
+  pdl_launch_dependents();
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < 8; ++s) {
+        mbar_init(&ctl->full[s], 1);
+        mbar_init(&ctl->empty[s], 1);
+      }
+      mbar_init(&ctl->tmem_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&ctl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();
+  const uint32_t tmem_base = ctl->tmem_base;
+  pdl_wait();
+
+  Roles st{0xffu, 0u, 0u};
+  const int q = warp & 3;
+  const int cq = (warp - 2) >> 2;
+  const int row = q * 32 + lane;
+  const int tid_e = static_cast<int>(threadIdx.x) - 64;
+  const int we = warp - 2;
+  const uint32_t tmem_d = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const int m = rb * kTileM + row;
+  const bool row_ok = m < P.M;
+  const size_t tile = static_cast<size_t>(kTileM) * kTileK;
+  const size_t blk_64 = static_cast<size_t>(rb) * tile;
+  const size_t blk_D = static_cast<size_t>(rb) * (P.Dp >> 6) * tile;
+  const size_t blk_S = static_cast<size_t>(rb) * (P.Sp >> 6) * tile;
+  const size_t blk_H = static_cast<size_t>(rb) * (P.Hp >> 6) * tile;
+  const size_t blk_G = static_cast<size_t>(rb) * (P.G3p >> 6) * tile;
+  const size_t hid_gs = static_cast<size_t>(P.m_pad) * P.Hp;
+  const size_t ND = static_cast<size_t>(P.M) * P.D, NS = static_cast<size_t>(P.M) * P.S;
+  const int rpc = kTileM / C;   // rows of the block per CTA in the row phases
+  const bool lncfg = P.layer_norm != 0;
+  int lnpar = 0;
+  auto tp = [&](int t, size_t off) { return P.tape + static_cast<size_t>(t) * P.tape_step + off; };
+  auto run_mainloop = [&](const RLayer& L, const OpA& a, bool active) {
+    if (warp == 0) {
+      if (active) produce(ctl, ring, ring_bytes, L, rank, a, st, 0, P.kg_max, nullptr);
+    } else if (warp == 1) {
+      if (active) issue_mma(ctl, ring, ring_bytes, L, tmem_base, a, st, 0, P.kg_max, nullptr);
+    }
+  };
+  // d loss / d a_t = columns [Sp, Sp + A) of the img_in dX the previous step left in g_za
+  auto extract_actions = [&](int t_act) {
+    if (warp < 2) return;
+    for (int i = tid_e; i < rpc * P.A; i += kEpiThreads) {
+      const int mm = rb * kTileM + rank * rpc + i / P.A, k = i % P.A;
+      if (mm < P.M)
+        P.g_actions[(static_cast<size_t>(t_act) * P.M + mm) * P.A + k] = __ldcg(P.g_za + static_cast<size_t>(mm) * P.ldZA + P.Sp + k);
+    }
+  };
+
+  for (int t = P.H; t >= 1; --t) {
+    // ---- d loss / d (reward, value) of state t -> head gradients; the previous step's action gradient ----------------
+    if (t < P.H) extract_actions(t);
+    if (warp >= 2 && tid_e < rpc) {
+      const int mm = rb * kTileM + rank * rpc + tid_e;
+      bwdops::head_grad_row(mm, P.g_rewards + static_cast<size_t>(t) * P.M, P.g_values + static_cast<size_t>(t) * P.M, P.M,
+                            P.m_pad, P.Gb, P.gb_reward, P.gb_critic, P.dy4);
+    }
+    layer_end(warp >= 2);
+    // ---- reward head + target critic, layers 4 .. 1: dX with the ELU' / LayerNorm backward of the layer below ---------
+    for (int l = 4; l >= 1; --l) {
+      const RLayer& L = P.t_head[l];
+      const int grp = rank / L.cpg;
+      const bool active = rank < L.ranks;
+      const bool ln = (l - 1 == 0) || lncfg;
+      OpA a;
+      a.nseg = 1;
+      a.A[0] = (l == 4) ? P.dy4 + static_cast<size_t>(grp) * P.m_pad * 64 + blk_64
+                        : P.dh[(l + 1) & 1] + static_cast<size_t>(grp) * hid_gs + blk_H;
+      a.kt[0] = L.kt;
+      run_mainloop(L, a, active);
+      if (warp >= 2 && active) {
+        BwdEpi o;
+        o.pre = reinterpret_cast<const __nv_bfloat16*>(tp(t, P.tp_head_pre[l - 1])) + static_cast<size_t>(P.gb0 + grp) * hid_gs + blk_H;
+        o.rstd = ln ? reinterpret_cast<const float*>(tp(t, P.tp_head_rstd[l - 1])) + static_cast<size_t>(P.gb0 + grp) * P.m_pad + rb * kTileM
+                    : nullptr;
+        o.out = P.dh[l & 1] + static_cast<size_t>(grp) * hid_gs + blk_H;
+        o.out_kpad = P.Hp;
+        epi_bwd(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st);
+      } else if (ln) {
+        __syncwarp();
+        cluster_sync_all();
+      }
+      if (ln) lnpar ^= 1;
+      layer_end(warp >= 2 && active);
+    }
+    // ---- layer 0 of the heads: the groups are K segments of one contraction -> d loss / d [h_t, z_t] ------------------
+    {
+      const RLayer& L = P.t_head[0];
+      const bool active = rank < L.ranks;
+      OpA a;
+      a.nseg = P.Gb;
+      for (int i = 0; i < P.Gb; ++i) {
+        a.A[i] = P.dh[1] + static_cast<size_t>(i) * hid_gs + blk_H;
+        a.kt[i] = P.Hp >> 6;
+      }
+      run_mainloop(L, a, active);
+      if (warp >= 2 && active) {
+        epi_begin(ctl, L, rank, tid_e, false, st);
+        epi_plain(ctl, L, rank, P.g_s + static_cast<size_t>(m) * P.ldS + L.col0[rank], L.width[rank], tmem_d, cq, row_ok);
+      }
+      layer_end(warp >= 2 && active);
+    }
+    // ---- z_t = onehot + p - p.detach(): d loss / d prior logits ------------------------------------------------------------
+    if (warp >= 2)
+      bwd_softmax_phase(P.logits + static_cast<size_t>(t) * NS, P.S, P.g_s + P.Dp, P.ldS, t < P.H ? P.g_za : nullptr, P.ldZA,
+                        P.g_logits, P.Sp, rb * kTileM + rank * rpc, rpc, P.M, P.groups, tid_e);
+    layer_end(warp >= 2);
+    // ---- prior MLP: logits -> y (ELU' / LayerNorm backward of prior 1) -> h_t ----------------------------------------------
+    {
+      const RLayer& L = P.t_prior2;
+      const bool active = rank < L.ranks;
+      OpA a;
+      a.nseg = 1;
+      a.A[0] = P.g_logits + blk_S; a.kt[0] = P.Sp >> 6;
+      run_mainloop(L, a, active);
+      if (warp >= 2 && active) {
+        BwdEpi o;
+        o.pre = reinterpret_cast<const __nv_bfloat16*>(tp(t, P.tp_y_pre)) + blk_D;
+        o.rstd = lncfg ? reinterpret_cast<const float*>(tp(t, P.tp_y_rstd)) + rb * kTileM : nullptr;
+        o.out = P.dp1 + blk_D;
+        o.out_kpad = P.Dp;
+        epi_bwd(ctl, L, rank, lncfg, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st);
+      } else if (lncfg) {
+        __syncwarp();
+        cluster_sync_all();
+      }
+      if (lncfg) lnpar ^= 1;
+      layer_end(warp >= 2 && active);
+    }
+    {
+      const RLayer& L = P.t_prior1;
+      const bool active = rank < L.ranks;
+      OpA a;
+      a.nseg = 1;
+      a.A[0] = P.dp1 + blk_D; a.kt[0] = P.Dp >> 6;
+      run_mainloop(L, a, active);
+      if (warp >= 2 && active) {
+        epi_begin(ctl, L, rank, tid_e, false, st);
+        epi_plain(ctl, L, rank, P.g_hprior + static_cast<size_t>(m) * P.D + L.col0[rank], L.width[rank], tmem_d, cq, row_ok);
+      }
+      layer_end(warp >= 2 && active);
+    }
+    // ---- h_t = GRU(x_t, h_{t-1}): gates + joint LayerNorm backward, one warp per row -------------------------------------------
+    if (warp >= 2) {
+      bwdops::GruBwdArgs ga{};
+      ga.scratch = reinterpret_cast<const float*>(tp(t, P.tp_gru_scratch)); ga.ld = P.tape_ld_scratch;
+      ga.stats = reinterpret_cast<const float*>(tp(t, P.tp_gru_stats));
+      ga.NB = P.gru_nb; ga.M = P.M; ga.m_pad = P.m_pad; ga.D = P.D;
+      ga.gamma = P.gru_gamma; ga.beta = P.gru_beta;
+      ga.eps = P.eps; ga.update_bias = -1.0f;
+      ga.h_prev = P.determ + static_cast<size_t>(t - 1) * ND; ga.ld_h = P.D;
+      ga.gh[0] = P.g_s; ga.ld_gh[0] = P.ldS;
+      ga.gh[1] = P.g_hprior; ga.ld_gh[1] = P.D;
+      ga.n_gh = 2;
+      if (t < P.H) {
+        ga.gh[2] = P.g_hdirect; ga.ld_gh[2] = P.D;
+        ga.gh[3] = P.g_hgru; ga.ld_gh[3] = P.D;
+        ga.n_gh = 4;
+      }
+      ga.g_pre = P.g_pre; ga.kpad = P.G3p;
+      ga.g_hdirect = P.g_hdirect;
+      bwd_gate_phase(ga, rb * kTileM + rank * rpc, rpc, we, lane);
+    }
+    layer_end(warp >= 2);
+    // ---- d / d x_t (with img_in's ELU' / LayerNorm backward) and d / d h_{t-1} through the gates: one phase, two groups -------
+    {
+      const RLayer& L = P.t_gru;
+      const int grp = rank / L.cpg;
+      const bool active = rank < L.ranks;
+      OpA a;
+      a.nseg = 1;
+      a.A[0] = P.g_pre + blk_G; a.kt[0] = P.G3p >> 6;
+      run_mainloop(L, a, active);
+      if (warp >= 2 && active && grp == 0) {
+        BwdEpi o;
+        o.pre = reinterpret_cast<const __nv_bfloat16*>(tp(t, P.tp_x_pre)) + blk_D;
+        o.rstd = lncfg ? reinterpret_cast<const float*>(tp(t, P.tp_x_rstd)) + rb * kTileM : nullptr;
+        o.out = P.dp_in + blk_D;
+        o.out_kpad = P.Dp;
+        epi_bwd(ctl, L, rank, lncfg, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st);
+      } else {
+        if (warp >= 2 && active) {
+          epi_begin(ctl, L, rank, tid_e, false, st);
+          const int gi = rank % L.cpg;
+          epi_plain(ctl, L, rank, P.g_hgru + static_cast<size_t>(m) * P.D + L.col0[gi], L.width[gi], tmem_d, cq, row_ok);
+        }
+        if (lncfg) {
+          __syncwarp();
+          cluster_sync_all();
+        }
+      }
+      if (lncfg) lnpar ^= 1;
+      layer_end(warp >= 2 && active);
+    }
+    // ---- x_t = ELU(LN?(W_in [z_{t-1}, a_{t-1}])): d loss / d z_{t-1}, d loss / d a_{t-1} -------------------------------------------
+    {
+      const RLayer& L = P.t_img_in;
+      const bool active = rank < L.ranks;
+      OpA a;
+      a.nseg = 1;
+      a.A[0] = P.dp_in + blk_D; a.kt[0] = P.Dp >> 6;
+      run_mainloop(L, a, active);
+      if (warp >= 2 && active) {
+        epi_begin(ctl, L, rank, tid_e, false, st);
+        epi_plain(ctl, L, rank, P.g_za + static_cast<size_t>(m) * P.ldZA + L.col0[rank], L.width[rank], tmem_d, cq, row_ok);
+      }
+      layer_end(warp >= 2 && active);
+    }
+  }
+  extract_actions(0);
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int g_rollout_cluster = 0;   // 0: not read yet
 unsigned long long* g_rollout_trace = nullptr;
 
@@ -1346,6 +1772,12 @@ extern "C" size_t rlsb_rollout_packed_bytes(const rlsb_imagine_cfg* cfg) {
   RPlan R;
   if (!cfg || make_rplan(*cfg, cluster_of(*cfg), R) != 0) return 0;
   return R.bytes;
+}
+
+extern "C" int rlsb_rollout_bwd_supported(const rlsb_imagine_cfg* cfg) {
+  RPlan R;
+  if (!cfg || make_rplan(*cfg, cluster_of(*cfg), R) != 0) return 0;
+  return R.bwd ? 1 : 0;
 }
 
 extern "C" int rlsb_rollout_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine_params* prm, void* packed, void* stream_) {
@@ -1409,8 +1841,52 @@ extern "C" int rlsb_rollout_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
       }
     }
   }
+  if (R.bwd) {
+    // transposed slabs: rows = in-features (LayerNorm gamma / beta of the layer BELOW ride along, indexed by the same rows)
+    auto addt = [&](const HLayer& L, int group, const float* w, long long ld, const float* g, const float* be, int n_out,
+                    int dst_k0, int k_lo, int k_hi, int n_rseg, const RowSeg* rs) -> int {
+      PackSeg sg[1] = {{dst_k0, 0, n_out}};
+      RLSB_TRY(add(L, group, w, ld, nullptr, g, be, n_out, 2, 1, sg));
+      RPackJob& j = J.job[J.n - 1];
+      j.n_rseg = n_rseg;
+      for (int i = 0; i < n_rseg; ++i) j.rseg[i] = rs[i];
+      j.k_lo = k_lo; j.k_hi = k_hi;
+      return 0;
+    };
+    for (int l = 1; l < 5; ++l) {
+      for (int gb = 0; gb < P.Gb; ++gb) {
+        const int g = P.gb0 + gb;
+        const rlsb_mlp_params* hp = (g == P.g_reward) ? &prm->reward : (g == P.g_discount) ? &prm->discount : &prm->critic;
+        const int n_out = (l == 4) ? 1 : P.Hd;
+        RowSeg rs[1] = {{0, 0, P.Hd}};
+        RLSB_TRY(addt(R.t_head[l], gb, hp->w[l], P.Hd, hp->ln_g[l - 1], hp->ln_b[l - 1], n_out, 0, 0, R.t_head[l].kt * 64, 1, rs));
+      }
+    }
+    for (int gb = 0; gb < P.Gb; ++gb) {   // layer 0: the gradient-carrying groups share one K axis
+      const int g = P.gb0 + gb;
+      const rlsb_mlp_params* hp = (g == P.g_reward) ? &prm->reward : (g == P.g_discount) ? &prm->discount : &prm->critic;
+      RowSeg rs[2] = {{0, 0, P.D}, {P.Dp, P.D, P.S}};
+      RLSB_TRY(addt(R.t_head[0], 0, hp->w[0], P.D + P.S, nullptr, nullptr, P.Hd, gb * P.Hp, gb * P.Hp, (gb + 1) * P.Hp, 2, rs));
+    }
+    {
+      RowSeg rs[1] = {{0, 0, P.D}};
+      RLSB_TRY(addt(R.t_prior2, 0, prm->prior2_w, P.D, prm->prior1_ln_g, prm->prior1_ln_b, P.S, 0, 0, P.Sp, 1, rs));
+      RLSB_TRY(addt(R.t_prior1, 0, prm->prior1_w, P.D, nullptr, nullptr, P.D, 0, 0, P.Dp, 1, rs));
+      // GRU weight (3D, 2D): in-features [x | h]; group 0 = d / d x (with img_in's LayerNorm below), group 1 = d / d h
+      RLSB_TRY(addt(R.t_gru, 0, prm->gru_w, 2 * P.D, prm->img_in_ln_g, prm->img_in_ln_b, 3 * P.D, 0, 0, P.G3p, 1, rs));
+      RowSeg rh[1] = {{0, P.D, P.D}};
+      RLSB_TRY(addt(R.t_gru, 1, prm->gru_w, 2 * P.D, nullptr, nullptr, 3 * P.D, 0, 0, P.G3p, 1, rh));
+      RowSeg ri[2] = {{0, 0, P.S}, {P.Sp, P.S, P.A}};
+      RLSB_TRY(addt(R.t_img_in, 0, prm->img_in_w, P.S + P.A, nullptr, nullptr, P.D, 0, 0, P.Dp, 2, ri));
+    }
+  }
   rpack_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(J);
   count_launch();
+  if (R.bwd) {
+    float* dst = reinterpret_cast<float*>(base + R.gru_ln_off);
+    RLSB_TRY(launch_copy_pad(prm->gru_ln_g, 3 * P.D, dst, 3 * P.D, 1.f, s));
+    RLSB_TRY(launch_copy_pad(prm->gru_ln_b, 3 * P.D, dst + 3 * P.D, 3 * P.D, 0.f, s));
+  }
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1545,6 +2021,94 @@ extern "C" int rlsb_rollout_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   lc.attrs = attr;
   lc.numAttrs = 2;
   e = cudaLaunchKernelEx(&lc, rollout_kernel, rp, ring_bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+
+extern "C" int rlsb_rollout_bwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N, const rlsb_imagine_out* fwd,
+                                const float* g_rewards, const float* g_values, float* g_actions, void* workspace, void* stream_) {
+  if (!cfg || !packed || !fwd || !g_rewards || !g_values || !g_actions || !workspace || N <= 0) return -1;
+  if (!fwd->tape || !fwd->determ || !fwd->logits) return -2;
+  if (N > (1LL << 24)) return -3;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const int C = cluster_of(*cfg);
+  RPlan R;
+  RLSB_TRY(make_rplan(*cfg, C, R));
+  if (!R.bwd) return -15;
+  const k1::Plan& P = R.P;
+  if ((P.D & 7) != 0) return -15;
+  const int H = cfg->H;
+  k1::Tape TP;
+  k1::make_tape(P, N, H, TP);
+  k1::BwdWorkspace W;
+  k1::make_bwd_workspace(P, N, W);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  auto f32 = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+
+  RolloutBwdParams rp{};
+  for (int l = 0; l < 5; ++l) fill_layer(rp.t_head[l], R.t_head[l], pk);
+  fill_layer(rp.t_prior2, R.t_prior2, pk);
+  fill_layer(rp.t_prior1, R.t_prior1, pk);
+  fill_layer(rp.t_gru, R.t_gru, pk);
+  fill_layer(rp.t_img_in, R.t_img_in, pk);
+  rp.C = C; rp.M = static_cast<int>(N); rp.m_pad = W.m_pad; rp.H = H;
+  rp.D = P.D; rp.S = P.S; rp.A = P.A; rp.Dp = P.Dp; rp.Sp = P.Sp; rp.Ap = P.Ap; rp.Hp = P.Hp; rp.G3p = P.G3p;
+  rp.Gb = P.Gb; rp.gb0 = P.gb0; rp.gb_reward = P.g_reward - P.gb0; rp.gb_critic = P.g_critic - P.gb0;
+  rp.groups = cfg->groups; rp.layer_norm = cfg->layer_norm; rp.gru_nb = P.gru.NB;
+  rp.eps = 1e-5f;
+  rp.determ = fwd->determ; rp.logits = fwd->logits;
+  rp.tape = static_cast<const uint8_t*>(fwd->tape); rp.tape_step = TP.step_bytes;
+  for (int l = 0; l < 4; ++l) {
+    rp.tp_head_pre[l] = TP.head_pre[l];
+    rp.tp_head_rstd[l] = TP.head_rstd[l];
+  }
+  rp.tp_x_pre = TP.x_pre; rp.tp_x_rstd = TP.x_rstd; rp.tp_gru_scratch = TP.gru_scratch; rp.tp_gru_stats = TP.gru_stats;
+  rp.tp_y_pre = TP.y_pre; rp.tp_y_rstd = TP.y_rstd;
+  rp.tape_ld_scratch = TP.ld_scratch;
+  // the gate backward's row code reads the GRU LayerNorm parameters in the reference's (3D) order (the forward slab's are
+  // permuted per CTA): a plain copy kept in the blob
+  rp.gru_gamma = reinterpret_cast<const float*>(pk + R.gru_ln_off);
+  rp.gru_beta = rp.gru_gamma + 3 * P.D;
+  rp.g_rewards = g_rewards; rp.g_values = g_values; rp.g_actions = g_actions;
+  rp.dy4 = bf(W.dy4); rp.dh[0] = bf(W.dh[0]); rp.dh[1] = bf(W.dh[1]); rp.g_logits = bf(W.g_logits); rp.dp1 = bf(W.dp1);
+  rp.g_pre = bf(W.g_pre); rp.dp_in = bf(W.dp_in);
+  rp.g_s = f32(W.g_s); rp.g_hprior = f32(W.g_hprior); rp.g_hdirect = f32(W.g_hdirect); rp.g_hgru = f32(W.g_hgru);
+  rp.g_za = f32(W.g_za);
+  rp.ldS = W.ldS; rp.ldZA = W.ldZA;
+  rp.kg_max = 4;
+  if (const char* env = getenv("RLSB_ROLLOUT_KG")) rp.kg_max = atoi(env) >= 1 ? atoi(env) : 1;
+
+  const int ring_bytes = (227 * 1024 - 1024 - static_cast<int>(sizeof(RCtl)) - 256) / 1024 * 1024;
+  const size_t smem = static_cast<size_t>(ring_bytes) + sizeof(RCtl) + 1024;
+  static PerDeviceOnce attr_once;
+  unsigned long long dev_bit = 0;
+  cudaError_t e;
+  if (attr_once.need(dev_bit)) {
+    e = cudaFuncSetAttribute(rollout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(rollout_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_once.done(dev_bit);
+  }
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(static_cast<unsigned>(W.m_pad / 128 * C));
+  lc.blockDim = dim3(kThreads);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(C);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl;
+  lc.attrs = attr;
+  lc.numAttrs = 2;
+  e = cudaLaunchKernelEx(&lc, rollout_bwd_kernel, rp, ring_bytes);
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return static_cast<int>(cudaGetLastError());

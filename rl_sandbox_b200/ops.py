@@ -478,9 +478,11 @@ class ImaginationEngine:
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")
         return out
 
-    def backward(self, out: dict, g_rewards: torch.Tensor, g_values: torch.Tensor, pin=None) -> torch.Tensor:
+    def backward(self, out: dict, g_rewards: torch.Tensor, g_values: torch.Tensor, pin=None,
+                 persistent: Optional[bool] = None) -> torch.Tensor:
         """d loss / d actions (H, N, A) from d loss / d rewards, d loss / d values (each (H+1, N)) through the
-        rollout recorded in ``out`` (made with tape=True): rlsb_imagine_bwd."""
+        rollout recorded in ``out`` (made with tape=True): rlsb_imagine_bwd (one launch per layer) or, up to
+        ``persistent_max_rows`` start states, rlsb_rollout_bwd (ONE persistent kernel; ``persistent`` forces either)."""
         if out.get("tape") is None:
             raise _lib.RlsbError("ImaginationEngine.backward needs a rollout made with tape=True")
         H = out["determ"].shape[0] - 1
@@ -505,6 +507,22 @@ class ImaginationEngine:
         co = ImagineOut(*[_ptr(out.get(k)) for k in ("determ", "logits", "stoch_idx", "stoch", "actions",
                                                       "rewards", "discounts", "values", "actor_raw",
                                                       "determ_packed", "stoch_packed", "tape")])
+        if persistent is None:
+            persistent = self.packed_ro is not None and n <= self.persistent_max_rows and os.environ.get("RLSB_PERSISTENT_BWD", "1") != "0"
+            if persistent:   # cluster sizes whose slices do not fit the epilogue's register plan fall back to the chain
+                probe = self.cfg.to_c()
+                probe.rollout_cluster = self.rollout_cluster_for(n)
+                persistent = self.lib.rlsb_rollout_bwd_supported(C.byref(probe)) == 1
+        elif persistent and self.packed_ro is None:
+            raise _lib.RlsbError("backward(persistent=True): flat RSSM without parity mode only")
+        self.last_backward_persistent = bool(persistent)
+        if persistent:
+            ccfg.rollout_cluster = self.rollout_cluster_for(n)
+            blob = self._packed_rollout(ccfg)
+            check(self.lib.rlsb_rollout_bwd(C.byref(ccfg), blob.data_ptr(), n, C.byref(co), g_rewards.data_ptr(),
+                                            g_values.data_ptr(), g_actions.data_ptr(), bws.data_ptr(), _stream()),
+                  "rlsb_rollout_bwd")
+            return g_actions
         check(self.lib.rlsb_imagine_bwd(C.byref(ccfg), self.packed.data_ptr(), n, C.byref(co), g_rewards.data_ptr(),
                                         g_values.data_ptr(), g_actions.data_ptr(), bws.data_ptr(), _stream()),
               "rlsb_imagine_bwd")

@@ -114,9 +114,15 @@ def test_persistent_rollout_plan_sizes_without_a_device():
         n = lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, rollout_cluster=cs)))
         assert 0.95 * chained < n < 1.15 * chained, (cs, n, chained)
     assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, rollout_cluster=4))) == 0   # 256 hidden units per CTA
-    sizes = [lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c2, rollout_cluster=cs))) for cs in (4, 8, 16)]
+    sizes = [lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**dict(c2, with_backward=0), rollout_cluster=cs))) for cs in (4, 8, 16)]
     assert all(s > 7_000_000 for s in sizes) and max(sizes) < 1.1 * min(sizes)         # same matrices, a little padding
+    with_bwd = [lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c2, rollout_cluster=cs))) for cs in (4, 8, 16)]
+    assert with_bwd[0] == sizes[0] and all(1.5 * a < b < 2.2 * a for a, b in zip(sizes[1:], with_bwd[1:]))   # + transposed slabs
     assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, rollout_cluster=0))) > 0  # 0 = library default
+    # the persistent backward kernel: continuous-action configs whose slices fit its epilogue's register plan
+    assert [lib.rlsb_rollout_bwd_supported(C.byref(_lib.ImagineCfg(**c2, rollout_cluster=cs))) for cs in (4, 8, 16)] == [0, 1, 1]
+    assert lib.rlsb_rollout_bwd_supported(C.byref(_lib.ImagineCfg(**c1, rollout_cluster=16))) == 0    # no with_backward
+    assert lib.rlsb_rollout_bwd(None, None, 0, None, None, None, None, None, None) < 0
     assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, parity=1))) == 0
     assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**dict(c2, with_backward=0), slots=4, attention_blocks=3))) == 0
     assert lib.rlsb_rollout_fwd(None, None, 0, None, None, None, None, None, None, None) < 0

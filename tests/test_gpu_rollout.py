@@ -148,11 +148,23 @@ def test_persistent_keeps_packed_states_and_tape_like_chained(ops, cuda, name):
     gen = torch.Generator(device="cuda").manual_seed(5)
     g_r = torch.randn(H + 1, N, device="cuda", generator=gen)
     g_v = torch.randn(H + 1, N, device="cuda", generator=gen)
-    ga = eng.backward(a, g_r, g_v).clone()
-    gb = eng.backward(b, g_r, g_v).clone()
+    ga = eng.backward(a, g_r, g_v, persistent=False).clone()
+    gb = eng.backward(b, g_r, g_v, persistent=False).clone()
     rows = alive[-1]
     e = rel_rms(gb[:, rows], ga[:, rows], "d loss / d actions from the persistent tape vs the chained tape")
     assert e < 2e-2 and torch.isfinite(gb).all()
+    # the backward rollout as ONE persistent kernel (rlsb_rollout_bwd) on either tape vs the chained rlsb_imagine_bwd
+    from rl_sandbox_b200 import _lib
+    lib = _lib.load()
+    for tag, o, want in (("chained tape", a, ga), ("persistent tape", b, gb)):
+        l0 = lib.rlsb_launch_count(0)
+        got = eng.backward(o, g_r, g_v, persistent=True).clone()
+        launches = lib.rlsb_launch_count(0) - l0
+        assert eng.last_backward_persistent and launches <= 4, launches
+        e = rel_rms(got, want, f"d loss / d actions, persistent backward vs chained backward ({tag})")
+        assert e < 1e-2 and torch.isfinite(got).all()
+    # reproducible
+    assert torch.equal(eng.backward(b, g_r, g_v, persistent=True), eng.backward(b, g_r, g_v, persistent=True))
 
 
 def test_persistent_training_rollout_skips_heads_of_last_state(ops, cuda):
