@@ -214,6 +214,8 @@ inline int make_rplan(const rlsb_imagine_cfg& cfg, int C, RPlan& R) {
     for (int l = 1; l < 5 && eb == 0; ++l)
       if (R.t_head[l].NC > 128) eb = -37;
     if (eb == 0 && (R.t_prior2.NC > 128 || R.t_gru.NC > 128 || P.Gb > 4)) eb = -37;
+    // gate-backward row phase: 16 / (128 / C) warps per row, at most two 4-unit slices per lane
+    if (eb == 0 && (C < 8 || P.D / 4 > 2 * 32 * (C / 8))) eb = -39;
     if (eb == 0) {
       R.gru_ln_off = k1::place(cur, static_cast<size_t>(2) * 3 * P.D * 4);
     } else {
@@ -387,11 +389,10 @@ __device__ __forceinline__ Ring make_ring(int ring_bytes, int NC, int kg_max) {
   return r;
 }
 
-// k tiles of the n-th group of a K segment of `left` remaining tiles: the first two groups of a layer are single tiles (the
-// first MMA starts after one tile's transfer, not after four), later ones fill the stage
+// k tiles of the n-th group of a K segment of `left` remaining tiles
 __device__ __forceinline__ int group_tiles(int n, int kg, int left) {
-  const int g = n < 2 ? 1 : kg;
-  return g < left ? g : left;
+  (void)n;   // (single-tile first groups were tried: the first MMA starts 0.2 us earlier, the main loops run 0.8 us longer)
+  return kg < left ? kg : left;
 }
 
 // producer thread: stream the A tiles of this row block and this CTA's weight slab through the stage ring
@@ -1369,6 +1370,8 @@ struct RolloutBwdParams {
   float *g_s, *g_hprior, *g_hdirect, *g_hgru, *g_za;
   long long ldS, ldZA;
   int kg_max;
+  unsigned long long* trace;   // profiling: [H+1][12 phases][8] %globaltimer stamps of cluster 0 (slots 0-2 producer / MMA,
+                               // 7 phase finished), nullptr = off
 };
 
 struct BwdEpi {
@@ -1379,23 +1382,166 @@ struct BwdEpi {
 };
 // (the register-hungry row phases are separate functions: the 64 live values of a softmax group or the gate gradients of a row
 // must not inflate the register allocation of the contraction phases around them)
+// straight-through softmax backward (rssm.py:34-37; bwdops::st_softmax_bwd_item restated for eight lanes per (row, group):
+// a lane holds four classes, max / sum / dot are three-step butterflies) — 4x the parallelism and no 64-value local arrays
 __device__ __noinline__ void bwd_softmax_phase(const float* logits, int S, const float* g_s_z, long long ldS, const float* g_za,
                                                long long ldZA, __nv_bfloat16* g_logits, int Sp, int row0, int rows, int M, int groups,
                                                int tid_e) {
-  for (int i = tid_e; i < rows * groups; i += kEpiThreads) {
-    const int mm = row0 + i / groups, g = i % groups;
-    if (mm < M) bwdops::st_softmax_bwd_item<true>(mm, g, logits, S, g_s_z, ldS, g_za, ldZA, g_logits, Sp);
+  const int lane = tid_e & 31, q = lane & 7;
+  const int items = rows * groups;
+  for (int base = (tid_e >> 5) * 4; base < items; base += (kEpiThreads >> 5) * 4) {
+    int it = base + (lane >> 3);
+    const bool live = it < items && row0 + it / groups < M;
+    if (!(it < items)) it = items - 1;
+    const int mm = min(row0 + it / groups, M - 1), g = it % groups;
+    const float4 l4 = __ldg(reinterpret_cast<const float4*>(logits + static_cast<size_t>(mm) * S + g * 32) + q);
+    float4 gz = __ldcg(reinterpret_cast<const float4*>(g_s_z + static_cast<size_t>(mm) * ldS + g * 32) + q);
+    if (g_za) {
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(g_za + static_cast<size_t>(mm) * ldZA + g * 32) + q);
+      gz.x += b.x; gz.y += b.y; gz.z += b.z; gz.w += b.w;
+    }
+    float mx = fmaxf(fmaxf(l4.x, l4.y), fmaxf(l4.z, l4.w));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float e0 = __expf(l4.x - mx), e1 = __expf(l4.y - mx), e2 = __expf(l4.z - mx), e3 = __expf(l4.w - mx);
+    float se = (e0 + e1) + (e2 + e3);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float inv = 1.0f / se;
+    e0 *= inv; e1 *= inv; e2 *= inv; e3 *= inv;
+    float dot = fmaf(gz.x, e0, fmaf(gz.y, e1, fmaf(gz.z, e2, gz.w * e3)));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (live) {
+      // classes [4q, 4q + 4) of the group: half of a 16-byte chunk of the packed image
+      const int col = g * 32 + q * 4;
+      __nv_bfloat16* dst = g_logits + packed_index(static_cast<size_t>(mm), static_cast<size_t>(col & ~7), static_cast<size_t>(Sp), kTileM) +
+                           (col & 4);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(rowops::bf2(e0 * (gz.x - dot), e1 * (gz.y - dot)),
+                                                   rowops::bf2(e2 * (gz.z - dot), e3 * (gz.w - dot)));
+    }
   }
 }
-__device__ __noinline__ void bwd_gate_phase(const bwdops::GruBwdArgs& ga, int row0, int rows, int we, int lane) {
-  for (int r = we; r < rows; r += 16) bwdops::gru_gate_bwd_row<true>(ga, row0 + r, lane);
-}
 
-// dX epilogue: acc = d loss / d y, y = ELU(LN?(pre)); ELU' and the LayerNorm backward (row sums over the group's CTAs through
-// the DSMEM exchange) -> packed bf16 d loss / d (pre-LayerNorm activation).  The thread's chunks stay in registers.
+// GRU gates + joint LayerNorm backward (common.py:69-81; bwdops::gru_gate_bwd_row restated): the `wpr` = 16 / rows warps of a
+// row take 4-unit slices of the D hidden units (a lane holds at most `kGateUnits` slices), the row sums of the LayerNorm
+// backward meet in shared memory, and the gate gradients of pass 1 stay in registers for pass 2.
+constexpr int kGateUnits = 2;
+__device__ __noinline__ void bwd_gate_phase(const bwdops::GruBwdArgs& a, int row0, int rows, int we, int lane, float2* red) {
+  const int D = a.D;
+  const int wpr = rows >= 16 ? 1 : 16 / rows;          // warps per row
+  const int r_local = we / wpr, half = we - r_local * wpr;
+  const bool has_row = r_local < rows;
+  const int m = row0 + (has_row ? r_local : 0);
+  const bool valid = has_row && m < a.M;
+  const int units = D >> 2;
+  const float inv_n = 1.0f / static_cast<float>(3 * D);
+  float mean = 0.f, rstd = 1.f;
+  if (valid) {
+    const float2* stp = reinterpret_cast<const float2*>(a.stats);
+    float s = 0.f, q = 0.f;
+    for (int b = 0; b < a.NB; ++b) {
+      const float2 v = __ldg(&stp[static_cast<size_t>(b) * a.m_pad + m]);
+      s += v.x;
+      q += v.y;
+    }
+    mean = s * inv_n;
+    rstd = 1.0f / sqrtf(fmaxf(q * inv_n - mean * mean, 0.f) + a.eps);
+  }
+  const float* src = a.scratch + static_cast<size_t>(m) * a.ld;
+  float dr[kGateUnits][4], dc[kGateUnits][4], du[kGateUnits][4], xr[kGateUnits][4], xc[kGateUnits][4], xu[kGateUnits][4];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < kGateUnits; ++k) {
+    const int u = half * 32 + lane + k * 32 * wpr;
+    if (valid && u < units) {
+      const int j0 = u * 4;
+      const float4 pr = *reinterpret_cast<const float4*>(src + j0), pc = *reinterpret_cast<const float4*>(src + D + j0),
+                   pu = *reinterpret_cast<const float4*>(src + 2 * D + j0);
+      const float4 hp = *reinterpret_cast<const float4*>(a.h_prev + static_cast<size_t>(m) * a.ld_h + j0);
+      float gh[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < a.n_gh; ++i) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.gh[i] + static_cast<size_t>(m) * a.ld_gh[i] + j0));
+        gh[0] += v.x; gh[1] += v.y; gh[2] += v.z; gh[3] += v.w;
+      }
+      const float4 gr4 = __ldg(reinterpret_cast<const float4*>(a.gamma + j0)), gc4 = __ldg(reinterpret_cast<const float4*>(a.gamma + D + j0)),
+                   gu4 = __ldg(reinterpret_cast<const float4*>(a.gamma + 2 * D + j0));
+      const float4 br4 = __ldg(reinterpret_cast<const float4*>(a.beta + j0)), bc4 = __ldg(reinterpret_cast<const float4*>(a.beta + D + j0)),
+                   bu4 = __ldg(reinterpret_cast<const float4*>(a.beta + 2 * D + j0));
+      const float vr[4] = {pr.x, pr.y, pr.z, pr.w}, vc[4] = {pc.x, pc.y, pc.z, pc.w}, vu[4] = {pu.x, pu.y, pu.z, pu.w};
+      const float vh[4] = {hp.x, hp.y, hp.z, hp.w};
+      const float ggr[4] = {gr4.x, gr4.y, gr4.z, gr4.w}, ggc[4] = {gc4.x, gc4.y, gc4.z, gc4.w}, ggu[4] = {gu4.x, gu4.y, gu4.z, gu4.w};
+      const float bbr[4] = {br4.x, br4.y, br4.z, br4.w}, bbc[4] = {bc4.x, bc4.y, bc4.z, bc4.w}, bbu[4] = {bu4.x, bu4.y, bu4.z, bu4.w};
+      float ghd[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xr[k][e] = (vr[e] - mean) * rstd;
+        xc[k][e] = (vc[e] - mean) * rstd;
+        xu[k][e] = (vu[e] - mean) * rstd;
+        const float nr = fmaf(xr[k][e], ggr[e], bbr[e]);
+        const float nc = fmaf(xc[k][e], ggc[e], bbc[e]);
+        const float nu = fmaf(xu[k][e], ggu[e], bbu[e]) + a.update_bias;
+        const float r = bwdops::fsig(nr);
+        const float c = bwdops::ftanh(r * nc);
+        const float uu = bwdops::fsig(nu);
+        const float g_u = gh[e] * (c - vh[e]);
+        const float g_t = gh[e] * uu * (1.0f - c * c);
+        dr[k][e] = g_t * nc * r * (1.0f - r) * ggr[e];
+        dc[k][e] = g_t * r * ggc[e];
+        du[k][e] = g_u * uu * (1.0f - uu) * ggu[e];
+        ghd[e] = gh[e] * (1.0f - uu);
+        s1 += dr[k][e] + dc[k][e] + du[k][e];
+        s2 += dr[k][e] * xr[k][e] + dc[k][e] * xc[k][e] + du[k][e] * xu[k][e];
+      }
+      *reinterpret_cast<float4*>(a.g_hdirect + static_cast<size_t>(m) * D + j0) = make_float4(ghd[0], ghd[1], ghd[2], ghd[3]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) red[we] = make_float2(s1, s2);
+  epi_bar(3);
+  float t1 = 0.f, t2 = 0.f;
+  for (int h = 0; h < wpr; ++h) {
+    const float2 v = red[r_local * wpr + h];
+    t1 += v.x;
+    t2 += v.y;
+  }
+  const float m1 = t1 * inv_n, m2 = t2 * inv_n;
+  if (has_row) {
+    const int row = m & 127;
+    __nv_bfloat16* img = a.g_pre + static_cast<size_t>(m >> 7) * (a.kpad >> 6) * (kTileM * kTileK);
+    auto put4 = [&](int col, float o0, float o1, float o2, float o3) {
+      *reinterpret_cast<uint2*>(img + pk_off(row, col & ~7) + (col & 4)) = make_uint2(rowops::bf2(o0, o1), rowops::bf2(o2, o3));
+    };
+#pragma unroll
+    for (int k = 0; k < kGateUnits; ++k) {
+      const int u = half * 32 + lane + k * 32 * wpr;
+      if (u < units) {
+        const int j0 = u * 4;
+        if (valid) {
+          put4(j0, rstd * (dr[k][0] - m1 - xr[k][0] * m2), rstd * (dr[k][1] - m1 - xr[k][1] * m2),
+               rstd * (dr[k][2] - m1 - xr[k][2] * m2), rstd * (dr[k][3] - m1 - xr[k][3] * m2));
+          put4(D + j0, rstd * (dc[k][0] - m1 - xc[k][0] * m2), rstd * (dc[k][1] - m1 - xc[k][1] * m2),
+               rstd * (dc[k][2] - m1 - xc[k][2] * m2), rstd * (dc[k][3] - m1 - xc[k][3] * m2));
+          put4(2 * D + j0, rstd * (du[k][0] - m1 - xu[k][0] * m2), rstd * (du[k][1] - m1 - xu[k][1] * m2),
+               rstd * (du[k][2] - m1 - xu[k][2] * m2), rstd * (du[k][3] - m1 - xu[k][3] * m2));
+        } else {   // padding rows of the operand image: zeros
+          put4(j0, 0.f, 0.f, 0.f, 0.f);
+          put4(D + j0, 0.f, 0.f, 0.f, 0.f);
+          put4(2 * D + j0, 0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    // padding columns [3D, kpad)
+    for (int c = (3 * D >> 2) + half * 32 + lane; c < (a.kpad >> 2); c += 32 * wpr) put4(c * 4, 0.f, 0.f, 0.f, 0.f);
+  }
+}
 template <int kBwdChunks>   // 8-column chunks per epilogue thread, at most: 2 (NC <= 64) or 4 (NC <= 128)
 __device__ __forceinline__ void epi_bwd_n(RCtl* ctl, const RLayer& L, int rank, bool ln, const BwdEpi& o, uint32_t tmem_d, int cq,
-                                          int row, bool row_ok, int tid_e, int par, Roles& st) {
+                                          int row, bool row_ok, int tid_e, int par, Roles& st, unsigned long long* trp) {
   const int gi = rank % L.cpg, g0 = rank - gi;
   const int width = L.width[gi], col0 = L.col0[gi];
   const int n_chunks = L.NC >> 3;
@@ -1409,6 +1555,7 @@ __device__ __forceinline__ void epi_bwd_n(RCtl* ctl, const RLayer& L, int rank, 
   }
   const float rstd = (ln && o.rstd) ? __ldg(o.rstd + row) : 1.0f;
   epi_begin(ctl, L, rank, tid_e, ln, st);
+  tr(trp, 3);
   uint32_t r[kBwdChunks][8];
 #pragma unroll
   for (int i = 0; i < kBwdChunks; ++i)
@@ -1444,9 +1591,11 @@ __device__ __forceinline__ void epi_bwd_n(RCtl* ctl, const RLayer& L, int rank, 
     }
   }
   float m1r = 0.f, m2r = 0.f;
+  tr(trp, 4);
   if (ln) {
     float2 total;
     ln_exchange(ctl, cq, row, s1, s2, g0, L.cpg, gi, L.n, 0.f, par, &total);
+    tr(trp, 5);
     const float inv_n = 1.0f / static_cast<float>(L.n);
     m1r = -total.x * inv_n * rstd;
     m2r = -total.y * inv_n * rstd;
@@ -1471,12 +1620,13 @@ __device__ __forceinline__ void epi_bwd_n(RCtl* ctl, const RLayer& L, int rank, 
     for (int ch = ((col0 + width + 7) >> 3) + cq; ch < (o.out_kpad >> 3); ch += 4)
       *reinterpret_cast<uint4*>(o.out + pk_off(row, ch * 8)) = make_uint4(0u, 0u, 0u, 0u);
   }
+  tr(trp, 6);
 }
 
 __device__ __noinline__ void epi_bwd(RCtl* ctl, const RLayer& L, int rank, bool ln, const BwdEpi& o, uint32_t tmem_d, int cq,
-                                     int row, bool row_ok, int tid_e, int par, Roles& st) {
-  if (L.NC <= 64) epi_bwd_n<2>(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, par, st);
-  else epi_bwd_n<4>(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, par, st);
+                                     int row, bool row_ok, int tid_e, int par, Roles& st, unsigned long long* trp) {
+  if (L.NC <= 64) epi_bwd_n<2>(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, par, st, trp);
+  else epi_bwd_n<4>(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, par, st, trp);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_constant__ RolloutBwdParams P, const int ring_bytes) {
@@ -1529,12 +1679,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
   const int rpc = kTileM / C;   // rows of the block per CTA in the row phases
   const bool lncfg = P.layer_norm != 0;
   int lnpar = 0;
+  const bool tracer = P.trace != nullptr && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 64);
+  unsigned long long* trp = nullptr;
+  int phase = 0;
+  auto stamp = [&](int t) { trp = tracer ? P.trace + (static_cast<size_t>(t) * 12 + phase) * 8 : nullptr; };
+  auto done = [&]() {
+    tr(trp, 7);
+    ++phase;
+  };
   auto tp = [&](int t, size_t off) { return P.tape + static_cast<size_t>(t) * P.tape_step + off; };
   auto run_mainloop = [&](const RLayer& L, const OpA& a, bool active) {
     if (warp == 0) {
-      if (active) produce(ctl, ring, ring_bytes, L, rank, a, st, 0, P.kg_max, nullptr);
+      if (active) produce(ctl, ring, ring_bytes, L, rank, a, st, 0, P.kg_max, trp);
     } else if (warp == 1) {
-      if (active) issue_mma(ctl, ring, ring_bytes, L, tmem_base, a, st, 0, P.kg_max, nullptr);
+      if (active) issue_mma(ctl, ring, ring_bytes, L, tmem_base, a, st, 0, P.kg_max, trp);
     }
   };
   // d loss / d a_t = columns [Sp, Sp + A) of the img_in dX the previous step left in g_za
@@ -1548,6 +1706,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
   };
 
   for (int t = P.H; t >= 1; --t) {
+    phase = 0;
+    stamp(t);
     // ---- d loss / d (reward, value) of state t -> head gradients; the previous step's action gradient ----------------
     if (t < P.H) extract_actions(t);
     if (warp >= 2 && tid_e < rpc) {
@@ -1556,6 +1716,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
                             P.m_pad, P.Gb, P.gb_reward, P.gb_critic, P.dy4);
     }
     layer_end(warp >= 2);
+    done();
+    stamp(t);
     // ---- reward head + target critic, layers 4 .. 1: dX with the ELU' / LayerNorm backward of the layer below ---------
     for (int l = 4; l >= 1; --l) {
       const RLayer& L = P.t_head[l];
@@ -1575,13 +1737,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
                     : nullptr;
         o.out = P.dh[l & 1] + static_cast<size_t>(grp) * hid_gs + blk_H;
         o.out_kpad = P.Hp;
-        epi_bwd(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st);
+        epi_bwd(ctl, L, rank, ln, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st, trp);
       } else if (ln) {
         __syncwarp();
         cluster_sync_all();
       }
       if (ln) lnpar ^= 1;
       layer_end(warp >= 2 && active);
+      done();
+      stamp(t);
     }
     // ---- layer 0 of the heads: the groups are K segments of one contraction -> d loss / d [h_t, z_t] ------------------
     {
@@ -1599,12 +1763,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
         epi_plain(ctl, L, rank, P.g_s + static_cast<size_t>(m) * P.ldS + L.col0[rank], L.width[rank], tmem_d, cq, row_ok);
       }
       layer_end(warp >= 2 && active);
+      done();
+      stamp(t);
     }
     // ---- z_t = onehot + p - p.detach(): d loss / d prior logits ------------------------------------------------------------
     if (warp >= 2)
       bwd_softmax_phase(P.logits + static_cast<size_t>(t) * NS, P.S, P.g_s + P.Dp, P.ldS, t < P.H ? P.g_za : nullptr, P.ldZA,
                         P.g_logits, P.Sp, rb * kTileM + rank * rpc, rpc, P.M, P.groups, tid_e);
     layer_end(warp >= 2);
+    done();
+    stamp(t);
     // ---- prior MLP: logits -> y (ELU' / LayerNorm backward of prior 1) -> h_t ----------------------------------------------
     {
       const RLayer& L = P.t_prior2;
@@ -1619,13 +1787,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
         o.rstd = lncfg ? reinterpret_cast<const float*>(tp(t, P.tp_y_rstd)) + rb * kTileM : nullptr;
         o.out = P.dp1 + blk_D;
         o.out_kpad = P.Dp;
-        epi_bwd(ctl, L, rank, lncfg, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st);
+        epi_bwd(ctl, L, rank, lncfg, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st, trp);
       } else if (lncfg) {
         __syncwarp();
         cluster_sync_all();
       }
       if (lncfg) lnpar ^= 1;
       layer_end(warp >= 2 && active);
+      done();
+      stamp(t);
     }
     {
       const RLayer& L = P.t_prior1;
@@ -1639,6 +1809,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
         epi_plain(ctl, L, rank, P.g_hprior + static_cast<size_t>(m) * P.D + L.col0[rank], L.width[rank], tmem_d, cq, row_ok);
       }
       layer_end(warp >= 2 && active);
+      done();
+      stamp(t);
     }
     // ---- h_t = GRU(x_t, h_{t-1}): gates + joint LayerNorm backward, one warp per row -------------------------------------------
     if (warp >= 2) {
@@ -1659,9 +1831,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
       }
       ga.g_pre = P.g_pre; ga.kpad = P.G3p;
       ga.g_hdirect = P.g_hdirect;
-      bwd_gate_phase(ga, rb * kTileM + rank * rpc, rpc, we, lane);
+      bwd_gate_phase(ga, rb * kTileM + rank * rpc, rpc, we, lane, &ctl->part[0][0]);
     }
     layer_end(warp >= 2);
+    done();
+    stamp(t);
     // ---- d / d x_t (with img_in's ELU' / LayerNorm backward) and d / d h_{t-1} through the gates: one phase, two groups -------
     {
       const RLayer& L = P.t_gru;
@@ -1677,7 +1851,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
         o.rstd = lncfg ? reinterpret_cast<const float*>(tp(t, P.tp_x_rstd)) + rb * kTileM : nullptr;
         o.out = P.dp_in + blk_D;
         o.out_kpad = P.Dp;
-        epi_bwd(ctl, L, rank, lncfg, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st);
+        epi_bwd(ctl, L, rank, lncfg, o, tmem_d, cq, row, row_ok, tid_e, lnpar, st, trp);
       } else {
         if (warp >= 2 && active) {
           epi_begin(ctl, L, rank, tid_e, false, st);
@@ -1691,6 +1865,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
       }
       if (lncfg) lnpar ^= 1;
       layer_end(warp >= 2 && active);
+      done();
+      stamp(t);
     }
     // ---- x_t = ELU(LN?(W_in [z_{t-1}, a_{t-1}])): d loss / d z_{t-1}, d loss / d a_{t-1} -------------------------------------------
     {
@@ -1705,6 +1881,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_bwd_kernel(const __grid_c
         epi_plain(ctl, L, rank, P.g_za + static_cast<size_t>(m) * P.ldZA + L.col0[rank], L.width[rank], tmem_d, cq, row_ok);
       }
       layer_end(warp >= 2 && active);
+      done();
+      stamp(t);
     }
   }
   extract_actions(0);
@@ -2081,6 +2259,7 @@ extern "C" int rlsb_rollout_bwd(const rlsb_imagine_cfg* cfg, const void* packed,
   rp.ldS = W.ldS; rp.ldZA = W.ldZA;
   rp.kg_max = 4;
   if (const char* env = getenv("RLSB_ROLLOUT_KG")) rp.kg_max = atoi(env) >= 1 ? atoi(env) : 1;
+  rp.trace = g_rollout_trace;
 
   const int ring_bytes = (227 * 1024 - 1024 - static_cast<int>(sizeof(RCtl)) - 256) / 1024 * 1024;
   const size_t smem = static_cast<size_t>(ring_bytes) + sizeof(RCtl) + 1024;

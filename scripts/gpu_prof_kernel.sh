@@ -1,7 +1,7 @@
 # one full ncu capture of a kernel of the default bench, with the per-instruction source page
-# usage: gpu_prof_kernel.sh <tag> <kernel regex> <launches to skip>
+# usage: [WORKLOAD=config1 WARMUP=3] gpu_prof_kernel.sh <tag> <kernel regex> <launches to skip>
 TAG=$1; RE=$2; SKIP=${3:-0}
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras"
+CMD="python bench.py ${WORKLOAD:+--workload $WORKLOAD} --steps 1 --warmup ${WARMUP:-1} --no-cpu-baseline --no-extras"
 $CMD > /dev/null 2>&1 || { echo plain run failed; exit 1; }
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$RE" -s $SKIP -c 1 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo full_exit=$?
