@@ -42,6 +42,12 @@ int rlsb_set_cluster_size(int cs);
  * shared memory and write it with one bulk copy (1, default; env RLSB_STAGED) or store 16 bytes per thread (0) — same
  * bits either way.  Any other value only queries.  Returns the value in effect. */
 int rlsb_set_staged_output(int on);
+/* tuning: the chained rollout (rlsb_imagine_fwd) runs LayerNorm + ELU of img_in / prior1 (rssm.py:179, :192) and the whole
+ * GRUCell (common.py:69-81) inside the epilogues of their contractions even where a row spans several n-blocks — the row
+ * statistics of the blocks' CTAs meet in global memory — instead of writing fp32 pre-activations for a second kernel
+ * (1, default; env RLSB_FUSED_RSSM; applies to flat RSSMs with D % 64 == 0 and no tape).  It changes the packed layout of the
+ * GRU weight: call rlsb_imagine_pack again after a change.  Any other value only queries.  Returns the value in effect. */
+int rlsb_set_fused_rssm(int on);
 
 /* ---- K2: lambda-return + shifted-cumprod weights + advantage --------------------------------
  * replaces ImaginativeCritic._lambda_return (agents/dreamer/ac.py:52-62), the discount

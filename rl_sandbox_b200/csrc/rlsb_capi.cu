@@ -7,6 +7,7 @@
 #include "rlsb_count.cuh"
 #include "rlsb_detmath.h"
 #include "rlsb_gemm.cuh"
+#include "rlsb_imagine_plan.cuh"
 #include "rlsb_kernels.cuh"
 #include "rlsb_wgrad.cuh"
 
@@ -50,6 +51,11 @@ extern "C" int rlsb_set_cluster_size(int cs) {
 }
 
 extern "C" int rlsb_set_staged_output(int on) { return set_gemm_staged_output(on); }
+
+extern "C" int rlsb_set_fused_rssm(int on) {
+  if (on == 0 || on == 1) k1::g_fused_rssm = on;
+  return k1::g_fused_rssm;
+}
 
 extern "C" int rlsb_check_device(void) {
   int dev = 0;

@@ -18,6 +18,7 @@
 #include "rlsb_gemm.cuh"
 #include "rlsb_count.cuh"
 #include "rlsb_ptx.cuh"
+#include "rlsb_rowops.cuh"
 
 namespace rlsb {
 
@@ -253,6 +254,25 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
 
 __device__ __forceinline__ void epi_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
+}
+
+// Cross-block LayerNorm (GemmParams::ln_sync): one thread of a CTA counts its tile into the row block's arrival counter
+// (release: the CTA's partial statistics were written and fenced before the barrier in front of this call) and spins until
+// all `n` n-blocks of the row block have arrived (acquire).  The last one to leave resets both counters for the next launch.
+// A partner that never arrives means the CTAs of the launch are not co-resident: trap (a launch error, not a hang).
+__device__ __forceinline__ void xln_arrive_wait(unsigned int* arrive, unsigned int* depart, unsigned int n) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(arrive), "r"(1u) : "memory");
+  unsigned int v;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(arrive) : "memory");
+    if (v >= n) break;
+    if (clock64() - t0 > (1ll << 32)) __trap();
+  }
+  if (atomicAdd(depart, 1u) == n - 1u) {
+    *reinterpret_cast<volatile unsigned int*>(depart) = 0u;
+    *reinterpret_cast<volatile unsigned int*>(arrive) = 0u;
+  }
 }
 
 // Pass 2 of the full-row epilogue with the output assembled in shared memory.  A thread owns one row, so its 16-byte
@@ -671,7 +691,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
   // staged output (ln_act_pass2_staged): two 16 KB slots for the output image (+ two for x_hat in the saving variant)
   uint8_t* stage_out = smem + static_cast<size_t>(stages) * stage_bytes;
   uint8_t* stage_pre = stage_out + 32768;
-  const uint32_t staging_bytes = p.staged_out ? (EPI == EPI_LN_ACT_SAVE ? 65536u : 32768u) : 0u;
+  const uint32_t staging_bytes = (p.staged_out || EPI == EPI_GRU) ? (EPI == EPI_LN_ACT_SAVE ? 65536u : 32768u) : 0u;
   uint8_t* xbuf = stage_out + staging_bytes;   // EPI_BWD: per-thread slots of the saved image (GemmParams::xbuf_bytes)
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(xbuf + (EPI == EPI_BWD ? static_cast<uint32_t>(p.xbuf_bytes) : 0u));
 
@@ -929,15 +949,18 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       const uint32_t s_bias = smem_u32(&ctl->bias[pb][0]);
       const uint32_t s_gam = smem_u32(&ctl->gamma[pb][0]);
       const uint32_t s_bet = smem_u32(&ctl->beta[pb][0]);
-      const bool has_ln = (kLnAct || EPI == EPI_BWD) && (p.ln_gamma != nullptr);
+      const bool has_ln = (kLnAct || EPI == EPI_BWD || EPI == EPI_GRU) && (p.ln_gamma != nullptr);
+      // LayerNorm over a row that spans the NB n-blocks of the group: statistics meet in global memory (GemmParams::ln_sync)
+      const bool xln = (kLnAct || EPI == EPI_GRU) && has_ln && p.NB > 1;
       // ---- stage this tile's parameters (overlaps the tile's main loop) ------------------------
       {
         const size_t poff = static_cast<size_t>(g) * p.NB * p.RB + col0;
+        const size_t lnoff = xln ? poff : static_cast<size_t>(g) * p.RB;
         for (int i = tid_e; i < p.RB; i += kEpiThreads) {
           if (EPI != EPI_BWD) sts32(s_bias + 4u * i, p.bias ? __ldg(p.bias + poff + i) : 0.f);
           if (has_ln) {
-            sts32(s_gam + 4u * i, __ldg(p.ln_gamma + static_cast<size_t>(g) * p.RB + i));
-            sts32(s_bet + 4u * i, __ldg(p.ln_beta + static_cast<size_t>(g) * p.RB + i));
+            sts32(s_gam + 4u * i, __ldg(p.ln_gamma + lnoff + i));
+            sts32(s_bet + 4u * i, __ldg(p.ln_beta + lnoff + i));
           }
         }
       }
@@ -947,6 +970,140 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * buf_cols) + lane_addr;
       const int m = tile_ok ? m_tile * kTileM + row : p.M + kTileM;   // padding tile: every row invalid
       const bool row_ok = tile_ok && row_is_valid(p, m);
+      // this block's row totals (identical in the row's four threads) -> totals over all NB blocks of the row
+      auto xln_exchange = [&](float tsum, float tsq, float& s_all, float& q_all) {
+        float2* st = reinterpret_cast<float2*>(p.stats) + static_cast<size_t>(g) * p.NB * m_pad;
+        if (tile_ok && cq == 0) {
+          st[static_cast<size_t>(nb) * m_pad + m] = make_float2(tsum, tsq);
+          __threadfence();
+        }
+        epi_bar(2);
+        if (tile_ok && tid_e == 0)
+          xln_arrive_wait(p.ln_sync + m_tile, p.ln_sync + p.m_tiles + m_tile, static_cast<unsigned int>(p.NB));
+        epi_bar(2);
+        s_all = 0.f;
+        q_all = 0.f;
+        if (tile_ok) {
+          for (int b = 0; b < p.NB; ++b) {
+            const float2 v = __ldcg(st + static_cast<size_t>(b) * m_pad + m);
+            s_all += v.x;
+            q_all += v.y;
+          }
+        }
+      };
+
+      if constexpr (EPI == EPI_GRU) {
+        // thread (row, cq) owns the chunks cq + 4 i, i < 6, of the block's 192 columns: i = 0, 1 reset | 2, 3 candidate |
+        // 4, 5 update pre-activations of the SAME hidden units 64 nb + 8 (cq + 4 j), j = i & 1.  The accumulator is copied
+        // to registers once (48 values) and its TMEM buffer handed back at once, so that waiting for the partner blocks'
+        // statistics never stalls the MMA warp.
+        float v[6][8];
+        float sum = 0.f, sq = 0.f;
+        {
+          uint32_t r[6][8];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) tmem_ld8(tmem_d + static_cast<uint32_t>((cq + 4 * i) * 8), r[i]);
+          tmem_ld_wait2(r[0], r[1]);
+          tmem_ld_wait2(r[2], r[3]);
+          tmem_ld_wait2(r[4], r[5]);
+          f32x2 sum2 = pk2(0.f, 0.f), sq2 = pk2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const uint32_t sb = s_bias + 32u * static_cast<uint32_t>(cq + 4 * i);
+            f32x2 b[4];
+            lds_2x2(sb, b[0], b[1]);
+            lds_2x2(sb + 16u, b[2], b[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const f32x2 x = fadd2(pk2u(r[i][2 * e], r[i][2 * e + 1]), b[e]);
+              sum2 = fadd2(sum2, x);
+              sq2 = ffma2(x, x, sq2);
+              unpk2(x, v[i][2 * e], v[i][2 * e + 1]);
+            }
+          }
+          float s0, s1, q0, q1;
+          unpk2(sum2, s0, s1);
+          unpk2(sq2, q0, q1);
+          sum = s0 + s1;
+          sq = q0 + q1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (pair && rank == 1) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->tmem_empty[buf]), 0u));
+          else mbar_arrive(&ctl->tmem_empty[buf]);
+        }
+        // h of the previous step for this thread's 2 x 8 hidden units (in flight across the exchange)
+        const int u0 = nb * 64;
+        float4 hp[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          hp[j][0] = hp[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok) {
+            const float4* src = reinterpret_cast<const float4*>(p.gru_h_prev + static_cast<size_t>(m) * p.gru_ld_h + u0 + (cq + 4 * j) * 8);
+            hp[j][0] = __ldg(src);
+            hp[j][1] = __ldg(src + 1);
+          }
+        }
+        sts64(s_part + 8u * (cq * kTileM + row), sum, sq);
+        epi_bar(2);
+        float tsum, tsq;
+        {
+          const float2 a0 = lds64(s_part + 8u * row), a1 = lds64(s_part + 8u * (kTileM + row)),
+                       a2 = lds64(s_part + 8u * (2 * kTileM + row)), a3 = lds64(s_part + 8u * (3 * kTileM + row));
+          tsum = (a0.x + a1.x) + (a2.x + a3.x);
+          tsq = (a0.y + a1.y) + (a2.y + a3.y);
+        }
+        float s_all, q_all;
+        xln_exchange(tsum, tsq, s_all, q_all);
+        const float mean = s_all * p.inv_n;
+        const float rstd = 1.0f / sqrtf(fmaxf(q_all * p.inv_n - mean * mean, 0.f) + p.ln_eps);
+        const float nmr = -mean * rstd;
+        const uint32_t slot = out_ph & 1u;
+        const uint32_t so = smem_u32(stage_out) + slot * 16384u + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t cr = 32u * static_cast<uint32_t>(cq + 4 * j);   // byte offset of the reset chunk's parameters
+          float y[8];
+          const float h[8] = {hp[j][0].x, hp[j][0].y, hp[j][0].z, hp[j][0].w, hp[j][1].x, hp[j][1].y, hp[j][1].z, hp[j][1].w};
+#pragma unroll
+          for (int e4 = 0; e4 < 2; ++e4) {
+            const float4 gr = lds128(s_gam + cr + 16u * e4), gc = lds128(s_gam + cr + 256u + 16u * e4),
+                         gu = lds128(s_gam + cr + 512u + 16u * e4);
+            const float4 br = lds128(s_bet + cr + 16u * e4), bc = lds128(s_bet + cr + 256u + 16u * e4),
+                         bu = lds128(s_bet + cr + 512u + 16u * e4);
+            const float wgr[4] = {gr.x, gr.y, gr.z, gr.w}, wgc[4] = {gc.x, gc.y, gc.z, gc.w}, wgu[4] = {gu.x, gu.y, gu.z, gu.w};
+            const float wbr[4] = {br.x, br.y, br.z, br.w}, wbc[4] = {bc.x, bc.y, bc.z, bc.w}, wbu[4] = {bu.x, bu.y, bu.z, bu.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = 4 * e4 + e;
+              const float rg = rowops::fast_sigmoid(fmaf(fmaf(v[j][k], rstd, nmr), wgr[e], wbr[e]));
+              const float cand = rowops::fast_tanh(rg * fmaf(fmaf(v[2 + j][k], rstd, nmr), wgc[e], wbc[e]));
+              const float ug = rowops::fast_sigmoid(fmaf(fmaf(v[4 + j][k], rstd, nmr), wgu[e], wbu[e]) + p.gru_update_bias);
+              y[k] = row_ok ? fmaf(ug, cand - h[k], h[k]) : 0.f;
+            }
+          }
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(p.gru_h_next + static_cast<size_t>(m) * p.gru_ld_hn + u0 + (cq + 4 * j) * 8);
+            dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+            dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+          }
+          sts128(so + ((static_cast<uint32_t>(cq + 4 * j) ^ static_cast<uint32_t>(row & 7)) << 4),
+                 make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+        }
+        // the packed bf16 image of h': k-tile nb of the row block, one 16 KB bulk store (two slots alternate)
+        if (tid_e == 0 && out_pending) bulk_wait_read<0>();
+        fence_proxy_async_smem();
+        epi_bar(4);
+        if (tid_e == 0 && tile_ok) {
+          bulk_s2g(p.out_bf16 + (static_cast<size_t>(m_tile) * (p.out_kpad >> 6) + nb) * (kTileM * kTileK),
+                   stage_out + slot * 16384u, 16384u);
+          bulk_commit();
+          out_pending = true;
+        }
+        out_ph ^= 1u;
+        continue;
+      }
 
       if (EPI == EPI_BWD) {
         if (tile_ok) {
@@ -1152,9 +1309,11 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
             if (cq == 0 && tile_ok)
               reinterpret_cast<float2*>(p.stats)[static_cast<size_t>(gnb) * m_pad + m] = make_float2(tsum, tsq);
           } else {
-            const float inv_n = n_valid == p.N ? p.inv_n : 1.0f / static_cast<float>(n_valid);
-            mean = tsum * inv_n;
-            const float var = fmaxf(tsq * inv_n - mean * mean, 0.f);
+            float ts = tsum, tq = tsq;
+            if (xln) xln_exchange(tsum, tsq, ts, tq);
+            const float inv_n = (xln || n_valid == p.N) ? p.inv_n : 1.0f / static_cast<float>(n_valid);
+            mean = ts * inv_n;
+            const float var = fmaxf(tq * inv_n - mean * mean, 0.f);
             rstd = 1.0f / sqrtf(var + p.ln_eps);
             if (p.save_rstd && cq == 0 && tile_ok) {
               if (p.alt_group_p1 == 0) p.save_rstd[static_cast<size_t>(g) * m_pad + m] = rstd;
@@ -1178,12 +1337,14 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
                                : (p.alt_group_p1 == 0 ? p.save_pre + goff + tile_off
                                                       : (alt ? p.save_pre + tile_off : nullptr));
         // staged: tile pointers without the row term (the slot already is the 128-row tile)
-        __nv_bfloat16* gout = obase - static_cast<size_t>(row) * kTileK;
+        // (NB > 1: this block's RB / 64 tiles of the image)
+        __nv_bfloat16* gout = obase - static_cast<size_t>(row) * kTileK + static_cast<size_t>(col0 >> 6) * (kTileM * kTileK);
         __nv_bfloat16* gpre = pbase ? pbase - static_cast<size_t>(row) * kTileK : nullptr;
+        const int kt_out = p.NB == 1 ? (p.out_kpad >> 6) : (p.RB >> 6);
 #define RLSB_P2(ACT, LN, SAVE)                                                                                            \
   do {                                                                                                                    \
     if (p.staged_out)                                                                                                     \
-      ln_act_pass2_staged<ACT, LN, SAVE>(tmem_d, cq, n_valid, p.out_kpad >> 6, row, tid_e, s_bias, s_gam, s_bet, rstd, nmr, \
+      ln_act_pass2_staged<ACT, LN, SAVE>(tmem_d, cq, n_valid, kt_out, row, tid_e, s_bias, s_gam, s_bet, rstd, nmr, \
                                          row_ok, stage_out, stage_pre, gout, gpre, out_ph, out_pending);                  \
     else                                                                                                                  \
       ln_act_pass2<ACT, LN, SAVE>(tmem_d, cq, my_chunks, n_valid, col0, row, s_bias, s_gam, s_bet, rstd, nmr, obase,      \
@@ -1220,7 +1381,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       }
     }
     if (bwd_colsum) flush_colsum(g_acc);
-    if (kLnAct && tid_e == 0 && out_pending) bulk_wait<0>();   // staged output: every bulk store has landed
+    if ((kLnAct || EPI == EPI_GRU) && tid_e == 0 && out_pending) bulk_wait<0>();   // staged output: every bulk store has landed
   }
 
   tc_fence_before();
@@ -1287,7 +1448,14 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   if (p.RB <= 0 || p.RB > 512 || (p.RB % 32) != 0) return -1;
   if (p.n_seg < 1 || p.n_seg > kMaxSeg) return -2;
   if (epilogue == EPI_LN_ACT && p.save_pre) epilogue = EPI_LN_ACT_SAVE;
-  if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB != 1 && p.ln_gamma != nullptr) return -3;  // LayerNorm needs the whole row
+  // LayerNorm needs the whole row: one block, or the cross-block exchange
+  const bool xln = (epilogue == EPI_LN_ACT || epilogue == EPI_GRU) && p.NB != 1 && p.ln_gamma != nullptr;
+  if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB != 1 && p.ln_gamma != nullptr && !p.ln_sync) return -3;
+  if (xln && (!p.ln_sync || !p.stats || p.G != 1 || p.N != p.NB * p.RB || p.row_period != 0)) return -3;
+  if (epilogue == EPI_GRU && (p.RB != 192 || !p.ln_gamma || !p.gru_h_prev || !p.gru_h_next || !p.out_bf16 || p.G != 1 ||
+                              p.out_kpad != p.NB * 64 || (p.gru_ld_h % 4) != 0 || (p.gru_ld_hn % 4) != 0 ||
+                              (reinterpret_cast<uintptr_t>(p.gru_h_prev) % 16) != 0 || (reinterpret_cast<uintptr_t>(p.gru_h_next) % 16) != 0))
+    return -10;
   if (p.M <= 0 || p.m_tiles != (p.M + kTileM - 1) / kTileM) return -4;
   if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE || epilogue == EPI_BWD) && ((p.out_kpad % 64) != 0 || p.out_kpad < p.N)) return -5;
   if (epilogue == EPI_BWD && ((p.NB != 1 && p.ln_gamma) || !p.bwd_pre || !p.out_bf16 || !p.group_major ||
@@ -1306,8 +1474,9 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   const bool staged_f32 = g_staged_f32 && (epilogue == EPI_PLAIN || epilogue == EPI_STATS) && (p.N % 32) == 0 &&
                           (p.ldo % 4) == 0 && p.out_f32 != nullptr && (reinterpret_cast<uintptr_t>(p.out_f32) % 16) == 0 &&
                           (p.out_group_stride % 4) == 0;
-  const bool staged = staged_f32 || (g_staged && (epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB == 1);
-  const int staging_bytes = staged ? (epilogue == EPI_LN_ACT_SAVE ? 65536 : 32768) : 0;
+  const bool staged = staged_f32 || (g_staged && (epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) &&
+                                     (p.NB == 1 || ((p.RB % 64) == 0 && p.NB * p.RB == p.out_kpad)));
+  const int staging_bytes = (staged || epilogue == EPI_GRU) ? (epilogue == EPI_LN_ACT_SAVE ? 65536 : 32768) : 0;
   int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256 - staging_bytes;
   static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
   // EPI_BWD: a 16-byte slot per epilogue thread and chunk for the saved image (two stages must still fit)
@@ -1373,6 +1542,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
     case EPI_LN_ACT: RLSB_LAUNCH(EPI_LN_ACT); break;
     case EPI_BWD: RLSB_LAUNCH(EPI_BWD); break;
     case EPI_LN_ACT_SAVE: RLSB_LAUNCH(EPI_LN_ACT_SAVE); break;
+    case EPI_GRU: RLSB_LAUNCH(EPI_GRU); break;
     default: return -7;
   }
 #undef RLSB_LAUNCH

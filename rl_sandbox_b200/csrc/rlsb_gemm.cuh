@@ -18,6 +18,9 @@ enum GemmEpilogue : int {
   EPI_LN_ACT = 2,  // full row in TMEM: [LayerNorm] -> activation -> packed bf16 (+ optional saves for backward)
   EPI_LN_ACT_SAVE = 4,  // EPI_LN_ACT that also stores save_pre / save_rstd (selected by the launcher when save_pre != nullptr)
   EPI_BWD = 3,     // full row in TMEM: acc = dL/d(act output); ELU' and LayerNorm backward -> packed bf16 dL/d(pre-LN)
+  EPI_GRU = 5,     // GRU cell (common.py:69-81) fused into its contraction: n-block nb holds the [reset | candidate | update]
+                   // pre-activations of hidden units [64 nb, 64 nb + 64) (RB = 192, weight rows permuted by the packer); the
+                   // joint LayerNorm over all 3D columns goes through the cross-block exchange (ln_sync); writes only h'
 };
 
 enum Activation : int { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2 };
@@ -72,6 +75,18 @@ struct GemmParams {
   int alt_group_p1;
   const __nv_bfloat16* alt_A;
   __nv_bfloat16* alt_out_bf16;
+  // ---- LayerNorm over a row that spans NB > 1 n-blocks (EPI_LN_ACT with NB > 1, EPI_GRU): every CTA writes its block's
+  //      (sum, sum of squares) per row into `stats` ([G][NB][M_pad][2], as EPI_STATS), counts itself into ln_sync[m_tile] and
+  //      waits until all NB blocks of the row block have arrived — the CTAs of a launch are co-resident (grid <= #SMs, one CTA
+  //      per SM) and walk the work items n-block-fastest, so the partners of a tile are running or finished.  The counters
+  //      reset themselves (second word per tile: departures); zero them once.  ln_sync: [2][m_tiles] uint32.
+  unsigned int* ln_sync;
+  // ---- EPI_GRU: h' = u * cand + (1 - u) * h ------------------------------------------------
+  const float* gru_h_prev;   // fp32 [M][gru_ld_h]
+  long long gru_ld_h;
+  float* gru_h_next;         // fp32 [M][gru_ld_hn]; the packed bf16 image goes to out_bf16 (out_kpad = NB * 64)
+  long long gru_ld_hn;
+  float gru_update_bias;
   // ---- set by launch_gemm (callers leave it 0): the full-row epilogue assembles each 128 x 64 output tile (16 KB, contiguous
   //      in the packed image) in shared memory and writes it with one bulk copy instead of 16-byte stores scattered over 32 rows
   int staged_out;

@@ -21,6 +21,13 @@
 
 namespace rlsb {
 
+namespace k1 {
+int g_fused_rssm = [] {
+  const char* e = getenv("RLSB_FUSED_RSSM");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+}  // namespace k1
+
 using namespace k1;
 
 namespace {
@@ -130,10 +137,18 @@ extern "C" int rlsb_imagine_pack(const rlsb_imagine_cfg* cfg, const rlsb_imagine
   {
     const LayerPlan& L = P.gru;  // input = cat[x, h]
     PackSeg segs[2] = {{0, 0, P.D}, {P.Dp, P.D, P.D}};
-    RLSB_TRY(pack_weight(P, prm->gru_w, 2 * P.D, L.N, wptr(L), L, 2, segs, s));
-    RLSB_TRY(copy_pad(prm->gru_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
-    RLSB_TRY(copy_pad(prm->gru_ln_g, L.N, fptr(L.g_off), L.N, 1.f, s));
-    RLSB_TRY(copy_pad(prm->gru_ln_b, L.N, fptr(L.b_off), L.N, 0.f, s));
+    if (P.gru_fused) {
+      // fused cell: n-block nb = [reset | candidate | update] rows of hidden units [64 nb, 64 nb + 64), vectors likewise
+      RLSB_TRY(launch_pack_perm(prm->gru_w, 2 * P.D, L.N, wptr(L), L.RB, L.NB * L.RB, L.kp, 2, segs, P.D, s));
+      RLSB_TRY(launch_copy_gru_perm(prm->gru_b, P.D, fptr(L.bias_off), 0.f, s));
+      RLSB_TRY(launch_copy_gru_perm(prm->gru_ln_g, P.D, fptr(L.g_off), 1.f, s));
+      RLSB_TRY(launch_copy_gru_perm(prm->gru_ln_b, P.D, fptr(L.b_off), 0.f, s));
+    } else {
+      RLSB_TRY(pack_weight(P, prm->gru_w, 2 * P.D, L.N, wptr(L), L, 2, segs, s));
+      RLSB_TRY(copy_pad(prm->gru_b, L.N, fptr(L.bias_off), L.NB * L.RB, 0.f, s));
+      RLSB_TRY(copy_pad(prm->gru_ln_g, L.N, fptr(L.g_off), L.N, 1.f, s));
+      RLSB_TRY(copy_pad(prm->gru_ln_b, L.N, fptr(L.b_off), L.N, 0.f, s));
+    }
   }
   {
     const LayerPlan& L = P.prior1;
@@ -269,6 +284,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   float* scratch = reinterpret_cast<float*>(ws + W.scratch);
   float* stats = reinterpret_cast<float*>(ws + W.stats);
   float* head_out = reinterpret_cast<float*>(ws + W.head_out);
+  unsigned int* ln_sync = reinterpret_cast<unsigned int*>(ws + W.ln_sync);
   const bool ln = cfg->layer_norm != 0;
   const float eps = 1e-5f;
   const size_t ND = static_cast<size_t>(Ms) * P.D, NS = static_cast<size_t>(Ms) * P.S;
@@ -326,6 +342,9 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     }
     e = cudaMemsetAsync(out->actions, 0, static_cast<size_t>(N) * P.A * 4, s);
     if (e != cudaSuccess) return static_cast<int>(e);
+    // counters of the cross-block LayerNorm (they reset themselves after every launch; cleared once per rollout anyway)
+    e = cudaMemsetAsync(ln_sync, 0, static_cast<size_t>(2) * ms_tiles * 4, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
     RLSB_TRY(launch_onehot_to_idx(z0, Ms, cfg->groups, cfg->classes, out->stoch_idx, s));
   }
 
@@ -349,6 +368,15 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       g.out_bf16 = outp; g.out_kpad = P.Dp; g.out_bf16_group_stride = 0;
       g.save_pre = reinterpret_cast<__nv_bfloat16*>(save_pre);
       g.save_rstd = has_ln ? reinterpret_cast<float*>(save_rstd) : nullptr;
+      return launch_gemm(g, EPI_LN_ACT, s);
+    }
+    if (g_fused_rssm && !save_pre && (L.RB % 64) == 0 && L.NB * L.RB == P.Dp && L.N == P.Dp) {
+      // the row spans NB n-blocks: LayerNorm statistics meet across the blocks' CTAs (GemmParams::ln_sync)
+      g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
+      g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
+      g.act = ACT_ELU;
+      g.out_bf16 = outp; g.out_kpad = P.Dp; g.out_bf16_group_stride = 0;
+      g.stats = stats; g.ln_sync = ln_sync;
       return launch_gemm(g, EPI_LN_ACT, s);
     }
     g.out_f32 = scratch; g.ldo = W.ld_scratch; g.out_group_stride = 0; g.stats = stats;
@@ -462,6 +490,16 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       g.n_seg = 2;
       g.A[0] = bf(W.xbf); g.a_ktiles[0] = P.Dp / 64;
       g.A[1] = hb; g.a_ktiles[1] = P.Dp / 64;
+      if (P.gru_fused) {
+        // the whole cell in the contraction's epilogue: only h' leaves the kernel (fp32 state + packed bf16 operand image)
+        g.ln_gamma = pf(P.gru.g_off); g.ln_beta = pf(P.gru.b_off);
+        g.stats = stats; g.ln_sync = ln_sync;
+        g.gru_h_prev = out->determ + static_cast<size_t>(t) * ND; g.gru_ld_h = P.D;
+        g.gru_h_next = out->determ + static_cast<size_t>(t + 1) * ND; g.gru_ld_hn = P.D;
+        g.gru_update_bias = -1.0f;
+        g.out_bf16 = himg(t + 1); g.out_kpad = P.Dp;
+        RLSB_TRY(launch_gemm(g, EPI_GRU, s));
+      } else {
       // with a tape the pre-LayerNorm gate activations of this transition are kept (slot t+1)
       float* gsc = tape ? reinterpret_cast<float*>(tp(t + 1, TP.gru_scratch)) : scratch;
       float* gst = tape ? reinterpret_cast<float*>(tp(t + 1, TP.gru_stats)) : stats;
@@ -471,6 +509,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
                                pf(P.gru.g_off), pf(P.gru.b_off), eps, -1.0f,
                                out->determ + static_cast<size_t>(t) * ND, P.D,
                                out->determ + static_cast<size_t>(t + 1) * ND, P.D, himg(t + 1), P.Dp, s));
+      }
     }
     // ---- prior logits = W2 ELU(LN?(W1 h' + b1)) + b2                      rssm.py:192 ----------
     const __nv_bfloat16* prior_in = himg(t + 1);

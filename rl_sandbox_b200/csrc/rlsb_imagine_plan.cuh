@@ -37,6 +37,11 @@ inline void plan_nb(LayerPlan& L) {
   }
 }
 
+// Fused RSSM epilogues of the chained rollout (rlsb_set_fused_rssm, default on): LayerNorm + ELU of img_in / prior1 and the
+// whole GRU cell run inside their contractions' epilogues even when a row spans several n-blocks (GemmParams::ln_sync);
+// 0 = contraction -> fp32 pre-activations -> ln_act_kernel / gru_gate_kernel.  Read by make_plan: re-pack after a change.
+extern int g_fused_rssm;
+
 // transposed weight image for a backward (dX) GEMM: rows = in-features (padded), K = out-features
 struct TLayer {
   int RB = 0, NB = 0, kp = 0;
@@ -54,6 +59,8 @@ struct Plan {
   // ---- split-operand contraction mode (cfg.parity): every weight image carries [Whi | Wlo | Whi] per input segment,
   //      i.e. LayerPlan::kp is three times the padded input width (rlsb_imagine_parity.cu)
   bool parity = false;
+  // ---- GRU cell fused into its contraction (EPI_GRU): P.gru has NB = D / 64 blocks of RB = 192 permuted rows
+  bool gru_fused = false;
   // ---- backward (cfg.with_backward): dX operands ----
   bool bwd = false;
   int Gb = 0, gb0 = 0;       // head groups that carry gradient: gb0 .. gb0+Gb-1 (reward .. target critic)
@@ -101,6 +108,12 @@ inline int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
   };
   P.img_in.N = P.D; P.img_in.kp = kmul * (P.Sp + P.Ap); finish(P.img_in, ru(P.D, 32));
   P.gru.N = 3 * P.D; P.gru.kp = kmul * 2 * P.Dp; finish(P.gru, 3 * P.D);
+  // (finish() placed NB * RB >= 3 D rows; the fused layout has exactly 3 D of them)
+  P.gru_fused = g_fused_rssm != 0 && !c.with_backward && !P.parity && P.K == 1 && (P.D % 64) == 0 && !P.gru.fullrow;
+  if (P.gru_fused) {
+    P.gru.NB = P.D / 64;
+    P.gru.RB = 192;
+  }
   P.prior1.N = P.D; P.prior1.kp = kmul * P.Dp;   finish(P.prior1, ru(P.D, 32));
   P.prior2.N = P.S; P.prior2.kp = kmul * P.Dp;   finish(P.prior2, 32);
   for (int l = 0; l < 5; ++l) {
@@ -173,6 +186,7 @@ inline void make_tape(const Plan& P, long long N, int H, Tape& T) {
 
 struct Workspace {
   size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
+  size_t ln_sync;   // [2][ms_pad / 128] uint32 arrival / departure counters of the cross-block LayerNorm (GemmParams::ln_sync)
   // slotted RSSM: per-slot operand planes for the heads and the mixer's buffers
   size_t hplanes, zplanes, hpost, mix_ln, mix_qkv, mix_upd, mix_fc;
   // split-operand mode (Plan::parity): fp32 pre-activation buffers, the residual ("lo") images and a zero image
@@ -203,6 +217,7 @@ inline void make_workspace(const Plan& P, long long N, Workspace& W) {
   if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
   W.stats = place(cur, static_cast<size_t>(nbmax) * ms_pad * 2 * 4);
   W.head_out = place(cur, static_cast<size_t>(P.G) * m_pad * 32 * 4);
+  W.ln_sync = place(cur, static_cast<size_t>(2) * (ms_pad / 128) * 4);
   W.ld_qkv = ru(3 * P.D, 4);
   W.hplanes = W.zplanes = W.hpost = W.mix_ln = W.mix_qkv = W.mix_upd = W.mix_fc = 0;
   if (P.K > 1) {

@@ -36,7 +36,18 @@ struct PackArgs {
   __nv_bfloat16* dst;
   int RB, rows_dst_pad, k_pad, n_seg;
   PackSeg seg[8];
+  int perm_D = 0;   // > 0: GRU weight for the fused cell (EPI_GRU): destination row 192 nb + 64 gate + u <- source row
+                    // gate * D + 64 nb + u (n-block nb holds [reset | candidate | update] of hidden units [64 nb, 64 nb + 64))
 };
+__host__ __device__ __forceinline__ long long gru_perm_row(long long r, int D) {
+  const long long nb = r / 192;
+  const int j = static_cast<int>(r - nb * 192);
+  return static_cast<long long>(j >> 6) * D + nb * 64 + (j & 63);
+}
+__global__ void copy_gru_perm_kernel(const float* src, int D, float* dst, float fill) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 3 * D) dst[i] = src ? src[gru_perm_row(i, D)] : fill;
+}
 
 __global__ void pack_kernel(const PackArgs a) {
   const long long chunks_per_row = a.k_pad >> 3;
@@ -44,6 +55,7 @@ __global__ void pack_kernel(const PackArgs a) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = i / chunks_per_row;
+    const long long srow = a.perm_D ? gru_perm_row(row, a.perm_D) : row;
     const int k0 = static_cast<int>(i - row * chunks_per_row) << 3;
     float v[8];
 #pragma unroll
@@ -54,7 +66,7 @@ __global__ void pack_kernel(const PackArgs a) {
         for (int s = 0; s < a.n_seg; ++s) {
           const int off = k - a.seg[s].dst_k0;
           if (off >= 0 && off < a.seg[s].len) {
-            x = __ldg(a.src + row * a.ld_src + a.seg[s].src_c0 + off);
+            x = __ldg(a.src + srow * a.ld_src + a.seg[s].src_c0 + off);
             if (a.seg[s].part) x = bf16_residual(x);
           }
         }
@@ -85,6 +97,7 @@ __global__ void pack_multi_kernel(const __grid_constant__ PackJobs J) {
     const long long li = i - J.first[j];
     const long long chunks_per_row = a.k_pad >> 3;
     const long long row = li / chunks_per_row;
+    const long long srow = a.perm_D ? gru_perm_row(row, a.perm_D) : row;
     const int k0 = static_cast<int>(li - row * chunks_per_row) << 3;
     float v[8];
 #pragma unroll
@@ -95,7 +108,7 @@ __global__ void pack_multi_kernel(const __grid_constant__ PackJobs J) {
         for (int s = 0; s < a.n_seg; ++s) {
           const int off = k - a.seg[s].dst_k0;
           if (off >= 0 && off < a.seg[s].len) {
-            x = __ldg(a.src + row * a.ld_src + a.seg[s].src_c0 + off);
+            x = __ldg(a.src + srow * a.ld_src + a.seg[s].src_c0 + off);
             if (a.seg[s].part) x = bf16_residual(x);
           }
         }
@@ -802,10 +815,23 @@ int flush_pads() {
 
 int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
                 int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream) {
+  return launch_pack_perm(src, ld_src, rows_src, dst, RB, rows_dst_pad, k_pad, n_seg, segs, 0, stream);
+}
+
+int launch_copy_gru_perm(const float* src, int D, float* dst, float fill, cudaStream_t stream) {
+  if (D <= 0 || (D % 64) != 0) return -1;
+  copy_gru_perm_kernel<<<(3 * D + 255) / 256, 256, 0, stream>>>(src, D, dst, fill);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_pack_perm(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB, int rows_dst_pad, int k_pad,
+                     int n_seg, const PackSeg* segs, int gru_perm_D, cudaStream_t stream) {
   if (n_seg < 0 || n_seg > 8 || (k_pad % 64) != 0 || RB <= 0 || (rows_dst_pad % RB) != 0) return -1;
+  if (gru_perm_D && (RB != 192 || (gru_perm_D % 64) != 0 || rows_src != 3 * gru_perm_D || rows_dst_pad != rows_src)) return -1;
   PackArgs a{};
   a.src = src; a.ld_src = ld_src; a.rows_src = rows_src; a.dst = dst; a.RB = RB;
-  a.rows_dst_pad = rows_dst_pad; a.k_pad = k_pad; a.n_seg = n_seg;
+  a.rows_dst_pad = rows_dst_pad; a.k_pad = k_pad; a.n_seg = n_seg; a.perm_D = gru_perm_D;
   for (int s = 0; s < n_seg; ++s) a.seg[s] = segs[s];
   const long long total = static_cast<long long>(rows_dst_pad) * (k_pad / 8);
   if (t_batch.active && t_batch.stream == stream) {

@@ -37,6 +37,12 @@ struct LaunchBatchScope {
 
 int launch_pack(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB,
                 int rows_dst_pad, int k_pad, int n_seg, const PackSeg* segs, cudaStream_t stream);
+// launch_pack with the GRU weight's row permutation for the fused cell (EPI_GRU, rlsb_gemm.cuh): gru_perm_D = D > 0 takes
+// destination row 192 nb + 64 gate + u from source row gate * D + 64 nb + u (RB must be 192, rows 3 D); 0 = launch_pack
+int launch_pack_perm(const float* src, long long ld_src, int rows_src, __nv_bfloat16* dst, int RB, int rows_dst_pad, int k_pad,
+                     int n_seg, const PackSeg* segs, int gru_perm_D, cudaStream_t stream);
+// the same permutation for the GRU's fp32 vectors of length 3 D (bias, LayerNorm gain / offset); src == nullptr: all `fill`
+int launch_copy_gru_perm(const float* src, int D, float* dst, float fill, cudaStream_t stream);
 
 // transposed variant: logical T[r][c] = src[c * ld_src + r] for r < rows, c < cols (nn.Linear weight
 // [cols = out, rows = in] -> operand whose rows are the in-features), zero padded

@@ -1,0 +1,11 @@
+# fused RSSM epilogues: parity tests, then A/B of the sweep bench with the switch off / on
+TAG=${1:-fz}
+timeout 300 python -m pytest tests/test_gpu_fused_rssm.py -m gpu -q -x -s 2>&1 | grep "fused rssm\|parity\|passed\|failed\|Error\|error" | tail -60
+for x in 0 1; do
+  RLSB_FUSED_RSSM=$x timeout 300 python bench.py --workload sweep --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_sweep_${x}_$TAG.json 2> gpurun_out/bench_sweep_${x}_$TAG.err; echo exit=$?
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_sweep_${x}_$TAG.json"))
+print("sweep RLSB_FUSED_RSSM=$x", round(d["ms_per_step"],3), round(d["e2e"]["ms_per_step"],3), d["gpu_launches"], d.get("imagination_only"), d["roofline"]["achieved"], d["roofline"]["ms_per_launch"])
+PY
+done

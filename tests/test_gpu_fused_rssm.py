@@ -1,0 +1,107 @@
+"""The chained rollout's fused RSSM epilogues (rlsb_set_fused_rssm, default on): LayerNorm + ELU of img_in / prior1 and the whole
+GRU cell (common.py:69-81) run inside their contractions even though a row spans several n-blocks — the blocks' CTAs exchange
+their row statistics through global memory and a self-resetting arrival counter (GemmParams::ln_sync) — against the unfused
+chain (contraction -> fp32 pre-activations -> ln_act_kernel / gru_gate_kernel) and the oracle.
+
+Same arithmetic, different summation order of the LayerNorm statistics (and 192- instead of 256-column blocks for the GRU):
+the two agree to fp32 rounding before each bf16 re-quantisation, so trajectories are compared on the rows whose draws coincide.
+The reference-golden parity tests of tests/test_gpu_imagine.py (c1, c1_long: D = 1024) run the fused path as the default.
+"""
+import pytest
+import torch
+
+from oracle import oracle_port as orc
+from tests._golden import load_case
+from tests.test_gpu_imagine import engine, rel_rms
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from rl_sandbox_b200 import ops as _ops
+    return _ops
+
+
+@pytest.fixture()
+def lib(cuda):
+    from rl_sandbox_b200 import _lib
+    lib = _lib.load()
+    before = lib.rlsb_set_fused_rssm(-1)
+    yield lib
+    lib.rlsb_set_fused_rssm(before)
+
+
+def _run(ops, lib, cuda, c, H, n, fused, h0, z0, lat, act, **kw):
+    assert lib.rlsb_set_fused_rssm(1 if fused else 0) == (1 if fused else 0)
+    eng = engine(ops, c["meta"], cuda, c, H, "chained")     # packs under the switch in effect
+    l0 = lib.rlsb_launch_count(0)
+    out = eng.rollout(h0.to(cuda), z0.to(cuda), None, lat.to(cuda), act.to(cuda), horizon=H, **kw)
+    torch.cuda.synchronize()
+    launches = lib.rlsb_launch_count(0) - l0
+    return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in out.items()}, launches
+
+
+@pytest.mark.parametrize("n", [1, 128, 129, 300, 800, 4096])
+def test_fused_matches_unfused_and_oracle(ops, lib, cuda, n):
+    """one row, an exact row block, an odd number of row blocks (a padding CTA in the last CTA pair), the configured 800
+    start states and 32 row blocks (more work items than CTA pairs: the self-resetting counters across work rounds)"""
+    c = load_case("c1")
+    m = c["meta"]
+    H = 4
+    h0, z0 = orc.make_start(n + 11, n, m["D"])
+    g = torch.Generator().manual_seed(n)
+    lat, act = torch.rand(H, n, 1024, generator=g), torch.rand(H, n, m["A"], generator=g)
+    a, la = _run(ops, lib, cuda, c, H, n, False, h0, z0, lat, act)
+    b, lb = _run(ops, lib, cuda, c, H, n, True, h0, z0, lat, act)
+    print(f"[fused rssm] n={n}: launches per rollout unfused {la}, fused {lb}")
+    assert lb <= la - 3 * H      # gru_gate_kernel + 2 x ln_act_kernel per step are gone
+    own = orc.sample_categorical(b["logits"][1:].cpu().view(H, n, 32, 32), lat.view(H, n, 32, 32))
+    assert torch.equal(own, b["stoch_idx"][1:].cpu().long())
+    same = (a["stoch_idx"] == b["stoch_idx"]).all(-1) & (a["actions"].argmax(-1) == b["actions"].argmax(-1))
+    alive = same.cumprod(0).bool()
+    frac = alive[-1].float().mean().item()
+    print(f"[fused rssm] n={n}: rows with identical draws over {H} steps: {frac:.3f}")
+    assert frac > 0.9 or n == 1
+    # the first transition runs every fused layer once from identical inputs
+    assert rel_rms(b["determ"][1], a["determ"][1], f"n={n} determ[1] fused vs unfused") < 1e-5
+    assert rel_rms(b["logits"][1], a["logits"][1], f"n={n} logits[1] fused vs unfused") < 2e-3
+    for k, lim in (("determ", 2e-4), ("logits", 2e-3), ("rewards", 1e-2), ("values", 1e-2)):
+        if alive.any():
+            assert rel_rms(b[k][alive], a[k][alive], f"n={n} {k} fused vs unfused") < lim
+    assert torch.isfinite(b["determ"]).all() and torch.isfinite(b["logits"]).all()
+    if n <= 300:
+        ref = orc.imagine(c["wm"], c["actor"], c["critic"], h0, z0, H=H, A=m["A"], discrete=True, predict_discount=True,
+                          latent_uniforms=lat, action_noise=act, bf16=True)
+        same = ((b["stoch_idx"].cpu().long() == ref["stoch_idx"]).all(-1)
+                & (b["actions"].cpu().argmax(-1) == ref["actions"].argmax(-1))).cumprod(0).bool()
+        assert same[-1].float().mean() > 0.9 or n == 1
+        assert rel_rms(b["determ"].cpu()[same], ref["determ"][same], f"n={n} determ fused vs bf16 oracle") < 1e-3
+        assert rel_rms(b["logits"].cpu()[same], ref["logits"][same], f"n={n} logits fused vs bf16 oracle") < 2e-3
+
+
+def test_fused_keeps_packed_state_images(ops, lib, cuda):
+    """the per-step packed bf16 images of h the actor-critic update reads afterwards (keep_packed) come from the GRU epilogue's
+    bulk stores: identical to the unfused gate kernel's up to the rounding of a bf16 value at a rounding boundary"""
+    from tests.test_gpu_rollout import unpack_image
+    c = load_case("c1")
+    m = c["meta"]
+    H, n = 3, 300
+    h0, z0 = orc.make_start(5, n, m["D"])
+    g = torch.Generator().manual_seed(6)
+    lat, act = torch.rand(H, n, 1024, generator=g), torch.rand(H, n, m["A"], generator=g)
+    a, _ = _run(ops, lib, cuda, c, H, n, False, h0, z0, lat, act, keep_packed=True)
+    b, _ = _run(ops, lib, cuda, c, H, n, True, h0, z0, lat, act, keep_packed=True)
+    kpad = b["determ_packed"].shape[-1]
+    for t in range(H + 1):
+        img = unpack_image(b["determ_packed"][t], n, kpad)
+        # the image is the bf16 rounding of the fp32 state the same kernel wrote
+        assert torch.equal(img[:, :m["D"]], b["determ"][t].bfloat16().float())
+        rows = b["determ_packed"].shape[1]
+        if rows > n:     # padding rows of the last row block stay zero
+            full = unpack_image(b["determ_packed"][t], rows, kpad)
+            assert not full[n:].any()
+    alive = (a["stoch_idx"] == b["stoch_idx"]).all(-1).cumprod(0).bool()
+    x = torch.stack([unpack_image(a["determ_packed"][t], n, kpad) for t in range(H + 1)])
+    y = torch.stack([unpack_image(b["determ_packed"][t], n, kpad) for t in range(H + 1)])
+    assert rel_rms(y[alive], x[alive], "packed h fused vs unfused") < 5e-3
