@@ -494,25 +494,39 @@ def main():
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel: the GRU contraction (tcgen05 GEMM, EPI_STATS) ------
+        # ---- roofline of the dominant kernel: the GRU contraction (tcgen05 GEMM) — with the fused RSSM epilogues (default,
+        #      D % 64 == 0, no tape) the whole GRU cell in ONE launch (EPI_GRU: LayerNorm, gates and the convex update in the
+        #      contraction's epilogue), else the contraction writing fp32 pre-activations + statistics (EPI_STATS) --------
         fl = dims["fl"]
         Kg, Ng = (2048, 3072) if fl == "c1" else (512, 600)   # packed K of cat[x, h]
-        rb, nb = ops.plan_blocks(Ng)
+        from rl_sandbox_b200 import _lib as _rl
+        gru_fused = fl == "c1" and _rl.load().rlsb_set_fused_rssm(-1) == 1
         xa = torch.randn(N, Kg, device=device)
         wa = torch.randn(Ng, Kg, device=device) / Kg ** 0.5
-        xp = ops.pack_rows(xa)
-        wp = ops.pack_rows(wa, row_block=rb, rows_pad=rb * nb, k_pad=Kg)
-        del xa
-        m_pad = ops.round_up(N, 128)
-        bufs = dict(out=torch.empty((m_pad, Ng), device=device), stats=torch.empty((nb, m_pad, 2), device=device),
-                    bias_p=torch.zeros(rb * nb, device=device))
+        if gru_fused:
+            cell = ops.GRUCellOp(D, D).pack(wa, None, None, None)
+            xp, hp = ops.pack_rows(xa[:, :D].contiguous()), ops.pack_rows(xa[:, D:].contiguous())
+            h_prev = xa[:, D:].contiguous()
+            del xa
+            bufs = dict(h_next=torch.empty((N, D), device=device),
+                        h_next_packed=torch.empty(ops.round_up(N, 128) * D, device=device, dtype=torch.bfloat16))
+            run_gru = lambda: cell.forward_packed(xp, hp, h_prev, N, **bufs)
+        else:
+            rb, nb = ops.plan_blocks(Ng)
+            xp = ops.pack_rows(xa)
+            wp = ops.pack_rows(wa, row_block=rb, rows_pad=rb * nb, k_pad=Kg)
+            del xa
+            m_pad = ops.round_up(N, 128)
+            bufs = dict(out=torch.empty((m_pad, Ng), device=device), stats=torch.empty((nb, m_pad, 2), device=device),
+                        bias_p=torch.zeros(rb * nb, device=device))
+            run_gru = lambda: ops.gemm_bias(xp, Kg, wp, rb, nb, None, N, Ng, want_stats=True, **bufs)
         for _ in range(3):
-            ops.gemm_bias(xp, Kg, wp, rb, nb, None, N, Ng, want_stats=True, **bufs)
+            run_gru()
         torch.cuda.synchronize()
         reps = 20
         ev0.record()
         for _ in range(reps):
-            ops.gemm_bias(xp, Kg, wp, rb, nb, None, N, Ng, want_stats=True, **bufs)
+            run_gru()
         ev1.record()
         torch.cuda.synchronize()
         gemm_ms = ev0.elapsed_time(ev1) / reps
@@ -525,16 +539,20 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("rows") == N and tj.get("D") == D:
+            if tj.get("rows") == N and tj.get("D") == D and bool(tj.get("gru_fused", False)) == gru_fused:
                 traffic = tj["dram_bytes_per_launch"]
-        roofline = {"bound": "tensor", "kernel": "gemm_kernel<EPI_STATS> (GRU contraction cat[x,h] -> 3D)",
+        roofline = {"bound": "tensor",
+                    "kernel": ("gemm_kernel<EPI_GRU> (GRU cell in one launch: contraction cat[x,h] -> 3D with LayerNorm, gates and "
+                               "the convex update in its epilogue)" if gru_fused else
+                               "gemm_kernel<EPI_STATS> (GRU contraction cat[x,h] -> 3D)"),
                     "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
                     "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)",
                     "frac_of_sustained": achieved / pk["tf_sus"], "peak_sustained": pk["tf_sus"],
                     "ms_per_launch": gemm_ms, "traffic": traffic,
-                    # the GRU CELL's bytes (common.py:69-81): x, h in (bf16) + h' out (fp32 + packed bf16) + the weights;
-                    # the contraction as executed also writes its fp32 pre-activations + statistics for the gate kernel
-                    "algorithmic_bytes": N * (2 * D * 2 + D * 4 + D * 2) + 3 * D * 2 * D * 2,
+                    # the GRU CELL's bytes (common.py:69-81): x, h in (bf16 operands) + h in fp32 (the convex update's operand)
+                    # + h' out (fp32 + packed bf16) + the weights; the unfused contraction instead writes its fp32
+                    # pre-activations + statistics for the gate kernel, which reads them back
+                    "algorithmic_bytes": N * (2 * D * 2 + D * 4 + D * 4 + D * 2) + 3 * D * 2 * D * 2,
                     "executed_bytes_unfused": N * (2 * D * 2 + 3 * D * 4) + 3 * D * 2 * D * 2,
                     "whole_rollout": {"tflops": k1_tflops, "frac": k1_tflops / pk["tf_sus"], "ms": k1_ms,
                                       "note": "reference-equivalent FLOPs of all layers / K1 time, vs sustained bf16"}}

@@ -94,6 +94,19 @@ int rlsb_pack_rows(const float* src, int64_t ld_src, int rows_src, void* dst_bf1
 /* out[M, N] (fp32, ld = ldo) = A[M, K] * W[N, K]^T + bias ; A packed (row block 128),
  * W packed with row block `rb` (n_blocks * rb >= N).  Thin wrapper over the kernel every
  * layer of the imagination path uses (replaces nn.Linear, utils/fc_nn.py:14-21). */
+/* GRUCell (agents/dreamer/common.py:58-81: Linear(cat[x, h]) -> LayerNorm over the 3D pre-activations -> reset / candidate /
+ * update gates -> h' = u * cand + (1 - u) * h) as ONE launch: the contraction's epilogue applies LayerNorm and gates and only
+ * h' leaves the kernel (fp32 + the packed bf16 operand image).  The rollout (rlsb_imagine_fwd) uses the same kernel; this entry
+ * point exposes the cell alone (parity tests against the reference module, bench.py's roofline of the dominant kernel).
+ *   D % 64 == 0, 3 D > 512; weight: nn.Linear(Dx + D, 3 D).weight ([3D][Dx + D] row-major), bias / LayerNorm gain / offset [3D]
+ *   x_packed / h_packed: packed bf16 images (row block 128) of x [M][Dx] (K padded to 64) and h [M][D]; h_prev fp32 [M][D]
+ *   h_next fp32 [M][D]; h_next_packed: packed bf16 [M_pad x D]; workspace: rlsb_gru_cell_workspace_bytes(D, M) */
+size_t rlsb_gru_cell_packed_bytes(int Dx, int D);
+size_t rlsb_gru_cell_workspace_bytes(int D, int M);
+int rlsb_gru_cell_pack(const float* weight, const float* bias, const float* ln_gamma, const float* ln_beta, int Dx, int D,
+                       void* packed, void* stream);
+int rlsb_gru_cell_fwd(const void* packed, int Dx, int D, const void* x_packed, const void* h_packed, const float* h_prev,
+                      int M, float update_bias, float eps, float* h_next, void* h_next_packed, void* workspace, void* stream);
 int rlsb_gemm_bias(const void* a_packed, int k_pad, const void* w_packed, int rb, int n_blocks,
                    const float* bias_padded, int M, int N, float* out, int64_t ldo, float* stats,
                    void* stream);

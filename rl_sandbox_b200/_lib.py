@@ -156,6 +156,10 @@ def load() -> C.CDLL:
         "rlsb_philox_uniform": (C.c_int, [u64, u32, u32, u32, i32, i64, vp, vp]),
         "rlsb_sample_latent": (C.c_int, [vp, i64, i32, vp, u64, u32, u32, vp, vp, vp]),
         "rlsb_pack_rows": (C.c_int, [vp, i64, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "rlsb_gru_cell_packed_bytes": (sz, [i32, i32]),
+        "rlsb_gru_cell_workspace_bytes": (sz, [i32, i32]),
+        "rlsb_gru_cell_pack": (C.c_int, [vp, vp, vp, vp, i32, i32, vp, vp]),
+        "rlsb_gru_cell_fwd": (C.c_int, [vp, i32, i32, vp, vp, vp, i32, f32, f32, vp, vp, vp, vp]),
         "rlsb_gemm_bias": (C.c_int, [vp, i32, vp, i32, i32, vp, i32, i32, vp, i64, vp, vp]),
         "rlsb_gemm_ln_act": (C.c_int, [vp, i32, vp, i32, vp, i32, i32, vp, vp, f32, i32, vp, i32, vp]),
         "rlsb_imagine_packed_bytes": (sz, [C.POINTER(ImagineCfg)]),

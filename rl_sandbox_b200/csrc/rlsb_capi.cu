@@ -53,7 +53,7 @@ extern "C" int rlsb_set_cluster_size(int cs) {
 extern "C" int rlsb_set_staged_output(int on) { return set_gemm_staged_output(on); }
 
 extern "C" int rlsb_set_fused_rssm(int on) {
-  if (on == 0 || on == 1) k1::g_fused_rssm = on;
+  if (on == 0 || on == 1 || on == 2) k1::g_fused_rssm = on;   // 2: img_in / prior1 only (A/B runs)
   return k1::g_fused_rssm;
 }
 
@@ -142,6 +142,83 @@ extern "C" int rlsb_gemm_bias(const void* a_packed, int k_pad, const void* w_pac
   g.bias = bias_padded;
   g.out_f32 = out; g.ldo = ldo; g.stats = stats;
   return launch_gemm(g, stats ? EPI_STATS : EPI_PLAIN, static_cast<cudaStream_t>(stream));
+}
+
+// ---- GRUCell as one launch (EPI_GRU) ---------------------------------------------------------------------------------
+namespace {
+struct GruCellLayout {
+  int kx, kp;               // padded K of x, of cat[x, h]
+  size_t w, b, g, e, bytes; // weight image, bias, LayerNorm gain / offset (permuted, fp32 [3D])
+};
+bool gru_cell_layout(int Dx, int D, GruCellLayout& L) {
+  if (Dx <= 0 || D <= 0 || (D % 64) != 0 || 3 * D <= 512) return false;
+  L.kx = (Dx + 63) / 64 * 64;
+  L.kp = L.kx + D;
+  L.w = 0;
+  L.b = (static_cast<size_t>(3) * D * L.kp * 2 + 1023) / 1024 * 1024;
+  L.g = L.b + static_cast<size_t>(3) * D * 4;
+  L.e = L.g + static_cast<size_t>(3) * D * 4;
+  L.bytes = L.e + static_cast<size_t>(3) * D * 4;
+  return true;
+}
+}  // namespace
+
+extern "C" size_t rlsb_gru_cell_packed_bytes(int Dx, int D) {
+  GruCellLayout L;
+  return gru_cell_layout(Dx, D, L) ? L.bytes : 0;
+}
+
+extern "C" size_t rlsb_gru_cell_workspace_bytes(int D, int M) {
+  if (D <= 0 || (D % 64) != 0 || M <= 0) return 0;
+  const size_t m_tiles = (static_cast<size_t>(M) + 127) / 128;
+  return static_cast<size_t>(D / 64) * m_tiles * 128 * 2 * 4 + m_tiles * 4;   // per-block row statistics | counters
+}
+
+extern "C" int rlsb_gru_cell_pack(const float* weight, const float* bias, const float* ln_gamma, const float* ln_beta, int Dx,
+                                  int D, void* packed, void* stream) {
+  GruCellLayout L;
+  if (!weight || !packed || !gru_cell_layout(Dx, D, L)) return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  PackSeg segs[2] = {{0, 0, Dx}, {L.kx, Dx, D}};
+  int e = launch_pack_perm(weight, Dx + D, 3 * D, reinterpret_cast<__nv_bfloat16*>(base + L.w), 192, 3 * D, L.kp, 2, segs, D, s);
+  if (e == 0) e = launch_copy_gru_perm(bias, D, reinterpret_cast<float*>(base + L.b), 0.f, s);
+  if (e == 0) e = launch_copy_gru_perm(ln_gamma, D, reinterpret_cast<float*>(base + L.g), 1.f, s);
+  if (e == 0) e = launch_copy_gru_perm(ln_beta, D, reinterpret_cast<float*>(base + L.e), 0.f, s);
+  return e;
+}
+
+extern "C" int rlsb_gru_cell_fwd(const void* packed, int Dx, int D, const void* x_packed, const void* h_packed,
+                                 const float* h_prev, int M, float update_bias, float eps, float* h_next, void* h_next_packed,
+                                 void* workspace, void* stream) {
+  GruCellLayout L;
+  if (!packed || !x_packed || !h_packed || !h_prev || !h_next || !h_next_packed || !workspace || M <= 0 ||
+      !gru_cell_layout(Dx, D, L))
+    return -1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint8_t* base = static_cast<const uint8_t*>(packed);
+  const int m_tiles = (M + 127) / 128;
+  GemmParams g{};
+  g.n_seg = 2;
+  g.A[0] = static_cast<const __nv_bfloat16*>(x_packed); g.a_ktiles[0] = L.kx / 64;
+  g.A[1] = static_cast<const __nv_bfloat16*>(h_packed); g.a_ktiles[1] = D / 64;
+  g.W = reinterpret_cast<const __nv_bfloat16*>(base + L.w);
+  g.RB = 192; g.NB = D / 64; g.G = 1;
+  g.M = M; g.m_tiles = m_tiles; g.N = 3 * D;
+  g.bias = reinterpret_cast<const float*>(base + L.b);
+  g.ln_gamma = reinterpret_cast<const float*>(base + L.g);
+  g.ln_beta = reinterpret_cast<const float*>(base + L.e);
+  g.ln_eps = eps;
+  g.stats = static_cast<float*>(workspace);
+  g.ln_sync = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) +
+                                              static_cast<size_t>(D / 64) * m_tiles * 128 * 2 * 4);
+  const cudaError_t ce = cudaMemsetAsync(g.ln_sync, 0, static_cast<size_t>(m_tiles) * 4, s);
+  if (ce != cudaSuccess) return static_cast<int>(ce);
+  g.gru_h_prev = h_prev; g.gru_ld_h = D;
+  g.gru_h_next = h_next; g.gru_ld_hn = D;
+  g.gru_update_bias = update_bias;
+  g.out_bf16 = static_cast<__nv_bfloat16*>(h_next_packed); g.out_kpad = D;
+  return launch_gemm(g, EPI_GRU, s);
 }
 
 extern "C" int rlsb_gemm_ln_act(const void* a_packed, int k_pad, const void* w_packed, int rb,

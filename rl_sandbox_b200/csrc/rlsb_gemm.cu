@@ -257,21 +257,20 @@ __device__ __forceinline__ void epi_bar(int id) {
 }
 
 // Cross-block LayerNorm (GemmParams::ln_sync): one thread of a CTA counts its tile into the row block's arrival counter
-// (release: the CTA's partial statistics were written and fenced before the barrier in front of this call) and spins until
-// all `n` n-blocks of the row block have arrived (acquire).  The last one to leave resets both counters for the next launch.
+// (release, cumulative over the CTA's partial statistics written before the barrier in front of this call) and spins until
+// all `n` n-blocks of the row block have arrived (acquire).  Every launch adds exactly n to every counter, so a counter is a
+// multiple of n between launches and the target follows from the value the own arrival found: no reset, no second counter.
 // A partner that never arrives means the CTAs of the launch are not co-resident: trap (a launch error, not a hang).
-__device__ __forceinline__ void xln_arrive_wait(unsigned int* arrive, unsigned int* depart, unsigned int n) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(arrive), "r"(1u) : "memory");
+__device__ __forceinline__ void xln_arrive_wait(unsigned int* arrive, unsigned int n) {
+  unsigned int old;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(arrive), "r"(1u) : "memory");
+  const unsigned int target = old - old % n + n;
   unsigned int v;
   const long long t0 = clock64();
   for (;;) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(arrive) : "memory");
-    if (v >= n) break;
+    if (static_cast<int>(v - target) >= 0) break;
     if (clock64() - t0 > (1ll << 32)) __trap();
-  }
-  if (atomicAdd(depart, 1u) == n - 1u) {
-    *reinterpret_cast<volatile unsigned int*>(depart) = 0u;
-    *reinterpret_cast<volatile unsigned int*>(arrive) = 0u;
   }
 }
 
@@ -973,21 +972,26 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       // this block's row totals (identical in the row's four threads) -> totals over all NB blocks of the row
       auto xln_exchange = [&](float tsum, float tsq, float& s_all, float& q_all) {
         float2* st = reinterpret_cast<float2*>(p.stats) + static_cast<size_t>(g) * p.NB * m_pad;
-        if (tile_ok && cq == 0) {
-          st[static_cast<size_t>(nb) * m_pad + m] = make_float2(tsum, tsq);
-          __threadfence();
-        }
+        if (tile_ok && cq == 0) st[static_cast<size_t>(nb) * m_pad + m] = make_float2(tsum, tsq);
         epi_bar(2);
-        if (tile_ok && tid_e == 0)
-          xln_arrive_wait(p.ln_sync + m_tile, p.ln_sync + p.m_tiles + m_tile, static_cast<unsigned int>(p.NB));
+        if (tile_ok && tid_e == 0) xln_arrive_wait(p.ln_sync + m_tile, static_cast<unsigned int>(p.NB));
         epi_bar(2);
         s_all = 0.f;
         q_all = 0.f;
         if (tile_ok) {
-          for (int b = 0; b < p.NB; ++b) {
-            const float2 v = __ldcg(st + static_cast<size_t>(b) * m_pad + m);
-            s_all += v.x;
-            q_all += v.y;
+          // all partials in flight at once (a loop of dependent-looking loads costs an L2 round trip each), summed in
+          // block order: the same totals in every CTA of the row block
+          const float2* src = st + m;
+          for (int b0 = 0; b0 < p.NB; b0 += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              v[i] = b0 + i < p.NB ? __ldcg(src + static_cast<size_t>(b0 + i) * m_pad) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              s_all += v[i].x;
+              q_all += v[i].y;
+            }
           }
         }
       };
@@ -1399,6 +1403,7 @@ int g_pair = 2;   // cta_group::2 for clusters of 2 (1: only n-blocks <= 256 col
 int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
 int g_staged = 1;         // full-row epilogues write their output through shared memory + bulk copies (RLSB_STAGED=0: 16-byte stores)
 int g_staged_f32 = 1;     // fp32 row-major outputs go through shared-memory slabs and leave as full lines (RLSB_STAGED_F32=0)
+int g_gru_clusters = 0;   // experiment: cap on the clusters of an EPI_GRU launch (RLSB_GRU_CLUSTERS)
 int g_bwd_xbuf = 1;       // EPI_BWD prefetches its saved x_hat chunks into shared memory with cp.async (RLSB_BWD_XBUF=0: global loads)
 
 }  // namespace
@@ -1425,6 +1430,7 @@ int init_device_info() {
     if (const char* env = getenv("RLSB_STAGED")) g_staged = atoi(env);
     if (const char* env = getenv("RLSB_STAGED_F32")) g_staged_f32 = atoi(env);
     if (const char* env = getenv("RLSB_BWD_XBUF")) g_bwd_xbuf = atoi(env);
+    if (const char* env = getenv("RLSB_GRU_CLUSTERS")) g_gru_clusters = atoi(env);
   }
   return 0;
 }
@@ -1497,6 +1503,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   q.inv_n = 1.0f / static_cast<float>(p.N);
   const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
   int clusters = g_num_sms / cs;
+  if (epilogue == EPI_GRU && g_gru_clusters > 0 && g_gru_clusters < clusters) clusters = g_gru_clusters;
   if (total_work < clusters) clusters = total_work;
   const int grid = clusters * cs;
 

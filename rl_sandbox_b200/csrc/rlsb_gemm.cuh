@@ -78,8 +78,9 @@ struct GemmParams {
   // ---- LayerNorm over a row that spans NB > 1 n-blocks (EPI_LN_ACT with NB > 1, EPI_GRU): every CTA writes its block's
   //      (sum, sum of squares) per row into `stats` ([G][NB][M_pad][2], as EPI_STATS), counts itself into ln_sync[m_tile] and
   //      waits until all NB blocks of the row block have arrived — the CTAs of a launch are co-resident (grid <= #SMs, one CTA
-  //      per SM) and walk the work items n-block-fastest, so the partners of a tile are running or finished.  The counters
-  //      reset themselves (second word per tile: departures); zero them once.  ln_sync: [2][m_tiles] uint32.
+  //      per SM) and walk the work items n-block-fastest, so the partners of a tile are running or finished.  Every launch
+  //      adds exactly NB to each counter and derives its target from the value found: zero them once and give every NB its
+  //      own array.  ln_sync: [m_tiles] uint32.
   unsigned int* ln_sync;
   // ---- EPI_GRU: h' = u * cand + (1 - u) * h ------------------------------------------------
   const float* gru_h_prev;   // fp32 [M][gru_ld_h]

@@ -24,7 +24,7 @@ namespace rlsb {
 namespace k1 {
 int g_fused_rssm = [] {
   const char* e = getenv("RLSB_FUSED_RSSM");
-  return (e && e[0] == '0') ? 0 : 1;
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;   // 2: LayerNorm + ELU layers only, GRU cell unfused
 }();
 }  // namespace k1
 
@@ -342,8 +342,8 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     }
     e = cudaMemsetAsync(out->actions, 0, static_cast<size_t>(N) * P.A * 4, s);
     if (e != cudaSuccess) return static_cast<int>(e);
-    // counters of the cross-block LayerNorm (they reset themselves after every launch; cleared once per rollout anyway)
-    e = cudaMemsetAsync(ln_sync, 0, static_cast<size_t>(2) * ms_tiles * 4, s);
+    // arrival counters of the cross-block LayerNorm (monotonic; cleared once per rollout)
+    e = cudaMemsetAsync(ln_sync, 0, static_cast<size_t>(3) * ms_tiles * 4, s);
     if (e != cudaSuccess) return static_cast<int>(e);
     RLSB_TRY(launch_onehot_to_idx(z0, Ms, cfg->groups, cfg->classes, out->stoch_idx, s));
   }
@@ -376,7 +376,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
       g.act = ACT_ELU;
       g.out_bf16 = outp; g.out_kpad = P.Dp; g.out_bf16_group_stride = 0;
-      g.stats = stats; g.ln_sync = ln_sync;
+      g.stats = stats; g.ln_sync = ln_sync + (&L == &P.img_in ? 0 : 2) * static_cast<size_t>(ms_tiles);
       return launch_gemm(g, EPI_LN_ACT, s);
     }
     g.out_f32 = scratch; g.ldo = W.ld_scratch; g.out_group_stride = 0; g.stats = stats;
@@ -493,7 +493,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       if (P.gru_fused) {
         // the whole cell in the contraction's epilogue: only h' leaves the kernel (fp32 state + packed bf16 operand image)
         g.ln_gamma = pf(P.gru.g_off); g.ln_beta = pf(P.gru.b_off);
-        g.stats = stats; g.ln_sync = ln_sync;
+        g.stats = stats; g.ln_sync = ln_sync + ms_tiles;
         g.gru_h_prev = out->determ + static_cast<size_t>(t) * ND; g.gru_ld_h = P.D;
         g.gru_h_next = out->determ + static_cast<size_t>(t + 1) * ND; g.gru_ld_hn = P.D;
         g.gru_update_bias = -1.0f;

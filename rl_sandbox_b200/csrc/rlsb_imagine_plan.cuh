@@ -109,7 +109,7 @@ inline int make_plan(const rlsb_imagine_cfg& c, Plan& P) {
   P.img_in.N = P.D; P.img_in.kp = kmul * (P.Sp + P.Ap); finish(P.img_in, ru(P.D, 32));
   P.gru.N = 3 * P.D; P.gru.kp = kmul * 2 * P.Dp; finish(P.gru, 3 * P.D);
   // (finish() placed NB * RB >= 3 D rows; the fused layout has exactly 3 D of them)
-  P.gru_fused = g_fused_rssm != 0 && !c.with_backward && !P.parity && P.K == 1 && (P.D % 64) == 0 && !P.gru.fullrow;
+  P.gru_fused = g_fused_rssm == 1 && !c.with_backward && !P.parity && P.K == 1 && (P.D % 64) == 0 && !P.gru.fullrow;
   if (P.gru_fused) {
     P.gru.NB = P.D / 64;
     P.gru.RB = 192;
@@ -186,7 +186,8 @@ inline void make_tape(const Plan& P, long long N, int H, Tape& T) {
 
 struct Workspace {
   size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
-  size_t ln_sync;   // [2][ms_pad / 128] uint32 arrival / departure counters of the cross-block LayerNorm (GemmParams::ln_sync)
+  size_t ln_sync;   // [3][ms_pad / 128] uint32 arrival counters of the cross-block LayerNorm (GemmParams::ln_sync), one array
+                    // per layer (img_in, GRU, prior1: a counter must always be advanced by the same NB)
   // slotted RSSM: per-slot operand planes for the heads and the mixer's buffers
   size_t hplanes, zplanes, hpost, mix_ln, mix_qkv, mix_upd, mix_fc;
   // split-operand mode (Plan::parity): fp32 pre-activation buffers, the residual ("lo") images and a zero image
@@ -217,7 +218,7 @@ inline void make_workspace(const Plan& P, long long N, Workspace& W) {
   if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
   W.stats = place(cur, static_cast<size_t>(nbmax) * ms_pad * 2 * 4);
   W.head_out = place(cur, static_cast<size_t>(P.G) * m_pad * 32 * 4);
-  W.ln_sync = place(cur, static_cast<size_t>(2) * (ms_pad / 128) * 4);
+  W.ln_sync = place(cur, static_cast<size_t>(3) * (ms_pad / 128) * 4);
   W.ld_qkv = ru(3 * P.D, 4);
   W.hplanes = W.zplanes = W.hpost = W.mix_ln = W.mix_qkv = W.mix_upd = W.mix_fc = 0;
   if (P.K > 1) {

@@ -224,6 +224,52 @@ def gemm_ln_act(a_packed, k_pad, w_packed, rb, bias, M, N, gamma, beta, eps, act
     return out
 
 
+class GRUCellOp:
+    """`GRUCell` of the reference (agents/dreamer/common.py:58-81, norm=True) as ONE launch: the tcgen05 contraction over
+    cat[x, h] with LayerNorm, gates and the convex update in its epilogue (csrc/rlsb_gemm.cu, EPI_GRU) — the kernel the chained
+    rollout runs per imagined step.  `pack(weight, bias, ln_weight, ln_bias)` takes the module's parameters
+    (`_layer.weight` [3D, Dx + D], `_layer.bias`, `_norm.weight`, `_norm.bias`); `forward(x, h)` returns h' (fp32) and keeps the
+    packed bf16 image of h' in `self.h_packed`."""
+
+    def __init__(self, Dx: int, D: int, update_bias: float = -1.0, eps: float = 1e-5):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.Dx, self.D, self.update_bias, self.eps = int(Dx), int(D), float(update_bias), float(eps)
+        nbytes = self.lib.rlsb_gru_cell_packed_bytes(self.Dx, self.D)
+        if nbytes == 0:
+            raise ValueError(f"GRUCellOp: unsupported sizes Dx={Dx}, D={D} (D % 64 == 0 and 3 D > 512 required)")
+        self.packed = torch.empty(nbytes, device="cuda", dtype=torch.uint8)
+        self._ws = None
+        self.h_packed = None
+
+    def pack(self, weight, bias, ln_weight, ln_bias):
+        w = _f32c(weight)
+        assert tuple(w.shape) == (3 * self.D, self.Dx + self.D)
+        keep = [w] + [None if t is None else _f32c(t) for t in (bias, ln_weight, ln_bias)]
+        check(self.lib.rlsb_gru_cell_pack(w.data_ptr(), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), self.Dx, self.D,
+                                          self.packed.data_ptr(), _stream()), "rlsb_gru_cell_pack")
+        return self
+
+    def forward_packed(self, x_packed, h_packed, h_prev, M, h_next=None, h_next_packed=None):
+        """operands already in the packed bf16 layout (benchmark loops: no re-pack inside)"""
+        need = self.lib.rlsb_gru_cell_workspace_bytes(self.D, M)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=h_prev.device, dtype=torch.uint8)
+        if h_next is None:
+            h_next = torch.empty((M, self.D), device=h_prev.device, dtype=torch.float32)
+        if h_next_packed is None:
+            h_next_packed = torch.empty(round_up(M, 128) * self.D, device=h_prev.device, dtype=torch.bfloat16)
+        check(self.lib.rlsb_gru_cell_fwd(self.packed.data_ptr(), self.Dx, self.D, x_packed.data_ptr(), h_packed.data_ptr(),
+                                         h_prev.data_ptr(), M, self.update_bias, self.eps, h_next.data_ptr(),
+                                         h_next_packed.data_ptr(), self._ws.data_ptr(), _stream()), "rlsb_gru_cell_fwd")
+        self.h_packed = h_next_packed
+        return h_next
+
+    def forward(self, x, h):
+        x, h = _f32c(x), _f32c(h)
+        return self.forward_packed(pack_rows(x), pack_rows(h), h, x.shape[0])
+
+
 def gemm_wgrad(dy_packed, n_pad, x_packed, k_pad, M):
     """out[n_pad, k_pad] = dY^T X from two packed images (weight-gradient contraction; test surface)."""
     _lib.require_device()

@@ -105,3 +105,28 @@ def test_fused_keeps_packed_state_images(ops, lib, cuda):
     x = torch.stack([unpack_image(a["determ_packed"][t], n, kpad) for t in range(H + 1)])
     y = torch.stack([unpack_image(b["determ_packed"][t], n, kpad) for t in range(H + 1)])
     assert rel_rms(y[alive], x[alive], "packed h fused vs unfused") < 5e-3
+
+
+@pytest.mark.parametrize("M,Dx,D", [(1, 1024, 1024), (300, 1024, 1024), (4096, 1024, 1024), (333, 200, 256), (129, 70, 192)])
+def test_gru_cell_op_matches_reference_module_math(ops, cuda, M, Dx, D):
+    """`GRUCell.forward` (common.py:69-81) as one launch through the C ABI (rlsb_gru_cell_fwd) against the oracle's restatement:
+    with bf16-rounded contraction operands (the tensor cores' arithmetic) to fp32 rounding, and against the fp32 module math
+    within the bf16-contraction tolerance"""
+    g = torch.Generator().manual_seed(M + D)
+    sd = {"c._layer.weight": torch.randn(3 * D, Dx + D, generator=g) / (Dx + D) ** 0.5,
+          "c._layer.bias": 0.1 * torch.randn(3 * D, generator=g),
+          "c._norm.weight": 1.0 + 0.1 * torch.randn(3 * D, generator=g),
+          "c._norm.bias": 0.1 * torch.randn(3 * D, generator=g)}
+    x, h = torch.randn(M, Dx, generator=g), torch.tanh(torch.randn(M, D, generator=g))
+    op = ops.GRUCellOp(Dx, D).pack(*(sd[k].to(cuda) for k in ("c._layer.weight", "c._layer.bias", "c._norm.weight", "c._norm.bias")))
+    out = op.forward(x.to(cuda), h.to(cuda))
+    again = op.forward(x.to(cuda), h.to(cuda))          # the arrival counters reset themselves
+    torch.cuda.synchronize()
+    assert torch.equal(out, again)
+    ref16 = orc.gru_cell(x, h, sd, "c.", bf16=True)
+    ref32 = orc.gru_cell(x, h, sd, "c.", bf16=False)
+    assert rel_rms(out, ref16, f"GRU cell M={M} Dx={Dx} D={D} vs bf16-operand oracle") < 2e-5
+    assert rel_rms(out, ref32, f"GRU cell M={M} Dx={Dx} D={D} vs fp32 module math") < 3e-3
+    from rl_sandbox_b200.ops import unpack_rows
+    img = unpack_rows(op.h_packed, M, D, k_pad=D)
+    assert torch.equal(img, out.bfloat16().float())
