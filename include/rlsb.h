@@ -48,6 +48,9 @@ int rlsb_set_staged_output(int on);
  * (1, default; env RLSB_FUSED_RSSM; applies to flat RSSMs with D % 64 == 0 and no tape).  It changes the packed layout of the
  * GRU weight: call rlsb_imagine_pack again after a change.  Any other value only queries.  Returns the value in effect. */
 int rlsb_set_fused_rssm(int on);
+/* profiling: %globaltimer stamps of the fused GRU cell's epilogue ([CTAs][64 tiles][8] uint64, see GemmParams::trace in
+ * csrc/rlsb_gemm.cuh; scripts/gru_cell_trace.py); NULL = off */
+void rlsb_gemm_set_trace(void* device_buffer);
 
 /* ---- K2: lambda-return + shifted-cumprod weights + advantage --------------------------------
  * replaces ImaginativeCritic._lambda_return (agents/dreamer/ac.py:52-62), the discount

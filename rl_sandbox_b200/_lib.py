@@ -150,6 +150,7 @@ def load() -> C.CDLL:
         "rlsb_set_cluster_size": (C.c_int, [i32]),
         "rlsb_set_staged_output": (C.c_int, [i32]),
         "rlsb_set_fused_rssm": (C.c_int, [i32]),
+        "rlsb_gemm_set_trace": (None, [vp]),
         "rlsb_lambda_return_fwd": (C.c_int, [vp, vp, vp, i32, i64, C.c_double, vp, vp, vp, i32, vp]),
         "rlsb_lambda_return_bwd": (C.c_int, [vp, vp, vp, vp, i32, i64, C.c_double, vp, vp, vp, vp]),
         "rlsb_sample_categorical": (C.c_int, [vp, vp, i64, i32, vp, vp]),

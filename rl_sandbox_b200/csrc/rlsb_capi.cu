@@ -52,6 +52,8 @@ extern "C" int rlsb_set_cluster_size(int cs) {
 
 extern "C" int rlsb_set_staged_output(int on) { return set_gemm_staged_output(on); }
 
+extern "C" void rlsb_gemm_set_trace(void* device_buffer) { set_gemm_trace(static_cast<unsigned long long*>(device_buffer)); }
+
 extern "C" int rlsb_set_fused_rssm(int on) {
   if (on == 0 || on == 1 || on == 2) k1::g_fused_rssm = on;   // 2: img_in / prior1 only (A/B runs)
   return k1::g_fused_rssm;
@@ -171,7 +173,7 @@ extern "C" size_t rlsb_gru_cell_packed_bytes(int Dx, int D) {
 extern "C" size_t rlsb_gru_cell_workspace_bytes(int D, int M) {
   if (D <= 0 || (D % 64) != 0 || M <= 0) return 0;
   const size_t m_tiles = (static_cast<size_t>(M) + 127) / 128;
-  return static_cast<size_t>(D / 64) * m_tiles * 128 * 2 * 4 + m_tiles * 4;   // per-block row statistics | counters
+  return static_cast<size_t>(D / 64) * m_tiles * 128 * 16;   // tagged per-block row statistics
 }
 
 extern "C" int rlsb_gru_cell_pack(const float* weight, const float* bias, const float* ln_gamma, const float* ln_beta, int Dx,
@@ -209,10 +211,9 @@ extern "C" int rlsb_gru_cell_fwd(const void* packed, int Dx, int D, const void* 
   g.ln_gamma = reinterpret_cast<const float*>(base + L.g);
   g.ln_beta = reinterpret_cast<const float*>(base + L.e);
   g.ln_eps = eps;
-  g.stats = static_cast<float*>(workspace);
-  g.ln_sync = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) +
-                                              static_cast<size_t>(D / 64) * m_tiles * 128 * 2 * 4);
-  const cudaError_t ce = cudaMemsetAsync(g.ln_sync, 0, static_cast<size_t>(m_tiles) * 4, s);
+  const size_t xbytes = static_cast<size_t>(D / 64) * m_tiles * 128 * 16;
+  g.xstats = static_cast<unsigned long long*>(workspace);
+  const cudaError_t ce = cudaMemsetAsync(g.xstats, 0, xbytes, s);   // all slots of a row start from the same tag
   if (ce != cudaSuccess) return static_cast<int>(ce);
   g.gru_h_prev = h_prev; g.gru_ld_h = D;
   g.gru_h_next = h_next; g.gru_ld_hn = D;

@@ -40,6 +40,7 @@ struct SmemCtl {
   float gamma[2][kMaxRB];
   float beta[2][kMaxRB];
   float2 part[4][kTileM];   // per column-quarter partial (sum, sumsq) of each row
+  float2 part2[4][kTileM];  // cross-block LayerNorm: per gathering thread partial totals of each row
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -252,25 +253,71 @@ __device__ __forceinline__ void ln_act_pass2(uint32_t tmem_d, int cq, int my_chu
 }
 
 
+__device__ __forceinline__ void trace_stamp(unsigned long long* p, int slot) {
+  if (p) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p[slot] = t;
+  }
+}
 __device__ __forceinline__ void epi_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEpiThreads) : "memory");
 }
 
-// Cross-block LayerNorm (GemmParams::ln_sync): one thread of a CTA counts its tile into the row block's arrival counter
-// (release, cumulative over the CTA's partial statistics written before the barrier in front of this call) and spins until
-// all `n` n-blocks of the row block have arrived (acquire).  Every launch adds exactly n to every counter, so a counter is a
-// multiple of n between launches and the target follows from the value the own arrival found: no reset, no second counter.
-// A partner that never arrives means the CTAs of the launch are not co-resident: trap (a launch error, not a hang).
-__device__ __forceinline__ void xln_arrive_wait(unsigned int* arrive, unsigned int n) {
-  unsigned int old;
-  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(arrive), "r"(1u) : "memory");
-  const unsigned int target = old - old % n + n;
-  unsigned int v;
-  const long long t0 = clock64();
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(arrive) : "memory");
-    if (static_cast<int>(v - target) >= 0) break;
-    if (clock64() - t0 > (1ll << 32)) __trap();
+// Cross-block LayerNorm (GemmParams::xstats): a block publishes a row's (sum, sum of squares) as two 64-bit words
+// {value, tag} — 64-bit relaxed gpu-scope stores are single-copy atomic, so a reader that finds the expected tag in a word
+// has its value: no fence, no counter, no atomics.  The tag of a launch is the previous tag of the slot + 1: every launch
+// writes every slot of a row exactly once, so all NB slots of a row carry the same tag between launches (zero them once).
+__device__ __forceinline__ void xst_store(unsigned long long* slot, float sum, float sq, uint32_t tag) {
+  const unsigned long long hi = static_cast<unsigned long long>(tag) << 32;
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(slot), "l"(hi | __float_as_uint(sum)) : "memory");
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(slot + 1), "l"(hi | __float_as_uint(sq)) : "memory");
+}
+__device__ __forceinline__ uint32_t xst_tag(const unsigned long long* slot) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
+  return static_cast<uint32_t>(w >> 32);
+}
+// sum over the blocks b = b_first, b_first + 4, ... < nb_total of row m: every block's words are polled until they carry `tag`
+// (normally the first read; a partner that never publishes means the CTAs of the launch are not co-resident: trap — a launch
+// error, not a hang).  Up to four blocks are in flight at once.
+__device__ __forceinline__ void xst_gather(const unsigned long long* base, size_t block_stride, int b_first, int nb_total,
+                                           uint32_t tag, float& s, float& q) {
+  s = 0.f;
+  q = 0.f;
+  for (int b0 = b_first; b0 < nb_total; b0 += 16) {
+    unsigned long long w0[4], w1[4];
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ok[i] = !(b0 + 4 * i < nb_total);
+      w0[i] = w1[i] = 0ull;
+    }
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!ok[i]) {
+          const unsigned long long* src = base + static_cast<size_t>(b0 + 4 * i) * block_stride;
+          asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0[i]), "=l"(w1[i]) : "l"(src) : "memory");
+        }
+      }
+      bool all = true;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!ok[i]) ok[i] = static_cast<uint32_t>(w0[i] >> 32) == tag && static_cast<uint32_t>(w1[i] >> 32) == tag;
+        all = all && ok[i];
+      }
+      if (all) break;
+      if (clock64() - t0 > (1ll << 32)) __trap();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (b0 + 4 * i < nb_total) {
+        s += __uint_as_float(static_cast<uint32_t>(w0[i]));
+        q += __uint_as_float(static_cast<uint32_t>(w1[i]));
+      }
+    }
   }
 }
 
@@ -889,6 +936,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
     const int m_pad = p.m_tiles * kTileM;
     const int my_chunks = p.RB >> 5;  // (RB / 8) / 4
     const uint32_t s_part = smem_u32(&ctl->part[0][0]);
+    const uint32_t s_part2 = smem_u32(&ctl->part2[0][0]);
     // EPI_BWD: per-CTA column sums (d_gamma | d_beta) of the current group live in the (unused) bias buffers
     const uint32_t s_acc = smem_u32(&ctl->bias[0][0]);
     const bool bwd_colsum = (EPI == EPI_BWD) && p.col_part != nullptr && p.ln_gamma != nullptr;
@@ -949,7 +997,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
       const uint32_t s_gam = smem_u32(&ctl->gamma[pb][0]);
       const uint32_t s_bet = smem_u32(&ctl->beta[pb][0]);
       const bool has_ln = (kLnAct || EPI == EPI_BWD || EPI == EPI_GRU) && (p.ln_gamma != nullptr);
-      // LayerNorm over a row that spans the NB n-blocks of the group: statistics meet in global memory (GemmParams::ln_sync)
+      // LayerNorm over a row that spans the NB n-blocks of the group: statistics meet in global memory (GemmParams::xstats)
       const bool xln = (kLnAct || EPI == EPI_GRU) && has_ln && p.NB > 1;
       // ---- stage this tile's parameters (overlaps the tile's main loop) ------------------------
       {
@@ -963,40 +1011,36 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           }
         }
       }
+      unsigned long long* trp = (EPI == EPI_GRU && p.trace && tid_e == 0 && it < 64)
+                                    ? p.trace + (static_cast<size_t>(blockIdx.x) * 64 + it) * 8 : nullptr;
       epi_bar(1);
+      trace_stamp(trp, 0);
       mbar_wait(&ctl->tmem_full[buf], use & 1u);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * buf_cols) + lane_addr;
       const int m = tile_ok ? m_tile * kTileM + row : p.M + kTileM;   // padding tile: every row invalid
       const bool row_ok = tile_ok && row_is_valid(p, m);
       // this block's row totals (identical in the row's four threads) -> totals over all NB blocks of the row
+      unsigned long long* xrow = xln && tile_ok ? p.xstats + 2 * static_cast<size_t>(m) : nullptr;   // + 2 m_pad per block
+      const uint32_t xtag = xrow ? xst_tag(xrow + 2 * static_cast<size_t>(nb) * m_pad) + 1u : 0u;
       auto xln_exchange = [&](float tsum, float tsq, float& s_all, float& q_all) {
-        float2* st = reinterpret_cast<float2*>(p.stats) + static_cast<size_t>(g) * p.NB * m_pad;
-        if (tile_ok && cq == 0) st[static_cast<size_t>(nb) * m_pad + m] = make_float2(tsum, tsq);
+        if (xrow && cq == 0) xst_store(xrow + 2 * static_cast<size_t>(nb) * m_pad, tsum, tsq, xtag);
+        trace_stamp(trp, 3);
+        // the row's four threads (one per column quarter) gather a quarter of the blocks each and meet in shared memory:
+        // summed in a fixed order, the same totals in every CTA of the row block
+        float ps = 0.f, pq = 0.f;
+        if (xrow) xst_gather(xrow, 2 * static_cast<size_t>(m_pad), cq, p.NB, xtag, ps, pq);
+        trace_stamp(trp, 4);
+        sts64(s_part2 + 8u * (cq * kTileM + row), ps, pq);
         epi_bar(2);
-        if (tile_ok && tid_e == 0) xln_arrive_wait(p.ln_sync + m_tile, static_cast<unsigned int>(p.NB));
-        epi_bar(2);
-        s_all = 0.f;
-        q_all = 0.f;
-        if (tile_ok) {
-          // all partials in flight at once (a loop of dependent-looking loads costs an L2 round trip each), summed in
-          // block order: the same totals in every CTA of the row block
-          const float2* src = st + m;
-          for (int b0 = 0; b0 < p.NB; b0 += 8) {
-            float2 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              v[i] = b0 + i < p.NB ? __ldcg(src + static_cast<size_t>(b0 + i) * m_pad) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              s_all += v[i].x;
-              q_all += v[i].y;
-            }
-          }
-        }
+        const float2 t0 = lds64(s_part2 + 8u * row), t1 = lds64(s_part2 + 8u * (kTileM + row)),
+                     t2 = lds64(s_part2 + 8u * (2 * kTileM + row)), t3 = lds64(s_part2 + 8u * (3 * kTileM + row));
+        s_all = (t0.x + t1.x) + (t2.x + t3.x);
+        q_all = (t0.y + t1.y) + (t2.y + t3.y);
       };
 
       if constexpr (EPI == EPI_GRU) {
+        trace_stamp(trp, 1);
         // thread (row, cq) owns the chunks cq + 4 i, i < 6, of the block's 192 columns: i = 0, 1 reset | 2, 3 candidate |
         // 4, 5 update pre-activations of the SAME hidden units 64 nb + 8 (cq + 4 j), j = i & 1.  The accumulator is copied
         // to registers once (48 values) and its TMEM buffer handed back at once, so that waiting for the partner blocks'
@@ -1037,6 +1081,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           if (pair && rank == 1) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctl->tmem_empty[buf]), 0u));
           else mbar_arrive(&ctl->tmem_empty[buf]);
         }
+        trace_stamp(trp, 2);
         // h of the previous step for this thread's 2 x 8 hidden units (in flight across the exchange)
         const int u0 = nb * 64;
         float4 hp[2][2];
@@ -1060,6 +1105,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
         }
         float s_all, q_all;
         xln_exchange(tsum, tsq, s_all, q_all);
+        trace_stamp(trp, 5);
         const float mean = s_all * p.inv_n;
         const float rstd = 1.0f / sqrtf(fmaxf(q_all * p.inv_n - mean * mean, 0.f) + p.ln_eps);
         const float nmr = -mean * rstd;
@@ -1095,6 +1141,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           sts128(so + ((static_cast<uint32_t>(cq + 4 * j) ^ static_cast<uint32_t>(row & 7)) << 4),
                  make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
         }
+        trace_stamp(trp, 6);
         // the packed bf16 image of h': k-tile nb of the row block, one 16 KB bulk store (two slots alternate)
         if (tid_e == 0 && out_pending) bulk_wait_read<0>();
         fence_proxy_async_smem();
@@ -1106,6 +1153,7 @@ gemm_kernel(const GemmParams p, const int stages, const int nbuf, const int cs) 
           out_pending = true;
         }
         out_ph ^= 1u;
+        trace_stamp(trp, 7);
         continue;
       }
 
@@ -1403,10 +1451,13 @@ int g_pair = 2;   // cta_group::2 for clusters of 2 (1: only n-blocks <= 256 col
 int g_cluster_size = 2;   // CTAs per cluster sharing a weight block (1, 2 or 4); RLSB_CLUSTER overrides
 int g_staged = 1;         // full-row epilogues write their output through shared memory + bulk copies (RLSB_STAGED=0: 16-byte stores)
 int g_staged_f32 = 1;     // fp32 row-major outputs go through shared-memory slabs and leave as full lines (RLSB_STAGED_F32=0)
+unsigned long long* g_trace = nullptr;
 int g_gru_clusters = 0;   // experiment: cap on the clusters of an EPI_GRU launch (RLSB_GRU_CLUSTERS)
 int g_bwd_xbuf = 1;       // EPI_BWD prefetches its saved x_hat chunks into shared memory with cp.async (RLSB_BWD_XBUF=0: global loads)
 
 }  // namespace
+
+void set_gemm_trace(unsigned long long* device_buffer) { g_trace = device_buffer; }
 
 int set_gemm_staged_output(int on) {
   if (on == 0 || on == 1) g_staged = on;
@@ -1456,8 +1507,8 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   if (epilogue == EPI_LN_ACT && p.save_pre) epilogue = EPI_LN_ACT_SAVE;
   // LayerNorm needs the whole row: one block, or the cross-block exchange
   const bool xln = (epilogue == EPI_LN_ACT || epilogue == EPI_GRU) && p.NB != 1 && p.ln_gamma != nullptr;
-  if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB != 1 && p.ln_gamma != nullptr && !p.ln_sync) return -3;
-  if (xln && (!p.ln_sync || !p.stats || p.G != 1 || p.N != p.NB * p.RB || p.row_period != 0)) return -3;
+  if ((epilogue == EPI_LN_ACT || epilogue == EPI_LN_ACT_SAVE) && p.NB != 1 && p.ln_gamma != nullptr && !p.xstats) return -3;
+  if (xln && (!p.xstats || p.G != 1 || p.N != p.NB * p.RB || p.row_period != 0)) return -3;
   if (epilogue == EPI_GRU && (p.RB != 192 || !p.ln_gamma || !p.gru_h_prev || !p.gru_h_next || !p.out_bf16 || p.G != 1 ||
                               p.out_kpad != p.NB * 64 || (p.gru_ld_h % 4) != 0 || (p.gru_ld_hn % 4) != 0 ||
                               (reinterpret_cast<uintptr_t>(p.gru_h_prev) % 16) != 0 || (reinterpret_cast<uintptr_t>(p.gru_h_next) % 16) != 0))
@@ -1484,7 +1535,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
                                      (p.NB == 1 || ((p.RB % 64) == 0 && p.NB * p.RB == p.out_kpad)));
   const int staging_bytes = (staged || epilogue == EPI_GRU) ? (epilogue == EPI_LN_ACT_SAVE ? 65536 : 32768) : 0;
   int budget = 227 * 1024 - 1024 /*align*/ - static_cast<int>(sizeof(SmemCtl)) - 256 - staging_bytes;
-  static_assert(sizeof(SmemCtl) < 20 * 1024, "control block grew");
+  static_assert(sizeof(SmemCtl) < 24 * 1024, "control block grew");
   // EPI_BWD: a 16-byte slot per epilogue thread and chunk for the saved image (two stages must still fit)
   // (latency-bound launches only — a tile or two per CTA: dino step 5.52 -> 5.30 ms; with many tiles per CTA the loads of
   // the next tile already overlap and the deeper stage ring is worth more: sweep step 33.5 vs 34.0 ms; RLSB_BWD_XBUF=2 forces it)
@@ -1501,6 +1552,7 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
   q.staged_out = staged ? 1 : 0;
   q.xbuf_bytes = xbuf_bytes;
   q.inv_n = 1.0f / static_cast<float>(p.N);
+  q.trace = epilogue == EPI_GRU ? g_trace : nullptr;
   const int total_work = p.G * p.NB * ((p.m_tiles + cs - 1) / cs);
   int clusters = g_num_sms / cs;
   if (epilogue == EPI_GRU && g_gru_clusters > 0 && g_gru_clusters < clusters) clusters = g_gru_clusters;

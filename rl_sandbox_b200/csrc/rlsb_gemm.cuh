@@ -20,7 +20,7 @@ enum GemmEpilogue : int {
   EPI_BWD = 3,     // full row in TMEM: acc = dL/d(act output); ELU' and LayerNorm backward -> packed bf16 dL/d(pre-LN)
   EPI_GRU = 5,     // GRU cell (common.py:69-81) fused into its contraction: n-block nb holds the [reset | candidate | update]
                    // pre-activations of hidden units [64 nb, 64 nb + 64) (RB = 192, weight rows permuted by the packer); the
-                   // joint LayerNorm over all 3D columns goes through the cross-block exchange (ln_sync); writes only h'
+                   // joint LayerNorm over all 3D columns goes through the cross-block exchange (xstats); writes only h'
 };
 
 enum Activation : int { ACT_NONE = 0, ACT_ELU = 1, ACT_RELU = 2 };
@@ -75,19 +75,23 @@ struct GemmParams {
   int alt_group_p1;
   const __nv_bfloat16* alt_A;
   __nv_bfloat16* alt_out_bf16;
-  // ---- LayerNorm over a row that spans NB > 1 n-blocks (EPI_LN_ACT with NB > 1, EPI_GRU): every CTA writes its block's
-  //      (sum, sum of squares) per row into `stats` ([G][NB][M_pad][2], as EPI_STATS), counts itself into ln_sync[m_tile] and
-  //      waits until all NB blocks of the row block have arrived — the CTAs of a launch are co-resident (grid <= #SMs, one CTA
-  //      per SM) and walk the work items n-block-fastest, so the partners of a tile are running or finished.  Every launch
-  //      adds exactly NB to each counter and derives its target from the value found: zero them once and give every NB its
-  //      own array.  ln_sync: [m_tiles] uint32.
-  unsigned int* ln_sync;
+  // ---- LayerNorm over a row that spans NB > 1 n-blocks (EPI_LN_ACT with NB > 1, EPI_GRU): every CTA publishes its block's
+  //      (sum, sum of squares) per row in xstats[nb][m] = two 64-bit words {value, tag} and gathers the NB blocks' words of its
+  //      rows, polling until they carry the launch's tag (= the slot's previous tag + 1) — the CTAs of a launch are co-resident
+  //      (grid <= #SMs, one CTA per SM) and walk the work items n-block-fastest, so the partners of a tile are running or
+  //      finished.  xstats: [NB][m_tiles * 128][2] uint64, owned by ONE layer (every launch must write every slot of a row once),
+  //      zeroed once.
+  unsigned long long* xstats;
   // ---- EPI_GRU: h' = u * cand + (1 - u) * h ------------------------------------------------
   const float* gru_h_prev;   // fp32 [M][gru_ld_h]
   long long gru_ld_h;
   float* gru_h_next;         // fp32 [M][gru_ld_hn]; the packed bf16 image goes to out_bf16 (out_kpad = NB * 64)
   long long gru_ld_hn;
   float gru_update_bias;
+  // profiling (set_gemm_trace): [gridDim.x][64 tiles][8] %globaltimer stamps of every CTA's first 64 EPI_GRU tiles — 0 tile's
+  // parameters staged, 1 accumulator ready, 2 copied to registers (TMEM buffer released), 3 statistics published,
+  // 4 all partners' statistics gathered, 5 totals known, 6 gates done, 7 bulk store issued; nullptr = off
+  unsigned long long* trace;
   // ---- set by launch_gemm (callers leave it 0): the full-row epilogue assembles each 128 x 64 output tile (16 KB, contiguous
   //      in the packed image) in shared memory and writes it with one bulk copy instead of 16-byte stores scattered over 32 rows
   int staged_out;
@@ -110,5 +114,7 @@ int gemm_cluster_size();
 // full-row epilogues write their output tiles through shared memory + bulk copies (1, default) or with 16-byte stores (0);
 // any other value only queries.  Returns the value in effect.
 int set_gemm_staged_output(int on);
+// profiling: device buffer for GemmParams::trace of the following EPI_GRU launches (nullptr = off)
+void set_gemm_trace(unsigned long long* device_buffer);
 
 }  // namespace rlsb

@@ -284,7 +284,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
   float* scratch = reinterpret_cast<float*>(ws + W.scratch);
   float* stats = reinterpret_cast<float*>(ws + W.stats);
   float* head_out = reinterpret_cast<float*>(ws + W.head_out);
-  unsigned int* ln_sync = reinterpret_cast<unsigned int*>(ws + W.ln_sync);
+  auto xstats = [&](int i) { return reinterpret_cast<unsigned long long*>(ws + W.xstats[i]); };   // img_in, GRU, prior1
   const bool ln = cfg->layer_norm != 0;
   const float eps = 1e-5f;
   const size_t ND = static_cast<size_t>(Ms) * P.D, NS = static_cast<size_t>(Ms) * P.S;
@@ -342,8 +342,8 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
     }
     e = cudaMemsetAsync(out->actions, 0, static_cast<size_t>(N) * P.A * 4, s);
     if (e != cudaSuccess) return static_cast<int>(e);
-    // arrival counters of the cross-block LayerNorm (monotonic; cleared once per rollout)
-    e = cudaMemsetAsync(ln_sync, 0, static_cast<size_t>(3) * ms_tiles * 4, s);
+    // tagged statistics of the cross-block LayerNorm: all slots of a row must start from the same tag
+    if (g_fused_rssm) e = cudaMemsetAsync(ws + W.xstats[0], 0, W.xstats_bytes, s);
     if (e != cudaSuccess) return static_cast<int>(e);
     RLSB_TRY(launch_onehot_to_idx(z0, Ms, cfg->groups, cfg->classes, out->stoch_idx, s));
   }
@@ -371,12 +371,12 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       return launch_gemm(g, EPI_LN_ACT, s);
     }
     if (g_fused_rssm && !save_pre && (L.RB % 64) == 0 && L.NB * L.RB == P.Dp && L.N == P.Dp) {
-      // the row spans NB n-blocks: LayerNorm statistics meet across the blocks' CTAs (GemmParams::ln_sync)
+      // the row spans NB n-blocks: LayerNorm statistics meet across the blocks' CTAs (GemmParams::xstats)
       g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
       g.ln_beta = has_ln ? pf(L.b_off) : nullptr;
       g.act = ACT_ELU;
       g.out_bf16 = outp; g.out_kpad = P.Dp; g.out_bf16_group_stride = 0;
-      g.stats = stats; g.ln_sync = ln_sync + (&L == &P.img_in ? 0 : 2) * static_cast<size_t>(ms_tiles);
+      g.xstats = xstats(&L == &P.img_in ? 0 : 2);
       return launch_gemm(g, EPI_LN_ACT, s);
     }
     g.out_f32 = scratch; g.ldo = W.ld_scratch; g.out_group_stride = 0; g.stats = stats;
@@ -493,7 +493,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       if (P.gru_fused) {
         // the whole cell in the contraction's epilogue: only h' leaves the kernel (fp32 state + packed bf16 operand image)
         g.ln_gamma = pf(P.gru.g_off); g.ln_beta = pf(P.gru.b_off);
-        g.stats = stats; g.ln_sync = ln_sync + ms_tiles;
+        g.xstats = xstats(1);
         g.gru_h_prev = out->determ + static_cast<size_t>(t) * ND; g.gru_ld_h = P.D;
         g.gru_h_next = out->determ + static_cast<size_t>(t + 1) * ND; g.gru_ld_hn = P.D;
         g.gru_update_bias = -1.0f;

@@ -38,7 +38,7 @@ inline void plan_nb(LayerPlan& L) {
 }
 
 // Fused RSSM epilogues of the chained rollout (rlsb_set_fused_rssm, default on): LayerNorm + ELU of img_in / prior1 and the
-// whole GRU cell run inside their contractions' epilogues even when a row spans several n-blocks (GemmParams::ln_sync);
+// whole GRU cell run inside their contractions' epilogues even when a row spans several n-blocks (GemmParams::xstats);
 // 0 = contraction -> fp32 pre-activations -> ln_act_kernel / gru_gate_kernel.  Read by make_plan: re-pack after a change.
 extern int g_fused_rssm;
 
@@ -186,8 +186,8 @@ inline void make_tape(const Plan& P, long long N, int H, Tape& T) {
 
 struct Workspace {
   size_t hbf[2], zbf[2], abf, xbf, ybf, hid[2], scratch, stats, head_out;
-  size_t ln_sync;   // [3][ms_pad / 128] uint32 arrival counters of the cross-block LayerNorm (GemmParams::ln_sync), one array
-                    // per layer (img_in, GRU, prior1: a counter must always be advanced by the same NB)
+  size_t xstats[3];     // tagged row statistics of the cross-block LayerNorm (GemmParams::xstats), one array per layer:
+  size_t xstats_bytes;  // img_in, GRU, prior1 ([NB][ms_pad][2] uint64 each; contiguous, cleared once per rollout)
   // slotted RSSM: per-slot operand planes for the heads and the mixer's buffers
   size_t hplanes, zplanes, hpost, mix_ln, mix_qkv, mix_upd, mix_fc;
   // split-operand mode (Plan::parity): fp32 pre-activation buffers, the residual ("lo") images and a zero image
@@ -218,7 +218,17 @@ inline void make_workspace(const Plan& P, long long N, Workspace& W) {
   if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
   W.stats = place(cur, static_cast<size_t>(nbmax) * ms_pad * 2 * 4);
   W.head_out = place(cur, static_cast<size_t>(P.G) * m_pad * 32 * 4);
-  W.ln_sync = place(cur, static_cast<size_t>(3) * (ms_pad / 128) * 4);
+  {
+    const LayerPlan* xl[3] = {&P.img_in, &P.gru, &P.prior1};
+    size_t tot = 0;
+    for (int i = 0; i < 3; ++i) tot += rus(static_cast<size_t>(xl[i]->NB) * ms_pad * 16, 1024);
+    size_t off = place(cur, tot);
+    W.xstats_bytes = tot;
+    for (int i = 0; i < 3; ++i) {
+      W.xstats[i] = off;
+      off += rus(static_cast<size_t>(xl[i]->NB) * ms_pad * 16, 1024);
+    }
+  }
   W.ld_qkv = ru(3 * P.D, 4);
   W.hplanes = W.zplanes = W.hpost = W.mix_ln = W.mix_qkv = W.mix_upd = W.mix_fc = 0;
   if (P.K > 1) {
