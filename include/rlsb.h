@@ -279,6 +279,10 @@ int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed, int64_t N,
  * Same cfg / noise / out / workspace (rlsb_imagine_workspace_bytes) / tape contract as rlsb_imagine_fwd for the flat
  * RSSM (slots <= 1, parity == 0, out->actor_slots == NULL); the packed weights are this kernel's own. */
 int rlsb_rollout_cluster_size(void);
+/* clusters of `cluster` (4 | 8 | 16) CTAs of the persistent kernels that the current device keeps resident at once
+ * (cudaOccupancyMaxActiveClusters: a cluster lives inside one GPC, so this is less than #SMs / cluster in general).  More row
+ * blocks than this run as a second wave at twice the time: callers pick the cluster size / the chained rollout by it. */
+int rlsb_rollout_max_clusters(int cluster);
 /* profiling aid: a device buffer of (H + 1) x 11 x 8 uint64 that the next rlsb_rollout_fwd launches fill with
  * %globaltimer stamps of cluster 0 — per step the 11 phases head layers 0-4, read-out / action draw, img_in, GRU, prior 1,
  * prior 2, latent draw; per phase 0 producer starts, 1 first stage landed, 2 MMAs issued, 3 accumulator ready,

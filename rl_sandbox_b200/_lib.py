@@ -169,6 +169,7 @@ def load() -> C.CDLL:
         "rlsb_imagine_fwd": (C.c_int, [C.POINTER(ImagineCfg), vp, i64, vp, vp, vp, C.POINTER(Noise),
                                        C.POINTER(ImagineOut), vp, vp]),
         "rlsb_rollout_cluster_size": (C.c_int, []),
+        "rlsb_rollout_max_clusters": (C.c_int, [i32]),
         "rlsb_rollout_set_trace": (None, [vp]),
         "rlsb_rollout_packed_bytes": (sz, [C.POINTER(ImagineCfg)]),
         "rlsb_rollout_pack": (C.c_int, [C.POINTER(ImagineCfg), C.POINTER(ImagineParams), vp, vp]),

@@ -83,8 +83,9 @@ class DreamerV2(RlAgent):
         self.cuda_graph = True
         self.cuda_graph_max_rows = int(os.environ.get('RLSB_GRAPH_MAX_ROWS', 32768))
         self.reuse_actor_forward = os.environ.get('RLSB_ACTOR_REUSE', '1') != '0'   # K1's actor activations feed K4
-        # below: launch-latency bound — the persistent rollout kernel (up to ImaginationEngine.persistent_max_rows = 2048
-        # start states; it has no actor slots) is the faster path, and the update recomputes the actor forward
+        # below: launch-latency bound — where the persistent rollout kernel runs (ImaginationEngine.would_run_persistent: up to
+        # persistent_max_rows = 2048 start states AND all row blocks resident in one wave; it has no actor slots) the update
+        # recomputes the actor forward
         self.reuse_actor_min_rows = 2049
         self.max_rows_per_pass = 131072   # start states per pass of the fused update (HBM sizing, _fused_step_chunked)
         # world-model half of train(): forward + backward captured in a CUDA graph per input shape (the observe loop is
@@ -518,7 +519,8 @@ class DreamerV2(RlAgent):
         # the rollout evaluates the actor on every state with the weights the update differentiates: it leaves the
         # actor's activations in the update's workspace and K4 runs the critic's forward only
         n_rows = initial_states.determ.shape[1] if static is None else static['h0'].shape[0]
-        reuse = self.reuse_actor_forward and not dyn and n_rows >= self.reuse_actor_min_rows
+        reuse = (self.reuse_actor_forward and not dyn
+                 and (n_rows >= self.reuse_actor_min_rows or not self._get_engine().would_run_persistent(n_rows)))
         if static is None:
             ac = self._get_ac_engine()
             slots = ac.actor_slots(initial_states.determ.shape[1], self.imagination_horizon) if reuse else None

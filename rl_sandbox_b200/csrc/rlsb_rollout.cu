@@ -1937,6 +1937,39 @@ using namespace rlsb::ro;
 
 extern "C" int rlsb_rollout_cluster_size(void) { return rollout_cluster_size(); }
 
+// clusters of `cluster` CTAs of the persistent rollout kernel the current device keeps resident at once (a cluster needs its
+// CTAs inside one GPC: fewer than #SMs / cluster in general); 0 on error.  Cached per cluster size.
+extern "C" int rlsb_rollout_max_clusters(int cluster) {
+  if (cluster != 4 && cluster != 8 && cluster != 16) return 0;
+  static int cached[3] = {-1, -1, -1};
+  int& slot = cached[cluster == 4 ? 0 : cluster == 8 ? 1 : 2];
+  if (slot >= 0) return slot;
+  if (cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  const int ring_bytes = (227 * 1024 - 1024 - static_cast<int>(sizeof(RCtl)) - 256) / 1024 * 1024;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(static_cast<unsigned>(cluster * 64));
+  lc.blockDim = dim3(kThreads);
+  lc.dynamicSmemBytes = static_cast<size_t>(ring_bytes) + sizeof(RCtl) + 1024;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, rollout_kernel, &lc) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  slot = n;
+  return n;
+}
+
 extern "C" void rlsb_rollout_set_trace(void* device_buffer) { g_rollout_trace = static_cast<unsigned long long*>(device_buffer); }
 
 namespace {

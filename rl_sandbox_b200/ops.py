@@ -352,6 +352,7 @@ class ImaginationEngine:
         # by the latency of its ~230 dependent launches.  RLSB_PERSISTENT=0 disables it, =1 forces it for any size.
         env = os.environ.get("RLSB_PERSISTENT", "")
         self.persistent_max_rows = {"0": 0, "1": 1 << 30}.get(env, 2048)
+        self._max_clusters = {}   # cluster size -> clusters the device keeps resident (rlsb_rollout_max_clusters)
         ro_bytes = self.lib.rlsb_rollout_packed_bytes(C.byref(self.ccfg)) if self.persistent_max_rows > 0 else 0
         # its weights are re-ordered per CTA of the cluster, i.e. they depend on the cluster size: packed on first use
         # after every `pack` (one blob per cluster size seen)
@@ -408,15 +409,35 @@ class ImaginationEngine:
 
     def rollout_cluster_for(self, n: int) -> int:
         """CTAs per cluster of the persistent rollout for n start states: the configured / RLSB_ROLLOUT_CLUSTER value, else
-        16 while every 128-row block still gets its own GPC (a cluster of 16 fills one; B200 has 8), else 8."""
+        16 while the device keeps all row blocks' clusters of 16 resident at once (rlsb_rollout_max_clusters: a cluster lives
+        inside one GPC — 7 of 16 on the pool's B200s, not 148 / 16 = 9), else 8."""
         if self.cfg.rollout_cluster:
             return int(self.cfg.rollout_cluster)
         if os.environ.get("RLSB_ROLLOUT_CLUSTER"):
             return int(self.lib.rlsb_rollout_cluster_size())
-        c = 16 if (n + 127) // 128 <= 8 else 8
-        if self.cfg.D > 640 and c == 4:
-            c = 8
-        return c
+        return 16 if (n + 127) // 128 <= self.rollout_max_clusters(16) else 8
+
+    def rollout_max_clusters(self, c: int) -> int:
+        v = self._max_clusters.get(c)
+        if v is None:
+            v = self._max_clusters[c] = int(self.lib.rlsb_rollout_max_clusters(int(c)))
+        return v
+
+    def would_run_persistent(self, n: int) -> bool:
+        """the engine's own choice for a rollout of n start states without actor slots: the persistent kernel while all row
+        blocks run in one wave — at config-1 dims (D = 1024) only with clusters of 16 (measured at 1024 / 1536 / 1920 start
+        states: with clusters of 8 the chained rollout and its fused epilogues are 2-10 % faster per step; at D = 200 the
+        persistent forward + backward win by 9-14 % up to 1920)"""
+        if self.packed_ro is None or n > self.persistent_max_rows:
+            return False
+        if self.persistent_max_rows >= (1 << 30):
+            return True
+        return self.rollout_fits_one_wave(n) and (self.cfg.D <= 512 or self.rollout_cluster_for(n) == 16)
+
+    def rollout_fits_one_wave(self, n: int) -> bool:
+        """all row blocks of n start states run concurrently in the persistent kernels (a second wave doubles their time:
+        the chained rollout is faster then)"""
+        return (n + 127) // 128 <= self.rollout_max_clusters(self.rollout_cluster_for(n))
 
     def _packed_rollout(self, ccfg) -> torch.Tensor:
         """the persistent kernel's weight blob for ccfg.rollout_cluster, re-packed when `pack` ran since it was made"""
@@ -508,7 +529,7 @@ class ImaginationEngine:
                    _ptr(None if precomp_actions is None else _f32c(precomp_actions)), _ptr(seed_device))
         ws = self.workspace(n, pin)
         if persistent is None:
-            persistent = self.packed_ro is not None and actor_slots is None and n <= self.persistent_max_rows
+            persistent = actor_slots is None and self.would_run_persistent(n)
         elif persistent and (self.packed_ro is None or actor_slots is not None):
             raise _lib.RlsbError("rollout(persistent=True): flat RSSM without parity mode / actor_slots only")
         self.last_rollout_persistent = bool(persistent)
@@ -554,7 +575,7 @@ class ImaginationEngine:
                                                       "rewards", "discounts", "values", "actor_raw",
                                                       "determ_packed", "stoch_packed", "tape")])
         if persistent is None:
-            persistent = self.packed_ro is not None and n <= self.persistent_max_rows and os.environ.get("RLSB_PERSISTENT_BWD", "1") != "0"
+            persistent = self.would_run_persistent(n) and os.environ.get("RLSB_PERSISTENT_BWD", "1") != "0"
             if persistent:   # cluster sizes whose slices do not fit the epilogue's register plan fall back to the chain
                 probe = self.cfg.to_c()
                 probe.rollout_cluster = self.rollout_cluster_for(n)

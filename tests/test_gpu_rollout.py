@@ -94,7 +94,8 @@ def test_persistent_ragged_row_counts_vs_oracle(ops, cuda, n):
     g = torch.Generator().manual_seed(n)
     lat, act = torch.rand(H, n, 1024, generator=g), torch.randn(H, n, m["A"], generator=g)
     out = eng.rollout(h0.to(cuda), z0.to(cuda), None, lat.to(cuda), act.to(cuda), horizon=H)
-    assert eng.last_rollout_persistent and eng.rollout_cluster_for(n) == (16 if n <= 1024 else 8)
+    blocks = (n + 127) // 128
+    assert eng.last_rollout_persistent and eng.rollout_cluster_for(n) == (16 if blocks <= eng.rollout_max_clusters(16) else 8)
     ref = orc.imagine(c["wm"], c["actor"], c["critic"], h0, z0, H=H, A=m["A"], discrete=False, predict_discount=False,
                       latent_uniforms=lat, action_noise=act, bf16=True)
     same = (out["stoch_idx"].cpu().long() == ref["stoch_idx"]).all(-1).cumprod(0).bool()
@@ -102,6 +103,27 @@ def test_persistent_ragged_row_counts_vs_oracle(ops, cuda, n):
     assert rel_rms(out["determ"].cpu()[same], ref["determ"][same], f"n={n} determ vs bf16 oracle") < 1e-3
     assert rel_rms(out["logits"].cpu()[same], ref["logits"][same], f"n={n} logits vs bf16 oracle") < 2e-3
     assert torch.isfinite(out["determ"]).all() and torch.isfinite(out["logits"]).all()
+
+
+def test_engine_picks_the_persistent_kernel_only_for_one_wave(ops, cuda):
+    """a cluster lives inside one GPC, so the device keeps fewer clusters resident than #SMs / cluster; row blocks beyond that
+    would run as a second wave at twice the time, and the engine takes the chained rollout instead"""
+    c = load_case("c2")
+    m = c["meta"]
+    eng = engine(ops, m, cuda, c, 2)
+    c16, c8 = eng.rollout_max_clusters(16), eng.rollout_max_clusters(8)
+    print(f"[rollout] resident clusters: {c16} of 16 CTAs, {c8} of 8 CTAs")
+    assert 1 <= c16 <= 148 // 16 and c16 <= c8 <= 148 // 8
+    for n in (128 * c16, 128 * c16 + 1, 128 * c8, 128 * c8 + 1):
+        if n > eng.persistent_max_rows:
+            continue
+        h0, z0 = orc.make_start(n, n, m["D"])
+        eng.rollout(h0.to(cuda), z0.to(cuda), None, None, None, horizon=2, seed=3)
+        blocks = (n + 127) // 128
+        assert eng.rollout_cluster_for(n) == (16 if blocks <= c16 else 8)
+        assert eng.last_rollout_persistent == (blocks <= c8), n      # (D = 200: clusters of 8 still pay)
+    big = engine(ops, load_case("c1")["meta"], cuda, load_case("c1"), 2)   # D = 1024: only with clusters of 16
+    assert big.would_run_persistent(128 * c16) and not big.would_run_persistent(128 * c16 + 1)
 
 
 @pytest.mark.parametrize("name", ["c2", "c2_ln"])
