@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RLSB_ABI_VERSION 5
+#define RLSB_ABI_VERSION 6
 
 /* ---- library / device ------------------------------------------------------------------- */
 int rlsb_abi_version(void);

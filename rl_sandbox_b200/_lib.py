@@ -74,7 +74,7 @@ AC_SCALAR_NAMES = {
     "loss_actor": 4, "critic/avg_target_value": 5, "critic/avg_lambda_value": 6, "critic/avg_predicted_value": 7,
     "actor/avg_val": 8, "actor/mean_val": 9, "actor/avg_sd": 10, "actor/min_val": 11, "actor/max_val": 12}
 AC_SCALARS = 16
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class SlotCfg(C.Structure):

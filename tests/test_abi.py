@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     missing = [n for n in names if n not in exported]
     assert not missing, f"declared in include/rlsb.h but not exported: {missing}"
-    assert lib.rlsb_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.rlsb_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_no_torch_types_in_abi():
