@@ -370,7 +370,7 @@ extern "C" int rlsb_imagine_fwd(const rlsb_imagine_cfg* cfg, const void* packed,
       g.save_rstd = has_ln ? reinterpret_cast<float*>(save_rstd) : nullptr;
       return launch_gemm(g, EPI_LN_ACT, s);
     }
-    if (g_fused_rssm && !save_pre && (L.RB % 64) == 0 && L.NB * L.RB == P.Dp && L.N == P.Dp) {
+    if (!save_pre && ln_layer_fused(P, L)) {
       // the row spans NB n-blocks: LayerNorm statistics meet across the blocks' CTAs (GemmParams::xstats)
       g.ln_gamma = has_ln ? pf(L.g_off) : nullptr;
       g.ln_beta = has_ln ? pf(L.b_off) : nullptr;

@@ -70,6 +70,11 @@ struct Plan {
   size_t packed_bytes;
 };
 
+// a LayerNorm / ELU layer of the RSSM runs with its epilogue fused (one block per row, or the cross-block exchange)
+inline bool ln_layer_fused(const Plan& P, const LayerPlan& L) {
+  return L.fullrow || (g_fused_rssm != 0 && (L.RB % 64) == 0 && L.NB * L.RB == P.Dp && L.N == P.Dp);
+}
+
 inline size_t place(size_t& cursor, size_t bytes) {
   cursor = rus(cursor, 1024);
   size_t off = cursor;
@@ -213,7 +218,9 @@ inline void make_workspace(const Plan& P, long long N, Workspace& W) {
   W.ybf = place(cur, static_cast<size_t>(ms_pad) * P.Dp * 2);
   for (int i = 0; i < 2; ++i) W.hid[i] = place(cur, static_cast<size_t>(P.G) * m_pad * P.Hp * 2);
   W.ld_scratch = ru(3 * P.D, 4);
-  W.scratch = place(cur, static_cast<size_t>(ms_pad) * W.ld_scratch * 4);
+  // fp32 pre-activations of the unfused stages (3 D floats per row): not needed when every RSSM layer is fused
+  const bool need_scratch = P.K > 1 || !P.gru_fused || !ln_layer_fused(P, P.img_in) || !ln_layer_fused(P, P.prior1);
+  W.scratch = place(cur, need_scratch ? static_cast<size_t>(ms_pad) * W.ld_scratch * 4 : 0);
   int nbmax = P.gru.NB;
   if (P.img_in.NB > nbmax) nbmax = P.img_in.NB;
   W.stats = place(cur, static_cast<size_t>(nbmax) * ms_pad * 2 * 4);
