@@ -126,3 +126,34 @@ def test_persistent_rollout_plan_sizes_without_a_device():
     assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**c1, parity=1))) == 0
     assert lib.rlsb_rollout_packed_bytes(C.byref(_lib.ImagineCfg(**dict(c2, with_backward=0), slots=4, attention_blocks=3))) == 0
     assert lib.rlsb_rollout_fwd(None, None, 0, None, None, None, None, None, None, None) < 0
+
+
+def test_fused_rssm_switch_and_gru_cell_sizes():
+    """host logic of the round-2 entry points (no GPU): the fused-epilogue switch is queryable / settable and decides whether
+    the workspace carries the fp32 pre-activation scratch; the stand-alone GRU cell reports its blob / workspace sizes and
+    rejects the sizes its kernel does not cover"""
+    from rl_sandbox_b200 import ops
+    lib = _lib.load()
+    before = lib.rlsb_set_fused_rssm(-1)
+    try:
+        cfg = ops.ImagineConfig(D=1024, A=17, discrete=True, layer_norm=True, predict_discount=True, H=15).to_c()
+        assert lib.rlsb_set_fused_rssm(1) == 1
+        fused = lib.rlsb_imagine_workspace_bytes(C.byref(cfg), 32768)
+        packed = lib.rlsb_imagine_packed_bytes(C.byref(cfg))
+        assert lib.rlsb_set_fused_rssm(0) == 0 and lib.rlsb_set_fused_rssm(7) == 0      # other values only query
+        unfused = lib.rlsb_imagine_workspace_bytes(C.byref(cfg), 32768)
+        assert unfused - fused > 32768 * 3 * 1024 * 4 * 0.9          # the 3 D fp32 scratch per row is gone
+        assert lib.rlsb_imagine_packed_bytes(C.byref(cfg)) == packed  # same blob size: the GRU rows are only permuted
+        assert lib.rlsb_set_fused_rssm(2) == 2
+        small = ops.ImagineConfig(D=200, A=6, discrete=True, layer_norm=True, predict_discount=True, H=15).to_c()
+        a = lib.rlsb_imagine_workspace_bytes(C.byref(small), 800)
+        lib.rlsb_set_fused_rssm(1)
+        assert lib.rlsb_imagine_workspace_bytes(C.byref(small), 800) == a   # D % 64 != 0: the unfused GRU either way
+    finally:
+        lib.rlsb_set_fused_rssm(before)
+    assert lib.rlsb_gru_cell_packed_bytes(1024, 1024) >= 3 * 1024 * 2048 * 2 + 3 * 3 * 1024 * 4
+    assert lib.rlsb_gru_cell_packed_bytes(70, 192) >= 3 * 192 * (128 + 192) * 2       # x padded to 128 columns
+    assert lib.rlsb_gru_cell_packed_bytes(200, 200) == 0 and lib.rlsb_gru_cell_packed_bytes(64, 128) == 0
+    assert lib.rlsb_gru_cell_workspace_bytes(1024, 300) == 16 * 384 * 16               # [D / 64][m_pad] x two 64-bit words
+    assert lib.rlsb_gru_cell_workspace_bytes(1000, 300) == 0
+    assert lib.rlsb_gru_cell_fwd(None, 1024, 1024, None, None, None, 1, -1.0, 1e-5, None, None, None, None) < 0
