@@ -20,6 +20,8 @@ Fixtures
                               target-critic values, lambda-returns (ac.py:64-66), cumprod weights
                               (dreamer_v2.py:192-197) and the critic / actor losses
                               (ac.py:68-81, 113-146) computed by the reference's own methods.
+  acting.npz                  DreamerV2.get_action (dreamer_v2.py:139-154) over four frames from reset(): recurrent state,
+                              actor probabilities and the action of every step (torch CPU generator seeded).
 Parameters are NOT stored: they are regenerated from a seed by oracle_port.make_params (the same
 tensors are loaded into the reference modules here), start states by oracle_port.make_start.
 """
@@ -312,6 +314,45 @@ def run_slot_attention():
     print("slot_attention.npz written:", out.shape, mod.last_attention.shape, len(names), "parameter gradients")
 
 
+ACT_CASE = dict(D=200, A=6, discrete=True, layer_norm=True, predict_discount=True, steps=4, param_seed=91, enc_seed=92,
+                frame_seed=93, torch_seed=94)
+
+
+def acting_frames(case=ACT_CASE):
+    g = torch.Generator().manual_seed(case["frame_seed"])
+    return torch.randint(0, 256, (case["steps"], 64, 64, 3), generator=g, dtype=torch.uint8)
+
+
+def run_acting():
+    """DreamerV2.get_action of the reference (dreamer_v2.py:139-154: preprocess, conv encoder on one frame, one RSSM.forward
+    step, actor, action draw) over a few frames from reset(), torch CPU generator seeded: the recurrent state after every
+    step, the actor's probabilities and the returned action (pins the acting path of the host mirror)."""
+    c = ACT_CASE
+    wm_sd, actor_sd, critic_sd = orc.make_params(c["param_seed"], D=c["D"], A=c["A"], discrete=c["discrete"],
+                                                 layer_norm=c["layer_norm"], predict_discount=c["predict_discount"])
+    agent = rh.build_agent(D=c["D"], A=c["A"], discrete=c["discrete"], layer_norm=c["layer_norm"],
+                           predict_discount=c["predict_discount"], H=3)
+    rh.load_params(agent, wm_sd, actor_sd, critic_sd)
+    wm = getattr(agent.world_model, "_orig_mod", agent.world_model)
+    wm.encoder.load_state_dict(orc.seeded_module_params(wm.encoder, c["enc_seed"]))
+    frames = acting_frames()
+    agent.reset()
+    torch.manual_seed(c["torch_seed"])
+    out = {k: [] for k in ("determ", "post_logits", "stoch_idx", "probs", "action")}
+    with torch.no_grad():
+        for f in frames:
+            a = agent.get_action(f.numpy())
+            st = agent._state
+            out["determ"].append(st.determ.reshape(-1).numpy().copy())
+            out["post_logits"].append(st.stoch_logits.reshape(-1).numpy().copy())
+            out["stoch_idx"].append(st.stoch.reshape(32, 32).argmax(-1).numpy().astype(np.uint8))
+            out["probs"].append(agent.actor.get_action(st).probs.reshape(-1).numpy().copy())
+            out["action"].append(int(a))
+    np.savez_compressed(OUT / "acting.npz", **{k: np.stack(v) for k, v in out.items()},
+                        action_probs_sum=agent._action_probs.numpy().copy(), meta=json.dumps(c))
+    print("acting.npz written:", out["action"])
+
+
 def main(argv=None):
     """no arguments: every fixture; otherwise the named imagine_<case> fixtures only (python -m oracle.gen_golden c1_long)"""
     import sys
@@ -323,6 +364,10 @@ def main(argv=None):
         run_slot_attention()
         run_slotted()
         run_observe()
+        run_acting()
+    if only == ["acting"]:
+        run_acting()
+        return
     for name, case in CASES.items():
         if not only or name in only:
             run_case(name, case)

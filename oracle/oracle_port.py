@@ -471,6 +471,23 @@ def make_mlp_sd(gen, prefix, n_in, n_out, hidden, layer_norm, randomize_ln=True)
     return sd
 
 
+def seeded_module_params(module: torch.nn.Module, seed: int, prefix: str = "") -> dict:
+    """Seeded parameters for a module whose state-dict names / shapes both sides share (the conv encoder of the acting
+    fixture): matrices / kernels ~ N(0, 1 / fan_in), norm gains 1 + 0.1 N, everything else 0.1 N; state-dict order."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in module.state_dict().items():
+        if not v.dtype.is_floating_point:
+            sd[prefix + k] = v.clone()
+        elif v.dim() > 1:
+            sd[prefix + k] = torch.randn(v.shape, generator=gen) / float(v[0].numel()) ** 0.5
+        elif k.endswith("weight"):
+            sd[prefix + k] = 1 + 0.1 * torch.randn(v.shape, generator=gen)
+        else:
+            sd[prefix + k] = 0.1 * torch.randn(v.shape, generator=gen)
+    return sd
+
+
 def make_params(seed, *, D, A, discrete, layer_norm, predict_discount, hidden=400, S=1024):
     """Random parameters under the reference's names."""
     gen = torch.Generator().manual_seed(seed)
