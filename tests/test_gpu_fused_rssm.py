@@ -130,3 +130,41 @@ def test_gru_cell_op_matches_reference_module_math(ops, cuda, M, Dx, D):
     from rl_sandbox_b200.ops import unpack_rows
     img = unpack_rows(op.h_packed, M, D, k_pad=D)
     assert torch.equal(img, out.bfloat16().float())
+
+
+@pytest.mark.parametrize("D,ln,discrete", [(1024, False, True), (576, True, False), (640, True, True), (256, True, True)])
+def test_fused_other_widths_and_no_layer_norm(ops, lib, cuda, D, ln, discrete):
+    """layer_norm = False (the GRU's own LayerNorm stays; img_in / prior1 run NB > 1 blocks without an exchange), D = 576
+    (three 192-column blocks per LayerNorm layer, nine GRU blocks), D = 640 (the LayerNorm layers do not tile into 64-column
+    multiples: they stay unfused next to the fused GRU) and D = 256 (single-block LayerNorm layers, four GRU blocks)"""
+    A, H, n = 7, 3, 300
+    wm, actor, critic = orc.make_params(1000 + D, D=D, A=A, discrete=discrete, layer_norm=ln, predict_discount=False)
+    h0, z0 = orc.make_start(D, n, D)
+    g = torch.Generator().manual_seed(D)
+    lat = torch.rand(H, n, 1024, generator=g)
+    act = torch.rand(H, n, A, generator=g) if discrete else torch.randn(H, n, A, generator=g)
+    to = lambda sd: {k: v.to(cuda) for k, v in sd.items()}
+    outs = []
+    for fused in (0, 1):
+        assert lib.rlsb_set_fused_rssm(fused) == fused
+        eng = ops.ImaginationEngine(ops.ImagineConfig(D=D, A=A, discrete=discrete, layer_norm=ln, predict_discount=False, H=H))
+        eng.persistent_max_rows = 0
+        eng.pack(to(wm), to(actor), to(critic))
+        l0 = lib.rlsb_launch_count(0)
+        o = eng.rollout(h0.to(cuda), z0.to(cuda), None, lat.to(cuda), act.to(cuda), horizon=H)
+        torch.cuda.synchronize()
+        outs.append(({k: (v.clone() if torch.is_tensor(v) else v) for k, v in o.items()}, lib.rlsb_launch_count(0) - l0))
+    (a, la), (b, lb) = outs
+    print(f"[fused rssm] D={D} ln={ln}: launches unfused {la}, fused {lb}")
+    assert lb < la
+    ref = orc.imagine(wm, actor, critic, h0, z0, H=H, A=A, discrete=discrete, predict_discount=False,
+                      latent_uniforms=lat, action_noise=act, bf16=True)
+    for name, o in (("unfused", a), ("fused", b)):
+        same = (o["stoch_idx"].cpu().long() == ref["stoch_idx"]).all(-1)
+        if discrete:
+            same &= o["actions"].cpu().argmax(-1) == ref["actions"].argmax(-1)
+        alive = same.cumprod(0).bool()
+        assert alive[-1].float().mean() > 0.9
+        assert rel_rms(o["determ"].cpu()[alive], ref["determ"][alive], f"D={D} ln={ln} determ {name} vs bf16 oracle") < 1e-3
+        assert rel_rms(o["logits"].cpu()[alive], ref["logits"][alive], f"D={D} ln={ln} logits {name} vs bf16 oracle") < 2e-3
+    assert rel_rms(b["determ"][1], a["determ"][1], f"D={D} determ[1] fused vs unfused") < 1e-5
