@@ -76,6 +76,7 @@ extern "C" const char* rlsb_error_string(int code) {
   switch (code) {
     case -100: return "no CUDA device";
     case -101: return "device is not sm_100 (B200); librlsb has no fallback";
+    case -11: return "cross-block LayerNorm: the device reports no resident cluster for this launch configuration";
     default: return "invalid argument";
   }
 }

@@ -14,6 +14,7 @@
 // Replaces (reference): nn.Linear + nn.LayerNorm + nn.ELU chains in
 // agents/dreamer/rssm.py:136-152, agents/dreamer/common.py:58-75, utils/fc_nn.py:14-22.
 #include <cstdlib>
+#include <mutex>
 
 #include "rlsb_gemm.cuh"
 #include "rlsb_count.cuh"
@@ -1492,6 +1493,34 @@ int pick_cluster(const GemmParams& p) {
 }
 }  // namespace
 
+namespace {
+// clusters of a launch configuration the current device keeps resident at once (cudaOccupancyMaxActiveClusters), cached per
+// (device, kernel variant, cluster size, shared memory)
+template <class K>
+int resident_clusters(K kernel, const cudaLaunchConfig_t& cfg, int variant) {
+  struct Entry { int dev, variant, cs; size_t smem; int n; };
+  static Entry cache[32];
+  static int used = 0;
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  const int cs = static_cast<int>(cfg.attrs[0].val.clusterDim.x);
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].dev == dev && cache[i].variant == variant && cache[i].cs == cs && cache[i].smem == cfg.dynamicSmemBytes)
+      return cache[i].n;
+  cudaLaunchConfig_t probe = cfg;
+  probe.numAttrs = 1;   // the cluster dimension only
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &probe) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (used < 32) cache[used++] = Entry{dev, variant, cs, cfg.dynamicSmemBytes, n};
+  return n;
+}
+}  // namespace
+
 int gemm_grid_size(const GemmParams& p) {
   if (init_device_info() != 0) return 0;
   const int cs = pick_cluster(p);
@@ -1590,6 +1619,12 @@ int launch_gemm(const GemmParams& p, int epilogue, cudaStream_t stream) {
                                227 * 1024);                                                      \
       if (e != cudaSuccess) return static_cast<int>(e);                                          \
       attr_once.done(dev_bit);                                                                   \
+    }                                                                                            \
+    if (xln) { /* the cross-block exchange spins on partner CTAs: every cluster of the launch must be resident */ \
+      const int cap = pair ? resident_clusters(gemm_kernel<EPI, true>, cfg, EPI * 2 + 1)         \
+                           : resident_clusters(gemm_kernel<EPI, false>, cfg, EPI * 2);           \
+      if (cap <= 0) return -11;                                                                  \
+      if (clusters > cap) cfg.gridDim = dim3(static_cast<unsigned>(cap * cs));                   \
     }                                                                                            \
     if (pair) e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, true>, q, stages, nbuf, cs);         \
     else e = cudaLaunchKernelEx(&cfg, gemm_kernel<EPI, false>, q, stages, nbuf, cs);             \
