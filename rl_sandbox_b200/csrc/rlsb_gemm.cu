@@ -8,8 +8,10 @@
 // * one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) into TMEM; smem
 //   stages are released with tcgen05.commit; accumulators are double buffered in TMEM when
 //   RB <= 256 so the epilogue of tile i overlaps the main loop of tile i+1;
-// * four epilogue warps own one TMEM lane (= one output row) per thread, which makes the
-//   LayerNorm statistics of rssm.py:136-152 / fc_nn.py:14-21 a per-thread reduction.
+// * sixteen epilogue warps (4 TMEM lane quarters x 4 column quarters) own one output row per thread, which makes the
+//   LayerNorm statistics of rssm.py:136-152 / fc_nn.py:14-21 a per-thread reduction; where a row spans several n-blocks
+//   (EPI_LN_ACT with NB > 1, EPI_GRU: the whole GRUCell of common.py:69-81) the blocks' CTAs exchange their row statistics
+//   through tagged 64-bit words in global memory (GemmParams::xstats) — no second kernel, no fp32 round trip.
 //
 // Replaces (reference): nn.Linear + nn.LayerNorm + nn.ELU chains in
 // agents/dreamer/rssm.py:136-152, agents/dreamer/common.py:58-75, utils/fc_nn.py:14-22.

@@ -1,6 +1,6 @@
 """The chained rollout's fused RSSM epilogues (rlsb_set_fused_rssm, default on): LayerNorm + ELU of img_in / prior1 and the whole
 GRU cell (common.py:69-81) run inside their contractions even though a row spans several n-blocks — the blocks' CTAs exchange
-their row statistics through global memory and a self-resetting arrival counter (GemmParams::ln_sync) — against the unfused
+their row statistics through global memory as tagged 64-bit words (GemmParams::xstats) — against the unfused
 chain (contraction -> fp32 pre-activations -> ln_act_kernel / gru_gate_kernel) and the oracle.
 
 Same arithmetic, different summation order of the LayerNorm statistics (and 192- instead of 256-column blocks for the GRU):
@@ -120,7 +120,7 @@ def test_gru_cell_op_matches_reference_module_math(ops, cuda, M, Dx, D):
     x, h = torch.randn(M, Dx, generator=g), torch.tanh(torch.randn(M, D, generator=g))
     op = ops.GRUCellOp(Dx, D).pack(*(sd[k].to(cuda) for k in ("c._layer.weight", "c._layer.bias", "c._norm.weight", "c._norm.bias")))
     out = op.forward(x.to(cuda), h.to(cuda))
-    again = op.forward(x.to(cuda), h.to(cuda))          # the arrival counters reset themselves
+    again = op.forward(x.to(cuda), h.to(cuda))          # a second launch on the same statistics slots (tags advance)
     torch.cuda.synchronize()
     assert torch.equal(out, again)
     ref16 = orc.gru_cell(x, h, sd, "c.", bf16=True)
