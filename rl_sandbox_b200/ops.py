@@ -403,6 +403,7 @@ class ImaginationEngine:
         check(self.lib.rlsb_imagine_pack(C.byref(self.ccfg), C.byref(p), self.packed.data_ptr(), _stream()),
               "rlsb_imagine_pack")
         self._params = p
+        self._packed_fused = int(self.lib.rlsb_set_fused_rssm(-1))   # decides the GRU rows' order inside the blob
         self._pack_version += 1
         # `keep` tensors must outlive the enqueued pack kernels: stream-ordered frees make that safe
         self._keep = keep
@@ -540,6 +541,9 @@ class ImaginationEngine:
                                             _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                             C.byref(co), ws.data_ptr(), _stream()), "rlsb_rollout_fwd")
             return out
+        if int(self.lib.rlsb_set_fused_rssm(-1)) != getattr(self, "_packed_fused", None):
+            raise _lib.RlsbError("rlsb_set_fused_rssm changed since ImaginationEngine.pack: the packed GRU weight has the other "
+                                 "row order — call pack() again")
         check(self.lib.rlsb_imagine_fwd(C.byref(ccfg), self.packed.data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")

@@ -168,3 +168,20 @@ def test_fused_other_widths_and_no_layer_norm(ops, lib, cuda, D, ln, discrete):
         assert rel_rms(o["determ"].cpu()[alive], ref["determ"][alive], f"D={D} ln={ln} determ {name} vs bf16 oracle") < 1e-3
         assert rel_rms(o["logits"].cpu()[alive], ref["logits"][alive], f"D={D} ln={ln} logits {name} vs bf16 oracle") < 2e-3
     assert rel_rms(b["determ"][1], a["determ"][1], f"D={D} determ[1] fused vs unfused") < 1e-5
+
+
+def test_switch_change_after_pack_is_rejected(ops, lib, cuda):
+    """the switch decides the row order of the packed GRU weight: a rollout on a blob packed under the other setting must
+    fail loudly instead of contracting permuted rows"""
+    from rl_sandbox_b200 import _lib
+    c = load_case("c1")
+    assert lib.rlsb_set_fused_rssm(1) == 1
+    eng = engine(ops, c["meta"], cuda, c, 2, "chained")
+    h0, z0 = orc.make_start(1, 8, c["meta"]["D"])
+    eng.rollout(h0.to(cuda), z0.to(cuda), None, None, None, horizon=2, seed=1)
+    lib.rlsb_set_fused_rssm(0)
+    with pytest.raises(_lib.RlsbError):
+        eng.rollout(h0.to(cuda), z0.to(cuda), None, None, None, horizon=2, seed=1)
+    to = lambda sd: {k: v.to(cuda) for k, v in sd.items()}
+    eng.pack(to(c["wm"]), to(c["actor"]), to(c["critic"]))
+    eng.rollout(h0.to(cuda), z0.to(cuda), None, None, None, horizon=2, seed=1)
