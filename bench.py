@@ -530,6 +530,29 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
         gemm_ms = ev0.elapsed_time(ev1) / reps
+        # beside the fused cell: the plain contraction (EPI_STATS, 256-column blocks) the unfused path runs before its gate kernel
+        contraction_only = None
+        if gru_fused:
+            rb, nb = ops.plan_blocks(Ng)
+            wp = ops.pack_rows(wa, row_block=rb, rows_pad=rb * nb, k_pad=Kg)
+            xp2 = ops.pack_rows(torch.randn(N, Kg, device=device))
+            m_pad = ops.round_up(N, 128)
+            b2 = dict(out=torch.empty((m_pad, Ng), device=device), stats=torch.empty((nb, m_pad, 2), device=device),
+                      bias_p=torch.zeros(rb * nb, device=device))
+            for _ in range(3):
+                ops.gemm_bias(xp2, Kg, wp, rb, nb, None, N, Ng, want_stats=True, **b2)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                ops.gemm_bias(xp2, Kg, wp, rb, nb, None, N, Ng, want_stats=True, **b2)
+            ev1.record()
+            torch.cuda.synchronize()
+            c_ms = ev0.elapsed_time(ev1) / reps
+            c_tf = N * GRU_FLOP[fl] / (c_ms * 1e-3) / 1e12
+            contraction_only = {"kernel": "gemm_kernel<EPI_STATS> (the contraction alone: fp32 pre-activations + statistics out, "
+                                          "gates in a second kernel)", "ms_per_launch": c_ms, "achieved": c_tf,
+                                "frac": c_tf / pk["tf_burst"], "frac_of_sustained": c_tf / pk["tf_sus"]}
+            del b2, xp2, wp
         # algorithmic FLOPs of the GRU contraction as the reference executes it (2*3D*2D per row)
         achieved = N * GRU_FLOP[fl] / (gemm_ms * 1e-3) / 1e12
         # the kernel is timed alone (20 back-to-back launches): the burst bf16 figure is its denominator; the sustained
@@ -548,7 +571,7 @@ def main():
                     "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
                     "peak_source": pk["source"] + ", burst bf16 (kernel timed alone)",
                     "frac_of_sustained": achieved / pk["tf_sus"], "peak_sustained": pk["tf_sus"],
-                    "ms_per_launch": gemm_ms, "traffic": traffic,
+                    "ms_per_launch": gemm_ms, "traffic": traffic, "contraction_only": contraction_only,
                     # the GRU CELL's bytes (common.py:69-81): x, h in (bf16 operands) + h in fp32 (the convex update's operand)
                     # + h' out (fp32 + packed bf16) + the weights; the unfused contraction instead writes its fp32
                     # pre-activations + statistics for the gate kernel, which reads them back
