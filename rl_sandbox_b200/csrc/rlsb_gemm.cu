@@ -282,8 +282,8 @@ __device__ __forceinline__ uint32_t xst_tag(const unsigned long long* slot) {
   return static_cast<uint32_t>(w >> 32);
 }
 // sum over the blocks b = b_first, b_first + 4, ... < nb_total of row m: every block's words are polled until they carry `tag`
-// (normally the first read; a partner that never publishes means the CTAs of the launch are not co-resident: trap — a launch
-// error, not a hang).  Up to four blocks are in flight at once.
+// (normally the first read; a partner that never publishes means the CTAs of the launch are not co-resident: trap after
+// 4 M polls — a launch error, not a hang).  Up to four blocks are in flight at once.
 __device__ __forceinline__ void xst_gather(const unsigned long long* base, size_t block_stride, int b_first, int nb_total,
                                            uint32_t tag, float& s, float& q) {
   s = 0.f;
@@ -296,8 +296,7 @@ __device__ __forceinline__ void xst_gather(const unsigned long long* base, size_
       ok[i] = !(b0 + 4 * i < nb_total);
       w0[i] = w1[i] = 0ull;
     }
-    const long long t0 = clock64();
-    for (;;) {
+    for (unsigned int polls = 0;; ++polls) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (!ok[i]) {
@@ -312,7 +311,7 @@ __device__ __forceinline__ void xst_gather(const unsigned long long* base, size_
         all = all && ok[i];
       }
       if (all) break;
-      if (clock64() - t0 > (1ll << 32)) __trap();
+      if (polls > (1u << 22)) __trap();   // ~ seconds of polling (counted in polls, not in wall time: a pre-empted context does not trip it)
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
