@@ -231,19 +231,26 @@ __global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
   }
 }
 
+// eight lanes per output column: each sums every eighth CTA's partial (all loads in flight), then a three-step butterfly —
+// a fixed order, so the sums are reproducible (a single thread walking the <= 148 partials took 22 us of L2 round trips)
 __global__ void colsum_reduce_kernel(const ColsumReduceParams p) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.G * 2 * p.RB) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t >> 3, l = t & 7;
+  const int total = p.G * 2 * p.RB;
   const int col = i % p.RB;
   const int which = (i / p.RB) & 1;
   const int g = i / (2 * p.RB);
-  if (col >= p.N) return;
-  float* dst = which == 0 ? p.dgamma[g] : p.dbeta[g];
-  if (!dst) return;
+  float* dst = nullptr;
+  if (i < total && col < p.N) dst = which == 0 ? p.dgamma[g] : p.dbeta[g];
   float acc = 0.f;
-  const size_t stride = static_cast<size_t>(p.G) * 2 * p.RB;
-  for (int c = 0; c < p.ctas; ++c) acc += __ldg(p.col_part + c * stride + i);
-  dst[col] = acc;
+  if (dst) {
+    const size_t stride = static_cast<size_t>(p.G) * 2 * p.RB;
+#pragma unroll 4
+    for (int c = l; c < p.ctas; c += 8) acc += __ldg(p.col_part + c * stride + i);
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (dst && l == 0) dst[col] = acc;
 }
 
 PerDeviceOnce g_wg_attr_once;
@@ -367,7 +374,7 @@ int launch_wgrad_reduce(const WgradReduceParams& p, cudaStream_t stream) {
 }
 
 int launch_colsum_reduce(const ColsumReduceParams& p, cudaStream_t stream) {
-  const int total = p.G * 2 * p.RB;
+  const int total = p.G * 2 * p.RB * 8;   // eight lanes per output
   colsum_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(p);
   count_launch();
   return static_cast<int>(cudaGetLastError());
