@@ -226,7 +226,8 @@ __global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
     float acc = 0.f;
     const size_t stride = static_cast<size_t>(p.G) * p.rows_pad * p.ld;
     const float* src = p.partial + i;
-    for (int s = 0; s < p.splits; ++s) acc += __ldg(src + s * stride);
+#pragma unroll 8
+    for (int s = 0; s < p.splits; ++s) acc += __ldg(src + s * stride);   // (same order: the loads of eight splits are in flight)
     *dst = p.accumulate ? *dst + acc : acc;
   }
 }
