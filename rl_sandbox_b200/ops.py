@@ -359,6 +359,7 @@ class ImaginationEngine:
         self.packed_ro: Optional[dict] = {} if ro_bytes else None
         self._ro_version: dict = {}
         self._pack_version = 0
+        self._chained_version = None   # (pack version, fused-epilogue switch) the chained blob was built for
         self._params = None
         self._ws = None
         self._ws_bytes = 0
@@ -400,10 +401,10 @@ class ImaginationEngine:
             p.discount = _mlp_params(wm_sd, "discount_predictor.", keep)
         if self.cfg.with_critic:
             p.critic = _mlp_params(critic_sd, target_prefix, keep)
-        check(self.lib.rlsb_imagine_pack(C.byref(self.ccfg), C.byref(p), self.packed.data_ptr(), _stream()),
-              "rlsb_imagine_pack")
+        # the blobs are (re-)built lazily, by the kernel that is about to read them (_packed_chained / _packed_rollout): at the
+        # configured 800 start states only the persistent kernels run, and packing the chained rollout's image as well cost
+        # ~ 60 us of every 3 ms step
         self._params = p
-        self._packed_fused = int(self.lib.rlsb_set_fused_rssm(-1))   # decides the GRU rows' order inside the blob
         self._pack_version += 1
         # `keep` tensors must outlive the enqueued pack kernels: stream-ordered frees make that safe
         self._keep = keep
@@ -439,6 +440,18 @@ class ImaginationEngine:
         """all row blocks of n start states run concurrently in the persistent kernels (a second wave doubles their time:
         the chained rollout is faster then)"""
         return (n + 127) // 128 <= self.rollout_max_clusters(self.rollout_cluster_for(n))
+
+    def _packed_chained(self) -> torch.Tensor:
+        """the chained kernels' weight blob (rlsb_imagine_fwd / rlsb_imagine_bwd), re-packed when `pack` ran since it was made
+        or the fused-epilogue switch (which decides the GRU rows' order inside the blob) changed"""
+        if self._params is None:
+            raise _lib.RlsbError("ImaginationEngine.rollout before pack")
+        fused = int(self.lib.rlsb_set_fused_rssm(-1))
+        if self._chained_version != (self._pack_version, fused):
+            check(self.lib.rlsb_imagine_pack(C.byref(self.ccfg), C.byref(self._params), self.packed.data_ptr(), _stream()),
+                  "rlsb_imagine_pack")
+            self._chained_version = (self._pack_version, fused)
+        return self.packed
 
     def _packed_rollout(self, ccfg) -> torch.Tensor:
         """the persistent kernel's weight blob for ccfg.rollout_cluster, re-packed when `pack` ran since it was made"""
@@ -541,10 +554,7 @@ class ImaginationEngine:
                                             _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                             C.byref(co), ws.data_ptr(), _stream()), "rlsb_rollout_fwd")
             return out
-        if int(self.lib.rlsb_set_fused_rssm(-1)) != getattr(self, "_packed_fused", None):
-            raise _lib.RlsbError("rlsb_set_fused_rssm changed since ImaginationEngine.pack: the packed GRU weight has the other "
-                                 "row order — call pack() again")
-        check(self.lib.rlsb_imagine_fwd(C.byref(ccfg), self.packed.data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
+        check(self.lib.rlsb_imagine_fwd(C.byref(ccfg), self._packed_chained().data_ptr(), n, h0.data_ptr(), z0.data_ptr(),
                                         _ptr(None if logits0 is None else _f32c(logits0)), C.byref(nz),
                                         C.byref(co), ws.data_ptr(), _stream()), "rlsb_imagine_fwd")
         return out
@@ -594,7 +604,7 @@ class ImaginationEngine:
                                             g_values.data_ptr(), g_actions.data_ptr(), bws.data_ptr(), _stream()),
                   "rlsb_rollout_bwd")
             return g_actions
-        check(self.lib.rlsb_imagine_bwd(C.byref(ccfg), self.packed.data_ptr(), n, C.byref(co), g_rewards.data_ptr(),
+        check(self.lib.rlsb_imagine_bwd(C.byref(ccfg), self._packed_chained().data_ptr(), n, C.byref(co), g_rewards.data_ptr(),
                                         g_values.data_ptr(), g_actions.data_ptr(), bws.data_ptr(), _stream()),
               "rlsb_imagine_bwd")
         return g_actions
